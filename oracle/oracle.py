@@ -1,0 +1,296 @@
+"""ctypes front-end of the CPU oracle (oracle/ref_ring.c) -- TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  The product package must never do so (it fails loudly without its CUDA .so).
+
+Also holds `py_*` pure-Python-int definitional functions (tier T0 of SURVEY.md 8c) used to
+cross-check the C restatement itself on small sizes.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libref_ring.so")
+
+u64 = C.c_uint64
+P64 = C.POINTER(C.c_uint64)
+PI = C.POINTER(C.c_int)
+
+# op codes: identical to include/b200ring.h (B200_OP_*) and oracle/ref_ring.c
+OPS = {
+    "Add": 0, "AddLazy": 1, "Sub": 2, "SubLazy": 3, "Neg": 4, "Reduce": 5, "ReduceLazy": 6,
+    "MForm": 7, "MFormLazy": 8, "IMForm": 9,
+    "MulCoeffsBarrett": 16, "MulCoeffsBarrettLazy": 17, "MulCoeffsBarrettThenAdd": 18,
+    "MulCoeffsBarrettThenAddLazy": 19,
+    "MulCoeffsMontgomery": 32, "MulCoeffsMontgomeryLazy": 33, "MulCoeffsMontgomeryThenAdd": 34,
+    "MulCoeffsMontgomeryThenAddLazy": 35, "MulCoeffsMontgomeryLazyThenAddLazy": 36,
+    "MulCoeffsMontgomeryThenSub": 37, "MulCoeffsMontgomeryThenSubLazy": 38,
+    "MulCoeffsMontgomeryLazyThenSubLazy": 39, "MulCoeffsMontgomeryLazyThenNeg": 40,
+    "MulScalarMontgomery": 48, "MulScalarMontgomeryLazy": 49, "MulScalarMontgomeryThenAdd": 50,
+    "AddScalar": 51, "SubScalar": 52,
+}
+
+
+def build(force=False):
+    """Compile oracle/ref_ring.c -> oracle/_build/libref_ring.so (gcc only, a few seconds)."""
+    src = os.path.join(_HERE, "ref_ring.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_SO)
+        sig = {
+            "ref_gen_mred_constant": (u64, [u64]),
+            "ref_gen_bred_constant": (None, [u64, P64]),
+            "ref_mform": (u64, [u64, u64, P64]), "ref_mform_lazy": (u64, [u64, u64, P64]),
+            "ref_imform": (u64, [u64, u64, u64]), "ref_imform_lazy": (u64, [u64, u64, u64]),
+            "ref_mred": (u64, [u64, u64, u64, u64]), "ref_mred_lazy": (u64, [u64, u64, u64, u64]),
+            "ref_bred": (u64, [u64, u64, u64, P64]), "ref_bred_lazy": (u64, [u64, u64, u64, P64]),
+            "ref_bred_add": (u64, [u64, u64, P64]), "ref_bred_add_lazy": (u64, [u64, u64, P64]),
+            "ref_cred": (u64, [u64, u64]), "ref_modexp": (u64, [u64, u64, u64]),
+            "ref_is_prime": (C.c_int, [u64]), "ref_unique_factors": (C.c_int, [u64, P64]),
+            "ref_primitive_root": (u64, [u64]), "ref_find_3n_primitive_root": (u64, [u64, u64]),
+            "ref_find_3n_rns_primes": (C.c_int, [u64, C.c_int, C.c_int, C.c_int, P64]),
+            "ref_pow2_new": (C.c_void_p, [C.c_int, u64]), "ref_pow2_free": (None, [C.c_void_p]),
+            "ref_pow2_constants": (None, [C.c_void_p, P64]),
+            "ref_pow2_tables": (None, [C.c_void_p, P64, P64]),
+            "ref_pow2_ntt": (None, [C.c_void_p, P64, P64, C.c_int]),
+            "ref_pow2_intt": (None, [C.c_void_p, P64, P64, C.c_int]),
+            "ref_vec_op": (C.c_int, [C.c_int, C.c_int, u64, P64, P64, P64, u64]),
+            "ref_3n_exponents": (C.c_int, [C.c_int, PI]),
+            "ref_3n_forward_horner": (None, [C.c_int, u64, u64, P64, P64]),
+            "ref_3n_forward_horner_at": (u64, [C.c_int, u64, u64, P64, C.c_int]),
+            "ref_3n_backward_gauss": (C.c_int, [C.c_int, u64, u64, P64, P64]),
+            "ref_3n_schoolbook": (None, [C.c_int, u64, P64, P64, P64]),
+            "ref_negacyclic_schoolbook": (None, [C.c_int, u64, P64, P64, P64]),
+            "ref_3n_new": (C.c_void_p, [C.c_int, u64, u64]), "ref_3n_free": (None, [C.c_void_p]),
+            "ref_3n_leaf_exponents": (None, [C.c_void_p, PI]), "ref_3n_go2fast": (None, [C.c_void_p, PI]),
+            "ref_3n_zetas": (None, [C.c_void_p, P64]),
+            "ref_3n_forward": (None, [C.c_void_p, P64, P64, C.c_int]),
+            "ref_3n_backward": (None, [C.c_void_p, P64, P64, C.c_int]),
+            "ref_fill_uniform": (None, [u64, u64, u64, u64, C.c_int, P64]),
+            "ref_num_threads": (C.c_int, []),
+            "ref_3n_batch": (None, [C.POINTER(C.c_void_p), C.c_int, P64, C.c_int, C.c_int, C.c_int]),
+            "ref_pow2_batch": (None, [C.POINTER(C.c_void_p), C.c_int, P64, C.c_int, C.c_int, C.c_int]),
+        }
+        for name, (res, args) in sig.items():
+            f = getattr(L, name)
+            f.restype, f.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    assert a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(P64)
+
+
+def _arr(x):
+    return np.ascontiguousarray(np.asarray(x, dtype=np.uint64))
+
+
+def bred_constant(q):
+    out = np.zeros(2, dtype=np.uint64)
+    lib().ref_gen_bred_constant(q, _p(out))
+    return out
+
+
+def fill_uniform(seed, poly, limb, q, N):
+    out = np.empty(N, dtype=np.uint64)
+    lib().ref_fill_uniform(seed, poly, limb, q, N, _p(out))
+    return out
+
+
+def find_3n_rns_primes(N, bitsize, count, budget=1 << 20):
+    out = np.zeros(count, dtype=np.uint64)
+    n = lib().ref_find_3n_rns_primes(N, bitsize, count, budget, _p(out))
+    if n < count:
+        raise ValueError("could not find enough 3N-friendly primes (found %d/%d)" % (n, count))
+    return [int(x) for x in out]
+
+
+def vec_op(name, q, p1, p2=None, p3=None, scalar=0):
+    """One limb of ring/vec_ops.go; returns the new p3."""
+    p1 = _arr(p1)
+    N = len(p1)
+    p2a = _arr(p2) if p2 is not None else None
+    out = _arr(p3).copy() if p3 is not None else np.zeros(N, dtype=np.uint64)
+    rc = lib().ref_vec_op(OPS[name], N, q, _p(p1), _p(p2a) if p2a is not None else None, _p(out), scalar)
+    if rc:
+        raise ValueError(name)
+    return out
+
+
+class Pow2SubRing:
+    """ring.SubRing with the Standard transformer (subring.go:74-214 + ntt.go)."""
+
+    def __init__(self, N, q):
+        self.N, self.q = N, q
+        self.h = lib().ref_pow2_new(N, q)
+        if not self.h:
+            raise ValueError("invalid power-of-two subring N=%d q=%d" % (N, q))
+        c = np.zeros(6, dtype=np.uint64)
+        lib().ref_pow2_constants(self.h, _p(c))
+        self.MRedConstant, self.BRedConstant = int(c[0]), (int(c[1]), int(c[2]))
+        self.PrimitiveRoot, self.NInv = int(c[3]), int(c[4])
+
+    def tables(self):
+        rf = np.empty(self.N, dtype=np.uint64)
+        rb = np.empty(self.N, dtype=np.uint64)
+        lib().ref_pow2_tables(self.h, _p(rf), _p(rb))
+        return rf, rb
+
+    def NTT(self, p, lazy=False):
+        p = _arr(p)
+        out = np.empty_like(p)
+        lib().ref_pow2_ntt(self.h, _p(p), _p(out), int(lazy))
+        return out
+
+    def INTT(self, p, lazy=False):
+        p = _arr(p)
+        out = np.empty_like(p)
+        lib().ref_pow2_intt(self.h, _p(p), _p(out), int(lazy))
+        return out
+
+    def __del__(self):
+        if getattr(self, "h", None) and _lib is not None:
+            _lib.ref_pow2_free(self.h)
+            self.h = None
+
+
+class ThreeNSubRing:
+    """3N ring Z_q[X]/(X^N - X^(N/2) + 1): fast transform (T2) with the Go slot order."""
+
+    def __init__(self, N, q, omega=None):
+        if omega is None:
+            omega = lib().ref_find_3n_primitive_root(q, 3 * N)  # subring.go:255-290 (deterministic)
+        self.N, self.q, self.omega = N, q, int(omega)
+        self.h = lib().ref_3n_new(N, q, self.omega)
+        if not self.h:
+            raise ValueError("invalid 3N subring N=%d q=%d omega=%d" % (N, q, self.omega))
+
+    def leaf_exponents(self):
+        out = np.empty(self.N, dtype=np.int32)
+        lib().ref_3n_leaf_exponents(self.h, out.ctypes.data_as(PI))
+        return out
+
+    def go2fast(self):
+        out = np.empty(self.N, dtype=np.int32)
+        lib().ref_3n_go2fast(self.h, out.ctypes.data_as(PI))
+        return out
+
+    def zetas(self):
+        out = np.empty(self.N, dtype=np.uint64)
+        lib().ref_3n_zetas(self.h, _p(out))
+        return out
+
+    def NTT(self, p, order=0):
+        p = _arr(p)
+        out = np.empty_like(p)
+        lib().ref_3n_forward(self.h, _p(p), _p(out), order)
+        return out
+
+    def INTT(self, p, order=0):
+        p = _arr(p)
+        out = np.empty_like(p)
+        lib().ref_3n_backward(self.h, _p(p), _p(out), order)
+        return out
+
+    def NTT_horner(self, p):
+        p = _arr(p)
+        out = np.empty_like(p)
+        lib().ref_3n_forward_horner(self.N, self.q, self.omega, _p(p), _p(out))
+        return out
+
+    def horner_at(self, p, exponent):
+        return int(lib().ref_3n_forward_horner_at(self.N, self.q, self.omega, _p(_arr(p)), int(exponent)))
+
+    def INTT_gauss(self, p):
+        p = _arr(p)
+        out = np.empty_like(p)
+        if lib().ref_3n_backward_gauss(self.N, self.q, self.omega, _p(p), _p(out)):
+            raise ValueError("singular Vandermonde")
+        return out
+
+    def __del__(self):
+        if getattr(self, "h", None) and _lib is not None:
+            _lib.ref_3n_free(self.h)
+            self.h = None
+
+
+def schoolbook_3n(N, q, a, b):
+    a, b = _arr(a), _arr(b)
+    c = np.empty(N, dtype=np.uint64)
+    lib().ref_3n_schoolbook(N, q, _p(a), _p(b), _p(c))
+    return c
+
+
+def schoolbook_negacyclic(N, q, a, b):
+    a, b = _arr(a), _arr(b)
+    c = np.empty(N, dtype=np.uint64)
+    lib().ref_negacyclic_schoolbook(N, q, _p(a), _p(b), _p(c))
+    return c
+
+
+def totatives(threeN):
+    out = np.empty(threeN, dtype=np.int32)
+    n = lib().ref_3n_exponents(threeN, out.ctypes.data_as(PI))
+    return out[:n].copy()
+
+
+def batch_transform(rings, data, inverse=False, threads=0):
+    """In-place transform of data[units][N]; unit u uses rings[u % len(rings)] (timed CPU baseline)."""
+    assert data.dtype == np.uint64 and data.flags["C_CONTIGUOUS"] and data.ndim == 2
+    hs = (C.c_void_p * len(rings))(*[r.h for r in rings])
+    fn = lib().ref_3n_batch if isinstance(rings[0], ThreeNSubRing) else lib().ref_pow2_batch
+    fn(hs, len(rings), _p(data), data.shape[0], int(inverse), threads)
+
+
+def num_threads():
+    return lib().ref_num_threads()
+
+
+# ---------------------------------------------------------------------------------------------
+# T0: pure-Python-int definitional functions (small sizes only)
+# ---------------------------------------------------------------------------------------------
+def py_bitrev(x, bits):
+    return int(format(x, "0%db" % bits)[::-1], 2) if bits else 0
+
+
+def py_pow2_ntt(N, q, g, coeffs):
+    """out[i] = f(psi^(2 brev(i)+1)), psi = g^((q-1)/2N): the definition ring/ntt.go computes."""
+    psi = pow(g, (q - 1) // (2 * N), q)
+    logn = N.bit_length() - 1
+    out = []
+    for i in range(N):
+        x = pow(psi, 2 * py_bitrev(i, logn) + 1, q)
+        acc = 0
+        for c in reversed(coeffs):
+            acc = (acc * x + int(c)) % q
+        out.append(acc)
+    return out
+
+
+def py_3n_ntt(N, q, omega, coeffs):
+    """ring/ntt_3n.go:82-109 with Python ints."""
+    from math import gcd
+    E = [e for e in range(1, 3 * N) if gcd(e, 3 * N) == 1]
+    out = []
+    for e in E:
+        x = pow(omega, e, q)
+        acc = 0
+        for c in reversed(coeffs):
+            acc = (acc * x + int(c)) % q
+        out.append(acc)
+    return out

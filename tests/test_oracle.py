@@ -1,0 +1,177 @@
+"""CPU-only tests that pin the oracle (oracle/ref_ring.c) before it is trusted as the checker.
+
+* power-of-two path: the 6 known-answer vectors of ring/ntt_test.go:10-89 (tests/golden/ntt_kat.json)
+* modular primitives: the property test of ring/ring_test.go:534-670 (BRed/MRed/MForm vs big ints
+  on the edge values 1, q-1, 2^64-1 for the 14 primes Qi60[18:32] of ring/test_params.go)
+* 3N path: vectors from the reference's Python prototype (tests/golden/ntt3n_proto.json), the
+  definition ring/ntt_3n.go:99-108 (Horner / Gaussian), round trips and schoolbook products as in
+  ring/ntt_3n_test.go:79-222,367-554.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, QI60
+from oracle import oracle as O
+
+
+def test_kat_pow2_forward_inverse_and_tables():
+    kat = json.load(open(os.path.join(GOLDEN, "ntt_kat.json")))["vectors"]
+    assert [v["N"] for v in kat] == [16, 32, 64, 128, 256, 512]
+    for v in kat:
+        for l, q in enumerate(v["Qis"]):
+            s = O.Pow2SubRing(v["N"], q)
+            x = np.array(v["poly"][l], dtype=np.uint64)
+            want = np.array(v["polyNTT"][l], dtype=np.uint64)
+            got = s.NTT(x)
+            assert (got == want).all(), (v["N"], l)
+            assert (s.INTT(want) == x).all()
+            lazy = s.NTT(x, lazy=True)
+            assert (lazy % np.uint64(q) == want).all() and int(lazy.max()) <= 6 * q - 2
+            if v["N"] <= 64:  # definitional: out[i] = f(psi^(2 brev(i)+1))
+                assert O.py_pow2_ntt(v["N"], q, s.PrimitiveRoot, v["poly"][l]) == [int(t) for t in got]
+            # table invariants of subring.go:187-205
+            rf, rb = s.tables()
+            one = O.lib().ref_mform(1, q, O._p(O.bred_constant(q)))
+            assert int(rf[0]) == one == int(rb[0])
+            prod = [O.lib().ref_mred(int(a), int(b), q, s.MRedConstant) for a, b in zip(rf, rb)]
+            assert all(p == one for p in prod)  # psi^k * psi^-k = 1 (Montgomery form)
+
+
+def test_modular_reduction_edge_values():
+    L = O.lib()
+    for q in QI60[18:32]:
+        brc = O.bred_constant(q)
+        qinv = L.ref_gen_mred_constant(q)
+        assert (qinv * q) % 2**64 == 1
+        assert (int(brc[0]) << 64 | int(brc[1])) == 2**128 // q
+        for x in (1, q - 1, 2**64 - 1):
+            assert L.ref_bred_add(x, q, O._p(brc)) == x % q
+            assert L.ref_mform(x, q, O._p(brc)) == (x << 64) % q
+            assert L.ref_imform(x, q, qinv) == (x * pow(2**64, -1, q)) % q
+            for y in (1, q - 1, 2**64 - 1):
+                assert L.ref_bred(x, y, q, O._p(brc)) == (x * y) % q
+                ym = L.ref_mform(y, q, O._p(brc))
+                assert L.ref_mred(x, ym, q, qinv) == (x * y) % q
+                lazy = L.ref_mred_lazy(x % q, ym, q, qinv)
+                assert lazy % q == (x * y) % q and lazy < 2 * q
+
+
+def test_vec_ops_against_python_ints():
+    q = QI60[0]
+    rng = np.random.default_rng(7)
+    N = 64
+    a = rng.integers(0, q, N, dtype=np.uint64)
+    b = rng.integers(0, q, N, dtype=np.uint64)
+    c = rng.integers(0, q, N, dtype=np.uint64)
+    rinv = pow(2**64, -1, q)
+    A, B, Cc = [int(x) for x in a], [int(x) for x in b], [int(x) for x in c]
+    chk = lambda got, want: [int(g) for g in got] == want
+    assert chk(O.vec_op("Add", q, a, b), [(x + y) % q for x, y in zip(A, B)])
+    assert chk(O.vec_op("Sub", q, a, b), [(x - y) % q for x, y in zip(A, B)])
+    assert chk(O.vec_op("MulCoeffsBarrett", q, a, b), [(x * y) % q for x, y in zip(A, B)])
+    assert chk(O.vec_op("MulCoeffsMontgomery", q, a, b), [(x * y * rinv) % q for x, y in zip(A, B)])
+    assert chk(O.vec_op("MulCoeffsMontgomeryThenAdd", q, a, b, c), [(z + x * y * rinv) % q for x, y, z in zip(A, B, Cc)])
+    assert chk(O.vec_op("MulCoeffsMontgomeryThenSub", q, a, b, c), [(z - x * y * rinv) % q for x, y, z in zip(A, B, Cc)])
+    assert chk(O.vec_op("MForm", q, a), [(x << 64) % q for x in A])
+    assert chk(O.vec_op("IMForm", q, a), [(x * rinv) % q for x in A])
+    big = rng.integers(0, 2**63, N, dtype=np.uint64) * np.uint64(2) + np.uint64(1)
+    assert chk(O.vec_op("Reduce", q, big), [int(x) % q for x in big])
+
+
+def test_3n_prototype_vectors():
+    vec = json.load(open(os.path.join(GOLDEN, "ntt3n_proto.json")))["vectors"]
+    assert len(vec) >= 8
+    for v in vec:
+        N, p, w = v["N"], v["p"], v["w"]
+        r = O.ThreeNSubRing(N, p, w)
+        assert [int(z) for z in r.zetas()] == v["zetas"]
+        assert [int(e) for e in r.leaf_exponents()] == v["leaf_exponents"]
+        x = np.array(v["coeffs"], dtype=np.uint64)
+        tree = r.NTT(x, order=1)
+        assert [int(t) for t in tree] == v["ntt_tree_order"]
+        assert (r.INTT(tree, order=1) == x).all()
+        go = r.NTT(x)  # Go order: slot k <-> w^E[k], E ascending totatives (ntt_3n.go:46-53)
+        assert [int(t) for t in go] == O.py_3n_ntt(N, p, w, v["coeffs"])
+        assert (go[np.arange(N)] == tree[r.go2fast()]).all()
+
+
+@pytest.mark.parametrize("N", [6, 12, 18, 24, 36, 48, 96, 192])
+def test_3n_definition_roundtrip_product(N):
+    q = O.find_3n_rns_primes(N, 60, 1)[0]
+    r = O.ThreeNSubRing(N, q)
+    assert pow(r.omega, 3 * N, q) == 1 and pow(r.omega, 3 * N // 2, q) != 1 and pow(r.omega, N, q) != 1
+    x = O.fill_uniform(11, 0, 0, q, N)
+    y = r.NTT(x)
+    assert (r.NTT_horner(x) == y).all()                     # ntt_3n.go:99-108
+    assert [int(t) for t in y] == O.py_3n_ntt(N, q, r.omega, x)
+    assert (r.INTT(y) == x).all()                           # ntt_3n_test.go:139-222
+    if N <= 96:
+        assert (r.INTT_gauss(y) == x).all()                 # ntt_3n.go:118-151,170-222
+    z = x.copy()
+    for _ in range(8):                                      # 8 repeated cycles, ntt_3n_test.go:183-199
+        z = r.INTT(r.NTT(z))
+    assert (z == x).all()
+    zero = np.zeros(N, dtype=np.uint64)
+    one = zero.copy(); one[0] = 1
+    assert (r.NTT(zero) == 0).all() and (r.NTT(one) == 1).all()
+    a = O.fill_uniform(12, 0, 0, q, N)
+    b = O.fill_uniform(13, 0, 0, q, N)
+    prod = np.array([(int(u) * int(v)) % q for u, v in zip(r.NTT(a), r.NTT(b))], dtype=np.uint64)
+    assert (r.INTT(prod) == O.schoolbook_3n(N, q, a, b)).all()   # ntt_3n_test.go:455-554
+
+
+def test_3n_fixed_product_n12():
+    # fixed operands of ring/ntt_3n_test.go:79-135 style: schoolbook mod X^12 - X^6 + 1, by hand
+    N, q = 12, O.find_3n_rns_primes(12, 20, 1)[0]
+    a = np.zeros(N, dtype=np.uint64); b = np.zeros(N, dtype=np.uint64)
+    a[11] = 1; b[1] = 1                      # X^11 * X = X^12 = X^6 - 1
+    c = O.schoolbook_3n(N, q, a, b)
+    want = np.zeros(N, dtype=np.uint64); want[6] = 1; want[0] = q - 1
+    assert (c == want).all()
+    r = O.ThreeNSubRing(N, q)
+    prod = np.array([(int(u) * int(v)) % q for u, v in zip(r.NTT(a), r.NTT(b))], dtype=np.uint64)
+    assert (r.INTT(prod) == want).all()
+
+
+def test_3n_config1_degree_3x2_12():
+    # BASELINE config 1: forward+inverse round trip, degree 3*2^12, single 3N-friendly prime
+    N = 3 * 2**12
+    q = O.find_3n_rns_primes(N, 60, 1)[0]
+    assert q == 0x10000000000a1001
+    r = O.ThreeNSubRing(N, q)
+    x = O.fill_uniform(0xB2000001, 0, 0, q, N)
+    y = r.NTT(x)
+    assert (r.NTT_horner(x) == y).all()
+    assert (r.INTT(y) == x).all()
+
+
+def test_3n_headline_size_spot_checks():
+    N = 3 * 2**15
+    qs = O.find_3n_rns_primes(N, 60, 24)
+    assert qs[0] == 0x1000000000248001 and qs[-1] == 0x10000000042b0001
+    r = O.ThreeNSubRing(N, qs[5])
+    x = O.fill_uniform(0xB2000003, 0, 5, qs[5], N)
+    y = r.NTT(x)
+    E = O.totatives(3 * N)
+    assert len(E) == N
+    rng = np.random.default_rng(3)
+    for k in list(rng.integers(0, N, 48)) + [0, 1, N - 1]:
+        assert r.horner_at(x, E[k]) == int(y[k])
+    assert (r.INTT(y) == x).all()
+
+
+def test_primes_and_roots():
+    assert O.lib().ref_primitive_root(576460752303439873) >= 3
+    for q in QI60[:4]:
+        assert O.lib().ref_is_prime(q) and not O.lib().ref_is_prime(q + 2)
+        f = np.zeros(16, dtype=np.uint64)
+        n = O.lib().ref_unique_factors(q - 1, O._p(f))
+        rem = q - 1
+        for p in f[:n]:
+            p = int(p); assert O.lib().ref_is_prime(p)
+            while rem % p == 0:
+                rem //= p
+        assert rem == 1
