@@ -1,0 +1,173 @@
+/*
+ * b200ring.h -- C ABI of the B200-native RNS NTT / NTT-domain multiply library.
+ *
+ * This is the drop-in boundary for the polynomial-arithmetic hot path of the Lattigo fork
+ * swanhong/matrix-fhe-lattigo (package ring/).  Every entry point names the reference
+ * interface it replaces (file:line, relative to the reference root).  A thin cgo file in
+ * package `ring` binds these symbols; tests and bench.py bind them
+ * with ctypes.  Plain pointers and sizes only; no C++ or torch types.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative B200_E* code; the message of the
+ *     last failure on the calling thread is b200_last_error().  The reference's constructors
+ *     return `error`, its hot functions panic (ring/ntt.go:211-214): the binding converts.
+ *   - a context is immutable after creation and may be used from many host threads
+ *     (ring/ring.go:192-194); work is enqueued on the context's CUDA stream and is
+ *     asynchronous until b200_sync() or a download.
+ *   - device polynomials are one contiguous [batch][L][N] uint64 allocation, limb-major like
+ *     ring.Poly.Coeffs (ring/poly.go:13-24); `level` selects limbs 0..level like
+ *     Ring.AtLevel (ring/ring.go:194-213, ring/ntt.go:128).
+ *   - in-place calls (in == out) are allowed everywhere (ring/ntt_3n.go:90-96).
+ *   - there is no CPU fallback: without a CUDA device every compute call fails with
+ *     B200_ENODEVICE.
+ */
+#ifndef B200RING_H
+#define B200RING_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define B200_API __attribute__((visibility("default")))
+#else
+#define B200_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200_ctx b200_ctx;   /* ring.Ring (ring/ring.go:76-89) + its SubRings on one GPU */
+typedef struct b200_poly b200_poly; /* ring.Poly (ring/poly.go:13-24), device resident, batched  */
+
+/* ring.Type (ring/ring.go:30-34).  ConjugateInvariant (1) is out of scope and rejected. */
+#define B200_RING_STANDARD 0 /* Z_q[X]/(X^N + 1), N = 2^k            */
+#define B200_RING_MATRIX 2   /* Z_q[X]/(X^N - X^(N/2) + 1), N = 2^a 3^b */
+
+/* error codes */
+#define B200_OK 0
+#define B200_EINVAL (-1)    /* bad argument / invalid ring parameters (constructor `error`) */
+#define B200_ENODEVICE (-2) /* no CUDA device or extension built without one                */
+#define B200_ECUDA (-3)     /* CUDA runtime failure; see b200_last_error()                  */
+#define B200_ESHAPE (-4)    /* polynomial / level / length mismatch (the reference panics)  */
+#define B200_ENOMEM (-5)
+
+/* flags of b200_ntt / b200_intt */
+#define B200_LAZY 1       /* NTTLazy / INTTLazy: output only guaranteed in [0,6q-2] / [0,2q-1]
+                             (ring/ntt.go:63-78); a canonical result is a valid lazy result */
+#define B200_TREE_ORDER 2 /* MATRIX rings only: keep NTT-domain slots in the transform's native
+                             tree order instead of the reference order (slot k <-> omega^E[k],
+                             E ascending totatives of 3N, ring/ntt_3n.go:46-53,235-243).
+                             MulCoeffs* is order agnostic, so fused pipelines may use it.    */
+
+/* Element-wise operators: op codes of b200_vec_op.  One code per function of ring/vec_ops.go /
+ * method of ring/operations.go; results are bit-identical to the Go functions, lazy ones included. */
+#define B200_OP_ADD 0                  /* Ring.Add              operations.go:11  vec_ops.go:7    */
+#define B200_OP_ADD_LAZY 1             /* Ring.AddLazy          operations.go:18  vec_ops.go:31   */
+#define B200_OP_SUB 2                  /* Ring.Sub              operations.go:25  vec_ops.go:55   */
+#define B200_OP_SUB_LAZY 3             /* Ring.SubLazy          operations.go:32  vec_ops.go:79   */
+#define B200_OP_NEG 4                  /* Ring.Neg              operations.go:39  vec_ops.go:103  */
+#define B200_OP_REDUCE 5               /* Ring.Reduce           operations.go:46  vec_ops.go:125  */
+#define B200_OP_REDUCE_LAZY 6          /* Ring.ReduceLazy       operations.go:53  vec_ops.go:147  */
+#define B200_OP_MFORM 7                /* Ring.MForm            operations.go:285 vec_ops.go:778  */
+#define B200_OP_MFORM_LAZY 8           /* Ring.MFormLazy        operations.go:292 vec_ops.go:800  */
+#define B200_OP_IMFORM 9               /* Ring.IMForm           operations.go:299 vec_ops.go:822  */
+#define B200_OP_MUL_BARRETT 16         /* Ring.MulCoeffsBarrett             operations.go:60  */
+#define B200_OP_MUL_BARRETT_LAZY 17    /* Ring.MulCoeffsBarrettLazy         operations.go:67  */
+#define B200_OP_MUL_BARRETT_ADD 18     /* Ring.MulCoeffsBarrettThenAdd      operations.go:74  */
+#define B200_OP_MUL_BARRETT_ADD_LAZY 19/* Ring.MulCoeffsBarrettThenAddLazy  operations.go:81  */
+#define B200_OP_MUL_MONT 32            /* Ring.MulCoeffsMontgomery                 operations.go:88  */
+#define B200_OP_MUL_MONT_LAZY 33       /* Ring.MulCoeffsMontgomeryLazy             operations.go:95  */
+#define B200_OP_MUL_MONT_ADD 34        /* Ring.MulCoeffsMontgomeryThenAdd          operations.go:109 */
+#define B200_OP_MUL_MONT_ADD_LAZY 35   /* Ring.MulCoeffsMontgomeryThenAddLazy      operations.go:116 */
+#define B200_OP_MUL_MONT_LAZY_ADD_LAZY 36 /* Ring.MulCoeffsMontgomeryLazyThenAddLazy operations.go:123 */
+#define B200_OP_MUL_MONT_SUB 37        /* Ring.MulCoeffsMontgomeryThenSub          operations.go:130 */
+#define B200_OP_MUL_MONT_SUB_LAZY 38   /* Ring.MulCoeffsMontgomeryThenSubLazy      operations.go:137 */
+#define B200_OP_MUL_MONT_LAZY_SUB_LAZY 39 /* Ring.MulCoeffsMontgomeryLazyThenSubLazy operations.go:144 */
+#define B200_OP_MUL_MONT_LAZY_NEG 40   /* Ring.MulCoeffsMontgomeryLazyThenNeg      operations.go:102 */
+#define B200_OP_MULSCALAR_MONT 48      /* SubRing.MulScalarMontgomery        subring_ops.go:202 */
+#define B200_OP_MULSCALAR_MONT_LAZY 49 /* SubRing.MulScalarMontgomeryLazy    subring_ops.go:209 */
+#define B200_OP_MULSCALAR_MONT_ADD 50  /* SubRing.MulScalarMontgomeryThenAdd subring_ops.go:216 */
+#define B200_OP_ADD_SCALAR 51          /* SubRing.AddScalar                  subring_ops.go:174 */
+#define B200_OP_SUB_SCALAR 52          /* SubRing.SubScalar                  subring_ops.go:195 */
+
+/* ---- library ------------------------------------------------------------------------------- */
+B200_API const char *b200_last_error(void);   /* message of the last failure on this thread ("" if none) */
+B200_API const char *b200_version(void);
+B200_API int b200_device_count(void);         /* 0 when no CUDA device is visible */
+
+/* ---- context: ring.NewRing / NewRingFromType / NewRingWithCustomNTT (ring/ring.go:264-356) ----
+ * Validates like the reference (ring degree ring.go:319-323 / subring.go:14-30, non-empty and
+ * distinct moduli ring.go:325-331, prime and = 1 mod NthRoot subring.go:140-146), generates the
+ * per-prime constants and twiddle tables (subring.go:74-111,129-214; ntt_3n.go:35-79) and uploads
+ * them to `device`.
+ *   roots == NULL or roots[i] == 0 : deterministic choice of the reference --
+ *       STANDARD: g = smallest primitive root >= 3 (subring.go:236-248), psi = g^((q-1)/2N);
+ *       MATRIX  : omega = g^((q-1)/3N) (subring.go:255-290).
+ *   roots[i] != 0 : STANDARD: the primitive root g of q_i (SubRing.PrimitiveRoot, skips factoring q-1);
+ *                   MATRIX  : the primitive 3N-th root omega the Go transformer drew at random
+ *                             (NumberTheoreticTransformer3N.psi3N, ntt_3n.go:39), so NTT-domain
+ *                             values agree with that Go ring.
+ */
+B200_API int b200_ctx_create(int ring_type, int N, int L, const uint64_t *moduli, const uint64_t *roots,
+                    int device, b200_ctx **out);
+B200_API void b200_ctx_destroy(b200_ctx *ctx);
+B200_API int b200_ctx_set_stream(b200_ctx *ctx, void *cuda_stream); /* cudaStream_t; NULL = default stream */
+B200_API int b200_sync(b200_ctx *ctx);                              /* wait for all enqueued work */
+B200_API int b200_ctx_n(const b200_ctx *ctx);                       /* Ring.N()                 */
+B200_API int b200_ctx_moduli_count(const b200_ctx *ctx);            /* Ring.ModuliChainLength() */
+B200_API int b200_ctx_ring_type(const b200_ctx *ctx);
+/* SubRing fields of limb i (ring/subring.go:35-55, ring/ntt.go:38-44):
+ *   out[0]=Modulus out[1]=MRedConstant out[2..3]=BRedConstant out[4]=Mask
+ *   out[5]=PrimitiveRoot g out[6]=NInv (Montgomery form; STANDARD only) out[7]=root used (psi or omega) */
+B200_API int b200_ctx_subring(const b200_ctx *ctx, int limb, uint64_t out[8]);
+/* STANDARD rings: NTTTable.RootsForward (inverse=0) / RootsBackward (inverse=1), N words, Montgomery
+ * form, bit-reversed order -- bit-identical to subring.go:187-205. */
+B200_API int b200_ctx_roots(const b200_ctx *ctx, int limb, int inverse, uint64_t *out, size_t n);
+
+/* ---- device polynomials: ring.Poly / Ring.NewPoly (ring/poly.go:18-24) ---------------------- */
+B200_API int b200_poly_alloc(b200_ctx *ctx, int batch, b200_poly **out); /* zero-filled [batch][L][N]   */
+/* wrap caller-owned device memory of batch*L*N words (e.g. a torch tensor); never freed here */
+B200_API int b200_poly_wrap(b200_ctx *ctx, void *device_ptr, int batch, b200_poly **out);
+B200_API void b200_poly_free(b200_poly *p);
+B200_API void *b200_poly_device_ptr(b200_poly *p);
+B200_API int b200_poly_batch(const b200_poly *p);
+/* one limb of one polynomial <-> a Go []uint64 (Poly.Coeffs[limb]); n must be >= N (ntt.go:212) */
+B200_API int b200_poly_upload_limb(b200_poly *p, int b, int limb, const uint64_t *host, size_t n);
+B200_API int b200_poly_download_limb(b200_poly *p, int b, int limb, uint64_t *host, size_t n);
+/* the whole [batch][L][N] block from/to one contiguous host buffer (pinned for full PCIe rate) */
+B200_API int b200_poly_upload(b200_poly *p, const uint64_t *host, size_t n_words);
+B200_API int b200_poly_download(b200_poly *p, uint64_t *host, size_t n_words);
+
+/* ---- transforms ---------------------------------------------------------------------------
+ * Ring.NTT / NTTLazy (ring/ntt.go:127-138) and Ring.INTT / INTTLazy (ring/ntt.go:141-152) on all
+ * batch x (level+1) limbs in one enqueue.  STANDARD: NumberTheoreticTransformerStandard
+ * (ntt.go:59-78; out[i] = f(psi^(2 bitrev(i)+1)), canonical).  MATRIX:
+ * NumberTheoreticTransformer3N.Forward/Backward (ntt_3n.go:82-156) computed in O(N log N). */
+B200_API int b200_ntt(b200_ctx *ctx, const b200_poly *in, b200_poly *out, int level, int flags);
+B200_API int b200_intt(b200_ctx *ctx, const b200_poly *in, b200_poly *out, int level, int flags);
+
+/* ---- element-wise family: p3 = op(p1, p2 [, p3]) (ring/operations.go, ring/vec_ops.go) -------
+ * p2 may be NULL for unary ops.  For *_SCALAR / MULSCALAR ops `scalars` holds one word per limb
+ * (level+1 of them; Montgomery form where the Go method says so); otherwise NULL. */
+B200_API int b200_vec_op(b200_ctx *ctx, int op, const b200_poly *p1, const b200_poly *p2, b200_poly *p3,
+                int level, const uint64_t *scalars);
+
+/* ---- fused ring product (BASELINE config 4; ring/ring_test.go:106-110 sequence) ---------------
+ * c = INTT( MulCoeffsMontgomery( MForm(NTT(a)), NTT(b) ) ) = a*b in the ring, coefficient domain,
+ * canonical.  a, b are left untouched unless they alias c. */
+B200_API int b200_polymul(b200_ctx *ctx, const b200_poly *a, const b200_poly *b, b200_poly *c, int level);
+
+/* ---- plugin granularity: ring.NumberTheoreticTransformer (ring/ntt.go:15-22) -----------------
+ * One limb, HOST slices in and out (upload -> transform -> download, synchronous).  This is what a
+ * NewRingWithCustomNTT factory (ring/ring.go:314) binds; it is correct but not the fast path. */
+B200_API int b200_subring_ntt_host(b200_ctx *ctx, int limb, const uint64_t *p1, uint64_t *p2, size_t n,
+                          int inverse, int flags);
+
+/* kernel launches enqueued by this context so far (bench.py's gpu_launches evidence) */
+B200_API uint64_t b200_ctx_launch_count(const b200_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200RING_H */

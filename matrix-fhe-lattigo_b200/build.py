@@ -1,0 +1,53 @@
+"""Build libb200ring.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
+
+    python matrix-fhe-lattigo_b200/build.py [--force]
+
+nvcc cross-compiles without a GPU.  Objects go to csrc/_obj/, the library to lib/libb200ring.so
+(git-ignored, shipped to the GPU box with the repo snapshot).
+"""
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(CSRC, "_obj")
+LIB = os.path.join(HERE, "lib", "libb200ring.so")
+SOURCES = ["b200ring.cu", "ewise.cu", "ntt_generic.cu", "ntt_big.cu"]
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+         "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr", "-ccbin", "g++"]
+
+
+def _deps():
+    hdr = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".hpp", ".cuh", ".h"))]
+    hdr.append(os.path.join(os.path.dirname(HERE), "include", "b200ring.h"))
+    return max(os.path.getmtime(h) for h in hdr)
+
+
+def _compile(src, force, hdr_mtime):
+    s = os.path.join(CSRC, src)
+    o = os.path.join(OBJ, src.replace(".cu", ".o"))
+    if not force and os.path.exists(o) and os.path.getmtime(o) >= max(os.path.getmtime(s), hdr_mtime):
+        return o, False
+    subprocess.check_call([NVCC] + FLAGS + ["-c", s, "-o", o])
+    return o, True
+
+
+def build(force=False, verbose=True):
+    os.makedirs(OBJ, exist_ok=True)
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    hm = _deps()
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        res = list(ex.map(lambda s: _compile(s, force, hm), SOURCES))
+    objs = [o for o, _ in res]
+    if force or any(ch for _, ch in res) or not os.path.exists(LIB):
+        subprocess.check_call([NVCC, "-shared", "-o", LIB] + objs + ["-cudart", "static", "-ccbin", "g++"])
+        if verbose:
+            print("built", LIB)
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv)

@@ -1,0 +1,83 @@
+"""ctypes binding of include/b200ring.h.  There is no fallback: if the CUDA library is missing the
+import of any compute symbol raises, and without a GPU every compute call returns B200_ENODEVICE."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libb200ring.so")
+
+u64 = C.c_uint64
+P64 = C.POINTER(C.c_uint64)
+VP = C.c_void_p
+
+# every symbol include/b200ring.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "b200_last_error": (C.c_char_p, []),
+    "b200_version": (C.c_char_p, []),
+    "b200_device_count": (C.c_int, []),
+    "b200_ctx_create": (C.c_int, [C.c_int, C.c_int, C.c_int, P64, P64, C.c_int, C.POINTER(VP)]),
+    "b200_ctx_destroy": (None, [VP]),
+    "b200_ctx_set_stream": (C.c_int, [VP, VP]),
+    "b200_sync": (C.c_int, [VP]),
+    "b200_ctx_n": (C.c_int, [VP]),
+    "b200_ctx_moduli_count": (C.c_int, [VP]),
+    "b200_ctx_ring_type": (C.c_int, [VP]),
+    "b200_ctx_subring": (C.c_int, [VP, C.c_int, P64]),
+    "b200_ctx_roots": (C.c_int, [VP, C.c_int, C.c_int, P64, C.c_size_t]),
+    "b200_poly_alloc": (C.c_int, [VP, C.c_int, C.POINTER(VP)]),
+    "b200_poly_wrap": (C.c_int, [VP, VP, C.c_int, C.POINTER(VP)]),
+    "b200_poly_free": (None, [VP]),
+    "b200_poly_device_ptr": (VP, [VP]),
+    "b200_poly_batch": (C.c_int, [VP]),
+    "b200_poly_upload_limb": (C.c_int, [VP, C.c_int, C.c_int, P64, C.c_size_t]),
+    "b200_poly_download_limb": (C.c_int, [VP, C.c_int, C.c_int, P64, C.c_size_t]),
+    "b200_poly_upload": (C.c_int, [VP, VP, C.c_size_t]),
+    "b200_poly_download": (C.c_int, [VP, VP, C.c_size_t]),
+    "b200_ntt": (C.c_int, [VP, VP, VP, C.c_int, C.c_int]),
+    "b200_intt": (C.c_int, [VP, VP, VP, C.c_int, C.c_int]),
+    "b200_vec_op": (C.c_int, [VP, C.c_int, VP, VP, VP, C.c_int, P64]),
+    "b200_polymul": (C.c_int, [VP, VP, VP, VP, C.c_int]),
+    "b200_subring_ntt_host": (C.c_int, [VP, C.c_int, P64, P64, C.c_size_t, C.c_int, C.c_int]),
+    "b200_ctx_launch_count": (C.c_uint64, [VP]),
+}
+
+B200_LAZY, B200_TREE_ORDER = 1, 2
+ENODEVICE = -2
+
+
+class B200Error(RuntimeError):
+    """A failed C-ABI call: `.code` is the B200_E* value, the message is b200_last_error()."""
+
+    def __init__(self, code, msg):
+        super().__init__(msg)
+        self.code = code
+
+
+_lib = None
+
+
+def load_library(path=None):
+    """dlopen the CUDA library and bind every declared symbol; raises if it was not built."""
+    global _lib
+    if _lib is None:
+        path = path or LIB_PATH
+        if not os.path.exists(path):
+            raise ImportError(
+                "b200ring: CUDA extension %s is missing -- build it with `python matrix-fhe-lattigo_b200/build.py` "
+                "(there is no CPU fallback)" % path)
+        L = C.CDLL(path)
+        for name, (res, args) in SYMBOLS.items():
+            f = getattr(L, name)   # AttributeError if the header and the library disagree
+            f.restype, f.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def lib():
+    return load_library()
+
+
+def check(rc):
+    if rc != 0:
+        raise B200Error(rc, lib().b200_last_error().decode())
+    return rc

@@ -1,0 +1,455 @@
+// b200ring.cu -- the C ABI of include/b200ring.h: context creation (per-prime constants and twiddle
+// tables, bit-identical to the reference's ring/subring.go:129-214), device polynomial management and
+// dispatch to the sm_100a kernels.  No CPU fallback: every compute entry point needs a CUDA device.
+#include <cstdio>
+#include <cstring>
+#include <set>
+
+#include "hostmath.hpp"
+#include "internal.hpp"
+
+namespace hm = hostmath;
+
+// ---- error plumbing -------------------------------------------------------------------------------
+static thread_local std::string g_err;
+void b200_set_error(const std::string &msg) { g_err = msg; }
+int b200_cuda_fail(cudaError_t e, const char *what) {
+    g_err = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return B200_ENODEVICE;
+    if (e == cudaErrorMemoryAllocation) return B200_ENOMEM;
+    return B200_ECUDA;
+}
+static int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+
+extern "C" const char *b200_last_error(void) { return g_err.c_str(); }
+extern "C" const char *b200_version(void) { return "b200ring 0.1 (sm_100a)"; }
+extern "C" int b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int b200_ensure_scratch(b200_ctx *ctx, size_t words) {
+    if (ctx->scratch_words >= words) return 0;
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_scratch) CUDA_TRY(cudaFree(ctx->d_scratch));
+    ctx->d_scratch = nullptr;
+    ctx->scratch_words = 0;
+    CUDA_TRY(cudaMalloc(&ctx->d_scratch, words * sizeof(u64)));
+    ctx->scratch_words = words;
+    return 0;
+}
+
+// ---- ring-degree validation (subring.go:14-30, ring.go:266,319-323) -------------------------------------
+static bool valid_3n_degree(int N, int *a_out, int *b_out) {
+    if (N <= 0) return false;
+    int a = 0, b = 0, t = N;
+    while (t % 2 == 0) t /= 2, ++a;
+    while (t % 3 == 0) t /= 3, ++b;
+    if (a_out) *a_out = a;
+    if (b_out) *b_out = b;
+    return t == 1;
+}
+
+static tw_t mk_tw(u64 w, u64 q) { return make_ulonglong2(w, hm::shoup(w, q)); }
+
+// STANDARD tables: Go-format (Montgomery, bit-reversed; subring.go:183-205) + plain/Shoup device format
+static void build_standard(b200_ctx *ctx, int i, std::vector<tw_t> &fwd, std::vector<tw_t> &inv, tw_t *misc) {
+    SubRingHost &s = ctx->sub[i];
+    const int N = ctx->N, logN = ctx->logN;
+    const u64 q = s.q, nth = 2 * (u64)N;
+    s.ninv = hm::mform(hm::invmod_prime(nth >> 1, q), q);                       // subring.go:183
+    const u64 psi = hm::powmod(s.g, (q - 1) / nth, q);                           // :187
+    const u64 psi_inv = hm::powmod(s.g, q - ((q - 1) / nth) - 1, q);             // :188
+    s.root = psi;
+    const u64 psi_m = hm::mform(psi, q), psi_inv_m = hm::mform(psi_inv, q);
+    s.roots_fwd.assign(N, 0);
+    s.roots_bwd.assign(N, 0);
+    s.roots_fwd[0] = s.roots_bwd[0] = hm::mform(1, q);
+    u64 pf = 1, pb = 1;   // plain-domain running powers
+    fwd[0] = inv[0] = mk_tw(1, q);
+    for (u64 j = 1; j < (u64)N; ++j) {                                           // :198-205
+        const u64 prev = hm::bitrev(j - 1, logN), cur = hm::bitrev(j, logN);
+        s.roots_fwd[cur] = hm::mred(s.roots_fwd[prev], psi_m, q, s.qinv);
+        s.roots_bwd[cur] = hm::mred(s.roots_bwd[prev], psi_inv_m, q, s.qinv);
+        pf = hm::mulmod(pf, psi, q);
+        pb = hm::mulmod(pb, psi_inv, q);
+        fwd[cur] = mk_tw(pf, q);
+        inv[cur] = mk_tw(pb, q);
+    }
+    const u64 ninv = hm::invmod_prime((u64)N % q, q);
+    misc[MISC_NINV] = mk_tw(ninv, q);
+    misc[MISC_NINV_W1] = mk_tw(hm::mulmod(ninv, inv[1].x, q), q);
+}
+
+// MATRIX tables: zetas in the order of the exponent tree: index 1 = omega^(N/2),
+// radix-3 layer with nb blocks at [nb + 2 blk, +1], radix-2 layer with nb blocks at [nb + blk].
+static void build_matrix(b200_ctx *ctx, int i, std::vector<tw_t> &fwd, std::vector<tw_t> &inv, tw_t *misc,
+                         std::vector<int> *leaf_out) {
+    SubRingHost &s = ctx->sub[i];
+    const int N = ctx->N;
+    const u64 q = s.q, omega = s.root, M = 3 * (u64)N;
+    std::vector<u64> pw(M);   // omega^e, e in [0, 3N)
+    pw[0] = 1;
+    for (u64 e = 1; e < M; ++e) pw[e] = hm::mulmod(pw[e - 1], omega, q);
+    auto set = [&](size_t idx, u64 e) {
+        e %= M;
+        fwd[idx] = mk_tw(pw[e], q);
+        inv[idx] = mk_tw(pw[(M - e) % M], q);
+    };
+    std::vector<u64> cur{M / 6, 5 * M / 6}, nxt;
+    set(0, 0);
+    set(1, cur[0]);
+    for (int l = 0; l < ctx->b; ++l) {              // radix-3 levels: e -> e/3 + {0, N, 2N}
+        const size_t nb = cur.size();
+        nxt.assign(3 * nb, 0);
+        for (size_t k = 0; k < nb; ++k) {
+            const u64 e = cur[k] / 3;
+            nxt[3 * k] = e; nxt[3 * k + 1] = e + M / 3; nxt[3 * k + 2] = e + 2 * (M / 3);
+            set(nb + 2 * k, e);
+            set(nb + 2 * k + 1, 2 * e);
+        }
+        cur.swap(nxt);
+    }
+    for (int l = 0; l < ctx->a - 1; ++l) {          // radix-2 levels: e -> e/2 + {0, 3N/2}
+        const size_t nb = cur.size();
+        nxt.assign(2 * nb, 0);
+        for (size_t k = 0; k < nb; ++k) {
+            const u64 e = cur[k] / 2;
+            nxt[2 * k] = e; nxt[2 * k + 1] = e + M / 2;
+            set(nb + k, e);
+        }
+        cur.swap(nxt);
+    }
+    if (leaf_out) {
+        leaf_out->resize(N);
+        for (int k = 0; k < N; ++k) (*leaf_out)[k] = (int)(cur[k] % M);
+    }
+    const u64 zeta = pw[N / 2], zeta5 = pw[(5 * (u64)N / 2) % M];
+    const u64 c = hm::invmod_prime(hm::submod(zeta, zeta5, q), q);
+    const u64 two_over_n = hm::mulmod(2, hm::invmod_prime((u64)N % q, q), q);
+    misc[MISC_OMEGA3] = mk_tw(pw[N], q);
+    misc[MISC_K1] = mk_tw(hm::mulmod(c, two_over_n, q), q);
+    misc[MISC_K2] = mk_tw(two_over_n, q);
+    misc[MISC_ZETA] = mk_tw(zeta, q);
+}
+
+extern "C" int b200_ctx_create(int ring_type, int N, int L, const uint64_t *moduli, const uint64_t *roots,
+                               int device, b200_ctx **out) {
+    if (!out) return fail(B200_EINVAL, "b200_ctx_create: out is NULL");
+    *out = nullptr;
+    int a = 0, b = 0;
+    const bool pow2 = N >= 8 && (N & (N - 1)) == 0;
+    const bool is3n = valid_3n_degree(N, &a, &b);
+    if (ring_type != B200_RING_STANDARD && ring_type != B200_RING_MATRIX)
+        return fail(B200_EINVAL, "invalid ring type");
+    if (!pow2 && !is3n)   // ring.go:319-323
+        return fail(B200_EINVAL, "invalid ring degree: must be a power of 2 greater than 8 or satisfy 3N = 2^a * 3^{b+1} condition");
+    if (ring_type == B200_RING_STANDARD && !pow2)
+        return fail(B200_EINVAL, "invalid ring degree: the Standard ring needs N to be a power of 2 greater than 8");
+    if (ring_type == B200_RING_MATRIX && !(N % 3 == 0 && is3n && N >= 8 && a >= 1))   // ring.go:301-303
+        return fail(B200_EINVAL, "matrix ring type requires N to satisfy 3N = 2^a * 3^{b+1} condition, got N=" + std::to_string(N));
+    if (L <= 0 || !moduli) return fail(B200_EINVAL, "invalid ModuliChain (must be a non-empty []uint64)");   // ring.go:325-327
+    {
+        std::set<u64> seen(moduli, moduli + L);
+        if ((int)seen.size() != L) return fail(B200_EINVAL, "invalid ModuliChain (moduli are not distinct)");   // ring.go:329-331
+    }
+    const u64 nthroot = ring_type == B200_RING_MATRIX ? 3 * (u64)N : 2 * (u64)N;
+    for (int i = 0; i < L; ++i) {
+        const u64 q = moduli[i];
+        if (!hm::is_prime(q)) return fail(B200_EINVAL, "invalid modulus: " + std::to_string(q) + " is not prime)");      // subring.go:140-142
+        if (q % nthroot != 1) return fail(B200_EINVAL, "invalid modulus: " + std::to_string(q) + " != 1 mod NthRoot)");   // subring.go:144-146
+        if (q >> 61) return fail(B200_EINVAL, "invalid modulus: " + std::to_string(q) + " exceeds 61 bits (lazy butterflies need 8q < 2^64, ring/ntt.go:169)");
+    }
+    int ndev = b200_device_count();
+    if (ndev <= 0) return fail(B200_ENODEVICE, "no CUDA device visible: b200ring has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(B200_EINVAL, "invalid device index " + std::to_string(device));
+    CUDA_TRY(cudaSetDevice(device));
+
+    b200_ctx *ctx = new b200_ctx();
+    ctx->ring_type = ring_type; ctx->N = N; ctx->L = L; ctx->device = device;
+    ctx->a = a; ctx->b = b;
+    while ((1 << ctx->logN) < N) ctx->logN++;
+    cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    ctx->sub.resize(L);
+
+    std::vector<LimbConst> consts(L);
+    std::vector<tw_t> fwd((size_t)L * N), inv((size_t)L * N), misc((size_t)L * MISC_COUNT, make_ulonglong2(0, 0));
+    std::vector<int> leaf;
+    for (int i = 0; i < L; ++i) {
+        SubRingHost &s = ctx->sub[i];
+        s.q = moduli[i];
+        s.qinv = hm::mred_constant(s.q);
+        hm::bred_constant(s.q, s.brc);
+        int bl = 0;
+        while (bl < 64 && ((s.q - 1) >> bl)) ++bl;
+        s.mask = bl >= 64 ? ~0ULL : ((1ULL << bl) - 1);   // subring.go:94
+        consts[i] = LimbConst{s.q, s.qinv, s.brc[0], s.brc[1]};
+        std::vector<tw_t> f(N), v(N);
+        const u64 given = roots ? roots[i] : 0;
+        if (ring_type == B200_RING_STANDARD) {
+            if (given) {
+                std::vector<u64> fac = hm::unique_factors(s.q - 1);
+                if (!hm::is_primitive_root(given % s.q, s.q, fac)) { delete ctx; return fail(B200_EINVAL, "roots[" + std::to_string(i) + "] is not a primitive root"); }
+                s.g = given;
+            } else {
+                s.g = hm::primitive_root(s.q, hm::unique_factors(s.q - 1));   // subring.go:218-251
+            }
+            build_standard(ctx, i, f, v, &misc[(size_t)i * MISC_COUNT]);
+        } else {
+            if (given) {
+                const u64 w = given % s.q;
+                if (hm::powmod(w, nthroot, s.q) != 1 || hm::powmod(w, nthroot / 2, s.q) == 1 || hm::powmod(w, nthroot / 3, s.q) == 1) {
+                    delete ctx;
+                    return fail(B200_EINVAL, "roots[" + std::to_string(i) + "] is not a primitive 3N-th root of unity");
+                }
+                s.root = w;
+            } else {
+                s.g = hm::primitive_root(s.q, hm::unique_factors(s.q - 1));
+                s.root = hm::powmod(s.g, (s.q - 1) / nthroot, s.q);           // subring.go:255-290
+            }
+            build_matrix(ctx, i, f, v, &misc[(size_t)i * MISC_COUNT], i == 0 ? &leaf : nullptr);
+        }
+        std::copy(f.begin(), f.end(), fwd.begin() + (size_t)i * N);
+        std::copy(v.begin(), v.end(), inv.begin() + (size_t)i * N);
+    }
+
+    auto up = [&](void **dst, const void *src, size_t bytes) -> cudaError_t {
+        cudaError_t e = cudaMalloc(dst, bytes);
+        if (e != cudaSuccess) return e;
+        return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+    };
+    cudaError_t e = up((void **)&ctx->d_consts, consts.data(), sizeof(LimbConst) * L);
+    if (e == cudaSuccess) e = up((void **)&ctx->d_fwd, fwd.data(), sizeof(tw_t) * fwd.size());
+    if (e == cudaSuccess) e = up((void **)&ctx->d_inv, inv.data(), sizeof(tw_t) * inv.size());
+    if (e == cudaSuccess) e = up((void **)&ctx->d_misc, misc.data(), sizeof(tw_t) * misc.size());
+    if (e == cudaSuccess && ring_type == B200_RING_MATRIX) {
+        // reference slot order: slot k <-> omega^E[k], E ascending totatives of 3N (ntt_3n.go:46-53,235-243)
+        std::vector<int> pos(3 * (size_t)N, -1), go2fast(N);
+        int k = 0;
+        for (int ex = 1; ex < 3 * N; ++ex)
+            if (ex % 2 != 0 && ex % 3 != 0) pos[ex] = k++;
+        for (int idx = 0; idx < N; ++idx) go2fast[pos[leaf[idx]]] = idx;
+        e = up((void **)&ctx->d_go2fast, go2fast.data(), sizeof(int) * N);
+    }
+    if (e != cudaSuccess) { b200_ctx_destroy(ctx); return b200_cuda_fail(e, "context table upload"); }
+    int rc = big_tables_create(ctx);
+    if (rc < 0) { b200_ctx_destroy(ctx); return rc; }
+    *out = ctx;
+    return B200_OK;
+}
+
+extern "C" void b200_ctx_destroy(b200_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    big_tables_destroy(ctx);
+    cudaFree(ctx->d_consts); cudaFree(ctx->d_fwd); cudaFree(ctx->d_inv); cudaFree(ctx->d_misc);
+    cudaFree(ctx->d_go2fast); cudaFree(ctx->d_scratch);
+    delete ctx;
+}
+extern "C" int b200_ctx_set_stream(b200_ctx *ctx, void *s) {
+    if (!ctx) return fail(B200_EINVAL, "ctx is NULL");
+    ctx->stream = (cudaStream_t)s;
+    return 0;
+}
+extern "C" int b200_sync(b200_ctx *ctx) {
+    if (!ctx) return fail(B200_EINVAL, "ctx is NULL");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+extern "C" int b200_ctx_n(const b200_ctx *ctx) { return ctx ? ctx->N : B200_EINVAL; }
+extern "C" int b200_ctx_moduli_count(const b200_ctx *ctx) { return ctx ? ctx->L : B200_EINVAL; }
+extern "C" int b200_ctx_ring_type(const b200_ctx *ctx) { return ctx ? ctx->ring_type : B200_EINVAL; }
+extern "C" uint64_t b200_ctx_launch_count(const b200_ctx *ctx) { return ctx ? ctx->launches.load() : 0; }
+
+extern "C" int b200_ctx_subring(const b200_ctx *ctx, int limb, uint64_t out[8]) {
+    if (!ctx || !out || limb < 0 || limb >= ctx->L) return fail(B200_EINVAL, "b200_ctx_subring: bad argument");
+    const SubRingHost &s = ctx->sub[limb];
+    out[0] = s.q; out[1] = s.qinv; out[2] = s.brc[0]; out[3] = s.brc[1]; out[4] = s.mask;
+    out[5] = s.g; out[6] = s.ninv; out[7] = s.root;
+    return 0;
+}
+extern "C" int b200_ctx_roots(const b200_ctx *ctx, int limb, int inverse, uint64_t *out, size_t n) {
+    if (!ctx || !out || limb < 0 || limb >= ctx->L) return fail(B200_EINVAL, "b200_ctx_roots: bad argument");
+    if (ctx->ring_type != B200_RING_STANDARD) return fail(B200_EINVAL, "b200_ctx_roots: only Standard rings carry RootsForward/RootsBackward");
+    if (n < (size_t)ctx->N) return fail(B200_ESHAPE, "b200_ctx_roots: len(out) < N");
+    const std::vector<u64> &t = inverse ? ctx->sub[limb].roots_bwd : ctx->sub[limb].roots_fwd;
+    std::memcpy(out, t.data(), sizeof(u64) * ctx->N);
+    return 0;
+}
+
+// ---- device polynomials ---------------------------------------------------------------------------
+static size_t poly_words(const b200_poly *p) { return (size_t)p->batch * p->ctx->L * p->ctx->N; }
+
+extern "C" int b200_poly_alloc(b200_ctx *ctx, int batch, b200_poly **out) {
+    if (!ctx || !out || batch <= 0) return fail(B200_EINVAL, "b200_poly_alloc: bad argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    b200_poly *p = new b200_poly();
+    p->ctx = ctx; p->batch = batch; p->owned = true;
+    const size_t bytes = poly_words(p) * sizeof(u64);
+    cudaError_t e = cudaMalloc(&p->d, bytes);
+    if (e == cudaSuccess) e = cudaMemsetAsync(p->d, 0, bytes, ctx->stream);
+    if (e != cudaSuccess) { cudaFree(p->d); delete p; return b200_cuda_fail(e, "b200_poly_alloc"); }
+    *out = p;
+    return 0;
+}
+extern "C" int b200_poly_wrap(b200_ctx *ctx, void *device_ptr, int batch, b200_poly **out) {
+    if (!ctx || !out || !device_ptr || batch <= 0) return fail(B200_EINVAL, "b200_poly_wrap: bad argument");
+    if ((uintptr_t)device_ptr % 16) return fail(B200_EINVAL, "b200_poly_wrap: device pointer must be 16-byte aligned");
+    b200_poly *p = new b200_poly();
+    p->ctx = ctx; p->batch = batch; p->owned = false; p->d = (u64 *)device_ptr;
+    *out = p;
+    return 0;
+}
+extern "C" void b200_poly_free(b200_poly *p) {
+    if (!p) return;
+    if (p->owned) { cudaSetDevice(p->ctx->device); cudaStreamSynchronize(p->ctx->stream); cudaFree(p->d); }
+    delete p;
+}
+extern "C" void *b200_poly_device_ptr(b200_poly *p) { return p ? p->d : nullptr; }
+extern "C" int b200_poly_batch(const b200_poly *p) { return p ? p->batch : B200_EINVAL; }
+
+static int limb_check(const b200_poly *p, int b, int limb, const void *host, size_t n, const char *who) {
+    if (!p || !host) return fail(B200_EINVAL, std::string(who) + ": NULL argument");
+    if (b < 0 || b >= p->batch || limb < 0 || limb >= p->ctx->L) return fail(B200_ESHAPE, std::string(who) + ": poly/limb index out of range");
+    if (n < (size_t)p->ctx->N) return fail(B200_ESHAPE, std::string(who) + ": len(slice)=" + std::to_string(n) + " < N=" + std::to_string(p->ctx->N));
+    return 0;
+}
+extern "C" int b200_poly_upload_limb(b200_poly *p, int b, int limb, const uint64_t *host, size_t n) {
+    if (int rc = limb_check(p, b, limb, host, n, "b200_poly_upload_limb")) return rc;
+    b200_ctx *c = p->ctx;
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemcpyAsync(p->d + ((size_t)b * c->L + limb) * c->N, host, sizeof(u64) * c->N, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));   // the Go slice may be reused as soon as we return
+    return 0;
+}
+extern "C" int b200_poly_download_limb(b200_poly *p, int b, int limb, uint64_t *host, size_t n) {
+    if (int rc = limb_check(p, b, limb, host, n, "b200_poly_download_limb")) return rc;
+    b200_ctx *c = p->ctx;
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemcpyAsync(host, p->d + ((size_t)b * c->L + limb) * c->N, sizeof(u64) * c->N, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+extern "C" int b200_poly_upload(b200_poly *p, const uint64_t *host, size_t n_words) {
+    if (!p || !host) return fail(B200_EINVAL, "b200_poly_upload: NULL argument");
+    if (n_words != poly_words(p)) return fail(B200_ESHAPE, "b200_poly_upload: expected batch*L*N words");
+    CUDA_TRY(cudaSetDevice(p->ctx->device));
+    CUDA_TRY(cudaMemcpyAsync(p->d, host, n_words * sizeof(u64), cudaMemcpyHostToDevice, p->ctx->stream));
+    return 0;   // asynchronous when `host` is pinned; ordered before later work on the stream
+}
+extern "C" int b200_poly_download(b200_poly *p, uint64_t *host, size_t n_words) {
+    if (!p || !host) return fail(B200_EINVAL, "b200_poly_download: NULL argument");
+    if (n_words != poly_words(p)) return fail(B200_ESHAPE, "b200_poly_download: expected batch*L*N words");
+    CUDA_TRY(cudaSetDevice(p->ctx->device));
+    CUDA_TRY(cudaMemcpyAsync(host, p->d, n_words * sizeof(u64), cudaMemcpyDeviceToHost, p->ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(p->ctx->stream));
+    return 0;
+}
+
+// ---- dispatch ---------------------------------------------------------------------------------------
+static int check_polys(b200_ctx *ctx, int level, const char *who, std::initializer_list<const b200_poly *> ps, int *batch) {
+    if (!ctx) return fail(B200_EINVAL, std::string(who) + ": ctx is NULL");
+    if (level < 0) return fail(B200_ESHAPE, std::string(who) + ": level cannot be negative");                       // ring.go:197-199
+    if (level >= ctx->L) return fail(B200_ESHAPE, std::string(who) + ": level cannot be larger than max level");    // ring.go:202-204
+    int bt = -1;
+    for (const b200_poly *p : ps) {
+        if (!p) return fail(B200_EINVAL, std::string(who) + ": NULL polynomial");
+        if (p->ctx != ctx) return fail(B200_ESHAPE, std::string(who) + ": polynomial belongs to another ring");
+        if (bt < 0) bt = p->batch;
+        if (p->batch != bt) return fail(B200_ESHAPE, std::string(who) + ": batch sizes differ");
+    }
+    *batch = bt;
+    return 0;
+}
+
+static int transform(b200_ctx *ctx, const b200_poly *in, b200_poly *out, int level, int flags, bool inverse, const char *who) {
+    int batch;
+    if (int rc = check_polys(ctx, level, who, {in, out}, &batch)) return rc;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    Span sp{batch, level + 1, ctx->L, 0};
+    int rc = launch_ntt_big(ctx, in->d, out->d, sp, inverse, flags);
+    if (rc == 1) rc = launch_ntt_generic(ctx, in->d, out->d, sp, inverse, flags);
+    return rc;
+}
+extern "C" int b200_ntt(b200_ctx *ctx, const b200_poly *in, b200_poly *out, int level, int flags) {
+    return transform(ctx, in, out, level, flags, false, "b200_ntt");
+}
+extern "C" int b200_intt(b200_ctx *ctx, const b200_poly *in, b200_poly *out, int level, int flags) {
+    return transform(ctx, in, out, level, flags, true, "b200_intt");
+}
+
+extern "C" int b200_vec_op(b200_ctx *ctx, int op, const b200_poly *p1, const b200_poly *p2, b200_poly *p3, int level,
+                           const uint64_t *scalars) {
+    int batch;
+    const bool unary = (op >= B200_OP_NEG && op <= B200_OP_IMFORM) || op >= B200_OP_MULSCALAR_MONT;
+    if (unary) {
+        if (int rc = check_polys(ctx, level, "b200_vec_op", {p1, p3}, &batch)) return rc;
+    } else {
+        if (int rc = check_polys(ctx, level, "b200_vec_op", {p1, p2, p3}, &batch)) return rc;
+    }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const u64 *d_sc = nullptr;
+    if (op >= B200_OP_MULSCALAR_MONT) {
+        if (!scalars) return fail(B200_EINVAL, "b200_vec_op: scalar op needs one scalar per limb");
+        // small per-call constant block; lives in the scratch-independent misc area of the stream order
+        u64 *tmp = nullptr;
+        CUDA_TRY(cudaMallocAsync(&tmp, sizeof(u64) * (level + 1), ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(tmp, scalars, sizeof(u64) * (level + 1), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));   // `scalars` is a pageable Go/host slice
+        d_sc = tmp;
+    }
+    int rc = launch_vec_op(ctx, op, p1->d, p2 ? p2->d : nullptr, p3->d, Span{batch, level + 1, ctx->L, 0}, d_sc);
+    if (d_sc) cudaFreeAsync((void *)d_sc, ctx->stream);
+    return rc;
+}
+
+extern "C" int b200_polymul(b200_ctx *ctx, const b200_poly *a, const b200_poly *b, b200_poly *c, int level) {
+    int batch;
+    if (int rc = check_polys(ctx, level, "b200_polymul", {a, b, c}, &batch)) return rc;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    Span sp{batch, level + 1, ctx->L, 0};
+    int rc = launch_polymul_big(ctx, a->d, b->d, c->d, sp);
+    if (rc != 1) return rc;
+    // generic composition: NTT(a), NTT(b) in tree order -> Barrett product (== MRed(MForm(a^), b^), canonical,
+    // ring/ring_test.go:106-110) -> INTT.  Two scratch polynomials.
+    const size_t words = (size_t)batch * ctx->L * ctx->N;
+    if (int r = b200_ensure_scratch(ctx, 2 * words)) return r;
+    u64 *ta = ctx->d_scratch, *tb = ctx->d_scratch + words;
+    const int tf = ctx->ring_type == B200_RING_MATRIX ? B200_TREE_ORDER : 0;
+    auto ntt = [&](const u64 *src, u64 *dst, bool inv) {
+        int r = launch_ntt_big(ctx, src, dst, sp, inv, tf);
+        if (r == 1) r = launch_ntt_generic(ctx, src, dst, sp, inv, tf);
+        return r;
+    };
+    if ((rc = ntt(a->d, ta, false))) return rc;
+    if ((rc = ntt(b->d, tb, false))) return rc;
+    if ((rc = launch_vec_op(ctx, B200_OP_MUL_BARRETT, ta, tb, ta, sp, nullptr))) return rc;
+    return ntt(ta, c->d, true);
+}
+
+extern "C" int b200_subring_ntt_host(b200_ctx *ctx, int limb, const uint64_t *p1, uint64_t *p2, size_t n, int inverse, int flags) {
+    if (!ctx || !p1 || !p2) return fail(B200_EINVAL, "b200_subring_ntt_host: NULL argument");
+    if (limb < 0 || limb >= ctx->L) return fail(B200_ESHAPE, "b200_subring_ntt_host: limb out of range");
+    if (n < (size_t)ctx->N)   // ring/ntt.go:211-214, ntt_3n.go:85-87
+        return fail(B200_ESHAPE, "cannot NTT: ensure that len(p1), len(p2)=" + std::to_string(n) + " >= N=" + std::to_string(ctx->N));
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    u64 *d = nullptr;
+    CUDA_TRY(cudaMallocAsync(&d, sizeof(u64) * ctx->N, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(d, p1, sizeof(u64) * ctx->N, cudaMemcpyHostToDevice, ctx->stream));
+    Span sp{1, 1, 1, limb};
+    int rc = launch_ntt_big(ctx, d, d, sp, inverse != 0, flags);
+    if (rc == 1) rc = launch_ntt_generic(ctx, d, d, sp, inverse != 0, flags);
+    if (rc == 0) {
+        cudaError_t e = cudaMemcpyAsync(p2, d, sizeof(u64) * ctx->N, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = b200_cuda_fail(e, "b200_subring_ntt_host download");
+    }
+    cudaFreeAsync(d, ctx->stream);
+    return rc;
+}

@@ -1,0 +1,76 @@
+// internal.hpp -- structures shared by the C-ABI layer and the kernel launchers.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/b200ring.h"
+#include "modarith.cuh"
+
+// {w, ws}: a constant and its Shoup companion floor(w*2^64/q); one 128-bit load.
+typedef ulonglong2 tw_t;
+
+// host copy of one prime's constants (ring.SubRing + NTTTable, subring.go:35-55, ntt.go:38-44)
+struct SubRingHost {
+    u64 q = 0, qinv = 0, brc[2] = {0, 0}, mask = 0;
+    u64 g = 0;        // SubRing.PrimitiveRoot (smallest primitive root >= 3, or caller supplied)
+    u64 ninv = 0;     // NTTTable.NInv, Montgomery form (STANDARD)
+    u64 root = 0;     // psi = g^((q-1)/2N) (STANDARD) or omega (MATRIX), plain domain
+    std::vector<u64> roots_fwd, roots_bwd;   // Go-format tables (STANDARD): Montgomery, bit-reversed
+};
+
+// indices into the per-limb misc constant block (MATRIX rings)
+enum { MISC_OMEGA3 = 0, MISC_K1 = 1, MISC_K2 = 2, MISC_ZETA = 3, MISC_NINV = 4, MISC_NINV_W1 = 5, MISC_COUNT = 8 };
+
+struct b200_ctx {
+    int ring_type = 0, N = 0, L = 0, device = 0;
+    int logN = 0;          // STANDARD: log2 N
+    int a = 0, b = 0;      // MATRIX: N = 2^a 3^b
+    cudaStream_t stream = nullptr;
+    int max_smem_optin = 0, sm_count = 0;
+    std::vector<SubRingHost> sub;
+    LimbConst *d_consts = nullptr;   // [L]
+    tw_t *d_fwd = nullptr;           // [L][N] forward twiddles (STANDARD: psi^brev(k); MATRIX: zetas)
+    tw_t *d_inv = nullptr;           // [L][N] their inverses
+    tw_t *d_misc = nullptr;          // [L][MISC_COUNT]
+    int *d_go2fast = nullptr;        // [N] MATRIX: reference slot k -> tree slot i
+    u64 *d_scratch = nullptr;        // grown on demand (generic large-N path, polymul temporaries)
+    size_t scratch_words = 0;
+    std::atomic<uint64_t> launches{0};
+    // optimised-path tables (ntt_big.cu); null when the ring shape is not covered
+    void *big = nullptr;
+};
+
+struct b200_poly {
+    b200_ctx *ctx = nullptr;
+    u64 *d = nullptr;
+    int batch = 0;
+    bool owned = false;
+};
+
+void b200_set_error(const std::string &msg);
+int b200_cuda_fail(cudaError_t e, const char *what);
+#define CUDA_TRY(expr)                                                    \
+    do {                                                                  \
+        cudaError_t _e = (expr);                                          \
+        if (_e != cudaSuccess) return b200_cuda_fail(_e, #expr);          \
+    } while (0)
+
+int b200_ensure_scratch(b200_ctx *ctx, size_t words);
+
+// kernel launchers (each returns 0 or a negative code; all enqueue on ctx->stream)
+// A launch covers `batch` polynomials x limbs [limb0, limb0+nl) of the ring; the buffers are laid out
+// [batch][Lbuf][N] and buffer limb j (j < nl) uses the ring's prime limb0 + j.
+struct Span {
+    int batch, nl, Lbuf, limb0;
+};
+int launch_vec_op(b200_ctx *ctx, int op, const u64 *p1, const u64 *p2, u64 *p3, Span sp, const u64 *d_scalars);
+int launch_ntt_generic(b200_ctx *ctx, const u64 *in, u64 *out, Span sp, bool inverse, int flags);
+// optimised two-pass path; returns 1 if the shape is not covered (caller falls back to generic)
+int big_tables_create(b200_ctx *ctx);
+void big_tables_destroy(b200_ctx *ctx);
+int launch_ntt_big(b200_ctx *ctx, const u64 *in, u64 *out, Span sp, bool inverse, int flags);
+int launch_polymul_big(b200_ctx *ctx, const u64 *a, const u64 *b, u64 *c, Span sp);

@@ -1,0 +1,329 @@
+"""Host-side mirror of the reference's `ring` package surface for the hot path, over the C ABI.
+
+Same names, argument meaning and error behaviour as the Go code so that tests read like the
+reference's own (ring/ring.go, ring/operations.go, ring/ntt.go, ring/poly.go, ring/subring_ops.go):
+constructors raise ValueError where Go returns an `error`; hot functions raise B200Error(ESHAPE)
+where Go panics.  A Poly here is a *batch* of device-resident polynomials ([batch][L][N] uint64);
+batch=1 is exactly a ring.Poly.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import B200Error, check, lib
+
+
+class Type(int):
+    """ring.Type (ring/ring.go:27-34)."""
+
+    def __str__(self):
+        return {0: "Standard", 1: "ConjugateInvariant", 2: "Matrix"}.get(int(self), "Invalid")
+
+
+Standard, ConjugateInvariant, Matrix = Type(0), Type(1), Type(2)
+
+_OPS = {
+    "Add": 0, "AddLazy": 1, "Sub": 2, "SubLazy": 3, "Neg": 4, "Reduce": 5, "ReduceLazy": 6,
+    "MForm": 7, "MFormLazy": 8, "IMForm": 9,
+    "MulCoeffsBarrett": 16, "MulCoeffsBarrettLazy": 17, "MulCoeffsBarrettThenAdd": 18,
+    "MulCoeffsBarrettThenAddLazy": 19,
+    "MulCoeffsMontgomery": 32, "MulCoeffsMontgomeryLazy": 33, "MulCoeffsMontgomeryThenAdd": 34,
+    "MulCoeffsMontgomeryThenAddLazy": 35, "MulCoeffsMontgomeryLazyThenAddLazy": 36,
+    "MulCoeffsMontgomeryThenSub": 37, "MulCoeffsMontgomeryThenSubLazy": 38,
+    "MulCoeffsMontgomeryLazyThenSubLazy": 39, "MulCoeffsMontgomeryLazyThenNeg": 40,
+}
+_UNARY = {"Neg", "Reduce", "ReduceLazy", "MForm", "MFormLazy", "IMForm"}
+_SCALAR_OPS = {"MulScalarMontgomery": 48, "MulScalarMontgomeryLazy": 49, "MulScalarMontgomeryThenAdd": 50,
+               "AddScalar": 51, "SubScalar": 52}
+
+
+def _is_valid_ring_degree_for_3n(N):   # ring/subring.go:14-30
+    if N <= 0:
+        return False
+    t = 3 * N
+    while t % 3 == 0:
+        t //= 3
+    return t > 0 and (t & (t - 1)) == 0
+
+
+def _u64_array(x):
+    return np.ascontiguousarray(np.asarray(x, dtype=np.uint64))
+
+
+class _Context:
+    """Owns one b200_ctx (shared by a Ring and its AtLevel views)."""
+
+    def __init__(self, ring_type, N, moduli, roots, device):
+        self.h = C.c_void_p()
+        q = (C.c_uint64 * max(len(moduli), 1))(*moduli)
+        r = (C.c_uint64 * len(moduli))(*roots) if roots is not None else None
+        rc = lib().b200_ctx_create(int(ring_type), N, len(moduli), q, r, device, C.byref(self.h))
+        if rc == -1:
+            raise ValueError(lib().b200_last_error().decode())   # the Go constructor's `error`
+        check(rc)
+
+    def __del__(self):
+        if getattr(self, "h", None) and capi._lib is not None:
+            capi._lib.b200_ctx_destroy(self.h)
+            self.h = None
+
+
+class SubRing:
+    """ring.SubRing (ring/subring.go:35-55): per-prime constants + the plugin-granularity transforms."""
+
+    def __init__(self, ring, index):
+        self._ring, self._i = ring, index
+        out = (C.c_uint64 * 8)()
+        check(lib().b200_ctx_subring(ring._ctx.h, index, out))
+        self.N = ring.N()
+        self.Modulus, self.MRedConstant = int(out[0]), int(out[1])
+        self.BRedConstant = (int(out[2]), int(out[3]))
+        self.Mask, self.PrimitiveRoot, self.NInv, self.Root = int(out[4]), int(out[5]), int(out[6]), int(out[7])
+
+    def _roots(self, inverse):
+        out = np.empty(self.N, dtype=np.uint64)
+        check(lib().b200_ctx_roots(self._ring._ctx.h, self._i, inverse, out.ctypes.data_as(capi.P64), self.N))
+        return out
+
+    @property
+    def RootsForward(self):
+        return self._roots(0)
+
+    @property
+    def RootsBackward(self):
+        return self._roots(1)
+
+    def _host(self, p1, p2, inverse, flags):
+        a = _u64_array(p1)
+        out = p2 if (isinstance(p2, np.ndarray) and p2.dtype == np.uint64 and p2.flags["C_CONTIGUOUS"]) else np.empty(max(len(a), 0), dtype=np.uint64)
+        n = min(len(a), len(out))
+        check(lib().b200_subring_ntt_host(self._ring._ctx.h, self._i, a.ctypes.data_as(capi.P64),
+                                          out.ctypes.data_as(capi.P64), n, inverse, flags))
+        return out
+
+    # NumberTheoreticTransformer (ring/ntt.go:15-22) on host slices
+    def NTT(self, p1, p2=None):
+        return self._host(p1, p2, 0, 0)
+
+    def NTTLazy(self, p1, p2=None):
+        return self._host(p1, p2, 0, capi.B200_LAZY)
+
+    def INTT(self, p1, p2=None):
+        return self._host(p1, p2, 1, 0)
+
+    def INTTLazy(self, p1, p2=None):
+        return self._host(p1, p2, 1, capi.B200_LAZY)
+
+
+class Poly:
+    """ring.Poly (ring/poly.go:13-24), device resident and batched: [batch][L][N] uint64."""
+
+    def __init__(self, ring, batch=1, _wrap=None, _keep=None):
+        self.ring, self.batch = ring, batch
+        self.h = C.c_void_p()
+        self._keep = _keep   # keeps a wrapped torch tensor alive
+        if _wrap is None:
+            check(lib().b200_poly_alloc(ring._ctx.h, batch, C.byref(self.h)))
+        else:
+            check(lib().b200_poly_wrap(ring._ctx.h, C.c_void_p(_wrap), batch, C.byref(self.h)))
+
+    @classmethod
+    def from_torch(cls, ring, tensor):
+        """Wrap a CUDA int64/uint64 torch tensor of shape [batch, L, N] without copying."""
+        L, N = ring.ModuliChainLength(), ring.N()
+        assert tensor.is_cuda and tensor.is_contiguous() and tensor.element_size() == 8
+        assert tuple(tensor.shape[-2:]) == (L, N), (tuple(tensor.shape), L, N)
+        batch = tensor.numel() // (L * N)
+        return cls(ring, batch, _wrap=tensor.data_ptr(), _keep=tensor)
+
+    def shape(self):
+        return (self.batch, self.ring.ModuliChainLength(), self.ring.N())
+
+    def N(self):
+        return self.ring.N()
+
+    def Level(self):
+        return self.ring.MaxLevel()
+
+    def set(self, host):
+        """Upload a [batch][L][N] (or [L][N] when batch == 1) host array."""
+        a = _u64_array(host).reshape(self.shape())
+        check(lib().b200_poly_upload(self.h, a.ctypes.data_as(C.c_void_p), a.size))
+        check(lib().b200_sync(self.ring._ctx.h))
+        return self
+
+    def get(self):
+        out = np.empty(self.shape(), dtype=np.uint64)
+        check(lib().b200_poly_download(self.h, out.ctypes.data_as(C.c_void_p), out.size))
+        return out
+
+    @property
+    def Coeffs(self):
+        """Host copy of the limbs: [L][N] for batch 1 (like Poly.Coeffs), else [batch][L][N]."""
+        a = self.get()
+        return a[0] if self.batch == 1 else a
+
+    def set_limb(self, b, limb, host):
+        a = _u64_array(host)
+        check(lib().b200_poly_upload_limb(self.h, b, limb, a.ctypes.data_as(capi.P64), len(a)))
+
+    def get_limb(self, b, limb, n=None):
+        out = np.empty(self.ring.N() if n is None else n, dtype=np.uint64)
+        check(lib().b200_poly_download_limb(self.h, b, limb, out.ctypes.data_as(capi.P64), len(out)))
+        return out
+
+    def Copy(self, other):
+        self.set(other.get() if isinstance(other, Poly) else other)
+
+    def CopyNew(self):
+        return Poly(self.ring, self.batch).set(self.get())
+
+    def Equal(self, other):
+        return bool((self.get() == other.get()).all())
+
+    def __del__(self):
+        if getattr(self, "h", None) and capi._lib is not None:
+            capi._lib.b200_poly_free(self.h)
+            self.h = None
+
+
+class Ring:
+    """ring.Ring (ring/ring.go:76-89) on one GPU."""
+
+    def __init__(self, ctx, ring_type, N, moduli, level, device):
+        self._ctx, self._type, self._N, self._moduli, self.level, self.device = ctx, ring_type, N, list(moduli), level, device
+        self.SubRings = [SubRing(self, i) for i in range(len(moduli))]
+
+    # -- accessors (ring/ring.go) --
+    def N(self):
+        return self._N
+
+    def NthRoot(self):
+        return (3 if self._type == Matrix else 2) * self._N
+
+    def Type(self):
+        return self._type
+
+    def Is3N(self):   # ring/ring.go:353 quirk: true for powers of two as well
+        return _is_valid_ring_degree_for_3n(self._N)
+
+    def Level(self):
+        return self.level
+
+    def MaxLevel(self):
+        return len(self._moduli) - 1
+
+    def ModuliChain(self):
+        return list(self._moduli)
+
+    def ModuliChainLength(self):
+        return len(self._moduli)
+
+    def AtLevel(self, level):   # ring/ring.go:194-213 (panics -> B200Error)
+        if level < 0:
+            raise B200Error(-4, "level cannot be negative")
+        if level > self.MaxLevel():
+            raise B200Error(-4, "level cannot be larger than max level")
+        r = Ring.__new__(Ring)
+        r.__dict__.update(self.__dict__)
+        r.level = level
+        return r
+
+    def NewPoly(self, batch=1):
+        return Poly(self, batch)
+
+    def SetStream(self, cuda_stream):
+        """Enqueue on this cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream)."""
+        check(lib().b200_ctx_set_stream(self._ctx.h, C.c_void_p(cuda_stream)))
+
+    def Sync(self):
+        check(lib().b200_sync(self._ctx.h))
+
+    def LaunchCount(self):
+        return int(lib().b200_ctx_launch_count(self._ctx.h))
+
+    # -- transforms (ring/ntt.go:127-152) --
+    def NTT(self, p1, p2, tree_order=False):
+        check(lib().b200_ntt(self._ctx.h, p1.h, p2.h, self.level, capi.B200_TREE_ORDER if tree_order else 0))
+
+    def NTTLazy(self, p1, p2, tree_order=False):
+        check(lib().b200_ntt(self._ctx.h, p1.h, p2.h, self.level, capi.B200_LAZY | (capi.B200_TREE_ORDER if tree_order else 0)))
+
+    def INTT(self, p1, p2, tree_order=False):
+        check(lib().b200_intt(self._ctx.h, p1.h, p2.h, self.level, capi.B200_TREE_ORDER if tree_order else 0))
+
+    def INTTLazy(self, p1, p2, tree_order=False):
+        check(lib().b200_intt(self._ctx.h, p1.h, p2.h, self.level, capi.B200_LAZY | (capi.B200_TREE_ORDER if tree_order else 0)))
+
+    # -- fused ring product (BASELINE config 4) --
+    def MulPoly(self, p1, p2, p3):
+        """p3 = p1 * p2 in the ring (NTT, NTT, MForm, MulCoeffsMontgomery, INTT fused on device)."""
+        check(lib().b200_polymul(self._ctx.h, p1.h, p2.h, p3.h, self.level))
+
+    def _vec(self, op, p1, p2, p3, scalars=None):
+        sc = None
+        if scalars is not None:
+            vals = [int(s) for s in scalars]
+            if len(vals) < self.level + 1:
+                raise B200Error(-4, "need one scalar per limb")
+            sc = (C.c_uint64 * (self.level + 1))(*vals[: self.level + 1])
+        check(lib().b200_vec_op(self._ctx.h, op, p1.h, p2.h if p2 is not None else None, p3.h, self.level, sc))
+
+    def Equal(self, p1, p2):   # ring/ring.go:546-558: reduces both sides, then compares limbs 0..level
+        a, b = self.NewPoly(p1.batch), self.NewPoly(p2.batch)
+        self.Reduce(p1, a)
+        self.Reduce(p2, b)
+        return bool((a.get()[:, : self.level + 1] == b.get()[:, : self.level + 1]).all())
+
+
+def _mk_binary(name, code):
+    def f(self, p1, p2, p3):
+        self._vec(code, p1, p2, p3)
+    f.__name__ = name
+    f.__doc__ = "Ring.%s(p1, p2, p3) -- ring/operations.go" % name
+    return f
+
+
+def _mk_unary(name, code):
+    def f(self, p1, p2):
+        self._vec(code, p1, None, p2)
+    f.__name__ = name
+    f.__doc__ = "Ring.%s(p1, p2) -- ring/operations.go" % name
+    return f
+
+
+def _mk_scalar(name, code):
+    def f(self, p1, scalars, p2):
+        self._vec(code, p1, None, p2, scalars)
+    f.__name__ = name
+    f.__doc__ = "per-limb SubRing.%s(p1, scalar_i, p2) -- ring/subring_ops.go" % name
+    return f
+
+
+for _n, _c in _OPS.items():
+    setattr(Ring, _n, _mk_unary(_n, _c) if _n in _UNARY else _mk_binary(_n, _c))
+for _n, _c in _SCALAR_OPS.items():
+    setattr(Ring, _n, _mk_scalar(_n, _c))
+
+
+def NewRingFromType(N, Moduli, ringType, device=0, roots=None):
+    """ring.NewRingFromType (ring/ring.go:291-308).  `roots`: see b200_ctx_create."""
+    ringType = Type(ringType)
+    if ringType == ConjugateInvariant:
+        raise ValueError("ConjugateInvariant rings are outside the B200 hot path (SURVEY.md section 2)")
+    if ringType not in (Standard, Matrix):
+        raise ValueError("invalid ring type")
+    moduli = [int(q) for q in Moduli]
+    ctx = _Context(ringType, N, moduli, roots, device)
+    return Ring(ctx, ringType, N, moduli, len(moduli) - 1, device)
+
+
+def NewRing(N, Moduli, device=0, roots=None):
+    """ring.NewRing (ring/ring.go:264-272): 3N transformer iff N % 3 == 0 and 3N = 2^a 3^(b+1)."""
+    is3n = N % 3 == 0 and _is_valid_ring_degree_for_3n(N)
+    return NewRingFromType(N, Moduli, Matrix if is3n else Standard, device, roots)
+
+
+def NewPoly(ring, batch=1):
+    return Poly(ring, batch)

@@ -1,0 +1,66 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library loads, exports every symbol the header
+declares, and the constructors validate exactly like ring.NewRing (ring/ring.go:314-356,
+ring/subring.go:129-146; cases of ring/ring_test.go:128-167).  No compute calls."""
+import os
+import re
+
+import pytest
+
+from conftest import ROOT, QI60
+import b200ring
+from b200ring import capi
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "b200ring.h")).read()
+    declared = set(re.findall(r"^B200_API [^;(]*?\b(b200_\w+)\(", hdr, re.M))
+    assert len(declared) >= 25
+    assert declared == set(capi.SYMBOLS), declared ^ set(capi.SYMBOLS)
+    L = capi.load_library()           # binds every symbol or raises AttributeError
+    for name in declared:
+        assert getattr(L, name) is not None
+    assert b"sm_100a" in L.b200_version()
+
+
+def test_header_cites_reference_for_every_entry_point():
+    hdr = open(os.path.join(ROOT, "include", "b200ring.h")).read()
+    for needle in ("ring/ring.go:264-356", "ring/ntt.go:127-138", "ring/ntt.go:15-22", "ring/poly.go", "ring/operations.go"):
+        assert needle in hdr
+
+
+@pytest.mark.parametrize("N,moduli,msg", [
+    (15, [QI60[0]], "invalid ring degree"),
+    (4, [QI60[0]], "invalid ring degree"),
+    (16, [], "invalid ModuliChain (must be a non-empty []uint64)"),
+    (16, [QI60[0], QI60[0]], "moduli are not distinct"),
+    (16, [QI60[0] + 2], "is not prime"),
+    (1 << 21, [QI60[0]], "!= 1 mod NthRoot"),
+    (24, [QI60[0]], "!= 1 mod NthRoot"),            # 3N ring needs q = 1 mod 72
+])
+def test_constructor_errors_like_reference(N, moduli, msg):
+    with pytest.raises(ValueError) as e:
+        b200ring.NewRing(N, moduli)
+    assert msg in str(e.value)
+
+
+def test_matrix_type_rejects_power_of_two_degree():
+    with pytest.raises(ValueError) as e:
+        b200ring.NewRingFromType(16, [QI60[0]], b200ring.Matrix)   # ring.go:301-303
+    assert "matrix ring type requires" in str(e.value)
+
+
+def test_no_cpu_fallback_without_device():
+    if capi.lib().b200_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(b200ring.B200Error) as e:
+        b200ring.NewRing(16, [576460752303439873])
+    assert e.value.code == capi.ENODEVICE and "no CPU fallback" in str(e.value)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "matrix-fhe-lattigo_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.replace("no oracle", ""), os.path.join(dirpath, f)

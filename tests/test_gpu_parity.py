@@ -1,0 +1,349 @@
+"""GPU parity tests: every call goes through the C ABI (b200ring -> libb200ring.so) and is compared
+bit-for-bit with the CPU oracle on the same seeded inputs, with the committed golden vectors, and --
+at BASELINE's full sizes -- through size-independent properties (round trip, product, linearity,
+spot evaluation by Horner).  Mirrors ring/ntt_test.go, ring/ntt_3n_test.go, ring/ring_test.go."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, QI60
+import b200ring
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+C3_PRIMES = [0x1000000000248001, 0x1000000000b00001, 0x1000000000cf8001, 0x1000000000ef0001,
+             0x1000000001568001, 0x10000000019a0001, 0x1000000001be0001, 0x1000000001cb8001,
+             0x1000000001eb0001, 0x10000000026d8001, 0x1000000002720001, 0x1000000002888001,
+             0x1000000002c30001, 0x1000000002c78001, 0x1000000002eb8001, 0x10000000030b0001,
+             0x1000000003260001, 0x1000000003530001, 0x1000000003650001, 0x1000000003698001,
+             0x1000000003e30001, 0x1000000003e78001, 0x1000000003ec0001, 0x10000000042b0001]
+
+
+def rand_poly(seed, batch, moduli, N):
+    out = np.empty((batch, len(moduli), N), dtype=np.uint64)
+    for b in range(batch):
+        for l, q in enumerate(moduli):
+            out[b, l] = O.fill_uniform(seed, b, l, q, N)
+    return out
+
+
+# ---------------------------------------------------------------- power-of-two ring
+def test_kat_ntt_test_go():
+    """ring/ntt_test.go:91-119 on the GPU: NTT(poly) == polyNTT and INTT(NTT(x)) == x, both limbs."""
+    kat = json.load(open(os.path.join(GOLDEN, "ntt_kat.json")))["vectors"]
+    for v in kat:
+        r = b200ring.NewRing(v["N"], v["Qis"])
+        assert r.Type() == b200ring.Standard
+        x, y, z = r.NewPoly(), r.NewPoly(), r.NewPoly()
+        x.set(np.array(v["poly"], dtype=np.uint64))
+        y.set(np.array(v["polyNTT"], dtype=np.uint64))
+        r.NTT(x, z)
+        assert r.Equal(z, y), "transformed poly and polyNTT should match"
+        assert (z.get() == y.get()).all()
+        r.INTT(z, z)
+        assert r.Equal(z, x), "invNTT should reverse NTT"
+        assert (z.get() == x.get()).all()
+
+
+def test_standard_tables_bit_identical_to_subring_go():
+    for N in (16, 1024):
+        r = b200ring.NewRing(N, [576460752303439873, 576460752303702017][: 2 if N == 16 else 1] if N == 16 else QI60[:2])
+        for i, q in enumerate(r.ModuliChain()):
+            s = O.Pow2SubRing(N, q)
+            sr = r.SubRings[i]
+            assert (sr.Modulus, sr.MRedConstant, sr.BRedConstant, sr.PrimitiveRoot, sr.NInv) == \
+                   (q, s.MRedConstant, s.BRedConstant, s.PrimitiveRoot, s.NInv)
+            rf, rb = s.tables()
+            assert (sr.RootsForward == rf).all() and (sr.RootsBackward == rb).all()
+            assert sr.Mask == (1 << (q - 1).bit_length()) - 1
+
+
+@pytest.mark.parametrize("logN", [3, 4, 7, 10, 12, 13, 14, 15, 16, 17])
+def test_standard_ntt_matches_oracle(logN):
+    N = 1 << logN
+    moduli = QI60[:3]
+    batch = 2
+    r = b200ring.NewRing(N, moduli)
+    host = rand_poly(0xB2000002, batch, moduli, N)
+    p, o = r.NewPoly(batch).set(host), r.NewPoly(batch)
+    r.NTT(p, o)
+    got = o.get()
+    subs = [O.Pow2SubRing(N, q) for q in moduli]
+    for b in range(batch):
+        for l in range(len(moduli)):
+            assert (got[b, l] == subs[l].NTT(host[b, l])).all(), (logN, b, l)
+    r.NTTLazy(p, o)
+    lazy = o.get()
+    for l, q in enumerate(moduli):
+        assert (lazy[:, l] % np.uint64(q) == got[:, l]).all() and int(lazy[:, l].max()) <= 6 * q - 2
+    r.INTT(o, o)                       # in place, from lazy input < 4q?  no: INTT wants < 2q -> use canonical
+    o.set(got)
+    r.INTT(o, o)
+    assert (o.get() == host).all()
+    o.set(got)
+    r.INTTLazy(o, o)
+    lz = o.get()
+    for l, q in enumerate(moduli):
+        assert (lz[:, l] % np.uint64(q) == host[:, l]).all() and int(lz[:, l].max()) <= 2 * q - 1
+    # AtLevel: only limbs 0..level are touched (ring/ntt.go:128)
+    o.set(host)
+    r.AtLevel(0).NTT(o, o)
+    after = o.get()
+    assert (after[:, 0] == got[:, 0]).all() and (after[:, 1:] == host[:, 1:]).all()
+
+
+def test_standard_polymul_pipeline_vs_schoolbook():
+    """NTT -> MForm -> MulCoeffsMontgomery -> INTT (ring/ring_test.go:106-110) == negacyclic schoolbook."""
+    N, moduli = 256, QI60[:2]
+    r = b200ring.NewRing(N, moduli)
+    ha, hb = rand_poly(21, 1, moduli, N), rand_poly(22, 1, moduli, N)
+    a, b, c = r.NewPoly().set(ha), r.NewPoly().set(hb), r.NewPoly()
+    r.NTT(a, a); r.NTT(b, b)
+    r.MForm(a, a)
+    r.MulCoeffsMontgomery(a, b, c)
+    r.INTT(c, c)
+    want = np.stack([O.schoolbook_negacyclic(N, q, ha[0, l], hb[0, l]) for l, q in enumerate(moduli)])
+    assert (c.get()[0] == want).all()
+    a.set(ha); b.set(hb)
+    r.MulPoly(a, b, c)
+    assert (c.get()[0] == want).all()
+
+
+# ---------------------------------------------------------------- element-wise family
+ALL_BINARY = ["Add", "AddLazy", "Sub", "SubLazy", "MulCoeffsBarrett", "MulCoeffsBarrettLazy",
+              "MulCoeffsBarrettThenAdd", "MulCoeffsBarrettThenAddLazy", "MulCoeffsMontgomery",
+              "MulCoeffsMontgomeryLazy", "MulCoeffsMontgomeryThenAdd", "MulCoeffsMontgomeryThenAddLazy",
+              "MulCoeffsMontgomeryLazyThenAddLazy", "MulCoeffsMontgomeryThenSub", "MulCoeffsMontgomeryThenSubLazy",
+              "MulCoeffsMontgomeryLazyThenSubLazy", "MulCoeffsMontgomeryLazyThenNeg"]
+ALL_UNARY = ["Neg", "Reduce", "ReduceLazy", "MForm", "MFormLazy", "IMForm"]
+ALL_SCALAR = ["MulScalarMontgomery", "MulScalarMontgomeryLazy", "MulScalarMontgomeryThenAdd", "AddScalar", "SubScalar"]
+
+
+@pytest.mark.parametrize("N", [16, 24, 3 * 2**10])
+def test_vec_ops_bit_exact(N):
+    is3n = N % 3 == 0
+    moduli = O.find_3n_rns_primes(N, 60, 3) if is3n else QI60[18:21]
+    r = b200ring.NewRing(N, moduli)
+    batch = 2
+    h1, h2, h3 = (rand_poly(s, batch, moduli, N) for s in (31, 32, 33))
+    # edge values of ring/ring_test.go:534-670 in the first slots
+    for l, q in enumerate(moduli):
+        h1[0, l, :3] = [1, q - 1, 0]
+        h2[0, l, :3] = [q - 1, q - 1, 1]
+    p1, p2 = r.NewPoly(batch).set(h1), r.NewPoly(batch).set(h2)
+    for name in ALL_BINARY:
+        p3 = r.NewPoly(batch).set(h3)
+        getattr(r, name)(p1, p2, p3)
+        got = p3.get()
+        for b in range(batch):
+            for l, q in enumerate(moduli):
+                assert (got[b, l] == O.vec_op(name, q, h1[b, l], h2[b, l], h3[b, l])).all(), (name, b, l)
+    big = h1.copy(); big[..., ::2] = np.uint64(2**64 - 1) - big[..., ::2]    # arbitrary 64-bit inputs for Reduce
+    for name in ALL_UNARY:
+        src = big if name.startswith("Reduce") else h1
+        p, o = r.NewPoly(batch).set(src), r.NewPoly(batch)
+        getattr(r, name)(p, o)
+        got = o.get()
+        for b in range(batch):
+            for l, q in enumerate(moduli):
+                assert (got[b, l] == O.vec_op(name, q, src[b, l])).all(), (name, b, l)
+    scal = [12345678901234567 % q for q in moduli]
+    for name in ALL_SCALAR:
+        p3 = r.NewPoly(batch).set(h3)
+        getattr(r, name)(p1, scal, p3)
+        got = p3.get()
+        for b in range(batch):
+            for l, q in enumerate(moduli):
+                assert (got[b, l] == O.vec_op(name, q, h1[b, l], None, h3[b, l], scalar=scal[l])).all(), (name, b, l)
+    # in place: p1 = p1 * p2
+    r.MulCoeffsMontgomery(p1, p2, p1)
+    got = p1.get()
+    for l, q in enumerate(moduli):
+        assert (got[1, l] == O.vec_op("MulCoeffsMontgomery", q, h1[1, l], h2[1, l])).all()
+
+
+# ---------------------------------------------------------------- 3N (Matrix) ring
+def test_3n_prototype_vectors_on_gpu():
+    vec = json.load(open(os.path.join(GOLDEN, "ntt3n_proto.json")))["vectors"]
+    for v in vec:
+        N = v["N"]
+        if N < 8:
+            continue                       # ring constructors need N >= 8 (ring/ring.go:20-23)
+        r = b200ring.NewRing(N, [v["p"]], roots=[v["w"]])
+        assert r.Type() == b200ring.Matrix
+        x, y = r.NewPoly().set(np.array([[v["coeffs"]]], dtype=np.uint64)), r.NewPoly()
+        r.NTT(x, y, tree_order=True)
+        assert [int(t) for t in y.get()[0, 0]] == v["ntt_tree_order"]
+        r.INTT(y, y, tree_order=True)
+        assert (y.get() == x.get()).all()
+        r.NTT(x, y)
+        assert [int(t) for t in y.get()[0, 0]] == O.py_3n_ntt(N, v["p"], v["w"], v["coeffs"])
+
+
+@pytest.mark.parametrize("N", [12, 18, 24, 36, 48, 96, 192, 3 * 2**7, 9 * 2**6, 3 * 2**12, 3 * 2**13, 27 * 2**10])
+def test_3n_matches_oracle_roundtrip_product(N):
+    moduli = O.find_3n_rns_primes(N, 60, 2)
+    batch = 2
+    r = b200ring.NewRing(N, moduli)               # deterministic omega (subring.go:255-290)
+    subs = [O.ThreeNSubRing(N, q) for q in moduli]
+    for s, sr in zip(subs, r.SubRings):
+        assert s.omega == sr.Root
+    host = rand_poly(0xB2000001, batch, moduli, N)
+    p, o = r.NewPoly(batch).set(host), r.NewPoly(batch)
+    r.NTT(p, o)
+    got = o.get()
+    for b in range(batch):
+        for l in range(len(moduli)):
+            assert (got[b, l] == subs[l].NTT(host[b, l])).all(), (N, b, l)
+    if N <= 192:
+        assert (got[0, 0] == subs[0].NTT_horner(host[0, 0])).all()       # ntt_3n.go:99-108
+    r.INTT(o, o)
+    assert (o.get() == host).all()                                       # ntt_3n_test.go:139-222
+    z = r.NewPoly(batch).set(host)
+    for _ in range(8):
+        r.NTT(z, z); r.INTT(z, z)
+    assert (z.get() == host).all()
+    zero, one = np.zeros((batch, len(moduli), N), dtype=np.uint64), np.zeros((batch, len(moduli), N), dtype=np.uint64)
+    one[..., 0] = 1
+    r.NTT(z.set(zero), z); assert (z.get() == 0).all()
+    r.NTT(z.set(one), z); assert (z.get() == 1).all()
+    # product == schoolbook mod X^N - X^(N/2) + 1 (ntt_3n_test.go:455-554)
+    if N <= 3 * 2**7:
+        ha, hb = rand_poly(41, batch, moduli, N), rand_poly(42, batch, moduli, N)
+        a, b, c = r.NewPoly(batch).set(ha), r.NewPoly(batch).set(hb), r.NewPoly(batch)
+        r.MulPoly(a, b, c)
+        got = c.get()
+        for bi in range(batch):
+            for l, q in enumerate(moduli):
+                assert (got[bi, l] == O.schoolbook_3n(N, q, ha[bi, l], hb[bi, l])).all()
+        r.NTT(a, a); r.NTT(b, b); r.MForm(a, a); r.MulCoeffsMontgomery(a, b, c); r.INTT(c, c)
+        assert (c.get() == got).all()
+
+
+def test_3n_random_omega_from_go_side():
+    """the Go transformer draws omega at random; the bridge passes it and slots must follow it."""
+    N = 48
+    q = O.find_3n_rns_primes(N, 60, 1)[0]
+    g = O.lib().ref_primitive_root(q)
+    omega = pow(g, 5 * (q - 1) // (3 * N), q)      # another primitive 3N-th root (5 is coprime to 144)
+    r = b200ring.NewRing(N, [q], roots=[omega])
+    x = rand_poly(5, 1, [q], N)
+    y = r.NewPoly()
+    r.NTT(r.NewPoly().set(x), y)
+    assert [int(t) for t in y.get()[0, 0]] == O.py_3n_ntt(N, q, omega, x[0, 0])
+    with pytest.raises(ValueError):
+        b200ring.NewRing(N, [q], roots=[pow(omega, 2, q)])   # order 3N/2: not primitive
+
+
+def test_plugin_granularity_host_slices():
+    """ring.NumberTheoreticTransformer (ring/ntt.go:15-22): per-limb host slices, in place allowed."""
+    N = 64
+    r = b200ring.NewRing(N, [576460752303439873, 576460752303702017])
+    x = O.fill_uniform(9, 0, 1, 576460752303702017, N)
+    s = O.Pow2SubRing(N, 576460752303702017)
+    y = r.SubRings[1].NTT(x)
+    assert (y == s.NTT(x)).all()
+    buf = x.copy()
+    r.SubRings[1].NTT(buf, buf)
+    assert (buf == y).all()
+    assert (r.SubRings[1].INTT(y) == x).all()
+    with pytest.raises(b200ring.B200Error):
+        r.SubRings[1].NTT(x[: N - 1])            # short slice: the reference panics (ntt.go:211-214)
+    N3 = 24
+    q3 = O.find_3n_rns_primes(N3, 60, 1)[0]
+    r3 = b200ring.NewRing(N3, [q3])
+    x3 = O.fill_uniform(9, 0, 0, q3, N3)
+    assert (r3.SubRings[0].NTT(x3) == O.ThreeNSubRing(N3, q3).NTT(x3)).all()
+
+
+def test_shape_errors_panic_like_reference():
+    r = b200ring.NewRing(16, [576460752303439873, 576460752303702017])
+    r2 = b200ring.NewRing(32, [576460752303439873])
+    a, b = r.NewPoly(), r2.NewPoly()
+    with pytest.raises(b200ring.B200Error):
+        r.NTT(a, b)
+    with pytest.raises(b200ring.B200Error):
+        r.AtLevel(2)
+    with pytest.raises(b200ring.B200Error):
+        r.NTT(a, r.NewPoly(2))
+
+
+# ---------------------------------------------------------------- BASELINE sizes (properties)
+def test_config1_3n_roundtrip_degree_3x2_12():
+    N, q = 3 * 2**12, 0x10000000000a1001
+    r = b200ring.NewRing(N, [q])
+    x = rand_poly(0xB2000001, 1, [q], N)
+    p, y = r.NewPoly().set(x), r.NewPoly()
+    r.NTT(p, y)
+    s = O.ThreeNSubRing(N, q)
+    assert (y.get()[0, 0] == s.NTT_horner(x[0, 0])).all()      # definitional O(N^2) check
+    r.INTT(y, y)
+    assert (y.get() == x).all()
+
+
+def test_config3_headline_size_3n():
+    """N = 3*2^15, L = 24: full parity on 2 polys x 24 limbs vs the oracle + Horner spot checks."""
+    N, moduli, batch = 3 * 2**15, C3_PRIMES, 2
+    r = b200ring.NewRing(N, moduli)
+    host = rand_poly(0xB2000003, batch, moduli, N)
+    p, o = r.NewPoly(batch).set(host), r.NewPoly(batch)
+    r.NTT(p, o)
+    got = o.get()
+    E = O.totatives(3 * N)
+    rng = np.random.default_rng(1)
+    for l, q in enumerate(moduli):
+        s = O.ThreeNSubRing(N, q)
+        for b in range(batch):
+            assert (got[b, l] == s.NTT(host[b, l])).all(), (b, l)
+        if l % 8 == 0:
+            for k in rng.integers(0, N, 8):
+                assert s.horner_at(host[0, l], E[k]) == int(got[0, l, k])
+    r.INTT(o, o)
+    assert (o.get() == host).all()
+    # linearity in the NTT domain: NTT(a + b) == NTT(a) + NTT(b)
+    a, b2, sm = r.NewPoly(1).set(host[:1]), r.NewPoly(1).set(host[1:]), r.NewPoly(1)
+    r.Add(a, b2, sm); r.NTT(sm, sm); r.NTT(a, a); r.NTT(b2, b2); r.Add(a, b2, a)
+    assert (sm.get() == a.get()).all()
+
+
+def test_config2_pow2_2_16_L24():
+    N, moduli, batch = 1 << 16, QI60[:24], 2
+    r = b200ring.NewRing(N, moduli)
+    host = rand_poly(0xB2000002, batch, moduli, N)
+    p, o = r.NewPoly(batch).set(host), r.NewPoly(batch)
+    r.NTT(p, o)
+    got = o.get()
+    for l, q in enumerate(moduli):
+        s = O.Pow2SubRing(N, q)
+        for b in range(batch):
+            assert (got[b, l] == s.NTT(host[b, l])).all(), (b, l)
+    r.INTT(o, o)
+    assert (o.get() == host).all()
+
+
+def test_config4_polymul_3n_L16():
+    """c = INTT(MulCoeffsMontgomery(MForm(NTT a), NTT b)) at N = 3*2^15, L = 16 vs the oracle; sparse
+    operands vs schoolbook at N = 3*2^12."""
+    N, moduli, batch = 3 * 2**15, C3_PRIMES[:16], 2
+    r = b200ring.NewRing(N, moduli)
+    ha, hb = rand_poly(0xB2000004, batch, moduli, N), rand_poly(0xB2000005, batch, moduli, N)
+    a, b, c = r.NewPoly(batch).set(ha), r.NewPoly(batch).set(hb), r.NewPoly(batch)
+    r.MulPoly(a, b, c)
+    got = c.get()
+    assert (a.get() == ha).all() and (b.get() == hb).all()      # operands untouched
+    for l, q in enumerate(moduli):
+        s = O.ThreeNSubRing(N, q)
+        for bi in range(batch):
+            fa, fb = s.NTT(ha[bi, l], order=1), s.NTT(hb[bi, l], order=1)
+            prod = O.vec_op("MulCoeffsBarrett", q, fa, fb)
+            assert (got[bi, l] == s.INTT(prod, order=1)).all(), (bi, l)
+    N2, q2 = 3 * 2**12, 0x10000000000a1001
+    r2 = b200ring.NewRing(N2, [q2])
+    sa = np.zeros((1, 1, N2), dtype=np.uint64); sb = rand_poly(7, 1, [q2], N2)
+    sa[0, 0, [0, 1, N2 // 2, N2 - 1]] = [3, q2 - 1, 5, 7]
+    c2 = r2.NewPoly()
+    r2.MulPoly(r2.NewPoly().set(sa), r2.NewPoly().set(sb), c2)
+    assert (c2.get()[0, 0] == O.schoolbook_3n(N2, q2, sa[0, 0], sb[0, 0])).all()
