@@ -164,6 +164,12 @@ B200_API int b200_polymul(b200_ctx *ctx, const b200_poly *a, const b200_poly *b,
 B200_API int b200_subring_ntt_host(b200_ctx *ctx, int limb, const uint64_t *p1, uint64_t *p2, size_t n,
                           int inverse, int flags);
 
+/* Per-kernel device timing for the roofline report: between begin and end every kernel launch of this
+ * context is bracketed by CUDA events on its stream.  end() writes one line per kernel name:
+ * "<kernel> <total_ms> <launches> <limb-units processed>\n". */
+B200_API int b200_profile_begin(b200_ctx *ctx);
+B200_API int b200_profile_end(b200_ctx *ctx, char *out, size_t cap);
+
 /* kernel launches enqueued by this context so far (bench.py's gpu_launches evidence) */
 B200_API uint64_t b200_ctx_launch_count(const b200_ctx *ctx);
 

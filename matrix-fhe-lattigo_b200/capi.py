@@ -39,6 +39,8 @@ SYMBOLS = {
     "b200_polymul": (C.c_int, [VP, VP, VP, VP, C.c_int]),
     "b200_subring_ntt_host": (C.c_int, [VP, C.c_int, P64, P64, C.c_size_t, C.c_int, C.c_int]),
     "b200_ctx_launch_count": (C.c_uint64, [VP]),
+    "b200_profile_begin": (C.c_int, [VP]),
+    "b200_profile_end": (C.c_int, [VP, C.c_char_p, C.c_size_t]),
 }
 
 B200_LAZY, B200_TREE_ORDER = 1, 2

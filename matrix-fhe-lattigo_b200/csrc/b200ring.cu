@@ -267,6 +267,44 @@ extern "C" int b200_ctx_moduli_count(const b200_ctx *ctx) { return ctx ? ctx->L 
 extern "C" int b200_ctx_ring_type(const b200_ctx *ctx) { return ctx ? ctx->ring_type : B200_EINVAL; }
 extern "C" uint64_t b200_ctx_launch_count(const b200_ctx *ctx) { return ctx ? ctx->launches.load() : 0; }
 
+// ---- per-kernel device timing ------------------------------------------------------------------------
+extern "C" int b200_profile_begin(b200_ctx *ctx) {
+    if (!ctx) return fail(B200_EINVAL, "ctx is NULL");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    for (auto &r : ctx->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    ctx->prof.clear();
+    ctx->profiling = true;
+    return 0;
+}
+extern "C" int b200_profile_end(b200_ctx *ctx, char *out, size_t cap) {
+    if (!ctx || !out || cap == 0) return fail(B200_EINVAL, "b200_profile_end: bad argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    ctx->profiling = false;
+    struct Acc { double ms = 0; long long launches = 0, units = 0; };
+    std::vector<std::pair<std::string, Acc>> acc;
+    for (auto &r : ctx->prof) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, r.e0, r.e1);
+        size_t i = 0;
+        for (; i < acc.size(); ++i) if (acc[i].first == r.name) break;
+        if (i == acc.size()) acc.push_back({r.name, Acc()});
+        acc[i].second.ms += ms; acc[i].second.launches++; acc[i].second.units += r.units;
+        cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+    }
+    ctx->prof.clear();
+    std::string s;
+    for (auto &kv : acc) {
+        char line[160];
+        snprintf(line, sizeof line, "%s %.6f %lld %lld\n", kv.first.c_str(), kv.second.ms, kv.second.launches, kv.second.units);
+        s += line;
+    }
+    if (s.size() + 1 > cap) return fail(B200_ESHAPE, "b200_profile_end: buffer too small");
+    std::memcpy(out, s.c_str(), s.size() + 1);
+    return 0;
+}
+
 extern "C" int b200_ctx_subring(const b200_ctx *ctx, int limb, uint64_t out[8]) {
     if (!ctx || !out || limb < 0 || limb >= ctx->L) return fail(B200_EINVAL, "b200_ctx_subring: bad argument");
     const SubRingHost &s = ctx->sub[limb];

@@ -40,6 +40,10 @@ struct b200_ctx {
     u64 *d_scratch = nullptr;        // grown on demand (generic large-N path, polymul temporaries)
     size_t scratch_words = 0;
     std::atomic<uint64_t> launches{0};
+    // optional per-kernel device timing (b200_profile_begin/end): CUDA events around each launch
+    bool profiling = false;
+    struct ProfRec { const char *name; cudaEvent_t e0, e1; long long units; };
+    std::vector<ProfRec> prof;
     // optimised-path tables (ntt_big.cu); null when the ring shape is not covered
     void *big = nullptr;
 };
@@ -60,6 +64,26 @@ int b200_cuda_fail(cudaError_t e, const char *what);
     } while (0)
 
 int b200_ensure_scratch(b200_ctx *ctx, size_t words);
+
+// RAII bracket around one kernel launch: counts it and, when profiling, times it with CUDA events
+struct LaunchScope {
+    b200_ctx *c;
+    int idx = -1;
+    LaunchScope(b200_ctx *ctx, const char *name, long long units) : c(ctx) {
+        c->launches++;
+        if (c->profiling) {
+            b200_ctx::ProfRec r{name, nullptr, nullptr, units};
+            cudaEventCreate(&r.e0);
+            cudaEventCreate(&r.e1);
+            cudaEventRecord(r.e0, c->stream);
+            c->prof.push_back(r);
+            idx = (int)c->prof.size() - 1;
+        }
+    }
+    ~LaunchScope() {
+        if (idx >= 0) cudaEventRecord(c->prof[idx].e1, c->stream);
+    }
+};
 
 // kernel launchers (each returns 0 or a negative code; all enqueue on ctx->stream)
 // A launch covers `batch` polynomials x limbs [limb0, limb0+nl) of the ring; the buffers are laid out

@@ -243,6 +243,21 @@ class Ring:
     def LaunchCount(self):
         return int(lib().b200_ctx_launch_count(self._ctx.h))
 
+    def Profile(self, fn):
+        """Run fn() with every kernel launch bracketed by CUDA events; returns
+        {kernel: {"ms": total, "launches": n, "units": limb-units}} (bench.py roofline)."""
+        check(lib().b200_profile_begin(self._ctx.h))
+        try:
+            fn()
+        finally:
+            buf = C.create_string_buffer(1 << 16)
+            check(lib().b200_profile_end(self._ctx.h, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, ms, launches, units = line.split()
+            out[name] = {"ms": float(ms), "launches": int(launches), "units": int(units)}
+        return out
+
     # -- transforms (ring/ntt.go:127-152) --
     def NTT(self, p1, p2, tree_order=False):
         check(lib().b200_ntt(self._ctx.h, p1.h, p2.h, self.level, capi.B200_TREE_ORDER if tree_order else 0))
