@@ -1,0 +1,149 @@
+// b200ring.hpp -- C++ host-side mirror of the reference's `ring` package surface for the hot path
+// (ring.Ring, ring.SubRing, ring.Poly; ring/ring.go, ring/poly.go, ring/ntt.go, ring/operations.go),
+// header-only, over the C ABI of b200ring.h.  The reference is Go; no Go toolchain exists in the build
+// image, so the compiled host side is C++ with the same names, argument meaning and error behaviour:
+// constructors throw std::invalid_argument where Go returns `error`, hot functions throw ring::Panic
+// where Go panics.  INTEGRATION.md shows the equivalent cgo file for package `ring`.
+#pragma once
+#include <cstdint>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "b200ring.h"
+
+namespace ring {
+
+enum Type { Standard = 0, ConjugateInvariant = 1, Matrix = 2 };   // ring/ring.go:30-34
+
+struct Panic : std::runtime_error {   // the reference's panic(...) on the hot path
+    int code;
+    Panic(int c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+
+inline void check(int rc) {
+    if (rc == B200_OK) return;
+    if (rc == B200_EINVAL) throw std::invalid_argument(b200_last_error());
+    throw Panic(rc, b200_last_error());
+}
+
+// isValidRingDegreeFor3N, ring/subring.go:14-30
+inline bool IsValidRingDegreeFor3N(int N) {
+    if (N <= 0) return false;
+    long t = 3L * N;
+    while (t % 3 == 0) t /= 3;
+    return t > 0 && (t & (t - 1)) == 0;
+}
+
+class Ring;
+
+// ring.Poly (ring/poly.go:13-24): device resident, `batch` polynomials of [L][N] words
+class Poly {
+  public:
+    Poly(const Ring &r, int batch = 1);
+    Poly(const Poly &) = delete;
+    Poly &operator=(const Poly &) = delete;
+    Poly(Poly &&o) noexcept : h_(o.h_), words_(o.words_), batch_(o.batch_) { o.h_ = nullptr; }
+    ~Poly() { if (h_) b200_poly_free(h_); }
+    int Batch() const { return batch_; }
+    // Poly.Coeffs[limb] of polynomial b  <->  a host slice of >= N words
+    void SetLimb(int b, int limb, const std::vector<uint64_t> &v) { check(b200_poly_upload_limb(h_, b, limb, v.data(), v.size())); }
+    std::vector<uint64_t> Limb(int b, int limb, size_t n) const {
+        std::vector<uint64_t> v(n);
+        check(b200_poly_download_limb(h_, b, limb, v.data(), v.size()));
+        return v;
+    }
+    void Set(const std::vector<uint64_t> &all) { check(b200_poly_upload(h_, all.data(), all.size())); }
+    std::vector<uint64_t> Get() const {
+        std::vector<uint64_t> v(words_);
+        check(b200_poly_download(h_, v.data(), v.size()));
+        return v;
+    }
+    b200_poly *handle() const { return h_; }
+
+  private:
+    b200_poly *h_ = nullptr;
+    size_t words_ = 0;
+    int batch_ = 0;
+};
+
+// ring.SubRing (ring/subring.go:35-55) view of one prime
+struct SubRing {
+    int N = 0;
+    uint64_t Modulus = 0, MRedConstant = 0, BRedConstant[2] = {0, 0}, Mask = 0, PrimitiveRoot = 0, NInv = 0, Root = 0;
+};
+
+class Ring {
+  public:
+    // ring.NewRing (ring/ring.go:264-272)
+    static Ring NewRing(int N, const std::vector<uint64_t> &Moduli, int device = 0, const std::vector<uint64_t> *roots = nullptr) {
+        const bool is3n = N % 3 == 0 && IsValidRingDegreeFor3N(N);
+        return NewRingFromType(N, Moduli, is3n ? Matrix : Standard, device, roots);
+    }
+    // ring.NewRingFromType (ring/ring.go:291-308)
+    static Ring NewRingFromType(int N, const std::vector<uint64_t> &Moduli, Type t, int device = 0,
+                                const std::vector<uint64_t> *roots = nullptr) {
+        if (t == ConjugateInvariant) throw std::invalid_argument("ConjugateInvariant rings are outside the B200 hot path");
+        b200_ctx *c = nullptr;
+        check(b200_ctx_create((int)t, N, (int)Moduli.size(), Moduli.data(), roots ? roots->data() : nullptr, device, &c));
+        return Ring(std::shared_ptr<b200_ctx>(c, b200_ctx_destroy), (int)Moduli.size() - 1);
+    }
+    int N() const { return b200_ctx_n(ctx_.get()); }
+    int Level() const { return level_; }
+    int MaxLevel() const { return b200_ctx_moduli_count(ctx_.get()) - 1; }
+    int ModuliChainLength() const { return b200_ctx_moduli_count(ctx_.get()); }
+    Type GetType() const { return (Type)b200_ctx_ring_type(ctx_.get()); }
+    Ring AtLevel(int level) const {   // ring/ring.go:194-213
+        if (level < 0) throw Panic(B200_ESHAPE, "level cannot be negative");
+        if (level > MaxLevel()) throw Panic(B200_ESHAPE, "level cannot be larger than max level");
+        return Ring(ctx_, level);
+    }
+    SubRing SubRingAt(int i) const {
+        uint64_t o[8];
+        check(b200_ctx_subring(ctx_.get(), i, o));
+        SubRing s;
+        s.N = N(); s.Modulus = o[0]; s.MRedConstant = o[1]; s.BRedConstant[0] = o[2]; s.BRedConstant[1] = o[3];
+        s.Mask = o[4]; s.PrimitiveRoot = o[5]; s.NInv = o[6]; s.Root = o[7];
+        return s;
+    }
+    Poly NewPoly(int batch = 1) const { return Poly(*this, batch); }
+    void Sync() const { check(b200_sync(ctx_.get())); }
+
+    // ring/ntt.go:127-152
+    void NTT(const Poly &p1, Poly &p2) const { check(b200_ntt(ctx_.get(), p1.handle(), p2.handle(), level_, 0)); }
+    void NTTLazy(const Poly &p1, Poly &p2) const { check(b200_ntt(ctx_.get(), p1.handle(), p2.handle(), level_, B200_LAZY)); }
+    void INTT(const Poly &p1, Poly &p2) const { check(b200_intt(ctx_.get(), p1.handle(), p2.handle(), level_, 0)); }
+    void INTTLazy(const Poly &p1, Poly &p2) const { check(b200_intt(ctx_.get(), p1.handle(), p2.handle(), level_, B200_LAZY)); }
+    // ring/operations.go (a representative subset by name; every op code is reachable through VecOp)
+    void VecOp(int op, const Poly &p1, const Poly *p2, Poly &p3) const {
+        check(b200_vec_op(ctx_.get(), op, p1.handle(), p2 ? p2->handle() : nullptr, p3.handle(), level_, nullptr));
+    }
+    void Add(const Poly &a, const Poly &b, Poly &c) const { VecOp(B200_OP_ADD, a, &b, c); }
+    void Sub(const Poly &a, const Poly &b, Poly &c) const { VecOp(B200_OP_SUB, a, &b, c); }
+    void Reduce(const Poly &a, Poly &c) const { VecOp(B200_OP_REDUCE, a, nullptr, c); }
+    void MForm(const Poly &a, Poly &c) const { VecOp(B200_OP_MFORM, a, nullptr, c); }
+    void IMForm(const Poly &a, Poly &c) const { VecOp(B200_OP_IMFORM, a, nullptr, c); }
+    void MulCoeffsMontgomery(const Poly &a, const Poly &b, Poly &c) const { VecOp(B200_OP_MUL_MONT, a, &b, c); }
+    void MulCoeffsMontgomeryThenAdd(const Poly &a, const Poly &b, Poly &c) const { VecOp(B200_OP_MUL_MONT_ADD, a, &b, c); }
+    void MulCoeffsBarrett(const Poly &a, const Poly &b, Poly &c) const { VecOp(B200_OP_MUL_BARRETT, a, &b, c); }
+    // fused NTT, NTT, MForm, MulCoeffsMontgomery, INTT (BASELINE config 4)
+    void MulPoly(const Poly &a, const Poly &b, Poly &c) const { check(b200_polymul(ctx_.get(), a.handle(), b.handle(), c.handle(), level_)); }
+    // NumberTheoreticTransformer (ring/ntt.go:15-22) for one prime, host slices
+    void SubRingNTT(int limb, const std::vector<uint64_t> &p1, std::vector<uint64_t> &p2, bool inverse = false, bool lazy = false) const {
+        check(b200_subring_ntt_host(ctx_.get(), limb, p1.data(), p2.data(), p1.size() < p2.size() ? p1.size() : p2.size(), inverse, lazy ? B200_LAZY : 0));
+    }
+    b200_ctx *handle() const { return ctx_.get(); }
+
+  private:
+    Ring(std::shared_ptr<b200_ctx> c, int level) : ctx_(std::move(c)), level_(level) {}
+    std::shared_ptr<b200_ctx> ctx_;
+    int level_;
+};
+
+inline Poly::Poly(const Ring &r, int batch) : batch_(batch) {
+    check(b200_poly_alloc(r.handle(), batch, &h_));
+    words_ = (size_t)batch * r.ModuliChainLength() * r.N();
+}
+
+}  // namespace ring

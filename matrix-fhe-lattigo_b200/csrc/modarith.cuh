@@ -64,3 +64,42 @@ __device__ __forceinline__ u64 shoup_lazy(u64 x, u64 w, u64 ws, u64 q) {
     return x * w - __umul64hi(x, ws) * q;
 }
 __device__ __forceinline__ u64 shoup(u64 x, u64 w, u64 ws, u64 q) { return csub(shoup_lazy(x, w, ws, q), q); }
+
+// ---- hand-scheduled variants for the tuned kernels (ntt_big.cu) -----------------------------------------
+// On sm_100a a 64-bit multiply is emulated on the 32-bit integer pipes: IMAD.WIDE (32x32->64, two FMA-pipe
+// slots), IMAD (one slot) and IADD3 (ALU pipe, half rate).  The ALU pipe is the binding resource of the
+// butterflies, so these forms trade ALU work for FMA-pipe work and drop what laziness allows.
+__device__ __forceinline__ u64 mulwide_u32(unsigned a, unsigned b) {
+    u64 r; asm("mul.wide.u32 %0, %1, %2;" : "=l"(r) : "r"(a), "r"(b)); return r;
+}
+__device__ __forceinline__ u64 madwide_u32(unsigned a, unsigned b, u64 c) {
+    u64 r; asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(c)); return r;
+}
+__device__ __forceinline__ unsigned madlo_u32(unsigned a, unsigned b, unsigned c) {
+    unsigned r; asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r;
+}
+__device__ __forceinline__ unsigned lo32(u64 x) { return (unsigned)x; }
+__device__ __forceinline__ unsigned hi32(u64 x) { return (unsigned)(x >> 32); }
+
+// x*w mod q in [0, 4q) for ANY 64-bit x.  The quotient estimate t drops the low partial product and the
+// low halves of the cross products of x*ws, so it is at most 2 below floor(x*ws/2^64); the remainder is
+// accumulated as x*w + t*(2^64 - q) on the low 64 bits (2 wide + 4 narrow multiply-adds, no subtraction).
+__device__ __forceinline__ u64 shoup4(u64 x, u64 w, u64 ws, u64 nq) {
+    const unsigned x0 = lo32(x), x1 = hi32(x);
+    const u64 t = mulwide_u32(x1, hi32(ws)) + hi32(mulwide_u32(x0, hi32(ws))) + hi32(mulwide_u32(x1, lo32(ws)));
+    const unsigned t0 = lo32(t), t1 = hi32(t);
+    const u64 r = madwide_u32(t0, lo32(nq), mulwide_u32(x0, lo32(w)));
+    unsigned r1 = hi32(r);
+    r1 = madlo_u32(x0, hi32(w), r1);
+    r1 = madlo_u32(x1, lo32(w), r1);
+    r1 = madlo_u32(t0, hi32(nq), r1);
+    r1 = madlo_u32(t1, lo32(nq), r1);
+    return ((u64)r1 << 32) | lo32(r);
+}
+// x >= m ? x - m : x with the subtraction done as a multiply-add by nm = 2^64 - m on the FMA pipe:
+// 3 ALU (compare + select) + 2 FMA instructions instead of 6 ALU.
+__device__ __forceinline__ u64 csub_fma(u64 x, u64 m, u64 nm) {
+    const unsigned k = x >= m ? 1u : 0u;
+    const u64 r = madwide_u32(k, lo32(nm), x);
+    return ((u64)madlo_u32(k, hi32(nm), hi32(r)) << 32) | lo32(r);
+}

@@ -43,23 +43,33 @@ __device__ __forceinline__ UnitRef unit_ref(const BigArgs &a) {
     return {a.in_dense ? dense : layout, a.out_dense ? dense : layout, a.sp.limb0 + l};
 }
 
-// Harvey butterflies.  forward: in [0,4q) -> out [0,4q);  inverse: in [0,2q) -> out [0,2q)
-__device__ __forceinline__ void bf_fwd(u64 &U, u64 &V, const tw_t w, u64 q, u64 twoq) {
-    const u64 u = csub(U, twoq);
-    const u64 t = shoup_lazy(V, w.x, w.y, q);
+// Per-prime constants of the lazy butterflies
+struct QC {
+    u64 q, twoq, fourq, nq, nfourq;
+    __device__ __forceinline__ explicit QC(u64 q_) : q(q_), twoq(2 * q_), fourq(4 * q_), nq(0 - q_), nfourq(0 - 4 * q_) {}
+};
+// Harvey butterflies on the approximate Shoup product (shoup4: [0,4q)).  q < 2^61 so 8q fits in 64 bits.
+//   forward (Cooley-Tukey):   in [0,8q) -> out [0,8q)
+//   inverse (Gentleman-Sande): in [0,4q) -> out [0,4q)
+__device__ __forceinline__ void bf_fwd(u64 &U, u64 &V, const tw_t w, const QC &c) {
+    const u64 u = csub_fma(U, c.fourq, c.nfourq);
+    const u64 t = shoup4(V, w.x, w.y, c.nq);
     U = u + t;
-    V = u - t + twoq;
+    V = u - t + c.fourq;
 }
-__device__ __forceinline__ void bf_inv(u64 &U, u64 &V, const tw_t w, u64 q, u64 twoq) {
-    const u64 s = U + V, d = U - V + twoq;
-    U = csub(s, twoq);
-    V = shoup_lazy(d, w.x, w.y, q);
+__device__ __forceinline__ void bf_inv(u64 &U, u64 &V, const tw_t w, const QC &c) {
+    const u64 s = U + V, d = U - V + c.fourq;
+    U = csub_fma(s, c.fourq, c.nfourq);
+    V = shoup4(d, w.x, w.y, c.nq);
 }
+// [0,8q) -> [0,q) and [0,4q) -> [0,2q)
+__device__ __forceinline__ u64 canon8(u64 x, const QC &c) { return csub(csub(csub(x, c.fourq), c.twoq), c.q); }
+__device__ __forceinline__ u64 to2q(u64 x, const QC &c) { return csub(x, c.twoq); }
 
 // 2^LOGM-point sub-transform held in registers; x[k] ordered along the sub-dimension (MSB first);
 // P = heap index of the sub-transform's root node.
 template <int LOGM>
-__device__ __forceinline__ void fwd_regs(u64 (&x)[1 << LOGM], unsigned P, const tw_t *__restrict__ tw, u64 q, u64 twoq) {
+__device__ __forceinline__ void fwd_regs(u64 (&x)[1 << LOGM], unsigned P, const tw_t *__restrict__ tw, const QC &c) {
 #pragma unroll
     for (int j = 0; j < LOGM; ++j) {
         const int half = (1 << LOGM) >> (j + 1);
@@ -67,12 +77,12 @@ __device__ __forceinline__ void fwd_regs(u64 (&x)[1 << LOGM], unsigned P, const 
         for (int g = 0; g < (1 << j); ++g) {
             const tw_t w = tw[(P << j) + g];
 #pragma unroll
-            for (int o = 0; o < half; ++o) bf_fwd(x[g * 2 * half + o], x[g * 2 * half + o + half], w, q, twoq);
+            for (int o = 0; o < half; ++o) bf_fwd(x[g * 2 * half + o], x[g * 2 * half + o + half], w, c);
         }
     }
 }
 template <int LOGM, int JMIN = 0>
-__device__ __forceinline__ void inv_regs(u64 (&x)[1 << LOGM], unsigned P, const tw_t *__restrict__ tw, u64 q, u64 twoq) {
+__device__ __forceinline__ void inv_regs(u64 (&x)[1 << LOGM], unsigned P, const tw_t *__restrict__ tw, const QC &c) {
 #pragma unroll
     for (int j = LOGM - 1; j >= JMIN; --j) {
         const int half = (1 << LOGM) >> (j + 1);
@@ -80,7 +90,7 @@ __device__ __forceinline__ void inv_regs(u64 (&x)[1 << LOGM], unsigned P, const 
         for (int g = 0; g < (1 << j); ++g) {
             const tw_t w = tw[(P << j) + g];
 #pragma unroll
-            for (int o = 0; o < half; ++o) bf_inv(x[g * 2 * half + o], x[g * 2 * half + o + half], w, q, twoq);
+            for (int o = 0; o < half; ++o) bf_inv(x[g * 2 * half + o], x[g * 2 * half + o + half], w, c);
         }
     }
 }
@@ -92,324 +102,390 @@ __device__ __forceinline__ void stg256(u64 *p, u64 a, u64 b, u64 c, u64 d) {
     asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
 }
 
-__device__ __forceinline__ int swz(int c) { return c + 2 * (c >> 4); }   // 16-word groups padded to 18
-constexpr int ROW_PITCH = 288;                                            // 256 words swizzled
-
 __device__ __forceinline__ unsigned rev_bits(unsigned x, int bits) { return bits ? (__brev(x) >> (32 - bits)) : 0u; }
 
 // ====================================================================================================
-// row pass: 8 radix-2 layers inside 256-word rows.  ROWS = 16 (STANDARD) or 24 (MATRIX: 6 blocks x 4 v).
+// row pass: 8 radix-2 layers inside 256-word rows, ONE WARP PER ROW (no CTA barrier on the hot path).
+// Three register groups of 3 + 3 + 2 layers on 8 words per lane; the two exchanges go through a
+// warp-private shared-memory buffer (index c + c/16: conflict-free for all four access patterns).
+//   G1: lane owns c = k*32 + lane            (layers on c bits 7..5; 256-byte coalesced loads)
+//   G2: lane owns c = hi3*32 + k*4 + lo2     (bits 4..2; hi3 = lane & 7, lo2 = lane >> 3)
+//   G3: lane owns c = lane*8 + k             (bits 1..0 on two 4-groups; 64 contiguous bytes per lane)
 // ====================================================================================================
-template <int ROWS, bool MATRIX>
-__device__ __forceinline__ int row_of(const BigArgs &a, int tile, int row, int &rowcode) {
-    if (!MATRIX) { rowcode = 0; return tile * ROWS + row; }
-    const int hd = row >> 2, vi = row & 3;
-    const int u = (int)rev_bits((unsigned)(tile * 4 + vi), a.logU);
-    rowcode = vi * 6 + 2 * (hd % 3) + hd / 3;          // position inside a 24-run of the reference order
+constexpr int WROW = 272;   // 256 words + 16 padding
+__device__ __forceinline__ int pad16(int c) { return c + (c >> 4); }
+
+// MATRIX: a CTA owns the 6 blocks (hd) x VT consecutive v = bitrev(u); rows are ordered hd*VT + vi
+template <bool MATRIX, int VT>
+__device__ __forceinline__ int row_of(const BigArgs &a, int tile, int w, int &rowcode) {
+    if (!MATRIX) { rowcode = 0; return tile * VT + w; }
+    const int hd = w / VT, vi = w - hd * VT;
+    const int u = (int)rev_bits((unsigned)(tile * VT + vi), a.logU);
+    rowcode = vi * 6 + 2 * (hd % 3) + hd / 3;          // position inside a 6*VT run of the reference order
     return (hd << a.logU) + u;
 }
 
-template <int ROWS, bool MATRIX>
-__global__ void __launch_bounds__(ROWS * 16)
+template <bool MATRIX, int VT>   // warps per CTA: MATRIX 6*VT, STANDARD VT
+__global__ void __launch_bounds__((MATRIX ? 6 : 1) * VT * 32)
 k_rows_fwd(const u64 *in, u64 *out, BigArgs a) {
+    constexpr int WARPS = (MATRIX ? 6 : 1) * VT, RUN = 6 * VT;
     extern __shared__ __align__(16) u64 sm[];
     const UnitRef ur = unit_ref(a);
     const int limb = ur.limb;
     const u64 q = a.consts[limb].q, twoq = 2 * q;
+    const QC qc(q);
     const tw_t *__restrict__ tw = a.fwd + (size_t)limb * a.N;
-    const int t = threadIdx.x, row = t >> 4, g = t & 15;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     int rowcode;
-    const int r = row_of<ROWS, MATRIX>(a, blockIdx.x, row, rowcode);
+    const int r = row_of<MATRIX, VT>(a, blockIdx.x, w, rowcode);
+    u64 *buf = sm + w * WROW;
     const u64 *src = in + ur.in + (size_t)r * 256;
-    u64 x[16];
-    // group 1: layers on c bits 7..4; thread owns c = k*16 + g
+    u64 x[8];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) x[k] = src[k * 16 + g];
+    for (int k = 0; k < 8; ++k) x[k] = src[k * 32 + lane];
     const unsigned P1 = (unsigned)(a.R + r);
-    fwd_regs<4>(x, P1, tw, q, twoq);
+    fwd_regs<3>(x, P1, tw, qc);
 #pragma unroll
-    for (int k = 0; k < 16; ++k) sm[row * ROW_PITCH + swz(k * 16 + g)] = x[k];
-    __syncthreads();
-    // group 2: layers on c bits 3..0; thread owns c = g*16 + k (contiguous)
+    for (int k = 0; k < 8; ++k) buf[pad16(k * 32 + lane)] = x[k];
+    __syncwarp();
+    const int hi3 = lane & 7, lo2 = lane >> 3;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = buf[pad16(hi3 * 32 + k * 4 + lo2)];
+    fwd_regs<3>(x, P1 * 8 + hi3, tw, qc);
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) buf[pad16(hi3 * 32 + k * 4 + lo2)] = x[k];
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = buf[pad16(lane * 8 + k)];
     {
-        const ulonglong2 *s2 = reinterpret_cast<const ulonglong2 *>(sm + row * ROW_PITCH + g * 18);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { const ulonglong2 v = s2[k]; x[2 * k] = v.x; x[2 * k + 1] = v.y; }
+        u64 (&lo)[4] = *reinterpret_cast<u64 (*)[4]>(&x[0]);
+        u64 (&hi)[4] = *reinterpret_cast<u64 (*)[4]>(&x[4]);
+        fwd_regs<2>(lo, P1 * 64 + lane * 2, tw, qc);
+        fwd_regs<2>(hi, P1 * 64 + lane * 2 + 1, tw, qc);
     }
-    fwd_regs<4>(x, P1 * 16 + g, tw, q, twoq);
-    if (!(a.flags & B200_LAZY)) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) x[k] = csub(csub(x[k], twoq), q);
-    }
+    for (int k = 0; k < 8; ++k) x[k] = (a.flags & B200_LAZY) ? csub(x[k], qc.fourq) : canon8(x[k], qc);   // lazy: [0,4q) <= 6q-2
     if (!MATRIX || (a.flags & B200_TREE_ORDER)) {
-        u64 *dst = out + ur.out + (size_t)r * 256 + g * 16;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) stg256(dst + 4 * k, x[4 * k], x[4 * k + 1], x[4 * k + 2], x[4 * k + 3]);
+        u64 *dst = out + ur.out + (size_t)r * 256 + lane * 8;
+        stg256(dst, x[0], x[1], x[2], x[3]);
+        stg256(dst + 4, x[4], x[5], x[6], x[7]);
     } else {
-        // reference order: slot = rev8(c)*6U + v*6 + (2d+h); stage the tile as [rev8(c)][24] (pitch 25)
+        // reference order: slot = rev8(c)*6U + v*6 + (2d+h); stage the tile as [rev8(c)][RUN] (pitch RUN+1)
         __syncthreads();
-        const int rg = (int)rev_bits((unsigned)g, 4);
+        const int rl = (int)rev_bits((unsigned)lane, 5);
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const int cr = (int)rev_bits((unsigned)k, 4) * 16 + rg;   // rev8(g*16 + k)
-            sm[cr * 25 + rowcode] = x[k];
-        }
+        for (int k = 0; k < 8; ++k) sm[((int)rev_bits((unsigned)k, 3) * 32 + rl) * (RUN + 1) + rowcode] = x[k];
         __syncthreads();
         const size_t run = (size_t)6 << a.logU;                       // 6U words between consecutive rev8(c)
-        u64 *dst = out + ur.out + (size_t)blockIdx.x * 24;
-        for (int o = t; o < 256 * 24; o += ROWS * 16) {
-            const int cr = o / 24, rem = o - cr * 24;
-            dst[(size_t)cr * run + rem] = sm[cr * 25 + rem];
+        u64 *dst = out + ur.out + (size_t)blockIdx.x * RUN;
+        for (int o = threadIdx.x; o < 256 * RUN; o += WARPS * 32) {
+            const int cr = o / RUN, rem = o - cr * RUN;
+            dst[(size_t)cr * run + rem] = sm[cr * (RUN + 1) + rem];
         }
     }
 }
 
-template <int ROWS, bool MATRIX>
-__global__ void __launch_bounds__(ROWS * 16)
+template <bool MATRIX, int VT>
+__global__ void __launch_bounds__((MATRIX ? 6 : 1) * VT * 32)
 k_rows_inv(const u64 *in, u64 *out, BigArgs a) {
+    constexpr int WARPS = (MATRIX ? 6 : 1) * VT, RUN = 6 * VT;
     extern __shared__ __align__(16) u64 sm[];
     const UnitRef ur = unit_ref(a);
     const int limb = ur.limb;
     const u64 q = a.consts[limb].q, twoq = 2 * q;
+    const QC qc(q);
     const tw_t *__restrict__ tw = a.inv + (size_t)limb * a.N;
-    const int t = threadIdx.x, row = t >> 4, g = t & 15;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     int rowcode;
-    const int r = row_of<ROWS, MATRIX>(a, blockIdx.x, row, rowcode);
-    u64 x[16];
+    const int r = row_of<MATRIX, VT>(a, blockIdx.x, w, rowcode);
+    u64 *buf = sm + w * WROW;
+    u64 x[8];
     if (!MATRIX || (a.flags & B200_TREE_ORDER)) {
-        const u64 *src = in + ur.in + (size_t)r * 256 + g * 16;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) ldg256(src + 4 * k, x[4 * k], x[4 * k + 1], x[4 * k + 2], x[4 * k + 3]);
+        const u64 *src = in + ur.in + (size_t)r * 256 + lane * 8;
+        ldg256(src, x[0], x[1], x[2], x[3]);
+        ldg256(src + 4, x[4], x[5], x[6], x[7]);
     } else {
         const size_t run = (size_t)6 << a.logU;
-        const u64 *src = in + ur.in + (size_t)blockIdx.x * 24;
-        for (int o = t; o < 256 * 24; o += ROWS * 16) {
-            const int cr = o / 24, rem = o - cr * 24;
-            sm[cr * 25 + rem] = src[(size_t)cr * run + rem];
+        const u64 *src = in + ur.in + (size_t)blockIdx.x * RUN;
+        for (int o = threadIdx.x; o < 256 * RUN; o += WARPS * 32) {
+            const int cr = o / RUN, rem = o - cr * RUN;
+            sm[cr * (RUN + 1) + rem] = src[(size_t)cr * run + rem];
         }
         __syncthreads();
-        const int rg = (int)rev_bits((unsigned)g, 4);
+        const int rl = (int)rev_bits((unsigned)lane, 5);
 #pragma unroll
-        for (int k = 0; k < 16; ++k) x[k] = sm[((int)rev_bits((unsigned)k, 4) * 16 + rg) * 25 + rowcode];
+        for (int k = 0; k < 8; ++k) x[k] = sm[((int)rev_bits((unsigned)k, 3) * 32 + rl) * (RUN + 1) + rowcode];
         __syncthreads();
     }
     const unsigned P1 = (unsigned)(a.R + r);
-    inv_regs<4>(x, P1 * 16 + g, tw, q, twoq);
     {
-        ulonglong2 *s2 = reinterpret_cast<ulonglong2 *>(sm + row * ROW_PITCH + g * 18);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) s2[k] = make_ulonglong2(x[2 * k], x[2 * k + 1]);
+        u64 (&lo)[4] = *reinterpret_cast<u64 (*)[4]>(&x[0]);
+        u64 (&hi)[4] = *reinterpret_cast<u64 (*)[4]>(&x[4]);
+        inv_regs<2>(lo, P1 * 64 + lane * 2, tw, qc);
+        inv_regs<2>(hi, P1 * 64 + lane * 2 + 1, tw, qc);
     }
-    __syncthreads();
 #pragma unroll
-    for (int k = 0; k < 16; ++k) x[k] = sm[row * ROW_PITCH + swz(k * 16 + g)];
-    inv_regs<4>(x, P1, tw, q, twoq);
+    for (int k = 0; k < 8; ++k) buf[pad16(lane * 8 + k)] = x[k];
+    __syncwarp();
+    const int hi3 = lane & 7, lo2 = lane >> 3;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = buf[pad16(hi3 * 32 + k * 4 + lo2)];
+    inv_regs<3>(x, P1 * 8 + hi3, tw, qc);
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) buf[pad16(hi3 * 32 + k * 4 + lo2)] = x[k];
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = buf[pad16(k * 32 + lane)];
+    inv_regs<3>(x, P1, tw, qc);
     u64 *dst = out + ur.out + (size_t)r * 256;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) dst[k * 16 + g] = x[k];
+    for (int k = 0; k < 8; ++k) dst[k * 32 + lane] = x[k];
 }
 
 // ====================================================================================================
-// column pass, STANDARD rings: SA + SB = log2(N) - 8 layers; a CTA owns 16 columns of all R rows
+// column pass.  A CTA owns CW adjacent columns of ALL rows (CW*8-byte row segments), CW*32 threads per
+// 256 rows.  Shared index of (row, c): pc(row*CW + c), padded every 64 words so that all three groups
+// are conflict-free.
 // ====================================================================================================
-template <int SA, int SB>
-__global__ void __launch_bounds__(16 << (SA > SB ? SA : SB))
-k_cols_fwd_std(const u64 *in, u64 *out, BigArgs a) {
+__device__ __forceinline__ int pc(int i) { return i + ((i >> 6) << 3); }
+
+// STANDARD, log2(N) = 16: 256 rows, layers on row bits [7..5] [4..2] [1..0]
+template <int CW>
+__global__ void __launch_bounds__(CW * 32)
+k_cols_fwd_std16(const u64 *in, u64 *out, BigArgs a) {
     extern __shared__ __align__(16) u64 sm[];
     const UnitRef ur = unit_ref(a);
     const int limb = ur.limb;
-    const size_t ibase = ur.in + (size_t)blockIdx.x * 16, obase = ur.out + (size_t)blockIdx.x * 16;
+    const size_t ibase = ur.in + (size_t)blockIdx.x * CW, obase = ur.out + (size_t)blockIdx.x * CW;
     const u64 q = a.consts[limb].q, twoq = 2 * q;
+    const QC qc(q);
     const tw_t *__restrict__ tw = a.fwd + (size_t)limb * a.N;
-    constexpr int MA = 1 << SA, MB = 1 << SB;
-    for (int t = threadIdx.x; t < 16 * MB; t += blockDim.x) {   // group A: rows k*MB + r_lo
-        const int c = t & 15, rlo = t >> 4;
-        u64 x[MA];
+    const int t = threadIdx.x, c = t % CW, g = t / CW;   // g in [0,32)
+    u64 x[8];
 #pragma unroll
-        for (int k = 0; k < MA; ++k) x[k] = in[ibase + (size_t)(k * MB + rlo) * 256 + c];
-        fwd_regs<SA>(x, 1u, tw, q, twoq);
+    for (int k = 0; k < 8; ++k) x[k] = in[ibase + (size_t)(k * 32 + g) * 256 + c];      // rows k*32 + g
+    fwd_regs<3>(x, 1u, tw, qc);
 #pragma unroll
-        for (int k = 0; k < MA; ++k) sm[(k * MB + rlo) * 16 + c] = x[k];
-    }
+    for (int k = 0; k < 8; ++k) sm[pc((k * 32 + g) * CW + c)] = x[k];
     __syncthreads();
-    for (int t = threadIdx.x; t < 16 * MA; t += blockDim.x) {   // group B: rows r_hi*MB + k
-        const int c = t & 15, rhi = t >> 4;
-        u64 x[MB];
+    const int lo2 = g & 3, hi3 = g >> 2;                                                 // rows hi3*32 + k*4 + lo2
 #pragma unroll
-        for (int k = 0; k < MB; ++k) x[k] = sm[(rhi * MB + k) * 16 + c];
-        fwd_regs<SB>(x, (unsigned)(MA + rhi), tw, q, twoq);
+    for (int k = 0; k < 8; ++k) x[k] = sm[pc((hi3 * 32 + k * 4 + lo2) * CW + c)];
+    fwd_regs<3>(x, 8u + hi3, tw, qc);
+    __syncthreads();
 #pragma unroll
-        for (int k = 0; k < MB; ++k) out[obase + (size_t)(rhi * MB + k) * 256 + c] = x[k];
+    for (int k = 0; k < 8; ++k) sm[pc((hi3 * 32 + k * 4 + lo2) * CW + c)] = x[k];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = sm[pc((g * 8 + k) * CW + c)];                     // rows g*8 + k
+    {
+        u64 (&lo)[4] = *reinterpret_cast<u64 (*)[4]>(&x[0]);
+        u64 (&hi)[4] = *reinterpret_cast<u64 (*)[4]>(&x[4]);
+        fwd_regs<2>(lo, 64u + g * 2, tw, qc);
+        fwd_regs<2>(hi, 64u + g * 2 + 1, tw, qc);
     }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) out[obase + (size_t)(g * 8 + k) * 256 + c] = x[k];
 }
 
-template <int SA, int SB>
-__global__ void __launch_bounds__(16 << (SA > SB ? SA : SB))
-k_cols_inv_std(const u64 *in, u64 *out, BigArgs a) {
+template <int CW>
+__global__ void __launch_bounds__(CW * 32)
+k_cols_inv_std16(const u64 *in, u64 *out, BigArgs a) {
     extern __shared__ __align__(16) u64 sm[];
     const UnitRef ur = unit_ref(a);
     const int limb = ur.limb;
-    const size_t ibase = ur.in + (size_t)blockIdx.x * 16, obase = ur.out + (size_t)blockIdx.x * 16;
+    const size_t ibase = ur.in + (size_t)blockIdx.x * CW, obase = ur.out + (size_t)blockIdx.x * CW;
     const u64 q = a.consts[limb].q, twoq = 2 * q;
+    const QC qc(q);
     const tw_t *__restrict__ tw = a.inv + (size_t)limb * a.N;
     const tw_t ninv = a.misc[limb * MISC_COUNT + MISC_NINV], ninv_w1 = a.misc[limb * MISC_COUNT + MISC_NINV_W1];
     const bool lazy = a.flags & B200_LAZY;
-    constexpr int MA = 1 << SA, MB = 1 << SB;
-    for (int t = threadIdx.x; t < 16 * MA; t += blockDim.x) {   // group B first (small strides)
-        const int c = t & 15, rhi = t >> 4;
-        u64 x[MB];
+    const int t = threadIdx.x, c = t % CW, g = t / CW;
+    u64 x[8];
 #pragma unroll
-        for (int k = 0; k < MB; ++k) x[k] = in[ibase + (size_t)(rhi * MB + k) * 256 + c];
-        inv_regs<SB>(x, (unsigned)(MA + rhi), tw, q, twoq);
-#pragma unroll
-        for (int k = 0; k < MB; ++k) sm[(rhi * MB + k) * 16 + c] = x[k];
+    for (int k = 0; k < 8; ++k) x[k] = in[ibase + (size_t)(g * 8 + k) * 256 + c];
+    {
+        u64 (&lo)[4] = *reinterpret_cast<u64 (*)[4]>(&x[0]);
+        u64 (&hi)[4] = *reinterpret_cast<u64 (*)[4]>(&x[4]);
+        inv_regs<2>(lo, 64u + g * 2, tw, qc);
+        inv_regs<2>(hi, 64u + g * 2 + 1, tw, qc);
     }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sm[pc((g * 8 + k) * CW + c)] = x[k];
     __syncthreads();
-    for (int t = threadIdx.x; t < 16 * MB; t += blockDim.x) {   // group A, last layer carries N^-1
-        const int c = t & 15, rlo = t >> 4;
-        u64 x[MA];
+    const int lo2 = g & 3, hi3 = g >> 2;
 #pragma unroll
-        for (int k = 0; k < MA; ++k) x[k] = sm[(k * MB + rlo) * 16 + c];
-        inv_regs<SA, 1>(x, 1u, tw, q, twoq);
+    for (int k = 0; k < 8; ++k) x[k] = sm[pc((hi3 * 32 + k * 4 + lo2) * CW + c)];
+    inv_regs<3>(x, 8u + hi3, tw, qc);
+    __syncthreads();
 #pragma unroll
-        for (int o = 0; o < MA / 2; ++o) {
-            const u64 U = x[o], V = x[o + MA / 2];
-            u64 X = shoup_lazy(U + V, ninv.x, ninv.y, q);
-            u64 Y = shoup_lazy(U - V + twoq, ninv_w1.x, ninv_w1.y, q);
-            if (!lazy) { X = csub(X, q); Y = csub(Y, q); }
-            x[o] = X; x[o + MA / 2] = Y;
-        }
+    for (int k = 0; k < 8; ++k) sm[pc((hi3 * 32 + k * 4 + lo2) * CW + c)] = x[k];
+    __syncthreads();
 #pragma unroll
-        for (int k = 0; k < MA; ++k) out[obase + (size_t)(k * MB + rlo) * 256 + c] = x[k];
+    for (int k = 0; k < 8; ++k) x[k] = sm[pc((k * 32 + g) * CW + c)];
+    inv_regs<3, 1>(x, 1u, tw, qc);
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {   // last layer carries N^-1
+        const u64 U = x[o], V = x[o + 4];
+        u64 X = shoup_lazy(U + V, ninv.x, ninv.y, q);
+        u64 Y = shoup_lazy(U - V + qc.fourq, ninv_w1.x, ninv_w1.y, q);   // inputs < 4q
+        if (!lazy) { X = csub(X, q); Y = csub(Y, q); }
+        x[o] = X; x[o + 4] = Y;
     }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) out[obase + (size_t)(k * 32 + g) * 256 + c] = x[k];
 }
 
-// ====================================================================================================
-// column pass, MATRIX rings (b = 1): cyclotomic + radix-3 + SA radix-2 layers in registers (6*2^SA words
-// per thread), exchange, SB radix-2 layers.  Rows are (hd, u): hd in [0,6) = 3h + d, u in [0, 2^(SA+SB)).
-// ====================================================================================================
-template <int SA, int SB>
-__global__ void __launch_bounds__(SA == 0 ? 16 << SB : 96 << SA)
-k_cols_fwd_m3(const u64 *in, u64 *out, BigArgs a) {
+// MATRIX, a = 15 (N = 3*2^15): rows (hd, u), hd in [0,6) = 3h + d, u in [0,64).
+//   G1: 12 words  (hd x u bit 5): cyclotomic, radix-3, radix-2 layer 0      -- CW*32 threads
+//   G2:  8 words  (u bits 4..2): radix-2 layers 1..3                          -- CW*48 threads
+//   G3:  8 words  (u bits 2..0, two 4-groups): radix-2 layers 4, 5            -- CW*48 threads
+template <int CW>
+__global__ void __launch_bounds__(CW * 48)
+k_cols_fwd_m3_15(const u64 *in, u64 *out, BigArgs a) {
     extern __shared__ __align__(16) u64 sm[];
     const UnitRef ur = unit_ref(a);
     const int limb = ur.limb;
-    const size_t ibase = ur.in + (size_t)blockIdx.x * 16, obase = ur.out + (size_t)blockIdx.x * 16;
+    const size_t ibase = ur.in + (size_t)blockIdx.x * CW, obase = ur.out + (size_t)blockIdx.x * CW;
     const u64 q = a.consts[limb].q, twoq = 2 * q, fourq = 4 * q;
+    const QC qc(q);
     const tw_t *__restrict__ tw = a.fwd + (size_t)limb * a.N;
     const tw_t om = a.misc[limb * MISC_COUNT + MISC_OMEGA3];
-    constexpr int MA = 1 << SA, MB = 1 << SB, U = MA * MB;
-    for (int t = threadIdx.x; t < 16 * MB; t += blockDim.x) {
-        const int c = t & 15, ulo = t >> 4;
-        u64 x[6][MA];
+    const int t = threadIdx.x, c = t % CW, g = t / CW;   // g in [0,48)
+    if (g < 32) {   // G1: rows hd*64 + b*32 + g
+        u64 x[6][2];
 #pragma unroll
         for (int hd = 0; hd < 6; ++hd)
 #pragma unroll
-            for (int k = 0; k < MA; ++k) x[hd][k] = in[ibase + (size_t)(hd * U + k * MB + ulo) * 256 + c];
+            for (int b = 0; b < 2; ++b) x[hd][b] = in[ibase + (size_t)(hd * 64 + b * 32 + g) * 256 + c];
         const tw_t zeta = tw[1];
 #pragma unroll
-        for (int k = 0; k < MA; ++k) {
+        for (int b = 0; b < 2; ++b) {
 #pragma unroll
             for (int d = 0; d < 3; ++d) {   // cyclotomic layer: in [0,2q) -> [0,4q)
-                const u64 lo = x[d][k], hi = x[d + 3][k];
+                const u64 lo = x[d][b], hi = x[d + 3][b];
                 const u64 tt = shoup_lazy(hi, zeta.x, zeta.y, q);
-                x[d][k] = lo + tt;
-                x[d + 3][k] = csub(lo + hi + twoq - tt, fourq);
+                x[d][b] = lo + tt;
+                x[d + 3][b] = csub(lo + hi + twoq - tt, fourq);
             }
 #pragma unroll
             for (int h = 0; h < 2; ++h) {   // radix-3 layer: [0,4q) -> [0,4q)
                 const tw_t z1 = tw[2 + 2 * h], z2 = tw[3 + 2 * h];
-                const u64 b0 = csub(x[3 * h][k], twoq);
-                const u64 t1 = shoup_lazy(x[3 * h + 1][k], z1.x, z1.y, q);
-                const u64 t2 = shoup_lazy(x[3 * h + 2][k], z2.x, z2.y, q);
+                const u64 b0 = csub(x[3 * h][b], twoq);
+                const u64 t1 = shoup_lazy(x[3 * h + 1][b], z1.x, z1.y, q);
+                const u64 t2 = shoup_lazy(x[3 * h + 2][b], z2.x, z2.y, q);
                 const u64 t3 = shoup_lazy(t1 + twoq - t2, om.x, om.y, q);
-                x[3 * h][k] = csub(b0 + t1 + t2, fourq);
-                x[3 * h + 1][k] = csub(b0 + twoq - t2 + t3, fourq);
-                x[3 * h + 2][k] = csub(b0 + fourq - t1 - t3, fourq);
+                x[3 * h][b] = csub(b0 + t1 + t2, fourq);
+                x[3 * h + 1][b] = csub(b0 + twoq - t2 + t3, fourq);
+                x[3 * h + 2][b] = csub(b0 + fourq - t1 - t3, fourq);
             }
         }
 #pragma unroll
         for (int hd = 0; hd < 6; ++hd) {
-            if (SA > 0) fwd_regs<SA>(x[hd], (unsigned)(6 + hd), tw, q, twoq);
+            bf_fwd(x[hd][0], x[hd][1], tw[6 + hd], qc);   // radix-2 layer 0 of block hd
 #pragma unroll
-            for (int k = 0; k < MA; ++k) sm[(hd * U + k * MB + ulo) * 16 + c] = x[hd][k];
+            for (int b = 0; b < 2; ++b) sm[pc((hd * 64 + b * 32 + g) * CW + c)] = x[hd][b];
         }
     }
     __syncthreads();
-    for (int t = threadIdx.x; t < 16 * 6 * MA; t += blockDim.x) {
-        const int c = t & 15, top = t >> 4;   // top = hd*MA + u_top
-        u64 x[MB];
+    u64 x[8];
+    {   // G2: g = top*4 + lo2, top = hd*2 + u5 in [0,12); rows top*32 + k*4 + lo2
+        const int lo2 = g & 3, top = g >> 2;
 #pragma unroll
-        for (int k = 0; k < MB; ++k) x[k] = sm[(top * MB + k) * 16 + c];
-        fwd_regs<SB>(x, (unsigned)(6 * MA + top), tw, q, twoq);
+        for (int k = 0; k < 8; ++k) x[k] = sm[pc((top * 32 + k * 4 + lo2) * CW + c)];
+        fwd_regs<3>(x, 12u + top, tw, qc);
+        __syncthreads();
 #pragma unroll
-        for (int k = 0; k < MB; ++k) out[obase + (size_t)(top * MB + k) * 256 + c] = x[k];
+        for (int k = 0; k < 8; ++k) sm[pc((top * 32 + k * 4 + lo2) * CW + c)] = x[k];
+    }
+    __syncthreads();
+    {   // G3: rows g*8 + k; sub-transform roots at depth 4: 96 + g*2 + {0,1}
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = sm[pc((g * 8 + k) * CW + c)];
+        u64 (&lo)[4] = *reinterpret_cast<u64 (*)[4]>(&x[0]);
+        u64 (&hi)[4] = *reinterpret_cast<u64 (*)[4]>(&x[4]);
+        fwd_regs<2>(lo, 96u + g * 2, tw, qc);
+        fwd_regs<2>(hi, 96u + g * 2 + 1, tw, qc);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) out[obase + (size_t)(g * 8 + k) * 256 + c] = x[k];
     }
 }
 
-template <int SA, int SB>
-__global__ void __launch_bounds__(SA == 0 ? 16 << SB : 96 << SA)
-k_cols_inv_m3(const u64 *in, u64 *out, BigArgs a) {
+template <int CW>
+__global__ void __launch_bounds__(CW * 48)
+k_cols_inv_m3_15(const u64 *in, u64 *out, BigArgs a) {
     extern __shared__ __align__(16) u64 sm[];
     const UnitRef ur = unit_ref(a);
     const int limb = ur.limb;
-    const size_t ibase = ur.in + (size_t)blockIdx.x * 16, obase = ur.out + (size_t)blockIdx.x * 16;
+    const size_t ibase = ur.in + (size_t)blockIdx.x * CW, obase = ur.out + (size_t)blockIdx.x * CW;
     const u64 q = a.consts[limb].q, twoq = 2 * q, fourq = 4 * q;
+    const QC qc(q);
     const tw_t *__restrict__ tw = a.inv + (size_t)limb * a.N;
     const tw_t *mc = a.misc + limb * MISC_COUNT;
-    const tw_t om = mc[MISC_OMEGA3], k1 = mc[MISC_K1], k2 = mc[MISC_K2], zeta = mc[MISC_ZETA];
     const bool lazy = a.flags & B200_LAZY;
-    constexpr int MA = 1 << SA, MB = 1 << SB, U = MA * MB;
-    for (int t = threadIdx.x; t < 16 * 6 * MA; t += blockDim.x) {
-        const int c = t & 15, top = t >> 4;
-        u64 x[MB];
+    const int t = threadIdx.x, c = t % CW, g = t / CW;
+    {
+        u64 x[8];
 #pragma unroll
-        for (int k = 0; k < MB; ++k) x[k] = in[ibase + (size_t)(top * MB + k) * 256 + c];
-        inv_regs<SB>(x, (unsigned)(6 * MA + top), tw, q, twoq);
+        for (int k = 0; k < 8; ++k) x[k] = in[ibase + (size_t)(g * 8 + k) * 256 + c];
+        u64 (&lo)[4] = *reinterpret_cast<u64 (*)[4]>(&x[0]);
+        u64 (&hi)[4] = *reinterpret_cast<u64 (*)[4]>(&x[4]);
+        inv_regs<2>(lo, 96u + g * 2, tw, qc);
+        inv_regs<2>(hi, 96u + g * 2 + 1, tw, qc);
 #pragma unroll
-        for (int k = 0; k < MB; ++k) sm[(top * MB + k) * 16 + c] = x[k];
+        for (int k = 0; k < 8; ++k) sm[pc((g * 8 + k) * CW + c)] = x[k];
+        __syncthreads();
+        const int lo2 = g & 3, top = g >> 2;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = sm[pc((top * 32 + k * 4 + lo2) * CW + c)];
+        inv_regs<3>(x, 12u + top, tw, qc);
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sm[pc((top * 32 + k * 4 + lo2) * CW + c)] = x[k];
     }
     __syncthreads();
-    for (int t = threadIdx.x; t < 16 * MB; t += blockDim.x) {
-        const int c = t & 15, ulo = t >> 4;
-        u64 x[6][MA];
+    if (g < 32) {
+        const tw_t om = mc[MISC_OMEGA3], k1 = mc[MISC_K1], k2 = mc[MISC_K2], zeta = mc[MISC_ZETA];
+        u64 x[6][2];
 #pragma unroll
         for (int hd = 0; hd < 6; ++hd) {
 #pragma unroll
-            for (int k = 0; k < MA; ++k) x[hd][k] = sm[(hd * U + k * MB + ulo) * 16 + c];
-            if (SA > 0) inv_regs<SA>(x[hd], (unsigned)(6 + hd), tw, q, twoq);
+            for (int b = 0; b < 2; ++b) x[hd][b] = sm[pc((hd * 64 + b * 32 + g) * CW + c)];
+            bf_inv(x[hd][0], x[hd][1], tw[6 + hd], qc);
         }
 #pragma unroll
-        for (int k = 0; k < MA; ++k) {
+        for (int b = 0; b < 2; ++b) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {   // inverse radix-3 (factor 3 deferred): [0,2q) -> [0,2q)
                 const tw_t z1 = tw[2 + 2 * h], z2 = tw[3 + 2 * h];
-                const u64 y0 = x[3 * h][k], y1 = x[3 * h + 1][k], y2 = x[3 * h + 2][k];
+                const u64 y0 = to2q(x[3 * h][b], qc), y1 = to2q(x[3 * h + 1][b], qc), y2 = to2q(x[3 * h + 2][b], qc);
                 const u64 s = shoup_lazy(y1 + twoq - y2, om.x, om.y, q);
-                x[3 * h][k] = csub(csub(y0 + y1 + y2, fourq), twoq);
-                x[3 * h + 1][k] = shoup_lazy(y0 + fourq - y1 - s, z1.x, z1.y, q);
-                x[3 * h + 2][k] = shoup_lazy(y0 + twoq - y2 + s, z2.x, z2.y, q);
+                x[3 * h][b] = csub(csub(y0 + y1 + y2, fourq), twoq);
+                x[3 * h + 1][b] = shoup_lazy(y0 + fourq - y1 - s, z1.x, z1.y, q);
+                x[3 * h + 2][b] = shoup_lazy(y0 + twoq - y2 + s, z2.x, z2.y, q);
             }
 #pragma unroll
             for (int d = 0; d < 3; ++d) {   // inverse cyclotomic layer with the 2/N scaling
-                const u64 lo = x[d][k], hi = x[d + 3][k];
+                const u64 lo = x[d][b], hi = x[d + 3][b];
                 u64 hh = shoup_lazy(lo + twoq - hi, k1.x, k1.y, q);
                 u64 ll = csub(shoup_lazy(lo, k2.x, k2.y, q) + twoq - shoup_lazy(hh, zeta.x, zeta.y, q), twoq);
                 if (!lazy) { ll = csub(ll, q); hh = csub(hh, q); }
-                x[d][k] = ll; x[d + 3][k] = hh;
+                x[d][b] = ll; x[d + 3][b] = hh;
             }
         }
 #pragma unroll
         for (int hd = 0; hd < 6; ++hd)
 #pragma unroll
-            for (int k = 0; k < MA; ++k) out[obase + (size_t)(hd * U + k * MB + ulo) * 256 + c] = x[hd][k];
+            for (int b = 0; b < 2; ++b) out[obase + (size_t)(hd * 64 + b * 32 + g) * 256 + c] = x[hd][b];
     }
 }
 
 // ---- host side ---------------------------------------------------------------------------------------
 struct BigPlan {
     bool covered = false;
-    int SA = 0, SB = 0;
+    int cw = 8, vt = 2;
     size_t chunk_units = 0;   // units per launch group so that a chunk's intermediate stays in L2
 };
 
@@ -426,42 +502,19 @@ int set_smem(K kern, size_t bytes) {
 
 typedef void (*kern_t)(const u64 *, u64 *, BigArgs);
 
-struct ColKernel { kern_t k; int threads; };
-
-ColKernel col_kernel(bool matrix, bool inverse, int SA, int SB) {
-#define STD(A, B) if (!matrix && SA == A && SB == B) return {inverse ? (kern_t)k_cols_inv_std<A, B> : (kern_t)k_cols_fwd_std<A, B>, 16 << (A > B ? A : B)};
-#define M3(A, B) if (matrix && SA == A && SB == B) return {inverse ? (kern_t)k_cols_inv_m3<A, B> : (kern_t)k_cols_fwd_m3<A, B>, A == 0 ? 16 << B : 96 << A};
-    STD(2, 2) STD(3, 2) STD(3, 3) STD(4, 3) STD(4, 4)
-    M3(0, 3) M3(0, 4) M3(1, 4) M3(2, 4)
-#undef STD
-#undef M3
-    return {nullptr, 0};
-}
-
 }  // namespace
 
 int big_tables_create(b200_ctx *ctx) {
     BigPlan *plan = new BigPlan();
     ctx->big = plan;
-    const int min_std = env_int("B200_BIG_MIN_LOGN", 15);
-    const int min_a = env_int("B200_BIG_MIN_A", 13);
-    if (ctx->ring_type == B200_RING_STANDARD) {
-        const int s = ctx->logN - 8;
-        if (ctx->logN >= 12 && ctx->logN <= 16 && ctx->logN >= min_std) {
-            plan->covered = true;
-            plan->SA = (s + 1) / 2;
-            plan->SB = s / 2;
-        }
-    } else if (ctx->b == 1 && ctx->a >= 12 && ctx->a <= 15 && ctx->a >= min_a) {
-        plan->covered = true;
-        plan->SB = ctx->a == 12 ? 3 : 4;
-        plan->SA = ctx->a - 9 - plan->SB;
-    }
-    if (plan->covered && !col_kernel(ctx->ring_type == B200_RING_MATRIX, false, plan->SA, plan->SB).k) plan->covered = false;
-    // chunking: keep (in + intermediate + out) of one chunk well inside L2
+    if (env_int("B200_NO_BIG", 0)) return 0;
+    if (ctx->ring_type == B200_RING_STANDARD) plan->covered = ctx->logN == 16;
+    else plan->covered = ctx->b == 1 && ctx->a == 15;
+    plan->cw = env_int("B200_CW", 8) == 16 ? 16 : 8;
+    plan->vt = env_int("B200_VT", 2) == 4 ? 4 : 2;
     int l2 = 0;
     cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, ctx->device);
-    const size_t budget = (size_t)env_int("B200_CHUNK_MB", l2 > 0 ? (l2 >> 20) / 4 : 24) << 20;
+    const size_t budget = (size_t)env_int("B200_CHUNK_MB", 512) << 20;
     plan->chunk_units = budget / ((size_t)ctx->N * sizeof(u64));
     if (plan->chunk_units < 1) plan->chunk_units = 1;
     return 0;
@@ -476,27 +529,40 @@ int launch_ntt_big(b200_ctx *ctx, const u64 *in, u64 *out, Span sp, bool inverse
     if (!plan || !plan->covered) return 1;
     const bool matrix = ctx->ring_type == B200_RING_MATRIX;
     const bool permute = matrix && !(flags & B200_TREE_ORDER);
-    const int N = ctx->N, R = N / 256;
+    const int N = ctx->N, R = N / 256, cw = plan->cw, vt = plan->vt;
     BigArgs a{ctx->d_consts, ctx->d_fwd, ctx->d_inv, ctx->d_misc, N, R, matrix ? ctx->a - 9 : 0, sp, 0, flags, 0, 0};
-    const ColKernel ck = col_kernel(matrix, inverse, plan->SA, plan->SB);
-    const size_t col_smem = (size_t)R * 16 * sizeof(u64);
-    const int rows = matrix ? 24 : 16;
-    const size_t row_smem = (size_t)rows * ROW_PITCH * sizeof(u64);
-    kern_t rk = matrix ? (inverse ? (kern_t)k_rows_inv<24, true> : (kern_t)k_rows_fwd<24, true>)
-                       : (inverse ? (kern_t)k_rows_inv<16, false> : (kern_t)k_rows_fwd<16, false>);
-    if (int rc = set_smem(ck.k, col_smem)) return rc;
+    kern_t ck, rk;
+    int col_threads, row_warps;
+    if (matrix) {
+        ck = cw == 16 ? (inverse ? (kern_t)k_cols_inv_m3_15<16> : (kern_t)k_cols_fwd_m3_15<16>)
+                      : (inverse ? (kern_t)k_cols_inv_m3_15<8> : (kern_t)k_cols_fwd_m3_15<8>);
+        col_threads = cw * 48;
+        rk = vt == 4 ? (inverse ? (kern_t)k_rows_inv<true, 4> : (kern_t)k_rows_fwd<true, 4>)
+                     : (inverse ? (kern_t)k_rows_inv<true, 2> : (kern_t)k_rows_fwd<true, 2>);
+        row_warps = 6 * vt;
+    } else {
+        ck = cw == 16 ? (inverse ? (kern_t)k_cols_inv_std16<16> : (kern_t)k_cols_fwd_std16<16>)
+                      : (inverse ? (kern_t)k_cols_inv_std16<8> : (kern_t)k_cols_fwd_std16<8>);
+        col_threads = cw * 32;
+        rk = inverse ? (kern_t)k_rows_inv<false, 4> : (kern_t)k_rows_fwd<false, 4>;
+        row_warps = 4;
+    }
+    const int rows_total = R * cw;
+    const size_t col_smem = (size_t)(rows_total + ((rows_total >> 6) << 3) + 8) * sizeof(u64);
+    size_t row_smem = (size_t)row_warps * WROW * sizeof(u64);
+    if (matrix) row_smem = std::max(row_smem, (size_t)256 * (6 * vt + 1) * sizeof(u64));
+    if (int rc = set_smem(ck, col_smem)) return rc;
     if (int rc = set_smem(rk, row_smem)) return rc;
-    // intermediate buffer: in place on `out` unless a slot permutation would make the row pass overwrite
-    // rows other CTAs still have to read
     const int units = sp.batch * sp.nl;
     const int chunk = (int)std::min<size_t>(std::min<size_t>(plan->chunk_units, 65535), (size_t)units);
     u64 *tmp = out;
+    // a slot permutation makes the row pass write rows other CTAs still have to read: go through a buffer
     const bool dense = permute && (!inverse || in == out);
-    if (dense) {   // a chunk-sized ring buffer, rewritten by every chunk: it never has to leave L2
+    if (dense) {
         if (int rc = b200_ensure_scratch(ctx, (size_t)chunk * N)) return rc;
         tmp = ctx->d_scratch;
     }
-    const int row_tiles = R / rows, col_tiles = 256 / 16;
+    const int row_tiles = R / row_warps, col_tiles = 256 / cw;
     for (int u0 = 0; u0 < units; u0 += chunk) {
         const int nu = std::min(chunk, units - u0);
         a.unit0 = u0;
@@ -505,14 +571,14 @@ int launch_ntt_big(b200_ctx *ctx, const u64 *in, u64 *out, Span sp, bool inverse
         second.in_dense = dense;
         if (!inverse) {
             { LaunchScope ls(ctx, matrix ? "cols_fwd_m3" : "cols_fwd_std", nu);
-              ck.k<<<dim3(col_tiles, nu), ck.threads, col_smem, ctx->stream>>>(in, tmp, first); }
+              ck<<<dim3(col_tiles, nu), col_threads, col_smem, ctx->stream>>>(in, tmp, first); }
             { LaunchScope ls(ctx, matrix ? "rows_fwd_m3" : "rows_fwd_std", nu);
-              rk<<<dim3(row_tiles, nu), rows * 16, row_smem, ctx->stream>>>(tmp, out, second); }
+              rk<<<dim3(row_tiles, nu), row_warps * 32, row_smem, ctx->stream>>>(tmp, out, second); }
         } else {
             { LaunchScope ls(ctx, matrix ? "rows_inv_m3" : "rows_inv_std", nu);
-              rk<<<dim3(row_tiles, nu), rows * 16, row_smem, ctx->stream>>>(in, tmp, first); }
+              rk<<<dim3(row_tiles, nu), row_warps * 32, row_smem, ctx->stream>>>(in, tmp, first); }
             { LaunchScope ls(ctx, matrix ? "cols_inv_m3" : "cols_inv_std", nu);
-              ck.k<<<dim3(col_tiles, nu), ck.threads, col_smem, ctx->stream>>>(tmp, out, second); }
+              ck<<<dim3(col_tiles, nu), col_threads, col_smem, ctx->stream>>>(tmp, out, second); }
         }
     }
     CUDA_TRY(cudaGetLastError());

@@ -1,0 +1,30 @@
+"""The C++ host-side mirror (include/b200ring.hpp) over the C ABI: compile tests/cpp/ring_host_test.cpp
+against libb200ring.so.  CPU: constructor validation only.  GPU: KAT round trip, plugin path, fused product."""
+import os
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+import b200ring
+
+
+def _build(tmp_path):
+    b200ring.load_library()
+    exe = str(tmp_path / "ring_host_test")
+    lib = os.path.join(ROOT, "matrix-fhe-lattigo_b200", "lib")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "ring_host_test.cpp"), "-o", exe,
+                           "-L" + lib, "-lb200ring", "-Wl,-rpath," + lib])
+    return exe
+
+
+def test_cpp_host_mirror_builds_and_validates(tmp_path):
+    r = subprocess.run([_build(tmp_path), "--no-gpu"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_host_mirror_on_gpu(tmp_path):
+    r = subprocess.run([_build(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout + r.stderr

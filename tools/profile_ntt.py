@@ -1,0 +1,61 @@
+#!/usr/bin/env python3
+"""Small driver for ncu / sweeps: builds the headline ring, runs NTT+INTT a few times.
+
+    python tools/profile_ntt.py [--ring 3n|pow2] [--polys 32] [--iters 2] [--time]
+"""
+import argparse
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+import b200ring  # noqa: E402
+import bench  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--ring", default="3n")
+ap.add_argument("--polys", type=int, default=32)
+ap.add_argument("--limbs", type=int, default=24)
+ap.add_argument("--iters", type=int, default=2)
+ap.add_argument("--time", action="store_true")
+args = ap.parse_args()
+
+QI60 = [0x1fffffffffe00001, 0x1fffffffffc80001, 0x1fffffffffb40001, 0x1fffffffff500001,
+        0x1fffffffff380001, 0x1fffffffff000001, 0x1ffffffffef00001, 0x1ffffffffee80001,
+        0x1ffffffffeb40001, 0x1ffffffffe780001, 0x1ffffffffe600001, 0x1ffffffffe4c0001,
+        0x1ffffffffdf40001, 0x1ffffffffdac0001, 0x1ffffffffda40001, 0x1ffffffffc680001,
+        0x1ffffffffc000001, 0x1ffffffffb880001, 0x1ffffffffb7c0001, 0x1ffffffffb300001,
+        0x1ffffffffb1c0001, 0x1ffffffffadc0001, 0x1ffffffffa400001, 0x1ffffffffa140001]
+if args.ring == "3n":
+    N, moduli = bench.N, bench.MODULI[: args.limbs]
+else:
+    N, moduli = 1 << 16, QI60[: args.limbs]
+ring = b200ring.NewRing(N, moduli)
+ring.SetStream(torch.cuda.current_stream().cuda_stream)
+data = torch.empty((args.polys, len(moduli), N), dtype=torch.int64, device="cuda")
+for l, q in enumerate(moduli):
+    data[:, l, :] = torch.randint(0, q, (args.polys, N), dtype=torch.int64, device="cuda")
+poly = b200ring.Poly.from_torch(ring, data)
+ref = data.clone()
+for _ in range(args.iters):
+    ring.NTT(poly, poly)
+    ring.INTT(poly, poly)
+torch.cuda.synchronize()
+assert torch.equal(ref, data)
+if args.time:
+    for _ in range(3):
+        ring.NTT(poly, poly); ring.INTT(poly, poly)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    e0.record()
+    for _ in range(reps):
+        ring.NTT(poly, poly); ring.INTT(poly, poly)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    units = 2 * args.polys * len(moduli)
+    rate = units / (ms * 1e-3)
+    print("ring=%s polys=%d limbs=%d chunkMB=%s: %.3f ms/step  %.0f limb-transforms/s  %.1f%% of HBM roofline" % (
+        args.ring, args.polys, len(moduli), os.environ.get("B200_CHUNK_MB", "dflt"), ms, rate, 100 * rate * 2 * N * 8 / 6.553e12))
+    prof = ring.Profile(lambda: (ring.NTT(poly, poly), ring.INTT(poly, poly)))
+    print("   ", {k: round(v["ms"], 3) for k, v in prof.items()})
