@@ -26,28 +26,32 @@ def _deps():
     return max(os.path.getmtime(h) for h in hdr)
 
 
-def _compile(src, force, hdr_mtime):
+def _compile(src, force, hdr_mtime, tag="", defines=()):
     s = os.path.join(CSRC, src)
-    o = os.path.join(OBJ, src.replace(".cu", ".o"))
+    o = os.path.join(OBJ, src.replace(".cu", tag + ".o"))
     if not force and os.path.exists(o) and os.path.getmtime(o) >= max(os.path.getmtime(s), hdr_mtime):
         return o, False
-    subprocess.check_call([NVCC] + FLAGS + ["-c", s, "-o", o])
+    subprocess.check_call([NVCC] + FLAGS + ["-D" + d for d in defines] + ["-c", s, "-o", o])
     return o, True
 
 
-def build(force=False, verbose=True):
+def build(force=False, verbose=True, tag="", defines=()):
+    """tag/defines: build an A/B tuning variant lib/libb200ring<tag>.so (select it with B200RING_LIB)."""
     os.makedirs(OBJ, exist_ok=True)
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    lib = LIB.replace(".so", tag + ".so")
     hm = _deps()
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
-        res = list(ex.map(lambda s: _compile(s, force, hm), SOURCES))
+        res = list(ex.map(lambda s: _compile(s, force, hm, tag if s == "ntt_big.cu" else "", defines if s == "ntt_big.cu" else ()), SOURCES))
     objs = [o for o, _ in res]
-    if force or any(ch for _, ch in res) or not os.path.exists(LIB):
-        subprocess.check_call([NVCC, "-shared", "-o", LIB] + objs + ["-cudart", "static", "-ccbin", "g++"])
+    if force or any(ch for _, ch in res) or not os.path.exists(lib):
+        subprocess.check_call([NVCC, "-shared", "-o", lib] + objs + ["-cudart", "static", "-ccbin", "g++", "-Wno-deprecated-gpu-targets"])
         if verbose:
-            print("built", LIB)
-    return LIB
+            print("built", lib)
+    return lib
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv)
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    tags = [a[6:] for a in sys.argv[1:] if a.startswith("--tag=")]
+    build(force="--force" in sys.argv, tag=("_" + tags[0]) if tags else "", defines=defs)

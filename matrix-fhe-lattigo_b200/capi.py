@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libb200ring.so")
+LIB_PATH = os.environ.get("B200RING_LIB") or os.path.join(_HERE, "lib", "libb200ring.so")   # env: A/B tuning builds
 
 u64 = C.c_uint64
 P64 = C.POINTER(C.c_uint64)

@@ -188,7 +188,16 @@ extern "C" int b200_ctx_create(int ring_type, int N, int L, const uint64_t *modu
         int bl = 0;
         while (bl < 64 && ((s.q - 1) >> bl)) ++bl;
         s.mask = bl >= 64 ? ~0ULL : ((1ULL << bl) - 1);   // subring.go:94
-        consts[i] = LimbConst{s.q, s.qinv, s.brc[0], s.brc[1]};
+        {
+            // quotient estimate constants: xs = x >> sh has <= 32 bits for x < 16q; qs = q >> sh has <= 28 bits;
+            // mul = floor(2^32 / (qs + 1)) underestimates 2^(32+sh)/q by < 2^-26 relative.
+            int bl = 0;
+            while (bl < 64 && (s.q >> bl)) ++bl;
+            const unsigned sh = bl > 28 ? (unsigned)(bl - 28) : 0u;
+            const u64 qs = s.q >> sh;
+            const unsigned mul = (unsigned)((1ULL << 32) / (qs + 1));
+            consts[i] = LimbConst{s.q, s.qinv, s.brc[0], s.brc[1], sh, mul, 0};
+        }
         std::vector<tw_t> f(N), v(N);
         const u64 given = roots ? roots[i] : 0;
         if (ring_type == B200_RING_STANDARD) {

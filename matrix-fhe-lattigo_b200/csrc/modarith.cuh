@@ -15,6 +15,9 @@ struct LimbConst {
     u64 qinv;     // MRedConstant = q^-1 mod 2^64            (modular_reduction.go:68-75)
     u64 brc_hi;   // BRedConstant[0] = floor(2^128/q) >> 64   (modular_reduction.go:99-107)
     u64 brc_lo;   // BRedConstant[1]
+    unsigned canon_shift;   // quotient estimate for x < 16q:  k = ((x >> canon_shift) * canon_mul) >> 32
+    unsigned canon_mul;     //   with floor(x/q) - 1 <= k <= floor(x/q)   (not in the reference; see canon_est)
+    u64 pad_;
 };
 
 __device__ __forceinline__ u64 csub(u64 x, u64 m) { return x >= m ? x - m : x; }   // CRed :200-205
@@ -102,4 +105,21 @@ __device__ __forceinline__ u64 csub_fma(u64 x, u64 m, u64 nm) {
     const unsigned k = x >= m ? 1u : 0u;
     const u64 r = madwide_u32(k, lo32(nm), x);
     return ((u64)madlo_u32(k, hi32(nm), hi32(r)) << 32) | lo32(r);
+}
+
+// hi-word-only variant of csub_fma (2 ALU + 2 FMA): subtracts when hi32(x) > hi32(m).  The result is
+// < m + 2^32 for x < 2m + 2^32, which the lazy butterflies tolerate when 8q + 2^33 <= 2^64.
+__device__ __forceinline__ u64 csub_fma_hi(u64 x, u64 m, u64 nm) {
+    unsigned k;
+    asm("{\n\t.reg .pred p;\n\tsetp.gt.u32 p, %1, %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(k) : "r"(hi32(x)), "r"(hi32(m)));
+    const u64 r = madwide_u32(k, lo32(nm), x);
+    return ((u64)madlo_u32(k, hi32(nm), hi32(r)) << 32) | lo32(r);
+}
+// x < 16q  ->  [0, q) through a 32-bit quotient estimate (1 shift + 1 mul.hi + 2 multiply-adds) and one
+// conditional subtraction, instead of a chain of three or four conditional subtractions.
+__device__ __forceinline__ u64 canon_est(u64 x, u64 q, u64 nq, unsigned sh, unsigned mul) {
+    const unsigned k = __umulhi((unsigned)(x >> sh), mul);
+    const u64 r = madwide_u32(k, lo32(nq), x);
+    const u64 y = ((u64)madlo_u32(k, hi32(nq), hi32(r)) << 32) | lo32(r);
+    return csub_fma(y, q, nq);
 }

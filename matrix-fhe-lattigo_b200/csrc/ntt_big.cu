@@ -22,6 +22,28 @@
 
 #include "internal.hpp"
 
+// tuning knobs (compile-time; `build.py --tag=X -DKNOB=v` builds lib/libb200ring_X.so for A/B timing, selected with
+// B200RING_LIB).  Occupancy beats ILP on these kernels: the minBlocks values cap registers at 40-56 per thread
+// (measured on B200: +45% on the 3N path over letting ptxas use 80-120 registers).
+#ifndef B200_CSUB_HI
+#define B200_CSUB_HI 0      // 1: compare high words only in the lazy conditional subtraction
+#endif
+#ifndef B200_CANON_EST
+#define B200_CANON_EST 1    // 1: final canonical reduction through a quotient estimate
+#endif
+#ifndef B200_MINB_ROWS_M3
+#define B200_MINB_ROWS_M3 4
+#endif
+#ifndef B200_MINB_COLS_M3
+#define B200_MINB_COLS_M3 3
+#endif
+#ifndef B200_MINB_ROWS_STD
+#define B200_MINB_ROWS_STD 12
+#endif
+#ifndef B200_MINB_COLS_STD
+#define B200_MINB_COLS_STD 6
+#endif
+
 namespace {
 
 struct BigArgs {
@@ -46,24 +68,39 @@ __device__ __forceinline__ UnitRef unit_ref(const BigArgs &a) {
 // Per-prime constants of the lazy butterflies
 struct QC {
     u64 q, twoq, fourq, nq, nfourq;
-    __device__ __forceinline__ explicit QC(u64 q_) : q(q_), twoq(2 * q_), fourq(4 * q_), nq(0 - q_), nfourq(0 - 4 * q_) {}
+    unsigned csh, cmul;
+    __device__ __forceinline__ explicit QC(const LimbConst &l)
+        : q(l.q), twoq(2 * l.q), fourq(4 * l.q), nq(0 - l.q), nfourq(0 - 4 * l.q), csh(l.canon_shift), cmul(l.canon_mul) {}
 };
+__device__ __forceinline__ u64 csub4(u64 x, const QC &c) {
+#if B200_CSUB_HI
+    return csub_fma_hi(x, c.fourq, c.nfourq);
+#else
+    return csub_fma(x, c.fourq, c.nfourq);
+#endif
+}
 // Harvey butterflies on the approximate Shoup product (shoup4: [0,4q)).  q < 2^61 so 8q fits in 64 bits.
 //   forward (Cooley-Tukey):   in [0,8q) -> out [0,8q)
 //   inverse (Gentleman-Sande): in [0,4q) -> out [0,4q)
 __device__ __forceinline__ void bf_fwd(u64 &U, u64 &V, const tw_t w, const QC &c) {
-    const u64 u = csub_fma(U, c.fourq, c.nfourq);
+    const u64 u = csub4(U, c);
     const u64 t = shoup4(V, w.x, w.y, c.nq);
     U = u + t;
     V = u - t + c.fourq;
 }
 __device__ __forceinline__ void bf_inv(u64 &U, u64 &V, const tw_t w, const QC &c) {
     const u64 s = U + V, d = U - V + c.fourq;
-    U = csub_fma(s, c.fourq, c.nfourq);
+    U = csub4(s, c);
     V = shoup4(d, w.x, w.y, c.nq);
 }
 // [0,8q) -> [0,q) and [0,4q) -> [0,2q)
-__device__ __forceinline__ u64 canon8(u64 x, const QC &c) { return csub(csub(csub(x, c.fourq), c.twoq), c.q); }
+__device__ __forceinline__ u64 canon8(u64 x, const QC &c) {
+#if B200_CANON_EST
+    return canon_est(x, c.q, c.nq, c.csh, c.cmul);
+#else
+    return csub(csub(csub(csub(x, c.fourq), c.twoq), c.q), c.q);
+#endif
+}
 __device__ __forceinline__ u64 to2q(u64 x, const QC &c) { return csub(x, c.twoq); }
 
 // 2^LOGM-point sub-transform held in registers; x[k] ordered along the sub-dimension (MSB first);
@@ -126,14 +163,14 @@ __device__ __forceinline__ int row_of(const BigArgs &a, int tile, int w, int &ro
 }
 
 template <bool MATRIX, int VT>   // warps per CTA: MATRIX 6*VT, STANDARD VT
-__global__ void __launch_bounds__((MATRIX ? 6 : 1) * VT * 32)
+__global__ void __launch_bounds__((MATRIX ? 6 : 1) * VT * 32, MATRIX ? B200_MINB_ROWS_M3 : B200_MINB_ROWS_STD)
 k_rows_fwd(const u64 *in, u64 *out, BigArgs a) {
     constexpr int WARPS = (MATRIX ? 6 : 1) * VT, RUN = 6 * VT;
     extern __shared__ __align__(16) u64 sm[];
     const UnitRef ur = unit_ref(a);
     const int limb = ur.limb;
     const u64 q = a.consts[limb].q, twoq = 2 * q;
-    const QC qc(q);
+    const QC qc(a.consts[limb]);
     const tw_t *__restrict__ tw = a.fwd + (size_t)limb * a.N;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     int rowcode;
@@ -179,22 +216,23 @@ k_rows_fwd(const u64 *in, u64 *out, BigArgs a) {
         __syncthreads();
         const size_t run = (size_t)6 << a.logU;                       // 6U words between consecutive rev8(c)
         u64 *dst = out + ur.out + (size_t)blockIdx.x * RUN;
-        for (int o = threadIdx.x; o < 256 * RUN; o += WARPS * 32) {
-            const int cr = o / RUN, rem = o - cr * RUN;
-            dst[(size_t)cr * run + rem] = sm[cr * (RUN + 1) + rem];
+        {   // WARPS*32 = 32*RUN threads: thread -> (cr0, rem) once, then cr advances by 32 per step
+            const int cr0 = threadIdx.x / RUN, rem = threadIdx.x - cr0 * RUN;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dst[(size_t)(cr0 + 32 * i) * run + rem] = sm[(cr0 + 32 * i) * (RUN + 1) + rem];
         }
     }
 }
 
 template <bool MATRIX, int VT>
-__global__ void __launch_bounds__((MATRIX ? 6 : 1) * VT * 32)
+__global__ void __launch_bounds__((MATRIX ? 6 : 1) * VT * 32, MATRIX ? B200_MINB_ROWS_M3 : B200_MINB_ROWS_STD)
 k_rows_inv(const u64 *in, u64 *out, BigArgs a) {
     constexpr int WARPS = (MATRIX ? 6 : 1) * VT, RUN = 6 * VT;
     extern __shared__ __align__(16) u64 sm[];
     const UnitRef ur = unit_ref(a);
     const int limb = ur.limb;
     const u64 q = a.consts[limb].q, twoq = 2 * q;
-    const QC qc(q);
+    const QC qc(a.consts[limb]);
     const tw_t *__restrict__ tw = a.inv + (size_t)limb * a.N;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     int rowcode;
@@ -208,9 +246,13 @@ k_rows_inv(const u64 *in, u64 *out, BigArgs a) {
     } else {
         const size_t run = (size_t)6 << a.logU;
         const u64 *src = in + ur.in + (size_t)blockIdx.x * RUN;
-        for (int o = threadIdx.x; o < 256 * RUN; o += WARPS * 32) {
-            const int cr = o / RUN, rem = o - cr * RUN;
-            sm[cr * (RUN + 1) + rem] = src[(size_t)cr * run + rem];
+        {
+            const int cr0 = threadIdx.x / RUN, rem = threadIdx.x - cr0 * RUN;
+            u64 v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = src[(size_t)(cr0 + 32 * i) * run + rem];     // all 8 loads in flight
+#pragma unroll
+            for (int i = 0; i < 8; ++i) sm[(cr0 + 32 * i) * (RUN + 1) + rem] = v[i];
         }
         __syncthreads();
         const int rl = (int)rev_bits((unsigned)lane, 5);
@@ -253,14 +295,14 @@ __device__ __forceinline__ int pc(int i) { return i + ((i >> 6) << 3); }
 
 // STANDARD, log2(N) = 16: 256 rows, layers on row bits [7..5] [4..2] [1..0]
 template <int CW>
-__global__ void __launch_bounds__(CW * 32)
+__global__ void __launch_bounds__(CW * 32, B200_MINB_COLS_STD)
 k_cols_fwd_std16(const u64 *in, u64 *out, BigArgs a) {
     extern __shared__ __align__(16) u64 sm[];
     const UnitRef ur = unit_ref(a);
     const int limb = ur.limb;
     const size_t ibase = ur.in + (size_t)blockIdx.x * CW, obase = ur.out + (size_t)blockIdx.x * CW;
     const u64 q = a.consts[limb].q, twoq = 2 * q;
-    const QC qc(q);
+    const QC qc(a.consts[limb]);
     const tw_t *__restrict__ tw = a.fwd + (size_t)limb * a.N;
     const int t = threadIdx.x, c = t % CW, g = t / CW;   // g in [0,32)
     u64 x[8];
@@ -291,14 +333,14 @@ k_cols_fwd_std16(const u64 *in, u64 *out, BigArgs a) {
 }
 
 template <int CW>
-__global__ void __launch_bounds__(CW * 32)
+__global__ void __launch_bounds__(CW * 32, B200_MINB_COLS_STD)
 k_cols_inv_std16(const u64 *in, u64 *out, BigArgs a) {
     extern __shared__ __align__(16) u64 sm[];
     const UnitRef ur = unit_ref(a);
     const int limb = ur.limb;
     const size_t ibase = ur.in + (size_t)blockIdx.x * CW, obase = ur.out + (size_t)blockIdx.x * CW;
     const u64 q = a.consts[limb].q, twoq = 2 * q;
-    const QC qc(q);
+    const QC qc(a.consts[limb]);
     const tw_t *__restrict__ tw = a.inv + (size_t)limb * a.N;
     const tw_t ninv = a.misc[limb * MISC_COUNT + MISC_NINV], ninv_w1 = a.misc[limb * MISC_COUNT + MISC_NINV_W1];
     const bool lazy = a.flags & B200_LAZY;
@@ -343,14 +385,14 @@ k_cols_inv_std16(const u64 *in, u64 *out, BigArgs a) {
 //   G2:  8 words  (u bits 4..2): radix-2 layers 1..3                          -- CW*48 threads
 //   G3:  8 words  (u bits 2..0, two 4-groups): radix-2 layers 4, 5            -- CW*48 threads
 template <int CW>
-__global__ void __launch_bounds__(CW * 48)
+__global__ void __launch_bounds__(CW * 48, B200_MINB_COLS_M3)
 k_cols_fwd_m3_15(const u64 *in, u64 *out, BigArgs a) {
     extern __shared__ __align__(16) u64 sm[];
     const UnitRef ur = unit_ref(a);
     const int limb = ur.limb;
     const size_t ibase = ur.in + (size_t)blockIdx.x * CW, obase = ur.out + (size_t)blockIdx.x * CW;
     const u64 q = a.consts[limb].q, twoq = 2 * q, fourq = 4 * q;
-    const QC qc(q);
+    const QC qc(a.consts[limb]);
     const tw_t *__restrict__ tw = a.fwd + (size_t)limb * a.N;
     const tw_t om = a.misc[limb * MISC_COUNT + MISC_OMEGA3];
     const int t = threadIdx.x, c = t % CW, g = t / CW;   // g in [0,48)
@@ -414,14 +456,14 @@ k_cols_fwd_m3_15(const u64 *in, u64 *out, BigArgs a) {
 }
 
 template <int CW>
-__global__ void __launch_bounds__(CW * 48)
+__global__ void __launch_bounds__(CW * 48, B200_MINB_COLS_M3)
 k_cols_inv_m3_15(const u64 *in, u64 *out, BigArgs a) {
     extern __shared__ __align__(16) u64 sm[];
     const UnitRef ur = unit_ref(a);
     const int limb = ur.limb;
     const size_t ibase = ur.in + (size_t)blockIdx.x * CW, obase = ur.out + (size_t)blockIdx.x * CW;
     const u64 q = a.consts[limb].q, twoq = 2 * q, fourq = 4 * q;
-    const QC qc(q);
+    const QC qc(a.consts[limb]);
     const tw_t *__restrict__ tw = a.inv + (size_t)limb * a.N;
     const tw_t *mc = a.misc + limb * MISC_COUNT;
     const bool lazy = a.flags & B200_LAZY;
