@@ -53,7 +53,7 @@ class ClockSampler:
     def __init__(self, gpu_index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "10"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -138,6 +138,32 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+def run_e2e(args, ring, data, polys, Ll, world, units_per_step, barrier, dev):
+    import torch
+    import b200ring
+    from b200ring import sharding
+    e2e_steps = max(1, min(args.steps, 3))
+    host_in = torch.empty((polys, Ll, N), dtype=torch.int64).pin_memory()
+    host_out = torch.empty((polys, Ll, N), dtype=torch.int64).pin_memory()
+    host_in.copy_(data.cpu())
+    nwords = polys * Ll * N
+
+    def e2e_step():   # the public host-buffer call: chunked H2D -> NTT -> INTT -> D2H, copies overlapped with compute
+        ring.TransformHost(host_in, host_out, ["NTT", "INTT"])
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = sharding.max_over_ranks(time.perf_counter() - t0, device=dev)
+    assert torch.equal(host_out, host_in), "e2e round trip mismatch"
+    return {"value": world * e2e_steps * units_per_step / e2e_s, "unit": UNIT, "h2d_bytes_per_step": nwords * 8,
+           "d2h_bytes_per_step": nwords * 8, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps}
+
+
+
 def run_gpu(args):
     import numpy as np
     import torch
@@ -225,29 +251,10 @@ def run_gpu(args):
             "note": "whole transform (both passes) against 16*N algorithmic bytes per limb-transform"}
 
     # end to end through the C ABI with HOST buffers: pinned H2D + NTT + INTT + D2H inside the timed region
-    e2e_steps = max(1, min(args.steps, 3))
-    host_in = torch.empty((polys, Ll, N), dtype=torch.int64).pin_memory()
-    host_out = torch.empty((polys, Ll, N), dtype=torch.int64).pin_memory()
-    host_in.copy_(data.cpu())
-    dpoly = ring.NewPoly(polys)
+    e2e = None
     nwords = polys * Ll * N
-
-    def e2e_step():
-        b200ring.capi.check(b200ring.lib().b200_poly_upload(dpoly.h, host_in.data_ptr(), nwords))
-        ring.NTT(dpoly, dpoly)
-        ring.INTT(dpoly, dpoly)
-        b200ring.capi.check(b200ring.lib().b200_poly_download(dpoly.h, host_out.data_ptr(), nwords))
-
-    e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    barrier()
-    e2e_s = sharding.max_over_ranks(time.perf_counter() - t0, device=dev)
-    assert torch.equal(host_out, host_in), "e2e round trip mismatch"
-    e2e = {"value": world * e2e_steps * units_per_step / e2e_s, "unit": UNIT, "h2d_bytes_per_step": nwords * 8,
-           "d2h_bytes_per_step": nwords * 8, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps}
+    if not args.no_e2e:
+        e2e = run_e2e(args, ring, data, polys, Ll, world, units_per_step, barrier, dev)
 
     if rank == 0:
         cpu = None
@@ -278,6 +285,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (ncu runs)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

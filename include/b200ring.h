@@ -158,6 +158,15 @@ B200_API int b200_vec_op(b200_ctx *ctx, int op, const b200_poly *p1, const b200_
  * canonical.  a, b are left untouched unless they alias c. */
 B200_API int b200_polymul(b200_ctx *ctx, const b200_poly *a, const b200_poly *b, b200_poly *c, int level);
 
+/* ---- host-buffer transforms (a caller without device-resident polynomials) ----------------------
+ * Applies ops[0..n_ops) in order (0 = Ring.NTT, 1 = Ring.INTT, ring/ntt.go:127-152) to `batch` polynomials
+ * held in HOST memory as [batch][L][N] words and writes the result to host_out (may equal host_in).  The
+ * batch is streamed through the GPU in chunks with the H2D copy, the kernels and the D2H copy of
+ * successive chunks overlapped on three streams; pinned host memory gives the full PCIe rate.
+ * Synchronous: the result is in host_out on return. */
+B200_API int b200_transform_host(b200_ctx *ctx, const uint64_t *host_in, uint64_t *host_out, int batch, int level,
+                        const int *ops, int n_ops, int flags);
+
 /* ---- plugin granularity: ring.NumberTheoreticTransformer (ring/ntt.go:15-22) -----------------
  * One limb, HOST slices in and out (upload -> transform -> download, synchronous).  This is what a
  * NewRingWithCustomNTT factory (ring/ring.go:314) binds; it is correct but not the fast path. */

@@ -1,6 +1,7 @@
 // b200ring.cu -- the C ABI of include/b200ring.h: context creation (per-prime constants and twiddle
 // tables, bit-identical to the reference's ring/subring.go:129-214), device polynomial management and
 // dispatch to the sm_100a kernels.  No CPU fallback: every compute entry point needs a CUDA device.
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <set>
@@ -32,9 +33,14 @@ extern "C" int b200_device_count(void) {
     return n;
 }
 
+static thread_local cudaStream_t tl_stream = nullptr;
+static thread_local bool tl_stream_on = false;
+cudaStream_t b200_cur_stream(b200_ctx *ctx) { return tl_stream_on ? tl_stream : ctx->stream; }
+void b200_set_stream_override(cudaStream_t s, bool active) { tl_stream = s; tl_stream_on = active; }
+
 int b200_ensure_scratch(b200_ctx *ctx, size_t words) {
     if (ctx->scratch_words >= words) return 0;
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(b200_cur_stream(ctx)));
     if (ctx->d_scratch) CUDA_TRY(cudaFree(ctx->d_scratch));
     ctx->d_scratch = nullptr;
     ctx->scratch_words = 0;
@@ -258,6 +264,13 @@ extern "C" void b200_ctx_destroy(b200_ctx *ctx) {
     big_tables_destroy(ctx);
     cudaFree(ctx->d_consts); cudaFree(ctx->d_fwd); cudaFree(ctx->d_inv); cudaFree(ctx->d_misc);
     cudaFree(ctx->d_go2fast); cudaFree(ctx->d_scratch);
+    if (ctx->pipe.ready) {
+        for (int i = 0; i < b200_ctx::HostPipe::NB; ++i) {
+            cudaFree(ctx->pipe.buf[i]);
+            cudaEventDestroy(ctx->pipe.up[i]); cudaEventDestroy(ctx->pipe.done[i]); cudaEventDestroy(ctx->pipe.freed[i]);
+        }
+        cudaStreamDestroy(ctx->pipe.h2d); cudaStreamDestroy(ctx->pipe.comp); cudaStreamDestroy(ctx->pipe.d2h);
+    }
     delete ctx;
 }
 extern "C" int b200_ctx_set_stream(b200_ctx *ctx, void *s) {
@@ -478,6 +491,77 @@ extern "C" int b200_polymul(b200_ctx *ctx, const b200_poly *a, const b200_poly *
     if ((rc = ntt(b->d, tb, false))) return rc;
     if ((rc = launch_vec_op(ctx, B200_OP_MUL_BARRETT, ta, tb, ta, sp, nullptr))) return rc;
     return ntt(ta, c->d, true);
+}
+
+// ---- pipelined host-buffer transforms ---------------------------------------------------------------------
+// The call a caller WITHOUT device-resident polynomials makes: the batch streams through the GPU in chunks,
+// H2D copy -> transforms -> D2H copy on three streams so that both PCIe directions and the SMs overlap.
+extern "C" int b200_transform_host(b200_ctx *ctx, const uint64_t *host_in, uint64_t *host_out, int batch, int level,
+                                   const int *ops, int n_ops, int flags) {
+    if (!ctx || !host_in || !host_out || !ops) return fail(B200_EINVAL, "b200_transform_host: NULL argument");
+    if (batch <= 0 || n_ops <= 0) return fail(B200_EINVAL, "b200_transform_host: empty batch or op list");
+    if (level < 0 || level >= ctx->L) return fail(B200_ESHAPE, "b200_transform_host: level out of range");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    typedef b200_ctx::HostPipe Pipe;
+    Pipe &p = ctx->pipe;
+    const size_t poly_words = (size_t)ctx->L * ctx->N;
+    // chunk = as many polynomials as fit ~128 MiB (at least 1): big enough for PCIe efficiency, small enough to overlap
+    int cpolys = (int)std::max<size_t>(1, ((size_t)128 << 20) / (poly_words * sizeof(u64)));
+    cpolys = std::min(cpolys, batch);
+    if (!p.ready) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&p.h2d, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&p.comp, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&p.d2h, cudaStreamNonBlocking));
+        for (int i = 0; i < Pipe::NB; ++i) {
+            CUDA_TRY(cudaEventCreateWithFlags(&p.up[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&p.done[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&p.freed[i], cudaEventDisableTiming));
+        }
+        p.ready = true;
+    }
+    if (p.buf_words < (size_t)cpolys * poly_words) {
+        CUDA_TRY(cudaDeviceSynchronize());
+        for (int i = 0; i < Pipe::NB; ++i) {
+            if (p.buf[i]) CUDA_TRY(cudaFree(p.buf[i]));
+            p.buf[i] = nullptr;
+            CUDA_TRY(cudaMalloc(&p.buf[i], (size_t)cpolys * poly_words * sizeof(u64)));
+        }
+        p.buf_words = (size_t)cpolys * poly_words;
+    }
+    int rc = 0;
+    b200_set_stream_override(p.comp, true);
+    // scratch for the slot permutation of MATRIX rings is sized once, before any work is in flight
+    if (ctx->ring_type == B200_RING_MATRIX && !(flags & B200_TREE_ORDER))
+        rc = b200_ensure_scratch(ctx, (size_t)cpolys * poly_words);
+    int nchunks = (batch + cpolys - 1) / cpolys;
+    for (int c = 0; c < nchunks && rc == 0; ++c) {
+        const int b0 = c * cpolys, nb = std::min(cpolys, batch - b0), s = c % Pipe::NB;
+        const size_t words = (size_t)nb * poly_words;
+        cudaError_t e = cudaSuccess;
+        if (c >= Pipe::NB) e = cudaStreamWaitEvent(p.h2d, p.freed[s], 0);          // staging buffer drained
+        if (e == cudaSuccess) e = cudaMemcpyAsync(p.buf[s], host_in + (size_t)b0 * poly_words, words * sizeof(u64), cudaMemcpyHostToDevice, p.h2d);
+        if (e == cudaSuccess) e = cudaEventRecord(p.up[s], p.h2d);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(p.comp, p.up[s], 0);
+        if (e != cudaSuccess) { rc = b200_cuda_fail(e, "b200_transform_host upload"); break; }
+        Span sp{nb, level + 1, ctx->L, 0};
+        for (int o = 0; o < n_ops && rc == 0; ++o) {
+            const bool inv = ops[o] != 0;
+            rc = launch_ntt_big(ctx, p.buf[s], p.buf[s], sp, inv, flags);
+            if (rc == 1) rc = launch_ntt_generic(ctx, p.buf[s], p.buf[s], sp, inv, flags);
+        }
+        if (rc) break;
+        e = cudaEventRecord(p.done[s], p.comp);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(p.d2h, p.done[s], 0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(host_out + (size_t)b0 * poly_words, p.buf[s], words * sizeof(u64), cudaMemcpyDeviceToHost, p.d2h);
+        if (e == cudaSuccess) e = cudaEventRecord(p.freed[s], p.d2h);
+        if (e != cudaSuccess) { rc = b200_cuda_fail(e, "b200_transform_host download"); break; }
+    }
+    b200_set_stream_override(nullptr, false);
+    cudaError_t e = cudaStreamSynchronize(p.d2h);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(p.comp);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(p.h2d);
+    if (rc == 0 && e != cudaSuccess) rc = b200_cuda_fail(e, "b200_transform_host sync");
+    return rc;
 }
 
 extern "C" int b200_subring_ntt_host(b200_ctx *ctx, int limb, const uint64_t *p1, uint64_t *p2, size_t n, int inverse, int flags) {

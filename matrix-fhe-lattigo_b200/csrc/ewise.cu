@@ -84,7 +84,7 @@ int run(b200_ctx *ctx, const u64 *p1, const u64 *p2, u64 *p3, Span sp, const u64
     for (int u0 = 0; u0 < units; u0 += 65535) {
         int nu = units - u0 < 65535 ? units - u0 : 65535;
         LaunchScope ls(ctx, "vec_op", nu);
-        k_vec_op<OP><<<dim3(chunks, nu), 256, 0, ctx->stream>>>(p1, p2, p3, ctx->d_consts, d_scalars, N, sp, u0);
+        k_vec_op<OP><<<dim3(chunks, nu), 256, 0, b200_cur_stream(ctx)>>>(p1, p2, p3, ctx->d_consts, d_scalars, N, sp, u0);
     }
     CUDA_TRY(cudaGetLastError());
     return 0;

@@ -46,6 +46,15 @@ struct b200_ctx {
     std::vector<ProfRec> prof;
     // optimised-path tables (ntt_big.cu); null when the ring shape is not covered
     void *big = nullptr;
+    // pipelined host-buffer path (b200_transform_host): copy/compute streams, events and staging buffers
+    struct HostPipe {
+        cudaStream_t h2d = nullptr, comp = nullptr, d2h = nullptr;
+        static constexpr int NB = 3;
+        u64 *buf[NB] = {nullptr, nullptr, nullptr};
+        size_t buf_words = 0;
+        cudaEvent_t up[NB], done[NB], freed[NB];
+        bool ready = false;
+    } pipe;
 };
 
 struct b200_poly {
@@ -64,6 +73,10 @@ int b200_cuda_fail(cudaError_t e, const char *what);
     } while (0)
 
 int b200_ensure_scratch(b200_ctx *ctx, size_t words);
+// the stream launchers enqueue on: the context's stream, or a per-thread override used by the pipelined
+// host-buffer entry point (b200_transform_host) while it drives its own compute stream
+cudaStream_t b200_cur_stream(b200_ctx *ctx);
+void b200_set_stream_override(cudaStream_t s, bool active);
 
 // RAII bracket around one kernel launch: counts it and, when profiling, times it with CUDA events
 struct LaunchScope {
@@ -75,13 +88,13 @@ struct LaunchScope {
             b200_ctx::ProfRec r{name, nullptr, nullptr, units};
             cudaEventCreate(&r.e0);
             cudaEventCreate(&r.e1);
-            cudaEventRecord(r.e0, c->stream);
+            cudaEventRecord(r.e0, b200_cur_stream(c));
             c->prof.push_back(r);
             idx = (int)c->prof.size() - 1;
         }
     }
     ~LaunchScope() {
-        if (idx >= 0) cudaEventRecord(c->prof[idx].e1, c->stream);
+        if (idx >= 0) cudaEventRecord(c->prof[idx].e1, b200_cur_stream(c));
     }
 };
 

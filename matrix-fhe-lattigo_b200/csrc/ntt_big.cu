@@ -28,6 +28,9 @@
 #ifndef B200_CSUB_HI
 #define B200_CSUB_HI 0      // 1: compare high words only in the lazy conditional subtraction
 #endif
+#ifndef B200_CSUB_ALU
+#define B200_CSUB_ALU 0     // 1: plain compare/select/subtract on the ALU pipe instead of the multiply-add form
+#endif
 #ifndef B200_CANON_EST
 #define B200_CANON_EST 1    // 1: final canonical reduction through a quotient estimate
 #endif
@@ -57,11 +60,14 @@ struct BigArgs {
 
 // word offsets of this CTA's unit in the input and output buffers, and its prime
 struct UnitRef { size_t in, out; int limb; };
+// Units are numbered LIMB-MAJOR (unit = limb*batch + poly) and sit on blockIdx.x, the tile on blockIdx.y:
+// CTAs that are scheduled together work on the same tile of the same prime for consecutive polynomials,
+// so they share one small set of twiddles (L1/L2 hits) instead of spreading over all L tables.
 __device__ __forceinline__ UnitRef unit_ref(const BigArgs &a) {
-    const int unit = a.unit0 + blockIdx.y;
-    const int l = unit % a.sp.nl;
-    const size_t layout = ((size_t)(unit / a.sp.nl) * a.sp.Lbuf + l) * (size_t)a.N;
-    const size_t dense = (size_t)blockIdx.y * (size_t)a.N;
+    const int unit = a.unit0 + blockIdx.x;
+    const int l = unit / a.sp.batch, b = unit - l * a.sp.batch;
+    const size_t layout = ((size_t)b * a.sp.Lbuf + l) * (size_t)a.N;
+    const size_t dense = (size_t)blockIdx.x * (size_t)a.N;
     return {a.in_dense ? dense : layout, a.out_dense ? dense : layout, a.sp.limb0 + l};
 }
 
@@ -75,6 +81,8 @@ struct QC {
 __device__ __forceinline__ u64 csub4(u64 x, const QC &c) {
 #if B200_CSUB_HI
     return csub_fma_hi(x, c.fourq, c.nfourq);
+#elif B200_CSUB_ALU
+    return csub(x, c.fourq);
 #else
     return csub_fma(x, c.fourq, c.nfourq);
 #endif
@@ -174,7 +182,7 @@ k_rows_fwd(const u64 *in, u64 *out, BigArgs a) {
     const tw_t *__restrict__ tw = a.fwd + (size_t)limb * a.N;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     int rowcode;
-    const int r = row_of<MATRIX, VT>(a, blockIdx.x, w, rowcode);
+    const int r = row_of<MATRIX, VT>(a, blockIdx.y, w, rowcode);
     u64 *buf = sm + w * WROW;
     const u64 *src = in + ur.in + (size_t)r * 256;
     u64 x[8];
@@ -215,7 +223,7 @@ k_rows_fwd(const u64 *in, u64 *out, BigArgs a) {
         for (int k = 0; k < 8; ++k) sm[((int)rev_bits((unsigned)k, 3) * 32 + rl) * (RUN + 1) + rowcode] = x[k];
         __syncthreads();
         const size_t run = (size_t)6 << a.logU;                       // 6U words between consecutive rev8(c)
-        u64 *dst = out + ur.out + (size_t)blockIdx.x * RUN;
+        u64 *dst = out + ur.out + (size_t)blockIdx.y * RUN;
         {   // WARPS*32 = 32*RUN threads: thread -> (cr0, rem) once, then cr advances by 32 per step
             const int cr0 = threadIdx.x / RUN, rem = threadIdx.x - cr0 * RUN;
 #pragma unroll
@@ -236,7 +244,7 @@ k_rows_inv(const u64 *in, u64 *out, BigArgs a) {
     const tw_t *__restrict__ tw = a.inv + (size_t)limb * a.N;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     int rowcode;
-    const int r = row_of<MATRIX, VT>(a, blockIdx.x, w, rowcode);
+    const int r = row_of<MATRIX, VT>(a, blockIdx.y, w, rowcode);
     u64 *buf = sm + w * WROW;
     u64 x[8];
     if (!MATRIX || (a.flags & B200_TREE_ORDER)) {
@@ -245,7 +253,7 @@ k_rows_inv(const u64 *in, u64 *out, BigArgs a) {
         ldg256(src + 4, x[4], x[5], x[6], x[7]);
     } else {
         const size_t run = (size_t)6 << a.logU;
-        const u64 *src = in + ur.in + (size_t)blockIdx.x * RUN;
+        const u64 *src = in + ur.in + (size_t)blockIdx.y * RUN;
         {
             const int cr0 = threadIdx.x / RUN, rem = threadIdx.x - cr0 * RUN;
             u64 v[8];
@@ -300,7 +308,7 @@ k_cols_fwd_std16(const u64 *in, u64 *out, BigArgs a) {
     extern __shared__ __align__(16) u64 sm[];
     const UnitRef ur = unit_ref(a);
     const int limb = ur.limb;
-    const size_t ibase = ur.in + (size_t)blockIdx.x * CW, obase = ur.out + (size_t)blockIdx.x * CW;
+    const size_t ibase = ur.in + (size_t)blockIdx.y * CW, obase = ur.out + (size_t)blockIdx.y * CW;
     const u64 q = a.consts[limb].q, twoq = 2 * q;
     const QC qc(a.consts[limb]);
     const tw_t *__restrict__ tw = a.fwd + (size_t)limb * a.N;
@@ -338,7 +346,7 @@ k_cols_inv_std16(const u64 *in, u64 *out, BigArgs a) {
     extern __shared__ __align__(16) u64 sm[];
     const UnitRef ur = unit_ref(a);
     const int limb = ur.limb;
-    const size_t ibase = ur.in + (size_t)blockIdx.x * CW, obase = ur.out + (size_t)blockIdx.x * CW;
+    const size_t ibase = ur.in + (size_t)blockIdx.y * CW, obase = ur.out + (size_t)blockIdx.y * CW;
     const u64 q = a.consts[limb].q, twoq = 2 * q;
     const QC qc(a.consts[limb]);
     const tw_t *__restrict__ tw = a.inv + (size_t)limb * a.N;
@@ -390,7 +398,7 @@ k_cols_fwd_m3_15(const u64 *in, u64 *out, BigArgs a) {
     extern __shared__ __align__(16) u64 sm[];
     const UnitRef ur = unit_ref(a);
     const int limb = ur.limb;
-    const size_t ibase = ur.in + (size_t)blockIdx.x * CW, obase = ur.out + (size_t)blockIdx.x * CW;
+    const size_t ibase = ur.in + (size_t)blockIdx.y * CW, obase = ur.out + (size_t)blockIdx.y * CW;
     const u64 q = a.consts[limb].q, twoq = 2 * q, fourq = 4 * q;
     const QC qc(a.consts[limb]);
     const tw_t *__restrict__ tw = a.fwd + (size_t)limb * a.N;
@@ -461,7 +469,7 @@ k_cols_inv_m3_15(const u64 *in, u64 *out, BigArgs a) {
     extern __shared__ __align__(16) u64 sm[];
     const UnitRef ur = unit_ref(a);
     const int limb = ur.limb;
-    const size_t ibase = ur.in + (size_t)blockIdx.x * CW, obase = ur.out + (size_t)blockIdx.x * CW;
+    const size_t ibase = ur.in + (size_t)blockIdx.y * CW, obase = ur.out + (size_t)blockIdx.y * CW;
     const u64 q = a.consts[limb].q, twoq = 2 * q, fourq = 4 * q;
     const QC qc(a.consts[limb]);
     const tw_t *__restrict__ tw = a.inv + (size_t)limb * a.N;
@@ -596,7 +604,7 @@ int launch_ntt_big(b200_ctx *ctx, const u64 *in, u64 *out, Span sp, bool inverse
     if (int rc = set_smem(ck, col_smem)) return rc;
     if (int rc = set_smem(rk, row_smem)) return rc;
     const int units = sp.batch * sp.nl;
-    const int chunk = (int)std::min<size_t>(std::min<size_t>(plan->chunk_units, 65535), (size_t)units);
+    const int chunk = (int)std::min<size_t>(plan->chunk_units, (size_t)units);
     u64 *tmp = out;
     // a slot permutation makes the row pass write rows other CTAs still have to read: go through a buffer
     const bool dense = permute && (!inverse || in == out);
@@ -613,14 +621,14 @@ int launch_ntt_big(b200_ctx *ctx, const u64 *in, u64 *out, Span sp, bool inverse
         second.in_dense = dense;
         if (!inverse) {
             { LaunchScope ls(ctx, matrix ? "cols_fwd_m3" : "cols_fwd_std", nu);
-              ck<<<dim3(col_tiles, nu), col_threads, col_smem, ctx->stream>>>(in, tmp, first); }
+              ck<<<dim3(nu, col_tiles), col_threads, col_smem, b200_cur_stream(ctx)>>>(in, tmp, first); }
             { LaunchScope ls(ctx, matrix ? "rows_fwd_m3" : "rows_fwd_std", nu);
-              rk<<<dim3(row_tiles, nu), row_warps * 32, row_smem, ctx->stream>>>(tmp, out, second); }
+              rk<<<dim3(nu, row_tiles), row_warps * 32, row_smem, b200_cur_stream(ctx)>>>(tmp, out, second); }
         } else {
             { LaunchScope ls(ctx, matrix ? "rows_inv_m3" : "rows_inv_std", nu);
-              rk<<<dim3(row_tiles, nu), row_warps * 32, row_smem, ctx->stream>>>(in, tmp, first); }
+              rk<<<dim3(nu, row_tiles), row_warps * 32, row_smem, b200_cur_stream(ctx)>>>(in, tmp, first); }
             { LaunchScope ls(ctx, matrix ? "cols_inv_m3" : "cols_inv_std", nu);
-              ck<<<dim3(col_tiles, nu), col_threads, col_smem, ctx->stream>>>(tmp, out, second); }
+              ck<<<dim3(nu, col_tiles), col_threads, col_smem, b200_cur_stream(ctx)>>>(tmp, out, second); }
         }
     }
     CUDA_TRY(cudaGetLastError());

@@ -275,7 +275,7 @@ int launch_ntt_generic(b200_ctx *ctx, const u64 *in, u64 *out, Span sp, bool inv
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         {
             LaunchScope ls(ctx, inverse ? "resident_inv" : "resident_fwd", units);
-            kern<<<units, threads, smem, ctx->stream>>>(in, out, ctx->d_consts, ctx->d_fwd, ctx->d_inv, ctx->d_misc,
+            kern<<<units, threads, smem, b200_cur_stream(ctx)>>>(in, out, ctx->d_consts, ctx->d_fwd, ctx->d_inv, ctx->d_misc,
                                                         ctx->d_go2fast, s, ctx->ring_type, flags);
         }
         CUDA_TRY(cudaGetLastError());
@@ -295,14 +295,14 @@ int launch_ntt_generic(b200_ctx *ctx, const u64 *in, u64 *out, Span sp, bool inv
     auto move = [&](const u64 *src, u64 *dst, int mode, int perm) {
         for_units([&](int u0, int nu) {
             LaunchScope ls(ctx, "layered_move", nu);
-            k_ntt_move<<<dim3(chunks, nu), 256, 0, ctx->stream>>>(src, dst, ctx->d_consts, ctx->d_go2fast, s, mode, perm, lazy, u0);
+            k_ntt_move<<<dim3(chunks, nu), 256, 0, b200_cur_stream(ctx)>>>(src, dst, ctx->d_consts, ctx->d_go2fast, s, mode, perm, lazy, u0);
         });
     };
     auto layer = [&](int kind, int p0, int p1) {
         LayerArgs la{kind, p0, p1};
         for_units([&](int u0, int nu) {
             LaunchScope ls(ctx, "layered_layer", nu);
-            k_ntt_layer<<<dim3(chunks, nu), 256, 0, ctx->stream>>>(work, ctx->d_consts, ctx->d_fwd, ctx->d_inv, ctx->d_misc, s, la, flags, u0);
+            k_ntt_layer<<<dim3(chunks, nu), 256, 0, b200_cur_stream(ctx)>>>(work, ctx->d_consts, ctx->d_fwd, ctx->d_inv, ctx->d_misc, s, la, flags, u0);
         });
     };
     if (!inverse) {

@@ -271,6 +271,25 @@ class Ring:
     def INTTLazy(self, p1, p2, tree_order=False):
         check(lib().b200_intt(self._ctx.h, p1.h, p2.h, self.level, capi.B200_LAZY | (capi.B200_TREE_ORDER if tree_order else 0)))
 
+    # -- host-buffer transforms: H2D, kernels and D2H of successive chunks overlapped --
+    def TransformHost(self, host_in, host_out, ops, tree_order=False):
+        """Apply ops (sequence of "NTT"/"INTT") to [batch][L][N] HOST polynomials; host_in/host_out are numpy
+        uint64 arrays or (pinned) torch int64 tensors.  Returns host_out."""
+        code = (C.c_int * len(ops))(*[{"NTT": 0, "INTT": 1}[o] for o in ops])
+
+        def ptr_words(a):
+            if hasattr(a, "data_ptr"):
+                return a.data_ptr(), a.numel()
+            return a.ctypes.data, a.size
+        pi, ni = ptr_words(host_in)
+        po, no = ptr_words(host_out)
+        per = self.ModuliChainLength() * self._N
+        if ni != no or ni % per:
+            raise B200Error(-4, "host buffers must hold [batch][L][N] words")
+        check(lib().b200_transform_host(self._ctx.h, C.c_void_p(pi), C.c_void_p(po), ni // per, self.level, code, len(ops),
+                                        capi.B200_TREE_ORDER if tree_order else 0))
+        return host_out
+
     # -- fused ring product (BASELINE config 4) --
     def MulPoly(self, p1, p2, p3):
         """p3 = p1 * p2 in the ring (NTT, NTT, MForm, MulCoeffsMontgomery, INTT fused on device)."""

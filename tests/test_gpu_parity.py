@@ -347,3 +347,26 @@ def test_config4_polymul_3n_L16():
     c2 = r2.NewPoly()
     r2.MulPoly(r2.NewPoly().set(sa), r2.NewPoly().set(sb), c2)
     assert (c2.get()[0, 0] == O.schoolbook_3n(N2, q2, sa[0, 0], sb[0, 0])).all()
+
+
+def test_transform_host_pipelined_chunks():
+    """b200_transform_host: HOST buffers streamed in chunks (H2D / kernels / D2H overlapped)."""
+    rng = np.random.default_rng(11)
+    for N, moduli, batch in ((1 << 16, QI60[:4], 150), (3 * 2**15, C3_PRIMES[:3], 70)):
+        r = b200ring.NewRing(N, moduli)
+        host = np.empty((batch, len(moduli), N), dtype=np.uint64)
+        for l, q in enumerate(moduli):
+            host[:, l, :] = rng.integers(0, q, (batch, N), dtype=np.uint64)
+        out = np.empty_like(host)
+        r.TransformHost(host, out, ["NTT"])
+        for b in (0, batch // 2, batch - 1):            # first, middle and last chunk
+            for l, q in enumerate(moduli):
+                s = O.ThreeNSubRing(N, q) if N % 3 == 0 else O.Pow2SubRing(N, q)
+                assert (out[b, l] == s.NTT(host[b, l])).all(), (N, b, l)
+        back = np.empty_like(host)
+        r.TransformHost(out, back, ["INTT"])
+        assert (back == host).all()
+        r.TransformHost(host, out, ["NTT", "INTT"])      # in one call, and in place
+        assert (out == host).all()
+        r.TransformHost(out, out, ["NTT", "INTT"])
+        assert (out == host).all()
