@@ -46,21 +46,31 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line).  The sampler is started
+    early (nvidia-smi needs a few hundred ms to come up) and samples are filtered to [mark_start, mark_end]."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.t0 = self.t1 = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "10"],
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
     def stop(self):
+        import datetime
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -69,19 +79,29 @@ class ClockSampler:
         self.f.flush()
         rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
         os.unlink(self.f.name)
-        sm, mx, reasons = [], [], set()
+        samples = []
         for r in rows:
             try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
+                ts = datetime.datetime.strptime(r[0].strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                samples.append((ts, float(r[1]), float(r[2]), [v.strip().lower().startswith("active") for v in r[5:9]]))
             except Exception:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                if v.strip().lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
+        if not samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        inside = [x for x in samples if self.t0 is not None and self.t0 - 0.02 <= x[0] <= self.t1 + 0.02]
+        where = "timed region"
+        if not inside:   # region shorter than the sampling period: take the samples closest to it
+            mid = 0.5 * ((self.t0 or samples[-1][0]) + (self.t1 or samples[-1][0]))
+            inside = sorted(samples, key=lambda x: abs(x[0] - mid))[:3]
+            where = "nearest to timed region"
+        sm = sorted(x[1] for x in inside)
+        reasons = set()
+        for x in inside:
+            for name, on in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), x[3]):
+                if on:
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(x[2] for x in inside), "reasons": sorted(reasons),
+                "samples": len(inside), "window": where}
 
 
 # ------------------------------------------------------------------------------------------ CPU arms
@@ -180,6 +200,7 @@ def run_gpu(args):
     idx, moduli, _ = sharding.shard_moduli(MODULI, world, rank)
     Ll = len(moduli)
     polys = POLYS_PER_GPU * world
+    sampler = ClockSampler(local_rank) if rank == 0 else None   # started early; samples filtered to the timed region
     ring = b200ring.NewRing(N, moduli, device=local_rank)
     ring.SetStream(torch.cuda.current_stream().cuda_stream)
 
@@ -218,7 +239,8 @@ def run_gpu(args):
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.mark_start()
     launches0 = ring.LaunchCount()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -226,6 +248,8 @@ def run_gpu(args):
         step()
     e1.record()
     barrier()
+    if sampler:
+        sampler.mark_end()
     ms = e0.elapsed_time(e1)
     launches = ring.LaunchCount() - launches0
     clocks = sampler.stop() if sampler else None
@@ -279,7 +303,7 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=int(os.environ.get("WORLD_SIZE", 1)))
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

@@ -43,6 +43,9 @@
 #ifndef B200_MINB_ROWS_STD
 #define B200_MINB_ROWS_STD 12
 #endif
+#ifndef B200_MINB_ROWS_MUL
+#define B200_MINB_ROWS_MUL 6
+#endif
 #ifndef B200_MINB_COLS_STD
 #define B200_MINB_COLS_STD 6
 #endif
@@ -170,25 +173,9 @@ __device__ __forceinline__ int row_of(const BigArgs &a, int tile, int w, int &ro
     return (hd << a.logU) + u;
 }
 
-template <bool MATRIX, int VT>   // warps per CTA: MATRIX 6*VT, STANDARD VT
-__global__ void __launch_bounds__((MATRIX ? 6 : 1) * VT * 32, MATRIX ? B200_MINB_ROWS_M3 : B200_MINB_ROWS_STD)
-k_rows_fwd(const u64 *in, u64 *out, BigArgs a) {
-    constexpr int WARPS = (MATRIX ? 6 : 1) * VT, RUN = 6 * VT;
-    extern __shared__ __align__(16) u64 sm[];
-    const UnitRef ur = unit_ref(a);
-    const int limb = ur.limb;
-    const u64 q = a.consts[limb].q, twoq = 2 * q;
-    const QC qc(a.consts[limb]);
-    const tw_t *__restrict__ tw = a.fwd + (size_t)limb * a.N;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    int rowcode;
-    const int r = row_of<MATRIX, VT>(a, blockIdx.y, w, rowcode);
-    u64 *buf = sm + w * WROW;
-    const u64 *src = in + ur.in + (size_t)r * 256;
-    u64 x[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) x[k] = src[k * 32 + lane];
-    const unsigned P1 = (unsigned)(a.R + r);
+// The 8 layers of one 256-word row held by one warp (x[k]: 8 words per lane, buf: the warp's exchange buffer).
+// forward: in  c = k*32 + lane  (values < 8q)  ->  out c = lane*8 + k  (values < 8q)
+__device__ __forceinline__ void row_fwd_core(u64 (&x)[8], u64 *buf, int lane, unsigned P1, const tw_t *__restrict__ tw, const QC &qc) {
     fwd_regs<3>(x, P1, tw, qc);
 #pragma unroll
     for (int k = 0; k < 8; ++k) buf[pad16(k * 32 + lane)] = x[k];
@@ -203,12 +190,55 @@ k_rows_fwd(const u64 *in, u64 *out, BigArgs a) {
     __syncwarp();
 #pragma unroll
     for (int k = 0; k < 8; ++k) x[k] = buf[pad16(lane * 8 + k)];
+    u64 (&lo)[4] = *reinterpret_cast<u64 (*)[4]>(&x[0]);
+    u64 (&hi)[4] = *reinterpret_cast<u64 (*)[4]>(&x[4]);
+    fwd_regs<2>(lo, P1 * 64 + lane * 2, tw, qc);
+    fwd_regs<2>(hi, P1 * 64 + lane * 2 + 1, tw, qc);
+    __syncwarp();   // the buffer may be reused by the caller
+}
+// inverse: in  c = lane*8 + k  (values < 4q)  ->  out c = k*32 + lane  (values < 4q)
+__device__ __forceinline__ void row_inv_core(u64 (&x)[8], u64 *buf, int lane, unsigned P1, const tw_t *__restrict__ tw, const QC &qc) {
     {
         u64 (&lo)[4] = *reinterpret_cast<u64 (*)[4]>(&x[0]);
         u64 (&hi)[4] = *reinterpret_cast<u64 (*)[4]>(&x[4]);
-        fwd_regs<2>(lo, P1 * 64 + lane * 2, tw, qc);
-        fwd_regs<2>(hi, P1 * 64 + lane * 2 + 1, tw, qc);
+        inv_regs<2>(lo, P1 * 64 + lane * 2, tw, qc);
+        inv_regs<2>(hi, P1 * 64 + lane * 2 + 1, tw, qc);
     }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) buf[pad16(lane * 8 + k)] = x[k];
+    __syncwarp();
+    const int hi3 = lane & 7, lo2 = lane >> 3;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = buf[pad16(hi3 * 32 + k * 4 + lo2)];
+    inv_regs<3>(x, P1 * 8 + hi3, tw, qc);
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) buf[pad16(hi3 * 32 + k * 4 + lo2)] = x[k];
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = buf[pad16(k * 32 + lane)];
+    inv_regs<3>(x, P1, tw, qc);
+}
+
+template <bool MATRIX, int VT>   // warps per CTA: MATRIX 6*VT, STANDARD VT
+__global__ void __launch_bounds__((MATRIX ? 6 : 1) * VT * 32, MATRIX ? B200_MINB_ROWS_M3 : B200_MINB_ROWS_STD)
+k_rows_fwd(const u64 *in, u64 *out, BigArgs a) {
+    constexpr int RUN = 6 * VT;
+    extern __shared__ __align__(16) u64 sm[];
+    const UnitRef ur = unit_ref(a);
+    const int limb = ur.limb;
+    const QC qc(a.consts[limb]);
+    const tw_t *__restrict__ tw = a.fwd + (size_t)limb * a.N;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int rowcode;
+    const int r = row_of<MATRIX, VT>(a, blockIdx.y, w, rowcode);
+    u64 *buf = sm + w * WROW;
+    const u64 *src = in + ur.in + (size_t)r * 256;
+    u64 x[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = src[k * 32 + lane];
+    const unsigned P1 = (unsigned)(a.R + r);
+    row_fwd_core(x, buf, lane, P1, tw, qc);
 #pragma unroll
     for (int k = 0; k < 8; ++k) x[k] = (a.flags & B200_LAZY) ? csub(x[k], qc.fourq) : canon8(x[k], qc);   // lazy: [0,4q) <= 6q-2
     if (!MATRIX || (a.flags & B200_TREE_ORDER)) {
@@ -235,11 +265,10 @@ k_rows_fwd(const u64 *in, u64 *out, BigArgs a) {
 template <bool MATRIX, int VT>
 __global__ void __launch_bounds__((MATRIX ? 6 : 1) * VT * 32, MATRIX ? B200_MINB_ROWS_M3 : B200_MINB_ROWS_STD)
 k_rows_inv(const u64 *in, u64 *out, BigArgs a) {
-    constexpr int WARPS = (MATRIX ? 6 : 1) * VT, RUN = 6 * VT;
+    constexpr int RUN = 6 * VT;
     extern __shared__ __align__(16) u64 sm[];
     const UnitRef ur = unit_ref(a);
     const int limb = ur.limb;
-    const u64 q = a.consts[limb].q, twoq = 2 * q;
     const QC qc(a.consts[limb]);
     const tw_t *__restrict__ tw = a.inv + (size_t)limb * a.N;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -269,29 +298,43 @@ k_rows_inv(const u64 *in, u64 *out, BigArgs a) {
         __syncthreads();
     }
     const unsigned P1 = (unsigned)(a.R + r);
-    {
-        u64 (&lo)[4] = *reinterpret_cast<u64 (*)[4]>(&x[0]);
-        u64 (&hi)[4] = *reinterpret_cast<u64 (*)[4]>(&x[4]);
-        inv_regs<2>(lo, P1 * 64 + lane * 2, tw, qc);
-        inv_regs<2>(hi, P1 * 64 + lane * 2 + 1, tw, qc);
-    }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) buf[pad16(lane * 8 + k)] = x[k];
-    __syncwarp();
-    const int hi3 = lane & 7, lo2 = lane >> 3;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) x[k] = buf[pad16(hi3 * 32 + k * 4 + lo2)];
-    inv_regs<3>(x, P1 * 8 + hi3, tw, qc);
-    __syncwarp();
-#pragma unroll
-    for (int k = 0; k < 8; ++k) buf[pad16(hi3 * 32 + k * 4 + lo2)] = x[k];
-    __syncwarp();
-#pragma unroll
-    for (int k = 0; k < 8; ++k) x[k] = buf[pad16(k * 32 + lane)];
-    inv_regs<3>(x, P1, tw, qc);
+    row_inv_core(x, buf, lane, P1, tw, qc);
     u64 *dst = out + ur.out + (size_t)r * 256;
 #pragma unroll
     for (int k = 0; k < 8; ++k) dst[k * 32 + lane] = x[k];
+}
+
+// Fused row stage of the ring product (BASELINE config 4): for one row of a^ = cols_fwd(a) and b^ = cols_fwd(b)
+// run the 8 forward layers of both, multiply slot-wise (a*b mod q, the value of MulCoeffsMontgomery(MForm(a), b),
+// ring/ring_test.go:106-110) and run the 8 inverse layers -- the NTT-domain polynomials never touch memory and no
+// slot permutation is needed because the product is order agnostic.  ta is overwritten with the result.
+__global__ void __launch_bounds__(128, B200_MINB_ROWS_MUL)
+k_rows_mul(u64 *ta, const u64 *tb, BigArgs a) {
+    extern __shared__ __align__(16) u64 sm[];
+    const UnitRef ur = unit_ref(a);
+    const int limb = ur.limb;
+    const LimbConst lc = a.consts[limb];
+    const QC qc(lc);
+    const tw_t *__restrict__ tw = a.fwd + (size_t)limb * a.N, *__restrict__ twi = a.inv + (size_t)limb * a.N;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int r = blockIdx.y * 4 + w;
+    u64 *buf = sm + w * WROW;
+    const unsigned P1 = (unsigned)(a.R + r);
+    u64 *pa = ta + ur.in + (size_t)r * 256;
+    const u64 *pb = tb + ur.in + (size_t)r * 256;
+    u64 x[8], y[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = pa[k * 32 + lane];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) y[k] = pb[k * 32 + lane];
+    row_fwd_core(x, buf, lane, P1, tw, qc);
+    row_fwd_core(y, buf, lane, P1, tw, qc);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)   // canonical operands -> Barrett product in [0, 2q)
+        x[k] = bred_lazy(canon8(x[k], qc), canon8(y[k], qc), lc.q, lc.brc_hi, lc.brc_lo);
+    row_inv_core(x, buf, lane, P1, twi, qc);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) pa[k * 32 + lane] = x[k];
 }
 
 // ====================================================================================================
@@ -309,7 +352,6 @@ k_cols_fwd_std16(const u64 *in, u64 *out, BigArgs a) {
     const UnitRef ur = unit_ref(a);
     const int limb = ur.limb;
     const size_t ibase = ur.in + (size_t)blockIdx.y * CW, obase = ur.out + (size_t)blockIdx.y * CW;
-    const u64 q = a.consts[limb].q, twoq = 2 * q;
     const QC qc(a.consts[limb]);
     const tw_t *__restrict__ tw = a.fwd + (size_t)limb * a.N;
     const int t = threadIdx.x, c = t % CW, g = t / CW;   // g in [0,32)
@@ -347,8 +389,8 @@ k_cols_inv_std16(const u64 *in, u64 *out, BigArgs a) {
     const UnitRef ur = unit_ref(a);
     const int limb = ur.limb;
     const size_t ibase = ur.in + (size_t)blockIdx.y * CW, obase = ur.out + (size_t)blockIdx.y * CW;
-    const u64 q = a.consts[limb].q, twoq = 2 * q;
     const QC qc(a.consts[limb]);
+    const u64 q = qc.q;
     const tw_t *__restrict__ tw = a.inv + (size_t)limb * a.N;
     const tw_t ninv = a.misc[limb * MISC_COUNT + MISC_NINV], ninv_w1 = a.misc[limb * MISC_COUNT + MISC_NINV_W1];
     const bool lazy = a.flags & B200_LAZY;
@@ -399,8 +441,8 @@ k_cols_fwd_m3_15(const u64 *in, u64 *out, BigArgs a) {
     const UnitRef ur = unit_ref(a);
     const int limb = ur.limb;
     const size_t ibase = ur.in + (size_t)blockIdx.y * CW, obase = ur.out + (size_t)blockIdx.y * CW;
-    const u64 q = a.consts[limb].q, twoq = 2 * q, fourq = 4 * q;
     const QC qc(a.consts[limb]);
+    const u64 q = qc.q, twoq = qc.twoq, fourq = qc.fourq;
     const tw_t *__restrict__ tw = a.fwd + (size_t)limb * a.N;
     const tw_t om = a.misc[limb * MISC_COUNT + MISC_OMEGA3];
     const int t = threadIdx.x, c = t % CW, g = t / CW;   // g in [0,48)
@@ -470,8 +512,8 @@ k_cols_inv_m3_15(const u64 *in, u64 *out, BigArgs a) {
     const UnitRef ur = unit_ref(a);
     const int limb = ur.limb;
     const size_t ibase = ur.in + (size_t)blockIdx.y * CW, obase = ur.out + (size_t)blockIdx.y * CW;
-    const u64 q = a.consts[limb].q, twoq = 2 * q, fourq = 4 * q;
     const QC qc(a.consts[limb]);
+    const u64 q = qc.q, twoq = qc.twoq, fourq = qc.fourq;
     const tw_t *__restrict__ tw = a.inv + (size_t)limb * a.N;
     const tw_t *mc = a.misc + limb * MISC_COUNT;
     const bool lazy = a.flags & B200_LAZY;
@@ -560,8 +602,8 @@ int big_tables_create(b200_ctx *ctx) {
     if (env_int("B200_NO_BIG", 0)) return 0;
     if (ctx->ring_type == B200_RING_STANDARD) plan->covered = ctx->logN == 16;
     else plan->covered = ctx->b == 1 && ctx->a == 15;
-    plan->cw = env_int("B200_CW", 8) == 16 ? 16 : 8;
-    plan->vt = env_int("B200_VT", 2) == 4 ? 4 : 2;
+    plan->cw = 8;   // 16-column tiles and 4-v row tiles were measured slower on B200 (fewer resident CTAs)
+    plan->vt = 2;
     int l2 = 0;
     cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, ctx->device);
     const size_t budget = (size_t)env_int("B200_CHUNK_MB", 512) << 20;
@@ -584,15 +626,12 @@ int launch_ntt_big(b200_ctx *ctx, const u64 *in, u64 *out, Span sp, bool inverse
     kern_t ck, rk;
     int col_threads, row_warps;
     if (matrix) {
-        ck = cw == 16 ? (inverse ? (kern_t)k_cols_inv_m3_15<16> : (kern_t)k_cols_fwd_m3_15<16>)
-                      : (inverse ? (kern_t)k_cols_inv_m3_15<8> : (kern_t)k_cols_fwd_m3_15<8>);
+        ck = inverse ? (kern_t)k_cols_inv_m3_15<8> : (kern_t)k_cols_fwd_m3_15<8>;
         col_threads = cw * 48;
-        rk = vt == 4 ? (inverse ? (kern_t)k_rows_inv<true, 4> : (kern_t)k_rows_fwd<true, 4>)
-                     : (inverse ? (kern_t)k_rows_inv<true, 2> : (kern_t)k_rows_fwd<true, 2>);
+        rk = inverse ? (kern_t)k_rows_inv<true, 2> : (kern_t)k_rows_fwd<true, 2>;
         row_warps = 6 * vt;
     } else {
-        ck = cw == 16 ? (inverse ? (kern_t)k_cols_inv_std16<16> : (kern_t)k_cols_fwd_std16<16>)
-                      : (inverse ? (kern_t)k_cols_inv_std16<8> : (kern_t)k_cols_fwd_std16<8>);
+        ck = inverse ? (kern_t)k_cols_inv_std16<8> : (kern_t)k_cols_fwd_std16<8>;
         col_threads = cw * 32;
         rk = inverse ? (kern_t)k_rows_inv<false, 4> : (kern_t)k_rows_fwd<false, 4>;
         row_warps = 4;
@@ -635,4 +674,54 @@ int launch_ntt_big(b200_ctx *ctx, const u64 *in, u64 *out, Span sp, bool inverse
     return 0;
 }
 
-int launch_polymul_big(b200_ctx *, const u64 *, const u64 *, u64 *, Span) { return 1; }
+// c = a * b in the ring: cols_fwd(a), cols_fwd(b) -> fused rows (fwd, fwd, multiply, inv) -> cols_inv, in chunks
+// whose two intermediates (dense ring buffers in the context scratch) stay small enough to live in L2.
+int launch_polymul_big(b200_ctx *ctx, const u64 *pa, const u64 *pb, u64 *pc, Span sp) {
+    BigPlan *plan = (BigPlan *)ctx->big;
+    if (!plan || !plan->covered) return 1;
+    const bool matrix = ctx->ring_type == B200_RING_MATRIX;
+    const int N = ctx->N, R = N / 256, cw = plan->cw;
+    const int flags = matrix ? B200_TREE_ORDER : 0;
+    BigArgs a{ctx->d_consts, ctx->d_fwd, ctx->d_inv, ctx->d_misc, N, R, matrix ? ctx->a - 9 : 0, sp, 0, flags, 0, 0};
+    kern_t cf, ci;
+    int col_threads;
+    if (matrix) {
+        cf = (kern_t)k_cols_fwd_m3_15<8>;
+        ci = (kern_t)k_cols_inv_m3_15<8>;
+        col_threads = cw * 48;
+    } else {
+        cf = (kern_t)k_cols_fwd_std16<8>;
+        ci = (kern_t)k_cols_inv_std16<8>;
+        col_threads = cw * 32;
+    }
+    const int rows_total = R * cw;
+    const size_t col_smem = (size_t)(rows_total + ((rows_total >> 6) << 3) + 8) * sizeof(u64);
+    const size_t row_smem = (size_t)4 * WROW * sizeof(u64);
+    if (int rc = set_smem(cf, col_smem)) return rc;
+    if (int rc = set_smem(ci, col_smem)) return rc;
+    const int units = sp.batch * sp.nl;
+    const size_t budget = (size_t)env_int("B200_MUL_CHUNK_MB", 512) << 20;   // per intermediate
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>(budget / ((size_t)N * sizeof(u64)), (size_t)units));
+    if (int rc = b200_ensure_scratch(ctx, (size_t)2 * chunk * N)) return rc;
+    u64 *ta = ctx->d_scratch, *tb = ctx->d_scratch + (size_t)chunk * N;
+    const int col_tiles = 256 / cw, row_tiles = R / 4;
+    cudaStream_t st = b200_cur_stream(ctx);
+    for (int u0 = 0; u0 < units; u0 += chunk) {
+        const int nu = std::min(chunk, units - u0);
+        a.unit0 = u0;
+        BigArgs to_dense = a, dense = a, from_dense = a;
+        to_dense.out_dense = 1;
+        dense.in_dense = dense.out_dense = 1;
+        from_dense.in_dense = 1;
+        { LaunchScope ls(ctx, matrix ? "cols_fwd_m3" : "cols_fwd_std", nu);
+          cf<<<dim3(nu, col_tiles), col_threads, col_smem, st>>>(pa, ta, to_dense); }
+        { LaunchScope ls(ctx, matrix ? "cols_fwd_m3" : "cols_fwd_std", nu);
+          cf<<<dim3(nu, col_tiles), col_threads, col_smem, st>>>(pb, tb, to_dense); }
+        { LaunchScope ls(ctx, "rows_mul", nu);
+          k_rows_mul<<<dim3(nu, row_tiles), 128, row_smem, st>>>(ta, tb, dense); }
+        { LaunchScope ls(ctx, matrix ? "cols_inv_m3" : "cols_inv_std", nu);
+          ci<<<dim3(nu, col_tiles), col_threads, col_smem, st>>>(ta, pc, from_dense); }
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}

@@ -59,3 +59,23 @@ if args.time:
         args.ring, args.polys, len(moduli), os.environ.get("B200_CHUNK_MB", "dflt"), ms, rate, 100 * rate * 2 * N * 8 / 6.553e12))
     prof = ring.Profile(lambda: (ring.NTT(poly, poly), ring.INTT(poly, poly)))
     print("   ", {k: round(v["ms"], 3) for k, v in prof.items()})
+if os.environ.get("B200_PROFILE_MUL"):
+    b = torch.empty_like(data)
+    for l, q in enumerate(moduli):
+        b[:, l, :] = torch.randint(0, q, (args.polys, N), dtype=torch.int64, device="cuda")
+    c = torch.empty_like(data)
+    pb, pc = b200ring.Poly.from_torch(ring, b), b200ring.Poly.from_torch(ring, c)
+    for _ in range(2):
+        ring.MulPoly(poly, pb, pc)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    e0.record()
+    for _ in range(reps):
+        ring.MulPoly(poly, pb, pc)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    units = args.polys * len(moduli)
+    print("polymul ring=%s: %.3f ms  %.0f limb-products/s  %.1f%% of HBM roofline (24N bytes/limb-product)" % (
+        args.ring, ms, units / (ms * 1e-3), 100 * units / (ms * 1e-3) * 3 * N * 8 / 6.553e12))
+    prof = ring.Profile(lambda: ring.MulPoly(poly, pb, pc))
+    print("   ", {k: round(v["ms"], 3) for k, v in prof.items()})
