@@ -40,7 +40,7 @@ m = sharding.max_over_ranks(1.0 + rank, device="cpu")
 assert m == 2.0, m
 dist.barrier()
 dist.destroy_process_group()
-print("rank", rank, "ok")
+os.write(1, ("rank%d-ok\n" % rank).encode())   # one atomic write per rank
 '''
 
 
@@ -52,4 +52,4 @@ def test_two_rank_gloo_gather_and_timing(tmp_path):
            "--master-addr", "127.0.0.1", "--master-port", "29617", str(script)]
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
+    assert "rank0-ok" in r.stdout and "rank1-ok" in r.stdout
