@@ -40,7 +40,7 @@ m = sharding.max_over_ranks(1.0 + rank, device="cpu")
 assert m == 2.0, m
 dist.barrier()
 dist.destroy_process_group()
-os.write(1, ("rank%d-ok\n" % rank).encode())   # one atomic write per rank
+os.write(1, ("rank" + str(rank) + "-ok\n").encode())   # one atomic write per rank
 '''
 
 
