@@ -266,8 +266,14 @@ def run_gpu(args):
         d = prof[dom]
         per_launch_bytes = d["units"] / d["launches"] * BYTES_PER_UNIT      # each pass reads + writes every word once
         achieved = per_launch_bytes / (d["ms"] / d["launches"] * 1e-3) / 1e9
+        traffic = None
+        try:   # DRAM bytes per launch from the committed ncu --set full capture of this command (profiles/)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            traffic = tj["dram_bytes_per_unit"][dom] * d["units"] / d["launches"]
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": peak_src, "launch_us": 1e3 * d["ms"] / d["launches"],
+                    "traffic": traffic, "algorithmic_bytes": per_launch_bytes, "peak_source": peak_src, "launch_us": 1e3 * d["ms"] / d["launches"],
                     "share_of_step": d["ms"] / sum(v["ms"] for v in prof.values()),
                     "kernels": {k: {"ms": v["ms"], "launches": v["launches"]} for k, v in prof.items()}}
     path_gbs = value / world * BYTES_PER_UNIT / 1e9
