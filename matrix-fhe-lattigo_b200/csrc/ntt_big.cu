@@ -574,12 +574,239 @@ k_cols_inv_m3_15(const u64 *in, u64 *out, BigArgs a) {
     }
 }
 
+// ====================================================================================================
+// generic column pass: any STANDARD ring with 2^12 <= N <= 2^17 and any MATRIX ring N = 3*2^a, 12 <= a <= 15.
+// Same structure as the tuned kernels above (8 columns per CTA, register groups of <= 3 layers, shared-memory
+// exchanges), with the group sizes as template parameters.  Row index = hi*2^(b0+S) + k*2^b0 + lo for the
+// group that owns row bits [b0, b0+S); the root node of its sub-transform is (ROOTS << (LOG-b0-S)) + hi.
+// ====================================================================================================
+constexpr int GCW = 8;
+
+template <int S, int ROOTS, int LOG, bool INV, bool FROM_G, bool TO_G, bool FOLD_NINV>
+__device__ __forceinline__ void col_group(const u64 *gin, size_t ibase, u64 *gout, size_t obase, u64 *sm, int b0,
+                                          const tw_t *__restrict__ tw, const QC &qc, const tw_t ninv, const tw_t ninv_w1, bool lazy) {
+    constexpr int M = 1 << S;
+    const int ntiles = (GCW * ROOTS) << (LOG - S);
+    for (int t = threadIdx.x; t < ntiles; t += blockDim.x) {
+        const int c = t & (GCW - 1), rest = t >> 3;
+        const int lo = rest & ((1 << b0) - 1), hi = rest >> b0;
+        const int row0 = (hi << (b0 + S)) + lo;
+        u64 x[M];
+#pragma unroll
+        for (int k = 0; k < M; ++k) {
+            const int row = row0 + (k << b0);
+            x[k] = FROM_G ? gin[ibase + (size_t)row * 256 + c] : sm[pc(row * GCW + c)];
+        }
+        const unsigned P = (unsigned)((ROOTS << (LOG - b0 - S)) + hi);
+        if (!INV) {
+            fwd_regs<S>(x, P, tw, qc);
+        } else if (!FOLD_NINV) {
+            inv_regs<S>(x, P, tw, qc);
+        } else {   // top group of the STANDARD inverse: the last layer carries N^-1
+            inv_regs<S, 1>(x, P, tw, qc);
+#pragma unroll
+            for (int o = 0; o < M / 2; ++o) {
+                const u64 U = x[o], V = x[o + M / 2];
+                u64 X = shoup_lazy(U + V, ninv.x, ninv.y, qc.q);
+                u64 Y = shoup_lazy(U - V + qc.fourq, ninv_w1.x, ninv_w1.y, qc.q);
+                if (!lazy) { X = csub(X, qc.q); Y = csub(Y, qc.q); }
+                x[o] = X; x[o + M / 2] = Y;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < M; ++k) {
+            const int row = row0 + (k << b0);
+            if (TO_G) gout[obase + (size_t)row * 256 + c] = x[k];
+            else sm[pc(row * GCW + c)] = x[k];
+        }
+    }
+}
+
+constexpr int minb_for(int threads, int target) { return target / threads < 1 ? 1 : (target / threads > 16 ? 16 : target / threads); }
+
+template <int LOGR, int S1, int S2, int S3, bool INV>
+__global__ void __launch_bounds__(LOGR >= 6 ? (GCW << (LOGR - 3)) : 64, minb_for(LOGR >= 6 ? (GCW << (LOGR - 3)) : 64, 1024))
+k_cols_std_g(const u64 *in, u64 *out, BigArgs a) {
+    static_assert(S1 + S2 + S3 == LOGR && S1 >= 1 && S2 >= 1, "group sizes");
+    extern __shared__ __align__(16) u64 sm[];
+    const UnitRef ur = unit_ref(a);
+    const int limb = ur.limb;
+    const size_t ibase = ur.in + (size_t)blockIdx.y * GCW, obase = ur.out + (size_t)blockIdx.y * GCW;
+    const QC qc(a.consts[limb]);
+    const tw_t *__restrict__ tw = (INV ? a.inv : a.fwd) + (size_t)limb * a.N;
+    const tw_t ninv = a.misc[limb * MISC_COUNT + MISC_NINV], ninv_w1 = a.misc[limb * MISC_COUNT + MISC_NINV_W1];
+    const bool lazy = a.flags & B200_LAZY;
+    if (!INV) {
+        col_group<S1, 1, LOGR, false, true, false, false>(in, ibase, out, obase, sm, S2 + S3, tw, qc, ninv, ninv_w1, lazy);
+        __syncthreads();
+        if (S3 == 0) {
+            col_group<S2, 1, LOGR, false, false, true, false>(in, ibase, out, obase, sm, 0, tw, qc, ninv, ninv_w1, lazy);
+        } else {
+            col_group<S2, 1, LOGR, false, false, false, false>(in, ibase, out, obase, sm, S3, tw, qc, ninv, ninv_w1, lazy);
+            __syncthreads();
+            col_group<(S3 ? S3 : 1), 1, LOGR, false, false, true, false>(in, ibase, out, obase, sm, 0, tw, qc, ninv, ninv_w1, lazy);
+        }
+    } else {
+        if (S3 == 0) {
+            col_group<S2, 1, LOGR, true, true, false, false>(in, ibase, out, obase, sm, 0, tw, qc, ninv, ninv_w1, lazy);
+        } else {
+            col_group<(S3 ? S3 : 1), 1, LOGR, true, true, false, false>(in, ibase, out, obase, sm, 0, tw, qc, ninv, ninv_w1, lazy);
+            __syncthreads();
+            col_group<S2, 1, LOGR, true, false, false, false>(in, ibase, out, obase, sm, S3, tw, qc, ninv, ninv_w1, lazy);
+        }
+        __syncthreads();
+        col_group<S1, 1, LOGR, true, false, true, true>(in, ibase, out, obase, sm, S2 + S3, tw, qc, ninv, ninv_w1, lazy);
+    }
+}
+
+// MATRIX: first group = cyclotomic + radix-3 + S1 radix-2 layers on 6*2^S1 words; then groups on the u bits.
+template <int LOGU, int S1, int S2, int S3, bool INV>
+__global__ void __launch_bounds__(LOGU >= 4 ? ((GCW * 6) << (LOGU - 3)) : 64, minb_for(LOGU >= 4 ? ((GCW * 6) << (LOGU - 3)) : 64, 768))
+k_cols_m3_g(const u64 *in, u64 *out, BigArgs a) {
+    static_assert(S1 + S2 + S3 == LOGU && S2 >= 1, "group sizes");
+    extern __shared__ __align__(16) u64 sm[];
+    const UnitRef ur = unit_ref(a);
+    const int limb = ur.limb;
+    const size_t ibase = ur.in + (size_t)blockIdx.y * GCW, obase = ur.out + (size_t)blockIdx.y * GCW;
+    const QC qc(a.consts[limb]);
+    const u64 q = qc.q, twoq = qc.twoq, fourq = qc.fourq;
+    const tw_t *__restrict__ tw = (INV ? a.inv : a.fwd) + (size_t)limb * a.N;
+    const tw_t *mc = a.misc + limb * MISC_COUNT;
+    const tw_t om = mc[MISC_OMEGA3], none = make_ulonglong2(0, 0);
+    const bool lazy = a.flags & B200_LAZY;
+    constexpr int MA = 1 << S1, U = 1 << LOGU, ULO = U >> S1;
+    if (!INV) {
+        for (int t = threadIdx.x; t < GCW * ULO; t += blockDim.x) {
+            const int c = t & (GCW - 1), ulo = t >> 3;
+            u64 x[6][MA];
+#pragma unroll
+            for (int hd = 0; hd < 6; ++hd)
+#pragma unroll
+                for (int k = 0; k < MA; ++k) x[hd][k] = in[ibase + (size_t)(hd * U + k * ULO + ulo) * 256 + c];
+            const tw_t zeta = tw[1];
+#pragma unroll
+            for (int k = 0; k < MA; ++k) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {   // cyclotomic layer: in [0,2q) -> [0,4q)
+                    const u64 lo = x[d][k], hi = x[d + 3][k];
+                    const u64 tt = shoup_lazy(hi, zeta.x, zeta.y, q);
+                    x[d][k] = lo + tt;
+                    x[d + 3][k] = csub(lo + hi + twoq - tt, fourq);
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {   // radix-3 layer: [0,4q) -> [0,4q)
+                    const tw_t z1 = tw[2 + 2 * h], z2 = tw[3 + 2 * h];
+                    const u64 b0 = csub(x[3 * h][k], twoq);
+                    const u64 t1 = shoup_lazy(x[3 * h + 1][k], z1.x, z1.y, q);
+                    const u64 t2 = shoup_lazy(x[3 * h + 2][k], z2.x, z2.y, q);
+                    const u64 t3 = shoup_lazy(t1 + twoq - t2, om.x, om.y, q);
+                    x[3 * h][k] = csub(b0 + t1 + t2, fourq);
+                    x[3 * h + 1][k] = csub(b0 + twoq - t2 + t3, fourq);
+                    x[3 * h + 2][k] = csub(b0 + fourq - t1 - t3, fourq);
+                }
+            }
+#pragma unroll
+            for (int hd = 0; hd < 6; ++hd) {
+                if (S1 > 0) fwd_regs<S1>(x[hd], (unsigned)(6 + hd), tw, qc);
+#pragma unroll
+                for (int k = 0; k < MA; ++k) sm[pc((hd * U + k * ULO + ulo) * GCW + c)] = x[hd][k];
+            }
+        }
+        __syncthreads();
+        if (S3 == 0) {
+            col_group<S2, 6, LOGU, false, false, true, false>(in, ibase, out, obase, sm, 0, tw, qc, none, none, lazy);
+        } else {
+            col_group<S2, 6, LOGU, false, false, false, false>(in, ibase, out, obase, sm, S3, tw, qc, none, none, lazy);
+            __syncthreads();
+            col_group<(S3 ? S3 : 1), 6, LOGU, false, false, true, false>(in, ibase, out, obase, sm, 0, tw, qc, none, none, lazy);
+        }
+    } else {
+        if (S3 == 0) {
+            col_group<S2, 6, LOGU, true, true, false, false>(in, ibase, out, obase, sm, 0, tw, qc, none, none, lazy);
+        } else {
+            col_group<(S3 ? S3 : 1), 6, LOGU, true, true, false, false>(in, ibase, out, obase, sm, 0, tw, qc, none, none, lazy);
+            __syncthreads();
+            col_group<S2, 6, LOGU, true, false, false, false>(in, ibase, out, obase, sm, S3, tw, qc, none, none, lazy);
+        }
+        __syncthreads();
+        const tw_t k1 = mc[MISC_K1], k2 = mc[MISC_K2], zeta = mc[MISC_ZETA];
+        for (int t = threadIdx.x; t < GCW * ULO; t += blockDim.x) {
+            const int c = t & (GCW - 1), ulo = t >> 3;
+            u64 x[6][MA];
+#pragma unroll
+            for (int hd = 0; hd < 6; ++hd) {
+#pragma unroll
+                for (int k = 0; k < MA; ++k) x[hd][k] = sm[pc((hd * U + k * ULO + ulo) * GCW + c)];
+                if (S1 > 0) inv_regs<S1>(x[hd], (unsigned)(6 + hd), tw, qc);
+            }
+#pragma unroll
+            for (int k = 0; k < MA; ++k) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {   // inverse radix-3 (factor 3 deferred)
+                    const tw_t z1 = tw[2 + 2 * h], z2 = tw[3 + 2 * h];
+                    const u64 y0 = to2q(x[3 * h][k], qc), y1 = to2q(x[3 * h + 1][k], qc), y2 = to2q(x[3 * h + 2][k], qc);
+                    const u64 sgm = shoup_lazy(y1 + twoq - y2, om.x, om.y, q);
+                    x[3 * h][k] = csub(csub(y0 + y1 + y2, fourq), twoq);
+                    x[3 * h + 1][k] = shoup_lazy(y0 + fourq - y1 - sgm, z1.x, z1.y, q);
+                    x[3 * h + 2][k] = shoup_lazy(y0 + twoq - y2 + sgm, z2.x, z2.y, q);
+                }
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {   // inverse cyclotomic layer with the 2/N scaling
+                    const u64 lo = x[d][k], hi = x[d + 3][k];
+                    u64 hh = shoup_lazy(lo + twoq - hi, k1.x, k1.y, q);
+                    u64 ll = csub(shoup_lazy(lo, k2.x, k2.y, q) + twoq - shoup_lazy(hh, zeta.x, zeta.y, q), twoq);
+                    if (!lazy) { ll = csub(ll, q); hh = csub(hh, q); }
+                    x[d][k] = ll; x[d + 3][k] = hh;
+                }
+            }
+#pragma unroll
+            for (int hd = 0; hd < 6; ++hd)
+#pragma unroll
+                for (int k = 0; k < MA; ++k) out[obase + (size_t)(hd * U + k * ULO + ulo) * 256 + c] = x[hd][k];
+        }
+    }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------
+typedef void (*kern_t)(const u64 *, u64 *, BigArgs);
+
 struct BigPlan {
     bool covered = false;
     int cw = 8, vt = 2;
+    kern_t cols_fwd = nullptr, cols_inv = nullptr;
+    int col_threads = 0;
     size_t chunk_units = 0;   // units per launch group so that a chunk's intermediate stays in L2
 };
+
+#define STD_G(L, A, B, C) case L: plan->cols_fwd = (kern_t)k_cols_std_g<L, A, B, C, false>; plan->cols_inv = (kern_t)k_cols_std_g<L, A, B, C, true>; \
+                                  plan->col_threads = L >= 6 ? (GCW << (L - 3)) : 64; break;
+#define M3_G(L, A, B, C) case L: plan->cols_fwd = (kern_t)k_cols_m3_g<L, A, B, C, false>; plan->cols_inv = (kern_t)k_cols_m3_g<L, A, B, C, true>; \
+                                 plan->col_threads = L >= 4 ? ((GCW * 6) << (L - 3)) : 64; break;
+// column-pass kernels for a ring shape: the hand-tuned ones for the two headline shapes, the generic family otherwise
+bool pick_col_kernels(BigPlan *plan, bool matrix, int log, bool force_generic) {
+    if (!matrix) {
+        if (log == 8 && !force_generic) {
+            plan->cols_fwd = (kern_t)k_cols_fwd_std16<8>; plan->cols_inv = (kern_t)k_cols_inv_std16<8>; plan->col_threads = 8 * 32;
+            return true;
+        }
+        switch (log) {
+            STD_G(4, 2, 2, 0) STD_G(5, 3, 2, 0) STD_G(6, 3, 3, 0) STD_G(7, 3, 2, 2) STD_G(8, 3, 3, 2) STD_G(9, 3, 3, 3)
+            default: return false;
+        }
+    } else {
+        if (log == 6 && !force_generic) {
+            plan->cols_fwd = (kern_t)k_cols_fwd_m3_15<8>; plan->cols_inv = (kern_t)k_cols_inv_m3_15<8>; plan->col_threads = 8 * 48;
+            return true;
+        }
+        switch (log) {
+            M3_G(3, 0, 3, 0) M3_G(4, 1, 3, 0) M3_G(5, 0, 3, 2) M3_G(6, 1, 3, 2)
+            default: return false;
+        }
+    }
+    return true;
+}
+#undef STD_G
+#undef M3_G
 
 int env_int(const char *name, int dflt) {
     const char *v = std::getenv(name);
@@ -592,16 +819,16 @@ int set_smem(K kern, size_t bytes) {
     return 0;
 }
 
-typedef void (*kern_t)(const u64 *, u64 *, BigArgs);
-
 }  // namespace
 
 int big_tables_create(b200_ctx *ctx) {
     BigPlan *plan = new BigPlan();
     ctx->big = plan;
     if (env_int("B200_NO_BIG", 0)) return 0;
-    if (ctx->ring_type == B200_RING_STANDARD) plan->covered = ctx->logN == 16;
-    else plan->covered = ctx->b == 1 && ctx->a == 15;
+    const bool matrix = ctx->ring_type == B200_RING_MATRIX;
+    const bool generic = env_int("B200_GENERIC_COLS", 0) != 0;
+    if (!matrix) plan->covered = ctx->logN >= 12 && ctx->logN <= 17 && pick_col_kernels(plan, false, ctx->logN - 8, generic);
+    else plan->covered = ctx->b == 1 && ctx->a >= 12 && ctx->a <= 15 && pick_col_kernels(plan, true, ctx->a - 9, generic);
     plan->cw = 8;   // 16-column tiles and 4-v row tiles were measured slower on B200 (fewer resident CTAs)
     plan->vt = 2;
     int l2 = 0;
@@ -623,16 +850,14 @@ int launch_ntt_big(b200_ctx *ctx, const u64 *in, u64 *out, Span sp, bool inverse
     const bool permute = matrix && !(flags & B200_TREE_ORDER);
     const int N = ctx->N, R = N / 256, cw = plan->cw, vt = plan->vt;
     BigArgs a{ctx->d_consts, ctx->d_fwd, ctx->d_inv, ctx->d_misc, N, R, matrix ? ctx->a - 9 : 0, sp, 0, flags, 0, 0};
-    kern_t ck, rk;
-    int col_threads, row_warps;
+    const kern_t ck = inverse ? plan->cols_inv : plan->cols_fwd;
+    const int col_threads = plan->col_threads;
+    kern_t rk;
+    int row_warps;
     if (matrix) {
-        ck = inverse ? (kern_t)k_cols_inv_m3_15<8> : (kern_t)k_cols_fwd_m3_15<8>;
-        col_threads = cw * 48;
         rk = inverse ? (kern_t)k_rows_inv<true, 2> : (kern_t)k_rows_fwd<true, 2>;
         row_warps = 6 * vt;
     } else {
-        ck = inverse ? (kern_t)k_cols_inv_std16<8> : (kern_t)k_cols_fwd_std16<8>;
-        col_threads = cw * 32;
         rk = inverse ? (kern_t)k_rows_inv<false, 4> : (kern_t)k_rows_fwd<false, 4>;
         row_warps = 4;
     }
@@ -683,17 +908,8 @@ int launch_polymul_big(b200_ctx *ctx, const u64 *pa, const u64 *pb, u64 *pc, Spa
     const int N = ctx->N, R = N / 256, cw = plan->cw;
     const int flags = matrix ? B200_TREE_ORDER : 0;
     BigArgs a{ctx->d_consts, ctx->d_fwd, ctx->d_inv, ctx->d_misc, N, R, matrix ? ctx->a - 9 : 0, sp, 0, flags, 0, 0};
-    kern_t cf, ci;
-    int col_threads;
-    if (matrix) {
-        cf = (kern_t)k_cols_fwd_m3_15<8>;
-        ci = (kern_t)k_cols_inv_m3_15<8>;
-        col_threads = cw * 48;
-    } else {
-        cf = (kern_t)k_cols_fwd_std16<8>;
-        ci = (kern_t)k_cols_inv_std16<8>;
-        col_threads = cw * 32;
-    }
+    const kern_t cf = plan->cols_fwd, ci = plan->cols_inv;
+    const int col_threads = plan->col_threads;
     const int rows_total = R * cw;
     const size_t col_smem = (size_t)(rows_total + ((rows_total >> 6) << 3) + 8) * sizeof(u64);
     const size_t row_smem = (size_t)4 * WROW * sizeof(u64);

@@ -370,3 +370,49 @@ def test_transform_host_pipelined_chunks():
         assert (out == host).all()
         r.TransformHost(out, out, ["NTT", "INTT"])
         assert (out == host).all()
+
+
+@pytest.mark.parametrize("env", [{"B200_GENERIC_COLS": "1"}, {"B200_NO_BIG": "1"}])
+@pytest.mark.parametrize("shape", [("std", 1 << 16), ("std", 1 << 15), ("m3", 3 * 2**15), ("m3", 3 * 2**14)])
+def test_alternative_kernel_paths_agree(env, shape, monkeypatch):
+    """The generic column-pass family and the shape-agnostic fallback (resident / layered kernels) must give the
+    same words as the default path: the knobs are read at ring construction."""
+    kind, N = shape
+    moduli = QI60[:2] if kind == "std" else O.find_3n_rns_primes(N, 60, 2)
+    host = rand_poly(77, 2, moduli, N)
+    ref = b200ring.NewRing(N, moduli)
+    a, want = ref.NewPoly(2).set(host), ref.NewPoly(2)
+    ref.NTT(a, want)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    alt = b200ring.NewRing(N, moduli)
+    b, got = alt.NewPoly(2).set(host), alt.NewPoly(2)
+    alt.NTT(b, got)
+    assert (got.get() == want.get()).all()
+    alt.INTT(got, got)
+    assert (got.get() == host).all()
+    sub = O.ThreeNSubRing(N, moduli[1]) if kind == "m3" else O.Pow2SubRing(N, moduli[1])
+    assert (want.get()[1, 1] == sub.NTT(host[1, 1])).all()
+
+
+def test_3n_lazy_and_tree_order_flags_headline_shape():
+    N, moduli = 3 * 2**15, C3_PRIMES[:2]
+    r = b200ring.NewRing(N, moduli)
+    host = rand_poly(5, 1, moduli, N)
+    p, o, t = r.NewPoly().set(host), r.NewPoly(), r.NewPoly()
+    r.NTT(p, o)
+    canon = o.get()
+    r.NTTLazy(p, o)
+    lazy = o.get()
+    for l, q in enumerate(moduli):
+        assert (lazy[0, l] % np.uint64(q) == canon[0, l]).all() and int(lazy[0, l].max()) <= 6 * q - 2
+    r.NTT(p, t, tree_order=True)
+    s = O.ThreeNSubRing(N, moduli[0])
+    assert (t.get()[0, 0] == s.NTT(host[0, 0], order=1)).all()
+    assert (canon[0, 0] == t.get()[0, 0][s.go2fast()]).all()
+    r.INTT(t, t, tree_order=True)
+    assert (t.get() == host).all()
+    r.INTTLazy(r.NewPoly().set(canon), o)
+    lz = o.get()
+    for l, q in enumerate(moduli):
+        assert (lz[0, l] % np.uint64(q) == host[0, l]).all() and int(lz[0, l].max()) <= 2 * q - 1

@@ -19,6 +19,8 @@ ap.add_argument("--polys", type=int, default=32)
 ap.add_argument("--limbs", type=int, default=24)
 ap.add_argument("--iters", type=int, default=2)
 ap.add_argument("--time", action="store_true")
+ap.add_argument("--logn", type=int, default=16)
+ap.add_argument("--a", type=int, default=15)
 args = ap.parse_args()
 
 QI60 = [0x1fffffffffe00001, 0x1fffffffffc80001, 0x1fffffffffb40001, 0x1fffffffff500001,
@@ -28,9 +30,14 @@ QI60 = [0x1fffffffffe00001, 0x1fffffffffc80001, 0x1fffffffffb40001, 0x1fffffffff
         0x1ffffffffc000001, 0x1ffffffffb880001, 0x1ffffffffb7c0001, 0x1ffffffffb300001,
         0x1ffffffffb1c0001, 0x1ffffffffadc0001, 0x1ffffffffa400001, 0x1ffffffffa140001]
 if args.ring == "3n":
-    N, moduli = bench.N, bench.MODULI[: args.limbs]
+    N = 3 << args.a
+    if args.a == 15:
+        moduli = bench.MODULI[: args.limbs]
+    else:
+        from oracle import oracle as O
+        moduli = O.find_3n_rns_primes(N, 60, args.limbs)
 else:
-    N, moduli = 1 << 16, QI60[: args.limbs]
+    N, moduli = 1 << args.logn, QI60[: args.limbs]
 ring = b200ring.NewRing(N, moduli)
 ring.SetStream(torch.cuda.current_stream().cuda_stream)
 data = torch.empty((args.polys, len(moduli), N), dtype=torch.int64, device="cuda")
@@ -56,7 +63,7 @@ if args.time:
     units = 2 * args.polys * len(moduli)
     rate = units / (ms * 1e-3)
     print("ring=%s polys=%d limbs=%d chunkMB=%s: %.3f ms/step  %.0f limb-transforms/s  %.1f%% of HBM roofline" % (
-        args.ring, args.polys, len(moduli), os.environ.get("B200_CHUNK_MB", "dflt"), ms, rate, 100 * rate * 2 * N * 8 / 6.553e12))
+        args.ring + ":N=%d" % N, args.polys, len(moduli), os.environ.get("B200_CHUNK_MB", "dflt"), ms, rate, 100 * rate * 2 * N * 8 / 6.553e12))
     prof = ring.Profile(lambda: (ring.NTT(poly, poly), ring.INTT(poly, poly)))
     print("   ", {k: round(v["ms"], 3) for k, v in prof.items()})
 if os.environ.get("B200_PROFILE_MUL"):
