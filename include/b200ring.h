@@ -90,6 +90,8 @@ typedef struct b200_poly b200_poly; /* ring.Poly (ring/poly.go:13-24), device re
 #define B200_OP_MULSCALAR_MONT_ADD 50  /* SubRing.MulScalarMontgomeryThenAdd subring_ops.go:216 */
 #define B200_OP_ADD_SCALAR 51          /* SubRing.AddScalar                  subring_ops.go:174 */
 #define B200_OP_SUB_SCALAR 52          /* SubRing.SubScalar                  subring_ops.go:195 */
+#define B200_OP_SUB_MULSCALAR_MONT_2Q 53 /* SubRing.SubThenMulScalarMontgomeryTwoModulus subring_ops.go:230:
+                                            p3 = MRed(2q - p2 + p1, scalar_i)                          */
 
 /* ---- library ------------------------------------------------------------------------------- */
 B200_API const char *b200_last_error(void);   /* message of the last failure on this thread ("" if none) */
@@ -152,6 +154,21 @@ B200_API int b200_intt(b200_ctx *ctx, const b200_poly *in, b200_poly *out, int l
  * (level+1 of them; Montgomery form where the Go method says so); otherwise NULL. */
 B200_API int b200_vec_op(b200_ctx *ctx, int op, const b200_poly *p1, const b200_poly *p2, b200_poly *p3,
                 int level, const uint64_t *scalars);
+
+/* ---- RNS rescale in the NTT domain ------------------------------------------------
+ * Ring.DivRoundByLastModulusNTT (round != 0, ring/scaling.go:130-156) / DivFloorByLastModulusNTT (round == 0,
+ * ring/scaling.go:6-19) at `level` >= 1 for the whole batch: p1 limbs 0..level-1 = (p0 - [p0]_{q_level}) / q_level.
+ * p0 in the NTT domain, canonical; p1 may equal p0 (limb `level` of p1 is left untouched). */
+B200_API int b200_div_by_last_modulus_ntt(b200_ctx *ctx, const b200_poly *p0, b200_poly *p1, int level, int round);
+
+/* ---- fused ciphertext tensor product in the NTT domain ----------------------------
+ * (a0, a1) x (b0, b1) -> c0 = a0*b0, c1 = a0*b1 + a1*b0, c2 = a1*b1, slot-wise, in ONE pass over 4 inputs and
+ * 3 outputs.  mform_first != 0: ckks.Evaluator.mulRelin (schemes/ckks/evaluator.go:821-834): MForm(a0), MForm(a1),
+ * then MulCoeffsMontgomery / ...ThenAdd, i.e. c = a*b mod q.  mform_first == 0: matrix_ckks.Evaluator.Mul
+ * (schemes/matrix_ckks/evaluator.go:163-173): plain MulCoeffsMontgomery, c = a*b*2^-64 mod q.  Bit-identical
+ * to those sequences (also for squaring, a == b).  Outputs may alias inputs but must be distinct from each other. */
+B200_API int b200_tensor(b200_ctx *ctx, const b200_poly *a0, const b200_poly *a1, const b200_poly *b0, const b200_poly *b1,
+                b200_poly *c0, b200_poly *c1, b200_poly *c2, int level, int mform_first);
 
 /* ---- fused ring product (BASELINE config 4; ring/ring_test.go:106-110 sequence) ---------------
  * c = INTT( MulCoeffsMontgomery( MForm(NTT(a)), NTT(b) ) ) = a*b in the ring, coefficient domain,

@@ -233,6 +233,14 @@ extern "C" int b200_ctx_create(int ring_type, int N, int L, const uint64_t *modu
         std::copy(v.begin(), v.end(), inv.begin() + (size_t)i * N);
     }
 
+    // RescaleConstants (ring/ring.go:361-379): rc[j-1][i] = MForm(q_i - q_j^-1 mod q_i) for i < j
+    ctx->rescale.assign((size_t)(L > 1 ? L - 1 : 0) * L, 0);
+    for (int j = 1; j < L; ++j)
+        for (int i = 0; i < j; ++i) {
+            const u64 qi = ctx->sub[i].q, qj = ctx->sub[j].q;
+            ctx->rescale[(size_t)(j - 1) * L + i] = hm::mform(qi - hm::invmod_prime(qj % qi, qi), qi);
+        }
+
     auto up = [&](void **dst, const void *src, size_t bytes) -> cudaError_t {
         cudaError_t e = cudaMalloc(dst, bytes);
         if (e != cudaSuccess) return e;
@@ -263,7 +271,7 @@ extern "C" void b200_ctx_destroy(b200_ctx *ctx) {
     cudaSetDevice(ctx->device);
     big_tables_destroy(ctx);
     cudaFree(ctx->d_consts); cudaFree(ctx->d_fwd); cudaFree(ctx->d_inv); cudaFree(ctx->d_misc);
-    cudaFree(ctx->d_go2fast); cudaFree(ctx->d_scratch);
+    cudaFree(ctx->d_go2fast); cudaFree(ctx->d_scratch); cudaFree(ctx->d_ws);
     if (ctx->pipe.ready) {
         for (int i = 0; i < b200_ctx::HostPipe::NB; ++i) {
             cudaFree(ctx->pipe.buf[i]);
@@ -447,7 +455,7 @@ extern "C" int b200_intt(b200_ctx *ctx, const b200_poly *in, b200_poly *out, int
 extern "C" int b200_vec_op(b200_ctx *ctx, int op, const b200_poly *p1, const b200_poly *p2, b200_poly *p3, int level,
                            const uint64_t *scalars) {
     int batch;
-    const bool unary = (op >= B200_OP_NEG && op <= B200_OP_IMFORM) || op >= B200_OP_MULSCALAR_MONT;
+    const bool unary = (op >= B200_OP_NEG && op <= B200_OP_IMFORM) || (op >= B200_OP_MULSCALAR_MONT && op <= B200_OP_SUB_SCALAR);
     if (unary) {
         if (int rc = check_polys(ctx, level, "b200_vec_op", {p1, p3}, &batch)) return rc;
     } else {
@@ -467,6 +475,50 @@ extern "C" int b200_vec_op(b200_ctx *ctx, int op, const b200_poly *p1, const b20
     int rc = launch_vec_op(ctx, op, p1->d, p2 ? p2->d : nullptr, p3->d, Span{batch, level + 1, ctx->L, 0}, d_sc);
     if (d_sc) cudaFreeAsync((void *)d_sc, ctx->stream);
     return rc;
+}
+
+// Ring.DivRoundByLastModulusNTT / DivFloorByLastModulusNTT (ring/scaling.go:6-19,130-156) for the whole batch:
+// INTT of the last limb -> spread to the lower limbs -> NTT of those -> SubThenMulScalarMontgomeryTwoModulus.
+extern "C" int b200_div_by_last_modulus_ntt(b200_ctx *ctx, const b200_poly *p0, b200_poly *p1, int level, int round) {
+    int batch;
+    if (int rc = check_polys(ctx, level, "b200_div_by_last_modulus_ntt", {p0, p1}, &batch)) return rc;
+    if (level < 1) return fail(B200_ESHAPE, "b200_div_by_last_modulus_ntt: needs level >= 1");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const size_t words = (size_t)batch * ctx->L * ctx->N;
+    if (ctx->ws_words < words) {
+        CUDA_TRY(cudaStreamSynchronize(b200_cur_stream(ctx)));
+        if (ctx->d_ws) CUDA_TRY(cudaFree(ctx->d_ws));
+        ctx->d_ws = nullptr; ctx->ws_words = 0;
+        CUDA_TRY(cudaMalloc(&ctx->d_ws, words * sizeof(u64)));
+        ctx->ws_words = words;
+    }
+    u64 *ws = ctx->d_ws;
+    const size_t off = (size_t)level * ctx->N;
+    auto ntt = [&](const u64 *src, u64 *dst, Span sp, bool inv) {
+        int r = launch_ntt_big(ctx, src, dst, sp, inv, 0);
+        if (r == 1) r = launch_ntt_generic(ctx, src, dst, sp, inv, 0);
+        return r;
+    };
+    int rc = ntt(p0->d + off, ws + off, Span{batch, 1, ctx->L, level}, true);          // scaling.go:134
+    if (rc) return rc;
+    if ((rc = launch_rescale_spread(ctx, ws, batch, level, round != 0))) return rc;      // :139-142
+    if ((rc = ntt(ws, ws, Span{batch, level, ctx->L, 0}, false))) return rc;             // :143
+    u64 *d_rc = nullptr;
+    CUDA_TRY(cudaMallocAsync(&d_rc, sizeof(u64) * level, b200_cur_stream(ctx)));
+    CUDA_TRY(cudaMemcpyAsync(d_rc, &ctx->rescale[(size_t)(level - 1) * ctx->L], sizeof(u64) * level, cudaMemcpyHostToDevice, b200_cur_stream(ctx)));
+    rc = launch_vec_op(ctx, B200_OP_SUB_MULSCALAR_MONT_2Q, ws, p0->d, p1->d, Span{batch, level, ctx->L, 0}, d_rc);   // :144
+    cudaFreeAsync(d_rc, b200_cur_stream(ctx));
+    return rc;
+}
+
+extern "C" int b200_tensor(b200_ctx *ctx, const b200_poly *a0, const b200_poly *a1, const b200_poly *b0, const b200_poly *b1,
+                           b200_poly *c0, b200_poly *c1, b200_poly *c2, int level, int mform_first) {
+    int batch;
+    if (int rc = check_polys(ctx, level, "b200_tensor", {a0, a1, b0, b1, c0, c1, c2}, &batch)) return rc;
+    if (c0 == c1 || c0 == c2 || c1 == c2 || c0->d == c1->d || c0->d == c2->d || c1->d == c2->d)
+        return fail(B200_ESHAPE, "b200_tensor: the three outputs must be distinct polynomials");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    return launch_tensor(ctx, a0->d, a1->d, b0->d, b1->d, c0->d, c1->d, c2->d, Span{batch, level + 1, ctx->L, 0}, mform_first != 0);
 }
 
 extern "C" int b200_polymul(b200_ctx *ctx, const b200_poly *a, const b200_poly *b, b200_poly *c, int level) {

@@ -37,12 +37,14 @@ __device__ __forceinline__ u64 apply(u64 x, u64 y, u64 z, u64 sc, const LimbCons
     case B200_OP_MULSCALAR_MONT_ADD: return csub(z + mred(x, sc, q, c.qinv), q);           // :708-728
     case B200_OP_ADD_SCALAR: return csub(x + sc, q);                                       // :575-595
     case B200_OP_SUB_SCALAR: return csub(x + q - sc, q);                                   // :642-662
+    case B200_OP_SUB_MULSCALAR_MONT_2Q: return mred(2 * q - y + x, sc, q, c.qinv);         // :752-776
     }
     return 0;
 }
 
 template <int OP> struct traits {
-    static constexpr bool binary = (OP <= B200_OP_SUB_LAZY) || (OP >= B200_OP_MUL_BARRETT && OP <= B200_OP_MUL_MONT_LAZY_NEG);
+    static constexpr bool binary = (OP <= B200_OP_SUB_LAZY) || (OP >= B200_OP_MUL_BARRETT && OP <= B200_OP_MUL_MONT_LAZY_NEG) ||
+                                   OP == B200_OP_SUB_MULSCALAR_MONT_2Q;
     static constexpr bool accum = OP == B200_OP_MUL_BARRETT_ADD || OP == B200_OP_MUL_BARRETT_ADD_LAZY ||
                                   OP == B200_OP_MUL_MONT_ADD || OP == B200_OP_MUL_MONT_ADD_LAZY ||
                                   OP == B200_OP_MUL_MONT_LAZY_ADD_LAZY || OP == B200_OP_MUL_MONT_SUB ||
@@ -90,7 +92,86 @@ int run(b200_ctx *ctx, const u64 *p1, const u64 *p2, u64 *p3, Span sp, const u64
     return 0;
 }
 
+// Fused degree-1 x degree-1 tensor product in the NTT domain: one pass over 4 inputs and 3 outputs (56 B/word)
+// instead of the 2 MForm + 3 MulCoeffsMontgomery + 1 ...ThenAdd passes (136 B/word) of
+// schemes/ckks/evaluator.go:821-834 / schemes/matrix_ckks/evaluator.go:163-173.  Results are the canonical
+// words those sequences produce.
+template <bool MFORM>
+__global__ void __launch_bounds__(256)
+k_tensor(const u64 *a0, const u64 *a1, const u64 *b0, const u64 *b1, u64 *c0, u64 *c1, u64 *c2,
+         const LimbConst *__restrict__ consts, int N, Span sp, int unit0) {
+    const int unit = unit0 + blockIdx.y;
+    const int limb = unit % sp.nl;
+    const size_t base = ((size_t)(unit / sp.nl) * sp.Lbuf + limb) * (size_t)N;
+    const LimbConst c = consts[sp.limb0 + limb];
+    const int n2 = N >> 1;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x) {
+        ulonglong2 x0 = reinterpret_cast<const ulonglong2 *>(a0 + base)[i], x1 = reinterpret_cast<const ulonglong2 *>(a1 + base)[i];
+        const ulonglong2 y0 = reinterpret_cast<const ulonglong2 *>(b0 + base)[i], y1 = reinterpret_cast<const ulonglong2 *>(b1 + base)[i];
+        if (MFORM) {
+            x0.x = mform(x0.x, c.q, c.brc_hi, c.brc_lo); x0.y = mform(x0.y, c.q, c.brc_hi, c.brc_lo);
+            x1.x = mform(x1.x, c.q, c.brc_hi, c.brc_lo); x1.y = mform(x1.y, c.q, c.brc_hi, c.brc_lo);
+        }
+        ulonglong2 r0, r1, r2;
+        r0.x = mred(x0.x, y0.x, c.q, c.qinv); r0.y = mred(x0.y, y0.y, c.q, c.qinv);
+        r2.x = mred(x1.x, y1.x, c.q, c.qinv); r2.y = mred(x1.y, y1.y, c.q, c.qinv);
+        r1.x = csub(mred(x0.x, y1.x, c.q, c.qinv) + mred(x1.x, y0.x, c.q, c.qinv), c.q);
+        r1.y = csub(mred(x0.y, y1.y, c.q, c.qinv) + mred(x1.y, y0.y, c.q, c.qinv), c.q);
+        reinterpret_cast<ulonglong2 *>(c0 + base)[i] = r0;
+        reinterpret_cast<ulonglong2 *>(c1 + base)[i] = r1;
+        reinterpret_cast<ulonglong2 *>(c2 + base)[i] = r2;
+    }
+}
+
+// Rescale helper (ring/scaling.go:137-143): x = coefficient-domain last limb [0, q_l); for every lower limb i
+// t_i = (x (+ pHalf mod q_l)) + (q_i - pHalf mod q_i), reduced to [0, q_i).  ws is a [batch][Lbuf][N] buffer whose
+// limb `level` holds x; limbs 0..level-1 receive t_i.
+__global__ void __launch_bounds__(256)
+k_rescale_spread(u64 *ws, const LimbConst *__restrict__ consts, int N, int Lbuf, int level, int round) {
+    const int b = blockIdx.y;
+    const u64 *x = ws + ((size_t)b * Lbuf + level) * (size_t)N;
+    const u64 ql = consts[level].q, phalf = (ql - 1) >> 1;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x) {
+        u64 v = x[j];
+        if (round) v = csub(v + phalf, ql);
+        for (int i = 0; i < level; ++i) {
+            const LimbConst c = consts[i];
+            const u64 add = round ? c.q - bred_add(phalf, c.q, c.brc_hi) : 0;
+            ws[((size_t)b * Lbuf + i) * (size_t)N + j] = csub(bred_add(v, c.q, c.brc_hi) + add, c.q);
+        }
+    }
+}
+
 }  // namespace
+
+int launch_rescale_spread(b200_ctx *ctx, u64 *ws, int batch, int level, bool round) {
+    const int N = ctx->N;
+    int chunks = (N + 255) / 256;
+    if (chunks > 256) chunks = 256;
+    for (int b0 = 0; b0 < batch; b0 += 65535) {
+        const int nb = batch - b0 < 65535 ? batch - b0 : 65535;
+        LaunchScope ls(ctx, "rescale_spread", (long long)nb * level);
+        k_rescale_spread<<<dim3(chunks, nb), 256, 0, b200_cur_stream(ctx)>>>(ws + (size_t)b0 * ctx->L * N, ctx->d_consts, N, ctx->L, level, round ? 1 : 0);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int launch_tensor(b200_ctx *ctx, const u64 *a0, const u64 *a1, const u64 *b0, const u64 *b1, u64 *c0, u64 *c1, u64 *c2,
+                  Span sp, bool mform_first) {
+    const int N = ctx->N, n2 = N >> 1;
+    int chunks = (n2 + 255) / 256;
+    if (chunks > 1024) chunks = 1024;
+    const int units = sp.batch * sp.nl;
+    for (int u0 = 0; u0 < units; u0 += 65535) {
+        const int nu = units - u0 < 65535 ? units - u0 : 65535;
+        LaunchScope ls(ctx, "tensor", nu);
+        if (mform_first) k_tensor<true><<<dim3(chunks, nu), 256, 0, b200_cur_stream(ctx)>>>(a0, a1, b0, b1, c0, c1, c2, ctx->d_consts, N, sp, u0);
+        else k_tensor<false><<<dim3(chunks, nu), 256, 0, b200_cur_stream(ctx)>>>(a0, a1, b0, b1, c0, c1, c2, ctx->d_consts, N, sp, u0);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
 
 int launch_vec_op(b200_ctx *ctx, int op, const u64 *p1, const u64 *p2, u64 *p3, Span sp, const u64 *d_scalars) {
 #define CASE(OP) case OP: return run<OP>(ctx, p1, p2, p3, sp, d_scalars);
@@ -102,7 +183,7 @@ int launch_vec_op(b200_ctx *ctx, int op, const u64 *p1, const u64 *p2, u64 *p3, 
         CASE(B200_OP_MUL_MONT_LAZY_ADD_LAZY) CASE(B200_OP_MUL_MONT_SUB) CASE(B200_OP_MUL_MONT_SUB_LAZY)
         CASE(B200_OP_MUL_MONT_LAZY_SUB_LAZY) CASE(B200_OP_MUL_MONT_LAZY_NEG)
         CASE(B200_OP_MULSCALAR_MONT) CASE(B200_OP_MULSCALAR_MONT_LAZY) CASE(B200_OP_MULSCALAR_MONT_ADD)
-        CASE(B200_OP_ADD_SCALAR) CASE(B200_OP_SUB_SCALAR)
+        CASE(B200_OP_ADD_SCALAR) CASE(B200_OP_SUB_SCALAR) CASE(B200_OP_SUB_MULSCALAR_MONT_2Q)
     }
 #undef CASE
     b200_set_error("b200_vec_op: unknown op code " + std::to_string(op));

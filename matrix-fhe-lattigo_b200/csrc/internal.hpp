@@ -39,6 +39,9 @@ struct b200_ctx {
     int *d_go2fast = nullptr;        // [N] MATRIX: reference slot k -> tree slot i
     u64 *d_scratch = nullptr;        // grown on demand (generic large-N path, polymul temporaries)
     size_t scratch_words = 0;
+    u64 *d_ws = nullptr;             // second workspace for composite operators that call the transforms (rescale)
+    size_t ws_words = 0;
+    std::vector<u64> rescale;        // RescaleConstants[level-1][i] (ring.go:361-379), row-major [L-1][L], Montgomery form
     std::atomic<uint64_t> launches{0};
     // optional per-kernel device timing (b200_profile_begin/end): CUDA events around each launch
     bool profiling = false;
@@ -105,6 +108,9 @@ struct Span {
     int batch, nl, Lbuf, limb0;
 };
 int launch_vec_op(b200_ctx *ctx, int op, const u64 *p1, const u64 *p2, u64 *p3, Span sp, const u64 *d_scalars);
+int launch_rescale_spread(b200_ctx *ctx, u64 *ws, int batch, int level, bool round);
+int launch_tensor(b200_ctx *ctx, const u64 *a0, const u64 *a1, const u64 *b0, const u64 *b1, u64 *c0, u64 *c1, u64 *c2,
+                  Span sp, bool mform_first);
 int launch_ntt_generic(b200_ctx *ctx, const u64 *in, u64 *out, Span sp, bool inverse, int flags);
 // optimised two-pass path; returns 1 if the shape is not covered (caller falls back to generic)
 int big_tables_create(b200_ctx *ctx);

@@ -34,6 +34,7 @@ _OPS = {
     "MulCoeffsMontgomeryLazyThenSubLazy": 39, "MulCoeffsMontgomeryLazyThenNeg": 40,
 }
 _UNARY = {"Neg", "Reduce", "ReduceLazy", "MForm", "MFormLazy", "IMForm"}
+_BINARY_SCALAR_OPS = {"SubThenMulScalarMontgomeryTwoModulus": 53}
 _SCALAR_OPS = {"MulScalarMontgomery": 48, "MulScalarMontgomeryLazy": 49, "MulScalarMontgomeryThenAdd": 50,
                "AddScalar": 51, "SubScalar": 52}
 
@@ -295,6 +296,19 @@ class Ring:
         """p3 = p1 * p2 in the ring (NTT, NTT, MForm, MulCoeffsMontgomery, INTT fused on device)."""
         check(lib().b200_polymul(self._ctx.h, p1.h, p2.h, p3.h, self.level))
 
+    def DivRoundByLastModulusNTT(self, p0, p1):
+        """ring/scaling.go:130-156 at this ring's level (the `buff` argument of the Go method is internal here)."""
+        check(lib().b200_div_by_last_modulus_ntt(self._ctx.h, p0.h, p1.h, self.level, 1))
+
+    def DivFloorByLastModulusNTT(self, p0, p1):
+        """ring/scaling.go:6-19."""
+        check(lib().b200_div_by_last_modulus_ntt(self._ctx.h, p0.h, p1.h, self.level, 0))
+
+    def TensorProduct(self, a0, a1, b0, b1, c0, c1, c2, mform=True):
+        """(a0,a1) x (b0,b1) -> (c0,c1,c2) in one pass: the MForm/MulCoeffsMontgomery[ThenAdd] sequence of
+        ckks.Evaluator.mulRelin (mform=True) or matrix_ckks.Evaluator.Mul (mform=False)."""
+        check(lib().b200_tensor(self._ctx.h, a0.h, a1.h, b0.h, b1.h, c0.h, c1.h, c2.h, self.level, int(mform)))
+
     def _vec(self, op, p1, p2, p3, scalars=None):
         sc = None
         if scalars is not None:
@@ -339,6 +353,18 @@ for _n, _c in _OPS.items():
     setattr(Ring, _n, _mk_unary(_n, _c) if _n in _UNARY else _mk_binary(_n, _c))
 for _n, _c in _SCALAR_OPS.items():
     setattr(Ring, _n, _mk_scalar(_n, _c))
+
+
+def _mk_binary_scalar(name, code):
+    def f(self, p1, p2, scalars, p3):
+        self._vec(code, p1, p2, p3, scalars)
+    f.__name__ = name
+    f.__doc__ = "per-limb SubRing.%s(p1, p2, scalar_i, p3) -- ring/subring_ops.go" % name
+    return f
+
+
+for _n, _c in _BINARY_SCALAR_OPS.items():
+    setattr(Ring, _n, _mk_binary_scalar(_n, _c))
 
 
 def NewRingFromType(N, Moduli, ringType, device=0, roots=None):

@@ -30,7 +30,7 @@ OPS = {
     "MulCoeffsMontgomeryThenSub": 37, "MulCoeffsMontgomeryThenSubLazy": 38,
     "MulCoeffsMontgomeryLazyThenSubLazy": 39, "MulCoeffsMontgomeryLazyThenNeg": 40,
     "MulScalarMontgomery": 48, "MulScalarMontgomeryLazy": 49, "MulScalarMontgomeryThenAdd": 50,
-    "AddScalar": 51, "SubScalar": 52,
+    "AddScalar": 51, "SubScalar": 52, "SubThenMulScalarMontgomeryTwoModulus": 53,
 }
 
 
@@ -79,6 +79,7 @@ def lib():
             "ref_3n_zetas": (None, [C.c_void_p, P64]),
             "ref_3n_forward": (None, [C.c_void_p, P64, P64, C.c_int]),
             "ref_3n_backward": (None, [C.c_void_p, P64, P64, C.c_int]),
+            "ref_div_by_last_modulus_ntt": (None, [C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_int, P64, P64, C.c_int]),
             "ref_fill_uniform": (None, [u64, u64, u64, u64, C.c_int, P64]),
             "ref_num_threads": (C.c_int, []),
             "ref_3n_batch": (None, [C.POINTER(C.c_void_p), C.c_int, P64, C.c_int, C.c_int, C.c_int]),
@@ -241,6 +242,17 @@ def schoolbook_negacyclic(N, q, a, b):
     c = np.empty(N, dtype=np.uint64)
     lib().ref_negacyclic_schoolbook(N, q, _p(a), _p(b), _p(c))
     return c
+
+
+def div_by_last_modulus_ntt(rings, p0, round=True):
+    """Ring.DivRoundByLastModulusNTT / DivFloorByLastModulusNTT (ring/scaling.go:6-19,130-156) on one polynomial
+    p0[nl][N] in the NTT domain; returns p1[nl-1][N]."""
+    p0 = _arr(p0)
+    nl, N = p0.shape
+    hs = (C.c_void_p * nl)(*[r.h for r in rings[:nl]])
+    out = np.empty((nl - 1, N), dtype=np.uint64)
+    lib().ref_div_by_last_modulus_ntt(1 if isinstance(rings[0], ThreeNSubRing) else 0, hs, nl, N, _p(p0), _p(out), int(round))
+    return out
 
 
 def totatives(threeN):

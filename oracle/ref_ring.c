@@ -362,7 +362,8 @@ enum {
     OP_MUL_BARRETT = 16, OP_MUL_BARRETT_LAZY, OP_MUL_BARRETT_ADD, OP_MUL_BARRETT_ADD_LAZY,
     OP_MUL_MONT = 32, OP_MUL_MONT_LAZY, OP_MUL_MONT_ADD, OP_MUL_MONT_ADD_LAZY, OP_MUL_MONT_LAZY_ADD_LAZY,
     OP_MUL_MONT_SUB, OP_MUL_MONT_SUB_LAZY, OP_MUL_MONT_LAZY_SUB_LAZY, OP_MUL_MONT_LAZY_NEG,
-    OP_MULSCALAR_MONT = 48, OP_MULSCALAR_MONT_LAZY, OP_MULSCALAR_MONT_ADD, OP_ADD_SCALAR, OP_SUB_SCALAR
+    OP_MULSCALAR_MONT = 48, OP_MULSCALAR_MONT_LAZY, OP_MULSCALAR_MONT_ADD, OP_ADD_SCALAR, OP_SUB_SCALAR,
+    OP_SUB_MULSCALAR_MONT_2Q
 };
 /* p3 = op(p1, p2 [, p3]) on one limb; scalar used by the *_SCALAR ops. Returns 0, or -1 on unknown op. */
 EXPORT int ref_vec_op(int op, int N, u64 q, const u64 *p1, const u64 *p2, u64 *p3, u64 scalar) {
@@ -399,6 +400,7 @@ EXPORT int ref_vec_op(int op, int N, u64 q, const u64 *p1, const u64 *p2, u64 *p
         case OP_MULSCALAR_MONT_ADD: z = cred(z + ref_mred(x, scalar, q, qinv), q); break; /* :708-728 */
         case OP_ADD_SCALAR: z = cred(x + scalar, q); break;                               /* :575-595 */
         case OP_SUB_SCALAR: z = cred(x + q - scalar, q); break;                           /* :642-662 */
+        case OP_SUB_MULSCALAR_MONT_2Q: z = ref_mred(twoq - y + x, scalar, q, qinv); break; /* :752-776 */
         default: return -1;
         }
         p3[i] = z;
@@ -691,6 +693,36 @@ EXPORT void ref_3n_backward(const ref_3n *s, const u64 *p1, u64 *p2, int order) 
     inv_tree(s, t);
     memcpy(p2, t, sizeof(u64) * N);
     free(t);
+}
+
+/* ---------------------------------------------------------------------------
+ * RNS rescale in the NTT domain: Ring.DivRoundByLastModulusNTT (ring/scaling.go:130-156) and
+ * Ring.DivFloorByLastModulusNTT (ring/scaling.go:6-19); RescaleConstants from ring/ring.go:361-379.
+ * kind 0 = power-of-two rings (ref_pow2 handles), 1 = 3N rings (ref_3n handles).  p0 = [nl][N] (NTT domain,
+ * canonical), p1 = [nl-1][N].  The Go "INTTLazy" is canonical for N >= 16 (ring/ntt.go:197-206) and for
+ * the 3N transformer (ntt_3n.go:154-156), which is what makes the result unique.
+ * ------------------------------------------------------------------------- */
+EXPORT void ref_div_by_last_modulus_ntt(int kind, void *const *rings, int nl, int N, const u64 *p0, u64 *p1, int round) {
+    const int level = nl - 1;
+    u64 *buffl = malloc(sizeof(u64) * N), *buffi = malloc(sizeof(u64) * N);
+    u64 ql;
+    if (kind == 1) { const ref_3n *r = rings[level]; ql = r->q; ref_3n_backward(r, p0 + (size_t)level * N, buffl, 0); }
+    else { const ref_pow2 *r = rings[level]; ql = r->q; ref_pow2_intt(r, p0 + (size_t)level * N, buffl, 1); }
+    const u64 phalf = (ql - 1) >> 1;
+    if (round) for (int j = 0; j < N; j++) buffl[j] = cred(buffl[j] + phalf, ql);                 /* AddScalar, scaling.go:139 */
+    for (int i = 0; i < level; i++) {
+        u64 qi, qinv, brc[2];
+        qi = kind == 1 ? ((const ref_3n *)rings[i])->q : ((const ref_pow2 *)rings[i])->q;
+        ref_gen_bred_constant(qi, brc);
+        qinv = ref_gen_mred_constant(qi);
+        const u64 rc = ref_mform(qi - ref_modexp(ql, qi - 2, qi), qi, brc);                         /* ring.go:372-374 */
+        const u64 add = round ? qi - ref_bred_add(phalf, qi, brc) : 0;                              /* scaling.go:142 */
+        for (int j = 0; j < N; j++) buffi[j] = buffl[j] + add;                                      /* AddScalarLazy */
+        if (kind == 1) ref_3n_forward(rings[i], buffi, buffi, 0); else ref_pow2_ntt(rings[i], buffi, buffi, 1);   /* NTTLazy */
+        for (int j = 0; j < N; j++)                                                                  /* vec_ops.go:752-776 */
+            p1[(size_t)i * N + j] = ref_mred(2 * qi - p0[(size_t)i * N + j] + buffi[j], rc, qi, qinv);
+    }
+    free(buffl); free(buffi);
 }
 
 /* ---------------------------------------------------------------------------

@@ -416,3 +416,89 @@ def test_3n_lazy_and_tree_order_flags_headline_shape():
     lz = o.get()
     for l, q in enumerate(moduli):
         assert (lz[0, l] % np.uint64(q) == host[0, l]).all() and int(lz[0, l].max()) <= 2 * q - 1
+
+
+@pytest.mark.parametrize("mform", [True, False])
+def test_tensor_product_matches_reference_sequence(mform):
+    """schemes/ckks/evaluator.go:821-834 (MForm first) and schemes/matrix_ckks/evaluator.go:163-173 (no MForm)."""
+    N, moduli, batch = 3 * 2**10, O.find_3n_rns_primes(3 * 2**10, 60, 3), 2
+    r = b200ring.NewRing(N, moduli)
+    h = [rand_poly(90 + i, batch, moduli, N) for i in range(4)]
+    a0, a1, b0, b1 = (r.NewPoly(batch).set(x) for x in h)
+    c0, c1, c2 = r.NewPoly(batch), r.NewPoly(batch), r.NewPoly(batch)
+    r.TensorProduct(a0, a1, b0, b1, c0, c1, c2, mform=mform)
+    g0, g1, g2 = c0.get(), c1.get(), c2.get()
+    for b in range(batch):
+        for l, q in enumerate(moduli):
+            x0, x1 = h[0][b, l], h[1][b, l]
+            if mform:
+                x0, x1 = O.vec_op("MForm", q, x0), O.vec_op("MForm", q, x1)
+            w0 = O.vec_op("MulCoeffsMontgomery", q, x0, h[2][b, l])
+            w2 = O.vec_op("MulCoeffsMontgomery", q, x1, h[3][b, l])
+            w1 = O.vec_op("MulCoeffsMontgomery", q, x0, h[3][b, l])
+            w1 = O.vec_op("MulCoeffsMontgomeryThenAdd", q, x1, h[2][b, l], w1)
+            assert (g0[b, l] == w0).all() and (g1[b, l] == w1).all() and (g2[b, l] == w2).all(), (mform, b, l)
+    # the same through the separate device operators, and the squaring case (c1 = 2 a0 a1)
+    t0, t1, d0, d1, d2 = (r.NewPoly(batch) for _ in range(5))
+    if mform:
+        r.MForm(a0, t0); r.MForm(a1, t1)
+    else:
+        t0.set(h[0]); t1.set(h[1])
+    r.MulCoeffsMontgomery(t0, b0, d0); r.MulCoeffsMontgomery(t1, b1, d2)
+    r.MulCoeffsMontgomery(t0, b1, d1); r.MulCoeffsMontgomeryThenAdd(t1, b0, d1)
+    assert (d0.get() == g0).all() and (d1.get() == g1).all() and (d2.get() == g2).all()
+    r.TensorProduct(a0, a1, a0, a1, c0, c1, c2, mform=mform)
+    r.MulCoeffsMontgomery(t0, a1, d1); r.Add(d1, d1, d1)
+    assert (c1.get() == d1.get()).all()
+    with pytest.raises(b200ring.B200Error):
+        r.TensorProduct(a0, a1, b0, b1, c0, c0, c2)
+
+
+@pytest.mark.parametrize("shape", [("std", 64, 3), ("std", 1 << 13, 4), ("m3", 24, 3), ("m3", 3 * 2**12, 3), ("m3", 3 * 2**15, 3)])
+def test_rescale_div_by_last_modulus_ntt(shape):
+    """Ring.DivRoundByLastModulusNTT / DivFloorByLastModulusNTT (ring/scaling.go:6-19,130-156) vs the oracle, and --
+    like ring/ring_test.go:242-331 -- vs rounded big-integer division on a few coefficients."""
+    kind, N, L = shape
+    moduli = QI60[:L] if kind == "std" else (C3_PRIMES[:L] if N == 3 * 2**15 else O.find_3n_rns_primes(N, 60, L))
+    rings = [O.Pow2SubRing(N, q) if kind == "std" else O.ThreeNSubRing(N, q) for q in moduli]
+    r = b200ring.NewRing(N, moduli)
+    batch = 2
+    host = rand_poly(123, batch, moduli, N)              # NTT-domain words, canonical
+    p0, p1 = r.NewPoly(batch).set(host), r.NewPoly(batch)
+    for rnd in (True, False):
+        (r.DivRoundByLastModulusNTT if rnd else r.DivFloorByLastModulusNTT)(p0, p1)
+        got = p1.get()
+        for b in range(batch):
+            want = O.div_by_last_modulus_ntt(rings, host[b], round=rnd)
+            assert (got[b, : L - 1] == want).all(), (shape, rnd, b)
+    assert (p0.get() == host).all()
+    # lower level through AtLevel, in place
+    q = r.NewPoly(batch).set(host)
+    r.AtLevel(L - 2).DivRoundByLastModulusNTT(q, q)
+    got = q.get()
+    want = O.div_by_last_modulus_ntt(rings[: L - 1], host[0, : L - 1], round=True)
+    assert (got[0, : L - 2] == want).all() and (got[:, L - 2:] == host[:, L - 2:]).all()
+    with pytest.raises(b200ring.B200Error):
+        r.AtLevel(0).DivRoundByLastModulusNTT(p0, p1)
+    # big-integer property on the first 4 coefficients (coefficient domain)
+    if N <= 64:
+        coeff = np.stack([rings[i].INTT(host[0, i]) for i in range(L)])
+        r.DivRoundByLastModulusNTT(p0, p1)
+        out = p1.get()[0]
+        from test_oracle import _crt
+        for j in range(4):
+            x = _crt(coeff[:, j], moduli)
+            w = (x + (moduli[-1] - 1) // 2) // moduli[-1]
+            for i in range(L - 1):
+                assert int(rings[i].INTT(out[i])[j]) == w % moduli[i]
+
+
+def test_sub_then_mulscalar_two_modulus_op():
+    N, moduli = 64, QI60[:2]
+    r = b200ring.NewRing(N, moduli)
+    h1, h2 = rand_poly(1, 1, moduli, N), rand_poly(2, 1, moduli, N)
+    sc = [987654321987654321 % q for q in moduli]
+    out = r.NewPoly()
+    r.SubThenMulScalarMontgomeryTwoModulus(r.NewPoly().set(h1), r.NewPoly().set(h2), sc, out)
+    for l, q in enumerate(moduli):
+        assert (out.get()[0, l] == O.vec_op("SubThenMulScalarMontgomeryTwoModulus", q, h1[0, l], h2[0, l], scalar=sc[l])).all()

@@ -175,3 +175,35 @@ def test_primes_and_roots():
             while rem % p == 0:
                 rem //= p
         assert rem == 1
+
+
+def _crt(residues, moduli):
+    x, M = 0, 1
+    for r, q in zip(residues, moduli):
+        t = ((int(r) - x) * pow(M, -1, q)) % q
+        x += M * t
+        M *= q
+    return x
+
+
+@pytest.mark.parametrize("kind", ["std", "m3"])
+def test_rescale_matches_big_integer_division(kind):
+    """ring/ring_test.go:242-331 (testDiv{Floor,Round}ByLastModulusMany): the restated DivRound/DivFloorByLastModulusNTT
+    equals rounded / floored division of the CRT-reconstructed coefficients by the last modulus."""
+    N = 32 if kind == "std" else 24
+    moduli = QI60[:3] if kind == "std" else O.find_3n_rns_primes(N, 60, 3)
+    rings = [O.Pow2SubRing(N, q) if kind == "std" else O.ThreeNSubRing(N, q) for q in moduli]
+    rng = np.random.default_rng(5)
+    Q = 1
+    for q in moduli:
+        Q *= q
+    coeffs = [int(rng.integers(0, 2**62)) * int(rng.integers(0, 2**62)) * int(rng.integers(0, 2**50)) % (Q // 10) for _ in range(N)]
+    p0 = np.array([[c % q for c in coeffs] for q in moduli], dtype=np.uint64)
+    p0_ntt = np.stack([r.NTT(p0[i]) for i, r in enumerate(rings)])
+    for rnd in (True, False):
+        got = O.div_by_last_modulus_ntt(rings, p0_ntt, round=rnd)
+        ql = moduli[-1]
+        want = [((c + (ql - 1) // 2) // ql) if rnd else (c // ql) for c in coeffs]
+        for i in range(len(moduli) - 1):
+            back = rings[i].INTT(got[i])
+            assert [int(v) for v in back] == [w % moduli[i] for w in want], (kind, rnd, i)

@@ -86,3 +86,21 @@ if os.environ.get("B200_PROFILE_MUL"):
         args.ring, ms, units / (ms * 1e-3), 100 * units / (ms * 1e-3) * 3 * N * 8 / 6.553e12))
     prof = ring.Profile(lambda: ring.MulPoly(poly, pb, pc))
     print("   ", {k: round(v["ms"], 3) for k, v in prof.items()})
+if os.environ.get("B200_PROFILE_VEC"):
+    b = torch.empty_like(data); c = torch.empty_like(data)
+    for l, q in enumerate(moduli):
+        b[:, l, :] = torch.randint(0, q, (args.polys, N), dtype=torch.int64, device="cuda")
+    pb, pc = b200ring.Poly.from_torch(ring, b), b200ring.Poly.from_torch(ring, c)
+    for name, nbuf in (("MulCoeffsMontgomery", 3), ("MulCoeffsMontgomeryThenAdd", 4), ("MulCoeffsBarrett", 3), ("Add", 3), ("MForm", 2), ("Reduce", 2)):
+        f = getattr(ring, name)
+        call = (lambda: f(poly, pc)) if nbuf == 2 else (lambda: f(poly, pb, pc))
+        for _ in range(3):
+            call()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            call()
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        gbs = nbuf * data.numel() * 8 / (ms * 1e-3) / 1e9
+        print("vec_op %-28s %.3f ms  %.0f GB/s  %.1f%% of HBM peak" % (name, ms, gbs, 100 * gbs / 6553))
