@@ -104,3 +104,33 @@ if os.environ.get("B200_PROFILE_VEC"):
         ms = e0.elapsed_time(e1) / 10
         gbs = nbuf * data.numel() * 8 / (ms * 1e-3) / 1e9
         print("vec_op %-28s %.3f ms  %.0f GB/s  %.1f%% of HBM peak" % (name, ms, gbs, 100 * gbs / 6553))
+if os.environ.get("B200_PROFILE_NEXT"):
+    # survey rows f-2 / f-3: fused tensor product and RNS rescale
+    bufs = [torch.empty_like(data) for _ in range(6)]
+    for t in bufs[:3]:
+        for l, q in enumerate(moduli):
+            t[:, l, :] = torch.randint(0, q, (args.polys, N), dtype=torch.int64, device="cuda")
+    a1, b0, b1, c0, c1, c2 = (b200ring.Poly.from_torch(ring, t) for t in bufs)
+
+    def timeit(fn, reps=5):
+        for _ in range(2):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+    ms = timeit(lambda: ring.TensorProduct(poly, a1, b0, b1, c0, c1, c2))
+    gbs = 7 * data.numel() * 8 / (ms * 1e-3) / 1e9
+    print("tensor product (4 in, 3 out): %.3f ms  %.0f GB/s  %.1f%% of HBM peak" % (ms, gbs, 100 * gbs / 6553))
+
+    def unfused():
+        ring.MForm(poly, c0); ring.MForm(a1, c2)
+        ring.MulCoeffsMontgomery(c0, b1, c1); ring.MulCoeffsMontgomeryThenAdd(c2, b0, c1)
+        ring.MulCoeffsMontgomery(c0, b0, c0); ring.MulCoeffsMontgomery(c2, b1, c2)
+    print("  same through separate operators: %.3f ms" % timeit(unfused))
+    ms = timeit(lambda: ring.DivRoundByLastModulusNTT(poly, c0))
+    Lq = len(moduli)
+    print("rescale DivRoundByLastModulusNTT (L=%d -> %d): %.3f ms for %d polys = %.0f polys/s, %d limb-transforms -> %.0f limb-transforms/s"
+          % (Lq, Lq - 1, ms, args.polys, args.polys / (ms * 1e-3), args.polys * Lq, args.polys * Lq / (ms * 1e-3)))
