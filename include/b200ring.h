@@ -155,6 +155,27 @@ B200_API int b200_intt(b200_ctx *ctx, const b200_poly *in, b200_poly *out, int l
 B200_API int b200_vec_op(b200_ctx *ctx, int op, const b200_poly *p1, const b200_poly *p2, b200_poly *p3,
                 int level, const uint64_t *scalars);
 
+/* ---- key switching: RNS basis extension, ModDown, gadget product ----------------------
+ * The ring of `ctx` is the concatenated chain Q_0..Q_{LQ-1}, P_0..P_{LP-1} (what ringqp.Ring fans out over,
+ * ring/ringqp/ring.go:12-17); polynomials keep the [batch][LQ+LP][N] layout, Q limbs first.
+ * b200_keyswitch_create precomputes what ring.NewBasisExtender / ring.NewDecomposer hold
+ * (ring/basis_extension.go:24-73,95-166,319-377); extension constants are generated on first use and cached. */
+typedef struct b200_keyswitch b200_keyswitch;
+B200_API int b200_keyswitch_create(b200_ctx *ctx, int LQ, b200_keyswitch **out);
+B200_API void b200_keyswitch_destroy(b200_keyswitch *ks);
+/* BasisExtender.ModUpQtoP (direction 0, basis_extension.go:184-198: reads Q limbs 0..levelQ of `in`, writes P limbs
+ * 0..levelP of `out`) / ModUpPtoQ (direction 1, :203-217).  Coefficient domain.  The words written are exactly the
+ * lazy representatives the Go code leaves (ModUpExact :282-308 then SubScalarBigint), float64 correction included. */
+B200_API int b200_mod_up(b200_keyswitch *ks, int direction, int levelQ, int levelP, const b200_poly *in, b200_poly *out);
+/* BasisExtender.ModDownQPtoQNTT (:241-258): p1 in basis QP, NTT domain -> p2 limbs 0..levelQ = round(p1 / P), canonical */
+B200_API int b200_mod_down_ntt(b200_keyswitch *ks, int levelQ, int levelP, const b200_poly *p1, b200_poly *p2);
+/* rlwe.Evaluator.GadgetProduct for NTT-domain operands and levelP >= 1 (core/rlwe/evaluator_gadget_product.go:16-30,
+ * 123-188, 455-478): ct = (<decomp(cx), key[.][0]>, <decomp(cx), key[.][1]>) / P mod Q.  cx: batch B, Q limbs used.
+ * key: 2*beta polynomials ordered [digit][component], NTT domain and Montgomery form over QP
+ * (GadgetCiphertext.Value[digit][0][component]), beta = (levelQ+levelP+1)/(levelP+1).  ct0, ct1: batch B, canonical. */
+B200_API int b200_gadget_product(b200_keyswitch *ks, int levelQ, int levelP, const b200_poly *cx, const b200_poly *key,
+                        b200_poly *ct0, b200_poly *ct1);
+
 /* ---- RNS rescale in the NTT domain ------------------------------------------------
  * Ring.DivRoundByLastModulusNTT (round != 0, ring/scaling.go:130-156) / DivFloorByLastModulusNTT (round == 0,
  * ring/scaling.go:6-19) at `level` >= 1 for the whole batch: p1 limbs 0..level-1 = (p0 - [p0]_{q_level}) / q_level.

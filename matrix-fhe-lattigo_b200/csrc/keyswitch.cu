@@ -1,0 +1,365 @@
+// keyswitch.cu -- RNS basis extension, ModDown and the hybrid key-switch gadget product.
+//
+// Reference: ring/basis_extension.go (GenModUpConstants :95-166, ModUpQtoP/ModUpPtoQ :184-217, ModDownQPtoQNTT
+// :241-258, ModUpExact :282-308, Decomposer.DecomposeAndSplit :381-502, reconstructRNS[Centered] :504-594, multSum
+// :597-673) and core/rlwe/evaluator_gadget_product.go (GadgetProduct :16-30, ModDown :33-45,
+// gadgetProductMultiplePLazy :123-188, DecomposeSingleNTT :455-478).
+//
+// The ring is ONE context over the concatenated chain Q_0..Q_{LQ-1}, P_0..P_{LP-1}; polynomials keep the usual
+// [batch][LQ+LP][N] layout.  The extension is the only cross-limb step of the path: one thread per coefficient
+// gathers the source limbs, runs the exact conversion (64-bit Montgomery products, 128-bit accumulation, the
+// float64 correction index v computed with the same IEEE operations in the same order as the Go code) and writes
+// every requested target limb.  Everything around it is the batched NTT / element-wise kernels of the hot path.
+#include <algorithm>
+#include <map>
+#include <string>
+
+#include "hostmath.hpp"
+#include "internal.hpp"
+
+namespace hm = hostmath;
+
+namespace {
+
+constexpr int EXT_THREADS = 128;
+constexpr int EXT_MAX_SRC = 64;
+
+// device-side description of one extension: source limbs -> target limbs
+struct ExtDesc {
+    int ns, nt;
+    const int *src_limb, *dst_limb;        // ring limb index (== layout limb index)
+    const u64 *half;                       // [ns]  addend before the reconstruction (Q/2 mod q_i), 0 if not centred
+    const u64 *qoverqiinvqi;               // [ns]  Montgomery form
+    const u64 *qoverqimodp;                // [nt][ns] Montgomery form
+    const u64 *vtimesqmodp;                // [nt][ns+1]
+    const u64 *sub;                        // [nt]  subtracted after the conversion (Q/2 mod p_j), 0 if not centred
+};
+
+// mode 0: exactly the lazy words ModUpQtoP/ModUpPtoQ leave (multSum, then SubScalar = CRed(x + p - s));
+// mode 1: the same residue reduced to [0, p) (feeds the transforms inside the gadget product / ModDown)
+__global__ void __launch_bounds__(EXT_THREADS)
+k_basis_extend(const u64 *src, u64 *dst, const LimbConst *__restrict__ consts, ExtDesc d, int N, int Lbuf, int mode) {
+    extern __shared__ u64 ysm[];   // [ns][EXT_THREADS]
+    const int b = blockIdx.y;
+    const int x = blockIdx.x * EXT_THREADS + threadIdx.x;
+    if (x >= N) return;
+    const u64 *s = src + (size_t)b * Lbuf * N + x;
+    u64 *o = dst + (size_t)b * Lbuf * N + x;
+    double vi = 0.0;
+    for (int i = 0; i < d.ns; ++i) {                                    // reconstructRNS[Centered]
+        const LimbConst c = consts[d.src_limb[i]];
+        const u64 y = mred(s[(size_t)d.src_limb[i] * N] + d.half[i], d.qoverqiinvqi[i], c.q, c.qinv);
+        ysm[i * EXT_THREADS + threadIdx.x] = y;
+        vi = __dadd_rn(vi, __ddiv_rn((double)y, (double)c.q));          // no contraction, same order as the Go loop
+    }
+    const unsigned v = (unsigned)(u64)vi;
+    for (int j = 0; j < d.nt; ++j) {                                    // multSum
+        const LimbConst c = consts[d.dst_limb[j]];
+        const u64 *row = d.qoverqimodp + (size_t)j * d.ns;
+        u64 rlo = 0, rhi = 0;
+        for (int i = 0; i < d.ns; ++i) {
+            const u64 y = ysm[i * EXT_THREADS + threadIdx.x], k = row[i];
+            const u64 mlo = y * k, mhi = __umul64hi(y, k);
+            rlo += mlo;
+            rhi += mhi + (rlo < mlo);
+        }
+        u64 r = rhi - __umul64hi(rlo * c.qinv, c.q) + c.q + d.vtimesqmodp[(size_t)j * (d.ns + 1) + v];   // [0, 3p)
+        r = csub(r + c.q - d.sub[j], c.q);                                                             // SubScalar
+        if (mode == 1) r = csub(csub(r, 2 * c.q), c.q);
+        o[(size_t)d.dst_limb[j] * N] = r;
+    }
+}
+
+// single-limb digit of DecomposeAndSplit (:402-428): centred lift of one limb, written canonically
+__global__ void __launch_bounds__(256)
+k_decompose_single(const u64 *src, u64 *dst, const LimbConst *__restrict__ consts, int src_limb, const int *dst_limb, int nt,
+                   int N, int Lbuf) {
+    const int b = blockIdx.y;
+    const int x = blockIdx.x * 256 + threadIdx.x;
+    if (x >= N) return;
+    const u64 q = consts[src_limb].q;
+    u64 coeff = src[((size_t)b * Lbuf + src_limb) * N + x];
+    const bool neg = coeff >= (q >> 1);
+    if (neg) coeff = q - coeff;
+    for (int j = 0; j < nt; ++j) {
+        const LimbConst c = consts[dst_limb[j]];
+        const u64 t = bred_add(coeff, c.q, c.brc_hi);
+        dst[((size_t)b * Lbuf + dst_limb[j]) * N + x] = neg ? csub(c.q - t, c.q) : t;
+    }
+}
+
+// acc_c[x] (+)= MRed(key[d][c][x], operand[x]) for both components; the operand of the digit's own limbs is the
+// NTT-domain input itself (rlwe/evaluator_gadget_product.go:466-472), all others come from the decomposition.
+__global__ void __launch_bounds__(256)
+k_gadget_mac(const u64 *cx, const u64 *c2, const u64 *key0, const u64 *key1, u64 *acc0, u64 *acc1,
+             const LimbConst *__restrict__ consts, const int *limbs, int nlimbs, int st, int ed, int N, int Lbuf, int first) {
+    const int unit = blockIdx.y;                       // (poly, limb index in `limbs`)
+    const int b = unit / nlimbs, limb = limbs[unit % nlimbs];
+    const LimbConst c = consts[limb];
+    const size_t base = ((size_t)b * Lbuf + limb) * (size_t)N, kbase = (size_t)limb * N;
+    const u64 *op = (limb >= st && limb < ed) ? cx : c2;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        const u64 v = op[base + i];
+        const u64 m0 = mred(key0[kbase + i], v, c.q, c.qinv), m1 = mred(key1[kbase + i], v, c.q, c.qinv);
+        acc0[base + i] = first ? m0 : csub(acc0[base + i] + m0, c.q);
+        acc1[base + i] = first ? m1 : csub(acc1[base + i] + m1, c.q);
+    }
+}
+
+struct Extender {
+    int ns = 0, nt = 0;
+    int *d_src = nullptr, *d_dst = nullptr;
+    u64 *d_half = nullptr, *d_qinvqi = nullptr, *d_qmodp = nullptr, *d_vq = nullptr, *d_sub = nullptr;
+    ExtDesc desc() const { return ExtDesc{ns, nt, d_src, d_dst, d_half, d_qinvqi, d_qmodp, d_vq, d_sub}; }
+    void release() {
+        cudaFree(d_src); cudaFree(d_dst); cudaFree(d_half); cudaFree(d_qinvqi); cudaFree(d_qmodp); cudaFree(d_vq); cudaFree(d_sub);
+    }
+};
+
+// (prod S) >> 1 mod m without big integers: prod S is odd, so ((prod S mod 2m) - 1) / 2 is the residue
+u64 half_of_product_mod(const std::vector<u64> &S, u64 m) {
+    const u64 m2 = 2 * m;
+    u64 r = 1;
+    for (u64 s : S) r = hm::mulmod(r, s % m2, m2);
+    return ((r - 1) >> 1) % m;
+}
+
+}  // namespace
+
+struct b200_keyswitch {
+    b200_ctx *ctx = nullptr;
+    int LQ = 0, LP = 0;
+    std::map<std::string, Extender> cache;
+    std::vector<std::vector<u64>> moddown;   // [levelP][i]: MForm((p_0..p_levelP)^-1 mod q_i)  (:24-49)
+    u64 *ws = nullptr;                       // cxInv, c2, acc0, acc1: 4 polys of [batch][L][N]
+    size_t ws_words = 0;
+    int *d_limbs = nullptr;                  // scratch list of limb indices for the MAC kernel
+};
+
+namespace {
+
+template <typename T>
+cudaError_t upload(T **dst, const std::vector<T> &v) {
+    cudaError_t e = cudaMalloc(dst, sizeof(T) * std::max<size_t>(v.size(), 1));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*dst, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice);
+}
+
+// GenModUpConstants (:95-166) for source limbs S and target limbs T of the ring, plus the centring scalars
+int get_extender(b200_keyswitch *ks, const std::vector<int> &src, const std::vector<int> &dst, bool centred, Extender **out) {
+    std::string key = centred ? "c" : "n";
+    for (int s : src) key += "s" + std::to_string(s);
+    for (int t : dst) key += "t" + std::to_string(t);
+    auto it = ks->cache.find(key);
+    if (it != ks->cache.end()) { *out = &it->second; return 0; }
+    b200_ctx *ctx = ks->ctx;
+    const int ns = (int)src.size(), nt = (int)dst.size();
+    if (ns > EXT_MAX_SRC) { b200_set_error("basis extension: too many source limbs"); return B200_EINVAL; }
+    std::vector<u64> S(ns), T(nt);
+    for (int i = 0; i < ns; ++i) S[i] = ctx->sub[src[i]].q;
+    for (int j = 0; j < nt; ++j) T[j] = ctx->sub[dst[j]].q;
+    std::vector<u64> half(ns, 0), qinvqi(ns), qmodp((size_t)nt * ns), vq((size_t)nt * (ns + 1)), sub(nt, 0);
+    for (int i = 0; i < ns; ++i) {
+        u64 star = 1;
+        for (int j = 0; j < ns; ++j) if (j != i) star = hm::mulmod(star, S[j] % S[i], S[i]);
+        qinvqi[i] = hm::mform(hm::invmod_prime(star, S[i]), S[i]);
+        if (centred) half[i] = half_of_product_mod(S, S[i]);
+    }
+    for (int j = 0; j < nt; ++j) {
+        const u64 pj = T[j];
+        for (int i = 0; i < ns; ++i) {
+            u64 star = 1;
+            for (int u = 0; u < ns; ++u) if (u != i) star = hm::mulmod(star, S[u] % pj, pj);
+            qmodp[(size_t)j * ns + i] = hm::mform(star, pj);
+        }
+        u64 qmod = 1;
+        for (int i = 0; i < ns; ++i) qmod = hm::mulmod(qmod, S[i] % pj, pj);
+        const u64 v = pj - qmod;
+        vq[(size_t)j * (ns + 1)] = 0;
+        for (int i = 1; i <= ns; ++i) { u64 t = vq[(size_t)j * (ns + 1) + i - 1] + v; vq[(size_t)j * (ns + 1) + i] = t >= pj ? t - pj : t; }
+        if (centred) sub[j] = half_of_product_mod(S, pj);
+    }
+    Extender e;
+    e.ns = ns; e.nt = nt;
+    cudaError_t ce = upload(&e.d_src, src);
+    if (ce == cudaSuccess) ce = upload(&e.d_dst, dst);
+    if (ce == cudaSuccess) ce = upload(&e.d_half, half);
+    if (ce == cudaSuccess) ce = upload(&e.d_qinvqi, qinvqi);
+    if (ce == cudaSuccess) ce = upload(&e.d_qmodp, qmodp);
+    if (ce == cudaSuccess) ce = upload(&e.d_vq, vq);
+    if (ce == cudaSuccess) ce = upload(&e.d_sub, sub);
+    if (ce != cudaSuccess) { e.release(); return b200_cuda_fail(ce, "basis extension constants"); }
+    *out = &(ks->cache[key] = e);
+    return 0;
+}
+
+int run_extend(b200_keyswitch *ks, Extender *e, const u64 *src, u64 *dst, int batch, int mode) {
+    b200_ctx *ctx = ks->ctx;
+    const int N = ctx->N;
+    LaunchScope ls(ctx, "basis_extend", (long long)batch * e->nt);
+    k_basis_extend<<<dim3((N + EXT_THREADS - 1) / EXT_THREADS, batch), EXT_THREADS, sizeof(u64) * e->ns * EXT_THREADS, b200_cur_stream(ctx)>>>(
+        src, dst, ctx->d_consts, e->desc(), N, ctx->L, mode);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int ntt_range(b200_ctx *ctx, const u64 *src, u64 *dst, int batch, int limb0, int nl, bool inverse) {
+    if (nl <= 0) return 0;
+    const size_t off = (size_t)limb0 * ctx->N;
+    Span sp{batch, nl, ctx->L, limb0};
+    int rc = launch_ntt_big(ctx, src + off, dst + off, sp, inverse, 0);
+    if (rc == 1) rc = launch_ntt_generic(ctx, src + off, dst + off, sp, inverse, 0);
+    return rc;
+}
+
+int ensure_ws(b200_keyswitch *ks, size_t words) {
+    if (ks->ws_words >= words) return 0;
+    CUDA_TRY(cudaStreamSynchronize(b200_cur_stream(ks->ctx)));
+    if (ks->ws) CUDA_TRY(cudaFree(ks->ws));
+    ks->ws = nullptr; ks->ws_words = 0;
+    CUDA_TRY(cudaMalloc(&ks->ws, words * sizeof(u64)));
+    ks->ws_words = words;
+    return 0;
+}
+
+std::vector<int> range(int a, int b) { std::vector<int> v; for (int i = a; i < b; ++i) v.push_back(i); return v; }
+
+int check_levels(const b200_keyswitch *ks, int levelQ, int levelP, const char *who) {
+    if (!ks) { b200_set_error(std::string(who) + ": NULL key-switch context"); return B200_EINVAL; }
+    if (levelQ < 0 || levelQ >= ks->LQ || levelP < 0 || levelP >= ks->LP) { b200_set_error(std::string(who) + ": level out of range"); return B200_ESHAPE; }
+    return 0;
+}
+int check_poly(const b200_keyswitch *ks, const b200_poly *p, const char *who) {
+    if (!p || p->ctx != ks->ctx) { b200_set_error(std::string(who) + ": polynomial does not belong to the QP ring"); return B200_ESHAPE; }
+    return 0;
+}
+
+// ModDownQPtoQNTT (:241-258): p1 (QP, NTT) -> out limbs 0..levelQ.  buf: a [batch][L][N] scratch polynomial.
+int mod_down_ntt(b200_keyswitch *ks, int levelQ, int levelP, const u64 *p1, u64 *out, u64 *buf, int batch) {
+    b200_ctx *ctx = ks->ctx;
+    const int LQ = ks->LQ;
+    int rc = ntt_range(ctx, p1, buf, batch, LQ, levelP + 1, true);                              // ringP.INTTLazy(p1P, buffP)
+    if (rc) return rc;
+    Extender *e;
+    if ((rc = get_extender(ks, range(LQ, LQ + levelP + 1), range(0, levelQ + 1), true, &e))) return rc;
+    if ((rc = run_extend(ks, e, buf, buf, batch, 1))) return rc;                                // ModUpPtoQ
+    if ((rc = ntt_range(ctx, buf, buf, batch, 0, levelQ + 1, false))) return rc;                // ringQ.NTTLazy
+    std::vector<u64> sc(levelQ + 1);
+    for (int i = 0; i <= levelQ; ++i) sc[i] = ctx->sub[i].q - ks->moddown[levelP][i];
+    u64 *d_sc = nullptr;
+    CUDA_TRY(cudaMallocAsync(&d_sc, sizeof(u64) * (levelQ + 1), b200_cur_stream(ctx)));
+    CUDA_TRY(cudaMemcpyAsync(d_sc, sc.data(), sizeof(u64) * (levelQ + 1), cudaMemcpyHostToDevice, b200_cur_stream(ctx)));
+    CUDA_TRY(cudaStreamSynchronize(b200_cur_stream(ctx)));   // sc is a stack vector
+    rc = launch_vec_op(ctx, B200_OP_SUB_MULSCALAR_MONT_2Q, buf, p1, out, Span{batch, levelQ + 1, ctx->L, 0}, d_sc);
+    cudaFreeAsync(d_sc, b200_cur_stream(ctx));
+    return rc;
+}
+
+}  // namespace
+
+extern "C" int b200_keyswitch_create(b200_ctx *ctx, int LQ, b200_keyswitch **out) {
+    if (!ctx || !out) { b200_set_error("b200_keyswitch_create: NULL argument"); return B200_EINVAL; }
+    if (LQ < 1 || LQ >= ctx->L) { b200_set_error("b200_keyswitch_create: the ring must hold LQ >= 1 ciphertext primes followed by >= 1 special primes"); return B200_EINVAL; }
+    b200_keyswitch *ks = new b200_keyswitch();
+    ks->ctx = ctx; ks->LQ = LQ; ks->LP = ctx->L - LQ;
+    ks->moddown.assign(ks->LP, std::vector<u64>(LQ));
+    for (int i = 0; i < LQ; ++i) {   // genmodDownConstants (:24-49)
+        const u64 qi = ctx->sub[i].q;
+        u64 prod = 1;
+        for (int j = 0; j < ks->LP; ++j) {
+            prod = hm::mulmod(prod, ctx->sub[LQ + j].q % qi, qi);
+            ks->moddown[j][i] = hm::mform(hm::invmod_prime(prod, qi), qi);
+        }
+    }
+    cudaSetDevice(ctx->device);
+    if (cudaMalloc(&ks->d_limbs, sizeof(int) * ctx->L) != cudaSuccess) { delete ks; return b200_cuda_fail(cudaGetLastError(), "b200_keyswitch_create"); }
+    *out = ks;
+    return 0;
+}
+extern "C" void b200_keyswitch_destroy(b200_keyswitch *ks) {
+    if (!ks) return;
+    cudaSetDevice(ks->ctx->device);
+    for (auto &kv : ks->cache) kv.second.release();
+    cudaFree(ks->ws); cudaFree(ks->d_limbs);
+    delete ks;
+}
+
+// BasisExtender.ModUpQtoP (:184-198, direction 0) / ModUpPtoQ (:203-217, direction 1): lazy words exactly as Go leaves them
+extern "C" int b200_mod_up(b200_keyswitch *ks, int direction, int levelQ, int levelP, const b200_poly *in, b200_poly *out) {
+    if (int rc = check_levels(ks, levelQ, levelP, "b200_mod_up")) return rc;
+    if (int rc = check_poly(ks, in, "b200_mod_up")) return rc;
+    if (int rc = check_poly(ks, out, "b200_mod_up")) return rc;
+    if (in->batch != out->batch) { b200_set_error("b200_mod_up: batch sizes differ"); return B200_ESHAPE; }
+    CUDA_TRY(cudaSetDevice(ks->ctx->device));
+    Extender *e;
+    const std::vector<int> q = range(0, levelQ + 1), p = range(ks->LQ, ks->LQ + levelP + 1);
+    if (int rc = get_extender(ks, direction == 0 ? q : p, direction == 0 ? p : q, true, &e)) return rc;
+    return run_extend(ks, e, in->d, out->d, in->batch, 0);
+}
+
+extern "C" int b200_mod_down_ntt(b200_keyswitch *ks, int levelQ, int levelP, const b200_poly *p1, b200_poly *p2) {
+    if (int rc = check_levels(ks, levelQ, levelP, "b200_mod_down_ntt")) return rc;
+    if (int rc = check_poly(ks, p1, "b200_mod_down_ntt")) return rc;
+    if (int rc = check_poly(ks, p2, "b200_mod_down_ntt")) return rc;
+    if (p1->batch != p2->batch) { b200_set_error("b200_mod_down_ntt: batch sizes differ"); return B200_ESHAPE; }
+    CUDA_TRY(cudaSetDevice(ks->ctx->device));
+    const size_t words = (size_t)p1->batch * ks->ctx->L * ks->ctx->N;
+    if (int rc = ensure_ws(ks, words)) return rc;
+    return mod_down_ntt(ks, levelQ, levelP, p1->d, p2->d, ks->ws, p1->batch);
+}
+
+// rlwe.Evaluator.GadgetProduct (NTT-domain operands, levelP >= 1): evaluator_gadget_product.go:16-30,123-188,455-478
+extern "C" int b200_gadget_product(b200_keyswitch *ks, int levelQ, int levelP, const b200_poly *cx, const b200_poly *key,
+                                   b200_poly *ct0, b200_poly *ct1) {
+    if (int rc = check_levels(ks, levelQ, levelP, "b200_gadget_product")) return rc;
+    for (const b200_poly *p : {cx, key, (const b200_poly *)ct0, (const b200_poly *)ct1})
+        if (int rc = check_poly(ks, p, "b200_gadget_product")) return rc;
+    if (levelP < 1) { b200_set_error("b200_gadget_product: the single-special-prime / bit-decomposition variant is not implemented"); return B200_EINVAL; }
+    b200_ctx *ctx = ks->ctx;
+    const int nbPi = levelP + 1, beta = (levelQ + levelP + 1) / (levelP + 1), LQ = ks->LQ, B = cx->batch, N = ctx->N;
+    if (key->batch < 2 * beta) { b200_set_error("b200_gadget_product: the key must hold 2*beta polynomials [digit][component]"); return B200_ESHAPE; }
+    if (ct0->batch != B || ct1->batch != B || ct0->d == ct1->d) { b200_set_error("b200_gadget_product: outputs must be two distinct polynomials of the input's batch size"); return B200_ESHAPE; }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const size_t words = (size_t)B * ctx->L * N;
+    if (int rc = ensure_ws(ks, 4 * words)) return rc;
+    u64 *cxinv = ks->ws, *c2 = ks->ws + words, *acc0 = ks->ws + 2 * words, *acc1 = ks->ws + 3 * words;
+    int rc = ntt_range(ctx, cx->d, cxinv, B, 0, levelQ + 1, true);                               // ringQ.INTT(cxNTT, cxInvNTT)
+    if (rc) return rc;
+    // limbs touched by the multiply-accumulate: Q_0..Q_levelQ and P_0..P_levelP
+    std::vector<int> limbs = range(0, levelQ + 1);
+    for (int j = 0; j <= levelP; ++j) limbs.push_back(LQ + j);
+    CUDA_TRY(cudaMemcpyAsync(ks->d_limbs, limbs.data(), sizeof(int) * limbs.size(), cudaMemcpyHostToDevice, b200_cur_stream(ctx)));
+    CUDA_TRY(cudaStreamSynchronize(b200_cur_stream(ctx)));
+    for (int d = 0; d < beta && rc == 0; ++d) {
+        const int st = d * nbPi, ed = std::min(st + nbPi, levelQ + 1);
+        std::vector<int> dst;
+        for (int j = 0; j <= levelQ; ++j) if (j < st || j >= ed) dst.push_back(j);
+        for (int j = 0; j <= levelP; ++j) dst.push_back(LQ + j);
+        if (ed - st == 1) {                                                                      // single-limb digit (:402-428)
+            Extender *e;   // only used as a cached holder of the target list
+            if ((rc = get_extender(ks, range(st, ed), dst, false, &e))) break;
+            LaunchScope ls(ctx, "decompose_single", (long long)B * (int)dst.size());
+            k_decompose_single<<<dim3((N + 255) / 256, B), 256, 0, b200_cur_stream(ctx)>>>(cxinv, c2, ctx->d_consts, st, e->d_dst, (int)dst.size(), N, ctx->L);
+        } else {                                                                                 // exact centred conversion (:430-500)
+            Extender *e;
+            if ((rc = get_extender(ks, range(st, ed), dst, true, &e))) break;
+            if ((rc = run_extend(ks, e, cxinv, c2, B, 1))) break;
+        }
+        // DecomposeSingleNTT (:466-477): NTT of every limb outside the digit, and of the P limbs
+        if ((rc = ntt_range(ctx, c2, c2, B, 0, st, false))) break;
+        if ((rc = ntt_range(ctx, c2, c2, B, ed, levelQ + 1 - ed, false))) break;
+        if ((rc = ntt_range(ctx, c2, c2, B, LQ, levelP + 1, false))) break;
+        const u64 *k0 = key->d + (size_t)(2 * d) * ctx->L * N, *k1 = key->d + (size_t)(2 * d + 1) * ctx->L * N;
+        {
+            int chunks = (N + 255) / 256;
+            if (chunks > 256) chunks = 256;
+            LaunchScope ls(ctx, "gadget_mac", (long long)B * (int)limbs.size());
+            k_gadget_mac<<<dim3(chunks, B * (int)limbs.size()), 256, 0, b200_cur_stream(ctx)>>>(cx->d, c2, k0, k1, acc0, acc1, ctx->d_consts,
+                                                                                               ks->d_limbs, (int)limbs.size(), st, ed, N, ctx->L, d == 0);
+        }
+        CUDA_TRY(cudaGetLastError());
+    }
+    if (rc) return rc;
+    if ((rc = mod_down_ntt(ks, levelQ, levelP, acc0, ct0->d, c2, B))) return rc;                 // eval.ModDown, NTT -> NTT (:40-45)
+    return mod_down_ntt(ks, levelQ, levelP, acc1, ct1->d, c2, B);
+}

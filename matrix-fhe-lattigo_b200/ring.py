@@ -325,6 +325,36 @@ class Ring:
         return bool((a.get()[:, : self.level + 1] == b.get()[:, : self.level + 1]).all())
 
 
+class KeySwitcher:
+    """ring.BasisExtender + ring.Decomposer + rlwe.Evaluator.GadgetProduct over one QP ring.
+    `ringQP` is a Ring over Q_0..Q_{LQ-1}, P_0..P_{LP-1}; all polynomials use its [batch][LQ+LP][N] layout."""
+
+    def __init__(self, ringQP, LQ):
+        self.ring, self.LQ, self.LP = ringQP, LQ, ringQP.ModuliChainLength() - LQ
+        self.h = C.c_void_p()
+        rc = lib().b200_keyswitch_create(ringQP._ctx.h, LQ, C.byref(self.h))
+        if rc == -1:
+            raise ValueError(lib().b200_last_error().decode())
+        check(rc)
+
+    def ModUpQtoP(self, levelQ, levelP, polQ, polP):   # ring/basis_extension.go:184-198
+        check(lib().b200_mod_up(self.h, 0, levelQ, levelP, polQ.h, polP.h))
+
+    def ModUpPtoQ(self, levelP, levelQ, polP, polQ):   # :203-217
+        check(lib().b200_mod_up(self.h, 1, levelQ, levelP, polP.h, polQ.h))
+
+    def ModDownQPtoQNTT(self, levelQ, levelP, p1, p2):   # :241-258
+        check(lib().b200_mod_down_ntt(self.h, levelQ, levelP, p1.h, p2.h))
+
+    def GadgetProduct(self, levelQ, levelP, cx, key, ct0, ct1):   # core/rlwe/evaluator_gadget_product.go:16-30
+        check(lib().b200_gadget_product(self.h, levelQ, levelP, cx.h, key.h, ct0.h, ct1.h))
+
+    def __del__(self):
+        if getattr(self, "h", None) and capi._lib is not None:
+            capi._lib.b200_keyswitch_destroy(self.h)
+            self.h = None
+
+
 def _mk_binary(name, code):
     def f(self, p1, p2, p3):
         self._vec(code, p1, p2, p3)

@@ -80,6 +80,9 @@ def lib():
             "ref_3n_forward": (None, [C.c_void_p, P64, P64, C.c_int]),
             "ref_3n_backward": (None, [C.c_void_p, P64, P64, C.c_int]),
             "ref_div_by_last_modulus_ntt": (None, [C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_int, P64, P64, C.c_int]),
+            "ref_gen_modup_constants": (C.c_void_p, [P64, C.c_int, P64, C.c_int]), "ref_muc_free": (None, [C.c_void_p]),
+            "ref_basis_extend": (None, [C.c_void_p, P64, P64, PI, C.c_int, C.c_int, P64]),
+            "ref_decompose_single": (None, [u64, P64, P64, C.c_int, C.c_int, P64]),
             "ref_fill_uniform": (None, [u64, u64, u64, u64, C.c_int, P64]),
             "ref_num_threads": (C.c_int, []),
             "ref_3n_batch": (None, [C.POINTER(C.c_void_p), C.c_int, P64, C.c_int, C.c_int, C.c_int]),
@@ -306,3 +309,138 @@ def py_3n_ntt(N, q, omega, coeffs):
             acc = (acc * x + int(c)) % q
         out.append(acc)
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# RNS basis extension, decomposition and gadget product: ring/basis_extension.go,
+# core/rlwe/evaluator_gadget_product.go.  Constants use Python big ints; the per-coefficient loops are C.
+# ---------------------------------------------------------------------------------------------
+class ModUpConstants:
+    """ring.GenModUpConstants(Q, P) (basis_extension.go:95-166)."""
+
+    def __init__(self, Q, P):
+        self.Q, self.P = [int(q) for q in Q], [int(p) for p in P]
+        qa, pa = _arr(self.Q), _arr(self.P)
+        self.h = lib().ref_gen_modup_constants(_p(qa), len(self.Q), _p(pa), len(self.P))
+
+    def extend(self, p1, targets=None, half=None):
+        """multSum of reconstructRNS[Centered] for the given target indices: lazy words, [len(targets)][N]."""
+        p1 = _arr(p1)
+        ns, N = p1.shape
+        assert ns == len(self.Q)
+        targets = list(range(len(self.P))) if targets is None else list(targets)
+        t = np.ascontiguousarray(np.asarray(targets, dtype=np.int32))
+        out = np.empty((len(targets), N), dtype=np.uint64)
+        h = _arr(half) if half is not None else None
+        lib().ref_basis_extend(self.h, _p(p1), _p(h) if h is not None else None, t.ctypes.data_as(PI), len(targets), N, _p(out))
+        return out
+
+    def __del__(self):
+        if getattr(self, "h", None) and _lib is not None:
+            _lib.ref_muc_free(self.h)
+            self.h = None
+
+
+def _prod(xs):
+    r = 1
+    for x in xs:
+        r *= int(x)
+    return r
+
+
+class BasisExtender:
+    """ring.BasisExtender (basis_extension.go:12-73,184-279) over moduli chains Q and P."""
+
+    def __init__(self, Q, P):
+        self.Q, self.P = [int(q) for q in Q], [int(p) for p in P]
+        self.QtoP = [ModUpConstants(self.Q[: i + 1], self.P) for i in range(len(self.Q))]
+        self.PtoQ = [ModUpConstants(self.P[: i + 1], self.Q) for i in range(len(self.P))]
+        rinv = lambda q: pow(2**64, 1, q)
+        # genmodDownConstants (:24-49): Montgomery form of (p_0 ... p_j)^-1 mod q_i
+        self.modDownPtoQ = [[(pow(_prod(self.P[: j + 1]), -1, q) * rinv(q)) % q for q in self.Q] for j in range(len(self.P))]
+
+    def ModUpQtoP(self, levelQ, levelP, polQ):
+        """:184-198  polQ [levelQ+1][N] -> polP [levelP+1][N] (lazy words exactly as the Go code leaves them)."""
+        QHalf = _prod(self.Q[: levelQ + 1]) >> 1
+        buff = np.stack([vec_op("AddScalar", q, polQ[i], scalar=QHalf % q) for i, q in enumerate(self.Q[: levelQ + 1])])
+        ext = self.QtoP[levelQ].extend(buff, range(levelP + 1))
+        return np.stack([vec_op("SubScalar", p, ext[j], scalar=QHalf % p) for j, p in enumerate(self.P[: levelP + 1])])
+
+    def ModUpPtoQ(self, levelP, levelQ, polP):
+        """:203-217"""
+        PHalf = _prod(self.P[: levelP + 1]) >> 1
+        buff = np.stack([vec_op("AddScalar", p, polP[j], scalar=PHalf % p) for j, p in enumerate(self.P[: levelP + 1])])
+        ext = self.PtoQ[levelP].extend(buff, range(levelQ + 1))
+        return np.stack([vec_op("SubScalar", q, ext[i], scalar=PHalf % q) for i, q in enumerate(self.Q[: levelQ + 1])])
+
+    def ModDownQPtoQNTT(self, levelQ, levelP, p1Q, p1P, ringsQ, ringsP):
+        """:241-258  (inputs NTT domain) -> p2Q [levelQ+1][N], canonical."""
+        buffP = np.stack([ringsP[j].INTT(p1P[j]) for j in range(levelP + 1)])
+        buffQ = self.ModUpPtoQ(levelP, levelQ, buffP)
+        out = []
+        for i, q in enumerate(self.Q[: levelQ + 1]):
+            b = ringsQ[i].NTT(buffQ[i] % np.uint64(q))
+            out.append(vec_op("SubThenMulScalarMontgomeryTwoModulus", q, b, p1Q[i], scalar=q - self.modDownPtoQ[levelP][i]))
+        return np.stack(out)
+
+
+def decompose_and_split(Q, P, levelQ, levelP, nbPi, digit, p0Q):
+    """ring.Decomposer.DecomposeAndSplit (basis_extension.go:381-502).  Returns (p1Q [levelQ+1][N], p1P [levelP+1][N]);
+    the limbs of the digit itself are returned as zeros (the caller overwrites them, rlwe/evaluator_gadget_product.go:466-472)."""
+    Q, P = [int(q) for q in Q], [int(p) for p in P]
+    p0Q = _arr(p0Q)
+    N = p0Q.shape[1]
+    st = digit * nbPi
+    decompLvl = nbPi - 2 if levelQ > nbPi * (digit + 1) - 1 else (levelQ % nbPi) - 1
+    outQ = np.zeros((levelQ + 1, N), dtype=np.uint64)
+    outP = np.zeros((levelP + 1, N), dtype=np.uint64)
+    if decompLvl < 0:
+        T = _arr(Q[: levelQ + 1] + P[: levelP + 1])
+        tmp = np.empty((len(T), N), dtype=np.uint64)
+        lib().ref_decompose_single(Q[st], _p(np.ascontiguousarray(p0Q[st])), _p(T), len(T), N, _p(tmp))
+        outQ[:], outP[:] = tmp[: levelQ + 1], tmp[levelQ + 1:]
+        return outQ, outP
+    ed = min(st + nbPi, levelQ + 1)
+    # NewDecomposer (:319-377): constants over Qi = Q[st : st+decompLvl+2], targets = Q (whole chain) + P[:nbPi]
+    muc = ModUpConstants(Q[st: st + decompLvl + 2], Q + P[:nbPi])
+    QBig = _prod(Q[st:ed])
+    QHalf = QBig >> 1
+    half = [QHalf % q for q in Q[st:ed]]
+    tq = [j for j in range(levelQ + 1) if not (st <= j < ed)]
+    tp = [len(Q) + j for j in range(levelP + 1)]
+    ext = muc.extend(np.ascontiguousarray(p0Q[st:ed]), tq + tp, half=half)
+    for k, j in enumerate(tq):
+        outQ[j] = vec_op("SubScalar", Q[j], ext[k], scalar=QHalf % Q[j])
+    for k, j in enumerate(range(levelP + 1)):
+        outP[j] = vec_op("SubScalar", P[j], ext[len(tq) + k], scalar=QHalf % P[j])
+    return outQ, outP
+
+
+def gadget_product(ringsQ, ringsP, levelQ, levelP, cx_ntt, key):
+    """rlwe.Evaluator.GadgetProduct for NTT-domain operands and levelP > 0
+    (core/rlwe/evaluator_gadget_product.go:16-30, 33-45, 123-188, 455-478).
+    cx_ntt: [levelQ+1][N]; key[i][c]: (Q part [LQ][N], P part [LP][N]) for digit i, component c, NTT + Montgomery form.
+    Returns (ct0, ct1), each [levelQ+1][N], canonical."""
+    Q = [r.q for r in ringsQ]
+    P = [r.q for r in ringsP]
+    nbPi = levelP + 1
+    beta = (levelQ + levelP + 1) // (levelP + 1)
+    cx_inv = np.stack([ringsQ[i].INTT(cx_ntt[i]) for i in range(levelQ + 1)])
+    N = cx_inv.shape[1]
+    accQ = [np.zeros((levelQ + 1, N), dtype=np.uint64) for _ in range(2)]
+    accP = [np.zeros((levelP + 1, N), dtype=np.uint64) for _ in range(2)]
+    for d in range(beta):
+        c2Q, c2P = decompose_and_split(Q, P, levelQ, levelP, nbPi, d, cx_inv)
+        st, ed = d * nbPi, d * nbPi + nbPi
+        for x in range(levelQ + 1):
+            c2Q[x] = cx_ntt[x] if st <= x < ed else ringsQ[x].NTT(c2Q[x] % np.uint64(Q[x]))
+        for j in range(levelP + 1):
+            c2P[j] = ringsP[j].NTT(c2P[j] % np.uint64(P[j]))
+        for c in range(2):
+            kq, kp = key[d][c]
+            for x in range(levelQ + 1):   # MulCoeffsMontgomeryLazy[ThenAddLazy] + Reduce: canonical sum
+                accQ[c][x] = vec_op("Add", Q[x], accQ[c][x], vec_op("MulCoeffsMontgomery", Q[x], kq[x], c2Q[x]))
+            for j in range(levelP + 1):
+                accP[c][j] = vec_op("Add", P[j], accP[c][j], vec_op("MulCoeffsMontgomery", P[j], kp[j], c2P[j]))
+    be = BasisExtender(Q, P)
+    return tuple(be.ModDownQPtoQNTT(levelQ, levelP, accQ[c], accP[c], ringsQ, ringsP) for c in range(2))

@@ -726,6 +726,99 @@ EXPORT void ref_div_by_last_modulus_ntt(int kind, void *const *rings, int nl, in
 }
 
 /* ---------------------------------------------------------------------------
+ * RNS basis extension: ring/basis_extension.go
+ * ------------------------------------------------------------------------- */
+typedef struct {
+    int ns, nt;          /* source / target modulus counts */
+    u64 *S, *T;
+    u64 *qoverqiinvqi;   /* [ns]        ((Q/q_i)^-1 mod q_i), Montgomery form          :117-129 */
+    u64 *qoverqimodp;    /* [nt][ns]    (Q/q_i mod p_j), Montgomery form                :131-142 */
+    u64 *vtimesqmodp;    /* [nt][ns+1]  (-v*Q mod p_j), v = 0..ns                        :145-161 */
+} ref_muc;
+
+/* GenModUpConstants, basis_extension.go:95-166 */
+EXPORT ref_muc *ref_gen_modup_constants(const u64 *Q, int nq, const u64 *P, int np) {
+    ref_muc *m = calloc(1, sizeof *m);
+    m->ns = nq; m->nt = np;
+    m->S = malloc(sizeof(u64) * nq); m->T = malloc(sizeof(u64) * np);
+    memcpy(m->S, Q, sizeof(u64) * nq); memcpy(m->T, P, sizeof(u64) * np);
+    m->qoverqiinvqi = malloc(sizeof(u64) * nq);
+    m->qoverqimodp = malloc(sizeof(u64) * (size_t)np * nq);
+    m->vtimesqmodp = malloc(sizeof(u64) * (size_t)np * (nq + 1));
+    for (int i = 0; i < nq; i++) {
+        u64 qi = Q[i], brc[2]; ref_gen_bred_constant(qi, brc);
+        u64 qinv = ref_gen_mred_constant(qi);
+        u64 star = ref_mform(1, qi, brc);
+        for (int j = 0; j < nq; j++) if (j != i) star = ref_mred(star, ref_mform(Q[j], qi, brc), qi, qinv);
+        /* ModexpMontgomery(star, qi-2): Montgomery form of the inverse */
+        u64 acc = ref_mform(1, qi, brc), base = star;
+        for (u64 e = qi - 2; e; e >>= 1) { if (e & 1) acc = ref_mred(acc, base, qi, qinv); base = ref_mred(base, base, qi, qinv); }
+        m->qoverqiinvqi[i] = acc;
+        for (int j = 0; j < np; j++) {
+            u64 pj = P[j], brp[2]; ref_gen_bred_constant(pj, brp);
+            u64 pinv = ref_gen_mred_constant(pj), st = 1;
+            for (int u = 0; u < nq; u++) if (u != i) st = ref_mred(st, ref_mform(Q[u], pj, brp), pj, pinv);
+            m->qoverqimodp[(size_t)j * nq + i] = ref_mform(st, pj, brp);
+        }
+    }
+    for (int j = 0; j < np; j++) {
+        u64 pj = P[j], brp[2]; ref_gen_bred_constant(pj, brp);
+        u64 pinv = ref_gen_mred_constant(pj), qmod = 1;
+        for (int i = 0; i < nq; i++) qmod = ref_mred(qmod, ref_mform(Q[i], pj, brp), pj, pinv);
+        u64 v = pj - qmod, *row = m->vtimesqmodp + (size_t)j * (nq + 1);
+        row[0] = 0;
+        for (int i = 1; i < nq + 1; i++) row[i] = cred(row[i - 1] + v, pj);
+    }
+    return m;
+}
+EXPORT void ref_muc_free(ref_muc *m) {
+    if (m) { free(m->S); free(m->T); free(m->qoverqiinvqi); free(m->qoverqimodp); free(m->vtimesqmodp); free(m); }
+}
+
+/* One coefficient of reconstructRNS[Centered] (:504-594) + multSum (:597-673).
+ * half == NULL: ModUpExact (:282-308).  half != NULL: the centered variant used by DecomposeAndSplit (:430-470).
+ * src[i] = word of source limb i; dst[j] receives the lazy result of multSum for target j in `targets`. */
+static void ext_one(const ref_muc *m, const u64 *src, const u64 *half, const int *targets, int ntargets, u64 *dst) {
+    u64 y[64];
+    double vi = 0;
+    for (int i = 0; i < m->ns; i++) {
+        u64 qi = m->S[i];
+        y[i] = ref_mred(src[i] + (half ? half[i] : 0), m->qoverqiinvqi[i], qi, ref_gen_mred_constant(qi));
+        vi += (double)y[i] / (double)qi;
+    }
+    const u64 v = (u64)vi;
+    for (int t = 0; t < ntargets; t++) {
+        const int j = targets[t];
+        const u64 pj = m->T[j], pinv = ref_gen_mred_constant(pj);
+        u128 acc = 0;
+        for (int i = 0; i < m->ns; i++) acc += (u128)y[i] * m->qoverqimodp[(size_t)j * m->ns + i];
+        const u64 hhi = mulhi((u64)acc * pinv, pj);
+        dst[t] = (u64)(acc >> 64) - hhi + pj + m->vtimesqmodp[(size_t)j * (m->ns + 1) + v];
+    }
+}
+/* p1 = [ns][N] source limbs, p2 = [ntargets][N]; targets = indices into the constants' target list */
+EXPORT void ref_basis_extend(const ref_muc *m, const u64 *p1, const u64 *half, const int *targets, int ntargets, int N, u64 *p2) {
+    u64 src[64], dst[128];
+    for (int x = 0; x < N; x++) {
+        for (int i = 0; i < m->ns; i++) src[i] = p1[(size_t)i * N + x];
+        ext_one(m, src, half, targets, ntargets, dst);
+        for (int t = 0; t < ntargets; t++) p2[(size_t)t * N + x] = dst[t];
+    }
+}
+/* single-limb digit of DecomposeAndSplit (:402-428): centred lift of one limb to the targets */
+EXPORT void ref_decompose_single(u64 q, const u64 *p0, const u64 *T, int nt, int N, u64 *p1) {
+    for (int j = 0; j < N; j++) {
+        u64 coeff = p0[j], pos = 1, neg = 0;
+        if (coeff >= (q >> 1)) { coeff = q - coeff; pos = 0; neg = 1; }
+        for (int i = 0; i < nt; i++) {
+            u64 brc[2]; ref_gen_bred_constant(T[i], brc);
+            const u64 tmp = ref_bred_add(coeff, T[i], brc);
+            p1[(size_t)i * N + j] = tmp * pos + (T[i] - tmp) * neg;
+        }
+    }
+}
+
+/* ---------------------------------------------------------------------------
  * Synthetic inputs: splitmix64 counter generator, rejection-sampled with the
  * prime's bit mask like ring/sampler_uniform.go:69-95.  Shared by C / Python / CUDA harness.
  * ------------------------------------------------------------------------- */

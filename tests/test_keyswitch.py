@@ -1,0 +1,164 @@
+"""RNS basis extension, ModDown and the key-switch gadget product.
+
+CPU part: the oracle restatement of ring/basis_extension.go against big-integer ground truth, as the
+reference does in ring/ring_test.go:707-884 (testExtendBasis), and an exact end-to-end property of the
+gadget product (a noiseless RNS gadget key returns (cx, cx*s) bit for bit).
+GPU part: b200_mod_up / b200_mod_down_ntt / b200_gadget_product through the C ABI against that oracle."""
+import numpy as np
+import pytest
+
+from conftest import QI60
+import b200ring
+from oracle import oracle as O
+
+
+def chains(kind, N, LQ, LP):
+    if kind == "std":
+        Q, P = QI60[:LQ], QI60[LQ: LQ + LP]
+        mk = lambda q: O.Pow2SubRing(N, q)
+    else:
+        pr = O.find_3n_rns_primes(N, 60, LQ + LP)
+        Q, P = pr[:LQ], pr[LQ:]
+        mk = lambda q: O.ThreeNSubRing(N, q)
+    return Q, P, [mk(q) for q in Q], [mk(p) for p in P]
+
+
+def gadget_key(Q, P, levelQ, levelP, N, s_ntt_Q, s_ntt_P):
+    """Noiseless RNS gadget: g_d = P (Q/D_d) ((Q/D_d)^-1 mod D_d); component 0 = g_d, component 1 = g_d * s.
+    NTT domain, Montgomery form (how rlwe stores evaluation keys, core/rlwe/keygenerator.go:70-71)."""
+    nbPi, beta = levelP + 1, (levelQ + levelP + 1) // (levelP + 1)
+    Qp, Pp = O._prod(Q[: levelQ + 1]), O._prod(P[: levelP + 1])
+    key = []
+    for d in range(beta):
+        D = O._prod(Q[d * nbPi: min((d + 1) * nbPi, levelQ + 1)])
+        g = Pp * (Qp // D) * pow(Qp // D, -1, D)
+        comps = []
+        for c in range(2):
+            def limb(m, s):
+                gm = (g % m) * pow(2, 64, m) % m
+                return np.full(N, gm, dtype=np.uint64) if c == 0 else np.array([gm * int(v) % m for v in s], dtype=np.uint64)
+            comps.append((np.stack([limb(q, s_ntt_Q[i]) for i, q in enumerate(Q[: levelQ + 1])]),
+                          np.stack([limb(p, s_ntt_P[j]) for j, p in enumerate(P[: levelP + 1])])))
+        key.append(comps)
+    return key
+
+
+def test_oracle_basis_extension_vs_big_integers():
+    N = 16
+    Q, P, rq, rp = chains("std", N, 4, 3)
+    be = O.BasisExtender(Q, P)
+    rng = np.random.default_rng(1)
+    Qp, Pp = O._prod(Q), O._prod(P)
+    coeffs = [int(rng.integers(0, 2**62)) ** 4 % Qp for _ in range(N)]
+    polQ = np.array([[c % q for c in coeffs] for q in Q], dtype=np.uint64)
+    polP = be.ModUpQtoP(3, 2, polQ)
+    for j, p in enumerate(P):   # exact centred conversion
+        assert [int(v) % p for v in polP[j]] == [(c if c <= Qp // 2 else c - Qp) % p for c in coeffs]
+    back = be.ModUpPtoQ(2, 3, np.array([[c % p for c in coeffs] for p in P], dtype=np.uint64) % np.uint64(2**63))
+    assert back.shape == (4, N)
+    xs = [int(rng.integers(0, 2**62)) ** 7 % (Qp * Pp) for _ in range(N)]
+    xQ = np.stack([rq[i].NTT(np.array([x % q for x in xs], dtype=np.uint64)) for i, q in enumerate(Q)])
+    xP = np.stack([rp[j].NTT(np.array([x % p for x in xs], dtype=np.uint64)) for j, p in enumerate(P)])
+    out = be.ModDownQPtoQNTT(3, 2, xQ, xP, rq, rp)
+    for i, q in enumerate(Q):   # rounded division by P
+        assert [int(v) for v in rq[i].INTT(out[i])] == [((x + Pp // 2) // Pp) % q for x in xs]
+
+
+@pytest.mark.parametrize("kind,N", [("std", 16), ("m3", 24)])
+@pytest.mark.parametrize("LQ,LP", [(5, 2), (4, 2), (3, 3), (6, 3)])
+def test_oracle_gadget_product_exact_property(kind, N, LQ, LP):
+    Q, P, rq, rp = chains(kind, N, LQ, LP)
+    rng = np.random.default_rng(3)
+    s = np.array(rng.integers(0, 3, N), dtype=np.uint64)
+    sQ, sP = np.stack([r.NTT(s) for r in rq]), np.stack([r.NTT(s) for r in rp])
+    key = gadget_key(Q, P, LQ - 1, LP - 1, N, sQ, sP)
+    cx = np.stack([rng.integers(0, q, N, dtype=np.uint64) for q in Q])
+    ct0, ct1 = O.gadget_product(rq, rp, LQ - 1, LP - 1, cx, key)
+    assert (ct0 == cx).all()
+    assert (ct1 == np.stack([O.vec_op("MulCoeffsBarrett", q, cx[i], sQ[i]) for i, q in enumerate(Q)])).all()
+
+
+# ---------------------------------------------------------------------------------------------- GPU
+def _qp_poly(ring, LQ, batch, q_part=None, p_part=None):
+    L, N = ring.ModuliChainLength(), ring.N()
+    h = np.zeros((batch, L, N), dtype=np.uint64)
+    if q_part is not None:
+        h[:, : q_part.shape[1]] = q_part
+    if p_part is not None:
+        h[:, LQ: LQ + p_part.shape[1]] = p_part
+    return ring.NewPoly(batch).set(h)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,N,LQ,LP", [("std", 64, 4, 3), ("m3", 48, 5, 2), ("std", 1 << 12, 6, 2)])
+def test_mod_up_and_mod_down_bit_exact(kind, N, LQ, LP):
+    Q, P, rq, rp = chains(kind, N, LQ, LP)
+    ring = b200ring.NewRing(N, Q + P)
+    ks = b200ring.KeySwitcher(ring, LQ)
+    be = O.BasisExtender(Q, P)
+    rng = np.random.default_rng(9)
+    batch = 2
+    hq = np.stack([np.stack([rng.integers(0, q, N, dtype=np.uint64) for q in Q]) for _ in range(batch)])
+    hp = np.stack([np.stack([rng.integers(0, p, N, dtype=np.uint64) for p in P]) for _ in range(batch)])
+    for levelQ, levelP in ((LQ - 1, LP - 1), (LQ - 2, LP - 1), (LQ - 1, 0)):
+        pin, pout = _qp_poly(ring, LQ, batch, hq, hp), ring.NewPoly(batch)
+        ks.ModUpQtoP(levelQ, levelP, pin, pout)
+        got = pout.get()
+        for b in range(batch):   # the lazy words of ModUpExact + SubScalarBigint, float64 correction included
+            assert (got[b, LQ: LQ + levelP + 1] == be.ModUpQtoP(levelQ, levelP, hq[b])).all(), (levelQ, levelP, b)
+        ks.ModUpPtoQ(levelP, levelQ, pin, pout)
+        got = pout.get()
+        for b in range(batch):
+            assert (got[b, : levelQ + 1] == be.ModUpPtoQ(levelP, levelQ, hp[b])).all()
+        ks.ModDownQPtoQNTT(levelQ, levelP, pin, pout)
+        got = pout.get()
+        for b in range(batch):
+            want = be.ModDownQPtoQNTT(levelQ, levelP, hq[b][: levelQ + 1], hp[b][: levelP + 1], rq, rp)
+            assert (got[b, : levelQ + 1] == want).all()
+    with pytest.raises(b200ring.B200Error):
+        ks.ModUpQtoP(LQ, 0, pin, pout)
+    with pytest.raises(ValueError):
+        b200ring.KeySwitcher(ring, LQ + LP)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,N,LQ,LP", [("std", 32, 5, 2), ("m3", 24, 4, 2), ("m3", 3 * 2**10, 6, 3), ("std", 1 << 13, 7, 2),
+                                          ("m3", 3 * 2**15, 6, 2)])
+def test_gadget_product_matches_oracle_and_exact_property(kind, N, LQ, LP):
+    Q, P, rq, rp = chains(kind, N, LQ, LP)
+    ring = b200ring.NewRing(N, Q + P)
+    ks = b200ring.KeySwitcher(ring, LQ)
+    rng = np.random.default_rng(17)
+    levelQ, levelP = LQ - 1, LP - 1
+    beta = (levelQ + levelP + 1) // (levelP + 1)
+    batch = 2
+    cx = np.stack([np.stack([rng.integers(0, q, N, dtype=np.uint64) for q in Q]) for _ in range(batch)])
+    # (1) random key: parity with the oracle restatement of rlwe.Evaluator.GadgetProduct
+    key = [[(np.stack([rng.integers(0, q, N, dtype=np.uint64) for q in Q]), np.stack([rng.integers(0, p, N, dtype=np.uint64) for p in P]))
+            for _ in range(2)] for _ in range(beta)]
+    hk = np.zeros((2 * beta, LQ + LP, N), dtype=np.uint64)
+    for d in range(beta):
+        for c in range(2):
+            hk[2 * d + c, :LQ], hk[2 * d + c, LQ:] = key[d][c]
+    pkey = ring.NewPoly(2 * beta).set(hk)
+    pcx, ct0, ct1 = _qp_poly(ring, LQ, batch, cx), ring.NewPoly(batch), ring.NewPoly(batch)
+    ks.GadgetProduct(levelQ, levelP, pcx, pkey, ct0, ct1)
+    g0, g1 = ct0.get(), ct1.get()
+    if N <= 3 * 2**10:
+        for b in range(batch):
+            w0, w1 = O.gadget_product(rq, rp, levelQ, levelP, cx[b], key)
+            assert (g0[b, :LQ] == w0).all() and (g1[b, :LQ] == w1).all(), (kind, N, b)
+    # (2) noiseless gadget key: GadgetProduct(cx) == (cx, cx*s) exactly, at any size
+    s = np.array(rng.integers(0, 3, N), dtype=np.uint64)
+    sQ, sP = np.stack([r.NTT(s) for r in rq]), np.stack([r.NTT(s) for r in rp])
+    gk = gadget_key(Q, P, levelQ, levelP, N, sQ, sP)
+    for d in range(beta):
+        for c in range(2):
+            hk[2 * d + c, :LQ], hk[2 * d + c, LQ:] = gk[d][c]
+    pkey.set(hk)
+    ks.GadgetProduct(levelQ, levelP, pcx, pkey, ct0, ct1)
+    g0, g1 = ct0.get(), ct1.get()
+    assert (g0[:, :LQ] == cx).all()
+    for i, q in enumerate(Q):
+        for b in range(batch):
+            assert (g1[b, i] == O.vec_op("MulCoeffsBarrett", q, cx[b, i], sQ[i])).all()
