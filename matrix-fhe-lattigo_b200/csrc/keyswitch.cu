@@ -11,6 +11,9 @@
 // float64 correction index v computed with the same IEEE operations in the same order as the Go code) and writes
 // every requested target limb.  Everything around it is the batched NTT / element-wise kernels of the hot path.
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <string>
 
@@ -133,7 +136,8 @@ struct b200_keyswitch {
     std::vector<std::vector<u64>> moddown;   // [levelP][i]: MForm((p_0..p_levelP)^-1 mod q_i)  (:24-49)
     u64 *ws = nullptr;                       // cxInv, c2, acc0, acc1: 4 polys of [batch][L][N]
     size_t ws_words = 0;
-    int *d_limbs = nullptr;                  // scratch list of limb indices for the MAC kernel
+    u64 *d_moddown = nullptr;                // [LP][LQ]: q_i - moddown[levelP][i], the scalar of the final ModDown pass
+    std::map<int, int *> limb_lists;         // (levelQ, levelP) -> device list of the limbs the multiply-accumulate touches
 };
 
 namespace {
@@ -244,15 +248,8 @@ int mod_down_ntt(b200_keyswitch *ks, int levelQ, int levelP, const u64 *p1, u64 
     if ((rc = get_extender(ks, range(LQ, LQ + levelP + 1), range(0, levelQ + 1), true, &e))) return rc;
     if ((rc = run_extend(ks, e, buf, buf, batch, 1))) return rc;                                // ModUpPtoQ
     if ((rc = ntt_range(ctx, buf, buf, batch, 0, levelQ + 1, false))) return rc;                // ringQ.NTTLazy
-    std::vector<u64> sc(levelQ + 1);
-    for (int i = 0; i <= levelQ; ++i) sc[i] = ctx->sub[i].q - ks->moddown[levelP][i];
-    u64 *d_sc = nullptr;
-    CUDA_TRY(cudaMallocAsync(&d_sc, sizeof(u64) * (levelQ + 1), b200_cur_stream(ctx)));
-    CUDA_TRY(cudaMemcpyAsync(d_sc, sc.data(), sizeof(u64) * (levelQ + 1), cudaMemcpyHostToDevice, b200_cur_stream(ctx)));
-    CUDA_TRY(cudaStreamSynchronize(b200_cur_stream(ctx)));   // sc is a stack vector
-    rc = launch_vec_op(ctx, B200_OP_SUB_MULSCALAR_MONT_2Q, buf, p1, out, Span{batch, levelQ + 1, ctx->L, 0}, d_sc);
-    cudaFreeAsync(d_sc, b200_cur_stream(ctx));
-    return rc;
+    return launch_vec_op(ctx, B200_OP_SUB_MULSCALAR_MONT_2Q, buf, p1, out, Span{batch, levelQ + 1, ctx->L, 0},
+                         ks->d_moddown + (size_t)levelP * LQ);
 }
 
 }  // namespace
@@ -272,7 +269,11 @@ extern "C" int b200_keyswitch_create(b200_ctx *ctx, int LQ, b200_keyswitch **out
         }
     }
     cudaSetDevice(ctx->device);
-    if (cudaMalloc(&ks->d_limbs, sizeof(int) * ctx->L) != cudaSuccess) { delete ks; return b200_cuda_fail(cudaGetLastError(), "b200_keyswitch_create"); }
+    std::vector<u64> sc((size_t)ks->LP * LQ);
+    for (int j = 0; j < ks->LP; ++j)
+        for (int i = 0; i < LQ; ++i) sc[(size_t)j * LQ + i] = ctx->sub[i].q - ks->moddown[j][i];
+    cudaError_t ce = upload(&ks->d_moddown, sc);
+    if (ce != cudaSuccess) { delete ks; return b200_cuda_fail(ce, "b200_keyswitch_create"); }
     *out = ks;
     return 0;
 }
@@ -280,7 +281,8 @@ extern "C" void b200_keyswitch_destroy(b200_keyswitch *ks) {
     if (!ks) return;
     cudaSetDevice(ks->ctx->device);
     for (auto &kv : ks->cache) kv.second.release();
-    cudaFree(ks->ws); cudaFree(ks->d_limbs);
+    cudaFree(ks->ws); cudaFree(ks->d_moddown);
+    for (auto &kv : ks->limb_lists) cudaFree(kv.second);
     delete ks;
 }
 
@@ -320,16 +322,29 @@ extern "C" int b200_gadget_product(b200_keyswitch *ks, int levelQ, int levelP, c
     if (key->batch < 2 * beta) { b200_set_error("b200_gadget_product: the key must hold 2*beta polynomials [digit][component]"); return B200_ESHAPE; }
     if (ct0->batch != B || ct1->batch != B || ct0->d == ct1->d) { b200_set_error("b200_gadget_product: outputs must be two distinct polynomials of the input's batch size"); return B200_ESHAPE; }
     CUDA_TRY(cudaSetDevice(ctx->device));
+    const bool trace = std::getenv("B200_KS_TRACE") != nullptr;
+    auto t_start = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!trace) return;
+        auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[ks] %-14s host %.1f us\n", what, std::chrono::duration<double, std::micro>(now - t_start).count());
+        t_start = now;
+    };
     const size_t words = (size_t)B * ctx->L * N;
     if (int rc = ensure_ws(ks, 4 * words)) return rc;
+    lap("ensure_ws");
     u64 *cxinv = ks->ws, *c2 = ks->ws + words, *acc0 = ks->ws + 2 * words, *acc1 = ks->ws + 3 * words;
     int rc = ntt_range(ctx, cx->d, cxinv, B, 0, levelQ + 1, true);                               // ringQ.INTT(cxNTT, cxInvNTT)
     if (rc) return rc;
+    lap("intt cx");
     // limbs touched by the multiply-accumulate: Q_0..Q_levelQ and P_0..P_levelP
     std::vector<int> limbs = range(0, levelQ + 1);
     for (int j = 0; j <= levelP; ++j) limbs.push_back(LQ + j);
-    CUDA_TRY(cudaMemcpyAsync(ks->d_limbs, limbs.data(), sizeof(int) * limbs.size(), cudaMemcpyHostToDevice, b200_cur_stream(ctx)));
-    CUDA_TRY(cudaStreamSynchronize(b200_cur_stream(ctx)));
+    int *&d_limbs = ks->limb_lists[levelQ * 64 + levelP];
+    if (!d_limbs) {
+        cudaError_t ce = upload(&d_limbs, limbs);
+        if (ce != cudaSuccess) return b200_cuda_fail(ce, "b200_gadget_product limb list");
+    }
     for (int d = 0; d < beta && rc == 0; ++d) {
         const int st = d * nbPi, ed = std::min(st + nbPi, levelQ + 1);
         std::vector<int> dst;
@@ -355,11 +370,15 @@ extern "C" int b200_gadget_product(b200_keyswitch *ks, int levelQ, int levelP, c
             if (chunks > 256) chunks = 256;
             LaunchScope ls(ctx, "gadget_mac", (long long)B * (int)limbs.size());
             k_gadget_mac<<<dim3(chunks, B * (int)limbs.size()), 256, 0, b200_cur_stream(ctx)>>>(cx->d, c2, k0, k1, acc0, acc1, ctx->d_consts,
-                                                                                               ks->d_limbs, (int)limbs.size(), st, ed, N, ctx->L, d == 0);
+                                                                                               d_limbs, (int)limbs.size(), st, ed, N, ctx->L, d == 0);
         }
         CUDA_TRY(cudaGetLastError());
+        lap("digit");
     }
     if (rc) return rc;
     if ((rc = mod_down_ntt(ks, levelQ, levelP, acc0, ct0->d, c2, B))) return rc;                 // eval.ModDown, NTT -> NTT (:40-45)
-    return mod_down_ntt(ks, levelQ, levelP, acc1, ct1->d, c2, B);
+    lap("moddown0");
+    rc = mod_down_ntt(ks, levelQ, levelP, acc1, ct1->d, c2, B);
+    lap("moddown1");
+    return rc;
 }

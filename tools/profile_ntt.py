@@ -134,3 +134,29 @@ if os.environ.get("B200_PROFILE_NEXT"):
     Lq = len(moduli)
     print("rescale DivRoundByLastModulusNTT (L=%d -> %d): %.3f ms for %d polys = %.0f polys/s, %d limb-transforms -> %.0f limb-transforms/s"
           % (Lq, Lq - 1, ms, args.polys, args.polys / (ms * 1e-3), args.polys * Lq, args.polys * Lq / (ms * 1e-3)))
+if os.environ.get("B200_PROFILE_KS"):
+    # key-switch gadget product at the shape of BASELINE config 5: LQ ciphertext primes + LP special primes
+    from oracle import oracle as O
+    LQ, LP, B = int(os.environ.get("KS_LQ", 24)), int(os.environ.get("KS_LP", 6)), int(os.environ.get("KS_B", 8))
+    primes = O.find_3n_rns_primes(N, 60, LQ + LP) if args.ring == "3n" else QI60[:LQ] + [0x1ffffffff6c80001, 0x1ffffffff6140001, 0x1ffffffff5f40001, 0x1ffffffff5700001, 0x1ffffffff4bc0001, 0x1ffffffff4380001][:LP]
+    rqp = b200ring.NewRing(N, primes)
+    rqp.SetStream(torch.cuda.current_stream().cuda_stream)
+    ks = b200ring.KeySwitcher(rqp, LQ)
+    beta = (LQ + LP - 1) // LP
+    mk = lambda n: torch.stack([torch.stack([torch.randint(0, q, (N,), dtype=torch.int64, device="cuda") for q in primes]) for _ in range(n)])
+    cx_t, key_t, o0_t, o1_t = mk(B), mk(2 * beta), mk(B), mk(B)
+    cx, key, o0, o1 = (b200ring.Poly.from_torch(rqp, t) for t in (cx_t, key_t, o0_t, o1_t))
+    for _ in range(2):
+        ks.GadgetProduct(LQ - 1, LP - 1, cx, key, o0, o1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    reps = 5
+    for _ in range(reps):
+        ks.GadgetProduct(LQ - 1, LP - 1, cx, key, o0, o1)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    nt = LQ + beta * (LQ + LP) - sum(min(LP, LQ - d * LP) for d in range(beta)) + 2 * (LP + LQ)
+    print("gadget product ring=%s N=%d LQ=%d LP=%d beta=%d batch=%d: %.3f ms = %.1f key-switches/s, %d limb-transforms each -> %.0f limb-transforms/s"
+          % (args.ring, N, LQ, LP, beta, B, ms, B / (ms * 1e-3), nt, B * nt / (ms * 1e-3)))
+    prof = rqp.Profile(lambda: ks.GadgetProduct(LQ - 1, LP - 1, cx, key, o0, o1))
+    print("   ", {k: round(v["ms"], 3) for k, v in prof.items()})
