@@ -176,6 +176,18 @@ B200_API int b200_mod_down_ntt(b200_keyswitch *ks, int levelQ, int levelP, const
 B200_API int b200_gadget_product(b200_keyswitch *ks, int levelQ, int levelP, const b200_poly *cx, const b200_poly *key,
                         b200_poly *ct0, b200_poly *ct1);
 
+/* Limb-sharded execution of the same gadget product (BASELINE config 5): every rank holds the QP ring
+ * but owns the Q limbs [q0, q1) and the P limbs [p0, p1); the two exchanges of the path are NCCL all-gathers the
+ * caller runs on the polynomials' device memory between these steps (see sharding.gadget_product_sharded):
+ *   1. b200_ntt_limbs(inverse) on the owned Q limbs of cx          -> all-gather the Q limbs of cxinv
+ *   2. b200_ks_decompose_mac: every digit into the owned targets, NTT, multiply-accumulate with the owned key limbs
+ *   3. b200_ntt_limbs(inverse) on the owned P limbs of acc0/acc1   -> all-gather the P limbs
+ *   4. b200_ks_mod_down_limbs: extension P -> owned Q limbs, NTT, final pass -> owned Q limbs of the result */
+B200_API int b200_ntt_limbs(b200_ctx *ctx, const b200_poly *in, b200_poly *out, int limb0, int nl, int inverse, int flags);
+B200_API int b200_ks_decompose_mac(b200_keyswitch *ks, int levelQ, int levelP, const b200_poly *cx, const b200_poly *cxinv,
+                          const b200_poly *key, b200_poly *acc0, b200_poly *acc1, int q0, int q1, int p0, int p1);
+B200_API int b200_ks_mod_down_limbs(b200_keyswitch *ks, int levelQ, int levelP, const b200_poly *acc, b200_poly *out, int q0, int q1);
+
 /* ---- RNS rescale in the NTT domain ------------------------------------------------
  * Ring.DivRoundByLastModulusNTT (round != 0, ring/scaling.go:130-156) / DivFloorByLastModulusNTT (round == 0,
  * ring/scaling.go:6-19) at `level` >= 1 for the whole batch: p1 limbs 0..level-1 = (p0 - [p0]_{q_level}) / q_level.

@@ -445,6 +445,20 @@ static int transform(b200_ctx *ctx, const b200_poly *in, b200_poly *out, int lev
     if (rc == 1) rc = launch_ntt_generic(ctx, in->d, out->d, sp, inverse, flags);
     return rc;
 }
+// Ring.NTT / INTT restricted to limbs [limb0, limb0+nl): what a rank of a limb-sharded ring runs on its share
+extern "C" int b200_ntt_limbs(b200_ctx *ctx, const b200_poly *in, b200_poly *out, int limb0, int nl, int inverse, int flags) {
+    int batch;
+    if (int rc = check_polys(ctx, 0, "b200_ntt_limbs", {in, out}, &batch)) return rc;
+    if (limb0 < 0 || nl < 0 || limb0 + nl > ctx->L) return fail(B200_ESHAPE, "b200_ntt_limbs: limb range out of bounds");
+    if (nl == 0) return 0;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const size_t off = (size_t)limb0 * ctx->N;
+    Span sp{batch, nl, ctx->L, limb0};
+    int rc = launch_ntt_big(ctx, in->d + off, out->d + off, sp, inverse != 0, flags);
+    if (rc == 1) rc = launch_ntt_generic(ctx, in->d + off, out->d + off, sp, inverse != 0, flags);
+    return rc;
+}
+
 extern "C" int b200_ntt(b200_ctx *ctx, const b200_poly *in, b200_poly *out, int level, int flags) {
     return transform(ctx, in, out, level, flags, false, "b200_ntt");
 }

@@ -238,18 +238,98 @@ int check_poly(const b200_keyswitch *ks, const b200_poly *p, const char *who) {
     return 0;
 }
 
-// ModDownQPtoQNTT (:241-258): p1 (QP, NTT) -> out limbs 0..levelQ.  buf: a [batch][L][N] scratch polynomial.
+// A rank's share of the chain: Q limbs [q0, q1) and P limbs [p0, p1) (P indices, i.e. ring limbs LQ+p0 ..).
+// One GPU owns everything: {0, levelQ+1, 0, levelP+1}.
+struct Own { int q0, q1, p0, p1; };
+
+// Final step of ModDownQPtoQNTT (:241-258) on the owned Q limbs.  acc: Q limbs in the NTT domain; its P limbs
+// 0..levelP already in the COEFFICIENT domain (ringP.INTTLazy done, all P limbs present).  buf: scratch polynomial.
+int mod_down_finish(b200_keyswitch *ks, int levelQ, int levelP, const u64 *acc, u64 *out, u64 *buf, int batch, Own o) {
+    b200_ctx *ctx = ks->ctx;
+    const int LQ = ks->LQ, nq = o.q1 - o.q0;
+    if (nq <= 0) return 0;
+    (void)levelQ;
+    Extender *e;
+    int rc = get_extender(ks, range(LQ, LQ + levelP + 1), range(o.q0, o.q1), true, &e);
+    if (rc) return rc;
+    if ((rc = run_extend(ks, e, acc, buf, batch, 1))) return rc;                                // ModUpPtoQ
+    if ((rc = ntt_range(ctx, buf, buf, batch, o.q0, nq, false))) return rc;                     // ringQ.NTTLazy
+    const size_t off = (size_t)o.q0 * ctx->N;
+    return launch_vec_op(ctx, B200_OP_SUB_MULSCALAR_MONT_2Q, buf + off, acc + off, out + off, Span{batch, nq, ctx->L, o.q0},
+                         ks->d_moddown + (size_t)levelP * LQ + o.q0);
+}
+
+// ModDownQPtoQNTT on one GPU: p1 (QP, NTT) -> out limbs 0..levelQ.  buf: a [batch][L][N] scratch polynomial.
 int mod_down_ntt(b200_keyswitch *ks, int levelQ, int levelP, const u64 *p1, u64 *out, u64 *buf, int batch) {
     b200_ctx *ctx = ks->ctx;
     const int LQ = ks->LQ;
-    int rc = ntt_range(ctx, p1, buf, batch, LQ, levelP + 1, true);                              // ringP.INTTLazy(p1P, buffP)
+    // ringP.INTTLazy(p1P, buffP): into the P limbs of buf, then extend from buf; the Q limbs of p1 are read in place
+    int rc = ntt_range(ctx, p1, buf, batch, LQ, levelP + 1, true);
     if (rc) return rc;
     Extender *e;
     if ((rc = get_extender(ks, range(LQ, LQ + levelP + 1), range(0, levelQ + 1), true, &e))) return rc;
-    if ((rc = run_extend(ks, e, buf, buf, batch, 1))) return rc;                                // ModUpPtoQ
-    if ((rc = ntt_range(ctx, buf, buf, batch, 0, levelQ + 1, false))) return rc;                // ringQ.NTTLazy
+    if ((rc = run_extend(ks, e, buf, buf, batch, 1))) return rc;
+    if ((rc = ntt_range(ctx, buf, buf, batch, 0, levelQ + 1, false))) return rc;
     return launch_vec_op(ctx, B200_OP_SUB_MULSCALAR_MONT_2Q, buf, p1, out, Span{batch, levelQ + 1, ctx->L, 0},
                          ks->d_moddown + (size_t)levelP * LQ);
+}
+
+// Digit loop of gadgetProductMultiplePLazy (:123-188) restricted to the owned limbs: decomposition of every digit
+// into the owned targets, their NTT, and the multiply-accumulate with the owned key limbs.  cxinv must hold ALL
+// Q limbs 0..levelQ in the coefficient domain (after the all-gather when sharded); cx the owned Q limbs in the NTT domain.
+int decompose_mac(b200_keyswitch *ks, int levelQ, int levelP, const u64 *cx, const u64 *cxinv, const u64 *key, u64 *c2,
+                  u64 *acc0, u64 *acc1, int B, Own o) {
+    b200_ctx *ctx = ks->ctx;
+    const int nbPi = levelP + 1, beta = (levelQ + levelP + 1) / (levelP + 1), LQ = ks->LQ, N = ctx->N;
+    std::vector<int> limbs = range(o.q0, o.q1);
+    for (int j = o.p0; j < o.p1; ++j) limbs.push_back(LQ + j);
+    if (limbs.empty()) return 0;
+    int *&d_limbs = ks->limb_lists[((o.q0 * 64 + o.q1) * 64 + o.p0) * 64 + o.p1];
+    if (!d_limbs) {
+        cudaError_t ce = upload(&d_limbs, limbs);
+        if (ce != cudaSuccess) return b200_cuda_fail(ce, "gadget product limb list");
+    }
+    int rc = 0;
+    for (int d = 0; d < beta && rc == 0; ++d) {
+        const int st = d * nbPi, ed = std::min(st + nbPi, levelQ + 1);
+        std::vector<int> dst;
+        for (int j = o.q0; j < o.q1; ++j) if (j < st || j >= ed) dst.push_back(j);
+        for (int j = o.p0; j < o.p1; ++j) dst.push_back(LQ + j);
+        if (!dst.empty()) {
+            if (ed - st == 1) {                                                                  // single-limb digit (:402-428)
+                Extender *e;   // only used as a cached holder of the target list
+                if ((rc = get_extender(ks, range(st, ed), dst, false, &e))) break;
+                LaunchScope ls(ctx, "decompose_single", (long long)B * (int)dst.size());
+                k_decompose_single<<<dim3((N + 255) / 256, B), 256, 0, b200_cur_stream(ctx)>>>(cxinv, c2, ctx->d_consts, st, e->d_dst, (int)dst.size(), N, ctx->L);
+            } else {                                                                             // exact centred conversion (:430-500)
+                Extender *e;
+                if ((rc = get_extender(ks, range(st, ed), dst, true, &e))) break;
+                if ((rc = run_extend(ks, e, cxinv, c2, B, 1))) break;
+            }
+            // DecomposeSingleNTT (:466-477): NTT of every owned limb outside the digit, and of the owned P limbs
+            const int a0 = o.q0, a1 = std::min(o.q1, st), b0 = std::max(o.q0, ed), b1 = o.q1;
+            if ((rc = ntt_range(ctx, c2, c2, B, a0, a1 - a0, false))) break;
+            if ((rc = ntt_range(ctx, c2, c2, B, b0, b1 - b0, false))) break;
+            if ((rc = ntt_range(ctx, c2, c2, B, LQ + o.p0, o.p1 - o.p0, false))) break;
+        }
+        const u64 *k0 = key + (size_t)(2 * d) * ctx->L * N, *k1 = key + (size_t)(2 * d + 1) * ctx->L * N;
+        int chunks = (N + 255) / 256;
+        if (chunks > 256) chunks = 256;
+        LaunchScope ls(ctx, "gadget_mac", (long long)B * (int)limbs.size());
+        k_gadget_mac<<<dim3(chunks, B * (int)limbs.size()), 256, 0, b200_cur_stream(ctx)>>>(cx, c2, k0, k1, acc0, acc1, ctx->d_consts,
+                                                                                           d_limbs, (int)limbs.size(), st, ed, N, ctx->L, d == 0);
+        CUDA_TRY(cudaGetLastError());
+    }
+    return rc;
+}
+
+int check_own(const b200_keyswitch *ks, int levelQ, int levelP, Own o, const char *who) {
+    if (o.q0 < 0 || o.q1 > levelQ + 1 || o.q0 > o.q1 || o.p0 < 0 || o.p1 > levelP + 1 || o.p0 > o.p1) {
+        b200_set_error(std::string(who) + ": owned limb ranges out of bounds");
+        return B200_ESHAPE;
+    }
+    (void)ks;
+    return 0;
 }
 
 }  // namespace
@@ -318,67 +398,53 @@ extern "C" int b200_gadget_product(b200_keyswitch *ks, int levelQ, int levelP, c
         if (int rc = check_poly(ks, p, "b200_gadget_product")) return rc;
     if (levelP < 1) { b200_set_error("b200_gadget_product: the single-special-prime / bit-decomposition variant is not implemented"); return B200_EINVAL; }
     b200_ctx *ctx = ks->ctx;
-    const int nbPi = levelP + 1, beta = (levelQ + levelP + 1) / (levelP + 1), LQ = ks->LQ, B = cx->batch, N = ctx->N;
+    const int beta = (levelQ + levelP + 1) / (levelP + 1), B = cx->batch, N = ctx->N;
     if (key->batch < 2 * beta) { b200_set_error("b200_gadget_product: the key must hold 2*beta polynomials [digit][component]"); return B200_ESHAPE; }
     if (ct0->batch != B || ct1->batch != B || ct0->d == ct1->d) { b200_set_error("b200_gadget_product: outputs must be two distinct polynomials of the input's batch size"); return B200_ESHAPE; }
     CUDA_TRY(cudaSetDevice(ctx->device));
-    const bool trace = std::getenv("B200_KS_TRACE") != nullptr;
-    auto t_start = std::chrono::steady_clock::now();
-    auto lap = [&](const char *what) {
-        if (!trace) return;
-        auto now = std::chrono::steady_clock::now();
-        std::fprintf(stderr, "[ks] %-14s host %.1f us\n", what, std::chrono::duration<double, std::micro>(now - t_start).count());
-        t_start = now;
-    };
     const size_t words = (size_t)B * ctx->L * N;
     if (int rc = ensure_ws(ks, 4 * words)) return rc;
-    lap("ensure_ws");
     u64 *cxinv = ks->ws, *c2 = ks->ws + words, *acc0 = ks->ws + 2 * words, *acc1 = ks->ws + 3 * words;
     int rc = ntt_range(ctx, cx->d, cxinv, B, 0, levelQ + 1, true);                               // ringQ.INTT(cxNTT, cxInvNTT)
     if (rc) return rc;
-    lap("intt cx");
-    // limbs touched by the multiply-accumulate: Q_0..Q_levelQ and P_0..P_levelP
-    std::vector<int> limbs = range(0, levelQ + 1);
-    for (int j = 0; j <= levelP; ++j) limbs.push_back(LQ + j);
-    int *&d_limbs = ks->limb_lists[levelQ * 64 + levelP];
-    if (!d_limbs) {
-        cudaError_t ce = upload(&d_limbs, limbs);
-        if (ce != cudaSuccess) return b200_cuda_fail(ce, "b200_gadget_product limb list");
-    }
-    for (int d = 0; d < beta && rc == 0; ++d) {
-        const int st = d * nbPi, ed = std::min(st + nbPi, levelQ + 1);
-        std::vector<int> dst;
-        for (int j = 0; j <= levelQ; ++j) if (j < st || j >= ed) dst.push_back(j);
-        for (int j = 0; j <= levelP; ++j) dst.push_back(LQ + j);
-        if (ed - st == 1) {                                                                      // single-limb digit (:402-428)
-            Extender *e;   // only used as a cached holder of the target list
-            if ((rc = get_extender(ks, range(st, ed), dst, false, &e))) break;
-            LaunchScope ls(ctx, "decompose_single", (long long)B * (int)dst.size());
-            k_decompose_single<<<dim3((N + 255) / 256, B), 256, 0, b200_cur_stream(ctx)>>>(cxinv, c2, ctx->d_consts, st, e->d_dst, (int)dst.size(), N, ctx->L);
-        } else {                                                                                 // exact centred conversion (:430-500)
-            Extender *e;
-            if ((rc = get_extender(ks, range(st, ed), dst, true, &e))) break;
-            if ((rc = run_extend(ks, e, cxinv, c2, B, 1))) break;
-        }
-        // DecomposeSingleNTT (:466-477): NTT of every limb outside the digit, and of the P limbs
-        if ((rc = ntt_range(ctx, c2, c2, B, 0, st, false))) break;
-        if ((rc = ntt_range(ctx, c2, c2, B, ed, levelQ + 1 - ed, false))) break;
-        if ((rc = ntt_range(ctx, c2, c2, B, LQ, levelP + 1, false))) break;
-        const u64 *k0 = key->d + (size_t)(2 * d) * ctx->L * N, *k1 = key->d + (size_t)(2 * d + 1) * ctx->L * N;
-        {
-            int chunks = (N + 255) / 256;
-            if (chunks > 256) chunks = 256;
-            LaunchScope ls(ctx, "gadget_mac", (long long)B * (int)limbs.size());
-            k_gadget_mac<<<dim3(chunks, B * (int)limbs.size()), 256, 0, b200_cur_stream(ctx)>>>(cx->d, c2, k0, k1, acc0, acc1, ctx->d_consts,
-                                                                                               d_limbs, (int)limbs.size(), st, ed, N, ctx->L, d == 0);
-        }
-        CUDA_TRY(cudaGetLastError());
-        lap("digit");
-    }
-    if (rc) return rc;
+    if ((rc = decompose_mac(ks, levelQ, levelP, cx->d, cxinv, key->d, c2, acc0, acc1, B, Own{0, levelQ + 1, 0, levelP + 1}))) return rc;
     if ((rc = mod_down_ntt(ks, levelQ, levelP, acc0, ct0->d, c2, B))) return rc;                 // eval.ModDown, NTT -> NTT (:40-45)
-    lap("moddown0");
-    rc = mod_down_ntt(ks, levelQ, levelP, acc1, ct1->d, c2, B);
-    lap("moddown1");
-    return rc;
+    return mod_down_ntt(ks, levelQ, levelP, acc1, ct1->d, c2, B);
+}
+
+// ---- limb-sharded execution (SURVEY.md 8e / BASELINE config 5): the same gadget product in three device steps,
+// separated by the two exchanges of the path (an all-gather of the coefficient-domain input limbs, and one of the
+// P limbs of the accumulators), which the caller performs with NCCL on the polynomials' device memory.
+extern "C" int b200_ks_decompose_mac(b200_keyswitch *ks, int levelQ, int levelP, const b200_poly *cx, const b200_poly *cxinv,
+                                     const b200_poly *key, b200_poly *acc0, b200_poly *acc1, int q0, int q1, int p0, int p1) {
+    if (int rc = check_levels(ks, levelQ, levelP, "b200_ks_decompose_mac")) return rc;
+    for (const b200_poly *p : {cx, cxinv, key, (const b200_poly *)acc0, (const b200_poly *)acc1})
+        if (int rc = check_poly(ks, p, "b200_ks_decompose_mac")) return rc;
+    const Own o{q0, q1, p0, p1};
+    if (int rc = check_own(ks, levelQ, levelP, o, "b200_ks_decompose_mac")) return rc;
+    if (levelP < 1) { b200_set_error("b200_ks_decompose_mac: needs levelP >= 1"); return B200_EINVAL; }
+    b200_ctx *ctx = ks->ctx;
+    const int beta = (levelQ + levelP + 1) / (levelP + 1), B = cx->batch;
+    if (key->batch < 2 * beta || cxinv->batch != B || acc0->batch != B || acc1->batch != B || acc0->d == acc1->d) {
+        b200_set_error("b200_ks_decompose_mac: batch sizes do not match");
+        return B200_ESHAPE;
+    }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const size_t words = (size_t)B * ctx->L * ctx->N;
+    if (int rc = ensure_ws(ks, words)) return rc;
+    return decompose_mac(ks, levelQ, levelP, cx->d, cxinv->d, key->d, ks->ws, acc0->d, acc1->d, B, o);
+}
+
+extern "C" int b200_ks_mod_down_limbs(b200_keyswitch *ks, int levelQ, int levelP, const b200_poly *acc, b200_poly *out, int q0, int q1) {
+    if (int rc = check_levels(ks, levelQ, levelP, "b200_ks_mod_down_limbs")) return rc;
+    if (int rc = check_poly(ks, acc, "b200_ks_mod_down_limbs")) return rc;
+    if (int rc = check_poly(ks, out, "b200_ks_mod_down_limbs")) return rc;
+    const Own o{q0, q1, 0, 0};
+    if (int rc = check_own(ks, levelQ, levelP, o, "b200_ks_mod_down_limbs")) return rc;
+    if (acc->batch != out->batch) { b200_set_error("b200_ks_mod_down_limbs: batch sizes differ"); return B200_ESHAPE; }
+    b200_ctx *ctx = ks->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const size_t words = (size_t)acc->batch * ctx->L * ctx->N;
+    if (int rc = ensure_ws(ks, words)) return rc;
+    return mod_down_finish(ks, levelQ, levelP, acc->d, out->d, ks->ws, acc->batch, o);
 }

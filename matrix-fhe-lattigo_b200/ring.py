@@ -291,6 +291,10 @@ class Ring:
                                         capi.B200_TREE_ORDER if tree_order else 0))
         return host_out
 
+    def NTTLimbs(self, p1, p2, limb0, nl, inverse=False):
+        """Ring.NTT / INTT on limbs [limb0, limb0+nl) only (a rank's share of a limb-sharded ring)."""
+        check(lib().b200_ntt_limbs(self._ctx.h, p1.h, p2.h, limb0, nl, int(inverse), 0))
+
     # -- fused ring product (BASELINE config 4) --
     def MulPoly(self, p1, p2, p3):
         """p3 = p1 * p2 in the ring (NTT, NTT, MForm, MulCoeffsMontgomery, INTT fused on device)."""
@@ -348,6 +352,13 @@ class KeySwitcher:
 
     def GadgetProduct(self, levelQ, levelP, cx, key, ct0, ct1):   # core/rlwe/evaluator_gadget_product.go:16-30
         check(lib().b200_gadget_product(self.h, levelQ, levelP, cx.h, key.h, ct0.h, ct1.h))
+
+    # limb-sharded steps (see sharding.gadget_product_sharded)
+    def DecomposeMac(self, levelQ, levelP, cx, cxinv, key, acc0, acc1, q0, q1, p0, p1):
+        check(lib().b200_ks_decompose_mac(self.h, levelQ, levelP, cx.h, cxinv.h, key.h, acc0.h, acc1.h, q0, q1, p0, p1))
+
+    def ModDownLimbs(self, levelQ, levelP, acc, out, q0, q1):
+        check(lib().b200_ks_mod_down_limbs(self.h, levelQ, levelP, acc.h, out.h, q0, q1))
 
     def __del__(self):
         if getattr(self, "h", None) and capi._lib is not None:

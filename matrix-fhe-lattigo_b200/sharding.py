@@ -69,3 +69,62 @@ def gather_limbs(local, L, world_size, rank):
     for r in range(world_size):
         out[:, r::world_size, :] = parts[r]
     return out
+
+
+def block_of_rank(n, world_size, rank):
+    """Contiguous share [lo, hi) of n limbs for `rank` (balanced; empty when n < world_size for the last ranks)."""
+    return (rank * n) // world_size, ((rank + 1) * n) // world_size
+
+
+def all_gather_limbs(t, lo_hi_of_rank, world_size):
+    """In-place all-gather of limb blocks of a [batch][L][N] tensor: rank r contributes t[:, lo_r:hi_r, :].
+    Blocks may have different sizes (padded to the largest for the collective)."""
+    import torch
+    import torch.distributed as dist
+    if world_size == 1:
+        return
+    spans = [lo_hi_of_rank(r) for r in range(world_size)]
+    width = max(hi - lo for lo, hi in spans)
+    if width == 0:
+        return
+    rank = dist.get_rank()
+    lo, hi = spans[rank]
+    send = torch.zeros((t.shape[0], width, t.shape[2]), dtype=t.dtype, device=t.device)
+    send[:, : hi - lo] = t[:, lo:hi]
+    recv = [torch.empty_like(send) for _ in range(world_size)]
+    dist.all_gather(recv, send)
+    for r, (a, b) in enumerate(spans):
+        if r != rank and b > a:
+            t[:, a:b] = recv[r][:, : b - a]
+
+
+def gadget_product_sharded(ks, ring, levelQ, levelP, cx_t, key, out0_t, out1_t, rank, world_size):
+    """rlwe.Evaluator.GadgetProduct with the limbs sharded over `world_size` GPUs (BASELINE config 5).
+
+    Every rank holds the QP ring; rank r owns the contiguous Q block block_of_rank(levelQ+1, G, r) and P block
+    block_of_rank(levelP+1, G, r).  cx_t / out*_t: [batch][LQ+LP][N] int64 CUDA tensors; on entry the owned Q limbs
+    of cx_t are valid (NTT domain), on exit the owned Q limbs of out0_t / out1_t hold the result.  `key`: b200 Poly
+    with the evaluation key (only the owned limbs are read).  Two NCCL all-gathers: the coefficient-domain input
+    limbs (levelQ+1 limbs per polynomial) and the P limbs of both accumulators."""
+    import torch
+    from .ring import Poly
+    LQ = ks.LQ
+    q0, q1 = block_of_rank(levelQ + 1, world_size, rank)
+    p0, p1 = block_of_rank(levelP + 1, world_size, rank)
+    cxinv_t, acc0_t, acc1_t = torch.empty_like(cx_t), torch.empty_like(cx_t), torch.empty_like(cx_t)
+    cx, cxinv, acc0, acc1, out0, out1 = (Poly.from_torch(ring, t) for t in (cx_t, cxinv_t, acc0_t, acc1_t, out0_t, out1_t))
+    ring.NTTLimbs(cx, cxinv, q0, q1 - q0, inverse=True)
+    ring.Sync()
+    all_gather_limbs(cxinv_t, lambda r: block_of_rank(levelQ + 1, world_size, r), world_size)
+    torch.cuda.current_stream().synchronize()
+    ks.DecomposeMac(levelQ, levelP, cx, cxinv, key, acc0, acc1, q0, q1, p0, p1)
+    for acc in (acc0, acc1):
+        ring.NTTLimbs(acc, acc, LQ + p0, p1 - p0, inverse=True)
+    ring.Sync()
+    for t in (acc0_t, acc1_t):
+        all_gather_limbs(t, lambda r: tuple(LQ + x for x in block_of_rank(levelP + 1, world_size, r)), world_size)
+    torch.cuda.current_stream().synchronize()
+    ks.ModDownLimbs(levelQ, levelP, acc0, out0, q0, q1)
+    ks.ModDownLimbs(levelQ, levelP, acc1, out1, q0, q1)
+    ring.Sync()
+    return q0, q1
