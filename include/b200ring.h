@@ -176,6 +176,14 @@ B200_API int b200_mod_down_ntt(b200_keyswitch *ks, int levelQ, int levelP, const
 B200_API int b200_gadget_product(b200_keyswitch *ks, int levelQ, int levelP, const b200_poly *cx, const b200_poly *key,
                         b200_poly *ct0, b200_poly *ct1);
 
+/* Ciphertext x ciphertext multiply with relinearisation, NTT domain in and out (BASELINE config 5):
+ * (c0, c1, c2) = tensor(a, b) as b200_tensor, then (out0, out1) = (c0, c1) + GadgetProduct(c2, rlk)
+ * (schemes/ckks/evaluator.go:821-853, core/rlwe/evaluator_evaluationkey.go:125-153).  The reference never composes
+ * this on a 3N ring (matrix_ckks.Evaluator.Mul stops at the tensor product): defined here as those steps in sequence. */
+B200_API int b200_mul_relin(b200_keyswitch *ks, int levelQ, int levelP, const b200_poly *a0, const b200_poly *a1,
+                   const b200_poly *b0, const b200_poly *b1, const b200_poly *rlk, b200_poly *out0, b200_poly *out1,
+                   int mform_first);
+
 /* Limb-sharded execution of the same gadget product (BASELINE config 5): every rank holds the QP ring
  * but owns the Q limbs [q0, q1) and the P limbs [p0, p1); the two exchanges of the path are NCCL all-gathers the
  * caller runs on the polynomials' device memory between these steps (see sharding.gadget_product_sharded):

@@ -448,3 +448,37 @@ extern "C" int b200_ks_mod_down_limbs(b200_keyswitch *ks, int levelQ, int levelP
     if (int rc = ensure_ws(ks, words)) return rc;
     return mod_down_finish(ks, levelQ, levelP, acc->d, out->d, ks->ws, acc->batch, o);
 }
+
+// Ciphertext x ciphertext multiply with relinearisation in the NTT domain (BASELINE config 5):
+// tensor product (schemes/ckks/evaluator.go:821-834, MForm first; schemes/matrix_ckks/evaluator.go:163-173 is the
+// same without MForm) followed by rlwe.Evaluator.Relinearize = GadgetProduct(c2, rlk) added to (c0, c1)
+// (schemes/ckks/evaluator.go:836-853, core/rlwe/evaluator_evaluationkey.go:125-153).  The reference never runs
+// this composition on a 3N ring: it is defined here as exactly these reference steps in sequence.
+extern "C" int b200_mul_relin(b200_keyswitch *ks, int levelQ, int levelP, const b200_poly *a0, const b200_poly *a1,
+                              const b200_poly *b0, const b200_poly *b1, const b200_poly *rlk, b200_poly *out0, b200_poly *out1,
+                              int mform_first) {
+    if (int rc = check_levels(ks, levelQ, levelP, "b200_mul_relin")) return rc;
+    for (const b200_poly *p : {a0, a1, b0, b1, rlk, (const b200_poly *)out0, (const b200_poly *)out1})
+        if (int rc = check_poly(ks, p, "b200_mul_relin")) return rc;
+    b200_ctx *ctx = ks->ctx;
+    const int B = a0->batch, N = ctx->N, beta = (levelQ + levelP + 1) / (levelP + 1);
+    if (levelP < 1) { b200_set_error("b200_mul_relin: needs levelP >= 1"); return B200_EINVAL; }
+    if (a1->batch != B || b0->batch != B || b1->batch != B || out0->batch != B || out1->batch != B || rlk->batch < 2 * beta || out0->d == out1->d) {
+        b200_set_error("b200_mul_relin: batch sizes do not match");
+        return B200_ESHAPE;
+    }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const size_t words = (size_t)B * ctx->L * N;
+    if (int rc = ensure_ws(ks, 8 * words)) return rc;
+    u64 *cxinv = ks->ws, *c2buf = ks->ws + words, *acc0 = ks->ws + 2 * words, *acc1 = ks->ws + 3 * words;
+    u64 *t0 = ks->ws + 4 * words, *t1 = ks->ws + 5 * words, *t2 = ks->ws + 6 * words, *g = ks->ws + 7 * words;
+    const Span spq{B, levelQ + 1, ctx->L, 0};
+    int rc = launch_tensor(ctx, a0->d, a1->d, b0->d, b1->d, t0, t1, t2, spq, mform_first != 0);
+    if (rc) return rc;
+    if ((rc = ntt_range(ctx, t2, cxinv, B, 0, levelQ + 1, true))) return rc;
+    if ((rc = decompose_mac(ks, levelQ, levelP, t2, cxinv, rlk->d, c2buf, acc0, acc1, B, Own{0, levelQ + 1, 0, levelP + 1}))) return rc;
+    if ((rc = mod_down_ntt(ks, levelQ, levelP, acc0, g, c2buf, B))) return rc;
+    if ((rc = launch_vec_op(ctx, B200_OP_ADD, t0, g, out0->d, spq, nullptr))) return rc;          // ringQ.Add(c0, tmpCt.Value[0], opOut.Value[0])
+    if ((rc = mod_down_ntt(ks, levelQ, levelP, acc1, g, c2buf, B))) return rc;
+    return launch_vec_op(ctx, B200_OP_ADD, t1, g, out1->d, spq, nullptr);
+}

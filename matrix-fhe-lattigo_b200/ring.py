@@ -353,6 +353,11 @@ class KeySwitcher:
     def GadgetProduct(self, levelQ, levelP, cx, key, ct0, ct1):   # core/rlwe/evaluator_gadget_product.go:16-30
         check(lib().b200_gadget_product(self.h, levelQ, levelP, cx.h, key.h, ct0.h, ct1.h))
 
+    def MulRelin(self, levelQ, levelP, a0, a1, b0, b1, rlk, out0, out1, mform=True):
+        """ct x ct multiply + relinearisation in the NTT domain: tensor product, GadgetProduct(c2, rlk), add
+        (schemes/ckks/evaluator.go:821-853)."""
+        check(lib().b200_mul_relin(self.h, levelQ, levelP, a0.h, a1.h, b0.h, b1.h, rlk.h, out0.h, out1.h, int(mform)))
+
     # limb-sharded steps (see sharding.gadget_product_sharded)
     def DecomposeMac(self, levelQ, levelP, cx, cxinv, key, acc0, acc1, q0, q1, p0, p1):
         check(lib().b200_ks_decompose_mac(self.h, levelQ, levelP, cx.h, cxinv.h, key.h, acc0.h, acc1.h, q0, q1, p0, p1))

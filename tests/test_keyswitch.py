@@ -162,3 +162,45 @@ def test_gadget_product_matches_oracle_and_exact_property(kind, N, LQ, LP):
     for i, q in enumerate(Q):
         for b in range(batch):
             assert (g1[b, i] == O.vec_op("MulCoeffsBarrett", q, cx[b, i], sQ[i])).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,N,LQ,LP", [("m3", 24, 4, 2), ("m3", 3 * 2**12, 6, 3), ("std", 1 << 12, 5, 2)])
+def test_mul_relin_is_tensor_plus_gadget_product(kind, N, LQ, LP):
+    """BASELINE config 5 (parity unpinned upstream): defined as the reference steps in sequence --
+    tensor product (ckks.mulRelin), Relinearize = GadgetProduct(c2, rlk), Add.  With a noiseless key for s^2 the
+    result is (c0 + c2*s2, c1) exactly."""
+    Q, P, rq, rp = chains(kind, N, LQ, LP)
+    ring = b200ring.NewRing(N, Q + P)
+    ks = b200ring.KeySwitcher(ring, LQ)
+    rng = np.random.default_rng(23)
+    levelQ, levelP = LQ - 1, LP - 1
+    beta = (levelQ + levelP + 1) // (levelP + 1)
+    batch = 2
+    h = [np.stack([np.stack([rng.integers(0, q, N, dtype=np.uint64) for q in Q]) for _ in range(batch)]) for _ in range(4)]
+    a0, a1, b0, b1 = (_qp_poly(ring, LQ, batch, x) for x in h)
+    s2 = np.array(rng.integers(0, 3, N), dtype=np.uint64)
+    sQ, sP = np.stack([r.NTT(s2) for r in rq]), np.stack([r.NTT(s2) for r in rp])
+    gk = gadget_key(Q, P, levelQ, levelP, N, sQ, sP)
+    # rlk: component 0 carries g*s2, component 1 carries 0  (relinearisation key of a noiseless "ciphertext of s^2")
+    hk = np.zeros((2 * beta, LQ + LP, N), dtype=np.uint64)
+    for d in range(beta):
+        hk[2 * d, :LQ], hk[2 * d, LQ:] = gk[d][1]
+    rlk = ring.NewPoly(2 * beta).set(hk)
+    o0, o1 = ring.NewPoly(batch), ring.NewPoly(batch)
+    ks.MulRelin(levelQ, levelP, a0, a1, b0, b1, rlk, o0, o1, mform=True)
+    # the same through the separate entry points
+    c0, c1, c2, g0, g1 = (ring.NewPoly(batch) for _ in range(5))
+    ring.AtLevel(levelQ).TensorProduct(a0, a1, b0, b1, c0, c1, c2, mform=True)
+    ks.GadgetProduct(levelQ, levelP, c2, rlk, g0, g1)
+    rl = ring.AtLevel(levelQ)
+    rl.Add(c0, g0, g0); rl.Add(c1, g1, g1)
+    assert (o0.get()[:, :LQ] == g0.get()[:, :LQ]).all() and (o1.get()[:, :LQ] == g1.get()[:, :LQ]).all()
+    # algebra: out0 = a0 b0 + (a1 b1) s2, out1 = a0 b1 + a1 b0   (slot-wise, mod q)
+    got0, got1 = o0.get(), o1.get()
+    for b in range(batch):
+        for i, q in enumerate(Q):
+            A0, A1, B0, B1 = ([int(v) for v in x[b, i]] for x in h)
+            S = [int(v) for v in sQ[i]]
+            assert [int(v) for v in got0[b, i]] == [(x * y + z * w % q * t) % q for x, y, z, w, t in zip(A0, B0, A1, B1, S)]
+            assert [int(v) for v in got1[b, i]] == [(x * w + z * y) % q for x, y, z, w in zip(A0, B0, A1, B1)]
