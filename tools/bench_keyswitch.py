@@ -1,0 +1,75 @@
+#!/usr/bin/env python3
+"""BASELINE config 5: key-switch gadget product at N = 3*2^15, LQ = 24, LP = 6 (beta = 4), limb-sharded over G GPUs
+with NCCL all-gathers (one of the coefficient-domain input limbs, one of the accumulators' P limbs).
+
+    python tools/bench_keyswitch.py                       # one GPU, b200_gadget_product
+    torchrun --nproc-per-node G tools/bench_keyswitch.py  # G ranks, sharding.gadget_product_sharded
+Prints one JSON line on rank 0 (key-switches/s for the whole job; the batch of ciphertexts is fixed = strong scaling).
+"""
+import argparse
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import b200ring  # noqa: E402
+from b200ring import sharding  # noqa: E402
+from oracle import oracle as O  # noqa: E402  (only to find the 3N-friendly primes of the shape)
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=16)
+ap.add_argument("--lq", type=int, default=24)
+ap.add_argument("--lp", type=int, default=6)
+ap.add_argument("--a", type=int, default=15)
+ap.add_argument("--reps", type=int, default=5)
+args = ap.parse_args()
+rank, local, world = sharding.init_process_group()
+dev = torch.device("cuda", local)
+torch.cuda.set_device(dev)
+N, LQ, LP, B = 3 << args.a, args.lq, args.lp, args.batch
+primes = O.find_3n_rns_primes(N, 60, LQ + LP)
+ring = b200ring.NewRing(N, primes, device=local)
+ring.SetStream(torch.cuda.current_stream().cuda_stream)
+ks = b200ring.KeySwitcher(ring, LQ)
+levelQ, levelP = LQ - 1, LP - 1
+beta = (levelQ + levelP + 1) // (levelP + 1)
+gen = torch.Generator(device=dev); gen.manual_seed(1234)          # same data on every rank
+mk = lambda n: torch.stack([torch.stack([torch.randint(0, q, (N,), dtype=torch.int64, device=dev, generator=gen) for q in primes]) for _ in range(n)])
+cx_t, key_t = mk(B), mk(2 * beta)
+key = b200ring.Poly.from_torch(ring, key_t)
+o0, o1 = torch.zeros_like(cx_t), torch.zeros_like(cx_t)
+
+
+def run():
+    if world == 1:
+        ks.GadgetProduct(levelQ, levelP, b200ring.Poly.from_torch(ring, cx_t), key, b200ring.Poly.from_torch(ring, o0), b200ring.Poly.from_torch(ring, o1))
+    else:
+        sharding.gadget_product_sharded(ks, ring, levelQ, levelP, cx_t, key, o0, o1, rank, world)
+
+
+def barrier():
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+
+
+for _ in range(2):
+    run()
+barrier()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(args.reps):
+    run()
+e1.record()
+barrier()
+ms = sharding.max_over_ranks(e0.elapsed_time(e1) / args.reps, device=dev)
+q0, q1 = sharding.block_of_rank(levelQ + 1, world, rank)
+chk = int(o0[:, q0:q1].sum().item()) & 0xFFFFFFFF
+if rank == 0:
+    print(json.dumps({"workload": "gadget product N=%d LQ=%d LP=%d beta=%d batch=%d" % (N, LQ, LP, beta, B), "n_gpus": world,
+                      "ms": ms, "key_switches_per_s": B / (ms * 1e-3), "limb_transforms_per_s": B * 180 / (ms * 1e-3) if (LQ, LP) == (24, 6) else None,
+                      "allgather_bytes_per_step": B * (LQ + 2 * LP) * N * 8, "checksum_rank0": chk}))
+if world > 1:
+    torch.distributed.destroy_process_group()
