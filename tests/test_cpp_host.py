@@ -9,12 +9,12 @@ from conftest import ROOT
 import b200ring
 
 
-def _build(tmp_path):
+def _build(tmp_path, src="ring_host_test.cpp"):
     b200ring.load_library()
-    exe = str(tmp_path / "ring_host_test")
+    exe = str(tmp_path / src.replace(".cpp", ""))
     lib = os.path.join(ROOT, "matrix-fhe-lattigo_b200", "lib")
     subprocess.check_call(["g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"),
-                           os.path.join(ROOT, "tests", "cpp", "ring_host_test.cpp"), "-o", exe,
+                           os.path.join(ROOT, "tests", "cpp", src), "-o", exe,
                            "-L" + lib, "-lb200ring", "-Wl,-rpath," + lib])
     return exe
 
@@ -27,4 +27,13 @@ def test_cpp_host_mirror_builds_and_validates(tmp_path):
 @pytest.mark.gpu
 def test_cpp_host_mirror_on_gpu(tmp_path):
     r = subprocess.run([_build(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_all_kernel_families_driver(tmp_path):
+    """tests/cpp/sanitize_driver.cpp: every kernel family once through the C ABI from C++ (round trips, fused product
+    vs operator sequence, host-buffer pipeline, key switch).  Also the binary to put under compute-sanitizer where
+    that tool is available (it is closed on the B200 pool of this build)."""
+    r = subprocess.run([_build(tmp_path, "sanitize_driver.cpp")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout + r.stderr
