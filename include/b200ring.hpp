@@ -127,6 +127,18 @@ class Ring {
     void MulCoeffsMontgomery(const Poly &a, const Poly &b, Poly &c) const { VecOp(B200_OP_MUL_MONT, a, &b, c); }
     void MulCoeffsMontgomeryThenAdd(const Poly &a, const Poly &b, Poly &c) const { VecOp(B200_OP_MUL_MONT_ADD, a, &b, c); }
     void MulCoeffsBarrett(const Poly &a, const Poly &b, Poly &c) const { VecOp(B200_OP_MUL_BARRETT, a, &b, c); }
+    // schemes/ckks/evaluator.go:821-834 (mform) / schemes/matrix_ckks/evaluator.go:163-173 (!mform): fused tensor product
+    void TensorProduct(const Poly &a0, const Poly &a1, const Poly &b0, const Poly &b1, Poly &c0, Poly &c1, Poly &c2, bool mform = true) const {
+        check(b200_tensor(ctx_.get(), a0.handle(), a1.handle(), b0.handle(), b1.handle(), c0.handle(), c1.handle(), c2.handle(), level_, mform));
+    }
+    // ring/scaling.go:130-156 and :6-19 (the Go `buff` argument is internal)
+    void DivRoundByLastModulusNTT(const Poly &p0, Poly &p1) const { check(b200_div_by_last_modulus_ntt(ctx_.get(), p0.handle(), p1.handle(), level_, 1)); }
+    void DivFloorByLastModulusNTT(const Poly &p0, Poly &p1) const { check(b200_div_by_last_modulus_ntt(ctx_.get(), p0.handle(), p1.handle(), level_, 0)); }
+    // NTT / INTT sequence on host-resident polynomials, copies overlapped with compute
+    void TransformHost(const std::vector<uint64_t> &in, std::vector<uint64_t> &out, const std::vector<int> &ops) const {
+        const size_t per = (size_t)ModuliChainLength() * N();
+        check(b200_transform_host(ctx_.get(), in.data(), out.data(), (int)(in.size() / per), level_, ops.data(), (int)ops.size(), 0));
+    }
     // fused NTT, NTT, MForm, MulCoeffsMontgomery, INTT (BASELINE config 4)
     void MulPoly(const Poly &a, const Poly &b, Poly &c) const { check(b200_polymul(ctx_.get(), a.handle(), b.handle(), c.handle(), level_)); }
     // NumberTheoreticTransformer (ring/ntt.go:15-22) for one prime, host slices
@@ -139,6 +151,30 @@ class Ring {
     Ring(std::shared_ptr<b200_ctx> c, int level) : ctx_(std::move(c)), level_(level) {}
     std::shared_ptr<b200_ctx> ctx_;
     int level_;
+};
+
+// ring.BasisExtender + ring.Decomposer + rlwe.Evaluator.GadgetProduct over one QP ring (Q limbs first)
+class KeySwitcher {
+  public:
+    KeySwitcher(const Ring &ringQP, int LQ) : ring_(ringQP) {
+        b200_keyswitch *k = nullptr;
+        check(b200_keyswitch_create(ringQP.handle(), LQ, &k));
+        ks_.reset(k, b200_keyswitch_destroy);
+    }
+    void ModUpQtoP(int levelQ, int levelP, const Poly &polQ, Poly &polP) const { check(b200_mod_up(ks_.get(), 0, levelQ, levelP, polQ.handle(), polP.handle())); }
+    void ModUpPtoQ(int levelP, int levelQ, const Poly &polP, Poly &polQ) const { check(b200_mod_up(ks_.get(), 1, levelQ, levelP, polP.handle(), polQ.handle())); }
+    void ModDownQPtoQNTT(int levelQ, int levelP, const Poly &p1, Poly &p2) const { check(b200_mod_down_ntt(ks_.get(), levelQ, levelP, p1.handle(), p2.handle())); }
+    void GadgetProduct(int levelQ, int levelP, const Poly &cx, const Poly &key, Poly &ct0, Poly &ct1) const {
+        check(b200_gadget_product(ks_.get(), levelQ, levelP, cx.handle(), key.handle(), ct0.handle(), ct1.handle()));
+    }
+    void MulRelin(int levelQ, int levelP, const Poly &a0, const Poly &a1, const Poly &b0, const Poly &b1, const Poly &rlk, Poly &o0, Poly &o1,
+                  bool mform = true) const {
+        check(b200_mul_relin(ks_.get(), levelQ, levelP, a0.handle(), a1.handle(), b0.handle(), b1.handle(), rlk.handle(), o0.handle(), o1.handle(), mform));
+    }
+
+  private:
+    Ring ring_;
+    std::shared_ptr<b200_keyswitch> ks_;
 };
 
 inline Poly::Poly(const Ring &r, int batch) : batch_(batch) {
