@@ -149,6 +149,19 @@ B200_API int b200_poly_download(b200_poly *p, uint64_t *host, size_t n_words);
 B200_API int b200_ntt(b200_ctx *ctx, const b200_poly *in, b200_poly *out, int level, int flags);
 B200_API int b200_intt(b200_ctx *ctx, const b200_poly *in, b200_poly *out, int level, int flags);
 
+/* ---- wire format -------------------------------------------------------------
+ * Poly.BinarySize / WriteTo / MarshalBinary / ReadFrom / UnmarshalBinary (ring/poly.go:97-160): the polynomial is a
+ * structs.Matrix[uint64] (utils/structs/matrix.go:57-128, vector.go:43-100) -- u64 limb count, then per limb a u64
+ * length and the words, little-endian.  `b` selects the polynomial of a batched handle; limbs 0..level are written.
+ * Unmarshal accepts at most L limbs of exactly N words (anything else is B200_ESHAPE and leaves the polynomial
+ * untouched), reports the level found (rows-1) and the bytes consumed, and leaves limbs above it unchanged. */
+B200_API int b200_poly_binary_size(const b200_ctx *ctx, int level, size_t *out);
+B200_API int b200_poly_marshal(const b200_poly *p, int b, int level, void *buf, size_t cap, size_t *written);
+B200_API int b200_poly_unmarshal(b200_poly *p, int b, const void *buf, size_t len, int *level_out, size_t *consumed);
+/* SubRing.Factors (ring/subring.go:45, :333-360): unique prime factors of Modulus-1, ascending; returns the count
+ * (out may be NULL to query it) or a negative error. */
+B200_API int b200_ctx_factors(const b200_ctx *ctx, int limb, uint64_t *out, int cap);
+
 /* ---- element-wise family: p3 = op(p1, p2 [, p3]) (ring/operations.go, ring/vec_ops.go) -------
  * p2 may be NULL for unary ops.  For *_SCALAR / MULSCALAR ops `scalars` holds one word per limb
  * (level+1 of them; Montgomery form where the Go method says so); otherwise NULL. */

@@ -44,7 +44,7 @@ class Poly {
     Poly(const Ring &r, int batch = 1);
     Poly(const Poly &) = delete;
     Poly &operator=(const Poly &) = delete;
-    Poly(Poly &&o) noexcept : h_(o.h_), words_(o.words_), batch_(o.batch_) { o.h_ = nullptr; }
+    Poly(Poly &&o) noexcept : h_(o.h_), words_(o.words_), n_(o.n_), batch_(o.batch_) { o.h_ = nullptr; }
     ~Poly() { if (h_) b200_poly_free(h_); }
     int Batch() const { return batch_; }
     // Poly.Coeffs[limb] of polynomial b  <->  a host slice of >= N words
@@ -60,11 +60,24 @@ class Poly {
         check(b200_poly_download(h_, v.data(), v.size()));
         return v;
     }
+    // Poly.MarshalBinary / UnmarshalBinary (ring/poly.go:97-160) of polynomial b: structs.Matrix[uint64] bytes
+    std::vector<unsigned char> MarshalBinary(int b, int level) const {
+        std::vector<unsigned char> buf(8 + (size_t)(level + 1) * (8 + 8 * n_));
+        size_t n = 0;
+        check(b200_poly_marshal(h_, b, level, buf.data(), buf.size(), &n));
+        buf.resize(n);
+        return buf;
+    }
+    int UnmarshalBinary(int b, const std::vector<unsigned char> &data, size_t *consumed = nullptr) {   // returns the level read
+        int level = -1;
+        check(b200_poly_unmarshal(h_, b, data.data(), data.size(), &level, consumed));
+        return level;
+    }
     b200_poly *handle() const { return h_; }
 
   private:
     b200_poly *h_ = nullptr;
-    size_t words_ = 0;
+    size_t words_ = 0, n_ = 0;
     int batch_ = 0;
 };
 
@@ -180,6 +193,7 @@ class KeySwitcher {
 inline Poly::Poly(const Ring &r, int batch) : batch_(batch) {
     check(b200_poly_alloc(r.handle(), batch, &h_));
     words_ = (size_t)batch * r.ModuliChainLength() * r.N();
+    n_ = (size_t)r.N();
 }
 
 }  // namespace ring

@@ -24,6 +24,10 @@ SYMBOLS = {
     "b200_ctx_ring_type": (C.c_int, [VP]),
     "b200_ctx_subring": (C.c_int, [VP, C.c_int, P64]),
     "b200_ctx_roots": (C.c_int, [VP, C.c_int, C.c_int, P64, C.c_size_t]),
+    "b200_ctx_factors": (C.c_int, [VP, C.c_int, P64, C.c_int]),
+    "b200_poly_binary_size": (C.c_int, [VP, C.c_int, C.POINTER(C.c_size_t)]),
+    "b200_poly_marshal": (C.c_int, [VP, C.c_int, C.c_int, VP, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "b200_poly_unmarshal": (C.c_int, [VP, C.c_int, VP, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
     "b200_poly_alloc": (C.c_int, [VP, C.c_int, C.POINTER(VP)]),
     "b200_poly_wrap": (C.c_int, [VP, VP, C.c_int, C.POINTER(VP)]),
     "b200_poly_free": (None, [VP]),
@@ -57,6 +61,7 @@ SYMBOLS = {
 
 B200_LAZY, B200_TREE_ORDER = 1, 2
 ENODEVICE = -2
+B200_EINVAL, B200_ENODEVICE, B200_ECUDA, B200_ESHAPE, B200_ENOMEM = -1, -2, -3, -4, -5
 
 
 class B200Error(RuntimeError):

@@ -420,6 +420,76 @@ extern "C" int b200_poly_download(b200_poly *p, uint64_t *host, size_t n_words) 
     return 0;
 }
 
+// ---- wire format ------------------------------------------------------------------
+// ring.Poly serialises as structs.Matrix[uint64] (ring/poly.go:97-160, utils/structs/matrix.go:57-128,
+// utils/structs/vector.go:43-100): u64 row count, then per limb a u64 length followed by the words, all
+// little-endian.  The device layout is the same limb-major stream without the 8-byte headers, so each limb is
+// one contiguous copy straight between the wire buffer and HBM.
+static inline void put_le64(unsigned char *p, u64 v) { for (int i = 0; i < 8; ++i) p[i] = (unsigned char)(v >> (8 * i)); }
+static inline u64 get_le64(const unsigned char *p) { u64 v = 0; for (int i = 0; i < 8; ++i) v |= (u64)p[i] << (8 * i); return v; }
+
+extern "C" int b200_poly_binary_size(const b200_ctx *ctx, int level, size_t *out) {
+    if (!ctx || !out) return fail(B200_EINVAL, "b200_poly_binary_size: NULL argument");
+    if (level < 0 || level >= ctx->L) return fail(B200_ESHAPE, "b200_poly_binary_size: level out of range");
+    *out = 8 + (size_t)(level + 1) * (8 + (size_t)ctx->N * 8);
+    return 0;
+}
+extern "C" int b200_poly_marshal(const b200_poly *p, int b, int level, void *buf, size_t cap, size_t *written) {
+    if (!p || !buf) return fail(B200_EINVAL, "b200_poly_marshal: NULL argument");
+    const b200_ctx *ctx = p->ctx;
+    if (b < 0 || b >= p->batch) return fail(B200_ESHAPE, "b200_poly_marshal: polynomial index out of range");
+    if (level < 0 || level >= ctx->L) return fail(B200_ESHAPE, "b200_poly_marshal: level out of range");
+    const size_t N = (size_t)ctx->N, row = 8 + N * 8, need = 8 + (size_t)(level + 1) * row;
+    if (cap < need) return fail(B200_ESHAPE, "b200_poly_marshal: buffer smaller than BinarySize()");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    unsigned char *w = static_cast<unsigned char *>(buf);
+    put_le64(w, (u64)(level + 1));
+    for (int l = 0; l <= level; ++l) {
+        unsigned char *r = w + 8 + (size_t)l * row;
+        put_le64(r, (u64)N);
+        CUDA_TRY(cudaMemcpyAsync(r + 8, p->d + ((size_t)b * ctx->L + l) * N, N * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (written) *written = need;
+    return 0;
+}
+extern "C" int b200_poly_unmarshal(b200_poly *p, int b, const void *buf, size_t len, int *level_out, size_t *consumed) {
+    if (!p || !buf) return fail(B200_EINVAL, "b200_poly_unmarshal: NULL argument");
+    const b200_ctx *ctx = p->ctx;
+    if (b < 0 || b >= p->batch) return fail(B200_ESHAPE, "b200_poly_unmarshal: polynomial index out of range");
+    const unsigned char *r = static_cast<const unsigned char *>(buf);
+    if (len < 8) return fail(B200_ESHAPE, "b200_poly_unmarshal: truncated input (no row count)");
+    const u64 rows = get_le64(r);
+    if (rows > (u64)ctx->L) return fail(B200_ESHAPE, "b200_poly_unmarshal: more limbs than the ring has moduli");
+    const size_t N = (size_t)ctx->N, row = 8 + N * 8;
+    // validate every header before touching the device so a malformed stream leaves the polynomial unchanged
+    size_t off = 8;
+    for (u64 l = 0; l < rows; ++l, off += row) {
+        if (len < off + 8) return fail(B200_ESHAPE, "b200_poly_unmarshal: truncated input (limb header)");
+        if (get_le64(r + off) != (u64)N) return fail(B200_ESHAPE, "b200_poly_unmarshal: limb length differs from the ring degree");
+        if (len < off + row) return fail(B200_ESHAPE, "b200_poly_unmarshal: truncated input (limb data)");
+    }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    for (u64 l = 0; l < rows; ++l)
+        CUDA_TRY(cudaMemcpyAsync(p->d + ((size_t)b * ctx->L + l) * N, r + 8 + (size_t)l * row + 8, N * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));   // the caller may reuse `buf` on return
+    if (level_out) *level_out = (int)rows - 1;
+    if (consumed) *consumed = off;
+    return 0;
+}
+// SubRing.Factors (ring/subring.go:45): unique prime factors of Modulus-1, ascending -- what
+// subRingParametersLiteral stores next to PrimitiveRoot (ring/subring.go:333-360).  Returns the count.
+extern "C" int b200_ctx_factors(const b200_ctx *ctx, int limb, uint64_t *out, int cap) {
+    if (!ctx) return fail(B200_EINVAL, "b200_ctx_factors: ctx is NULL");
+    if (limb < 0 || limb >= ctx->L) return fail(B200_ESHAPE, "b200_ctx_factors: limb out of range");
+    const std::vector<u64> f = hm::unique_factors(ctx->sub[limb].q - 1);
+    if (out) {
+        if (cap < (int)f.size()) return fail(B200_ESHAPE, "b200_ctx_factors: output too small");
+        for (size_t i = 0; i < f.size(); ++i) out[i] = f[i];
+    }
+    return (int)f.size();
+}
+
 // ---- dispatch ---------------------------------------------------------------------------------------
 static int check_polys(b200_ctx *ctx, int level, const char *who, std::initializer_list<const b200_poly *> ps, int *batch) {
     if (!ctx) return fail(B200_EINVAL, std::string(who) + ": ctx is NULL");

@@ -87,9 +87,16 @@ __device__ __forceinline__ unsigned hi32(u64 x) { return (unsigned)(x >> 32); }
 // x*w mod q in [0, 4q) for ANY 64-bit x.  The quotient estimate t drops the low partial product and the
 // low halves of the cross products of x*ws, so it is at most 2 below floor(x*ws/2^64); the remainder is
 // accumulated as x*w + t*(2^64 - q) on the low 64 bits (2 wide + 4 narrow multiply-adds, no subtraction).
+#ifndef B200_SHOUP_MULHI
+#define B200_SHOUP_MULHI 0
+#endif
 __device__ __forceinline__ u64 shoup4(u64 x, u64 w, u64 ws, u64 nq) {
     const unsigned x0 = lo32(x), x1 = hi32(x);
+#if B200_SHOUP_MULHI
+    const u64 t = mulwide_u32(x1, hi32(ws)) + __umulhi(x0, hi32(ws)) + __umulhi(x1, lo32(ws));
+#else
     const u64 t = mulwide_u32(x1, hi32(ws)) + hi32(mulwide_u32(x0, hi32(ws))) + hi32(mulwide_u32(x1, lo32(ws)));
+#endif
     const unsigned t0 = lo32(t), t1 = hi32(t);
     const u64 r = madwide_u32(t0, lo32(nq), mulwide_u32(x0, lo32(w)));
     unsigned r1 = hi32(r);

@@ -174,6 +174,44 @@ class Poly:
         check(lib().b200_poly_download_limb(self.h, b, limb, out.ctypes.data_as(capi.P64), len(out)))
         return out
 
+    # -- wire format (ring/poly.go:97-160): structs.Matrix[uint64], little-endian --
+    def BinarySize(self, level=None):
+        out = C.c_size_t()
+        check(lib().b200_poly_binary_size(self.ring._ctx.h, self.ring.level if level is None else level, C.byref(out)))
+        return out.value
+
+    def MarshalBinary(self, b=0, level=None):
+        """Poly.MarshalBinary for polynomial `b` of the batch, limbs 0..level (default: the ring's level)."""
+        level = self.ring.level if level is None else level
+        buf = np.empty(self.BinarySize(level), dtype=np.uint8)
+        n = C.c_size_t()
+        check(lib().b200_poly_marshal(self.h, b, level, buf.ctypes.data_as(C.c_void_p), buf.size, C.byref(n)))
+        return buf[: n.value].tobytes()
+
+    def UnmarshalBinary(self, data, b=0):
+        """Poly.UnmarshalBinary into polynomial `b`; returns (level found, bytes consumed)."""
+        a = np.frombuffer(bytes(data), dtype=np.uint8)
+        lvl, used = C.c_int(), C.c_size_t()
+        check(lib().b200_poly_unmarshal(self.h, b, a.ctypes.data_as(C.c_void_p), a.size, C.byref(lvl), C.byref(used)))
+        return lvl.value, used.value
+
+    def WriteTo(self, w, b=0, level=None):
+        """Poly.WriteTo: writes exactly BinarySize() bytes on the binary file object `w`."""
+        data = self.MarshalBinary(b, level)
+        w.write(data)
+        return len(data)
+
+    def ReadFrom(self, r, b=0):
+        """Poly.ReadFrom: consumes one serialised polynomial from the binary file object `r`."""
+        head = r.read(8)
+        if len(head) != 8:
+            raise B200Error(capi.B200_ESHAPE, "Poly.ReadFrom: truncated input (no row count)")
+        rows = int.from_bytes(head, "little")
+        if rows > self.ring.ModuliChainLength():
+            raise B200Error(capi.B200_ESHAPE, "Poly.ReadFrom: more limbs than the ring has moduli")
+        body = r.read(rows * (8 + 8 * self.ring.N()))
+        return self.UnmarshalBinary(head + body, b)[1]
+
     def Copy(self, other):
         self.set(other.get() if isinstance(other, Poly) else other)
 
@@ -205,6 +243,33 @@ class Ring:
 
     def Type(self):
         return self._type
+
+    # -- parameters literal (ring/ring.go:560-608, ring/subring.go:330-360) --
+    def parametersLiteral(self):
+        """ringParametersLiteral: one subRingParametersLiteral per prime, field for field as the Go struct.
+        Reference quirks kept on purpose: a 3N SubRing reports Type Standard (subring.go:114-123), LogN =
+        bits.Len64(N-1) (so N = 3*2^15 gives 17) and PrimitiveRoot = omega (subring.go:165)."""
+        out = []
+        for i, s in enumerate(self.SubRings):
+            n = lib().b200_ctx_factors(self._ctx.h, i, None, 0)
+            if n < 0:
+                check(n)
+            f = (C.c_uint64 * max(n, 1))()
+            rc = lib().b200_ctx_factors(self._ctx.h, i, f, n)
+            if rc < 0:
+                check(rc)
+            out.append({"Type": 0, "LogN": (self._N - 1).bit_length(), "NthRoot": self.NthRoot() // self._N,
+                        "Modulus": s.Modulus, "Factors": [int(f[k]) for k in range(n)],
+                        "PrimitiveRoot": s.Root if self._type == Matrix else s.PrimitiveRoot})
+        return out
+
+    def MarshalJSON(self):
+        """Ring.MarshalJSON (ring/ring.go:587-589): the bytes encoding/json produces for the literal."""
+        import json
+        return json.dumps(self.parametersLiteral(), separators=(",", ":")).encode()
+
+    def MarshalBinary(self):   # ring/ring.go:577-579
+        return self.MarshalJSON()
 
     def Is3N(self):   # ring/ring.go:353 quirk: true for powers of two as well
         return _is_valid_ring_degree_for_3n(self._N)
@@ -429,6 +494,40 @@ def NewRing(N, Moduli, device=0, roots=None):
     """ring.NewRing (ring/ring.go:264-272): 3N transformer iff N % 3 == 0 and 3N = 2^a 3^(b+1)."""
     is3n = N % 3 == 0 and _is_valid_ring_degree_for_3n(N)
     return NewRingFromType(N, Moduli, Matrix if is3n else Standard, device, roots)
+
+
+def UnmarshalJSON(data, device=0, N=None):
+    """Ring.UnmarshalJSON / UnmarshalBinary (ring/ring.go:582-657, ring/subring.go:362-417).
+
+    Power-of-two rings are rebuilt from the literal exactly as the reference does (same primitive root, hence the
+    same tables).  A literal written by a 3N ring (NthRoot == 3) does not determine N -- the reference stores
+    only bits.Len64(N-1) and itself rebuilds a wrong power-of-two ring from it -- so it is refused unless the caller
+    supplies the ring degree with `N=`."""
+    import json
+    lit = json.loads(bytes(data).decode())
+    if not isinstance(lit, list) or not lit:
+        raise ValueError("invalid ring literal")
+    for k, p in enumerate(lit):
+        if p["Type"] == int(ConjugateInvariant):
+            raise ValueError("ConjugateInvariant rings are outside the B200 hot path (SURVEY.md section 2)")
+        if p["Type"] != int(Standard):
+            raise ValueError("invalid ring type")
+        if k and (p["LogN"] != lit[0]["LogN"] or p["NthRoot"] != lit[0]["NthRoot"]):
+            raise ValueError("invalid SubRings: all SubRings must have the same ring degree and NthRoot")
+    nth = lit[0]["NthRoot"]
+    moduli = [int(p["Modulus"]) for p in lit]
+    roots = [int(p["PrimitiveRoot"]) for p in lit]
+    if nth == 3:
+        if N is None:
+            raise ValueError("3N ring literal does not determine the ring degree (LogN = %d); pass N=" % lit[0]["LogN"])
+        if (N - 1).bit_length() != lit[0]["LogN"] or N % 3 != 0 or not _is_valid_ring_degree_for_3n(N):
+            raise ValueError("N does not match the literal")
+        return NewRingFromType(N, moduli, Matrix, device, roots)
+    if nth < 2:
+        raise ValueError("invalid ring type: NthRoot must be at least 2N but is %dN" % nth)
+    if nth != 2:
+        raise ValueError("invalid NthRoot: only 2N (Standard) and 3N (Matrix) rings are supported")
+    return NewRingFromType(1 << lit[0]["LogN"], moduli, Standard, device, roots)
 
 
 def NewPoly(ring, batch=1):

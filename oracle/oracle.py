@@ -444,3 +444,56 @@ def gadget_product(ringsQ, ringsP, levelQ, levelP, cx_ntt, key):
                 accP[c][j] = vec_op("Add", P[j], accP[c][j], vec_op("MulCoeffsMontgomery", P[j], kp[j], c2P[j]))
     be = BasisExtender(Q, P)
     return tuple(be.ModDownQPtoQNTT(levelQ, levelP, accQ[c], accP[c], ringsQ, ringsP) for c in range(2))
+
+
+# ---- wire format -------------------------------------------------------------------
+def poly_marshal(coeffs):
+    """ring.Poly.MarshalBinary (ring/poly.go:97-160) = structs.Matrix[uint64].WriteTo (utils/structs/matrix.go:76-104)
+    over structs.Vector[uint64].WriteTo (utils/structs/vector.go:82-102): u64 row count, then per row a u64 length and
+    the words, little-endian (utils/buffer/writer.go:325).  coeffs: list of 1-D uint64 rows (rows may be ragged)."""
+    out = [len(coeffs).to_bytes(8, "little")]
+    for row in coeffs:
+        row = np.asarray(row, dtype="<u8")
+        out.append(len(row).to_bytes(8, "little"))
+        out.append(row.tobytes())
+    return b"".join(out)
+
+
+def poly_unmarshal(data):
+    """ring.Poly.UnmarshalBinary (matrix.go:119-153, vector.go ReadFrom): returns (rows, bytes consumed)."""
+    rows = int.from_bytes(data[:8], "little")
+    off, out = 8, []
+    for _ in range(rows):
+        n = int.from_bytes(data[off:off + 8], "little")
+        off += 8
+        if len(data) < off + 8 * n:
+            raise ValueError("truncated input")
+        out.append(np.frombuffer(data, dtype="<u8", count=n, offset=off).astype(np.uint64))
+        off += 8 * n
+    return out, off
+
+
+def unique_factors(m):
+    """utils/factorization.GetFactors (factorization.go:19-86): unique prime factors, ascending."""
+    buf = np.zeros(64, dtype=np.uint64)
+    n = lib().ref_unique_factors(m, _p(buf))
+    return [int(x) for x in buf[:n]]
+
+
+def ring_literal_json(N, moduli, nthroot_over_n, roots=None):
+    """Ring.MarshalJSON (ring/ring.go:565-589) of subRingParametersLiteral (ring/subring.go:333-360) in Go's
+    encoding/json form (declaration-order keys, no whitespace).  Type is 0 for Standard and for 3N sub-rings
+    (subring.go:114-123); LogN = bits.Len64(N-1); PrimitiveRoot = smallest primitive root g >= 3 (subring.go:218-251),
+    or omega = g^((q-1)/3N) for a 3N ring (subring.go:165, 255-290) unless given."""
+    import json
+    lit = []
+    for i, q in enumerate(moduli):
+        if roots is not None:
+            root = int(roots[i])
+        elif nthroot_over_n == 3:
+            root = int(lib().ref_find_3n_primitive_root(q, 3 * N))
+        else:
+            root = int(lib().ref_primitive_root(q))
+        lit.append({"Type": 0, "LogN": (N - 1).bit_length(), "NthRoot": nthroot_over_n, "Modulus": int(q),
+                    "Factors": unique_factors(q - 1), "PrimitiveRoot": root})
+    return json.dumps(lit, separators=(",", ":")).encode()

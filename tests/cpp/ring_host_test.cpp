@@ -53,6 +53,20 @@ int main(int argc, char **argv) {
     r.MulPoly(a, b, c2);
     r.NTT(a, a); r.NTT(b, b); r.MForm(a, a); r.MulCoeffsMontgomery(a, b, c); r.INTT(c, c);
     EXPECT(c.Get() == c2.Get());
+    // wire format (ring/poly.go:97-160): rows | (len | words)*, little-endian; round trip through a second poly
+    {
+        const std::vector<unsigned char> w = c.MarshalBinary(0, 1);
+        EXPECT(w.size() == 8 + 2 * (8 + 16 * 8) && w[0] == 2 && w[8] == 16);
+        uint64_t first = 0;
+        for (int i = 0; i < 8; ++i) first |= (uint64_t)w[16 + i] << (8 * i);
+        EXPECT(first == c.Limb(0, 0, 16)[0]);
+        ring::Poly c3 = r.NewPoly();
+        size_t used = 0;
+        EXPECT(c3.UnmarshalBinary(0, w, &used) == 1 && used == w.size() && c3.Get() == c.Get());
+        bool bad = false;
+        try { c3.UnmarshalBinary(0, std::vector<unsigned char>(w.begin(), w.end() - 1)); } catch (const ring::Panic &) { bad = true; }
+        EXPECT(bad);
+    }
     bool panicked = false;
     try { r.AtLevel(5); } catch (const ring::Panic &) { panicked = true; }
     EXPECT(panicked);

@@ -35,6 +35,20 @@ __global__ void __launch_bounds__(256) k(u32 *out, u32 seed, long long *clk) {
             if (MODE == 8) { asm volatile("add.u32 %0, %0, %1;" : "+r"(a[c]) : "r"(b[c]));                    // 2:1 IMAD : IADD3
                              asm volatile("mad.lo.u32 %0, %0, %1, %1;" : "+r"(b[c]) : "r"(a[c]));
                              asm volatile("mad.lo.u32 %0, %0, %1, %1;" : "+r"(b[c]) : "r"(a[c])); }
+            if (MODE == 9) asm volatile("mad.hi.u32 %0, %0, %1, %1;" : "+r"(a[c]) : "r"(b[c]));               // IMAD.HI
+            if (MODE == 10) asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(w[c]) : "r"(a[c]), "r"(b[c]));     // IMAD.WIDE, no accumulate
+            if (MODE == 11) { asm volatile("add.u32 %0, %0, %1;" : "+r"(a[c]) : "r"(b[c]));                   // 2:1 IADD3 : IMAD.WIDE
+                              asm volatile("add.u32 %0, %0, %1;" : "+r"(b[c]) : "r"(a[c]));
+                              asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[c]) : "r"(a[c]), "r"(b[c])); }
+            if (MODE == 12) { asm volatile("add.u32 %0, %0, %1;" : "+r"(a[c]) : "r"(b[c]));                   // 2:1 IADD3 : IMAD
+                              asm volatile("add.u32 %0, %0, %1;" : "+r"(b[c]) : "r"(a[c]));
+                              asm volatile("mad.lo.u32 %0, %0, %1, %1;" : "+r"(b[c]) : "r"(a[c])); }
+            if (MODE == 13) { asm volatile("add.u32 %0, %0, %1;" : "+r"(a[c]) : "r"(b[c]));                   // 1:1 IADD3 : IMAD.HI
+                              asm volatile("mad.hi.u32 %0, %0, %1, %1;" : "+r"(b[c]) : "r"(a[c])); }
+            if (MODE == 14) { asm volatile("add.u32 %0, %0, %1;" : "+r"(a[c]) : "r"(b[c]));                   // 3:1 IADD3 : IMAD.WIDE
+                              asm volatile("add.u32 %0, %0, %1;" : "+r"(b[c]) : "r"(a[c]));
+                              asm volatile("add.u32 %0, %0, %1;" : "+r"(a[c]) : "r"(b[c]));
+                              asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[c]) : "r"(a[c]), "r"(b[c])); }
         }
     }
     long long t1 = clock64();
@@ -82,5 +96,11 @@ int main() {
     run<3>("IADD3 : IMAD  1:1", sms, 2);
     run<8>("IADD3 : IMAD  1:2", sms, 3);
     run<4>("IADD3 : IMAD.WIDE 1:1", sms, 2);
+    run<9>("IMAD.HI.U32", sms, 1);
+    run<10>("IMAD.WIDE.U32 (mul)", sms, 1);
+    run<12>("IADD3 : IMAD  2:1", sms, 3);
+    run<11>("IADD3 : IMAD.WIDE 2:1", sms, 3);
+    run<14>("IADD3 : IMAD.WIDE 3:1", sms, 4);
+    run<13>("IADD3 : IMAD.HI 1:1", sms, 2);
     return 0;
 }
