@@ -282,11 +282,13 @@ extern "C" void b200_ctx_destroy(b200_ctx *ctx) {
     delete ctx;
 }
 extern "C" int b200_ctx_set_stream(b200_ctx *ctx, void *s) {
+    CtxLock lk(ctx);
     if (!ctx) return fail(B200_EINVAL, "ctx is NULL");
     ctx->stream = (cudaStream_t)s;
     return 0;
 }
 extern "C" int b200_sync(b200_ctx *ctx) {
+    CtxLock lk(ctx);
     if (!ctx) return fail(B200_EINVAL, "ctx is NULL");
     CUDA_TRY(cudaSetDevice(ctx->device));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -299,6 +301,7 @@ extern "C" uint64_t b200_ctx_launch_count(const b200_ctx *ctx) { return ctx ? ct
 
 // ---- per-kernel device timing ------------------------------------------------------------------------
 extern "C" int b200_profile_begin(b200_ctx *ctx) {
+    CtxLock lk(ctx);
     if (!ctx) return fail(B200_EINVAL, "ctx is NULL");
     CUDA_TRY(cudaSetDevice(ctx->device));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -308,6 +311,7 @@ extern "C" int b200_profile_begin(b200_ctx *ctx) {
     return 0;
 }
 extern "C" int b200_profile_end(b200_ctx *ctx, char *out, size_t cap) {
+    CtxLock lk(ctx);
     if (!ctx || !out || cap == 0) return fail(B200_EINVAL, "b200_profile_end: bad argument");
     CUDA_TRY(cudaSetDevice(ctx->device));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -389,6 +393,7 @@ static int limb_check(const b200_poly *p, int b, int limb, const void *host, siz
     return 0;
 }
 extern "C" int b200_poly_upload_limb(b200_poly *p, int b, int limb, const uint64_t *host, size_t n) {
+    CtxLock lk(p ? p->ctx : nullptr);
     if (int rc = limb_check(p, b, limb, host, n, "b200_poly_upload_limb")) return rc;
     b200_ctx *c = p->ctx;
     CUDA_TRY(cudaSetDevice(c->device));
@@ -397,6 +402,7 @@ extern "C" int b200_poly_upload_limb(b200_poly *p, int b, int limb, const uint64
     return 0;
 }
 extern "C" int b200_poly_download_limb(b200_poly *p, int b, int limb, uint64_t *host, size_t n) {
+    CtxLock lk(p ? p->ctx : nullptr);
     if (int rc = limb_check(p, b, limb, host, n, "b200_poly_download_limb")) return rc;
     b200_ctx *c = p->ctx;
     CUDA_TRY(cudaSetDevice(c->device));
@@ -405,6 +411,7 @@ extern "C" int b200_poly_download_limb(b200_poly *p, int b, int limb, uint64_t *
     return 0;
 }
 extern "C" int b200_poly_upload(b200_poly *p, const uint64_t *host, size_t n_words) {
+    CtxLock lk(p ? p->ctx : nullptr);
     if (!p || !host) return fail(B200_EINVAL, "b200_poly_upload: NULL argument");
     if (n_words != poly_words(p)) return fail(B200_ESHAPE, "b200_poly_upload: expected batch*L*N words");
     CUDA_TRY(cudaSetDevice(p->ctx->device));
@@ -412,6 +419,7 @@ extern "C" int b200_poly_upload(b200_poly *p, const uint64_t *host, size_t n_wor
     return 0;   // asynchronous when `host` is pinned; ordered before later work on the stream
 }
 extern "C" int b200_poly_download(b200_poly *p, uint64_t *host, size_t n_words) {
+    CtxLock lk(p ? p->ctx : nullptr);
     if (!p || !host) return fail(B200_EINVAL, "b200_poly_download: NULL argument");
     if (n_words != poly_words(p)) return fail(B200_ESHAPE, "b200_poly_download: expected batch*L*N words");
     CUDA_TRY(cudaSetDevice(p->ctx->device));
@@ -435,6 +443,7 @@ extern "C" int b200_poly_binary_size(const b200_ctx *ctx, int level, size_t *out
     return 0;
 }
 extern "C" int b200_poly_marshal(const b200_poly *p, int b, int level, void *buf, size_t cap, size_t *written) {
+    CtxLock lk(p ? p->ctx : nullptr);
     if (!p || !buf) return fail(B200_EINVAL, "b200_poly_marshal: NULL argument");
     const b200_ctx *ctx = p->ctx;
     if (b < 0 || b >= p->batch) return fail(B200_ESHAPE, "b200_poly_marshal: polynomial index out of range");
@@ -454,6 +463,7 @@ extern "C" int b200_poly_marshal(const b200_poly *p, int b, int level, void *buf
     return 0;
 }
 extern "C" int b200_poly_unmarshal(b200_poly *p, int b, const void *buf, size_t len, int *level_out, size_t *consumed) {
+    CtxLock lk(p ? p->ctx : nullptr);
     if (!p || !buf) return fail(B200_EINVAL, "b200_poly_unmarshal: NULL argument");
     const b200_ctx *ctx = p->ctx;
     if (b < 0 || b >= p->batch) return fail(B200_ESHAPE, "b200_poly_unmarshal: polynomial index out of range");
@@ -517,6 +527,7 @@ static int transform(b200_ctx *ctx, const b200_poly *in, b200_poly *out, int lev
 }
 // Ring.NTT / INTT restricted to limbs [limb0, limb0+nl): what a rank of a limb-sharded ring runs on its share
 extern "C" int b200_ntt_limbs(b200_ctx *ctx, const b200_poly *in, b200_poly *out, int limb0, int nl, int inverse, int flags) {
+    CtxLock lk(ctx);
     int batch;
     if (int rc = check_polys(ctx, 0, "b200_ntt_limbs", {in, out}, &batch)) return rc;
     if (limb0 < 0 || nl < 0 || limb0 + nl > ctx->L) return fail(B200_ESHAPE, "b200_ntt_limbs: limb range out of bounds");
@@ -530,14 +541,17 @@ extern "C" int b200_ntt_limbs(b200_ctx *ctx, const b200_poly *in, b200_poly *out
 }
 
 extern "C" int b200_ntt(b200_ctx *ctx, const b200_poly *in, b200_poly *out, int level, int flags) {
+    CtxLock lk(ctx);
     return transform(ctx, in, out, level, flags, false, "b200_ntt");
 }
 extern "C" int b200_intt(b200_ctx *ctx, const b200_poly *in, b200_poly *out, int level, int flags) {
+    CtxLock lk(ctx);
     return transform(ctx, in, out, level, flags, true, "b200_intt");
 }
 
 extern "C" int b200_vec_op(b200_ctx *ctx, int op, const b200_poly *p1, const b200_poly *p2, b200_poly *p3, int level,
                            const uint64_t *scalars) {
+    CtxLock lk(ctx);
     int batch;
     const bool unary = (op >= B200_OP_NEG && op <= B200_OP_IMFORM) || (op >= B200_OP_MULSCALAR_MONT && op <= B200_OP_SUB_SCALAR);
     if (unary) {
@@ -564,6 +578,7 @@ extern "C" int b200_vec_op(b200_ctx *ctx, int op, const b200_poly *p1, const b20
 // Ring.DivRoundByLastModulusNTT / DivFloorByLastModulusNTT (ring/scaling.go:6-19,130-156) for the whole batch:
 // INTT of the last limb -> spread to the lower limbs -> NTT of those -> SubThenMulScalarMontgomeryTwoModulus.
 extern "C" int b200_div_by_last_modulus_ntt(b200_ctx *ctx, const b200_poly *p0, b200_poly *p1, int level, int round) {
+    CtxLock lk(ctx);
     int batch;
     if (int rc = check_polys(ctx, level, "b200_div_by_last_modulus_ntt", {p0, p1}, &batch)) return rc;
     if (level < 1) return fail(B200_ESHAPE, "b200_div_by_last_modulus_ntt: needs level >= 1");
@@ -597,6 +612,7 @@ extern "C" int b200_div_by_last_modulus_ntt(b200_ctx *ctx, const b200_poly *p0, 
 
 extern "C" int b200_tensor(b200_ctx *ctx, const b200_poly *a0, const b200_poly *a1, const b200_poly *b0, const b200_poly *b1,
                            b200_poly *c0, b200_poly *c1, b200_poly *c2, int level, int mform_first) {
+    CtxLock lk(ctx);
     int batch;
     if (int rc = check_polys(ctx, level, "b200_tensor", {a0, a1, b0, b1, c0, c1, c2}, &batch)) return rc;
     if (c0 == c1 || c0 == c2 || c1 == c2 || c0->d == c1->d || c0->d == c2->d || c1->d == c2->d)
@@ -606,6 +622,7 @@ extern "C" int b200_tensor(b200_ctx *ctx, const b200_poly *a0, const b200_poly *
 }
 
 extern "C" int b200_polymul(b200_ctx *ctx, const b200_poly *a, const b200_poly *b, b200_poly *c, int level) {
+    CtxLock lk(ctx);
     int batch;
     if (int rc = check_polys(ctx, level, "b200_polymul", {a, b, c}, &batch)) return rc;
     CUDA_TRY(cudaSetDevice(ctx->device));
@@ -634,6 +651,7 @@ extern "C" int b200_polymul(b200_ctx *ctx, const b200_poly *a, const b200_poly *
 // H2D copy -> transforms -> D2H copy on three streams so that both PCIe directions and the SMs overlap.
 extern "C" int b200_transform_host(b200_ctx *ctx, const uint64_t *host_in, uint64_t *host_out, int batch, int level,
                                    const int *ops, int n_ops, int flags) {
+    CtxLock lk(ctx);
     if (!ctx || !host_in || !host_out || !ops) return fail(B200_EINVAL, "b200_transform_host: NULL argument");
     if (batch <= 0 || n_ops <= 0) return fail(B200_EINVAL, "b200_transform_host: empty batch or op list");
     if (level < 0 || level >= ctx->L) return fail(B200_ESHAPE, "b200_transform_host: level out of range");
@@ -701,6 +719,7 @@ extern "C" int b200_transform_host(b200_ctx *ctx, const uint64_t *host_in, uint6
 }
 
 extern "C" int b200_subring_ntt_host(b200_ctx *ctx, int limb, const uint64_t *p1, uint64_t *p2, size_t n, int inverse, int flags) {
+    CtxLock lk(ctx);
     if (!ctx || !p1 || !p2) return fail(B200_EINVAL, "b200_subring_ntt_host: NULL argument");
     if (limb < 0 || limb >= ctx->L) return fail(B200_ESHAPE, "b200_subring_ntt_host: limb out of range");
     if (n < (size_t)ctx->N)   // ring/ntt.go:211-214, ntt_3n.go:85-87

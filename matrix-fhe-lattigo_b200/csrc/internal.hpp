@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <mutex>
 #include <cstdint>
 #include <string>
 #include <vector>
@@ -43,6 +44,10 @@ struct b200_ctx {
     size_t ws_words = 0;
     std::vector<u64> rescale;        // RescaleConstants[level-1][i] (ring.go:361-379), row-major [L-1][L], Montgomery form
     std::atomic<uint64_t> launches{0};
+    // Ring/SubRing are "thread safe" in the reference (ring/ring.go:192-194): goroutines may call the same ring
+    // concurrently.  Every compute entry point holds this lock while it enqueues, so the launches of one call
+    // (which share the scratch buffers) are never interleaved with another call's on the context's stream.
+    std::recursive_mutex mu;
     // optional per-kernel device timing (b200_profile_begin/end): CUDA events around each launch
     bool profiling = false;
     struct ProfRec { const char *name; cudaEvent_t e0, e1; long long units; };
@@ -65,6 +70,14 @@ struct b200_poly {
     u64 *d = nullptr;
     int batch = 0;
     bool owned = false;
+};
+
+struct CtxLock {
+    std::recursive_mutex *m;
+    explicit CtxLock(const b200_ctx *c) : m(c ? &const_cast<b200_ctx *>(c)->mu : nullptr) { if (m) m->lock(); }
+    ~CtxLock() { if (m) m->unlock(); }
+    CtxLock(const CtxLock &) = delete;
+    CtxLock &operator=(const CtxLock &) = delete;
 };
 
 void b200_set_error(const std::string &msg);

@@ -335,6 +335,7 @@ int check_own(const b200_keyswitch *ks, int levelQ, int levelP, Own o, const cha
 }  // namespace
 
 extern "C" int b200_keyswitch_create(b200_ctx *ctx, int LQ, b200_keyswitch **out) {
+    CtxLock lk(ctx);
     if (!ctx || !out) { b200_set_error("b200_keyswitch_create: NULL argument"); return B200_EINVAL; }
     if (LQ < 1 || LQ >= ctx->L) { b200_set_error("b200_keyswitch_create: the ring must hold LQ >= 1 ciphertext primes followed by >= 1 special primes"); return B200_EINVAL; }
     b200_keyswitch *ks = new b200_keyswitch();
@@ -368,6 +369,7 @@ extern "C" void b200_keyswitch_destroy(b200_keyswitch *ks) {
 
 // BasisExtender.ModUpQtoP (:184-198, direction 0) / ModUpPtoQ (:203-217, direction 1): lazy words exactly as Go leaves them
 extern "C" int b200_mod_up(b200_keyswitch *ks, int direction, int levelQ, int levelP, const b200_poly *in, b200_poly *out) {
+    CtxLock lk(ks ? ks->ctx : nullptr);
     if (int rc = check_levels(ks, levelQ, levelP, "b200_mod_up")) return rc;
     if (int rc = check_poly(ks, in, "b200_mod_up")) return rc;
     if (int rc = check_poly(ks, out, "b200_mod_up")) return rc;
@@ -380,6 +382,7 @@ extern "C" int b200_mod_up(b200_keyswitch *ks, int direction, int levelQ, int le
 }
 
 extern "C" int b200_mod_down_ntt(b200_keyswitch *ks, int levelQ, int levelP, const b200_poly *p1, b200_poly *p2) {
+    CtxLock lk(ks ? ks->ctx : nullptr);
     if (int rc = check_levels(ks, levelQ, levelP, "b200_mod_down_ntt")) return rc;
     if (int rc = check_poly(ks, p1, "b200_mod_down_ntt")) return rc;
     if (int rc = check_poly(ks, p2, "b200_mod_down_ntt")) return rc;
@@ -393,6 +396,7 @@ extern "C" int b200_mod_down_ntt(b200_keyswitch *ks, int levelQ, int levelP, con
 // rlwe.Evaluator.GadgetProduct (NTT-domain operands, levelP >= 1): evaluator_gadget_product.go:16-30,123-188,455-478
 extern "C" int b200_gadget_product(b200_keyswitch *ks, int levelQ, int levelP, const b200_poly *cx, const b200_poly *key,
                                    b200_poly *ct0, b200_poly *ct1) {
+    CtxLock lk(ks ? ks->ctx : nullptr);
     if (int rc = check_levels(ks, levelQ, levelP, "b200_gadget_product")) return rc;
     for (const b200_poly *p : {cx, key, (const b200_poly *)ct0, (const b200_poly *)ct1})
         if (int rc = check_poly(ks, p, "b200_gadget_product")) return rc;
@@ -417,6 +421,7 @@ extern "C" int b200_gadget_product(b200_keyswitch *ks, int levelQ, int levelP, c
 // P limbs of the accumulators), which the caller performs with NCCL on the polynomials' device memory.
 extern "C" int b200_ks_decompose_mac(b200_keyswitch *ks, int levelQ, int levelP, const b200_poly *cx, const b200_poly *cxinv,
                                      const b200_poly *key, b200_poly *acc0, b200_poly *acc1, int q0, int q1, int p0, int p1) {
+    CtxLock lk(ks ? ks->ctx : nullptr);
     if (int rc = check_levels(ks, levelQ, levelP, "b200_ks_decompose_mac")) return rc;
     for (const b200_poly *p : {cx, cxinv, key, (const b200_poly *)acc0, (const b200_poly *)acc1})
         if (int rc = check_poly(ks, p, "b200_ks_decompose_mac")) return rc;
@@ -436,6 +441,7 @@ extern "C" int b200_ks_decompose_mac(b200_keyswitch *ks, int levelQ, int levelP,
 }
 
 extern "C" int b200_ks_mod_down_limbs(b200_keyswitch *ks, int levelQ, int levelP, const b200_poly *acc, b200_poly *out, int q0, int q1) {
+    CtxLock lk(ks ? ks->ctx : nullptr);
     if (int rc = check_levels(ks, levelQ, levelP, "b200_ks_mod_down_limbs")) return rc;
     if (int rc = check_poly(ks, acc, "b200_ks_mod_down_limbs")) return rc;
     if (int rc = check_poly(ks, out, "b200_ks_mod_down_limbs")) return rc;
@@ -457,6 +463,7 @@ extern "C" int b200_ks_mod_down_limbs(b200_keyswitch *ks, int levelQ, int levelP
 extern "C" int b200_mul_relin(b200_keyswitch *ks, int levelQ, int levelP, const b200_poly *a0, const b200_poly *a1,
                               const b200_poly *b0, const b200_poly *b1, const b200_poly *rlk, b200_poly *out0, b200_poly *out1,
                               int mform_first) {
+    CtxLock lk(ks ? ks->ctx : nullptr);
     if (int rc = check_levels(ks, levelQ, levelP, "b200_mul_relin")) return rc;
     for (const b200_poly *p : {a0, a1, b0, b1, rlk, (const b200_poly *)out0, (const b200_poly *)out1})
         if (int rc = check_poly(ks, p, "b200_mul_relin")) return rc;

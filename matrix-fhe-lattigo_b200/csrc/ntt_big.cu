@@ -575,7 +575,7 @@ k_cols_inv_m3_15(const u64 *in, u64 *out, BigArgs a) {
 }
 
 // ====================================================================================================
-// generic column pass: any STANDARD ring with 2^12 <= N <= 2^17 and any MATRIX ring N = 3*2^a, 12 <= a <= 15.
+// generic column pass: any STANDARD ring with 2^10 <= N <= 2^17 and any MATRIX ring N = 3*2^a, 10 <= a <= 16.
 // Same structure as the tuned kernels above (8 columns per CTA, register groups of <= 3 layers, shared-memory
 // exchanges), with the group sizes as template parameters.  Row index = hi*2^(b0+S) + k*2^b0 + lo for the
 // group that owns row bits [b0, b0+S); the root node of its sub-transform is (ROOTS << (LOG-b0-S)) + hi.
@@ -622,10 +622,12 @@ __device__ __forceinline__ void col_group(const u64 *gin, size_t ibase, u64 *gou
     }
 }
 
+constexpr int std_col_threads(int L) { if (L >= 6) return GCW << (L - 3); return 64; }
+constexpr int m3_col_threads(int L) { if (L >= 4) return (GCW * 6) << (L - 3); return 64; }
 constexpr int minb_for(int threads, int target) { return target / threads < 1 ? 1 : (target / threads > 16 ? 16 : target / threads); }
 
 template <int LOGR, int S1, int S2, int S3, bool INV>
-__global__ void __launch_bounds__(LOGR >= 6 ? (GCW << (LOGR - 3)) : 64, minb_for(LOGR >= 6 ? (GCW << (LOGR - 3)) : 64, 1024))
+__global__ void __launch_bounds__(std_col_threads(LOGR), minb_for(std_col_threads(LOGR), 1024))
 k_cols_std_g(const u64 *in, u64 *out, BigArgs a) {
     static_assert(S1 + S2 + S3 == LOGR && S1 >= 1 && S2 >= 1, "group sizes");
     extern __shared__ __align__(16) u64 sm[];
@@ -661,7 +663,7 @@ k_cols_std_g(const u64 *in, u64 *out, BigArgs a) {
 
 // MATRIX: first group = cyclotomic + radix-3 + S1 radix-2 layers on 6*2^S1 words; then groups on the u bits.
 template <int LOGU, int S1, int S2, int S3, bool INV>
-__global__ void __launch_bounds__(LOGU >= 4 ? ((GCW * 6) << (LOGU - 3)) : 64, minb_for(LOGU >= 4 ? ((GCW * 6) << (LOGU - 3)) : 64, 768))
+__global__ void __launch_bounds__(m3_col_threads(LOGU), minb_for(m3_col_threads(LOGU), 768))
 k_cols_m3_g(const u64 *in, u64 *out, BigArgs a) {
     static_assert(S1 + S2 + S3 == LOGU && S2 >= 1, "group sizes");
     extern __shared__ __align__(16) u64 sm[];
@@ -779,9 +781,9 @@ struct BigPlan {
 };
 
 #define STD_G(L, A, B, C) case L: plan->cols_fwd = (kern_t)k_cols_std_g<L, A, B, C, false>; plan->cols_inv = (kern_t)k_cols_std_g<L, A, B, C, true>; \
-                                  plan->col_threads = L >= 6 ? (GCW << (L - 3)) : 64; break;
+                                  plan->col_threads = std_col_threads(L); break;
 #define M3_G(L, A, B, C) case L: plan->cols_fwd = (kern_t)k_cols_m3_g<L, A, B, C, false>; plan->cols_inv = (kern_t)k_cols_m3_g<L, A, B, C, true>; \
-                                 plan->col_threads = L >= 4 ? ((GCW * 6) << (L - 3)) : 64; break;
+                                 plan->col_threads = m3_col_threads(L); break;
 // column-pass kernels for a ring shape: the hand-tuned ones for the two headline shapes, the generic family otherwise
 bool pick_col_kernels(BigPlan *plan, bool matrix, int log, bool force_generic) {
     if (!matrix) {
@@ -790,7 +792,7 @@ bool pick_col_kernels(BigPlan *plan, bool matrix, int log, bool force_generic) {
             return true;
         }
         switch (log) {
-            STD_G(4, 2, 2, 0) STD_G(5, 3, 2, 0) STD_G(6, 3, 3, 0) STD_G(7, 3, 2, 2) STD_G(8, 3, 3, 2) STD_G(9, 3, 3, 3)
+            STD_G(2, 1, 1, 0) STD_G(3, 2, 1, 0) STD_G(4, 2, 2, 0) STD_G(5, 3, 2, 0) STD_G(6, 3, 3, 0) STD_G(7, 3, 2, 2) STD_G(8, 3, 3, 2) STD_G(9, 3, 3, 3)
             default: return false;
         }
     } else {
@@ -799,7 +801,7 @@ bool pick_col_kernels(BigPlan *plan, bool matrix, int log, bool force_generic) {
             return true;
         }
         switch (log) {
-            M3_G(3, 0, 3, 0) M3_G(4, 1, 3, 0) M3_G(5, 0, 3, 2) M3_G(6, 1, 3, 2)
+            M3_G(1, 0, 1, 0) M3_G(2, 0, 2, 0) M3_G(3, 0, 3, 0) M3_G(4, 1, 3, 0) M3_G(5, 0, 3, 2) M3_G(6, 1, 3, 2) M3_G(7, 1, 3, 3)
             default: return false;
         }
     }
@@ -827,8 +829,8 @@ int big_tables_create(b200_ctx *ctx) {
     if (env_int("B200_NO_BIG", 0)) return 0;
     const bool matrix = ctx->ring_type == B200_RING_MATRIX;
     const bool generic = env_int("B200_GENERIC_COLS", 0) != 0;
-    if (!matrix) plan->covered = ctx->logN >= 12 && ctx->logN <= 17 && pick_col_kernels(plan, false, ctx->logN - 8, generic);
-    else plan->covered = ctx->b == 1 && ctx->a >= 12 && ctx->a <= 15 && pick_col_kernels(plan, true, ctx->a - 9, generic);
+    if (!matrix) plan->covered = ctx->logN >= 10 && ctx->logN <= 17 && pick_col_kernels(plan, false, ctx->logN - 8, generic);
+    else plan->covered = ctx->b == 1 && ctx->a >= 10 && ctx->a <= 16 && pick_col_kernels(plan, true, ctx->a - 9, generic);
     plan->cw = 8;   // 16-column tiles and 4-v row tiles were measured slower on B200 (fewer resident CTAs)
     plan->vt = 2;
     int l2 = 0;

@@ -61,7 +61,7 @@ def test_standard_tables_bit_identical_to_subring_go():
             assert sr.Mask == (1 << (q - 1).bit_length()) - 1
 
 
-@pytest.mark.parametrize("logN", [3, 4, 7, 10, 12, 13, 14, 15, 16, 17])
+@pytest.mark.parametrize("logN", [3, 4, 7, 9, 10, 11, 12, 13, 14, 15, 16, 17])
 def test_standard_ntt_matches_oracle(logN):
     N = 1 << logN
     moduli = QI60[:3]
@@ -120,6 +120,22 @@ ALL_BINARY = ["Add", "AddLazy", "Sub", "SubLazy", "MulCoeffsBarrett", "MulCoeffs
               "MulCoeffsMontgomeryLazyThenSubLazy", "MulCoeffsMontgomeryLazyThenNeg"]
 ALL_UNARY = ["Neg", "Reduce", "ReduceLazy", "MForm", "MFormLazy", "IMForm"]
 ALL_SCALAR = ["MulScalarMontgomery", "MulScalarMontgomeryLazy", "MulScalarMontgomeryThenAdd", "AddScalar", "SubScalar"]
+
+
+@pytest.mark.parametrize("logN", [8, 10, 11, 13])
+def test_standard_fused_product_equals_operator_sequence(logN):
+    """ring/ring_test.go:106-110 at the sizes where the column-pass kernel family changes shape."""
+    N, moduli = 1 << logN, QI60[:3]
+    r = b200ring.NewRing(N, moduli)
+    ha, hb = rand_poly(51, 2, moduli, N), rand_poly(52, 2, moduli, N)
+    a, b, c = r.NewPoly(2).set(ha), r.NewPoly(2).set(hb), r.NewPoly(2)
+    r.MulPoly(a, b, c)
+    got = c.get()
+    r.NTT(a, a); r.NTT(b, b); r.MForm(a, a); r.MulCoeffsMontgomery(a, b, c); r.INTT(c, c)
+    assert (c.get() == got).all()
+    for l, q in enumerate(moduli[:1]):   # one limb against the negacyclic schoolbook product
+        if N <= 1 << 10:
+            assert (got[0, l] == O.schoolbook_negacyclic(N, q, ha[0, l], hb[0, l])).all()
 
 
 @pytest.mark.parametrize("N", [16, 24, 3 * 2**10])
@@ -183,7 +199,7 @@ def test_3n_prototype_vectors_on_gpu():
         assert [int(t) for t in y.get()[0, 0]] == O.py_3n_ntt(N, v["p"], v["w"], v["coeffs"])
 
 
-@pytest.mark.parametrize("N", [12, 18, 24, 36, 48, 96, 192, 3 * 2**7, 9 * 2**6, 3 * 2**12, 3 * 2**13, 27 * 2**10])
+@pytest.mark.parametrize("N", [12, 18, 24, 36, 48, 96, 192, 3 * 2**7, 9 * 2**6, 3 * 2**10, 3 * 2**11, 3 * 2**12, 3 * 2**13, 27 * 2**10])
 def test_3n_matches_oracle_roundtrip_product(N):
     moduli = O.find_3n_rns_primes(N, 60, 2)
     batch = 2
@@ -211,16 +227,16 @@ def test_3n_matches_oracle_roundtrip_product(N):
     r.NTT(z.set(zero), z); assert (z.get() == 0).all()
     r.NTT(z.set(one), z); assert (z.get() == 1).all()
     # product == schoolbook mod X^N - X^(N/2) + 1 (ntt_3n_test.go:455-554)
+    ha, hb = rand_poly(41, batch, moduli, N), rand_poly(42, batch, moduli, N)
+    a, b, c = r.NewPoly(batch).set(ha), r.NewPoly(batch).set(hb), r.NewPoly(batch)
+    r.MulPoly(a, b, c)
+    got = c.get()
     if N <= 3 * 2**7:
-        ha, hb = rand_poly(41, batch, moduli, N), rand_poly(42, batch, moduli, N)
-        a, b, c = r.NewPoly(batch).set(ha), r.NewPoly(batch).set(hb), r.NewPoly(batch)
-        r.MulPoly(a, b, c)
-        got = c.get()
         for bi in range(batch):
             for l, q in enumerate(moduli):
                 assert (got[bi, l] == O.schoolbook_3n(N, q, ha[bi, l], hb[bi, l])).all()
-        r.NTT(a, a); r.NTT(b, b); r.MForm(a, a); r.MulCoeffsMontgomery(a, b, c); r.INTT(c, c)
-        assert (c.get() == got).all()
+    r.NTT(a, a); r.NTT(b, b); r.MForm(a, a); r.MulCoeffsMontgomery(a, b, c); r.INTT(c, c)
+    assert (c.get() == got).all()                                        # fused product == operator sequence
 
 
 def test_3n_random_omega_from_go_side():
@@ -373,7 +389,8 @@ def test_transform_host_pipelined_chunks():
 
 
 @pytest.mark.parametrize("env", [{"B200_GENERIC_COLS": "1"}, {"B200_NO_BIG": "1"}])
-@pytest.mark.parametrize("shape", [("std", 1 << 16), ("std", 1 << 15), ("m3", 3 * 2**15), ("m3", 3 * 2**14)])
+@pytest.mark.parametrize("shape", [("std", 1 << 16), ("std", 1 << 15), ("m3", 3 * 2**15), ("m3", 3 * 2**14),
+                                   ("std", 1 << 10), ("std", 1 << 11), ("m3", 3 * 2**10), ("m3", 3 * 2**11), ("m3", 3 * 2**16)])
 def test_alternative_kernel_paths_agree(env, shape, monkeypatch):
     """The generic column-pass family and the shape-agnostic fallback (resident / layered kernels) must give the
     same words as the default path: the knobs are read at ring construction."""
