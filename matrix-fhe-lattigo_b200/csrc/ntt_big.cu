@@ -163,6 +163,12 @@ __device__ __forceinline__ unsigned rev_bits(unsigned x, int bits) { return bits
 constexpr int WROW = 272;   // 256 words + 16 padding
 __device__ __forceinline__ int pad16(int c) { return c + (c >> 4); }
 
+// Staging index of the MATRIX slot permutation: row cr = rev8(c) of the [256][RUN] tile.  A half-warp writes the
+// 16 rows cr = 2j (+1) of one column; with the odd pitch RUN+1 alone those fall on 8 bank pairs (2-way conflict),
+// the extra word every other 16 rows spreads them over all 16 while row-sequential reads stay conflict-free.
+template <int RUN>
+__device__ __forceinline__ int stage_row(int cr) { return cr * (RUN + 1) + ((cr >> 4) & 1); }
+
 // MATRIX: a CTA owns the 6 blocks (hd) x VT consecutive v = bitrev(u); rows are ordered hd*VT + vi
 template <bool MATRIX, int VT>
 __device__ __forceinline__ int row_of(const BigArgs &a, int tile, int w, int &rowcode) {
@@ -250,14 +256,14 @@ k_rows_fwd(const u64 *in, u64 *out, BigArgs a) {
         __syncthreads();
         const int rl = (int)rev_bits((unsigned)lane, 5);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) sm[((int)rev_bits((unsigned)k, 3) * 32 + rl) * (RUN + 1) + rowcode] = x[k];
+        for (int k = 0; k < 8; ++k) sm[stage_row<RUN>((int)rev_bits((unsigned)k, 3) * 32 + rl) + rowcode] = x[k];
         __syncthreads();
         const size_t run = (size_t)6 << a.logU;                       // 6U words between consecutive rev8(c)
         u64 *dst = out + ur.out + (size_t)blockIdx.y * RUN;
         {   // WARPS*32 = 32*RUN threads: thread -> (cr0, rem) once, then cr advances by 32 per step
             const int cr0 = threadIdx.x / RUN, rem = threadIdx.x - cr0 * RUN;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) dst[(size_t)(cr0 + 32 * i) * run + rem] = sm[(cr0 + 32 * i) * (RUN + 1) + rem];
+            for (int i = 0; i < 8; ++i) dst[(size_t)(cr0 + 32 * i) * run + rem] = sm[stage_row<RUN>(cr0 + 32 * i) + rem];
         }
     }
 }
@@ -289,12 +295,12 @@ k_rows_inv(const u64 *in, u64 *out, BigArgs a) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = src[(size_t)(cr0 + 32 * i) * run + rem];     // all 8 loads in flight
 #pragma unroll
-            for (int i = 0; i < 8; ++i) sm[(cr0 + 32 * i) * (RUN + 1) + rem] = v[i];
+            for (int i = 0; i < 8; ++i) sm[stage_row<RUN>(cr0 + 32 * i) + rem] = v[i];
         }
         __syncthreads();
         const int rl = (int)rev_bits((unsigned)lane, 5);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) x[k] = sm[((int)rev_bits((unsigned)k, 3) * 32 + rl) * (RUN + 1) + rowcode];
+        for (int k = 0; k < 8; ++k) x[k] = sm[stage_row<RUN>((int)rev_bits((unsigned)k, 3) * 32 + rl) + rowcode];
         __syncthreads();
     }
     const unsigned P1 = (unsigned)(a.R + r);
@@ -866,7 +872,7 @@ int launch_ntt_big(b200_ctx *ctx, const u64 *in, u64 *out, Span sp, bool inverse
     const int rows_total = R * cw;
     const size_t col_smem = (size_t)(rows_total + ((rows_total >> 6) << 3) + 8) * sizeof(u64);
     size_t row_smem = (size_t)row_warps * WROW * sizeof(u64);
-    if (matrix) row_smem = std::max(row_smem, (size_t)256 * (6 * vt + 1) * sizeof(u64));
+    if (matrix) row_smem = std::max(row_smem, (size_t)(256 * (6 * vt + 1) + 1) * sizeof(u64));
     if (int rc = set_smem(ck, col_smem)) return rc;
     if (int rc = set_smem(rk, row_smem)) return rc;
     const int units = sp.batch * sp.nl;
