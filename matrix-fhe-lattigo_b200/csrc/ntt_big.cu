@@ -154,11 +154,36 @@ __device__ __forceinline__ void inv_regs(u64 (&x)[1 << LOGM], unsigned P, const 
     }
 }
 
+#ifndef B200_STREAM_DATA
+#define B200_STREAM_DATA 0   // 1: polynomial words bypass L1 allocation (ld/st.global.cs) so that L1 keeps the twiddles
+#endif
+__device__ __forceinline__ u64 ldd(const u64 *p) {
+#if B200_STREAM_DATA
+    return __ldcs(p);
+#else
+    return *p;
+#endif
+}
+__device__ __forceinline__ void std_(u64 *p, u64 v) {
+#if B200_STREAM_DATA
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
 __device__ __forceinline__ void ldg256(const u64 *p, u64 &a, u64 &b, u64 &c, u64 &d) {
+#if B200_STREAM_DATA
+    asm volatile("ld.global.cs.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p) : "memory");
+#else
     asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p) : "memory");
+#endif
 }
 __device__ __forceinline__ void stg256(u64 *p, u64 a, u64 b, u64 c, u64 d) {
+#if B200_STREAM_DATA
+    asm volatile("st.global.cs.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+#else
     asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+#endif
 }
 
 __device__ __forceinline__ unsigned rev_bits(unsigned x, int bits) { return bits ? (__brev(x) >> (32 - bits)) : 0u; }
@@ -188,6 +213,24 @@ __device__ __forceinline__ int row_of(const BigArgs &a, int tile, int w, int &ro
     const int u = (int)rev_bits((unsigned)(tile * VT + vi), a.logU);
     rowcode = vi * 6 + 2 * (hd % 3) + hd / 3;          // position inside a 6*VT run of the reference order
     return (hd << a.logU) + u;
+}
+
+#ifndef B200_TW_PREFETCH
+#define B200_TW_PREFETCH 0
+#endif
+// Warm L1 with the twiddles of groups 2 and 3 of row node P1 (heap order: level k of the row's subtree is the
+// contiguous run tw[P1*2^k, (P1+1)*2^k)): 31 lines of 128 B, one per lane, requested while the row's data loads are
+// still in flight so that the later, dependent twiddle loads hit L1 instead of waiting on L2.
+__device__ __forceinline__ void prefetch_row_twiddles(const tw_t *__restrict__ tw, unsigned P1, int lane) {
+#if B200_TW_PREFETCH
+    // lines (8 entries of 16 B each): level 3: 1, level 4: 2, level 5: 4, level 6: 8, level 7: 16
+    const int lvl = lane < 1 ? 3 : lane < 3 ? 4 : lane < 7 ? 5 : lane < 15 ? 6 : 7;
+    const int line = lane - ((1 << (lvl - 3)) - 1);
+    if (lane < 31) {
+        const tw_t *p = tw + ((size_t)P1 << lvl) + (size_t)line * 8;
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+    }
+#endif
 }
 
 // The 8 layers of one 256-word row held by one warp (x[k]: 8 words per lane, buf: the warp's exchange buffer).
@@ -251,10 +294,11 @@ k_rows_fwd(const u64 *in, u64 *out, BigArgs a) {
     const int r = row_of<MATRIX, VT>(a, blockIdx.y, w, rowcode);
     u64 *buf = sm + w * WROW;
     const u64 *src = in + ur.in + (size_t)r * 256;
+    const unsigned P1 = (unsigned)(a.R + r);
+    prefetch_row_twiddles(tw, P1, lane);
     u64 x[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) x[k] = src[k * 32 + lane];
-    const unsigned P1 = (unsigned)(a.R + r);
+    for (int k = 0; k < 8; ++k) x[k] = ldd(src + k * 32 + lane);
     row_fwd_core(x, buf, lane, P1, tw, qc);
 #pragma unroll
     for (int k = 0; k < 8; ++k) x[k] = (a.flags & B200_LAZY) ? csub(x[k], qc.fourq) : canon8(x[k], qc);   // lazy: [0,4q) <= 6q-2
@@ -274,7 +318,7 @@ k_rows_fwd(const u64 *in, u64 *out, BigArgs a) {
         {   // WARPS*32 = 32*RUN threads: thread -> (cr0, rem) once, then cr advances by 32 per step
             const int cr0 = threadIdx.x / RUN, rem = threadIdx.x - cr0 * RUN;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) dst[(size_t)(cr0 + 32 * i) * run + rem] = sm[stage_row<RUN>(cr0 + 32 * i) + rem];
+            for (int i = 0; i < 8; ++i) std_(dst + (size_t)(cr0 + 32 * i) * run + rem, sm[stage_row<RUN>(cr0 + 32 * i) + rem]);
         }
     }
 }
@@ -292,6 +336,8 @@ k_rows_inv(const u64 *in, u64 *out, BigArgs a) {
     int rowcode;
     const int r = row_of<MATRIX, VT>(a, blockIdx.y, w, rowcode);
     u64 *buf = sm + w * WROW;
+    const unsigned P1 = (unsigned)(a.R + r);
+    prefetch_row_twiddles(tw, P1, lane);
     u64 x[8];
     if (!MATRIX || (a.flags & B200_TREE_ORDER)) {
         const u64 *src = in + ur.in + (size_t)r * 256 + lane * 8;
@@ -304,7 +350,7 @@ k_rows_inv(const u64 *in, u64 *out, BigArgs a) {
             const int cr0 = threadIdx.x / RUN, rem = threadIdx.x - cr0 * RUN;
             u64 v[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = src[(size_t)(cr0 + 32 * i) * run + rem];     // all 8 loads in flight
+            for (int i = 0; i < 8; ++i) v[i] = ldd(src + (size_t)(cr0 + 32 * i) * run + rem);     // all 8 loads in flight
 #pragma unroll
             for (int i = 0; i < 8; ++i) sm[stage_row<RUN>(cr0 + 32 * i) + rem] = v[i];
         }
@@ -314,11 +360,10 @@ k_rows_inv(const u64 *in, u64 *out, BigArgs a) {
         for (int k = 0; k < 8; ++k) x[k] = sm[stage_row<RUN>((int)rev_bits((unsigned)k, 3) * 32 + rl) + rowcode];
         __syncthreads();
     }
-    const unsigned P1 = (unsigned)(a.R + r);
     row_inv_core(x, buf, lane, P1, tw, qc);
     u64 *dst = out + ur.out + (size_t)r * 256;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) dst[k * 32 + lane] = x[k];
+    for (int k = 0; k < 8; ++k) std_(dst + k * 32 + lane, x[k]);
 }
 
 // Fused row stage of the ring product (BASELINE config 4): for one row of a^ = cols_fwd(a) and b^ = cols_fwd(b)
@@ -374,7 +419,7 @@ k_cols_fwd_std16(const u64 *in, u64 *out, BigArgs a) {
     const int t = threadIdx.x, c = t % CW, g = t / CW;   // g in [0,32)
     u64 x[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) x[k] = in[ibase + (size_t)(k * 32 + g) * 256 + c];      // rows k*32 + g
+    for (int k = 0; k < 8; ++k) x[k] = ldd(in + ibase + (size_t)(k * 32 + g) * 256 + c);      // rows k*32 + g
     fwd_regs<3>(x, 1u, tw, qc);
 #pragma unroll
     for (int k = 0; k < 8; ++k) sm[pc((k * 32 + g) * CW + c)] = x[k];
@@ -396,7 +441,7 @@ k_cols_fwd_std16(const u64 *in, u64 *out, BigArgs a) {
         fwd_regs<2>(hi, 64u + g * 2 + 1, tw, qc);
     }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) out[obase + (size_t)(g * 8 + k) * 256 + c] = x[k];
+    for (int k = 0; k < 8; ++k) std_(out + obase + (size_t)(g * 8 + k) * 256 + c, x[k]);
 }
 
 template <int CW>
@@ -414,7 +459,7 @@ k_cols_inv_std16(const u64 *in, u64 *out, BigArgs a) {
     const int t = threadIdx.x, c = t % CW, g = t / CW;
     u64 x[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) x[k] = in[ibase + (size_t)(g * 8 + k) * 256 + c];
+    for (int k = 0; k < 8; ++k) x[k] = ldd(in + ibase + (size_t)(g * 8 + k) * 256 + c);
     {
         u64 (&lo)[4] = *reinterpret_cast<u64 (*)[4]>(&x[0]);
         u64 (&hi)[4] = *reinterpret_cast<u64 (*)[4]>(&x[4]);
@@ -444,7 +489,7 @@ k_cols_inv_std16(const u64 *in, u64 *out, BigArgs a) {
         x[o] = X; x[o + 4] = Y;
     }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) out[obase + (size_t)(k * 32 + g) * 256 + c] = x[k];
+    for (int k = 0; k < 8; ++k) std_(out + obase + (size_t)(k * 32 + g) * 256 + c, x[k]);
 }
 
 // MATRIX, a = 15 (N = 3*2^15): rows (hd, u), hd in [0,6) = 3h + d, u in [0,64).
@@ -468,7 +513,7 @@ k_cols_fwd_m3_15(const u64 *in, u64 *out, BigArgs a) {
 #pragma unroll
         for (int hd = 0; hd < 6; ++hd)
 #pragma unroll
-            for (int b = 0; b < 2; ++b) x[hd][b] = in[ibase + (size_t)(hd * 64 + b * 32 + g) * 256 + c];
+            for (int b = 0; b < 2; ++b) x[hd][b] = ldd(in + ibase + (size_t)(hd * 64 + b * 32 + g) * 256 + c);
         const tw_t zeta = tw[1];
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
@@ -518,7 +563,7 @@ k_cols_fwd_m3_15(const u64 *in, u64 *out, BigArgs a) {
         fwd_regs<2>(lo, 96u + g * 2, tw, qc);
         fwd_regs<2>(hi, 96u + g * 2 + 1, tw, qc);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) out[obase + (size_t)(g * 8 + k) * 256 + c] = x[k];
+        for (int k = 0; k < 8; ++k) std_(out + obase + (size_t)(g * 8 + k) * 256 + c, x[k]);
     }
 }
 
@@ -538,7 +583,7 @@ k_cols_inv_m3_15(const u64 *in, u64 *out, BigArgs a) {
     {
         u64 x[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) x[k] = in[ibase + (size_t)(g * 8 + k) * 256 + c];
+        for (int k = 0; k < 8; ++k) x[k] = ldd(in + ibase + (size_t)(g * 8 + k) * 256 + c);
         u64 (&lo)[4] = *reinterpret_cast<u64 (*)[4]>(&x[0]);
         u64 (&hi)[4] = *reinterpret_cast<u64 (*)[4]>(&x[4]);
         inv_regs<2>(lo, 96u + g * 2, tw, qc);
@@ -587,7 +632,7 @@ k_cols_inv_m3_15(const u64 *in, u64 *out, BigArgs a) {
 #pragma unroll
         for (int hd = 0; hd < 6; ++hd)
 #pragma unroll
-            for (int b = 0; b < 2; ++b) out[obase + (size_t)(hd * 64 + b * 32 + g) * 256 + c] = x[hd][b];
+            for (int b = 0; b < 2; ++b) std_(out + obase + (size_t)(hd * 64 + b * 32 + g) * 256 + c, x[hd][b]);
     }
 }
 
@@ -612,7 +657,7 @@ __device__ __forceinline__ void col_group(const u64 *gin, size_t ibase, u64 *gou
 #pragma unroll
         for (int k = 0; k < M; ++k) {
             const int row = row0 + (k << b0);
-            x[k] = FROM_G ? gin[ibase + (size_t)row * 256 + c] : sm[pc(row * GCW + c)];
+            x[k] = FROM_G ? ldd(gin + ibase + (size_t)row * 256 + c) : sm[pc(row * GCW + c)];
         }
         const unsigned P = (unsigned)((ROOTS << (LOG - b0 - S)) + hi);
         if (!INV) {
@@ -633,7 +678,7 @@ __device__ __forceinline__ void col_group(const u64 *gin, size_t ibase, u64 *gou
 #pragma unroll
         for (int k = 0; k < M; ++k) {
             const int row = row0 + (k << b0);
-            if (TO_G) gout[obase + (size_t)row * 256 + c] = x[k];
+            if (TO_G) std_(gout + obase + (size_t)row * 256 + c, x[k]);
             else sm[pc(row * GCW + c)] = x[k];
         }
     }
@@ -701,7 +746,7 @@ k_cols_m3_g(const u64 *in, u64 *out, BigArgs a) {
 #pragma unroll
             for (int hd = 0; hd < 6; ++hd)
 #pragma unroll
-                for (int k = 0; k < MA; ++k) x[hd][k] = in[ibase + (size_t)(hd * U + k * ULO + ulo) * 256 + c];
+                for (int k = 0; k < MA; ++k) x[hd][k] = ldd(in + ibase + (size_t)(hd * U + k * ULO + ulo) * 256 + c);
             const tw_t zeta = tw[1];
 #pragma unroll
             for (int k = 0; k < MA; ++k) {
@@ -781,7 +826,7 @@ k_cols_m3_g(const u64 *in, u64 *out, BigArgs a) {
 #pragma unroll
             for (int hd = 0; hd < 6; ++hd)
 #pragma unroll
-                for (int k = 0; k < MA; ++k) out[obase + (size_t)(hd * U + k * ULO + ulo) * 256 + c] = x[hd][k];
+                for (int k = 0; k < MA; ++k) std_(out + obase + (size_t)(hd * U + k * ULO + ulo) * 256 + c, x[hd][k]);
         }
     }
 }
