@@ -153,7 +153,7 @@ def run_reference(args):
             "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -300,13 +300,32 @@ def run_gpu(args):
                            "parallelism": "limb-sharded x%d, no collective" % world},
                 "roofline": roofline, "path_roofline": path, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
                 "clocks": clocks, "verified_against_oracle": verified}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         torch.distributed.destroy_process_group()
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Libraries (NCCL prints its version banner on stdout at communicator creation) must not add lines to the ONE
+    JSON line of the contract: route fd 1 to stderr for the run and keep the real stdout for emit()."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=int(os.environ.get("WORLD_SIZE", 1)))
     ap.add_argument("--steps", type=int, default=20)
