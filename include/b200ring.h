@@ -162,6 +162,19 @@ B200_API int b200_poly_unmarshal(b200_poly *p, int b, const void *buf, size_t le
  * (out may be NULL to query it) or a negative error. */
 B200_API int b200_ctx_factors(const b200_ctx *ctx, int limb, uint64_t *out, int cap);
 
+/* ---- fused all-gather over NVLink peer memory (one process per GPU) ------------------------------
+ * The key switch is the one step of the path with a real exchange (ring/basis_extension.go:381-502 needs every limb
+ * of a digit per coefficient).  b200_poly_ipc_export gives a 64-byte CUDA IPC handle of a polynomial allocated by
+ * b200_poly_alloc; a peer process maps it with b200_peer_open (and unmaps with b200_peer_close).
+ * b200_intt_limbs_gather = Ring.INTT on limbs [limb0, limb0+nl) of `in` into `out` and into the same limbs of the
+ * npeers (<= 7) mapped polynomials, the stores to the peers issued by the transform's last kernel.  The caller
+ * orders the peers' reads after it (any cross-GPU barrier on the stream, e.g. a one-word all-reduce). */
+B200_API int b200_poly_ipc_export(const b200_poly *p, unsigned char handle[64]);
+B200_API int b200_peer_open(b200_ctx *ctx, const unsigned char handle[64], void **device_ptr);
+B200_API int b200_peer_close(b200_ctx *ctx, void *device_ptr);
+B200_API int b200_intt_limbs_gather(b200_ctx *ctx, const b200_poly *in, b200_poly *out, int limb0, int nl, int flags,
+                           int npeers, void *const *peer_polys);
+
 /* ---- element-wise family: p3 = op(p1, p2 [, p3]) (ring/operations.go, ring/vec_ops.go) -------
  * p2 may be NULL for unary ops.  For *_SCALAR / MULSCALAR ops `scalars` holds one word per limb
  * (level+1 of them; Montgomery form where the Go method says so); otherwise NULL. */

@@ -25,6 +25,10 @@ SYMBOLS = {
     "b200_ctx_subring": (C.c_int, [VP, C.c_int, P64]),
     "b200_ctx_roots": (C.c_int, [VP, C.c_int, C.c_int, P64, C.c_size_t]),
     "b200_ctx_factors": (C.c_int, [VP, C.c_int, P64, C.c_int]),
+    "b200_poly_ipc_export": (C.c_int, [VP, C.c_char_p]),
+    "b200_peer_open": (C.c_int, [VP, C.c_char_p, C.POINTER(VP)]),
+    "b200_peer_close": (C.c_int, [VP, VP]),
+    "b200_intt_limbs_gather": (C.c_int, [VP, VP, VP, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(VP)]),
     "b200_poly_binary_size": (C.c_int, [VP, C.c_int, C.POINTER(C.c_size_t)]),
     "b200_poly_marshal": (C.c_int, [VP, C.c_int, C.c_int, VP, C.c_size_t, C.POINTER(C.c_size_t)]),
     "b200_poly_unmarshal": (C.c_int, [VP, C.c_int, VP, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),

@@ -540,6 +540,82 @@ extern "C" int b200_ntt_limbs(b200_ctx *ctx, const b200_poly *in, b200_poly *out
     return rc;
 }
 
+// ---- fused all-gather over NVLink peer memory (key-switch exchanges) --------------------------
+// One process per GPU: a rank exports its (library-allocated) polynomial with CUDA IPC, the peers map it, and the
+// inverse transform of the owned limbs writes its result into every rank's copy from inside the last kernel.
+extern "C" int b200_poly_ipc_export(const b200_poly *p, unsigned char handle[64]) {
+    if (!p || !handle) return fail(B200_EINVAL, "b200_poly_ipc_export: NULL argument");
+    if (!p->owned) return fail(B200_EINVAL, "b200_poly_ipc_export: only polynomials allocated by b200_poly_alloc can be exported");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CUDA_TRY(cudaSetDevice(p->ctx->device));
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, p->d));
+    std::memcpy(handle, &h, 64);
+    return 0;
+}
+extern "C" int b200_peer_open(b200_ctx *ctx, const unsigned char handle[64], void **device_ptr) {
+    if (!ctx || !handle || !device_ptr) return fail(B200_EINVAL, "b200_peer_open: NULL argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    CUDA_TRY(cudaIpcOpenMemHandle(device_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+extern "C" int b200_peer_close(b200_ctx *ctx, void *device_ptr) {
+    if (!ctx || !device_ptr) return fail(B200_EINVAL, "b200_peer_close: NULL argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaIpcCloseMemHandle(device_ptr));
+    return 0;
+}
+
+// shape-agnostic fallback of the fused gather: copy the freshly written limbs to the peers
+__global__ void __launch_bounds__(256)
+k_scatter_limbs(const u64 *src, PeerOut po, Span sp, int N) {
+    const int unit = blockIdx.y, b = unit / sp.nl, l = unit - b * sp.nl;
+    const size_t base = ((size_t)b * sp.Lbuf + l) * (size_t)N;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        const u64 v = src[base + i];
+        for (int k = 0; k < po.n; ++k) po.p[k][base + i] = v;
+    }
+}
+
+// Ring.INTT on limbs [limb0, limb0+nl) of `in` into `out` AND into the same limbs of npeers polynomials that live on
+// other GPUs (device pointers from b200_peer_open, same [batch][L][N] layout): the all-gather of the key switch
+// (coefficient-domain limbs before the basis extension, basis_extension.go:381-502) done by the producing kernel.
+// The caller orders the peers' reads after this call with any cross-GPU barrier on the stream.
+extern "C" int b200_intt_limbs_gather(b200_ctx *ctx, const b200_poly *in, b200_poly *out, int limb0, int nl, int flags,
+                                      int npeers, void *const *peer_polys) {
+    CtxLock lk(ctx);
+    int batch;
+    if (int rc = check_polys(ctx, 0, "b200_intt_limbs_gather", {in, out}, &batch)) return rc;
+    if (limb0 < 0 || nl < 0 || limb0 + nl > ctx->L) return fail(B200_ESHAPE, "b200_intt_limbs_gather: limb range out of bounds");
+    if (npeers < 0 || npeers > 7 || (npeers && !peer_polys)) return fail(B200_EINVAL, "b200_intt_limbs_gather: at most 7 peers");
+    if (nl == 0) return 0;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const size_t off = (size_t)limb0 * ctx->N;
+    PeerOut po;
+    po.n = npeers;
+    for (int i = 0; i < npeers; ++i) {
+        if (!peer_polys[i]) return fail(B200_EINVAL, "b200_intt_limbs_gather: NULL peer pointer");
+        po.p[i] = static_cast<u64 *>(peer_polys[i]) + off;
+    }
+    Span sp{batch, nl, ctx->L, limb0};
+    int rc = launch_ntt_big(ctx, in->d + off, out->d + off, sp, true, flags, &po);
+    if (rc != 1) return rc;
+    rc = launch_ntt_big(ctx, in->d + off, out->d + off, sp, true, flags);
+    if (rc == 1) rc = launch_ntt_generic(ctx, in->d + off, out->d + off, sp, true, flags);
+    if (rc || npeers == 0) return rc;
+    int chunks = (ctx->N + 255) / 256;
+    if (chunks > 64) chunks = 64;
+    {
+        LaunchScope ls(ctx, "scatter_limbs", (long long)batch * nl);
+        k_scatter_limbs<<<dim3(chunks, batch * nl), 256, 0, b200_cur_stream(ctx)>>>(out->d + off, po, sp, ctx->N);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int b200_ntt(b200_ctx *ctx, const b200_poly *in, b200_poly *out, int level, int flags) {
     CtxLock lk(ctx);
     return transform(ctx, in, out, level, flags, false, "b200_ntt");

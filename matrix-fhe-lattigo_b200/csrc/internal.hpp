@@ -128,5 +128,11 @@ int launch_ntt_generic(b200_ctx *ctx, const u64 *in, u64 *out, Span sp, bool inv
 // optimised two-pass path; returns 1 if the shape is not covered (caller falls back to generic)
 int big_tables_create(b200_ctx *ctx);
 void big_tables_destroy(b200_ctx *ctx);
-int launch_ntt_big(b200_ctx *ctx, const u64 *in, u64 *out, Span sp, bool inverse, int flags);
+// Extra destinations of an inverse transform on other GPUs of the box (peer device memory mapped through CUDA IPC):
+// the last pass stores every output word to `out` and to the same offset of each p[i] (fused all-gather over NVLink).
+struct PeerOut {
+    int n = 0;
+    u64 *p[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+int launch_ntt_big(b200_ctx *ctx, const u64 *in, u64 *out, Span sp, bool inverse, int flags, const PeerOut *peers = nullptr);
 int launch_polymul_big(b200_ctx *ctx, const u64 *a, const u64 *b, u64 *c, Span sp);

@@ -70,6 +70,7 @@ struct BigArgs {
     Span sp;
     int unit0, flags;
     int in_dense, out_dense;   // the pointer is a dense [chunk][N] ring buffer indexed by blockIdx.y
+    PeerOut peers;             // GATHER kernels only: mirrors of `out` on other GPUs
 };
 
 // word offsets of this CTA's unit in the input and output buffers, and its prime
@@ -170,6 +171,14 @@ __device__ __forceinline__ void std_(u64 *p, u64 v) {
 #else
     *p = v;
 #endif
+}
+template <bool GATHER>
+__device__ __forceinline__ void store_out(const PeerOut &po, u64 *out, size_t idx, u64 v) {
+    std_(out + idx, v);
+    if (GATHER) {   // peer-to-peer stores over NVLink; issued from the compute kernel so that they overlap the math
+#pragma unroll 1
+        for (int i = 0; i < po.n; ++i) po.p[i][idx] = v;
+    }
 }
 __device__ __forceinline__ void ldg256(const u64 *p, u64 &a, u64 &b, u64 &c, u64 &d) {
 #if B200_STREAM_DATA
@@ -444,7 +453,7 @@ k_cols_fwd_std16(const u64 *in, u64 *out, BigArgs a) {
     for (int k = 0; k < 8; ++k) std_(out + obase + (size_t)(g * 8 + k) * 256 + c, x[k]);
 }
 
-template <int CW>
+template <int CW, bool GATHER = false>
 __global__ void __launch_bounds__(CW * 32, B200_MINB_COLS_STD * 8 / CW)
 k_cols_inv_std16(const u64 *in, u64 *out, BigArgs a) {
     extern __shared__ __align__(16) u64 sm[];
@@ -489,7 +498,7 @@ k_cols_inv_std16(const u64 *in, u64 *out, BigArgs a) {
         x[o] = X; x[o + 4] = Y;
     }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) std_(out + obase + (size_t)(k * 32 + g) * 256 + c, x[k]);
+    for (int k = 0; k < 8; ++k) store_out<GATHER>(a.peers, out, obase + (size_t)(k * 32 + g) * 256 + c, x[k]);
 }
 
 // MATRIX, a = 15 (N = 3*2^15): rows (hd, u), hd in [0,6) = 3h + d, u in [0,64).
@@ -567,7 +576,7 @@ k_cols_fwd_m3_15(const u64 *in, u64 *out, BigArgs a) {
     }
 }
 
-template <int CW>
+template <int CW, bool GATHER = false>
 __global__ void __launch_bounds__(CW * 48, B200_MINB_COLS_M3 * 8 / CW)
 k_cols_inv_m3_15(const u64 *in, u64 *out, BigArgs a) {
     extern __shared__ __align__(16) u64 sm[];
@@ -632,7 +641,7 @@ k_cols_inv_m3_15(const u64 *in, u64 *out, BigArgs a) {
 #pragma unroll
         for (int hd = 0; hd < 6; ++hd)
 #pragma unroll
-            for (int b = 0; b < 2; ++b) std_(out + obase + (size_t)(hd * 64 + b * 32 + g) * 256 + c, x[hd][b]);
+            for (int b = 0; b < 2; ++b) store_out<GATHER>(a.peers, out, obase + (size_t)(hd * 64 + b * 32 + g) * 256 + c, x[hd][b]);
     }
 }
 
@@ -644,9 +653,10 @@ k_cols_inv_m3_15(const u64 *in, u64 *out, BigArgs a) {
 // ====================================================================================================
 constexpr int GCW = 8;
 
-template <int S, int ROOTS, int LOG, bool INV, bool FROM_G, bool TO_G, bool FOLD_NINV>
+template <int S, int ROOTS, int LOG, bool INV, bool FROM_G, bool TO_G, bool FOLD_NINV, bool GATHER = false>
 __device__ __forceinline__ void col_group(const u64 *gin, size_t ibase, u64 *gout, size_t obase, u64 *sm, int b0,
-                                          const tw_t *__restrict__ tw, const QC &qc, const tw_t ninv, const tw_t ninv_w1, bool lazy) {
+                                          const tw_t *__restrict__ tw, const QC &qc, const tw_t ninv, const tw_t ninv_w1, bool lazy,
+                                          const PeerOut *po = nullptr) {
     constexpr int M = 1 << S;
     const int ntiles = (GCW * ROOTS) << (LOG - S);
     for (int t = threadIdx.x; t < ntiles; t += blockDim.x) {
@@ -678,7 +688,7 @@ __device__ __forceinline__ void col_group(const u64 *gin, size_t ibase, u64 *gou
 #pragma unroll
         for (int k = 0; k < M; ++k) {
             const int row = row0 + (k << b0);
-            if (TO_G) std_(gout + obase + (size_t)row * 256 + c, x[k]);
+            if (TO_G) { if (GATHER) store_out<true>(*po, gout, obase + (size_t)row * 256 + c, x[k]); else std_(gout + obase + (size_t)row * 256 + c, x[k]); }
             else sm[pc(row * GCW + c)] = x[k];
         }
     }
@@ -688,7 +698,7 @@ constexpr int std_col_threads(int L) { if (L >= 6) return GCW << (L - 3); return
 constexpr int m3_col_threads(int L) { if (L >= 4) return (GCW * 6) << (L - 3); return 64; }
 constexpr int minb_for(int threads, int target) { return target / threads < 1 ? 1 : (target / threads > 16 ? 16 : target / threads); }
 
-template <int LOGR, int S1, int S2, int S3, bool INV>
+template <int LOGR, int S1, int S2, int S3, bool INV, bool GATHER = false>
 __global__ void __launch_bounds__(std_col_threads(LOGR), minb_for(std_col_threads(LOGR), 1024))
 k_cols_std_g(const u64 *in, u64 *out, BigArgs a) {
     static_assert(S1 + S2 + S3 == LOGR && S1 >= 1 && S2 >= 1, "group sizes");
@@ -719,12 +729,12 @@ k_cols_std_g(const u64 *in, u64 *out, BigArgs a) {
             col_group<S2, 1, LOGR, true, false, false, false>(in, ibase, out, obase, sm, S3, tw, qc, ninv, ninv_w1, lazy);
         }
         __syncthreads();
-        col_group<S1, 1, LOGR, true, false, true, true>(in, ibase, out, obase, sm, S2 + S3, tw, qc, ninv, ninv_w1, lazy);
+        col_group<S1, 1, LOGR, true, false, true, true, GATHER>(in, ibase, out, obase, sm, S2 + S3, tw, qc, ninv, ninv_w1, lazy, &a.peers);
     }
 }
 
 // MATRIX: first group = cyclotomic + radix-3 + S1 radix-2 layers on 6*2^S1 words; then groups on the u bits.
-template <int LOGU, int S1, int S2, int S3, bool INV>
+template <int LOGU, int S1, int S2, int S3, bool INV, bool GATHER = false>
 __global__ void __launch_bounds__(m3_col_threads(LOGU), minb_for(m3_col_threads(LOGU), 768))
 k_cols_m3_g(const u64 *in, u64 *out, BigArgs a) {
     static_assert(S1 + S2 + S3 == LOGU && S2 >= 1, "group sizes");
@@ -826,7 +836,7 @@ k_cols_m3_g(const u64 *in, u64 *out, BigArgs a) {
 #pragma unroll
             for (int hd = 0; hd < 6; ++hd)
 #pragma unroll
-                for (int k = 0; k < MA; ++k) std_(out + obase + (size_t)(hd * U + k * ULO + ulo) * 256 + c, x[hd][k]);
+                for (int k = 0; k < MA; ++k) store_out<GATHER>(a.peers, out, obase + (size_t)(hd * U + k * ULO + ulo) * 256 + c, x[hd][k]);
         }
     }
 }
@@ -837,20 +847,23 @@ typedef void (*kern_t)(const u64 *, u64 *, BigArgs);
 struct BigPlan {
     bool covered = false;
     int cw_fwd = 8, cw_inv = 8, vt = 2;
-    kern_t cols_fwd = nullptr, cols_inv = nullptr;
+    kern_t cols_fwd = nullptr, cols_inv = nullptr, cols_inv_gather = nullptr;
     int col_threads_fwd = 0, col_threads_inv = 0;
     size_t chunk_units = 0;   // units per launch group so that a chunk's intermediate stays in L2
 };
 
 #define STD_G(L, A, B, C) case L: plan->cols_fwd = (kern_t)k_cols_std_g<L, A, B, C, false>; plan->cols_inv = (kern_t)k_cols_std_g<L, A, B, C, true>; \
+                                  plan->cols_inv_gather = (kern_t)k_cols_std_g<L, A, B, C, true, true>; \
                                   plan->col_threads_fwd = plan->col_threads_inv = std_col_threads(L); break;
 #define M3_G(L, A, B, C) case L: plan->cols_fwd = (kern_t)k_cols_m3_g<L, A, B, C, false>; plan->cols_inv = (kern_t)k_cols_m3_g<L, A, B, C, true>; \
+                                 plan->cols_inv_gather = (kern_t)k_cols_m3_g<L, A, B, C, true, true>; \
                                  plan->col_threads_fwd = plan->col_threads_inv = m3_col_threads(L); break;
 // column-pass kernels for a ring shape: the hand-tuned ones for the two headline shapes, the generic family otherwise
 bool pick_col_kernels(BigPlan *plan, bool matrix, int log, bool force_generic) {
     if (!matrix) {
         if (log == 8 && !force_generic) {
             plan->cols_fwd = (kern_t)k_cols_fwd_std16<B200_CW_STD>; plan->cols_inv = (kern_t)k_cols_inv_std16<B200_CW_STD>;
+            plan->cols_inv_gather = (kern_t)k_cols_inv_std16<B200_CW_STD, true>;
             plan->cw_fwd = plan->cw_inv = B200_CW_STD;
             plan->col_threads_fwd = plan->col_threads_inv = B200_CW_STD * 32;
             return true;
@@ -862,6 +875,7 @@ bool pick_col_kernels(BigPlan *plan, bool matrix, int log, bool force_generic) {
     } else {
         if (log == 6 && !force_generic) {
             plan->cols_fwd = (kern_t)k_cols_fwd_m3_15<B200_CW_M3_FWD>; plan->cols_inv = (kern_t)k_cols_inv_m3_15<B200_CW_M3_INV>;
+            plan->cols_inv_gather = (kern_t)k_cols_inv_m3_15<B200_CW_M3_INV, true>;
             plan->cw_fwd = B200_CW_M3_FWD; plan->cw_inv = B200_CW_M3_INV;
             plan->col_threads_fwd = B200_CW_M3_FWD * 48; plan->col_threads_inv = B200_CW_M3_INV * 48;
             return true;
@@ -910,14 +924,16 @@ void big_tables_destroy(b200_ctx *ctx) {
     ctx->big = nullptr;
 }
 
-int launch_ntt_big(b200_ctx *ctx, const u64 *in, u64 *out, Span sp, bool inverse, int flags) {
+int launch_ntt_big(b200_ctx *ctx, const u64 *in, u64 *out, Span sp, bool inverse, int flags, const PeerOut *peers) {
     BigPlan *plan = (BigPlan *)ctx->big;
     if (!plan || !plan->covered) return 1;
+    const bool gather = peers && peers->n > 0;
+    if (gather && !inverse) return 1;   // only the inverse transform has a fused all-gather
     const bool matrix = ctx->ring_type == B200_RING_MATRIX;
     const bool permute = matrix && !(flags & B200_TREE_ORDER);
     const int N = ctx->N, R = N / 256, cw = inverse ? plan->cw_inv : plan->cw_fwd, vt = plan->vt;
     BigArgs a{ctx->d_consts, ctx->d_fwd, ctx->d_inv, ctx->d_misc, N, R, matrix ? ctx->a - 9 : 0, sp, 0, flags, 0, 0};
-    const kern_t ck = inverse ? plan->cols_inv : plan->cols_fwd;
+    const kern_t ck = inverse ? (gather ? plan->cols_inv_gather : plan->cols_inv) : plan->cols_fwd;
     const int col_threads = inverse ? plan->col_threads_inv : plan->col_threads_fwd;
     kern_t rk;
     int row_warps;
@@ -950,6 +966,7 @@ int launch_ntt_big(b200_ctx *ctx, const u64 *in, u64 *out, Span sp, bool inverse
         BigArgs first = a, second = a;
         first.out_dense = dense;
         second.in_dense = dense;
+        if (gather) second.peers = *peers;
         if (!inverse) {
             { LaunchScope ls(ctx, matrix ? "cols_fwd_m3" : "cols_fwd_std", nu);
               ck<<<dim3(nu, col_tiles), col_threads, col_smem, b200_cur_stream(ctx)>>>(in, tmp, first); }

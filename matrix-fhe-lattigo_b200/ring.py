@@ -174,6 +174,15 @@ class Poly:
         check(lib().b200_poly_download_limb(self.h, b, limb, out.ctypes.data_as(capi.P64), len(out)))
         return out
 
+    def DevicePtr(self):
+        return lib().b200_poly_device_ptr(self.h)
+
+    def IpcHandle(self):
+        """64-byte CUDA IPC handle of this (library-allocated) polynomial for Ring.OpenPeer in another process."""
+        buf = C.create_string_buffer(64)
+        check(lib().b200_poly_ipc_export(self.h, buf))
+        return buf.raw
+
     # -- wire format (ring/poly.go:97-160): structs.Matrix[uint64], little-endian --
     def BinarySize(self, level=None):
         out = C.c_size_t()
@@ -359,6 +368,22 @@ class Ring:
     def NTTLimbs(self, p1, p2, limb0, nl, inverse=False):
         """Ring.NTT / INTT on limbs [limb0, limb0+nl) only (a rank's share of a limb-sharded ring)."""
         check(lib().b200_ntt_limbs(self._ctx.h, p1.h, p2.h, limb0, nl, int(inverse), 0))
+
+    # -- fused all-gather over NVLink peer memory (one process per GPU) --
+    def OpenPeer(self, handle):
+        """Map a polynomial exported by another process (Poly.IpcHandle) into this rank; returns its device pointer."""
+        ptr = C.c_void_p()
+        check(lib().b200_peer_open(self._ctx.h, bytes(handle), C.byref(ptr)))
+        return ptr.value
+
+    def ClosePeer(self, ptr):
+        check(lib().b200_peer_close(self._ctx.h, C.c_void_p(ptr)))
+
+    def INTTLimbsGather(self, p1, p2, limb0, nl, peers):
+        """Ring.INTT on limbs [limb0, limb0+nl) of p1 into p2 and into the same limbs of the mapped peer polynomials
+        (device pointers from OpenPeer), written from inside the transform's last kernel."""
+        arr = (C.c_void_p * max(len(peers), 1))(*peers)
+        check(lib().b200_intt_limbs_gather(self._ctx.h, p1.h, p2.h, limb0, nl, 0, len(peers), arr))
 
     # -- fused ring product (BASELINE config 4) --
     def MulPoly(self, p1, p2, p3):

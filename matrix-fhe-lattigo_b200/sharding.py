@@ -128,3 +128,59 @@ def gadget_product_sharded(ks, ring, levelQ, levelP, cx_t, key, out0_t, out1_t, 
     ks.ModDownLimbs(levelQ, levelP, acc1, out1, q0, q1)
     ring.Sync()
     return q0, q1
+
+
+class ShardedKeySwitch:
+    """gadget_product_sharded with both exchanges fused into the producing kernels.
+
+    Every rank keeps three library-allocated work polynomials (coefficient-domain input, two accumulators), exports
+    them with CUDA IPC once, and maps the peers' copies.  The inverse transforms that precede the two exchanges of the
+    path then store their output into every rank's copy over NVLink from inside their last kernel
+    (b200_intt_limbs_gather); what is left of the collectives is a one-word all-reduce per exchange that orders the
+    peers' reads after the writes.  Those two barriers also protect the buffers against the next call (a rank cannot
+    pass barrier k before every rank has finished the work it queued ahead of barrier k)."""
+
+    def __init__(self, ks, ring, batch, rank, world_size):
+        import torch
+        import torch.distributed as dist
+        self.ks, self.ring, self.rank, self.world = ks, ring, rank, world_size
+        self.cxinv, self.acc0, self.acc1 = ring.NewPoly(batch), ring.NewPoly(batch), ring.NewPoly(batch)
+        ring.Sync()
+        mine = [p.IpcHandle() for p in (self.cxinv, self.acc0, self.acc1)]
+        everyone = [None] * world_size
+        if world_size > 1:
+            dist.all_gather_object(everyone, mine)
+        else:
+            everyone[0] = mine
+        self._mapped = [[ring.OpenPeer(everyone[r][i]) for r in range(world_size) if r != rank] for i in range(3)]
+        self._flag = torch.zeros(1, dtype=torch.int32, device="cuda:%d" % ring.device)
+
+    def _barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self._flag)   # stream-ordered: later kernels on this stream wait for every rank's earlier ones
+
+    def gadget_product(self, levelQ, levelP, cx, key, out0, out1):
+        """cx: owned Q limbs valid (NTT domain); out0/out1: the owned Q limbs receive the result."""
+        ks, ring, LQ = self.ks, self.ring, self.ks.LQ
+        q0, q1 = block_of_rank(levelQ + 1, self.world, self.rank)
+        p0, p1 = block_of_rank(levelP + 1, self.world, self.rank)
+        ring.INTTLimbsGather(cx, self.cxinv, q0, q1 - q0, self._mapped[0])
+        self._barrier()
+        ks.DecomposeMac(levelQ, levelP, cx, self.cxinv, key, self.acc0, self.acc1, q0, q1, p0, p1)
+        ring.INTTLimbsGather(self.acc0, self.acc0, LQ + p0, p1 - p0, self._mapped[1])
+        ring.INTTLimbsGather(self.acc1, self.acc1, LQ + p0, p1 - p0, self._mapped[2])
+        self._barrier()
+        ks.ModDownLimbs(levelQ, levelP, self.acc0, out0, q0, q1)
+        ks.ModDownLimbs(levelQ, levelP, self.acc1, out1, q0, q1)
+        return q0, q1
+
+    def close(self):
+        self.ring.Sync()
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        for group in self._mapped:
+            for ptr in group:
+                self.ring.ClosePeer(ptr)
+        self._mapped = [[], [], []]

@@ -78,6 +78,37 @@ def test_sharded_steps_emulated_on_one_gpu(kind, N, LQ, LP, G):
             assert (got[:, qb[r][0]: qb[r][1]] == want[:, qb[r][0]: qb[r][1]]).all(), (c, r)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,N", [("m3", 3 * 2**15), ("std", 1 << 16), ("std", 1 << 13), ("m3", 3 * 2**12), ("std", 64), ("m3", 9 * 2**6)])
+def test_gather_inverse_writes_every_destination(kind, N):
+    """b200_intt_limbs_gather with the 'peers' on the same GPU: every destination receives the transform of the
+    requested limbs (tuned, generic and fallback kernel families) and nothing else is touched."""
+    L, batch = 4, 2
+    primes = QI60[:L] if kind == "std" else O.find_3n_rns_primes(N, 60, L)
+    ring = b200ring.NewRing(N, primes)
+    rng = np.random.default_rng(9)
+    host = np.stack([np.stack([rng.integers(0, q, N, dtype=np.uint64) for q in primes]) for _ in range(batch)])
+    src, want = ring.NewPoly(batch).set(host), ring.NewPoly(batch)
+    ring.INTT(src, want)
+    w = want.get()
+    for limb0, nl, npeers in ((1, 2, 3), (0, 4, 1), (3, 1, 7), (2, 2, 0)):
+        sentinel = np.full_like(host, 12345)
+        out = ring.NewPoly(batch).set(sentinel)
+        peers = [ring.NewPoly(batch).set(sentinel) for _ in range(npeers)]
+        ring.INTTLimbsGather(src, out, limb0, nl, [p.DevicePtr() for p in peers])
+        for dst in [out] + peers:
+            g = dst.get()
+            assert (g[:, limb0:limb0 + nl] == w[:, limb0:limb0 + nl]).all()
+            mask = np.ones(L, dtype=bool); mask[limb0:limb0 + nl] = False
+            assert (g[:, mask] == 12345).all()
+    # in place (the accumulators of the key switch are transformed where they are)
+    peer = ring.NewPoly(batch)
+    ring.INTTLimbsGather(src, src, 0, L, [peer.DevicePtr()])
+    assert (src.get() == w).all() and (peer.get() == w).all()
+    with pytest.raises(b200ring.B200Error):
+        ring.INTTLimbsGather(src, src, 0, L, [peer.DevicePtr()] * 8)
+
+
 WORKER = r'''
 import os, sys
 sys.path.insert(0, %r)
@@ -104,6 +135,13 @@ o0, o1 = torch.zeros_like(cx_t), torch.zeros_like(cx_t)
 sharding.gadget_product_sharded(ks, ring, levelQ, levelP, cx_t, key, o0, o1, rank, world)
 g0, g1 = o0.cpu().numpy().view(np.uint64), o1.cpu().numpy().view(np.uint64)
 assert (g0[:, q0:q1] == w0.get()[:, q0:q1]).all() and (g1[:, q0:q1] == w1.get()[:, q0:q1]).all(), "sharded result differs"
+# the same with both exchanges fused into the producing kernels (peer stores over NVLink + one-word barriers)
+fused = sharding.ShardedKeySwitch(ks, ring, batch, rank, world)
+cxp = ring.NewPoly(batch).set(mine); f0, f1 = ring.NewPoly(batch), ring.NewPoly(batch)
+for _ in range(3):                                                        # repeated calls reuse the mapped buffers
+    fused.gadget_product(levelQ, levelP, cxp, key, f0, f1)
+assert (f0.get()[:, q0:q1] == w0.get()[:, q0:q1]).all() and (f1.get()[:, q0:q1] == w1.get()[:, q0:q1]).all(), "fused sharded result differs"
+fused.close()
 dist.barrier(); dist.destroy_process_group()
 os.write(1, ("rank" + str(rank) + "-ok\n").encode())
 '''

@@ -24,6 +24,7 @@ ap.add_argument("--lq", type=int, default=24)
 ap.add_argument("--lp", type=int, default=6)
 ap.add_argument("--a", type=int, default=15)
 ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--fused", action="store_true", help="exchanges fused into the inverse transforms (peer stores over NVLink)")
 args = ap.parse_args()
 rank, local, world = sharding.init_process_group()
 dev = torch.device("cuda", local)
@@ -42,8 +43,16 @@ key = b200ring.Poly.from_torch(ring, key_t)
 o0, o1 = torch.zeros_like(cx_t), torch.zeros_like(cx_t)
 
 
+fused = None
+if args.fused:
+    fused = sharding.ShardedKeySwitch(ks, ring, B, rank, world)
+    cx_p, o0_p, o1_p = b200ring.Poly.from_torch(ring, cx_t), b200ring.Poly.from_torch(ring, o0), b200ring.Poly.from_torch(ring, o1)
+
+
 def run():
-    if world == 1:
+    if fused is not None:
+        fused.gadget_product(levelQ, levelP, cx_p, key, o0_p, o1_p)
+    elif world == 1:
         ks.GadgetProduct(levelQ, levelP, b200ring.Poly.from_torch(ring, cx_t), key, b200ring.Poly.from_torch(ring, o0), b200ring.Poly.from_torch(ring, o1))
     else:
         sharding.gadget_product_sharded(ks, ring, levelQ, levelP, cx_t, key, o0, o1, rank, world)
@@ -68,8 +77,10 @@ ms = sharding.max_over_ranks(e0.elapsed_time(e1) / args.reps, device=dev)
 q0, q1 = sharding.block_of_rank(levelQ + 1, world, rank)
 chk = int(o0[:, q0:q1].sum().item()) & 0xFFFFFFFF
 if rank == 0:
-    print(json.dumps({"workload": "gadget product N=%d LQ=%d LP=%d beta=%d batch=%d" % (N, LQ, LP, beta, B), "n_gpus": world,
+    print(json.dumps({"workload": "gadget product N=%d LQ=%d LP=%d beta=%d batch=%d" % (N, LQ, LP, beta, B), "n_gpus": world, "fused_exchanges": bool(args.fused),
                       "ms": ms, "key_switches_per_s": B / (ms * 1e-3), "limb_transforms_per_s": B * 180 / (ms * 1e-3) if (LQ, LP) == (24, 6) else None,
                       "allgather_bytes_per_step": B * (LQ + 2 * LP) * N * 8, "checksum_rank0": chk}))
+if fused is not None:
+    fused.close()
 if world > 1:
     torch.distributed.destroy_process_group()
