@@ -6,6 +6,7 @@
 // where Go panics.  INTEGRATION.md shows the equivalent cgo file for package `ring`.
 #pragma once
 #include <cstdint>
+#include <array>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -73,6 +74,12 @@ class Poly {
         check(b200_poly_unmarshal(h_, b, data.data(), data.size(), &level, consumed));
         return level;
     }
+    std::array<unsigned char, 64> IpcHandle() const {   // CUDA IPC handle for Ring::OpenPeer in another process
+        std::array<unsigned char, 64> h{};
+        check(b200_poly_ipc_export(h_, h.data()));
+        return h;
+    }
+    void *DevicePtr() const { return b200_poly_device_ptr(h_); }
     b200_poly *handle() const { return h_; }
 
   private:
@@ -151,6 +158,21 @@ class Ring {
     void TransformHost(const std::vector<uint64_t> &in, std::vector<uint64_t> &out, const std::vector<int> &ops) const {
         const size_t per = (size_t)ModuliChainLength() * N();
         check(b200_transform_host(ctx_.get(), in.data(), out.data(), (int)(in.size() / per), level_, ops.data(), (int)ops.size(), 0));
+    }
+    // a rank's share of a limb-sharded ring: transforms on limbs [limb0, limb0+nl) only
+    void NTTLimbs(const Poly &p1, Poly &p2, int limb0, int nl, bool inverse = false) const {
+        check(b200_ntt_limbs(ctx_.get(), p1.handle(), p2.handle(), limb0, nl, inverse, 0));
+    }
+    // inverse transform whose last kernel also stores into the same limbs of polynomials mapped from other GPUs
+    // (Poly::IpcHandle in the owning process, OpenPeer here): the key switch's all-gather fused into its producer
+    void *OpenPeer(const std::array<unsigned char, 64> &handle) const {
+        void *ptr = nullptr;
+        check(b200_peer_open(ctx_.get(), handle.data(), &ptr));
+        return ptr;
+    }
+    void ClosePeer(void *ptr) const { check(b200_peer_close(ctx_.get(), ptr)); }
+    void INTTLimbsGather(const Poly &p1, Poly &p2, int limb0, int nl, const std::vector<void *> &peers) const {
+        check(b200_intt_limbs_gather(ctx_.get(), p1.handle(), p2.handle(), limb0, nl, 0, (int)peers.size(), peers.data()));
     }
     // fused NTT, NTT, MForm, MulCoeffsMontgomery, INTT (BASELINE config 4)
     void MulPoly(const Poly &a, const Poly &b, Poly &c) const { check(b200_polymul(ctx_.get(), a.handle(), b.handle(), c.handle(), level_)); }

@@ -67,6 +67,13 @@ int main(int argc, char **argv) {
         try { c3.UnmarshalBinary(0, std::vector<unsigned char>(w.begin(), w.end() - 1)); } catch (const ring::Panic &) { bad = true; }
         EXPECT(bad);
     }
+    {   // inverse transform with extra destinations (the key switch's fused all-gather; here the "peer" is local)
+        ring::Poly g1 = r.NewPoly(), g2 = r.NewPoly(), peer = r.NewPoly();
+        r.NTT(x, z);
+        r.INTT(z, g1);
+        r.INTTLimbsGather(z, g2, 0, 2, {peer.DevicePtr()});
+        EXPECT(g1.Get() == g2.Get() && peer.Get() == g1.Get());
+    }
     bool panicked = false;
     try { r.AtLevel(5); } catch (const ring::Panic &) { panicked = true; }
     EXPECT(panicked);
