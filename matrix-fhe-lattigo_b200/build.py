@@ -42,7 +42,8 @@ def build(force=False, verbose=True, tag="", defines=()):
     lib = LIB.replace(".so", tag + ".so")
     hm = _deps()
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
-        res = list(ex.map(lambda s: _compile(s, force, hm, tag if s == "ntt_big.cu" else "", defines if s == "ntt_big.cu" else ()), SOURCES))
+        tuned = ("ntt_big.cu", "keyswitch.cu")   # the sources that have compile-time tuning knobs
+        res = list(ex.map(lambda s: _compile(s, force, hm, tag if s in tuned else "", defines if s in tuned else ()), SOURCES))
     objs = [o for o, _ in res]
     if force or any(ch for _, ch in res) or not os.path.exists(lib):
         subprocess.check_call([NVCC, "-shared", "-o", lib] + objs + ["-cudart", "static", "-ccbin", "g++", "-Wno-deprecated-gpu-targets"])

@@ -73,6 +73,84 @@ k_basis_extend(const u64 *src, u64 *dst, const LimbConst *__restrict__ consts, E
     }
 }
 
+// Specialisation for the digit sizes the key switch uses (NS <= 8 source limbs): all per-prime constants of the CTA
+// staged once in shared memory, the source residues in registers, two coefficients per thread so that every constant
+// read feeds two 128-bit multiply-accumulates.  Same arithmetic, same order of the float64 operations.
+#ifndef B200_EXT_CPT
+#define B200_EXT_CPT 2
+#endif
+constexpr int EXT_CPT = B200_EXT_CPT;   // coefficients per thread
+template <int NS>
+__global__ void __launch_bounds__(EXT_THREADS)
+k_basis_extend_ns(const u64 *src, u64 *dst, const LimbConst *__restrict__ consts, ExtDesc d, int N, int Lbuf, int mode) {
+    extern __shared__ __align__(16) u64 csm[];
+    // layout: src: q[NS] qinv[NS] half[NS] qinvqi[NS] qd[NS] | per target: q qinv sub k[NS] vq[NS+1]
+    u64 *sq = csm, *sqinv = sq + NS, *shalf = sqinv + NS, *sfac = shalf + NS;
+    double *sqd = reinterpret_cast<double *>(sfac + NS);
+    u64 *tg = reinterpret_cast<u64 *>(sqd + NS);
+    constexpr int TSTRIDE = 3 + NS + NS + 1;
+    for (int i = threadIdx.x; i < NS; i += EXT_THREADS) {
+        const LimbConst c = consts[d.src_limb[i]];
+        sq[i] = c.q; sqinv[i] = c.qinv; shalf[i] = d.half[i]; sfac[i] = d.qoverqiinvqi[i]; sqd[i] = (double)c.q;
+    }
+    for (int t = threadIdx.x; t < d.nt * TSTRIDE; t += EXT_THREADS) {
+        const int j = t / TSTRIDE, f = t - j * TSTRIDE;
+        u64 v;
+        if (f == 0) v = consts[d.dst_limb[j]].q;
+        else if (f == 1) v = consts[d.dst_limb[j]].qinv;
+        else if (f == 2) v = d.sub[j];
+        else if (f < 3 + NS) v = d.qoverqimodp[(size_t)j * NS + (f - 3)];
+        else v = d.vtimesqmodp[(size_t)j * (NS + 1) + (f - 3 - NS)];
+        tg[t] = v;
+    }
+    __syncthreads();
+    const int b = blockIdx.y;
+    const int x0 = blockIdx.x * (EXT_THREADS * EXT_CPT) + threadIdx.x;
+    const u64 *s = src + (size_t)b * Lbuf * N;
+    u64 *o = dst + (size_t)b * Lbuf * N;
+    u64 y[EXT_CPT][NS];
+    unsigned v[EXT_CPT];
+    bool live[EXT_CPT];
+#pragma unroll
+    for (int e = 0; e < EXT_CPT; ++e) {
+        const int x = x0 + e * EXT_THREADS;
+        live[e] = x < N;
+        double vi = 0.0;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {                                      // reconstructRNS[Centered]
+            const u64 w = live[e] ? s[(size_t)d.src_limb[i] * N + x] : 0;
+            y[e][i] = mred(w + shalf[i], sfac[i], sq[i], sqinv[i]);
+            vi = __dadd_rn(vi, __ddiv_rn((double)y[e][i], sqd[i]));         // no contraction, same order as the Go loop
+        }
+        v[e] = (unsigned)(u64)vi;
+    }
+    for (int j = 0; j < d.nt; ++j) {                                        // multSum
+        const u64 *t = tg + j * TSTRIDE;
+        const u64 q = t[0], qinv = t[1], sub = t[2];
+        u64 rlo[EXT_CPT], rhi[EXT_CPT];
+#pragma unroll
+        for (int e = 0; e < EXT_CPT; ++e) rlo[e] = rhi[e] = 0;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            const u64 k = t[3 + i];
+#pragma unroll
+            for (int e = 0; e < EXT_CPT; ++e) {
+                const u64 mlo = y[e][i] * k, mhi = __umul64hi(y[e][i], k);
+                rlo[e] += mlo;
+                rhi[e] += mhi + (rlo[e] < mlo);
+            }
+        }
+        u64 *oj = o + (size_t)d.dst_limb[j] * N;
+#pragma unroll
+        for (int e = 0; e < EXT_CPT; ++e) {
+            u64 r = rhi[e] - __umul64hi(rlo[e] * qinv, q) + q + t[3 + NS + v[e]];   // [0, 3p)
+            r = csub(r + q - sub, q);                                           // SubScalar
+            if (mode == 1) r = csub(csub(r, 2 * q), q);
+            if (live[e]) oj[x0 + e * EXT_THREADS] = r;
+        }
+    }
+}
+
 // single-limb digit of DecomposeAndSplit (:402-428): centred lift of one limb, written canonically
 __global__ void __launch_bounds__(256)
 k_decompose_single(const u64 *src, u64 *dst, const LimbConst *__restrict__ consts, int src_limb, const int *dst_limb, int nt,
@@ -93,19 +171,43 @@ k_decompose_single(const u64 *src, u64 *dst, const LimbConst *__restrict__ const
 
 // acc_c[x] (+)= MRed(key[d][c][x], operand[x]) for both components; the operand of the digit's own limbs is the
 // NTT-domain input itself (rlwe/evaluator_gadget_product.go:466-472), all others come from the decomposition.
+// Up to MAC_DIGITS digits per pass: the accumulators are read (unless `first`) and written once for the whole group
+// instead of once per digit (4 of every 7 words a per-digit pass moves).
+constexpr int MAC_DIGITS = 4;
+struct MacGroup {
+    const u64 *op[MAC_DIGITS];             // decomposition of digit g (NTT domain), [batch][L][N]
+    const u64 *k0[MAC_DIGITS], *k1[MAC_DIGITS];
+    int st[MAC_DIGITS], ed[MAC_DIGITS];    // the digit's own limbs read the input itself
+};
+template <int ND>
 __global__ void __launch_bounds__(256)
-k_gadget_mac(const u64 *cx, const u64 *c2, const u64 *key0, const u64 *key1, u64 *acc0, u64 *acc1,
-             const LimbConst *__restrict__ consts, const int *limbs, int nlimbs, int st, int ed, int N, int Lbuf, int first) {
-    const int unit = blockIdx.y;                       // (poly, limb index in `limbs`)
+k_gadget_mac_group(const u64 *cx, MacGroup m, u64 *acc0, u64 *acc1, const LimbConst *__restrict__ consts, const int *limbs,
+                   int nlimbs, int N, int Lbuf, int first) {
+    const int unit = blockIdx.y;
     const int b = unit / nlimbs, limb = limbs[unit % nlimbs];
     const LimbConst c = consts[limb];
     const size_t base = ((size_t)b * Lbuf + limb) * (size_t)N, kbase = (size_t)limb * N;
-    const u64 *op = (limb >= st && limb < ed) ? cx : c2;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
-        const u64 v = op[base + i];
-        const u64 m0 = mred(key0[kbase + i], v, c.q, c.qinv), m1 = mred(key1[kbase + i], v, c.q, c.qinv);
-        acc0[base + i] = first ? m0 : csub(acc0[base + i] + m0, c.q);
-        acc1[base + i] = first ? m1 : csub(acc1[base + i] + m1, c.q);
+    const u64 *op[ND];
+#pragma unroll
+    for (int g = 0; g < ND; ++g) op[g] = (limb >= m.st[g] && limb < m.ed[g]) ? cx : m.op[g];
+    for (int i = 2 * (blockIdx.x * blockDim.x + threadIdx.x); i < N; i += 2 * gridDim.x * blockDim.x) {
+        ulonglong2 a0 = make_ulonglong2(0, 0), a1 = make_ulonglong2(0, 0);
+        if (!first) {
+            a0 = *reinterpret_cast<const ulonglong2 *>(acc0 + base + i);
+            a1 = *reinterpret_cast<const ulonglong2 *>(acc1 + base + i);
+        }
+#pragma unroll
+        for (int g = 0; g < ND; ++g) {
+            const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(op[g] + base + i);
+            const ulonglong2 x0 = *reinterpret_cast<const ulonglong2 *>(m.k0[g] + kbase + i);
+            const ulonglong2 x1 = *reinterpret_cast<const ulonglong2 *>(m.k1[g] + kbase + i);
+            a0.x = csub(a0.x + mred(x0.x, v.x, c.q, c.qinv), c.q);
+            a0.y = csub(a0.y + mred(x0.y, v.y, c.q, c.qinv), c.q);
+            a1.x = csub(a1.x + mred(x1.x, v.x, c.q, c.qinv), c.q);
+            a1.y = csub(a1.y + mred(x1.y, v.y, c.q, c.qinv), c.q);
+        }
+        *reinterpret_cast<ulonglong2 *>(acc0 + base + i) = a0;
+        *reinterpret_cast<ulonglong2 *>(acc1 + base + i) = a1;
     }
 }
 
@@ -201,8 +303,19 @@ int run_extend(b200_keyswitch *ks, Extender *e, const u64 *src, u64 *dst, int ba
     b200_ctx *ctx = ks->ctx;
     const int N = ctx->N;
     LaunchScope ls(ctx, "basis_extend", (long long)batch * e->nt);
-    k_basis_extend<<<dim3((N + EXT_THREADS - 1) / EXT_THREADS, batch), EXT_THREADS, sizeof(u64) * e->ns * EXT_THREADS, b200_cur_stream(ctx)>>>(
-        src, dst, ctx->d_consts, e->desc(), N, ctx->L, mode);
+    cudaStream_t st = b200_cur_stream(ctx);
+    const int ns = e->ns;
+    const size_t csm = sizeof(u64) * ((size_t)5 * ns + (size_t)e->nt * (3 + 2 * ns + 1));
+    const dim3 grid2((N + EXT_THREADS * EXT_CPT - 1) / (EXT_THREADS * EXT_CPT), batch);
+    static const bool generic_only = std::getenv("B200_EXT_GENERIC") != nullptr;
+#define EXT_NS(K) case K: k_basis_extend_ns<K><<<grid2, EXT_THREADS, csm, st>>>(src, dst, ctx->d_consts, e->desc(), N, ctx->L, mode); break;
+    if (ns >= 1 && ns <= 8 && csm <= 48 * 1024 && !generic_only) {
+        switch (ns) { EXT_NS(1) EXT_NS(2) EXT_NS(3) EXT_NS(4) EXT_NS(5) EXT_NS(6) EXT_NS(7) EXT_NS(8) }
+    } else {
+        k_basis_extend<<<dim3((N + EXT_THREADS - 1) / EXT_THREADS, batch), EXT_THREADS, sizeof(u64) * ns * EXT_THREADS, st>>>(
+            src, dst, ctx->d_consts, e->desc(), N, ctx->L, mode);
+    }
+#undef EXT_NS
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -277,6 +390,7 @@ int mod_down_ntt(b200_keyswitch *ks, int levelQ, int levelP, const u64 *p1, u64 
 // Digit loop of gadgetProductMultiplePLazy (:123-188) restricted to the owned limbs: decomposition of every digit
 // into the owned targets, their NTT, and the multiply-accumulate with the owned key limbs.  cxinv must hold ALL
 // Q limbs 0..levelQ in the coefficient domain (after the all-gather when sharded); cx the owned Q limbs in the NTT domain.
+// c2: min(beta, MAC_DIGITS) scratch polynomials of [B][L][N] words.
 int decompose_mac(b200_keyswitch *ks, int levelQ, int levelP, const u64 *cx, const u64 *cxinv, const u64 *key, u64 *c2,
                   u64 *acc0, u64 *acc1, int B, Own o) {
     b200_ctx *ctx = ks->ctx;
@@ -289,35 +403,55 @@ int decompose_mac(b200_keyswitch *ks, int levelQ, int levelP, const u64 *cx, con
         cudaError_t ce = upload(&d_limbs, limbs);
         if (ce != cudaSuccess) return b200_cuda_fail(ce, "gadget product limb list");
     }
+    // digits are processed in groups of MAC_DIGITS: decomposition + NTT per digit into its own slot of c2, then ONE
+    // multiply-accumulate pass over the group
+    const size_t words = (size_t)B * ctx->L * N;
     int rc = 0;
-    for (int d = 0; d < beta && rc == 0; ++d) {
-        const int st = d * nbPi, ed = std::min(st + nbPi, levelQ + 1);
-        std::vector<int> dst;
-        for (int j = o.q0; j < o.q1; ++j) if (j < st || j >= ed) dst.push_back(j);
-        for (int j = o.p0; j < o.p1; ++j) dst.push_back(LQ + j);
-        if (!dst.empty()) {
-            if (ed - st == 1) {                                                                  // single-limb digit (:402-428)
-                Extender *e;   // only used as a cached holder of the target list
-                if ((rc = get_extender(ks, range(st, ed), dst, false, &e))) break;
-                LaunchScope ls(ctx, "decompose_single", (long long)B * (int)dst.size());
-                k_decompose_single<<<dim3((N + 255) / 256, B), 256, 0, b200_cur_stream(ctx)>>>(cxinv, c2, ctx->d_consts, st, e->d_dst, (int)dst.size(), N, ctx->L);
-            } else {                                                                             // exact centred conversion (:430-500)
-                Extender *e;
-                if ((rc = get_extender(ks, range(st, ed), dst, true, &e))) break;
-                if ((rc = run_extend(ks, e, cxinv, c2, B, 1))) break;
+    for (int d0 = 0; d0 < beta && rc == 0; d0 += MAC_DIGITS) {
+        const int nd = std::min(MAC_DIGITS, beta - d0);
+        MacGroup mg{};
+        for (int g = 0; g < nd && rc == 0; ++g) {
+            const int d = d0 + g;
+            const int st = d * nbPi, ed = std::min(st + nbPi, levelQ + 1);
+            u64 *c2d = c2 + (size_t)g * words;
+            std::vector<int> dst;
+            for (int j = o.q0; j < o.q1; ++j) if (j < st || j >= ed) dst.push_back(j);
+            for (int j = o.p0; j < o.p1; ++j) dst.push_back(LQ + j);
+            if (!dst.empty()) {
+                if (ed - st == 1) {                                                                  // single-limb digit (:402-428)
+                    Extender *e;   // only used as a cached holder of the target list
+                    if ((rc = get_extender(ks, range(st, ed), dst, false, &e))) break;
+                    LaunchScope ls(ctx, "decompose_single", (long long)B * (int)dst.size());
+                    k_decompose_single<<<dim3((N + 255) / 256, B), 256, 0, b200_cur_stream(ctx)>>>(cxinv, c2d, ctx->d_consts, st, e->d_dst, (int)dst.size(), N, ctx->L);
+                } else {                                                                             // exact centred conversion (:430-500)
+                    Extender *e;
+                    if ((rc = get_extender(ks, range(st, ed), dst, true, &e))) break;
+                    if ((rc = run_extend(ks, e, cxinv, c2d, B, 1))) break;
+                }
+                // DecomposeSingleNTT (:466-477): NTT of every owned limb outside the digit, and of the owned P limbs
+                const int a0 = o.q0, a1 = std::min(o.q1, st), b0 = std::max(o.q0, ed), b1 = o.q1;
+                if ((rc = ntt_range(ctx, c2d, c2d, B, a0, a1 - a0, false))) break;
+                if ((rc = ntt_range(ctx, c2d, c2d, B, b0, b1 - b0, false))) break;
+                if ((rc = ntt_range(ctx, c2d, c2d, B, LQ + o.p0, o.p1 - o.p0, false))) break;
             }
-            // DecomposeSingleNTT (:466-477): NTT of every owned limb outside the digit, and of the owned P limbs
-            const int a0 = o.q0, a1 = std::min(o.q1, st), b0 = std::max(o.q0, ed), b1 = o.q1;
-            if ((rc = ntt_range(ctx, c2, c2, B, a0, a1 - a0, false))) break;
-            if ((rc = ntt_range(ctx, c2, c2, B, b0, b1 - b0, false))) break;
-            if ((rc = ntt_range(ctx, c2, c2, B, LQ + o.p0, o.p1 - o.p0, false))) break;
+            mg.op[g] = c2d;
+            mg.k0[g] = key + (size_t)(2 * d) * ctx->L * N;
+            mg.k1[g] = key + (size_t)(2 * d + 1) * ctx->L * N;
+            mg.st[g] = st; mg.ed[g] = ed;
         }
-        const u64 *k0 = key + (size_t)(2 * d) * ctx->L * N, *k1 = key + (size_t)(2 * d + 1) * ctx->L * N;
-        int chunks = (N + 255) / 256;
-        if (chunks > 256) chunks = 256;
-        LaunchScope ls(ctx, "gadget_mac", (long long)B * (int)limbs.size());
-        k_gadget_mac<<<dim3(chunks, B * (int)limbs.size()), 256, 0, b200_cur_stream(ctx)>>>(cx, c2, k0, k1, acc0, acc1, ctx->d_consts,
-                                                                                           d_limbs, (int)limbs.size(), st, ed, N, ctx->L, d == 0);
+        if (rc) break;
+        int chunks = (N / 2 + 255) / 256;
+        if (chunks > 128) chunks = 128;
+        const dim3 grid(chunks, B * (int)limbs.size());
+        LaunchScope ls(ctx, "gadget_mac", (long long)B * (int)limbs.size() * nd);
+        cudaStream_t st_ = b200_cur_stream(ctx);
+        const int first = d0 == 0, nl = (int)limbs.size();
+        switch (nd) {
+        case 1: k_gadget_mac_group<1><<<grid, 256, 0, st_>>>(cx, mg, acc0, acc1, ctx->d_consts, d_limbs, nl, N, ctx->L, first); break;
+        case 2: k_gadget_mac_group<2><<<grid, 256, 0, st_>>>(cx, mg, acc0, acc1, ctx->d_consts, d_limbs, nl, N, ctx->L, first); break;
+        case 3: k_gadget_mac_group<3><<<grid, 256, 0, st_>>>(cx, mg, acc0, acc1, ctx->d_consts, d_limbs, nl, N, ctx->L, first); break;
+        default: k_gadget_mac_group<4><<<grid, 256, 0, st_>>>(cx, mg, acc0, acc1, ctx->d_consts, d_limbs, nl, N, ctx->L, first); break;
+        }
         CUDA_TRY(cudaGetLastError());
     }
     return rc;
@@ -407,8 +541,9 @@ extern "C" int b200_gadget_product(b200_keyswitch *ks, int levelQ, int levelP, c
     if (ct0->batch != B || ct1->batch != B || ct0->d == ct1->d) { b200_set_error("b200_gadget_product: outputs must be two distinct polynomials of the input's batch size"); return B200_ESHAPE; }
     CUDA_TRY(cudaSetDevice(ctx->device));
     const size_t words = (size_t)B * ctx->L * N;
-    if (int rc = ensure_ws(ks, 4 * words)) return rc;
-    u64 *cxinv = ks->ws, *c2 = ks->ws + words, *acc0 = ks->ws + 2 * words, *acc1 = ks->ws + 3 * words;
+    const int slots = std::min(beta, MAC_DIGITS);
+    if (int rc = ensure_ws(ks, (3 + slots) * words)) return rc;
+    u64 *cxinv = ks->ws, *acc0 = ks->ws + words, *acc1 = ks->ws + 2 * words, *c2 = ks->ws + 3 * words;
     int rc = ntt_range(ctx, cx->d, cxinv, B, 0, levelQ + 1, true);                               // ringQ.INTT(cxNTT, cxInvNTT)
     if (rc) return rc;
     if ((rc = decompose_mac(ks, levelQ, levelP, cx->d, cxinv, key->d, c2, acc0, acc1, B, Own{0, levelQ + 1, 0, levelP + 1}))) return rc;
@@ -436,7 +571,7 @@ extern "C" int b200_ks_decompose_mac(b200_keyswitch *ks, int levelQ, int levelP,
     }
     CUDA_TRY(cudaSetDevice(ctx->device));
     const size_t words = (size_t)B * ctx->L * ctx->N;
-    if (int rc = ensure_ws(ks, words)) return rc;
+    if (int rc = ensure_ws(ks, (size_t)std::min(beta, MAC_DIGITS) * words)) return rc;
     return decompose_mac(ks, levelQ, levelP, cx->d, cxinv->d, key->d, ks->ws, acc0->d, acc1->d, B, o);
 }
 
@@ -476,9 +611,9 @@ extern "C" int b200_mul_relin(b200_keyswitch *ks, int levelQ, int levelP, const 
     }
     CUDA_TRY(cudaSetDevice(ctx->device));
     const size_t words = (size_t)B * ctx->L * N;
-    if (int rc = ensure_ws(ks, 8 * words)) return rc;
-    u64 *cxinv = ks->ws, *c2buf = ks->ws + words, *acc0 = ks->ws + 2 * words, *acc1 = ks->ws + 3 * words;
-    u64 *t0 = ks->ws + 4 * words, *t1 = ks->ws + 5 * words, *t2 = ks->ws + 6 * words, *g = ks->ws + 7 * words;
+    if (int rc = ensure_ws(ks, (size_t)(7 + std::min(beta, MAC_DIGITS)) * words)) return rc;
+    u64 *cxinv = ks->ws, *acc0 = ks->ws + words, *acc1 = ks->ws + 2 * words;
+    u64 *t0 = ks->ws + 3 * words, *t1 = ks->ws + 4 * words, *t2 = ks->ws + 5 * words, *g = ks->ws + 6 * words, *c2buf = ks->ws + 7 * words;
     const Span spq{B, levelQ + 1, ctx->L, 0};
     int rc = launch_tensor(ctx, a0->d, a1->d, b0->d, b1->d, t0, t1, t2, spq, mform_first != 0);
     if (rc) return rc;
