@@ -127,23 +127,38 @@ k_basis_extend_ns(const u64 *src, u64 *dst, const LimbConst *__restrict__ consts
     for (int j = 0; j < d.nt; ++j) {                                        // multSum
         const u64 *t = tg + j * TSTRIDE;
         const u64 q = t[0], qinv = t[1], sub = t[2];
-        u64 rlo[EXT_CPT], rhi[EXT_CPT];
+        // 128-bit sum of the NS products y_i * k_i by columns of 32-bit partial products (each computed once):
+        //   A  = sum y0*k0 (64 bits + carry count cc),  S1 = sum (y0*k1 + y1*k0),  S2 = sum y1*k1
+        // y_i, k_i < 2^61 so their high words are < 2^29: S2 cannot overflow, S1 holds 4 sources (8 terms < 2^61).
+        u64 A[EXT_CPT], S1a[EXT_CPT], S1b[EXT_CPT], S2[EXT_CPT];
+        unsigned cc[EXT_CPT];
 #pragma unroll
-        for (int e = 0; e < EXT_CPT; ++e) rlo[e] = rhi[e] = 0;
+        for (int e = 0; e < EXT_CPT; ++e) { A[e] = S1a[e] = S1b[e] = S2[e] = 0; cc[e] = 0; }
 #pragma unroll
         for (int i = 0; i < NS; ++i) {
             const u64 k = t[3 + i];
+            const unsigned k0 = lo32(k), k1 = hi32(k);
 #pragma unroll
             for (int e = 0; e < EXT_CPT; ++e) {
-                const u64 mlo = y[e][i] * k, mhi = __umul64hi(y[e][i], k);
-                rlo[e] += mlo;
-                rhi[e] += mhi + (rlo[e] < mlo);
+                const unsigned y0 = lo32(y[e][i]), y1 = hi32(y[e][i]);
+                const u64 p00 = mulwide_u32(y0, k0);
+                asm("add.cc.u64 %0, %0, %2;\n\taddc.u32 %1, %1, 0;" : "+l"(A[e]), "+r"(cc[e]) : "l"(p00));
+                if (i < 4) S1a[e] = madwide_u32(y1, k0, madwide_u32(y0, k1, S1a[e]));
+                else S1b[e] = madwide_u32(y1, k0, madwide_u32(y0, k1, S1b[e]));
+                S2[e] = madwide_u32(y1, k1, S2[e]);
             }
         }
         u64 *oj = o + (size_t)d.dst_limb[j] * N;
 #pragma unroll
         for (int e = 0; e < EXT_CPT; ++e) {
-            u64 r = rhi[e] - __umul64hi(rlo[e] * qinv, q) + q + t[3 + NS + v[e]];   // [0, 3p)
+            u64 rlo = A[e], rhi = (u64)cc[e] + S2[e] + (S1a[e] >> 32);
+            const u64 sa = S1a[e] << 32;
+            rlo += sa; rhi += rlo < sa;
+            if (NS > 4) {
+                const u64 sb = S1b[e] << 32;
+                rlo += sb; rhi += (S1b[e] >> 32) + (rlo < sb);
+            }
+            u64 r = rhi - __umul64hi(rlo * qinv, q) + q + t[3 + NS + v[e]];   // [0, 3p)
             r = csub(r + q - sub, q);                                           // SubScalar
             if (mode == 1) r = csub(csub(r, 2 * q), q);
             if (live[e]) oj[x0 + e * EXT_THREADS] = r;
