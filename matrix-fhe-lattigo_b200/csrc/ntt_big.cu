@@ -28,8 +28,17 @@
 #ifndef B200_CSUB_HI
 #define B200_CSUB_HI 0      // 1: compare high words only in the lazy conditional subtraction
 #endif
-#ifndef B200_CSUB_ALU
-#define B200_CSUB_ALU 0     // 1: plain compare/select/subtract on the ALU pipe instead of the multiply-add form
+// conditional subtraction of 4q inside the lazy butterflies: 1 = compare/select/subtract on the ALU pipe, 0 = as a
+// multiply-add by 2^64-4q on the multiply pipe.  Measured per kernel on B200: the forward (Cooley-Tukey) kernels are
+// 3-4 % faster with the ALU form, the inverse row kernels 1-2 % faster with the multiply-add form.
+#ifndef B200_CSUB_ALU_FWD
+#define B200_CSUB_ALU_FWD 1
+#endif
+#ifndef B200_CSUB_ALU_INV
+#define B200_CSUB_ALU_INV 0        // inverse row kernels
+#endif
+#ifndef B200_CSUB_ALU_INV_COLS
+#define B200_CSUB_ALU_INV_COLS 1   // inverse column kernels (1-1.5 % faster with the ALU form)
 #endif
 #ifndef B200_CANON_EST
 #define B200_CANON_EST 1    // 1: final canonical reduction through a quotient estimate
@@ -93,27 +102,27 @@ struct QC {
     __device__ __forceinline__ explicit QC(const LimbConst &l)
         : q(l.q), twoq(2 * l.q), fourq(4 * l.q), nq(0 - l.q), nfourq(0 - 4 * l.q), csh(l.canon_shift), cmul(l.canon_mul) {}
 };
+template <bool ALU>
 __device__ __forceinline__ u64 csub4(u64 x, const QC &c) {
 #if B200_CSUB_HI
     return csub_fma_hi(x, c.fourq, c.nfourq);
-#elif B200_CSUB_ALU
-    return csub(x, c.fourq);
 #else
-    return csub_fma(x, c.fourq, c.nfourq);
+    return ALU ? csub(x, c.fourq) : csub_fma(x, c.fourq, c.nfourq);
 #endif
 }
 // Harvey butterflies on the approximate Shoup product (shoup4: [0,4q)).  q < 2^61 so 8q fits in 64 bits.
 //   forward (Cooley-Tukey):   in [0,8q) -> out [0,8q)
 //   inverse (Gentleman-Sande): in [0,4q) -> out [0,4q)
 __device__ __forceinline__ void bf_fwd(u64 &U, u64 &V, const tw_t w, const QC &c) {
-    const u64 u = csub4(U, c);
+    const u64 u = csub4<B200_CSUB_ALU_FWD != 0>(U, c);
     const u64 t = shoup4(V, w.x, w.y, c.nq);
     U = u + t;
     V = u - t + c.fourq;
 }
+template <bool ALU>
 __device__ __forceinline__ void bf_inv(u64 &U, u64 &V, const tw_t w, const QC &c) {
     const u64 s = U + V, d = U - V + c.fourq;
-    U = csub4(s, c);
+    U = csub4<ALU>(s, c);
     V = shoup4(d, w.x, w.y, c.nq);
 }
 // [0,8q) -> [0,q) and [0,4q) -> [0,2q)
@@ -141,7 +150,7 @@ __device__ __forceinline__ void fwd_regs(u64 (&x)[1 << LOGM], unsigned P, const 
         }
     }
 }
-template <int LOGM, int JMIN = 0>
+template <int LOGM, int JMIN = 0, bool ALU = (B200_CSUB_ALU_INV != 0)>
 __device__ __forceinline__ void inv_regs(u64 (&x)[1 << LOGM], unsigned P, const tw_t *__restrict__ tw, const QC &c) {
 #pragma unroll
     for (int j = LOGM - 1; j >= JMIN; --j) {
@@ -150,7 +159,7 @@ __device__ __forceinline__ void inv_regs(u64 (&x)[1 << LOGM], unsigned P, const 
         for (int g = 0; g < (1 << j); ++g) {
             const tw_t w = tw[(P << j) + g];
 #pragma unroll
-            for (int o = 0; o < half; ++o) bf_inv(x[g * 2 * half + o], x[g * 2 * half + o + half], w, c);
+            for (int o = 0; o < half; ++o) bf_inv<ALU>(x[g * 2 * half + o], x[g * 2 * half + o + half], w, c);
         }
     }
 }
@@ -472,8 +481,8 @@ k_cols_inv_std16(const u64 *in, u64 *out, BigArgs a) {
     {
         u64 (&lo)[4] = *reinterpret_cast<u64 (*)[4]>(&x[0]);
         u64 (&hi)[4] = *reinterpret_cast<u64 (*)[4]>(&x[4]);
-        inv_regs<2>(lo, 64u + g * 2, tw, qc);
-        inv_regs<2>(hi, 64u + g * 2 + 1, tw, qc);
+        inv_regs<2, 0, (B200_CSUB_ALU_INV_COLS != 0)>(lo, 64u + g * 2, tw, qc);
+        inv_regs<2, 0, (B200_CSUB_ALU_INV_COLS != 0)>(hi, 64u + g * 2 + 1, tw, qc);
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k) sm[pc((g * 8 + k) * CW + c)] = x[k];
@@ -481,14 +490,14 @@ k_cols_inv_std16(const u64 *in, u64 *out, BigArgs a) {
     const int lo2 = g & 3, hi3 = g >> 2;
 #pragma unroll
     for (int k = 0; k < 8; ++k) x[k] = sm[pc((hi3 * 32 + k * 4 + lo2) * CW + c)];
-    inv_regs<3>(x, 8u + hi3, tw, qc);
+    inv_regs<3, 0, (B200_CSUB_ALU_INV_COLS != 0)>(x, 8u + hi3, tw, qc);
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < 8; ++k) sm[pc((hi3 * 32 + k * 4 + lo2) * CW + c)] = x[k];
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < 8; ++k) x[k] = sm[pc((k * 32 + g) * CW + c)];
-    inv_regs<3, 1>(x, 1u, tw, qc);
+    inv_regs<3, 1, (B200_CSUB_ALU_INV_COLS != 0)>(x, 1u, tw, qc);
 #pragma unroll
     for (int o = 0; o < 4; ++o) {   // last layer carries N^-1
         const u64 U = x[o], V = x[o + 4];
@@ -595,15 +604,15 @@ k_cols_inv_m3_15(const u64 *in, u64 *out, BigArgs a) {
         for (int k = 0; k < 8; ++k) x[k] = ldd(in + ibase + (size_t)(g * 8 + k) * 256 + c);
         u64 (&lo)[4] = *reinterpret_cast<u64 (*)[4]>(&x[0]);
         u64 (&hi)[4] = *reinterpret_cast<u64 (*)[4]>(&x[4]);
-        inv_regs<2>(lo, 96u + g * 2, tw, qc);
-        inv_regs<2>(hi, 96u + g * 2 + 1, tw, qc);
+        inv_regs<2, 0, (B200_CSUB_ALU_INV_COLS != 0)>(lo, 96u + g * 2, tw, qc);
+        inv_regs<2, 0, (B200_CSUB_ALU_INV_COLS != 0)>(hi, 96u + g * 2 + 1, tw, qc);
 #pragma unroll
         for (int k = 0; k < 8; ++k) sm[pc((g * 8 + k) * CW + c)] = x[k];
         __syncthreads();
         const int lo2 = g & 3, top = g >> 2;
 #pragma unroll
         for (int k = 0; k < 8; ++k) x[k] = sm[pc((top * 32 + k * 4 + lo2) * CW + c)];
-        inv_regs<3>(x, 12u + top, tw, qc);
+        inv_regs<3, 0, (B200_CSUB_ALU_INV_COLS != 0)>(x, 12u + top, tw, qc);
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < 8; ++k) sm[pc((top * 32 + k * 4 + lo2) * CW + c)] = x[k];
@@ -616,7 +625,7 @@ k_cols_inv_m3_15(const u64 *in, u64 *out, BigArgs a) {
         for (int hd = 0; hd < 6; ++hd) {
 #pragma unroll
             for (int b = 0; b < 2; ++b) x[hd][b] = sm[pc((hd * 64 + b * 32 + g) * CW + c)];
-            bf_inv(x[hd][0], x[hd][1], tw[6 + hd], qc);
+            bf_inv<(B200_CSUB_ALU_INV_COLS != 0)>(x[hd][0], x[hd][1], tw[6 + hd], qc);
         }
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
@@ -673,9 +682,9 @@ __device__ __forceinline__ void col_group(const u64 *gin, size_t ibase, u64 *gou
         if (!INV) {
             fwd_regs<S>(x, P, tw, qc);
         } else if (!FOLD_NINV) {
-            inv_regs<S>(x, P, tw, qc);
+            inv_regs<S, 0, (B200_CSUB_ALU_INV_COLS != 0)>(x, P, tw, qc);
         } else {   // top group of the STANDARD inverse: the last layer carries N^-1
-            inv_regs<S, 1>(x, P, tw, qc);
+            inv_regs<S, 1, (B200_CSUB_ALU_INV_COLS != 0)>(x, P, tw, qc);
 #pragma unroll
             for (int o = 0; o < M / 2; ++o) {
                 const u64 U = x[o], V = x[o + M / 2];
@@ -811,7 +820,7 @@ k_cols_m3_g(const u64 *in, u64 *out, BigArgs a) {
             for (int hd = 0; hd < 6; ++hd) {
 #pragma unroll
                 for (int k = 0; k < MA; ++k) x[hd][k] = sm[pc((hd * U + k * ULO + ulo) * GCW + c)];
-                if (S1 > 0) inv_regs<S1>(x[hd], (unsigned)(6 + hd), tw, qc);
+                if (S1 > 0) inv_regs<S1, 0, (B200_CSUB_ALU_INV_COLS != 0)>(x[hd], (unsigned)(6 + hd), tw, qc);
             }
 #pragma unroll
             for (int k = 0; k < MA; ++k) {
