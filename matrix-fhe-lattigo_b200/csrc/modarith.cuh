@@ -124,9 +124,11 @@ __device__ __forceinline__ u64 csub_fma_hi(u64 x, u64 m, u64 nm) {
 }
 // x < 16q  ->  [0, q) through a 32-bit quotient estimate (1 shift + 1 mul.hi + 2 multiply-adds) and one
 // conditional subtraction, instead of a chain of three or four conditional subtractions.
+// FINAL_ALU: the last conditional subtraction as compare/select/subtract (ALU pipe) instead of a multiply-add.
+template <bool FINAL_ALU = false>
 __device__ __forceinline__ u64 canon_est(u64 x, u64 q, u64 nq, unsigned sh, unsigned mul) {
     const unsigned k = __umulhi((unsigned)(x >> sh), mul);
     const u64 r = madwide_u32(k, lo32(nq), x);
     const u64 y = ((u64)madlo_u32(k, hi32(nq), hi32(r)) << 32) | lo32(r);
-    return csub_fma(y, q, nq);
+    return FINAL_ALU ? csub(y, q) : csub_fma(y, q, nq);
 }

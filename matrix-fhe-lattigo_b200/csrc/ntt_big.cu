@@ -57,11 +57,18 @@
 #ifndef B200_MINB_ROWS_M3
 #define B200_MINB_ROWS_M3 4
 #endif
-#ifndef B200_MINB_COLS_M3
-#define B200_MINB_COLS_M3 3   // CTAs per SM at 8 columns per CTA; scaled by 8/CW for narrower tiles
+// CTAs per SM at 8 columns per CTA (scaled by 8/CW for narrower tiles), i.e. the register cap: forward 40, inverse 56
+#ifndef B200_MINB_COLS_M3_FWD
+#define B200_MINB_COLS_M3_FWD 4
 #endif
-#ifndef B200_MINB_ROWS_STD
-#define B200_MINB_ROWS_STD 12
+#ifndef B200_MINB_COLS_M3_INV
+#define B200_MINB_COLS_M3_INV 3
+#endif
+#ifndef B200_MINB_ROWS_STD_FWD
+#define B200_MINB_ROWS_STD_FWD 8    // 4-warp CTAs per SM: forward 64 registers, inverse 40
+#endif
+#ifndef B200_MINB_ROWS_STD_INV
+#define B200_MINB_ROWS_STD_INV 12
 #endif
 #ifndef B200_MINB_ROWS_MUL
 #define B200_MINB_ROWS_MUL 6
@@ -126,9 +133,10 @@ __device__ __forceinline__ void bf_inv(u64 &U, u64 &V, const tw_t w, const QC &c
     V = shoup4(d, w.x, w.y, c.nq);
 }
 // [0,8q) -> [0,q) and [0,4q) -> [0,2q)
+template <bool FINAL_ALU = false>
 __device__ __forceinline__ u64 canon8(u64 x, const QC &c) {
 #if B200_CANON_EST
-    return canon_est(x, c.q, c.nq, c.csh, c.cmul);
+    return canon_est<FINAL_ALU>(x, c.q, c.nq, c.csh, c.cmul);
 #else
     return csub(csub(csub(csub(x, c.fourq), c.twoq), c.q), c.q);
 #endif
@@ -299,7 +307,7 @@ __device__ __forceinline__ void row_inv_core(u64 (&x)[8], u64 *buf, int lane, un
 }
 
 template <bool MATRIX, int VT>   // warps per CTA: MATRIX 6*VT, STANDARD VT
-__global__ void __launch_bounds__((MATRIX ? 6 : 1) * VT * 32, MATRIX ? B200_MINB_ROWS_M3 : B200_MINB_ROWS_STD)
+__global__ void __launch_bounds__((MATRIX ? 6 : 1) * VT * 32, MATRIX ? B200_MINB_ROWS_M3 : B200_MINB_ROWS_STD_FWD)
 k_rows_fwd(const u64 *in, u64 *out, BigArgs a) {
     constexpr int RUN = 6 * VT;
     extern __shared__ __align__(16) u64 sm[];
@@ -319,7 +327,7 @@ k_rows_fwd(const u64 *in, u64 *out, BigArgs a) {
     for (int k = 0; k < 8; ++k) x[k] = ldd(src + k * 32 + lane);
     row_fwd_core(x, buf, lane, P1, tw, qc);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) x[k] = (a.flags & B200_LAZY) ? csub(x[k], qc.fourq) : canon8(x[k], qc);   // lazy: [0,4q) <= 6q-2
+    for (int k = 0; k < 8; ++k) x[k] = (a.flags & B200_LAZY) ? csub(x[k], qc.fourq) : canon8<!MATRIX>(x[k], qc);   // lazy: [0,4q) <= 6q-2
     if (!MATRIX || (a.flags & B200_TREE_ORDER)) {
         u64 *dst = out + ur.out + (size_t)r * 256 + lane * 8;
         stg256(dst, x[0], x[1], x[2], x[3]);
@@ -342,7 +350,7 @@ k_rows_fwd(const u64 *in, u64 *out, BigArgs a) {
 }
 
 template <bool MATRIX, int VT>
-__global__ void __launch_bounds__((MATRIX ? 6 : 1) * VT * 32, MATRIX ? B200_MINB_ROWS_M3 : B200_MINB_ROWS_STD)
+__global__ void __launch_bounds__((MATRIX ? 6 : 1) * VT * 32, MATRIX ? B200_MINB_ROWS_M3 : B200_MINB_ROWS_STD_INV)
 k_rows_inv(const u64 *in, u64 *out, BigArgs a) {
     constexpr int RUN = 6 * VT;
     extern __shared__ __align__(16) u64 sm[];
@@ -515,7 +523,7 @@ k_cols_inv_std16(const u64 *in, u64 *out, BigArgs a) {
 //   G2:  8 words  (u bits 4..2): radix-2 layers 1..3                          -- CW*48 threads
 //   G3:  8 words  (u bits 2..0, two 4-groups): radix-2 layers 4, 5            -- CW*48 threads
 template <int CW>
-__global__ void __launch_bounds__(CW * 48, B200_MINB_COLS_M3 * 8 / CW)
+__global__ void __launch_bounds__(CW * 48, B200_MINB_COLS_M3_FWD * 8 / CW)
 k_cols_fwd_m3_15(const u64 *in, u64 *out, BigArgs a) {
     extern __shared__ __align__(16) u64 sm[];
     const UnitRef ur = unit_ref(a);
@@ -586,7 +594,7 @@ k_cols_fwd_m3_15(const u64 *in, u64 *out, BigArgs a) {
 }
 
 template <int CW, bool GATHER = false>
-__global__ void __launch_bounds__(CW * 48, B200_MINB_COLS_M3 * 8 / CW)
+__global__ void __launch_bounds__(CW * 48, B200_MINB_COLS_M3_INV * 8 / CW)
 k_cols_inv_m3_15(const u64 *in, u64 *out, BigArgs a) {
     extern __shared__ __align__(16) u64 sm[];
     const UnitRef ur = unit_ref(a);
