@@ -54,8 +54,14 @@
 #ifndef B200_CW_STD
 #define B200_CW_STD 8
 #endif
+#ifndef B200_VT_STD
+#define B200_VT_STD 4         // rows (warps) per power-of-two row CTA; R >= 4 for every covered shape
+#endif
+#ifndef B200_VT_M3
+#define B200_VT_M3 2          // v-tiles (6 rows each) per 3N row CTA
+#endif
 #ifndef B200_MINB_ROWS_M3
-#define B200_MINB_ROWS_M3 4
+#define B200_MINB_ROWS_M3 4   // CTAs per SM at B200_VT_M3 = 2 (scaled by 2/VT)
 #endif
 // CTAs per SM at 8 columns per CTA (scaled by 8/CW for narrower tiles), i.e. the register cap: forward 40, inverse 56
 #ifndef B200_MINB_COLS_M3_FWD
@@ -307,7 +313,7 @@ __device__ __forceinline__ void row_inv_core(u64 (&x)[8], u64 *buf, int lane, un
 }
 
 template <bool MATRIX, int VT>   // warps per CTA: MATRIX 6*VT, STANDARD VT
-__global__ void __launch_bounds__((MATRIX ? 6 : 1) * VT * 32, MATRIX ? B200_MINB_ROWS_M3 : B200_MINB_ROWS_STD_FWD)
+__global__ void __launch_bounds__((MATRIX ? 6 : 1) * VT * 32, MATRIX ? B200_MINB_ROWS_M3 * 2 / VT : B200_MINB_ROWS_STD_FWD * 4 / VT)
 k_rows_fwd(const u64 *in, u64 *out, BigArgs a) {
     constexpr int RUN = 6 * VT;
     extern __shared__ __align__(16) u64 sm[];
@@ -350,7 +356,7 @@ k_rows_fwd(const u64 *in, u64 *out, BigArgs a) {
 }
 
 template <bool MATRIX, int VT>
-__global__ void __launch_bounds__((MATRIX ? 6 : 1) * VT * 32, MATRIX ? B200_MINB_ROWS_M3 : B200_MINB_ROWS_STD_INV)
+__global__ void __launch_bounds__((MATRIX ? 6 : 1) * VT * 32, MATRIX ? B200_MINB_ROWS_M3 * 2 / VT : B200_MINB_ROWS_STD_INV * 4 / VT)
 k_rows_inv(const u64 *in, u64 *out, BigArgs a) {
     constexpr int RUN = 6 * VT;
     extern __shared__ __align__(16) u64 sm[];
@@ -928,7 +934,7 @@ int big_tables_create(b200_ctx *ctx) {
     const bool generic = env_int("B200_GENERIC_COLS", 0) != 0;
     if (!matrix) plan->covered = ctx->logN >= 10 && ctx->logN <= 17 && pick_col_kernels(plan, false, ctx->logN - 8, generic);
     else plan->covered = ctx->b == 1 && ctx->a >= 10 && ctx->a <= 16 && pick_col_kernels(plan, true, ctx->a - 9, generic);
-    plan->vt = 2;   // 16-column tiles and 4-v row tiles were measured slower on B200 (fewer resident CTAs)
+    plan->vt = B200_VT_M3;   // 16-column tiles and 4-v row tiles were measured slower on B200 (fewer resident CTAs)
     int l2 = 0;
     cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, ctx->device);
     const size_t budget = (size_t)env_int("B200_CHUNK_MB", 512) << 20;
@@ -955,11 +961,11 @@ int launch_ntt_big(b200_ctx *ctx, const u64 *in, u64 *out, Span sp, bool inverse
     kern_t rk;
     int row_warps;
     if (matrix) {
-        rk = inverse ? (kern_t)k_rows_inv<true, 2> : (kern_t)k_rows_fwd<true, 2>;
+        rk = inverse ? (kern_t)k_rows_inv<true, B200_VT_M3> : (kern_t)k_rows_fwd<true, B200_VT_M3>;
         row_warps = 6 * vt;
     } else {
-        rk = inverse ? (kern_t)k_rows_inv<false, 4> : (kern_t)k_rows_fwd<false, 4>;
-        row_warps = 4;
+        rk = inverse ? (kern_t)k_rows_inv<false, B200_VT_STD> : (kern_t)k_rows_fwd<false, B200_VT_STD>;
+        row_warps = B200_VT_STD;
     }
     const int rows_total = R * cw;
     const size_t col_smem = (size_t)(rows_total + ((rows_total >> 6) << 3) + 8) * sizeof(u64);
