@@ -100,11 +100,15 @@ struct UnitRef { size_t in, out; int limb; };
 // Units are numbered LIMB-MAJOR (unit = limb*batch + poly) and sit on blockIdx.x, the tile on blockIdx.y:
 // CTAs that are scheduled together work on the same tile of the same prime for consecutive polynomials,
 // so they share one small set of twiddles (L1/L2 hits) instead of spreading over all L tables.
+// The column pass swaps the roles (COLS: tile on blockIdx.x, unit on blockIdx.y): every column tile of a unit uses the
+// same twiddles, and neighbouring tiles share DRAM bursts when they run together (-8 % on the forward 3N kernel).
+template <bool COLS = false>
 __device__ __forceinline__ UnitRef unit_ref(const BigArgs &a) {
-    const int unit = a.unit0 + blockIdx.x;
+    const int u = COLS ? blockIdx.y : blockIdx.x;
+    const int unit = a.unit0 + u;
     const int l = unit / a.sp.batch, b = unit - l * a.sp.batch;
     const size_t layout = ((size_t)b * a.sp.Lbuf + l) * (size_t)a.N;
-    const size_t dense = (size_t)blockIdx.x * (size_t)a.N;
+    const size_t dense = (size_t)u * (size_t)a.N;
     return {a.in_dense ? dense : layout, a.out_dense ? dense : layout, a.sp.limb0 + l};
 }
 
@@ -443,9 +447,9 @@ template <int CW>
 __global__ void __launch_bounds__(CW * 32, B200_MINB_COLS_STD * 8 / CW)
 k_cols_fwd_std16(const u64 *in, u64 *out, BigArgs a) {
     extern __shared__ __align__(16) u64 sm[];
-    const UnitRef ur = unit_ref(a);
+    const UnitRef ur = unit_ref<true>(a);
     const int limb = ur.limb;
-    const size_t ibase = ur.in + (size_t)blockIdx.y * CW, obase = ur.out + (size_t)blockIdx.y * CW;
+    const size_t ibase = ur.in + (size_t)blockIdx.x * CW, obase = ur.out + (size_t)blockIdx.x * CW;
     const QC qc(a.consts[limb]);
     const tw_t *__restrict__ tw = a.fwd + (size_t)limb * a.N;
     const int t = threadIdx.x, c = t % CW, g = t / CW;   // g in [0,32)
@@ -480,9 +484,9 @@ template <int CW, bool GATHER = false>
 __global__ void __launch_bounds__(CW * 32, B200_MINB_COLS_STD * 8 / CW)
 k_cols_inv_std16(const u64 *in, u64 *out, BigArgs a) {
     extern __shared__ __align__(16) u64 sm[];
-    const UnitRef ur = unit_ref(a);
+    const UnitRef ur = unit_ref<true>(a);
     const int limb = ur.limb;
-    const size_t ibase = ur.in + (size_t)blockIdx.y * CW, obase = ur.out + (size_t)blockIdx.y * CW;
+    const size_t ibase = ur.in + (size_t)blockIdx.x * CW, obase = ur.out + (size_t)blockIdx.x * CW;
     const QC qc(a.consts[limb]);
     const u64 q = qc.q;
     const tw_t *__restrict__ tw = a.inv + (size_t)limb * a.N;
@@ -532,9 +536,9 @@ template <int CW>
 __global__ void __launch_bounds__(CW * 48, B200_MINB_COLS_M3_FWD * 8 / CW)
 k_cols_fwd_m3_15(const u64 *in, u64 *out, BigArgs a) {
     extern __shared__ __align__(16) u64 sm[];
-    const UnitRef ur = unit_ref(a);
+    const UnitRef ur = unit_ref<true>(a);
     const int limb = ur.limb;
-    const size_t ibase = ur.in + (size_t)blockIdx.y * CW, obase = ur.out + (size_t)blockIdx.y * CW;
+    const size_t ibase = ur.in + (size_t)blockIdx.x * CW, obase = ur.out + (size_t)blockIdx.x * CW;
     const QC qc(a.consts[limb]);
     const u64 q = qc.q, twoq = qc.twoq, fourq = qc.fourq;
     const tw_t *__restrict__ tw = a.fwd + (size_t)limb * a.N;
@@ -603,9 +607,9 @@ template <int CW, bool GATHER = false>
 __global__ void __launch_bounds__(CW * 48, B200_MINB_COLS_M3_INV * 8 / CW)
 k_cols_inv_m3_15(const u64 *in, u64 *out, BigArgs a) {
     extern __shared__ __align__(16) u64 sm[];
-    const UnitRef ur = unit_ref(a);
+    const UnitRef ur = unit_ref<true>(a);
     const int limb = ur.limb;
-    const size_t ibase = ur.in + (size_t)blockIdx.y * CW, obase = ur.out + (size_t)blockIdx.y * CW;
+    const size_t ibase = ur.in + (size_t)blockIdx.x * CW, obase = ur.out + (size_t)blockIdx.x * CW;
     const QC qc(a.consts[limb]);
     const u64 q = qc.q, twoq = qc.twoq, fourq = qc.fourq;
     const tw_t *__restrict__ tw = a.inv + (size_t)limb * a.N;
@@ -726,9 +730,9 @@ __global__ void __launch_bounds__(std_col_threads(LOGR), minb_for(std_col_thread
 k_cols_std_g(const u64 *in, u64 *out, BigArgs a) {
     static_assert(S1 + S2 + S3 == LOGR && S1 >= 1 && S2 >= 1, "group sizes");
     extern __shared__ __align__(16) u64 sm[];
-    const UnitRef ur = unit_ref(a);
+    const UnitRef ur = unit_ref<true>(a);
     const int limb = ur.limb;
-    const size_t ibase = ur.in + (size_t)blockIdx.y * GCW, obase = ur.out + (size_t)blockIdx.y * GCW;
+    const size_t ibase = ur.in + (size_t)blockIdx.x * GCW, obase = ur.out + (size_t)blockIdx.x * GCW;
     const QC qc(a.consts[limb]);
     const tw_t *__restrict__ tw = (INV ? a.inv : a.fwd) + (size_t)limb * a.N;
     const tw_t ninv = a.misc[limb * MISC_COUNT + MISC_NINV], ninv_w1 = a.misc[limb * MISC_COUNT + MISC_NINV_W1];
@@ -762,9 +766,9 @@ __global__ void __launch_bounds__(m3_col_threads(LOGU), minb_for(m3_col_threads(
 k_cols_m3_g(const u64 *in, u64 *out, BigArgs a) {
     static_assert(S1 + S2 + S3 == LOGU && S2 >= 1, "group sizes");
     extern __shared__ __align__(16) u64 sm[];
-    const UnitRef ur = unit_ref(a);
+    const UnitRef ur = unit_ref<true>(a);
     const int limb = ur.limb;
-    const size_t ibase = ur.in + (size_t)blockIdx.y * GCW, obase = ur.out + (size_t)blockIdx.y * GCW;
+    const size_t ibase = ur.in + (size_t)blockIdx.x * GCW, obase = ur.out + (size_t)blockIdx.x * GCW;
     const QC qc(a.consts[limb]);
     const u64 q = qc.q, twoq = qc.twoq, fourq = qc.fourq;
     const tw_t *__restrict__ tw = (INV ? a.inv : a.fwd) + (size_t)limb * a.N;
@@ -940,6 +944,7 @@ int big_tables_create(b200_ctx *ctx) {
     const size_t budget = (size_t)env_int("B200_CHUNK_MB", 512) << 20;
     plan->chunk_units = budget / ((size_t)ctx->N * sizeof(u64));
     if (plan->chunk_units < 1) plan->chunk_units = 1;
+    if (plan->chunk_units > 65535) plan->chunk_units = 65535;   // units sit on gridDim.y in the column pass
     return 0;
 }
 void big_tables_destroy(b200_ctx *ctx) {
@@ -990,16 +995,17 @@ int launch_ntt_big(b200_ctx *ctx, const u64 *in, u64 *out, Span sp, bool inverse
         first.out_dense = dense;
         second.in_dense = dense;
         if (gather) second.peers = *peers;
+        const dim3 cgrid(col_tiles, nu);   // tiles run together, units on y (chunk_units <= 65535)
         if (!inverse) {
             { LaunchScope ls(ctx, matrix ? "cols_fwd_m3" : "cols_fwd_std", nu);
-              ck<<<dim3(nu, col_tiles), col_threads, col_smem, b200_cur_stream(ctx)>>>(in, tmp, first); }
+              ck<<<cgrid, col_threads, col_smem, b200_cur_stream(ctx)>>>(in, tmp, first); }
             { LaunchScope ls(ctx, matrix ? "rows_fwd_m3" : "rows_fwd_std", nu);
               rk<<<dim3(nu, row_tiles), row_warps * 32, row_smem, b200_cur_stream(ctx)>>>(tmp, out, second); }
         } else {
             { LaunchScope ls(ctx, matrix ? "rows_inv_m3" : "rows_inv_std", nu);
               rk<<<dim3(nu, row_tiles), row_warps * 32, row_smem, b200_cur_stream(ctx)>>>(in, tmp, first); }
             { LaunchScope ls(ctx, matrix ? "cols_inv_m3" : "cols_inv_std", nu);
-              ck<<<dim3(nu, col_tiles), col_threads, col_smem, b200_cur_stream(ctx)>>>(tmp, out, second); }
+              ck<<<cgrid, col_threads, col_smem, b200_cur_stream(ctx)>>>(tmp, out, second); }
         }
     }
     CUDA_TRY(cudaGetLastError());
@@ -1023,7 +1029,7 @@ int launch_polymul_big(b200_ctx *ctx, const u64 *pa, const u64 *pb, u64 *pc, Spa
     if (int rc = set_smem(ci, smem_i)) return rc;
     const int units = sp.batch * sp.nl;
     const size_t budget = (size_t)env_int("B200_MUL_CHUNK_MB", 512) << 20;   // per intermediate
-    const int chunk = (int)std::max<size_t>(1, std::min<size_t>(budget / ((size_t)N * sizeof(u64)), (size_t)units));
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(budget / ((size_t)N * sizeof(u64)), 65535), (size_t)units));
     if (int rc = b200_ensure_scratch(ctx, (size_t)2 * chunk * N)) return rc;
     u64 *ta = ctx->d_scratch, *tb = ctx->d_scratch + (size_t)chunk * N;
     const int tiles_f = 256 / plan->cw_fwd, tiles_i = 256 / plan->cw_inv, row_tiles = R / 4;
@@ -1035,14 +1041,15 @@ int launch_polymul_big(b200_ctx *ctx, const u64 *pa, const u64 *pb, u64 *pc, Spa
         to_dense.out_dense = 1;
         dense.in_dense = dense.out_dense = 1;
         from_dense.in_dense = 1;
+        const dim3 gf(tiles_f, nu), gi(tiles_i, nu);
         { LaunchScope ls(ctx, matrix ? "cols_fwd_m3" : "cols_fwd_std", nu);
-          cf<<<dim3(nu, tiles_f), plan->col_threads_fwd, smem_f, st>>>(pa, ta, to_dense); }
+          cf<<<gf, plan->col_threads_fwd, smem_f, st>>>(pa, ta, to_dense); }
         { LaunchScope ls(ctx, matrix ? "cols_fwd_m3" : "cols_fwd_std", nu);
-          cf<<<dim3(nu, tiles_f), plan->col_threads_fwd, smem_f, st>>>(pb, tb, to_dense); }
+          cf<<<gf, plan->col_threads_fwd, smem_f, st>>>(pb, tb, to_dense); }
         { LaunchScope ls(ctx, "rows_mul", nu);
           k_rows_mul<<<dim3(nu, row_tiles), 128, row_smem, st>>>(ta, tb, dense); }
         { LaunchScope ls(ctx, matrix ? "cols_inv_m3" : "cols_inv_std", nu);
-          ci<<<dim3(nu, tiles_i), plan->col_threads_inv, smem_i, st>>>(ta, pc, from_dense); }
+          ci<<<gi, plan->col_threads_inv, smem_i, st>>>(ta, pc, from_dense); }
     }
     CUDA_TRY(cudaGetLastError());
     return 0;

@@ -19,6 +19,7 @@ WANT = [
     ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "pipe_fma_inst%"),
     ("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "pipe_fma_cycles%"),
     ("sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active", "pipe_fmaheavy_cycles%"),
+    ("sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed", "pipe_fmaheavy_cycles%(elapsed)"),
     ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "pipe_lsu%"),
     ("dram__bytes_read.sum", "dram_read"), ("dram__bytes_write.sum", "dram_write"),
     ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram%"),
