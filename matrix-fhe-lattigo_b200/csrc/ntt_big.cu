@@ -43,16 +43,19 @@
 #ifndef B200_CANON_EST
 #define B200_CANON_EST 1    // 1: final canonical reduction through a quotient estimate
 #endif
-// columns per CTA in the hand-tuned column kernels (the generic family uses 8).  Measured on B200: the forward 3N
-// kernel gains 6% from 4-column tiles (192-thread CTAs, shorter barrier waits); the other three do not.
+// columns per CTA in the hand-tuned column kernels (the generic family uses 8).  Measured on B200: all four tuned
+// kernels gain 2-6% from 4-column tiles (192-thread CTAs, shorter barrier waits).
 #ifndef B200_CW_M3_FWD
 #define B200_CW_M3_FWD 4
 #endif
 #ifndef B200_CW_M3_INV
-#define B200_CW_M3_INV 8
+#define B200_CW_M3_INV 4
 #endif
-#ifndef B200_CW_STD
-#define B200_CW_STD 8
+#ifndef B200_CW_STD_FWD
+#define B200_CW_STD_FWD 4
+#endif
+#ifndef B200_CW_STD_INV
+#define B200_CW_STD_INV 4
 #endif
 #ifndef B200_VT_STD
 #define B200_VT_STD 4         // rows (warps) per power-of-two row CTA; R >= 4 for every covered shape
@@ -889,10 +892,10 @@ struct BigPlan {
 bool pick_col_kernels(BigPlan *plan, bool matrix, int log, bool force_generic) {
     if (!matrix) {
         if (log == 8 && !force_generic) {
-            plan->cols_fwd = (kern_t)k_cols_fwd_std16<B200_CW_STD>; plan->cols_inv = (kern_t)k_cols_inv_std16<B200_CW_STD>;
-            plan->cols_inv_gather = (kern_t)k_cols_inv_std16<B200_CW_STD, true>;
-            plan->cw_fwd = plan->cw_inv = B200_CW_STD;
-            plan->col_threads_fwd = plan->col_threads_inv = B200_CW_STD * 32;
+            plan->cols_fwd = (kern_t)k_cols_fwd_std16<B200_CW_STD_FWD>; plan->cols_inv = (kern_t)k_cols_inv_std16<B200_CW_STD_INV>;
+            plan->cols_inv_gather = (kern_t)k_cols_inv_std16<B200_CW_STD_INV, true>;
+            plan->cw_fwd = B200_CW_STD_FWD; plan->cw_inv = B200_CW_STD_INV;
+            plan->col_threads_fwd = B200_CW_STD_FWD * 32; plan->col_threads_inv = B200_CW_STD_INV * 32;
             return true;
         }
         switch (log) {
