@@ -681,7 +681,10 @@ k_cols_inv_m3_15(const u64 *in, u64 *out, BigArgs a) {
 // exchanges), with the group sizes as template parameters.  Row index = hi*2^(b0+S) + k*2^b0 + lo for the
 // group that owns row bits [b0, b0+S); the root node of its sub-transform is (ROOTS << (LOG-b0-S)) + hi.
 // ====================================================================================================
-constexpr int GCW = 8;
+#ifndef B200_GCW_LOG
+#define B200_GCW_LOG 3
+#endif
+constexpr int GCW_LOG = B200_GCW_LOG, GCW = 1 << GCW_LOG;   // columns per CTA of the generic column kernels
 
 template <int S, int ROOTS, int LOG, bool INV, bool FROM_G, bool TO_G, bool FOLD_NINV, bool GATHER = false>
 __device__ __forceinline__ void col_group(const u64 *gin, size_t ibase, u64 *gout, size_t obase, u64 *sm, int b0,
@@ -690,7 +693,7 @@ __device__ __forceinline__ void col_group(const u64 *gin, size_t ibase, u64 *gou
     constexpr int M = 1 << S;
     const int ntiles = (GCW * ROOTS) << (LOG - S);
     for (int t = threadIdx.x; t < ntiles; t += blockDim.x) {
-        const int c = t & (GCW - 1), rest = t >> 3;
+        const int c = t & (GCW - 1), rest = t >> GCW_LOG;
         const int lo = rest & ((1 << b0) - 1), hi = rest >> b0;
         const int row0 = (hi << (b0 + S)) + lo;
         u64 x[M];
@@ -781,7 +784,7 @@ k_cols_m3_g(const u64 *in, u64 *out, BigArgs a) {
     constexpr int MA = 1 << S1, U = 1 << LOGU, ULO = U >> S1;
     if (!INV) {
         for (int t = threadIdx.x; t < GCW * ULO; t += blockDim.x) {
-            const int c = t & (GCW - 1), ulo = t >> 3;
+            const int c = t & (GCW - 1), ulo = t >> GCW_LOG;
             u64 x[6][MA];
 #pragma unroll
             for (int hd = 0; hd < 6; ++hd)
@@ -835,7 +838,7 @@ k_cols_m3_g(const u64 *in, u64 *out, BigArgs a) {
         __syncthreads();
         const tw_t k1 = mc[MISC_K1], k2 = mc[MISC_K2], zeta = mc[MISC_ZETA];
         for (int t = threadIdx.x; t < GCW * ULO; t += blockDim.x) {
-            const int c = t & (GCW - 1), ulo = t >> 3;
+            const int c = t & (GCW - 1), ulo = t >> GCW_LOG;
             u64 x[6][MA];
 #pragma unroll
             for (int hd = 0; hd < 6; ++hd) {
@@ -876,7 +879,7 @@ typedef void (*kern_t)(const u64 *, u64 *, BigArgs);
 
 struct BigPlan {
     bool covered = false;
-    int cw_fwd = 8, cw_inv = 8, vt = 2;
+    int cw_fwd = GCW, cw_inv = GCW, vt = 2;
     kern_t cols_fwd = nullptr, cols_inv = nullptr, cols_inv_gather = nullptr;
     int col_threads_fwd = 0, col_threads_inv = 0;
     size_t chunk_units = 0;   // units per launch group so that a chunk's intermediate stays in L2
