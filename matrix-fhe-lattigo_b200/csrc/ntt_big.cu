@@ -51,6 +51,10 @@
 #ifndef B200_CW_M3_INV
 #define B200_CW_M3_INV 4
 #endif
+// the GATHER instantiations also store to peer GPUs: wider tiles make longer contiguous NVLink writes
+#ifndef B200_CW_GATHER
+#define B200_CW_GATHER 16
+#endif
 #ifndef B200_CW_STD_FWD
 #define B200_CW_STD_FWD 4
 #endif
@@ -879,26 +883,26 @@ typedef void (*kern_t)(const u64 *, u64 *, BigArgs);
 
 struct BigPlan {
     bool covered = false;
-    int cw_fwd = GCW, cw_inv = GCW, vt = 2;
+    int cw_fwd = GCW, cw_inv = GCW, cw_gather = GCW, vt = 2;
     kern_t cols_fwd = nullptr, cols_inv = nullptr, cols_inv_gather = nullptr;
-    int col_threads_fwd = 0, col_threads_inv = 0;
+    int col_threads_fwd = 0, col_threads_inv = 0, col_threads_gather = 0;
     size_t chunk_units = 0;   // units per launch group so that a chunk's intermediate stays in L2
 };
 
 #define STD_G(L, A, B, C) case L: plan->cols_fwd = (kern_t)k_cols_std_g<L, A, B, C, false>; plan->cols_inv = (kern_t)k_cols_std_g<L, A, B, C, true>; \
                                   plan->cols_inv_gather = (kern_t)k_cols_std_g<L, A, B, C, true, true>; \
-                                  plan->col_threads_fwd = plan->col_threads_inv = std_col_threads(L); break;
+                                  plan->col_threads_fwd = plan->col_threads_inv = plan->col_threads_gather = std_col_threads(L); break;
 #define M3_G(L, A, B, C) case L: plan->cols_fwd = (kern_t)k_cols_m3_g<L, A, B, C, false>; plan->cols_inv = (kern_t)k_cols_m3_g<L, A, B, C, true>; \
                                  plan->cols_inv_gather = (kern_t)k_cols_m3_g<L, A, B, C, true, true>; \
-                                 plan->col_threads_fwd = plan->col_threads_inv = m3_col_threads(L); break;
+                                 plan->col_threads_fwd = plan->col_threads_inv = plan->col_threads_gather = m3_col_threads(L); break;
 // column-pass kernels for a ring shape: the hand-tuned ones for the two headline shapes, the generic family otherwise
 bool pick_col_kernels(BigPlan *plan, bool matrix, int log, bool force_generic) {
     if (!matrix) {
         if (log == 8 && !force_generic) {
             plan->cols_fwd = (kern_t)k_cols_fwd_std16<B200_CW_STD_FWD>; plan->cols_inv = (kern_t)k_cols_inv_std16<B200_CW_STD_INV>;
-            plan->cols_inv_gather = (kern_t)k_cols_inv_std16<B200_CW_STD_INV, true>;
-            plan->cw_fwd = B200_CW_STD_FWD; plan->cw_inv = B200_CW_STD_INV;
-            plan->col_threads_fwd = B200_CW_STD_FWD * 32; plan->col_threads_inv = B200_CW_STD_INV * 32;
+            plan->cols_inv_gather = (kern_t)k_cols_inv_std16<B200_CW_GATHER, true>;
+            plan->cw_fwd = B200_CW_STD_FWD; plan->cw_inv = B200_CW_STD_INV; plan->cw_gather = B200_CW_GATHER;
+            plan->col_threads_fwd = B200_CW_STD_FWD * 32; plan->col_threads_inv = B200_CW_STD_INV * 32; plan->col_threads_gather = B200_CW_GATHER * 32;
             return true;
         }
         switch (log) {
@@ -908,9 +912,9 @@ bool pick_col_kernels(BigPlan *plan, bool matrix, int log, bool force_generic) {
     } else {
         if (log == 6 && !force_generic) {
             plan->cols_fwd = (kern_t)k_cols_fwd_m3_15<B200_CW_M3_FWD>; plan->cols_inv = (kern_t)k_cols_inv_m3_15<B200_CW_M3_INV>;
-            plan->cols_inv_gather = (kern_t)k_cols_inv_m3_15<B200_CW_M3_INV, true>;
-            plan->cw_fwd = B200_CW_M3_FWD; plan->cw_inv = B200_CW_M3_INV;
-            plan->col_threads_fwd = B200_CW_M3_FWD * 48; plan->col_threads_inv = B200_CW_M3_INV * 48;
+            plan->cols_inv_gather = (kern_t)k_cols_inv_m3_15<B200_CW_GATHER, true>;
+            plan->cw_fwd = B200_CW_M3_FWD; plan->cw_inv = B200_CW_M3_INV; plan->cw_gather = B200_CW_GATHER;
+            plan->col_threads_fwd = B200_CW_M3_FWD * 48; plan->col_threads_inv = B200_CW_M3_INV * 48; plan->col_threads_gather = B200_CW_GATHER * 48;
             return true;
         }
         switch (log) {
@@ -965,10 +969,10 @@ int launch_ntt_big(b200_ctx *ctx, const u64 *in, u64 *out, Span sp, bool inverse
     if (gather && !inverse) return 1;   // only the inverse transform has a fused all-gather
     const bool matrix = ctx->ring_type == B200_RING_MATRIX;
     const bool permute = matrix && !(flags & B200_TREE_ORDER);
-    const int N = ctx->N, R = N / 256, cw = inverse ? plan->cw_inv : plan->cw_fwd, vt = plan->vt;
+    const int N = ctx->N, R = N / 256, cw = inverse ? (gather ? plan->cw_gather : plan->cw_inv) : plan->cw_fwd, vt = plan->vt;
     BigArgs a{ctx->d_consts, ctx->d_fwd, ctx->d_inv, ctx->d_misc, N, R, matrix ? ctx->a - 9 : 0, sp, 0, flags, 0, 0};
     const kern_t ck = inverse ? (gather ? plan->cols_inv_gather : plan->cols_inv) : plan->cols_fwd;
-    const int col_threads = inverse ? plan->col_threads_inv : plan->col_threads_fwd;
+    const int col_threads = inverse ? (gather ? plan->col_threads_gather : plan->col_threads_inv) : plan->col_threads_fwd;
     kern_t rk;
     int row_warps;
     if (matrix) {

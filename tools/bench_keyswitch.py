@@ -24,6 +24,7 @@ ap.add_argument("--lq", type=int, default=24)
 ap.add_argument("--lp", type=int, default=6)
 ap.add_argument("--a", type=int, default=15)
 ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--profile", action="store_true", help="per-kernel CUDA-event times of one call on every rank")
 ap.add_argument("--fused", action="store_true", help="exchanges fused into the inverse transforms (peer stores over NVLink)")
 args = ap.parse_args()
 rank, local, world = sharding.init_process_group()
@@ -80,6 +81,13 @@ if rank == 0:
     print(json.dumps({"workload": "gadget product N=%d LQ=%d LP=%d beta=%d batch=%d" % (N, LQ, LP, beta, B), "n_gpus": world, "fused_exchanges": bool(args.fused),
                       "ms": ms, "key_switches_per_s": B / (ms * 1e-3), "limb_transforms_per_s": B * 180 / (ms * 1e-3) if (LQ, LP) == (24, 6) else None,
                       "allgather_bytes_per_step": B * (LQ + 2 * LP) * N * 8, "checksum_rank0": chk}))
+if args.profile:
+    prof = ring.Profile(run)
+    barrier()
+    for r in range(world):
+        if r == rank:
+            sys.stderr.write("rank %d: %s\n" % (rank, {k: round(v["ms"], 3) for k, v in prof.items()}))
+        barrier()
 if fused is not None:
     fused.close()
 if world > 1:
