@@ -250,6 +250,7 @@ extern "C" int b200_ctx_create(int ring_type, int N, int L, const uint64_t *modu
     if (e == cudaSuccess) e = up((void **)&ctx->d_fwd, fwd.data(), sizeof(tw_t) * fwd.size());
     if (e == cudaSuccess) e = up((void **)&ctx->d_inv, inv.data(), sizeof(tw_t) * inv.size());
     if (e == cudaSuccess) e = up((void **)&ctx->d_misc, misc.data(), sizeof(tw_t) * misc.size());
+    if (e == cudaSuccess && !ctx->rescale.empty()) e = up((void **)&ctx->d_rescale, ctx->rescale.data(), sizeof(u64) * ctx->rescale.size());
     if (e == cudaSuccess && ring_type == B200_RING_MATRIX) {
         // reference slot order: slot k <-> omega^E[k], E ascending totatives of 3N (ntt_3n.go:46-53,235-243)
         std::vector<int> pos(3 * (size_t)N, -1), go2fast(N);
@@ -271,7 +272,7 @@ extern "C" void b200_ctx_destroy(b200_ctx *ctx) {
     cudaSetDevice(ctx->device);
     big_tables_destroy(ctx);
     cudaFree(ctx->d_consts); cudaFree(ctx->d_fwd); cudaFree(ctx->d_inv); cudaFree(ctx->d_misc);
-    cudaFree(ctx->d_go2fast); cudaFree(ctx->d_scratch); cudaFree(ctx->d_ws);
+    cudaFree(ctx->d_go2fast); cudaFree(ctx->d_scratch); cudaFree(ctx->d_ws); cudaFree(ctx->d_rescale);
     if (ctx->pipe.ready) {
         for (int i = 0; i < b200_ctx::HostPipe::NB; ++i) {
             cudaFree(ctx->pipe.buf[i]);
@@ -678,12 +679,8 @@ extern "C" int b200_div_by_last_modulus_ntt(b200_ctx *ctx, const b200_poly *p0, 
     if (rc) return rc;
     if ((rc = launch_rescale_spread(ctx, ws, batch, level, round != 0))) return rc;      // :139-142
     if ((rc = ntt(ws, ws, Span{batch, level, ctx->L, 0}, false))) return rc;             // :143
-    u64 *d_rc = nullptr;
-    CUDA_TRY(cudaMallocAsync(&d_rc, sizeof(u64) * level, b200_cur_stream(ctx)));
-    CUDA_TRY(cudaMemcpyAsync(d_rc, &ctx->rescale[(size_t)(level - 1) * ctx->L], sizeof(u64) * level, cudaMemcpyHostToDevice, b200_cur_stream(ctx)));
-    rc = launch_vec_op(ctx, B200_OP_SUB_MULSCALAR_MONT_2Q, ws, p0->d, p1->d, Span{batch, level, ctx->L, 0}, d_rc);   // :144
-    cudaFreeAsync(d_rc, b200_cur_stream(ctx));
-    return rc;
+    return launch_vec_op(ctx, B200_OP_SUB_MULSCALAR_MONT_2Q, ws, p0->d, p1->d, Span{batch, level, ctx->L, 0},
+                         ctx->d_rescale + (size_t)(level - 1) * ctx->L);                         // :144
 }
 
 extern "C" int b200_tensor(b200_ctx *ctx, const b200_poly *a0, const b200_poly *a1, const b200_poly *b0, const b200_poly *b1,

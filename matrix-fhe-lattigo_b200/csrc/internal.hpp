@@ -43,6 +43,7 @@ struct b200_ctx {
     u64 *d_ws = nullptr;             // second workspace for composite operators that call the transforms (rescale)
     size_t ws_words = 0;
     std::vector<u64> rescale;        // RescaleConstants[level-1][i] (ring.go:361-379), row-major [L-1][L], Montgomery form
+    u64 *d_rescale = nullptr;        // the same table on the device
     std::atomic<uint64_t> launches{0};
     // Ring/SubRing are "thread safe" in the reference (ring/ring.go:192-194): goroutines may call the same ring
     // concurrently.  Every compute entry point holds this lock while it enqueues, so the launches of one call
