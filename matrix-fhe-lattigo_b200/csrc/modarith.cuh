@@ -90,14 +90,27 @@ __device__ __forceinline__ unsigned hi32(u64 x) { return (unsigned)(x >> 32); }
 #ifndef B200_SHOUP_MULHI
 #define B200_SHOUP_MULHI 0
 #endif
+// B200_SHOUP_ALU_SUM: sum the three quotient terms with explicit add-with-carry instructions.  Otherwise ptxas folds
+// one high half into the 64-bit addend of a wide multiply and pays two moves to build that register pair.
+#ifndef B200_SHOUP_ALU_SUM
+#define B200_SHOUP_ALU_SUM 0
+#endif
 __device__ __forceinline__ u64 shoup4(u64 x, u64 w, u64 ws, u64 nq) {
     const unsigned x0 = lo32(x), x1 = hi32(x);
+#if B200_SHOUP_ALU_SUM
+    const u64 C = mulwide_u32(x1, hi32(ws));
+    const unsigned a = hi32(mulwide_u32(x0, hi32(ws))), b = hi32(mulwide_u32(x1, lo32(ws)));
+    unsigned t0, t1;
+    asm("{\n\t.reg .u32 s, k;\n\tadd.cc.u32 s, %2, %3;\n\taddc.u32 k, 0, 0;\n\tadd.cc.u32 %0, %4, s;\n\taddc.u32 %1, %5, k;\n\t}"
+        : "=r"(t0), "=r"(t1) : "r"(a), "r"(b), "r"(lo32(C)), "r"(hi32(C)));
+#else
 #if B200_SHOUP_MULHI
     const u64 t = mulwide_u32(x1, hi32(ws)) + __umulhi(x0, hi32(ws)) + __umulhi(x1, lo32(ws));
 #else
     const u64 t = mulwide_u32(x1, hi32(ws)) + hi32(mulwide_u32(x0, hi32(ws))) + hi32(mulwide_u32(x1, lo32(ws)));
 #endif
     const unsigned t0 = lo32(t), t1 = hi32(t);
+#endif
     const u64 r = madwide_u32(t0, lo32(nq), mulwide_u32(x0, lo32(w)));
     unsigned r1 = hi32(r);
     r1 = madlo_u32(x0, hi32(w), r1);
