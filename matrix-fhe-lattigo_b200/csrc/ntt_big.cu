@@ -43,6 +43,9 @@
 #ifndef B200_CANON_EST
 #define B200_CANON_EST 1    // 1: final canonical reduction through a quotient estimate
 #endif
+#ifndef B200_CANON_FINAL_ALU_M3
+#define B200_CANON_FINAL_ALU_M3 0   // last conditional subtraction of the 3N forward row pass: 1 = compare/select, 0 = multiply-add
+#endif
 // columns per CTA in the hand-tuned column kernels (the generic family uses 8).  Measured on B200: all four tuned
 // kernels gain 2-6% from 4-column tiles (192-thread CTAs, shorter barrier waits).
 #ifndef B200_CW_M3_FWD
@@ -344,7 +347,7 @@ k_rows_fwd(const u64 *in, u64 *out, BigArgs a) {
     for (int k = 0; k < 8; ++k) x[k] = ldd(src + k * 32 + lane);
     row_fwd_core(x, buf, lane, P1, tw, qc);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) x[k] = (a.flags & B200_LAZY) ? csub(x[k], qc.fourq) : canon8<!MATRIX>(x[k], qc);   // lazy: [0,4q) <= 6q-2
+    for (int k = 0; k < 8; ++k) x[k] = (a.flags & B200_LAZY) ? csub(x[k], qc.fourq) : canon8<(!MATRIX || B200_CANON_FINAL_ALU_M3)>(x[k], qc);   // lazy: [0,4q) <= 6q-2
     if (!MATRIX || (a.flags & B200_TREE_ORDER)) {
         u64 *dst = out + ur.out + (size_t)r * 256 + lane * 8;
         stg256(dst, x[0], x[1], x[2], x[3]);

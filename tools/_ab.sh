@@ -2,7 +2,7 @@
 for t in "$@"; do
   lib=matrix-fhe-lattigo_b200/lib/libb200ring${t:+_$t}.so
   for r in 1 2; do
-    echo "== ${t:-default} 3n"; B200RING_LIB=$PWD/$lib python tools/profile_ntt.py --ring 3n --polys 128 --limbs 24 --iters 1 --time 2>&1 | grep -v "^    " | tail -2
+    echo "== ${t:-default} 3n"; B200RING_LIB=$PWD/$lib python tools/profile_ntt.py --ring 3n --polys 128 --limbs 24 --iters 1 --time 2>&1 | tail -2
   done
-  echo "== ${t:-default} pow2"; B200RING_LIB=$PWD/$lib python tools/profile_ntt.py --ring pow2 --polys 128 --limbs 24 --iters 1 --time 2>&1 | grep -v "^    " | tail -2
+  echo "== ${t:-default} pow2"; B200RING_LIB=$PWD/$lib python tools/profile_ntt.py --ring pow2 --polys 128 --limbs 24 --iters 1 --time 2>&1 | tail -2
 done

@@ -133,6 +133,27 @@ __global__ void __launch_bounds__(128, 8) k_bf(u64 *data, const tw_t *twi, const
                     for (int o = 0; o < half; ++o) { if (MODE == 6) bf_int_v<1>(x[g * 2 * half + o], x[g * 2 * half + o + half], w, c); else bf_int(x[g * 2 * half + o], x[g * 2 * half + o + half], w, c); }
                 }
             }
+        } else if (MODE == 7) {
+            // primes with 15q < 2^64: no conditional subtraction for 3 layers ([0,2q) -> [0,14q)), then one quotient-estimate reduction
+#pragma unroll
+            for (int l = 0; l < LAYERS; ++l) {
+                const int j = l % 3, half = 4 >> j;
+#pragma unroll
+                for (int g = 0; g < (1 << j); ++g) {
+                    const tw_t w = twi[(((P + l / 3) << j) + g) & (TWN - 1)];
+#pragma unroll
+                    for (int o = 0; o < half; ++o) {
+                        u64 &U = x[g * 2 * half + o], &V = x[g * 2 * half + o + half];
+                        const u64 t = shoup4(V, w.x, w.y, c.nq);
+                        V = U - t + c.fourq;
+                        U = U + t;
+                    }
+                }
+                if (j == 2) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) x[k] = red2q(x[k], c);
+                }
+            }
         } else {
             // inputs in [0,2q) plus an offset C = k*q: the window [C - 0.51 L q, C + 2q + 0.51 L q] must stay inside
             // [0, 8q):  L <= 3 with C = 2q, L <= 5 with C = 3q
@@ -295,6 +316,10 @@ int main() {
     { std::vector<u64> rx;
       bench<6, 5>("integer, quotient summed on ALU", sms, d, in, d_ti, d_tf, c, &rx);
       size_t badx = 0; for (size_t i = 0; i < rx.size() && i < r3.size(); ++i) badx += rx[i] != r3[i];
+      printf("   parity vs integer: %zu mismatches\n", badx);
+      bench<0, 6>("integer, 6 layers/iter", sms, d, in, d_ti, d_tf, c, &r3);
+      bench<7, 6>("integer, csub-free 3-layer groups", sms, d, in, d_ti, d_tf, c, &rx);
+      badx = 0; for (size_t i = 0; i < rx.size() && i < r3.size(); ++i) badx += rx[i] != r3[i];
       printf("   parity vs integer: %zu mismatches\n", badx);
       bench<3, 5>("diag: integer part only, 5 layers", sms, d, in, d_ti, d_tf, c, &rx);
       bench<4, 5>("diag: FP64 part only, 5 layers", sms, d, in, d_ti, d_tf, c, &rx);
