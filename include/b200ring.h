@@ -40,9 +40,10 @@ extern "C" {
 typedef struct b200_ctx b200_ctx;   /* ring.Ring (ring/ring.go:76-89) + its SubRings on one GPU */
 typedef struct b200_poly b200_poly; /* ring.Poly (ring/poly.go:13-24), device resident, batched  */
 
-/* ring.Type (ring/ring.go:30-34).  ConjugateInvariant (1) is out of scope and rejected. */
-#define B200_RING_STANDARD 0 /* Z_q[X]/(X^N + 1), N = 2^k            */
-#define B200_RING_MATRIX 2   /* Z_q[X]/(X^N - X^(N/2) + 1), N = 2^a 3^b */
+/* ring.Type (ring/ring.go:30-34) */
+#define B200_RING_STANDARD 0            /* Z_q[X]/(X^N + 1), N = 2^k                                  */
+#define B200_RING_CONJUGATE_INVARIANT 1 /* Z_q[X + X^-1]/(X^2N + 1), N = 2^k coefficients (ring/ntt.go:80-124) */
+#define B200_RING_MATRIX 2              /* Z_q[X]/(X^N - X^(N/2) + 1), N = 2^a 3^b                    */
 
 /* error codes */
 #define B200_OK 0
@@ -105,6 +106,7 @@ B200_API int b200_device_count(void);         /* 0 when no CUDA device is visibl
  * them to `device`.
  *   roots == NULL or roots[i] == 0 : deterministic choice of the reference --
  *       STANDARD: g = smallest primitive root >= 3 (subring.go:236-248), psi = g^((q-1)/2N);
+ *       CONJUGATE_INVARIANT (NewRingConjugateInvariant, ring.go:280-282): the same g, psi = g^((q-1)/4N), q = 1 mod 4N;
  *       MATRIX  : omega = g^((q-1)/3N) (subring.go:255-290).
  *   roots[i] != 0 : STANDARD: the primitive root g of q_i (SubRing.PrimitiveRoot, skips factoring q-1);
  *                   MATRIX  : the primitive 3N-th root omega the Go transformer drew at random
@@ -121,10 +123,10 @@ B200_API int b200_ctx_moduli_count(const b200_ctx *ctx);            /* Ring.Modu
 B200_API int b200_ctx_ring_type(const b200_ctx *ctx);
 /* SubRing fields of limb i (ring/subring.go:35-55, ring/ntt.go:38-44):
  *   out[0]=Modulus out[1]=MRedConstant out[2..3]=BRedConstant out[4]=Mask
- *   out[5]=PrimitiveRoot g out[6]=NInv (Montgomery form; STANDARD only) out[7]=root used (psi or omega) */
+ *   out[5]=PrimitiveRoot g out[6]=NInv (Montgomery form; not MATRIX) out[7]=root used (psi or omega) */
 B200_API int b200_ctx_subring(const b200_ctx *ctx, int limb, uint64_t out[8]);
-/* STANDARD rings: NTTTable.RootsForward (inverse=0) / RootsBackward (inverse=1), N words, Montgomery
- * form, bit-reversed order -- bit-identical to subring.go:187-205. */
+/* STANDARD / CONJUGATE_INVARIANT rings: NTTTable.RootsForward (inverse=0) / RootsBackward (inverse=1), NthRoot/2 =
+ * N (2N for conjugate-invariant rings) words, Montgomery form, bit-reversed order -- bit-identical to subring.go:187-205. */
 B200_API int b200_ctx_roots(const b200_ctx *ctx, int limb, int inverse, uint64_t *out, size_t n);
 
 /* ---- device polynomials: ring.Poly / Ring.NewPoly (ring/poly.go:18-24) ---------------------- */
@@ -236,6 +238,11 @@ B200_API int b200_div_by_last_modulus_ntt(b200_ctx *ctx, const b200_poly *p0, b2
  * to those sequences (also for squaring, a == b).  Outputs may alias inputs but must be distinct from each other. */
 B200_API int b200_tensor(b200_ctx *ctx, const b200_poly *a0, const b200_poly *a1, const b200_poly *b0, const b200_poly *b1,
                 b200_poly *c0, b200_poly *c1, b200_poly *c2, int level, int mform_first);
+
+/* Ring.UnfoldConjugateInvariantToStandard (ring/conjugate_invariant.go:7-23): limbs 0..level of `ci` (a polynomial of the
+ * conjugate-invariant ring `ctx`, N words per limb) into `st`, a polynomial of a ring of degree 2N over the same moduli:
+ * st[j] = ci[j], st[2N-1-j] = ci[j]. */
+B200_API int b200_unfold_ci_to_standard(b200_ctx *ctx, const b200_poly *ci, b200_poly *st, int level);
 
 /* ---- fused ring product (BASELINE config 4; ring/ring_test.go:106-110 sequence) ---------------
  * c = INTT( MulCoeffsMontgomery( MForm(NTT(a)), NTT(b) ) ) = a*b in the ring, coefficient domain,

@@ -101,10 +101,13 @@ class Ring {
         const bool is3n = N % 3 == 0 && IsValidRingDegreeFor3N(N);
         return NewRingFromType(N, Moduli, is3n ? Matrix : Standard, device, roots);
     }
+    // ring.NewRingConjugateInvariant (ring/ring.go:280-282): NthRoot = 4N
+    static Ring NewRingConjugateInvariant(int N, const std::vector<uint64_t> &Moduli, int device = 0) {
+        return NewRingFromType(N, Moduli, ConjugateInvariant, device);
+    }
     // ring.NewRingFromType (ring/ring.go:291-308)
     static Ring NewRingFromType(int N, const std::vector<uint64_t> &Moduli, Type t, int device = 0,
                                 const std::vector<uint64_t> *roots = nullptr) {
-        if (t == ConjugateInvariant) throw std::invalid_argument("ConjugateInvariant rings are outside the B200 hot path");
         b200_ctx *c = nullptr;
         check(b200_ctx_create((int)t, N, (int)Moduli.size(), Moduli.data(), roots ? roots->data() : nullptr, device, &c));
         return Ring(std::shared_ptr<b200_ctx>(c, b200_ctx_destroy), (int)Moduli.size() - 1);

@@ -56,6 +56,7 @@ SYMBOLS = {
     "b200_div_by_last_modulus_ntt": (C.c_int, [VP, VP, VP, C.c_int, C.c_int]),
     "b200_tensor": (C.c_int, [VP, VP, VP, VP, VP, VP, VP, VP, C.c_int, C.c_int]),
     "b200_polymul": (C.c_int, [VP, VP, VP, VP, C.c_int]),
+    "b200_unfold_ci_to_standard": (C.c_int, [VP, VP, VP, C.c_int]),
     "b200_transform_host": (C.c_int, [VP, VP, VP, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int]),
     "b200_subring_ntt_host": (C.c_int, [VP, C.c_int, P64, P64, C.c_size_t, C.c_int, C.c_int]),
     "b200_ctx_launch_count": (C.c_uint64, [VP]),

@@ -91,6 +91,47 @@ static void build_standard(b200_ctx *ctx, int i, std::vector<tw_t> &fwd, std::ve
     misc[MISC_NINV_W1] = mk_tw(hm::mulmod(ninv, inv[1].x, q), q);
 }
 
+// CONJUGATE_INVARIANT tables (NewRingConjugateInvariant, ring.go:280-282: NthRoot = 4N).  The Go-format tables hold 2N
+// entries (subring.go:183-205).  The transform (ntt.go:754-786) is a folding layer with RootsForward[1] followed by the
+// layers m = 2, 4, .., N that read RootsForward[m + i], i < m/2: the left half of every level of the 2N-point tree.
+// Relabelled level m' = m/2 that is exactly the heap order of an N-point transform, table[m' + i] = Roots4N[2m' + i],
+// so the STANDARD kernels run it unchanged; the inverse (ntt.go:1104-1158) mirrors it with NInv = (2N)^-1.
+static void build_ci(b200_ctx *ctx, int i, std::vector<tw_t> &fwd, std::vector<tw_t> &inv, tw_t *misc) {
+    SubRingHost &s = ctx->sub[i];
+    const int N = ctx->N, logH = ctx->logN + 1;
+    const u64 q = s.q, nth = 4 * (u64)N, half = nth >> 1;
+    s.ninv = hm::mform(hm::invmod_prime(half % q, q), q);                        // subring.go:183
+    const u64 psi = hm::powmod(s.g, (q - 1) / nth, q);                           // :187
+    const u64 psi_inv = hm::powmod(s.g, q - ((q - 1) / nth) - 1, q);             // :188
+    s.root = psi;
+    const u64 psi_m = hm::mform(psi, q), psi_inv_m = hm::mform(psi_inv, q);
+    s.roots_fwd.assign(half, 0);
+    s.roots_bwd.assign(half, 0);
+    s.roots_fwd[0] = s.roots_bwd[0] = hm::mform(1, q);
+    std::vector<u64> pf(half), pb(half);   // plain-domain copies of the two tables
+    pf[0] = pb[0] = 1;
+    u64 f = 1, b = 1;
+    for (u64 j = 1; j < half; ++j) {                                             // :198-205
+        const u64 prev = hm::bitrev(j - 1, logH), cur = hm::bitrev(j, logH);
+        s.roots_fwd[cur] = hm::mred(s.roots_fwd[prev], psi_m, q, s.qinv);
+        s.roots_bwd[cur] = hm::mred(s.roots_bwd[prev], psi_inv_m, q, s.qinv);
+        f = hm::mulmod(f, psi, q);
+        b = hm::mulmod(b, psi_inv, q);
+        pf[cur] = f; pb[cur] = b;
+    }
+    fwd[0] = inv[0] = mk_tw(1, q);
+    for (u64 m = 1; m < (u64)N; m <<= 1)
+        for (u64 k = 0; k < m; ++k) {
+            fwd[m + k] = mk_tw(pf[2 * m + k], q);
+            inv[m + k] = mk_tw(pb[2 * m + k], q);
+        }
+    const u64 ninv = hm::invmod_prime(half % q, q);
+    misc[MISC_NINV] = mk_tw(ninv, q);
+    misc[MISC_NINV_W1] = mk_tw(hm::mulmod(ninv, inv[1].x, q), q);
+    misc[MISC_CI_F] = mk_tw(pf[1], q);
+    misc[MISC_CI_FINV] = mk_tw(pb[1], q);
+}
+
 // MATRIX tables: zetas in the order of the exponent tree: index 1 = omega^(N/2),
 // radix-3 layer with nb blocks at [nb + 2 blk, +1], radix-2 layer with nb blocks at [nb + blk].
 static void build_matrix(b200_ctx *ctx, int i, std::vector<tw_t> &fwd, std::vector<tw_t> &inv, tw_t *misc,
@@ -150,12 +191,14 @@ extern "C" int b200_ctx_create(int ring_type, int N, int L, const uint64_t *modu
     int a = 0, b = 0;
     const bool pow2 = N >= 8 && (N & (N - 1)) == 0;
     const bool is3n = valid_3n_degree(N, &a, &b);
-    if (ring_type != B200_RING_STANDARD && ring_type != B200_RING_MATRIX)
+    if (ring_type != B200_RING_STANDARD && ring_type != B200_RING_MATRIX && ring_type != B200_RING_CONJUGATE_INVARIANT)
         return fail(B200_EINVAL, "invalid ring type");
     if (!pow2 && !is3n)   // ring.go:319-323
         return fail(B200_EINVAL, "invalid ring degree: must be a power of 2 greater than 8 or satisfy 3N = 2^a * 3^{b+1} condition");
     if (ring_type == B200_RING_STANDARD && !pow2)
         return fail(B200_EINVAL, "invalid ring degree: the Standard ring needs N to be a power of 2 greater than 8");
+    if (ring_type == B200_RING_CONJUGATE_INVARIANT && !pow2)   // the reference's 6N variant runs radix-2 butterflies on a non-power-of-two length
+        return fail(B200_EINVAL, "invalid ring degree: the ConjugateInvariant ring needs N to be a power of 2 greater than 8");
     if (ring_type == B200_RING_MATRIX && !(N % 3 == 0 && is3n && N >= 8 && a >= 1))   // ring.go:301-303
         return fail(B200_EINVAL, "matrix ring type requires N to satisfy 3N = 2^a * 3^{b+1} condition, got N=" + std::to_string(N));
     if (L <= 0 || !moduli) return fail(B200_EINVAL, "invalid ModuliChain (must be a non-empty []uint64)");   // ring.go:325-327
@@ -163,7 +206,7 @@ extern "C" int b200_ctx_create(int ring_type, int N, int L, const uint64_t *modu
         std::set<u64> seen(moduli, moduli + L);
         if ((int)seen.size() != L) return fail(B200_EINVAL, "invalid ModuliChain (moduli are not distinct)");   // ring.go:329-331
     }
-    const u64 nthroot = ring_type == B200_RING_MATRIX ? 3 * (u64)N : 2 * (u64)N;
+    const u64 nthroot = ring_type == B200_RING_MATRIX ? 3 * (u64)N : ring_type == B200_RING_CONJUGATE_INVARIANT ? 4 * (u64)N : 2 * (u64)N;
     for (int i = 0; i < L; ++i) {
         const u64 q = moduli[i];
         if (!hm::is_prime(q)) return fail(B200_EINVAL, "invalid modulus: " + std::to_string(q) + " is not prime)");      // subring.go:140-142
@@ -177,6 +220,7 @@ extern "C" int b200_ctx_create(int ring_type, int N, int L, const uint64_t *modu
 
     b200_ctx *ctx = new b200_ctx();
     ctx->ring_type = ring_type; ctx->N = N; ctx->L = L; ctx->device = device;
+    ctx->core_type = ring_type == B200_RING_MATRIX ? B200_RING_MATRIX : B200_RING_STANDARD;
     ctx->a = a; ctx->b = b;
     while ((1 << ctx->logN) < N) ctx->logN++;
     cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
@@ -206,7 +250,7 @@ extern "C" int b200_ctx_create(int ring_type, int N, int L, const uint64_t *modu
         }
         std::vector<tw_t> f(N), v(N);
         const u64 given = roots ? roots[i] : 0;
-        if (ring_type == B200_RING_STANDARD) {
+        if (ring_type != B200_RING_MATRIX) {
             if (given) {
                 std::vector<u64> fac = hm::unique_factors(s.q - 1);
                 if (!hm::is_primitive_root(given % s.q, s.q, fac)) { delete ctx; return fail(B200_EINVAL, "roots[" + std::to_string(i) + "] is not a primitive root"); }
@@ -214,7 +258,8 @@ extern "C" int b200_ctx_create(int ring_type, int N, int L, const uint64_t *modu
             } else {
                 s.g = hm::primitive_root(s.q, hm::unique_factors(s.q - 1));   // subring.go:218-251
             }
-            build_standard(ctx, i, f, v, &misc[(size_t)i * MISC_COUNT]);
+            if (ring_type == B200_RING_STANDARD) build_standard(ctx, i, f, v, &misc[(size_t)i * MISC_COUNT]);
+            else build_ci(ctx, i, f, v, &misc[(size_t)i * MISC_COUNT]);
         } else {
             if (given) {
                 const u64 w = given % s.q;
@@ -349,10 +394,10 @@ extern "C" int b200_ctx_subring(const b200_ctx *ctx, int limb, uint64_t out[8]) 
 }
 extern "C" int b200_ctx_roots(const b200_ctx *ctx, int limb, int inverse, uint64_t *out, size_t n) {
     if (!ctx || !out || limb < 0 || limb >= ctx->L) return fail(B200_EINVAL, "b200_ctx_roots: bad argument");
-    if (ctx->ring_type != B200_RING_STANDARD) return fail(B200_EINVAL, "b200_ctx_roots: only Standard rings carry RootsForward/RootsBackward");
-    if (n < (size_t)ctx->N) return fail(B200_ESHAPE, "b200_ctx_roots: len(out) < N");
+    if (ctx->ring_type == B200_RING_MATRIX) return fail(B200_EINVAL, "b200_ctx_roots: Matrix rings carry no RootsForward/RootsBackward");
     const std::vector<u64> &t = inverse ? ctx->sub[limb].roots_bwd : ctx->sub[limb].roots_fwd;
-    std::memcpy(out, t.data(), sizeof(u64) * ctx->N);
+    if (n < t.size()) return fail(B200_ESHAPE, "b200_ctx_roots: len(out) < NthRoot/2");
+    std::memcpy(out, t.data(), sizeof(u64) * t.size());
     return 0;
 }
 
@@ -517,13 +562,27 @@ static int check_polys(b200_ctx *ctx, int level, const char *who, std::initializ
     return 0;
 }
 
+// The transform of the ring: tuned two-pass kernels where the shape is covered, generic kernels otherwise.  Conjugate-
+// invariant rings add their folding layer (launch_ci_fold): before the butterflies of the forward transform, after those
+// of the inverse (ring/ntt.go:754-786,1104-1158).
+int launch_ntt(b200_ctx *ctx, const u64 *in, u64 *out, Span sp, bool inverse, int flags) {
+    const bool ci = ctx->ring_type == B200_RING_CONJUGATE_INVARIANT;
+    if (ci && !inverse) {
+        if (int rc = launch_ci_fold(ctx, in, out, sp, false)) return rc;
+        in = out;
+    }
+    int rc = launch_ntt_big(ctx, in, out, sp, inverse, flags);
+    if (rc == 1) rc = launch_ntt_generic(ctx, in, out, sp, inverse, flags);
+    if (rc == 0 && ci && inverse) rc = launch_ci_fold(ctx, out, out, sp, true);
+    return rc;
+}
+
 static int transform(b200_ctx *ctx, const b200_poly *in, b200_poly *out, int level, int flags, bool inverse, const char *who) {
     int batch;
     if (int rc = check_polys(ctx, level, who, {in, out}, &batch)) return rc;
     CUDA_TRY(cudaSetDevice(ctx->device));
     Span sp{batch, level + 1, ctx->L, 0};
-    int rc = launch_ntt_big(ctx, in->d, out->d, sp, inverse, flags);
-    if (rc == 1) rc = launch_ntt_generic(ctx, in->d, out->d, sp, inverse, flags);
+    int rc = launch_ntt(ctx, in->d, out->d, sp, inverse, flags);
     return rc;
 }
 // Ring.NTT / INTT restricted to limbs [limb0, limb0+nl): what a rank of a limb-sharded ring runs on its share
@@ -536,8 +595,7 @@ extern "C" int b200_ntt_limbs(b200_ctx *ctx, const b200_poly *in, b200_poly *out
     CUDA_TRY(cudaSetDevice(ctx->device));
     const size_t off = (size_t)limb0 * ctx->N;
     Span sp{batch, nl, ctx->L, limb0};
-    int rc = launch_ntt_big(ctx, in->d + off, out->d + off, sp, inverse != 0, flags);
-    if (rc == 1) rc = launch_ntt_generic(ctx, in->d + off, out->d + off, sp, inverse != 0, flags);
+    int rc = launch_ntt(ctx, in->d + off, out->d + off, sp, inverse != 0, flags);
     return rc;
 }
 
@@ -602,10 +660,10 @@ extern "C" int b200_intt_limbs_gather(b200_ctx *ctx, const b200_poly *in, b200_p
         po.p[i] = static_cast<u64 *>(peer_polys[i]) + off;
     }
     Span sp{batch, nl, ctx->L, limb0};
-    int rc = launch_ntt_big(ctx, in->d + off, out->d + off, sp, true, flags, &po);
+    // the fused peer stores live in the last butterfly pass, which is not the last step of a conjugate-invariant transform
+    int rc = ctx->ring_type == B200_RING_CONJUGATE_INVARIANT ? 1 : launch_ntt_big(ctx, in->d + off, out->d + off, sp, true, flags, &po);
     if (rc != 1) return rc;
-    rc = launch_ntt_big(ctx, in->d + off, out->d + off, sp, true, flags);
-    if (rc == 1) rc = launch_ntt_generic(ctx, in->d + off, out->d + off, sp, true, flags);
+    rc = launch_ntt(ctx, in->d + off, out->d + off, sp, true, flags);
     if (rc || npeers == 0) return rc;
     int chunks = (ctx->N + 255) / 256;
     if (chunks > 64) chunks = 64;
@@ -671,8 +729,7 @@ extern "C" int b200_div_by_last_modulus_ntt(b200_ctx *ctx, const b200_poly *p0, 
     u64 *ws = ctx->d_ws;
     const size_t off = (size_t)level * ctx->N;
     auto ntt = [&](const u64 *src, u64 *dst, Span sp, bool inv) {
-        int r = launch_ntt_big(ctx, src, dst, sp, inv, 0);
-        if (r == 1) r = launch_ntt_generic(ctx, src, dst, sp, inv, 0);
+        int r = launch_ntt(ctx, src, dst, sp, inv, 0);
         return r;
     };
     int rc = ntt(p0->d + off, ws + off, Span{batch, 1, ctx->L, level}, true);          // scaling.go:134
@@ -694,13 +751,27 @@ extern "C" int b200_tensor(b200_ctx *ctx, const b200_poly *a0, const b200_poly *
     return launch_tensor(ctx, a0->d, a1->d, b0->d, b1->d, c0->d, c1->d, c2->d, Span{batch, level + 1, ctx->L, 0}, mform_first != 0);
 }
 
+// Ring.UnfoldConjugateInvariantToStandard (ring/conjugate_invariant.go:7-23): limbs 0..level of a polynomial of a
+// conjugate-invariant ring of degree N into a polynomial of a ring of degree 2N over the same moduli.
+extern "C" int b200_unfold_ci_to_standard(b200_ctx *ctx, const b200_poly *ci, b200_poly *st, int level) {
+    CtxLock lk(ctx);
+    if (!ctx || !ci || !st || ci->ctx != ctx || !st->ctx) return fail(B200_EINVAL, "b200_unfold_ci_to_standard: NULL argument or foreign polynomial");
+    if (2 * ctx->N != st->ctx->N)   // conjugate_invariant.go:10-12 (panic)
+        return fail(B200_ESHAPE, "cannot UnfoldConjugateInvariantToStandard: Ring degree of polyConjugateInvariant must be twice the ring degree of polyStandard");
+    if (level < 0 || level >= ctx->L || level >= st->ctx->L) return fail(B200_ESHAPE, "b200_unfold_ci_to_standard: level out of range");
+    if (ci->batch != st->batch) return fail(B200_ESHAPE, "b200_unfold_ci_to_standard: batch sizes differ");
+    if (ci->ctx->device != st->ctx->device) return fail(B200_ESHAPE, "b200_unfold_ci_to_standard: polynomials live on different devices");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    return launch_ci_unfold(ctx, ci->d, st->d, ctx->N, ci->batch, level + 1, ctx->L, st->ctx->L);
+}
+
 extern "C" int b200_polymul(b200_ctx *ctx, const b200_poly *a, const b200_poly *b, b200_poly *c, int level) {
     CtxLock lk(ctx);
     int batch;
     if (int rc = check_polys(ctx, level, "b200_polymul", {a, b, c}, &batch)) return rc;
     CUDA_TRY(cudaSetDevice(ctx->device));
     Span sp{batch, level + 1, ctx->L, 0};
-    int rc = launch_polymul_big(ctx, a->d, b->d, c->d, sp);
+    int rc = ctx->ring_type == B200_RING_CONJUGATE_INVARIANT ? 1 : launch_polymul_big(ctx, a->d, b->d, c->d, sp);   // the fused rows skip the folding layer
     if (rc != 1) return rc;
     // generic composition: NTT(a), NTT(b) in tree order -> Barrett product (== MRed(MForm(a^), b^), canonical,
     // ring/ring_test.go:106-110) -> INTT.  Two scratch polynomials.
@@ -709,8 +780,7 @@ extern "C" int b200_polymul(b200_ctx *ctx, const b200_poly *a, const b200_poly *
     u64 *ta = ctx->d_scratch, *tb = ctx->d_scratch + words;
     const int tf = ctx->ring_type == B200_RING_MATRIX ? B200_TREE_ORDER : 0;
     auto ntt = [&](const u64 *src, u64 *dst, bool inv) {
-        int r = launch_ntt_big(ctx, src, dst, sp, inv, tf);
-        if (r == 1) r = launch_ntt_generic(ctx, src, dst, sp, inv, tf);
+        int r = launch_ntt(ctx, src, dst, sp, inv, tf);
         return r;
     };
     if ((rc = ntt(a->d, ta, false))) return rc;
@@ -773,8 +843,7 @@ extern "C" int b200_transform_host(b200_ctx *ctx, const uint64_t *host_in, uint6
         Span sp{nb, level + 1, ctx->L, 0};
         for (int o = 0; o < n_ops && rc == 0; ++o) {
             const bool inv = ops[o] != 0;
-            rc = launch_ntt_big(ctx, p.buf[s], p.buf[s], sp, inv, flags);
-            if (rc == 1) rc = launch_ntt_generic(ctx, p.buf[s], p.buf[s], sp, inv, flags);
+            rc = launch_ntt(ctx, p.buf[s], p.buf[s], sp, inv, flags);
         }
         if (rc) break;
         e = cudaEventRecord(p.done[s], p.comp);
@@ -802,8 +871,7 @@ extern "C" int b200_subring_ntt_host(b200_ctx *ctx, int limb, const uint64_t *p1
     CUDA_TRY(cudaMallocAsync(&d, sizeof(u64) * ctx->N, ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(d, p1, sizeof(u64) * ctx->N, cudaMemcpyHostToDevice, ctx->stream));
     Span sp{1, 1, 1, limb};
-    int rc = launch_ntt_big(ctx, d, d, sp, inverse != 0, flags);
-    if (rc == 1) rc = launch_ntt_generic(ctx, d, d, sp, inverse != 0, flags);
+    int rc = launch_ntt(ctx, d, d, sp, inverse != 0, flags);
     if (rc == 0) {
         cudaError_t e = cudaMemcpyAsync(p2, d, sizeof(u64) * ctx->N, cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);

@@ -123,6 +123,48 @@ k_tensor(const u64 *a0, const u64 *a1, const u64 *b0, const u64 *b1, u64 *c0, u6
     }
 }
 
+// Folding layer of the conjugate-invariant transform (ring/ntt.go:764-770 forward, :1149-1157 inverse): with F the
+// fourth root of unity RootsForward[1] (inverse: RootsBackward[1])
+//   out[j] = in[j] - F*in[N-j] for 0 < j < N (j and N-j are handled by the same thread, so in == out is allowed),
+//   out[0] = in[0] (inverse: 2*in[0]).
+// Inputs < 2q, outputs canonical.  HBM-bound: 16 B/word, one Shoup multiply per word.
+__global__ void __launch_bounds__(256)
+k_ci_fold(const u64 *in, u64 *out, const LimbConst *__restrict__ consts, const tw_t *__restrict__ misc, int N, Span sp, int unit0, int inverse) {
+    const int unit = unit0 + blockIdx.y;
+    const int limb = unit % sp.nl;
+    const size_t base = ((size_t)(unit / sp.nl) * sp.Lbuf + limb) * (size_t)N;
+    const u64 q = consts[sp.limb0 + limb].q;
+    const tw_t F = misc[(sp.limb0 + limb) * MISC_COUNT + (inverse ? MISC_CI_FINV : MISC_CI_F)];
+    const u64 *a = in + base;
+    u64 *o = out + base;
+    const int half = N >> 1;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j <= half; j += gridDim.x * blockDim.x) {
+        if (j == 0) {
+            const u64 x = csub(a[0], q);
+            o[0] = inverse ? csub(x << 1, q) : x;                     // :770 / :1157 CRed(p2[0] << 1)
+        } else {
+            const u64 x = csub(a[j], q), y = csub(a[N - j], q);
+            const u64 fx = shoup(x, F.x, F.y, q), fy = shoup(y, F.x, F.y, q);
+            o[j] = csub(x + q - fy, q);
+            if (j != half) o[N - j] = csub(y + q - fx, q);
+        }
+    }
+}
+
+// Ring.UnfoldConjugateInvariantToStandard (ring/conjugate_invariant.go:7-23): the compressed N words of every limb to
+// the 2N words of the standard ring, out[j] = in[j], out[2N-1-j] = in[j].
+__global__ void __launch_bounds__(256)
+k_ci_unfold(const u64 *in, u64 *out, int N, int Lin, int Lout, int nl) {
+    const int unit = blockIdx.y, limb = unit % nl, b = unit / nl;
+    const u64 *a = in + ((size_t)b * Lin + limb) * (size_t)N;
+    u64 *o = out + ((size_t)b * Lout + limb) * (size_t)(2 * N);
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x) {
+        const u64 v = a[j];
+        o[j] = v;
+        o[2 * N - 1 - j] = v;
+    }
+}
+
 // Rescale helper (ring/scaling.go:137-143): x = coefficient-domain last limb [0, q_l); for every lower limb i
 // t_i = (x (+ pHalf mod q_l)) + (q_i - pHalf mod q_i), reduced to [0, q_i).  ws is a [batch][Lbuf][N] buffer whose
 // limb `level` holds x; limbs 0..level-1 receive t_i.
@@ -143,6 +185,30 @@ k_rescale_spread(u64 *ws, const LimbConst *__restrict__ consts, int N, int Lbuf,
 }
 
 }  // namespace
+
+int launch_ci_fold(b200_ctx *ctx, const u64 *in, u64 *out, Span sp, bool inverse) {
+    const int N = ctx->N;
+    int chunks = (N / 2 + 1 + 255) / 256;
+    if (chunks > 512) chunks = 512;
+    const int units = sp.batch * sp.nl;
+    for (int u0 = 0; u0 < units; u0 += 65535) {
+        const int nu = units - u0 < 65535 ? units - u0 : 65535;
+        LaunchScope ls(ctx, inverse ? "ci_fold_inv" : "ci_fold_fwd", nu);
+        k_ci_fold<<<dim3(chunks, nu), 256, 0, b200_cur_stream(ctx)>>>(in, out, ctx->d_consts, ctx->d_misc, N, sp, u0, inverse ? 1 : 0);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int launch_ci_unfold(b200_ctx *ctx, const u64 *in, u64 *out, int N, int batch, int nl, int Lin, int Lout) {
+    int chunks = (N + 255) / 256;
+    if (chunks > 512) chunks = 512;
+    if ((long long)batch * nl > 65535) { b200_set_error("b200_unfold_ci_to_standard: more than 65535 limb units"); return B200_ESHAPE; }
+    LaunchScope ls(ctx, "ci_unfold", (long long)batch * nl);
+    k_ci_unfold<<<dim3(chunks, batch * nl), 256, 0, b200_cur_stream(ctx)>>>(in, out, N, Lin, Lout, nl);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
 
 int launch_rescale_spread(b200_ctx *ctx, u64 *ws, int batch, int level, bool round) {
     const int N = ctx->N;

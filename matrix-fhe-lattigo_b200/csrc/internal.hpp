@@ -25,9 +25,12 @@ struct SubRingHost {
 
 // indices into the per-limb misc constant block (MATRIX rings)
 enum { MISC_OMEGA3 = 0, MISC_K1 = 1, MISC_K2 = 2, MISC_ZETA = 3, MISC_NINV = 4, MISC_NINV_W1 = 5, MISC_COUNT = 8 };
+// conjugate-invariant rings: the fourth roots of unity of the folding layer (RootsForward[1], RootsBackward[1])
+enum { MISC_CI_F = 6, MISC_CI_FINV = 7 };
 
 struct b200_ctx {
     int ring_type = 0, N = 0, L = 0, device = 0;
+    int core_type = 0;     // butterfly network the kernels run: STANDARD (also for conjugate-invariant rings) or MATRIX
     int logN = 0;          // STANDARD: log2 N
     int a = 0, b = 0;      // MATRIX: N = 2^a 3^b
     cudaStream_t stream = nullptr;
@@ -136,4 +139,9 @@ struct PeerOut {
     u64 *p[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 int launch_ntt_big(b200_ctx *ctx, const u64 *in, u64 *out, Span sp, bool inverse, int flags, const PeerOut *peers = nullptr);
+// the transform of the ring, whatever its type: tuned two-pass kernels where the shape is covered, generic kernels
+// otherwise, plus the folding layer of conjugate-invariant rings (ring/ntt.go:754-786,1104-1158)
+int launch_ntt(b200_ctx *ctx, const u64 *in, u64 *out, Span sp, bool inverse, int flags);
+int launch_ci_fold(b200_ctx *ctx, const u64 *in, u64 *out, Span sp, bool inverse);
+int launch_ci_unfold(b200_ctx *ctx, const u64 *in, u64 *out, int N, int batch, int nl, int Lin, int Lout);
 int launch_polymul_big(b200_ctx *ctx, const u64 *a, const u64 *b, u64 *c, Span sp);

@@ -339,8 +339,7 @@ int ntt_range(b200_ctx *ctx, const u64 *src, u64 *dst, int batch, int limb0, int
     if (nl <= 0) return 0;
     const size_t off = (size_t)limb0 * ctx->N;
     Span sp{batch, nl, ctx->L, limb0};
-    int rc = launch_ntt_big(ctx, src + off, dst + off, sp, inverse, 0);
-    if (rc == 1) rc = launch_ntt_generic(ctx, src + off, dst + off, sp, inverse, 0);
+    int rc = launch_ntt(ctx, src + off, dst + off, sp, inverse, 0);
     return rc;
 }
 

@@ -276,7 +276,7 @@ int launch_ntt_generic(b200_ctx *ctx, const u64 *in, u64 *out, Span sp, bool inv
         {
             LaunchScope ls(ctx, inverse ? "resident_inv" : "resident_fwd", units);
             kern<<<units, threads, smem, b200_cur_stream(ctx)>>>(in, out, ctx->d_consts, ctx->d_fwd, ctx->d_inv, ctx->d_misc,
-                                                        ctx->d_go2fast, s, ctx->ring_type, flags);
+                                                        ctx->d_go2fast, s, ctx->core_type, flags);
         }
         CUDA_TRY(cudaGetLastError());
         return 0;

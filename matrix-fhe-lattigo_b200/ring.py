@@ -83,8 +83,9 @@ class SubRing:
         self.Mask, self.PrimitiveRoot, self.NInv, self.Root = int(out[4]), int(out[5]), int(out[6]), int(out[7])
 
     def _roots(self, inverse):
-        out = np.empty(self.N, dtype=np.uint64)
-        check(lib().b200_ctx_roots(self._ring._ctx.h, self._i, inverse, out.ctypes.data_as(capi.P64), self.N))
+        n = self._ring.NthRoot() // 2        # subring.go:190-191: NthRoot/2 entries
+        out = np.empty(n, dtype=np.uint64)
+        check(lib().b200_ctx_roots(self._ring._ctx.h, self._i, inverse, out.ctypes.data_as(capi.P64), n))
         return out
 
     @property
@@ -248,7 +249,28 @@ class Ring:
         return self._N
 
     def NthRoot(self):
-        return (3 if self._type == Matrix else 2) * self._N
+        return {int(Matrix): 3, int(ConjugateInvariant): 4}.get(int(self._type), 2) * self._N
+
+    def ConjugateInvariantRing(self):
+        """Ring.ConjugateInvariantRing (ring/ring.go:95-110): the conjugate-invariant ring of half the degree over the
+        same moduli (the receiver itself if it already is one)."""
+        if self._type == ConjugateInvariant:
+            return self
+        if self._type != Standard:
+            raise ValueError("cannot ConjugateInvariantRing: the ring is not a power-of-two ring")
+        return NewRingFromType(self._N >> 1, self._moduli[: self.level + 1], ConjugateInvariant, self.device)
+
+    def StandardRing(self):
+        """Ring.StandardRing (ring/ring.go:112-127): the standard ring of twice the degree over the same moduli."""
+        if self._type == Standard:
+            return self
+        if self._type != ConjugateInvariant:
+            raise ValueError("cannot StandardRing: the ring is not a conjugate-invariant ring")
+        return NewRingFromType(self._N << 1, self._moduli[: self.level + 1], Standard, self.device)
+
+    def UnfoldConjugateInvariantToStandard(self, polyConjugateInvariant, polyStandard):
+        """ring/conjugate_invariant.go:7-23 (the receiver is the conjugate-invariant ring)."""
+        check(lib().b200_unfold_ci_to_standard(self._ctx.h, polyConjugateInvariant.h, polyStandard.h, self.level))
 
     def Type(self):
         return self._type
@@ -267,7 +289,8 @@ class Ring:
             rc = lib().b200_ctx_factors(self._ctx.h, i, f, n)
             if rc < 0:
                 check(rc)
-            out.append({"Type": 0, "LogN": (self._N - 1).bit_length(), "NthRoot": self.NthRoot() // self._N,
+            out.append({"Type": int(self._type) if self._type == ConjugateInvariant else 0,
+                        "LogN": (self._N - 1).bit_length(), "NthRoot": self.NthRoot() // self._N,
                         "Modulus": s.Modulus, "Factors": [int(f[k]) for k in range(n)],
                         "PrimitiveRoot": s.Root if self._type == Matrix else s.PrimitiveRoot})
         return out
@@ -506,13 +529,16 @@ for _n, _c in _BINARY_SCALAR_OPS.items():
 def NewRingFromType(N, Moduli, ringType, device=0, roots=None):
     """ring.NewRingFromType (ring/ring.go:291-308).  `roots`: see b200_ctx_create."""
     ringType = Type(ringType)
-    if ringType == ConjugateInvariant:
-        raise ValueError("ConjugateInvariant rings are outside the B200 hot path (SURVEY.md section 2)")
-    if ringType not in (Standard, Matrix):
+    if ringType not in (Standard, ConjugateInvariant, Matrix):
         raise ValueError("invalid ring type")
     moduli = [int(q) for q in Moduli]
     ctx = _Context(ringType, N, moduli, roots, device)
     return Ring(ctx, ringType, N, moduli, len(moduli) - 1, device)
+
+
+def NewRingConjugateInvariant(N, Moduli, device=0, roots=None):
+    """ring.NewRingConjugateInvariant (ring/ring.go:280-282): Z_q[X + X^-1]/(X^2N + 1), moduli = 1 mod 4N."""
+    return NewRingFromType(N, Moduli, ConjugateInvariant, device, roots)
 
 
 def NewRing(N, Moduli, device=0, roots=None):
@@ -533,9 +559,7 @@ def UnmarshalJSON(data, device=0, N=None):
     if not isinstance(lit, list) or not lit:
         raise ValueError("invalid ring literal")
     for k, p in enumerate(lit):
-        if p["Type"] == int(ConjugateInvariant):
-            raise ValueError("ConjugateInvariant rings are outside the B200 hot path (SURVEY.md section 2)")
-        if p["Type"] != int(Standard):
+        if p["Type"] not in (int(Standard), int(ConjugateInvariant)):
             raise ValueError("invalid ring type")
         if k and (p["LogN"] != lit[0]["LogN"] or p["NthRoot"] != lit[0]["NthRoot"]):
             raise ValueError("invalid SubRings: all SubRings must have the same ring degree and NthRoot")
@@ -550,8 +574,12 @@ def UnmarshalJSON(data, device=0, N=None):
         return NewRingFromType(N, moduli, Matrix, device, roots)
     if nth < 2:
         raise ValueError("invalid ring type: NthRoot must be at least 2N but is %dN" % nth)
+    if lit[0]["Type"] == int(ConjugateInvariant):
+        if nth != 4:
+            raise ValueError("invalid NthRoot: a ConjugateInvariant ring has NthRoot 4N")
+        return NewRingFromType(1 << lit[0]["LogN"], moduli, ConjugateInvariant, device, roots)
     if nth != 2:
-        raise ValueError("invalid NthRoot: only 2N (Standard) and 3N (Matrix) rings are supported")
+        raise ValueError("invalid NthRoot: only 2N (Standard), 4N (ConjugateInvariant) and 3N (Matrix) rings are supported")
     return NewRingFromType(1 << lit[0]["LogN"], moduli, Standard, device, roots)
 
 

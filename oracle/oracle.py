@@ -67,6 +67,11 @@ def lib():
             "ref_pow2_tables": (None, [C.c_void_p, P64, P64]),
             "ref_pow2_ntt": (None, [C.c_void_p, P64, P64, C.c_int]),
             "ref_pow2_intt": (None, [C.c_void_p, P64, P64, C.c_int]),
+            "ref_ci_new": (C.c_void_p, [C.c_int, u64]), "ref_ci_free": (None, [C.c_void_p]),
+            "ref_ci_constants": (None, [C.c_void_p, P64]),
+            "ref_ci_tables": (None, [C.c_void_p, P64, P64]),
+            "ref_ci_ntt": (None, [C.c_void_p, P64, P64, C.c_int]),
+            "ref_ci_intt": (None, [C.c_void_p, P64, P64, C.c_int]),
             "ref_vec_op": (C.c_int, [C.c_int, C.c_int, u64, P64, P64, P64, u64]),
             "ref_3n_exponents": (C.c_int, [C.c_int, PI]),
             "ref_3n_forward_horner": (None, [C.c_int, u64, u64, P64, P64]),
@@ -170,6 +175,43 @@ class Pow2SubRing:
     def __del__(self):
         if getattr(self, "h", None) and _lib is not None:
             _lib.ref_pow2_free(self.h)
+            self.h = None
+
+
+class ConjugateInvariantSubRing:
+    """ring.SubRing with the ConjugateInvariant transformer (NthRoot = 4N; ring/ntt.go:80-124,716-786,1088-1158)."""
+
+    def __init__(self, N, q):
+        self.N, self.q = N, q
+        self.h = lib().ref_ci_new(N, q)
+        if not self.h:
+            raise ValueError("invalid conjugate-invariant subring N=%d q=%d" % (N, q))
+        c = np.zeros(6, dtype=np.uint64)
+        lib().ref_ci_constants(self.h, _p(c))
+        self.MRedConstant, self.BRedConstant = int(c[0]), (int(c[1]), int(c[2]))
+        self.PrimitiveRoot, self.NInv = int(c[3]), int(c[4])
+
+    def tables(self):
+        rf = np.empty(2 * self.N, dtype=np.uint64)
+        rb = np.empty(2 * self.N, dtype=np.uint64)
+        lib().ref_ci_tables(self.h, _p(rf), _p(rb))
+        return rf, rb
+
+    def NTT(self, p, lazy=False):
+        p = _arr(p)
+        out = np.empty_like(p)
+        lib().ref_ci_ntt(self.h, _p(p), _p(out), int(lazy))
+        return out
+
+    def INTT(self, p, lazy=False):
+        p = _arr(p)
+        out = np.empty_like(p)
+        lib().ref_ci_intt(self.h, _p(p), _p(out), int(lazy))
+        return out
+
+    def __del__(self):
+        if getattr(self, "h", None) and _lib is not None:
+            _lib.ref_ci_free(self.h)
             self.h = None
 
 

@@ -354,6 +354,108 @@ EXPORT void ref_pow2_intt(const ref_pow2 *s, const u64 *p1, u64 *p2, int lazy) {
 }
 
 /* ---------------------------------------------------------------------------
+ * conjugate-invariant ring Z_q[X + X^-1]/(X^2N + 1): ring/ntt.go:80-124 (transformer), :716-786 (forward),
+ * :1088-1158 (inverse); constructor NewRingConjugateInvariant (ring/ring.go:280-282) = NthRoot 4N, so the tables
+ * of generateNTTConstants (subring.go:183-205) hold 2N entries, bit-reversed over log2(2N) bits, and
+ * NInv = (2N)^-1 in Montgomery form.
+ * ------------------------------------------------------------------------- */
+typedef struct {
+    int N, logN;      /* ring degree N (the compressed representation), log2 N */
+    u64 q, qinv, brc[2], g, ninv;
+    u64 *rf, *rb;     /* 2N entries each */
+} ref_ci;
+
+EXPORT ref_ci *ref_ci_new(int N, u64 q) {
+    if (N < 2 || (N & (N - 1))) return NULL;
+    u64 nth = 4 * (u64)N;
+    if (!ref_is_prime(q) || q % nth != 1) return NULL;
+    ref_ci *s = calloc(1, sizeof *s);
+    s->N = N; s->q = q;
+    while ((1 << s->logN) < N) s->logN++;
+    ref_gen_bred_constant(q, s->brc);
+    s->qinv = ref_gen_mred_constant(q);
+    s->g = ref_primitive_root(q);
+    s->ninv = ref_mform(ref_modexp(nth >> 1, q - 2, q), q, s->brc);                  /* subring.go:183 */
+    u64 psi = ref_mform(ref_modexp(s->g, (q - 1) / nth, q), q, s->brc);              /* :187 */
+    u64 psiinv = ref_mform(ref_modexp(s->g, q - ((q - 1) / nth) - 1, q), q, s->brc); /* :188 */
+    u64 half = nth >> 1;
+    s->rf = malloc(sizeof(u64) * half); s->rb = malloc(sizeof(u64) * half);
+    s->rf[0] = s->rb[0] = ref_mform(1, q, s->brc);
+    for (u64 j = 1; j < half; j++) {                                                 /* :198-205 */
+        u64 prev = bitrev(j - 1, s->logN + 1), cur = bitrev(j, s->logN + 1);
+        s->rf[cur] = ref_mred(s->rf[prev], psi, q, s->qinv);
+        s->rb[cur] = ref_mred(s->rb[prev], psiinv, q, s->qinv);
+    }
+    return s;
+}
+EXPORT void ref_ci_free(ref_ci *s) { if (s) { free(s->rf); free(s->rb); free(s); } }
+EXPORT void ref_ci_constants(const ref_ci *s, u64 out[6]) {
+    out[0] = s->qinv; out[1] = s->brc[0]; out[2] = s->brc[1]; out[3] = s->g; out[4] = s->ninv; out[5] = (u64)s->logN;
+}
+EXPORT void ref_ci_tables(const ref_ci *s, u64 *rf, u64 *rb) {
+    memcpy(rf, s->rf, sizeof(u64) * 2 * s->N); memcpy(rb, s->rb, sizeof(u64) * 2 * s->N);
+}
+/* nttConjugateInvariantLazy, ntt.go:754-786 (p1 and p2 may alias: the mirrored pair is read before it is written) */
+static void ci_ntt_lazy(const ref_ci *s, const u64 *p1, u64 *p2) {
+    int N = s->N; u64 q = s->q, twoq = 2 * q, fourq = 4 * q;
+    u64 F = s->rf[1];
+    for (int jx = 1, jy = N - 1; jx < (N >> 1); jx++, jy--) {
+        u64 a = p1[jx], b = p1[jy];
+        p2[jx] = a + twoq - ref_mred_lazy(b, F, q, s->qinv);
+        p2[jy] = b + twoq - ref_mred_lazy(a, F, q, s->qinv);
+    }
+    p2[N >> 1] = p1[N >> 1] + twoq - ref_mred_lazy(p1[N >> 1], F, q, s->qinv);
+    p2[0] = p1[0];
+    int t = N;
+    for (int m = 2; m < 2 * N; m <<= 1) {
+        t >>= 1;
+        int h = m >> 1;
+        for (int i = 0, j1 = 0; i < h; i++, j1 += 2 * t) {
+            u64 Fm = s->rf[m + i];
+            for (int j = j1; j < j1 + t; j++) bfly(&p2[j], &p2[j + t], Fm, twoq, fourq, q, s->qinv);
+        }
+    }
+}
+/* inttConjugateInvariantLazy, ntt.go:1104-1158 */
+static void ci_intt_lazy(const ref_ci *s, const u64 *p1, u64 *p2) {
+    int N = s->N; u64 q = s->q, twoq = 2 * q, fourq = 4 * q;
+    if (p1 != p2) memcpy(p2, p1, sizeof(u64) * N);
+    int t = 1, h = N >> 1;
+    for (int i = 0, j1 = 0; i < h; i++, j1 += 2 * t) {
+        u64 F = s->rb[N + i];
+        for (int j = j1; j < j1 + t; j++) ibfly(&p2[j], &p2[j + t], F, twoq, fourq, q, s->qinv);
+    }
+    t <<= 1;
+    for (int m = N >> 1; m > 1; m >>= 1) {
+        h = m >> 1;
+        for (int i = 0, j1 = 0; i < h; i++, j1 += 2 * t) {
+            u64 F = s->rb[m + i];
+            for (int j = j1; j < j1 + t; j++) ibfly(&p2[j], &p2[j + t], F, twoq, fourq, q, s->qinv);
+        }
+        t <<= 1;
+    }
+    u64 F = s->rb[1];
+    for (int jx = 1, jy = N - 1; jx < (N >> 1); jx++, jy--) {
+        u64 a = p2[jx], b = p2[jy];
+        p2[jx] = a + twoq - ref_mred_lazy(b, F, q, s->qinv);
+        p2[jy] = b + twoq - ref_mred_lazy(a, F, q, s->qinv);
+    }
+    p2[N >> 1] = p2[N >> 1] + twoq - ref_mred_lazy(p2[N >> 1], F, q, s->qinv);
+    p2[0] = cred(p2[0] << 1, q);
+}
+/* NTTConjugateInvariant / ...Lazy, ntt.go:716-726 */
+EXPORT void ref_ci_ntt(const ref_ci *s, const u64 *p1, u64 *p2, int lazy) {
+    ci_ntt_lazy(s, p1, p2);
+    if (!lazy) for (int i = 0; i < s->N; i++) p2[i] = ref_bred_add(p2[i], s->q, s->brc);
+}
+/* INTTConjugateInvariant / ...Lazy, ntt.go:728-738 */
+EXPORT void ref_ci_intt(const ref_ci *s, const u64 *p1, u64 *p2, int lazy) {
+    ci_intt_lazy(s, p1, p2);
+    for (int i = 0; i < s->N; i++)
+        p2[i] = lazy ? ref_mred_lazy(p2[i], s->ninv, s->q, s->qinv) : ref_mred(p2[i], s->ninv, s->q, s->qinv);
+}
+
+/* ---------------------------------------------------------------------------
  * element-wise family: ring/vec_ops.go (op codes shared with include/b200ring.h)
  * ------------------------------------------------------------------------- */
 enum {
