@@ -7,7 +7,7 @@ __path__.insert(0, _PKG)
 
 from .capi import lib, B200Error, load_library  # noqa: E402,F401
 from .ring import (  # noqa: E402,F401
-    Type, Standard, ConjugateInvariant, Matrix, Ring, SubRing, Poly, KeySwitcher, NewRing, NewRingFromType, NewRingConjugateInvariant, NewPoly,
+    Type, Standard, ConjugateInvariant, Matrix, Ring, SubRing, Poly, KeySwitcher, NewRing, NewRingFromType, NewRingConjugateInvariant, NewPoly, AutomorphismNTTIndex,
     UnmarshalJSON,
 )
 from . import sharding  # noqa: E402,F401

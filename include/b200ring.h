@@ -239,6 +239,21 @@ B200_API int b200_div_by_last_modulus_ntt(b200_ctx *ctx, const b200_poly *p0, b2
 B200_API int b200_tensor(b200_ctx *ctx, const b200_poly *a0, const b200_poly *a1, const b200_poly *b0, const b200_poly *b1,
                 b200_poly *c0, b200_poly *c1, b200_poly *c2, int level, int mform_first);
 
+/* ---- automorphisms X -> X^gen of power-of-two rings (ring/automorphism.go) -----------------------------------------
+ * b200_automorphism_ntt_index: AutomorphismNTTIndex (:12-35), host only, N words.
+ * b200_automorphism_ntt: Ring.AutomorphismNTT (:38-46), the table computed on the device; with add_lazy != 0 the result is
+ *   added to `out` like AutomorphismNTTWithIndexThenAddLazy (:82-110).  b200_automorphism_ntt_with_index takes the
+ *   caller's table (AutomorphismNTTWithIndex :50-79).  b200_automorphism: Ring.Automorphism (:113-176), coefficient
+ *   domain, Standard and ConjugateInvariant branches.  None of them works in place (the reference says so, :37,:49,:112);
+ *   Matrix rings and out-of-range tables return B200_ESHAPE where the Go code panics.
+ * b200_fold_standard_to_ci: Ring.FoldStandardToConjugateInvariant (ring/conjugate_invariant.go:28-44). */
+B200_API int b200_automorphism_ntt_index(int N, uint64_t NthRoot, uint64_t GalEl, uint64_t *index);
+B200_API int b200_automorphism_ntt(b200_ctx *ctx, const b200_poly *in, uint64_t gen, b200_poly *out, int level, int add_lazy);
+B200_API int b200_automorphism_ntt_with_index(b200_ctx *ctx, const b200_poly *in, const uint64_t *index, size_t n, b200_poly *out,
+                                     int level, int add_lazy);
+B200_API int b200_automorphism(b200_ctx *ctx, const b200_poly *in, uint64_t gen, b200_poly *out, int level);
+B200_API int b200_fold_standard_to_ci(b200_ctx *ctx, const b200_poly *st, const uint64_t *index, size_t n, b200_poly *ci, int level);
+
 /* Ring.UnfoldConjugateInvariantToStandard (ring/conjugate_invariant.go:7-23): limbs 0..level of `ci` (a polynomial of the
  * conjugate-invariant ring `ctx`, N words per limb) into `st`, a polynomial of a ring of degree 2N over the same moduli:
  * st[j] = ci[j], st[2N-1-j] = ci[j]. */

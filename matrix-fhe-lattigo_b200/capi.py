@@ -57,6 +57,11 @@ SYMBOLS = {
     "b200_tensor": (C.c_int, [VP, VP, VP, VP, VP, VP, VP, VP, C.c_int, C.c_int]),
     "b200_polymul": (C.c_int, [VP, VP, VP, VP, C.c_int]),
     "b200_unfold_ci_to_standard": (C.c_int, [VP, VP, VP, C.c_int]),
+    "b200_automorphism_ntt_index": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, P64]),
+    "b200_automorphism_ntt": (C.c_int, [VP, VP, C.c_uint64, VP, C.c_int, C.c_int]),
+    "b200_automorphism_ntt_with_index": (C.c_int, [VP, VP, P64, C.c_size_t, VP, C.c_int, C.c_int]),
+    "b200_automorphism": (C.c_int, [VP, VP, C.c_uint64, VP, C.c_int]),
+    "b200_fold_standard_to_ci": (C.c_int, [VP, VP, P64, C.c_size_t, VP, C.c_int]),
     "b200_transform_host": (C.c_int, [VP, VP, VP, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int]),
     "b200_subring_ntt_host": (C.c_int, [VP, C.c_int, P64, P64, C.c_size_t, C.c_int, C.c_int]),
     "b200_ctx_launch_count": (C.c_uint64, [VP]),

@@ -317,7 +317,7 @@ extern "C" void b200_ctx_destroy(b200_ctx *ctx) {
     cudaSetDevice(ctx->device);
     big_tables_destroy(ctx);
     cudaFree(ctx->d_consts); cudaFree(ctx->d_fwd); cudaFree(ctx->d_inv); cudaFree(ctx->d_misc);
-    cudaFree(ctx->d_go2fast); cudaFree(ctx->d_scratch); cudaFree(ctx->d_ws); cudaFree(ctx->d_rescale);
+    cudaFree(ctx->d_go2fast); cudaFree(ctx->d_scratch); cudaFree(ctx->d_ws); cudaFree(ctx->d_rescale); cudaFree(ctx->d_index);
     if (ctx->pipe.ready) {
         for (int i = 0; i < b200_ctx::HostPipe::NB; ++i) {
             cudaFree(ctx->pipe.buf[i]);
@@ -749,6 +749,96 @@ extern "C" int b200_tensor(b200_ctx *ctx, const b200_poly *a0, const b200_poly *
         return fail(B200_ESHAPE, "b200_tensor: the three outputs must be distinct polynomials");
     CUDA_TRY(cudaSetDevice(ctx->device));
     return launch_tensor(ctx, a0->d, a1->d, b0->d, b1->d, c0->d, c1->d, c2->d, Span{batch, level + 1, ctx->L, 0}, mform_first != 0);
+}
+
+// ---- automorphisms X -> X^gen (ring/automorphism.go) ------------------------------------------------------------
+static u64 ring_nthroot(const b200_ctx *ctx) {
+    return (ctx->ring_type == B200_RING_MATRIX ? 3 : ctx->ring_type == B200_RING_CONJUGATE_INVARIANT ? 4 : 2) * (u64)ctx->N;
+}
+// AutomorphismNTTIndex (:12-35), a pure host function
+extern "C" int b200_automorphism_ntt_index(int N, uint64_t NthRoot, uint64_t GalEl, uint64_t *index) {
+    if (!index) return fail(B200_EINVAL, "b200_automorphism_ntt_index: index is NULL");
+    if (N <= 0 || (N & (N - 1))) return fail(B200_EINVAL, "N must be a power of two");                 // :14-16
+    if (NthRoot == 0 || (NthRoot & (NthRoot - 1))) return fail(B200_EINVAL, "NthRoot must be w power of two");   // :18-20
+    int lognth = 0;
+    while (((u64)1 << (lognth + 1)) < NthRoot) lognth++;
+    const u64 mask = NthRoot - 1;
+    for (int i = 0; i < N; ++i) {
+        const u64 t1 = 2 * hm::bitrev((u64)i, lognth) + 1;
+        index[i] = hm::bitrev((((GalEl * t1) & mask) - 1) >> 1, lognth);
+    }
+    return 0;
+}
+static int stage_index(b200_ctx *ctx, const uint64_t *index, size_t n, size_t need, u64 bound, const char *who, const u64 **d_out) {
+    if (!index || n < need) return fail(B200_ESHAPE, std::string(who) + ": len(index) < N");
+    for (size_t i = 0; i < need; ++i)
+        if (index[i] >= bound) return fail(B200_ESHAPE, std::string(who) + ": index out of range");   // the Go loop panics
+    if (ctx->index_words < need) {
+        CUDA_TRY(cudaStreamSynchronize(b200_cur_stream(ctx)));
+        if (ctx->d_index) CUDA_TRY(cudaFree(ctx->d_index));
+        ctx->d_index = nullptr; ctx->index_words = 0;
+        CUDA_TRY(cudaMalloc(&ctx->d_index, need * sizeof(u64)));
+        ctx->index_words = need;
+    }
+    // stream-ordered after the previous call's kernel; a pageable source is staged before the call returns
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_index, index, need * sizeof(u64), cudaMemcpyHostToDevice, b200_cur_stream(ctx)));
+    *d_out = ctx->d_index;
+    return 0;
+}
+// Ring.AutomorphismNTT (:38-46) with add_lazy == 0, the table computed on the device; add_lazy != 0 accumulates like
+// AutomorphismNTTWithIndexThenAddLazy (:82-110).  Not in place (:37).
+extern "C" int b200_automorphism_ntt(b200_ctx *ctx, const b200_poly *in, uint64_t gen, b200_poly *out, int level, int add_lazy) {
+    CtxLock lk(ctx);
+    int batch;
+    if (int rc = check_polys(ctx, level, "b200_automorphism_ntt", {in, out}, &batch)) return rc;
+    if (ctx->ring_type == B200_RING_MATRIX) return fail(B200_ESHAPE, "N must be a power of two");          // panic(err), :41-43
+    if (in->d == out->d) return fail(B200_ESHAPE, "b200_automorphism_ntt: the result cannot be in-place");
+    const u64 nth = ring_nthroot(ctx);
+    if (ctx->ring_type == B200_RING_CONJUGATE_INVARIANT && (gen & 3) != 1)   // slots >= N of the 2N-point transform: the Go loop indexes out of range
+        return fail(B200_ESHAPE, "b200_automorphism_ntt: index out of range (conjugate-invariant rings need gen = 1 mod 4)");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    return launch_automorphism_ntt(ctx, in->d, out->d, nullptr, gen, nth, ctx->N, ctx->L, batch, level + 1, add_lazy ? 1 : 0);
+}
+// Ring.AutomorphismNTTWithIndex (:50-79) / ...ThenAddLazy (:82-110) with the caller's table
+extern "C" int b200_automorphism_ntt_with_index(b200_ctx *ctx, const b200_poly *in, const uint64_t *index, size_t n, b200_poly *out,
+                                                int level, int add_lazy) {
+    CtxLock lk(ctx);
+    int batch;
+    if (int rc = check_polys(ctx, level, "b200_automorphism_ntt_with_index", {in, out}, &batch)) return rc;
+    if (in->d == out->d) return fail(B200_ESHAPE, "b200_automorphism_ntt_with_index: the result cannot be in-place");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const u64 *d_index;
+    if (int rc = stage_index(ctx, index, n, (size_t)ctx->N, (u64)ctx->N, "b200_automorphism_ntt_with_index", &d_index)) return rc;
+    return launch_automorphism_ntt(ctx, in->d, out->d, d_index, 0, ring_nthroot(ctx), ctx->N, ctx->L, batch, level + 1, add_lazy ? 1 : 0);
+}
+// Ring.Automorphism (:113-176), coefficient domain; not in place
+extern "C" int b200_automorphism(b200_ctx *ctx, const b200_poly *in, uint64_t gen, b200_poly *out, int level) {
+    CtxLock lk(ctx);
+    int batch;
+    if (int rc = check_polys(ctx, level, "b200_automorphism", {in, out}, &batch)) return rc;
+    if (ctx->ring_type == B200_RING_MATRIX) return fail(B200_ESHAPE, "b200_automorphism: N must be a power of two");
+    if (in->d == out->d) return fail(B200_ESHAPE, "b200_automorphism: the result cannot be in-place");
+    if (!(gen & 1)) return fail(B200_ESHAPE, "b200_automorphism: gen must be odd");   // an even gen is not a permutation: racing writes
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    return launch_automorphism_coeff(ctx, in->d, out->d, gen, batch, level + 1);
+}
+// Ring.FoldStandardToConjugateInvariant (ring/conjugate_invariant.go:28-44): ctx is the conjugate-invariant ring (degree N),
+// st a polynomial of a ring of degree 2N over the same moduli, index the table permuteNTTIndexInv (N entries < 2N):
+// ci[j] = st[index[j]] + st[j] mod q.
+extern "C" int b200_fold_standard_to_ci(b200_ctx *ctx, const b200_poly *st, const uint64_t *index, size_t n, b200_poly *ci, int level) {
+    CtxLock lk(ctx);
+    if (!ctx || !ci || !st || ci->ctx != ctx || !st->ctx) return fail(B200_EINVAL, "b200_fold_standard_to_ci: NULL argument or foreign polynomial");
+    if (st->ctx->N != 2 * ctx->N)   // :31-33 (panic)
+        return fail(B200_ESHAPE, "cannot FoldStandardToConjugateInvariant: Ring degree of polyStandard must be 2N and ring degree of polyConjugateInvariant must be N");
+    if (level < 0 || level >= ctx->L || level >= st->ctx->L) return fail(B200_ESHAPE, "b200_fold_standard_to_ci: level out of range");
+    if (ci->batch != st->batch) return fail(B200_ESHAPE, "b200_fold_standard_to_ci: batch sizes differ");
+    if (ci->ctx->device != st->ctx->device) return fail(B200_ESHAPE, "b200_fold_standard_to_ci: polynomials live on different devices");
+    for (int i = 0; i <= level; ++i)
+        if (ctx->sub[i].q != st->ctx->sub[i].q) return fail(B200_ESHAPE, "b200_fold_standard_to_ci: the rings do not share their moduli");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const u64 *d_index;
+    if (int rc = stage_index(ctx, index, n, (size_t)ctx->N, 2 * (u64)ctx->N, "b200_fold_standard_to_ci", &d_index)) return rc;
+    return launch_automorphism_ntt(ctx, st->d, ci->d, d_index, 0, 4 * (u64)ctx->N, st->ctx->N, st->ctx->L, ci->batch, level + 1, 2);
 }
 
 // Ring.UnfoldConjugateInvariantToStandard (ring/conjugate_invariant.go:7-23): limbs 0..level of a polynomial of a

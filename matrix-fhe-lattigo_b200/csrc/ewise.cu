@@ -165,6 +165,60 @@ k_ci_unfold(const u64 *in, u64 *out, int N, int Lin, int Lout, int nl) {
     }
 }
 
+// Automorphisms of power-of-two rings (ring/automorphism.go).  NTT domain: a gather through the table of
+// AutomorphismNTTIndex (:12-35), computed on the fly when no table is given:
+//   index[i] = brev(((gen*(2*brev(i)+1) & (NthRoot-1)) - 1) >> 1)      (brev over log2(NthRoot)-1 bits)
+// mode 0: out[j] = in[index[j]]  (AutomorphismNTTWithIndex :50-79);  mode 1: out[j] += in[index[j]]  (...ThenAddLazy :82-110);
+// mode 2: out[j] = in[index[j]] + in[j] mod q  (FoldStandardToConjugateInvariant, conjugate_invariant.go:28-44: `in` is a
+// polynomial of the standard ring of degree 2N, `out` one of the conjugate-invariant ring of degree N).
+struct AutoArgs {
+    const u64 *index;      // device table or nullptr
+    u64 gen, mask;
+    int lognth;
+    int n_out, n_in, l_out, l_in, nl, mode;
+};
+__device__ __forceinline__ unsigned brev_bits(unsigned x, int bits) { return bits ? (__brev(x) >> (32 - bits)) : 0u; }
+__global__ void __launch_bounds__(256)
+k_automorphism_ntt(const u64 *in, u64 *out, const LimbConst *__restrict__ consts, AutoArgs a, int unit0) {
+    const int unit = unit0 + blockIdx.y, limb = unit % a.nl, b = unit / a.nl;
+    const u64 *y = in + ((size_t)b * a.l_in + limb) * (size_t)a.n_in;
+    u64 *z = out + ((size_t)b * a.l_out + limb) * (size_t)a.n_out;
+    const u64 q = consts[limb].q;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < a.n_out; j += gridDim.x * blockDim.x) {
+        u64 x;
+        if (a.index) x = a.index[j];
+        else {
+            const u64 t1 = 2 * (u64)brev_bits((unsigned)j, a.lognth) + 1;
+            const u64 t2 = (((a.gen * t1) & a.mask) - 1) >> 1;
+            x = brev_bits((unsigned)t2, a.lognth);
+        }
+        const u64 v = y[x];
+        if (a.mode == 0) z[j] = v;
+        else if (a.mode == 1) z[j] += v;
+        else z[j] = csub(v + y[j], q);
+    }
+}
+// Coefficient domain, Ring.Automorphism (:113-176): out[(i*gen) mod N] = +-in[i]; the conjugate-invariant branch
+// (:124-151) walks the 2N exponents of the unfolded polynomial.  A negated zero is written as q, like the Go expression.
+__global__ void __launch_bounds__(256)
+k_automorphism_coeff(const u64 *in, u64 *out, const LimbConst *__restrict__ consts, int N, int L, int nl, u64 gen, int ci, int unit0) {
+    const int unit = unit0 + blockIdx.y, limb = unit % nl, b = unit / nl;
+    const size_t base = ((size_t)b * L + limb) * (size_t)N;
+    const u64 q = consts[limb].q, n = (u64)N;
+    const u64 span = ci ? 2 * n : n, mask = span - 1;
+    const int logn = 64 - __clzll(mask);                                   // bits.Len64(mask)
+    for (u64 i = blockIdx.x * blockDim.x + threadIdx.x; i < span; i += (u64)gridDim.x * blockDim.x) {
+        const u64 raw = i * gen, index = raw & mask;
+        u64 tmp = (raw >> logn) & 1, idx = i;
+        if (ci) {
+            if (index >= n) continue;
+            if (idx >= n) { idx = 2 * n - idx; tmp ^= 1; }
+        }
+        const u64 v = in[base + idx];
+        out[base + index] = tmp ? q - v : v;
+    }
+}
+
 // Rescale helper (ring/scaling.go:137-143): x = coefficient-domain last limb [0, q_l); for every lower limb i
 // t_i = (x (+ pHalf mod q_l)) + (q_i - pHalf mod q_i), reduced to [0, q_i).  ws is a [batch][Lbuf][N] buffer whose
 // limb `level` holds x; limbs 0..level-1 receive t_i.
@@ -206,6 +260,39 @@ int launch_ci_unfold(b200_ctx *ctx, const u64 *in, u64 *out, int N, int batch, i
     if ((long long)batch * nl > 65535) { b200_set_error("b200_unfold_ci_to_standard: more than 65535 limb units"); return B200_ESHAPE; }
     LaunchScope ls(ctx, "ci_unfold", (long long)batch * nl);
     k_ci_unfold<<<dim3(chunks, batch * nl), 256, 0, b200_cur_stream(ctx)>>>(in, out, N, Lin, Lout, nl);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int launch_automorphism_ntt(b200_ctx *ctx, const u64 *in, u64 *out, const u64 *d_index, u64 gen, u64 nthroot, int n_in, int l_in,
+                            int batch, int nl, int mode) {
+    AutoArgs a{};
+    a.index = d_index; a.gen = gen; a.mask = nthroot - 1;
+    a.lognth = 0;
+    while (((u64)1 << (a.lognth + 1)) < nthroot) a.lognth++;
+    a.n_out = ctx->N; a.n_in = n_in; a.l_out = ctx->L; a.l_in = l_in; a.nl = nl; a.mode = mode;
+    int chunks = (ctx->N + 255) / 256;
+    if (chunks > 512) chunks = 512;
+    const int units = batch * nl;
+    for (int u0 = 0; u0 < units; u0 += 65535) {
+        const int nu = units - u0 < 65535 ? units - u0 : 65535;
+        LaunchScope ls(ctx, "automorphism_ntt", nu);
+        k_automorphism_ntt<<<dim3(chunks, nu), 256, 0, b200_cur_stream(ctx)>>>(in, out, ctx->d_consts, a, u0);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int launch_automorphism_coeff(b200_ctx *ctx, const u64 *in, u64 *out, u64 gen, int batch, int nl) {
+    const int ci = ctx->ring_type == B200_RING_CONJUGATE_INVARIANT ? 1 : 0;
+    int chunks = ((ci ? 2 : 1) * ctx->N + 255) / 256;
+    if (chunks > 512) chunks = 512;
+    const int units = batch * nl;
+    for (int u0 = 0; u0 < units; u0 += 65535) {
+        const int nu = units - u0 < 65535 ? units - u0 : 65535;
+        LaunchScope ls(ctx, "automorphism", nu);
+        k_automorphism_coeff<<<dim3(chunks, nu), 256, 0, b200_cur_stream(ctx)>>>(in, out, ctx->d_consts, ctx->N, ctx->L, nl, gen, ci, u0);
+    }
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

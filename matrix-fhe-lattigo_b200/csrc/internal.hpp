@@ -47,6 +47,8 @@ struct b200_ctx {
     size_t ws_words = 0;
     std::vector<u64> rescale;        // RescaleConstants[level-1][i] (ring.go:361-379), row-major [L-1][L], Montgomery form
     u64 *d_rescale = nullptr;        // the same table on the device
+    u64 *d_index = nullptr;          // staging for caller-supplied automorphism tables (AutomorphismNTTWithIndex)
+    size_t index_words = 0;
     std::atomic<uint64_t> launches{0};
     // Ring/SubRing are "thread safe" in the reference (ring/ring.go:192-194): goroutines may call the same ring
     // concurrently.  Every compute entry point holds this lock while it enqueues, so the launches of one call
@@ -143,5 +145,10 @@ int launch_ntt_big(b200_ctx *ctx, const u64 *in, u64 *out, Span sp, bool inverse
 // otherwise, plus the folding layer of conjugate-invariant rings (ring/ntt.go:754-786,1104-1158)
 int launch_ntt(b200_ctx *ctx, const u64 *in, u64 *out, Span sp, bool inverse, int flags);
 int launch_ci_fold(b200_ctx *ctx, const u64 *in, u64 *out, Span sp, bool inverse);
+// ring/automorphism.go: NTT-domain gather (mode 0 assign, 1 add, 2 fold standard -> conjugate-invariant) and the
+// coefficient-domain permutation with sign
+int launch_automorphism_ntt(b200_ctx *ctx, const u64 *in, u64 *out, const u64 *d_index, u64 gen, u64 nthroot, int n_in, int l_in,
+                            int batch, int nl, int mode);
+int launch_automorphism_coeff(b200_ctx *ctx, const u64 *in, u64 *out, u64 gen, int batch, int nl);
 int launch_ci_unfold(b200_ctx *ctx, const u64 *in, u64 *out, int N, int batch, int nl, int Lin, int Lout);
 int launch_polymul_big(b200_ctx *ctx, const u64 *a, const u64 *b, u64 *c, Span sp);

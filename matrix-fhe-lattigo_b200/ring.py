@@ -268,6 +268,30 @@ class Ring:
             raise ValueError("cannot StandardRing: the ring is not a conjugate-invariant ring")
         return NewRingFromType(self._N << 1, self._moduli[: self.level + 1], Standard, self.device)
 
+    # -- automorphisms X -> X^gen (ring/automorphism.go); none of them works in place --
+    def AutomorphismNTT(self, polIn, gen, polOut):
+        check(lib().b200_automorphism_ntt(self._ctx.h, polIn.h, int(gen) % (1 << 64), polOut.h, self.level, 0))
+
+    def _auto_index(self, polIn, index, polOut, add):
+        idx = _u64_array(index)
+        check(lib().b200_automorphism_ntt_with_index(self._ctx.h, polIn.h, idx.ctypes.data_as(capi.P64), len(idx), polOut.h,
+                                                     self.level, add))
+
+    def AutomorphismNTTWithIndex(self, polIn, index, polOut):
+        self._auto_index(polIn, index, polOut, 0)
+
+    def AutomorphismNTTWithIndexThenAddLazy(self, polIn, index, polOut):
+        self._auto_index(polIn, index, polOut, 1)
+
+    def Automorphism(self, polIn, gen, polOut):
+        check(lib().b200_automorphism(self._ctx.h, polIn.h, int(gen) % (1 << 64), polOut.h, self.level))
+
+    def FoldStandardToConjugateInvariant(self, polyStandard, permuteNTTIndexInv, polyConjugateInvariant):
+        """ring/conjugate_invariant.go:28-44 (the receiver is the conjugate-invariant ring)."""
+        idx = _u64_array(permuteNTTIndexInv)
+        check(lib().b200_fold_standard_to_ci(self._ctx.h, polyStandard.h, idx.ctypes.data_as(capi.P64), len(idx),
+                                             polyConjugateInvariant.h, self.level))
+
     def UnfoldConjugateInvariantToStandard(self, polyConjugateInvariant, polyStandard):
         """ring/conjugate_invariant.go:7-23 (the receiver is the conjugate-invariant ring)."""
         check(lib().b200_unfold_ci_to_standard(self._ctx.h, polyConjugateInvariant.h, polyStandard.h, self.level))
@@ -534,6 +558,16 @@ def NewRingFromType(N, Moduli, ringType, device=0, roots=None):
     moduli = [int(q) for q in Moduli]
     ctx = _Context(ringType, N, moduli, roots, device)
     return Ring(ctx, ringType, N, moduli, len(moduli) - 1, device)
+
+
+def AutomorphismNTTIndex(N, NthRoot, GalEl):
+    """ring.AutomorphismNTTIndex (ring/automorphism.go:12-35); raises ValueError where Go returns an error."""
+    out = np.empty(max(N, 0), dtype=np.uint64)
+    rc = lib().b200_automorphism_ntt_index(N, int(NthRoot) % (1 << 64), int(GalEl) % (1 << 64), out.ctypes.data_as(capi.P64))
+    if rc == -1:
+        raise ValueError(lib().b200_last_error().decode())
+    check(rc)
+    return out
 
 
 def NewRingConjugateInvariant(N, Moduli, device=0, roots=None):

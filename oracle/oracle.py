@@ -72,6 +72,8 @@ def lib():
             "ref_ci_tables": (None, [C.c_void_p, P64, P64]),
             "ref_ci_ntt": (None, [C.c_void_p, P64, P64, C.c_int]),
             "ref_ci_intt": (None, [C.c_void_p, P64, P64, C.c_int]),
+            "ref_automorphism_ntt_index": (C.c_int, [C.c_int, u64, u64, P64]),
+            "ref_automorphism": (None, [C.c_int, u64, C.c_int, u64, P64, P64]),
             "ref_vec_op": (C.c_int, [C.c_int, C.c_int, u64, P64, P64, P64, u64]),
             "ref_3n_exponents": (C.c_int, [C.c_int, PI]),
             "ref_3n_forward_horner": (None, [C.c_int, u64, u64, P64, P64]),
@@ -176,6 +178,22 @@ class Pow2SubRing:
         if getattr(self, "h", None) and _lib is not None:
             _lib.ref_pow2_free(self.h)
             self.h = None
+
+
+def automorphism_ntt_index(N, nthroot, galel):
+    """ring.AutomorphismNTTIndex (ring/automorphism.go:12-35)."""
+    out = np.empty(N, dtype=np.uint64)
+    if lib().ref_automorphism_ntt_index(N, nthroot, galel % (1 << 64), _p(out)):
+        raise ValueError("N and NthRoot must be powers of two")
+    return out
+
+
+def automorphism(N, q, gen, p, conjugate_invariant=False):
+    """Ring.Automorphism on one limb, coefficient domain (ring/automorphism.go:113-176).  Not in place."""
+    p = _arr(p)
+    out = np.zeros_like(p)
+    lib().ref_automorphism(N, q, int(conjugate_invariant), gen % (1 << 64), _p(p), _p(out))
+    return out
 
 
 class ConjugateInvariantSubRing:

@@ -456,6 +456,47 @@ EXPORT void ref_ci_intt(const ref_ci *s, const u64 *p1, u64 *p2, int lazy) {
 }
 
 /* ---------------------------------------------------------------------------
+ * automorphisms X -> X^gen of power-of-two rings: ring/automorphism.go
+ * ------------------------------------------------------------------------- */
+/* AutomorphismNTTIndex, automorphism.go:12-35.  Returns 0, or -1 if N or NthRoot is not a power of two. */
+EXPORT int ref_automorphism_ntt_index(int N, u64 nthroot, u64 galel, u64 *index) {
+    if (N <= 0 || (N & (N - 1)) || nthroot == 0 || (nthroot & (nthroot - 1))) return -1;
+    int lognth = 0;
+    while (((u64)1 << (lognth + 1)) < nthroot) lognth++;          /* bits.Len64(NthRoot-1) - 1 */
+    u64 mask = nthroot - 1;
+    for (int i = 0; i < N; i++) {
+        u64 tmp1 = 2 * bitrev((u64)i, lognth) + 1;
+        u64 tmp2 = (((galel * tmp1) & mask) - 1) >> 1;
+        index[i] = bitrev(tmp2, lognth);
+    }
+    return 0;
+}
+/* Ring.Automorphism on one limb, automorphism.go:113-176 (ci != 0: the conjugate-invariant branch :124-151).  A negated
+ * zero coefficient is written as q, exactly like the Go expression. */
+EXPORT void ref_automorphism(int N, u64 q, int ci, u64 gen, const u64 *in, u64 *out) {
+    u64 n = (u64)N;
+    if (ci) {
+        u64 mask = 2 * n - 1;
+        int logn = 0; while (((u64)1 << logn) <= mask) logn++;    /* bits.Len64(mask) */
+        for (u64 i = 0; i < 2 * n; i++) {
+            u64 raw = i * gen, index = raw & mask, tmp = (raw >> logn) & 1;
+            if (index < n) {
+                u64 idx = i;
+                if (idx >= n) { idx = 2 * n - idx; tmp ^= 1; }
+                out[index] = (in[idx] * (tmp ^ 1)) | ((q - in[idx]) * tmp);
+            }
+        }
+    } else {
+        u64 mask = n - 1;
+        int logn = 0; while (((u64)1 << logn) <= mask) logn++;
+        for (u64 i = 0; i < n; i++) {
+            u64 raw = i * gen, index = raw & mask, tmp = (raw >> logn) & 1;
+            out[index] = (in[i] * (tmp ^ 1)) | ((q - in[i]) * tmp);
+        }
+    }
+}
+
+/* ---------------------------------------------------------------------------
  * element-wise family: ring/vec_ops.go (op codes shared with include/b200ring.h)
  * ------------------------------------------------------------------------- */
 enum {
