@@ -80,8 +80,11 @@ k_basis_extend(const u64 *src, u64 *dst, const LimbConst *__restrict__ consts, E
 #define B200_EXT_CPT 2
 #endif
 constexpr int EXT_CPT = B200_EXT_CPT;   // coefficients per thread
+#ifndef B200_EXT_MINB
+#define B200_EXT_MINB 5                 // CTAs per SM the register allocation must allow (128-thread CTAs; measured 1..8 on B200: 5 is 4 % faster than 1)
+#endif
 template <int NS>
-__global__ void __launch_bounds__(EXT_THREADS)
+__global__ void __launch_bounds__(EXT_THREADS, B200_EXT_MINB)
 k_basis_extend_ns(const u64 *src, u64 *dst, const LimbConst *__restrict__ consts, ExtDesc d, int N, int Lbuf, int mode) {
     extern __shared__ __align__(16) u64 csm[];
     // layout: src: q[NS] qinv[NS] half[NS] qinvqi[NS] qd[NS] | per target: q qinv sub k[NS] vq[NS+1]
@@ -159,8 +162,8 @@ k_basis_extend_ns(const u64 *src, u64 *dst, const LimbConst *__restrict__ consts
                 rlo += sb; rhi += (S1b[e] >> 32) + (rlo < sb);
             }
             u64 r = rhi - __umul64hi(rlo * qinv, q) + q + t[3 + NS + v[e]];   // [0, 3p)
-            r = csub(r + q - sub, q);                                           // SubScalar
-            if (mode == 1) r = csub(csub(r, 2 * q), q);
+            if (mode == 1) r = csub(csub(r + q - sub, 2 * q), q);               // the same residue, canonical: [0,4p) -> [0,p)
+            else r = csub(r + q - sub, q);                                      // SubScalar, the lazy word Go leaves
             if (live[e]) oj[x0 + e * EXT_THREADS] = r;
         }
     }
@@ -194,12 +197,24 @@ struct MacGroup {
     const u64 *k0[MAC_DIGITS], *k1[MAC_DIGITS];
     int st[MAC_DIGITS], ed[MAC_DIGITS];    // the digit's own limbs read the input itself
 };
+__device__ __forceinline__ void mac128(u64 &lo, u64 &hi, u64 x, u64 y) {
+    const u64 pl = x * y;
+    lo += pl;
+    hi += __umul64hi(x, y) + (lo < pl);
+}
+// a (canonical) + (hi:lo) * 2^-64 mod q, canonical; hi < q
+__device__ __forceinline__ u64 fold128(u64 a, u64 lo, u64 hi, u64 q, u64 qinv) {
+    const u64 r = hi - __umul64hi(lo * qinv, q) + q;     // MRedLazy of the 128-bit sum: [0, 2q)
+    return csub(csub(a + r, 2 * q), q);
+}
 template <int ND>
 __global__ void __launch_bounds__(256)
 k_gadget_mac_group(const u64 *cx, MacGroup m, u64 *acc0, u64 *acc1, const LimbConst *__restrict__ consts, const int *limbs,
                    int nlimbs, int N, int Lbuf, int first) {
-    const int unit = blockIdx.y;
-    const int b = unit / nlimbs, limb = limbs[unit % nlimbs];
+    // limb-major units: the polynomials of the batch that share a key limb run back to back, so the 2*ND key limbs
+    // they all read (the larger half of the traffic) are served from L2 after the first one
+    const int unit = blockIdx.y, batch = gridDim.y / nlimbs;
+    const int b = unit % batch, limb = limbs[unit / batch];
     const LimbConst c = consts[limb];
     const size_t base = ((size_t)b * Lbuf + limb) * (size_t)N, kbase = (size_t)limb * N;
     const u64 *op[ND];
@@ -211,16 +226,24 @@ k_gadget_mac_group(const u64 *cx, MacGroup m, u64 *acc0, u64 *acc1, const LimbCo
             a0 = *reinterpret_cast<const ulonglong2 *>(acc0 + base + i);
             a1 = *reinterpret_cast<const ulonglong2 *>(acc1 + base + i);
         }
+        // The ND products of one word are summed as 128-bit integers and reduced ONCE: sum < ND*q^2 < q*2^64 for
+        // ND <= 4 and q < 2^61, so one Montgomery reduction returns the same residue as the ND reduced products of
+        // MulCoeffsMontgomery[Lazy]ThenAdd[Lazy] (evaluator_gadget_product.go:160-176) at half the multiplications.
+        u64 lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
 #pragma unroll
         for (int g = 0; g < ND; ++g) {
             const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(op[g] + base + i);
             const ulonglong2 x0 = *reinterpret_cast<const ulonglong2 *>(m.k0[g] + kbase + i);
             const ulonglong2 x1 = *reinterpret_cast<const ulonglong2 *>(m.k1[g] + kbase + i);
-            a0.x = csub(a0.x + mred(x0.x, v.x, c.q, c.qinv), c.q);
-            a0.y = csub(a0.y + mred(x0.y, v.y, c.q, c.qinv), c.q);
-            a1.x = csub(a1.x + mred(x1.x, v.x, c.q, c.qinv), c.q);
-            a1.y = csub(a1.y + mred(x1.y, v.y, c.q, c.qinv), c.q);
+            mac128(lo[0], hi[0], x0.x, v.x);
+            mac128(lo[1], hi[1], x0.y, v.y);
+            mac128(lo[2], hi[2], x1.x, v.x);
+            mac128(lo[3], hi[3], x1.y, v.y);
         }
+        a0.x = fold128(a0.x, lo[0], hi[0], c.q, c.qinv);
+        a0.y = fold128(a0.y, lo[1], hi[1], c.q, c.qinv);
+        a1.x = fold128(a1.x, lo[2], hi[2], c.q, c.qinv);
+        a1.y = fold128(a1.y, lo[3], hi[3], c.q, c.qinv);
         *reinterpret_cast<ulonglong2 *>(acc0 + base + i) = a0;
         *reinterpret_cast<ulonglong2 *>(acc1 + base + i) = a1;
     }
