@@ -203,6 +203,12 @@ B200_API int b200_mod_down_ntt(b200_keyswitch *ks, int levelQ, int levelP, const
  * (GadgetCiphertext.Value[digit][0][component]), beta = (levelQ+levelP+1)/(levelP+1).  ct0, ct1: batch B, canonical. */
 B200_API int b200_gadget_product(b200_keyswitch *ks, int levelQ, int levelP, const b200_poly *cx, const b200_poly *key,
                         b200_poly *ct0, b200_poly *ct1);
+/* The same for a gadget ciphertext with a power-of-two base (BaseTwoDecomposition = pw2 > 0, which the reference allows with
+ * one special prime only, core/rlwe/params.go:615-632): gadgetProductSinglePAndBitDecompLazy with mask != 0
+ * (evaluator_gadget_product.go:190-320) + ModDown.  sizes[i] = len(gadgetCt.Value[i]) for i <= levelQ; `key` holds
+ * 2*sum(sizes) polynomials ordered [limb i][window j][component].  pw2 == 0 forwards to b200_gadget_product. */
+B200_API int b200_gadget_product_bit_decomp(b200_keyswitch *ks, int levelQ, int levelP, int pw2, const int *sizes, const b200_poly *cx,
+                                   const b200_poly *key, b200_poly *ct0, b200_poly *ct1);
 
 /* Ciphertext x ciphertext multiply with relinearisation, NTT domain in and out (BASELINE config 5):
  * (c0, c1, c2) = tensor(a, b) as b200_tensor, then (out0, out1) = (c0, c1) + GadgetProduct(c2, rlk)

@@ -187,6 +187,22 @@ k_decompose_single(const u64 *src, u64 *dst, const LimbConst *__restrict__ const
     }
 }
 
+// Power-of-two digit of gadgetProductSinglePAndBitDecompLazy (evaluator_gadget_product.go:232-235, ring.MaskVec
+// vec_ops.go:870-890): cw = (cxInvNTT[src_limb] >> w) & mask, the same small integer for every limb it is transformed
+// under (:241-246,:252-257); written reduced, which is the identity whenever 2^pw2 <= q.
+__global__ void __launch_bounds__(256)
+k_mask_spread(const u64 *src, u64 *dst, const LimbConst *__restrict__ consts, int src_limb, const int *dst_limb, int nt,
+              int N, int Lbuf, int w, u64 mask) {
+    const int b = blockIdx.y;
+    const int x = blockIdx.x * 256 + threadIdx.x;
+    if (x >= N) return;
+    const u64 v = (src[((size_t)b * Lbuf + src_limb) * N + x] >> w) & mask;
+    for (int j = 0; j < nt; ++j) {
+        const LimbConst c = consts[dst_limb[j]];
+        dst[((size_t)b * Lbuf + dst_limb[j]) * N + x] = bred_add(v, c.q, c.brc_hi);
+    }
+}
+
 // acc_c[x] (+)= MRed(key[d][c][x], operand[x]) for both components; the operand of the digit's own limbs is the
 // NTT-domain input itself (rlwe/evaluator_gadget_product.go:466-472), all others come from the decomposition.
 // Up to MAC_DIGITS digits per pass: the accumulators are read (unless `first`) and written once for the whole group
@@ -494,6 +510,62 @@ int decompose_mac(b200_keyswitch *ks, int levelQ, int levelP, const u64 *cx, con
     return rc;
 }
 
+// Digit loop of gadgetProductSinglePAndBitDecompLazy (:190-320) with a power-of-two base (mask != 0): for every Q limb i
+// and every window j < sizes[i], the window of the coefficient-domain limb is spread over all limbs of QP, transformed and
+// multiply-accumulated with key[i][j][c].  No basis extension.  The key holds 2 * sum(sizes) polynomials ordered [i][j][c].
+int bitdecomp_mac(b200_keyswitch *ks, int levelQ, int levelP, int pw2, const int *sizes, const u64 *cxinv, const u64 *key,
+                  u64 *c2, u64 *acc0, u64 *acc1, int B) {
+    b200_ctx *ctx = ks->ctx;
+    const int LQ = ks->LQ, N = ctx->N;
+    std::vector<int> limbs = range(0, levelQ + 1);
+    for (int j = 0; j <= levelP; ++j) limbs.push_back(LQ + j);
+    int *&d_limbs = ks->limb_lists[((0 * 64 + (levelQ + 1)) * 64 + 0) * 64 + (levelP + 1)];
+    if (!d_limbs) {
+        cudaError_t ce = upload(&d_limbs, limbs);
+        if (ce != cudaSuccess) return b200_cuda_fail(ce, "gadget product limb list");
+    }
+    const u64 mask = pw2 >= 64 ? ~0ULL : ((1ULL << pw2) - 1);
+    const size_t words = (size_t)B * ctx->L * N;
+    const int nl = (int)limbs.size();
+    std::vector<std::pair<int, int>> digits;
+    for (int i = 0; i <= levelQ; ++i)
+        for (int j = 0; j < sizes[i]; ++j) digits.push_back({i, j});
+    int rc = 0;
+    for (size_t d0 = 0; d0 < digits.size() && rc == 0; d0 += MAC_DIGITS) {
+        const int nd = (int)std::min<size_t>(MAC_DIGITS, digits.size() - d0);
+        MacGroup mg{};
+        for (int g = 0; g < nd && rc == 0; ++g) {
+            const int i = digits[d0 + g].first, j = digits[d0 + g].second;
+            u64 *c2d = c2 + (size_t)g * words;
+            {
+                LaunchScope ls(ctx, "mask_spread", (long long)B * nl);
+                k_mask_spread<<<dim3((N + 255) / 256, B), 256, 0, b200_cur_stream(ctx)>>>(cxinv, c2d, ctx->d_consts, i, d_limbs, nl, N, ctx->L, j * pw2, mask);
+            }
+            if ((rc = ntt_range(ctx, c2d, c2d, B, 0, levelQ + 1, false))) break;
+            if ((rc = ntt_range(ctx, c2d, c2d, B, LQ, levelP + 1, false))) break;
+            mg.op[g] = c2d;
+            mg.k0[g] = key + (size_t)(2 * (d0 + g)) * ctx->L * N;
+            mg.k1[g] = key + (size_t)(2 * (d0 + g) + 1) * ctx->L * N;
+            mg.st[g] = mg.ed[g] = 0;   // no limb reads the input itself
+        }
+        if (rc) break;
+        int chunks = (N / 2 + 255) / 256;
+        if (chunks > 128) chunks = 128;
+        const dim3 grid(chunks, B * nl);
+        LaunchScope ls(ctx, "gadget_mac", (long long)B * nl * nd);
+        cudaStream_t st_ = b200_cur_stream(ctx);
+        const int first = d0 == 0;
+        switch (nd) {
+        case 1: k_gadget_mac_group<1><<<grid, 256, 0, st_>>>(cxinv, mg, acc0, acc1, ctx->d_consts, d_limbs, nl, N, ctx->L, first); break;
+        case 2: k_gadget_mac_group<2><<<grid, 256, 0, st_>>>(cxinv, mg, acc0, acc1, ctx->d_consts, d_limbs, nl, N, ctx->L, first); break;
+        case 3: k_gadget_mac_group<3><<<grid, 256, 0, st_>>>(cxinv, mg, acc0, acc1, ctx->d_consts, d_limbs, nl, N, ctx->L, first); break;
+        default: k_gadget_mac_group<4><<<grid, 256, 0, st_>>>(cxinv, mg, acc0, acc1, ctx->d_consts, d_limbs, nl, N, ctx->L, first); break;
+        }
+        CUDA_TRY(cudaGetLastError());
+    }
+    return rc;
+}
+
 int check_own(const b200_keyswitch *ks, int levelQ, int levelP, Own o, const char *who) {
     if (o.q0 < 0 || o.q1 > levelQ + 1 || o.q0 > o.q1 || o.p0 < 0 || o.p1 > levelP + 1 || o.p0 > o.p1) {
         b200_set_error(std::string(who) + ": owned limb ranges out of bounds");
@@ -564,14 +636,15 @@ extern "C" int b200_mod_down_ntt(b200_keyswitch *ks, int levelQ, int levelP, con
     return mod_down_ntt(ks, levelQ, levelP, p1->d, p2->d, ks->ws, p1->batch);
 }
 
-// rlwe.Evaluator.GadgetProduct (NTT-domain operands, levelP >= 1): evaluator_gadget_product.go:16-30,123-188,455-478
+// rlwe.Evaluator.GadgetProduct (NTT-domain operands): evaluator_gadget_product.go:16-30,123-188,455-478.  With one special
+// prime (levelP == 0) the reference takes gadgetProductSinglePAndBitDecompLazy (:190-320) with mask == 0, which is the same
+// digit loop with one-limb digits (DecomposeAndSplit with nbPi = 1, :213-215) and gives the same canonical result.
 extern "C" int b200_gadget_product(b200_keyswitch *ks, int levelQ, int levelP, const b200_poly *cx, const b200_poly *key,
                                    b200_poly *ct0, b200_poly *ct1) {
     CtxLock lk(ks ? ks->ctx : nullptr);
     if (int rc = check_levels(ks, levelQ, levelP, "b200_gadget_product")) return rc;
     for (const b200_poly *p : {cx, key, (const b200_poly *)ct0, (const b200_poly *)ct1})
         if (int rc = check_poly(ks, p, "b200_gadget_product")) return rc;
-    if (levelP < 1) { b200_set_error("b200_gadget_product: the single-special-prime / bit-decomposition variant is not implemented"); return B200_EINVAL; }
     b200_ctx *ctx = ks->ctx;
     const int beta = (levelQ + levelP + 1) / (levelP + 1), B = cx->batch, N = ctx->N;
     if (key->batch < 2 * beta) { b200_set_error("b200_gadget_product: the key must hold 2*beta polynomials [digit][component]"); return B200_ESHAPE; }
@@ -588,6 +661,40 @@ extern "C" int b200_gadget_product(b200_keyswitch *ks, int levelQ, int levelP, c
     return mod_down_ntt(ks, levelQ, levelP, acc1, ct1->d, c2, B);
 }
 
+// rlwe.Evaluator.GadgetProduct for a gadget ciphertext with a power-of-two base (BaseTwoDecomposition = pw2 > 0, one
+// special prime): gadgetProductSinglePAndBitDecompLazy (evaluator_gadget_product.go:190-320) followed by ModDown (:33-45).
+// sizes[i] = BaseTwoDecompositionVectorSize()[i] = len(gadgetCt.Value[i]) for i <= levelQ; the key holds
+// 2 * sum(sizes) polynomials ordered [i][j][component].  pw2 == 0 is b200_gadget_product.
+extern "C" int b200_gadget_product_bit_decomp(b200_keyswitch *ks, int levelQ, int levelP, int pw2, const int *sizes, const b200_poly *cx,
+                                              const b200_poly *key, b200_poly *ct0, b200_poly *ct1) {
+    if (pw2 == 0) return b200_gadget_product(ks, levelQ, levelP, cx, key, ct0, ct1);
+    CtxLock lk(ks ? ks->ctx : nullptr);
+    if (int rc = check_levels(ks, levelQ, levelP, "b200_gadget_product_bit_decomp")) return rc;
+    for (const b200_poly *p : {cx, key, (const b200_poly *)ct0, (const b200_poly *)ct1})
+        if (int rc = check_poly(ks, p, "b200_gadget_product_bit_decomp")) return rc;
+    if (levelP != 0) { b200_set_error("b200_gadget_product_bit_decomp: a power-of-two base needs exactly one special prime (levelP == 0, rlwe/params.go:621)"); return B200_EINVAL; }
+    if (pw2 < 0 || pw2 > 60 || !sizes) { b200_set_error("b200_gadget_product_bit_decomp: invalid base"); return B200_EINVAL; }
+    long long total = 0;
+    for (int i = 0; i <= levelQ; ++i) {
+        if (sizes[i] < 1 || (long long)(sizes[i] - 1) * pw2 >= 64) { b200_set_error("b200_gadget_product_bit_decomp: invalid BaseTwoDecompositionVectorSize"); return B200_ESHAPE; }
+        total += sizes[i];
+    }
+    b200_ctx *ctx = ks->ctx;
+    const int B = cx->batch, N = ctx->N;
+    if (key->batch < 2 * total) { b200_set_error("b200_gadget_product_bit_decomp: the key must hold 2*sum(sizes) polynomials [limb][window][component]"); return B200_ESHAPE; }
+    if (ct0->batch != B || ct1->batch != B || ct0->d == ct1->d) { b200_set_error("b200_gadget_product_bit_decomp: outputs must be two distinct polynomials of the input's batch size"); return B200_ESHAPE; }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const size_t words = (size_t)B * ctx->L * N;
+    const int slots = (int)std::min<long long>(total, MAC_DIGITS);
+    if (int rc = ensure_ws(ks, (3 + slots) * words)) return rc;
+    u64 *cxinv = ks->ws, *acc0 = ks->ws + words, *acc1 = ks->ws + 2 * words, *c2 = ks->ws + 3 * words;
+    int rc = ntt_range(ctx, cx->d, cxinv, B, 0, levelQ + 1, true);                               // ringQ.INTT(cx, cxInvNTT) (:201-203)
+    if (rc) return rc;
+    if ((rc = bitdecomp_mac(ks, levelQ, levelP, pw2, sizes, cxinv, key->d, c2, acc0, acc1, B))) return rc;
+    if ((rc = mod_down_ntt(ks, levelQ, levelP, acc0, ct0->d, c2, B))) return rc;
+    return mod_down_ntt(ks, levelQ, levelP, acc1, ct1->d, c2, B);
+}
+
 // ---- limb-sharded execution (SURVEY.md 8e / BASELINE config 5): the same gadget product in three device steps,
 // separated by the two exchanges of the path (an all-gather of the coefficient-domain input limbs, and one of the
 // P limbs of the accumulators), which the caller performs with NCCL on the polynomials' device memory.
@@ -599,7 +706,6 @@ extern "C" int b200_ks_decompose_mac(b200_keyswitch *ks, int levelQ, int levelP,
         if (int rc = check_poly(ks, p, "b200_ks_decompose_mac")) return rc;
     const Own o{q0, q1, p0, p1};
     if (int rc = check_own(ks, levelQ, levelP, o, "b200_ks_decompose_mac")) return rc;
-    if (levelP < 1) { b200_set_error("b200_ks_decompose_mac: needs levelP >= 1"); return B200_EINVAL; }
     b200_ctx *ctx = ks->ctx;
     const int beta = (levelQ + levelP + 1) / (levelP + 1), B = cx->batch;
     if (key->batch < 2 * beta || cxinv->batch != B || acc0->batch != B || acc1->batch != B || acc0->d == acc1->d) {
@@ -641,7 +747,6 @@ extern "C" int b200_mul_relin(b200_keyswitch *ks, int levelQ, int levelP, const 
         if (int rc = check_poly(ks, p, "b200_mul_relin")) return rc;
     b200_ctx *ctx = ks->ctx;
     const int B = a0->batch, N = ctx->N, beta = (levelQ + levelP + 1) / (levelP + 1);
-    if (levelP < 1) { b200_set_error("b200_mul_relin: needs levelP >= 1"); return B200_EINVAL; }
     if (a1->batch != B || b0->batch != B || b1->batch != B || out0->batch != B || out1->batch != B || rlk->batch < 2 * beta || out0->d == out1->d) {
         b200_set_error("b200_mul_relin: batch sizes do not match");
         return B200_ESHAPE;

@@ -490,6 +490,11 @@ class KeySwitcher:
     def GadgetProduct(self, levelQ, levelP, cx, key, ct0, ct1):   # core/rlwe/evaluator_gadget_product.go:16-30
         check(lib().b200_gadget_product(self.h, levelQ, levelP, cx.h, key.h, ct0.h, ct1.h))
 
+    def GadgetProductBitDecomp(self, levelQ, levelP, pw2, sizes, cx, key, ct0, ct1):
+        """GadgetProduct with a power-of-two base (evaluator_gadget_product.go:190-320); sizes = BaseTwoDecompositionVectorSize."""
+        sz = (C.c_int * len(sizes))(*[int(v) for v in sizes])
+        check(lib().b200_gadget_product_bit_decomp(self.h, levelQ, levelP, pw2, sz, cx.h, key.h, ct0.h, ct1.h))
+
     def MulRelin(self, levelQ, levelP, a0, a1, b0, b1, rlk, out0, out1, mform=True):
         """ct x ct multiply + relinearisation in the NTT domain: tensor product, GadgetProduct(c2, rlk), add
         (schemes/ckks/evaluator.go:821-853)."""

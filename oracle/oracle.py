@@ -477,8 +477,9 @@ def decompose_and_split(Q, P, levelQ, levelP, nbPi, digit, p0Q):
 
 
 def gadget_product(ringsQ, ringsP, levelQ, levelP, cx_ntt, key):
-    """rlwe.Evaluator.GadgetProduct for NTT-domain operands and levelP > 0
-    (core/rlwe/evaluator_gadget_product.go:16-30, 33-45, 123-188, 455-478).
+    """rlwe.Evaluator.GadgetProduct for NTT-domain operands
+    (core/rlwe/evaluator_gadget_product.go:16-30, 33-45, 123-188, 455-478).  With levelP == 0 this is also the result of
+    gadgetProductSinglePAndBitDecompLazy with mask == 0 (:190-320): one-limb digits through DecomposeAndSplit(nbPi = 1).
     cx_ntt: [levelQ+1][N]; key[i][c]: (Q part [LQ][N], P part [LP][N]) for digit i, component c, NTT + Montgomery form.
     Returns (ct0, ct1), each [levelQ+1][N], canonical."""
     Q = [r.q for r in ringsQ]
@@ -502,6 +503,33 @@ def gadget_product(ringsQ, ringsP, levelQ, levelP, cx_ntt, key):
                 accQ[c][x] = vec_op("Add", Q[x], accQ[c][x], vec_op("MulCoeffsMontgomery", Q[x], kq[x], c2Q[x]))
             for j in range(levelP + 1):
                 accP[c][j] = vec_op("Add", P[j], accP[c][j], vec_op("MulCoeffsMontgomery", P[j], kp[j], c2P[j]))
+    be = BasisExtender(Q, P)
+    return tuple(be.ModDownQPtoQNTT(levelQ, levelP, accQ[c], accP[c], ringsQ, ringsP) for c in range(2))
+
+
+def gadget_product_bit_decomp(ringsQ, ringsP, levelQ, pw2, sizes, cx_ntt, key):
+    """rlwe.Evaluator.GadgetProduct for one special prime and a power-of-two base pw2 > 0:
+    gadgetProductSinglePAndBitDecompLazy with mask != 0 (core/rlwe/evaluator_gadget_product.go:190-320) + ModDown (:33-45).
+    key[i][j][c]: (Q part [LQ][N], P part [1][N]) for limb i, window j < sizes[i], component c.  Canonical outputs."""
+    Q = [r.q for r in ringsQ]
+    P = [r.q for r in ringsP]
+    levelP = 0
+    mask = np.uint64((1 << pw2) - 1)
+    cx_inv = np.stack([ringsQ[i].INTT(cx_ntt[i]) for i in range(levelQ + 1)])
+    N = cx_inv.shape[1]
+    accQ = [np.zeros((levelQ + 1, N), dtype=np.uint64) for _ in range(2)]
+    accP = [np.zeros((levelP + 1, N), dtype=np.uint64) for _ in range(2)]
+    for i in range(levelQ + 1):
+        for j in range(sizes[i]):
+            cw = (cx_inv[i] >> np.uint64(j * pw2)) & mask                     # ring.MaskVec (vec_ops.go:870-890)
+            for c in range(2):
+                kq, kp = key[i][j][c]
+                for x in range(levelQ + 1):
+                    cwn = ringsQ[x].NTT(cw % np.uint64(Q[x]))
+                    accQ[c][x] = vec_op("Add", Q[x], accQ[c][x], vec_op("MulCoeffsMontgomery", Q[x], kq[x], cwn))
+                for u in range(levelP + 1):
+                    cwn = ringsP[u].NTT(cw % np.uint64(P[u]))
+                    accP[c][u] = vec_op("Add", P[u], accP[c][u], vec_op("MulCoeffsMontgomery", P[u], kp[u], cwn))
     be = BasisExtender(Q, P)
     return tuple(be.ModDownQPtoQNTT(levelQ, levelP, accQ[c], accP[c], ringsQ, ringsP) for c in range(2))
 

@@ -204,3 +204,104 @@ def test_mul_relin_is_tensor_plus_gadget_product(kind, N, LQ, LP):
             S = [int(v) for v in sQ[i]]
             assert [int(v) for v in got0[b, i]] == [(x * y + z * w % q * t) % q for x, y, z, w, t in zip(A0, B0, A1, B1, S)]
             assert [int(v) for v in got1[b, i]] == [(x * w + z * y) % q for x, y, z, w in zip(A0, B0, A1, B1)]
+
+
+# ------------------------------------------------------------------ one special prime / power-of-two base
+def pow2_gadget_key(Q, P, levelQ, pw2, sizes, N, s_ntt_Q, s_ntt_P):
+    """Noiseless gadget for gadgetProductSinglePAndBitDecompLazy: g_{i,j} = P * 2^(j*pw2) * (Q/q_i) ((Q/q_i)^-1 mod q_i);
+    component 0 = g, component 1 = g*s (NTT domain, Montgomery form).  sum_ij window_ij(cx_i) * g_ij = P*cx mod Q exactly."""
+    Qp, Pp = O._prod(Q[: levelQ + 1]), P[0]
+    key = []
+    for i in range(levelQ + 1):
+        qi = Q[i]
+        base = Pp * (Qp // qi) * pow(Qp // qi, -1, qi)
+        row = []
+        for j in range(sizes[i]):
+            g = base << (j * pw2)
+            comps = []
+            for c in range(2):
+                def limb(m, s):
+                    gm = (g % m) * pow(2, 64, m) % m
+                    return np.full(N, gm, dtype=np.uint64) if c == 0 else np.array([gm * int(v) % m for v in s], dtype=np.uint64)
+                comps.append((np.stack([limb(q, s_ntt_Q[u]) for u, q in enumerate(Q[: levelQ + 1])]),
+                              np.stack([limb(P[0], s_ntt_P[0])])))
+            row.append(comps)
+        key.append(row)
+    return key
+
+
+@pytest.mark.parametrize("kind,N", [("std", 16), ("m3", 24)])
+def test_oracle_single_special_prime_and_pow2_base(kind, N):
+    LQ = 3
+    Q, P, rq, rp = chains(kind, N, LQ, 1)
+    rng = np.random.default_rng(5)
+    s = np.array(rng.integers(0, 3, N), dtype=np.uint64)
+    sQ, sP = np.stack([r.NTT(s) for r in rq]), np.stack([r.NTT(s) for r in rp])
+    cx = np.stack([rng.integers(0, q, N, dtype=np.uint64) for q in Q])
+    want1 = np.stack([O.vec_op("MulCoeffsBarrett", q, cx[i], sQ[i]) for i, q in enumerate(Q)])
+    # mask == 0 (:213-215): one-limb digits
+    ct0, ct1 = O.gadget_product(rq, rp, LQ - 1, 0, cx, gadget_key(Q, P, LQ - 1, 0, N, sQ, sP))
+    assert (ct0 == cx).all() and (ct1 == want1).all()
+    # power-of-two base: the windows of every limb rebuild cx exactly
+    for pw2 in (16, 21):
+        sizes = [(q.bit_length() + pw2 - 1) // pw2 for q in Q]              # rlwe/params.go:626-628
+        ct0, ct1 = O.gadget_product_bit_decomp(rq, rp, LQ - 1, pw2, sizes, cx, pow2_gadget_key(Q, P, LQ - 1, pw2, sizes, N, sQ, sP))
+        assert (ct0 == cx).all() and (ct1 == want1).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,N,LQ", [("std", 32, 3), ("m3", 24, 4), ("std", 1 << 12, 5), ("m3", 3 * 2**12, 3)])
+def test_gadget_product_single_special_prime_and_pow2_base(kind, N, LQ):
+    Q, P, rq, rp = chains(kind, N, LQ, 1)
+    ring = b200ring.NewRing(N, Q + P)
+    ks = b200ring.KeySwitcher(ring, LQ)
+    rng = np.random.default_rng(29)
+    batch = 2
+    cx = np.stack([np.stack([rng.integers(0, q, N, dtype=np.uint64) for q in Q]) for _ in range(batch)])
+    pcx, ct0, ct1 = _qp_poly(ring, LQ, batch, cx), ring.NewPoly(batch), ring.NewPoly(batch)
+    s = np.array(rng.integers(0, 3, N), dtype=np.uint64)
+    sQ, sP = np.stack([r.NTT(s) for r in rq]), np.stack([r.NTT(s) for r in rp])
+    want1 = np.stack([np.stack([O.vec_op("MulCoeffsBarrett", q, cx[b, i], sQ[i]) for i, q in enumerate(Q)]) for b in range(batch)])
+    for levelQ in (LQ - 1, LQ - 2):
+        # (1) mask == 0 through b200_gadget_product with levelP == 0: random key against the oracle, then the exact property
+        beta = levelQ + 1
+        key = [[(np.stack([rng.integers(0, q, N, dtype=np.uint64) for q in Q]), np.stack([rng.integers(0, p, N, dtype=np.uint64) for p in P]))
+                for _ in range(2)] for _ in range(beta)]
+        hk = np.zeros((2 * beta, LQ + 1, N), dtype=np.uint64)
+        for d in range(beta):
+            for c in range(2):
+                hk[2 * d + c, :LQ], hk[2 * d + c, LQ:] = key[d][c]
+        pkey = ring.NewPoly(2 * beta).set(hk)
+        ks.GadgetProduct(levelQ, 0, pcx, pkey, ct0, ct1)
+        if N <= 1 << 12:
+            for b in range(batch):
+                w0, w1 = O.gadget_product(rq, rp, levelQ, 0, cx[b][: levelQ + 1], [[(kq[: levelQ + 1], kp) for kq, kp in d] for d in key])
+                assert (ct0.get()[b, : levelQ + 1] == w0).all() and (ct1.get()[b, : levelQ + 1] == w1).all()
+        # (2) power-of-two base
+        for pw2 in (20, 13):
+            sizes = [(q.bit_length() + pw2 - 1) // pw2 for q in Q[: levelQ + 1]]
+            total = sum(sizes)
+            rkey = [[[(np.stack([rng.integers(0, q, N, dtype=np.uint64) for q in Q[: levelQ + 1]]), np.stack([rng.integers(0, P[0], N, dtype=np.uint64)]))
+                      for _ in range(2)] for _ in range(sizes[i])] for i in range(levelQ + 1)]
+            gk = pow2_gadget_key(Q, P, levelQ, pw2, sizes, N, sQ, sP)
+            for use, exact in ((rkey, False), (gk, True)):
+                if not exact and N > 1 << 10:
+                    continue                                                  # the oracle's per-window transforms are slow
+                hk = np.zeros((2 * total, LQ + 1, N), dtype=np.uint64)
+                k = 0
+                for i in range(levelQ + 1):
+                    for j in range(sizes[i]):
+                        for c in range(2):
+                            hk[k, : levelQ + 1], hk[k, LQ:] = use[i][j][c]
+                            k += 1
+                pk = ring.NewPoly(2 * total).set(hk)
+                ks.GadgetProductBitDecomp(levelQ, 0, pw2, sizes, pcx, pk, ct0, ct1)
+                g0, g1 = ct0.get(), ct1.get()
+                if exact:
+                    assert (g0[:, : levelQ + 1] == cx[:, : levelQ + 1]).all() and (g1[:, : levelQ + 1] == want1[:, : levelQ + 1]).all()
+                else:
+                    for b in range(batch):
+                        w0, w1 = O.gadget_product_bit_decomp(rq[: levelQ + 1], rp, levelQ, pw2, sizes, cx[b][: levelQ + 1], use)
+                        assert (g0[b, : levelQ + 1] == w0).all() and (g1[b, : levelQ + 1] == w1).all()
+    with pytest.raises(b200ring.B200Error):
+        ks.GadgetProductBitDecomp(LQ - 1, 0, 20, [1] * LQ, pcx, ring.NewPoly(1), ct0, ct1)      # key too small

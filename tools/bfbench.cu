@@ -48,10 +48,25 @@ __device__ __forceinline__ u64 shoup4_alu(u64 x, u64 w, u64 ws, u64 nq) {
     r1 = madlo_u32(t1, lo32(nq), r1);
     return ((u64)r1 << 32) | lo32(r);
 }
+// quotient through carry-chained mad.hi: t = x1*wsh + hi32(x0*wsh) + hi32(x1*wsl) with the additions folded into the multiplies
+__device__ __forceinline__ u64 shoup4_madhi(u64 x, u64 w, u64 ws, u64 nq) {
+    const unsigned x0 = lo32(x), x1 = hi32(x);
+    const u64 C = mulwide_u32(x1, hi32(ws));
+    unsigned t0 = lo32(C), t1 = hi32(C);
+    asm("mad.hi.cc.u32 %0, %2, %3, %0;\n\taddc.u32 %1, %1, 0;" : "+r"(t0), "+r"(t1) : "r"(x0), "r"(hi32(ws)));
+    asm("mad.hi.cc.u32 %0, %2, %3, %0;\n\taddc.u32 %1, %1, 0;" : "+r"(t0), "+r"(t1) : "r"(x1), "r"(lo32(ws)));
+    const u64 r = madwide_u32(t0, lo32(nq), mulwide_u32(x0, lo32(w)));
+    unsigned r1 = hi32(r);
+    r1 = madlo_u32(x0, hi32(w), r1);
+    r1 = madlo_u32(x1, lo32(w), r1);
+    r1 = madlo_u32(t0, hi32(nq), r1);
+    r1 = madlo_u32(t1, lo32(nq), r1);
+    return ((u64)r1 << 32) | lo32(r);
+}
 template <int V>
 __device__ __forceinline__ void bf_int_v(u64 &U, u64 &V_, const tw_t w, const QC &c) {
     const u64 u = csub(U, c.fourq);
-    const u64 t = V == 1 ? shoup4_alu(V_, w.x, w.y, c.nq) : shoup4(V_, w.x, w.y, c.nq);
+    const u64 t = V == 2 ? shoup4_madhi(V_, w.x, w.y, c.nq) : V == 1 ? shoup4_alu(V_, w.x, w.y, c.nq) : shoup4(V_, w.x, w.y, c.nq);
     U = u + t;
     V_ = u - t + c.fourq;
 }
@@ -122,7 +137,7 @@ __global__ void __launch_bounds__(128, 8) k_bf(u64 *data, const tw_t *twi, const
 #pragma unroll 1
     for (int it = 0; it < iters; ++it) {
         const unsigned P = (it * 7 + (threadIdx.x & lanemask)) & 31;
-        if (MODE == 0 || MODE == 6) {
+        if (MODE == 0 || MODE == 6 || MODE == 8) {
 #pragma unroll
             for (int l = 0; l < LAYERS; ++l) {
                 const int j = l % 3, half = 4 >> j;
@@ -130,7 +145,7 @@ __global__ void __launch_bounds__(128, 8) k_bf(u64 *data, const tw_t *twi, const
                 for (int g = 0; g < (1 << j); ++g) {
                     const tw_t w = twi[(((P + l / 3) << j) + g) & (TWN - 1)];
 #pragma unroll
-                    for (int o = 0; o < half; ++o) { if (MODE == 6) bf_int_v<1>(x[g * 2 * half + o], x[g * 2 * half + o + half], w, c); else bf_int(x[g * 2 * half + o], x[g * 2 * half + o + half], w, c); }
+                    for (int o = 0; o < half; ++o) { if (MODE == 8) bf_int_v<2>(x[g * 2 * half + o], x[g * 2 * half + o + half], w, c); else if (MODE == 6) bf_int_v<1>(x[g * 2 * half + o], x[g * 2 * half + o + half], w, c); else bf_int(x[g * 2 * half + o], x[g * 2 * half + o + half], w, c); }
                 }
             }
         } else if (MODE == 7) {
@@ -177,7 +192,7 @@ __global__ void __launch_bounds__(128, 8) k_bf(u64 *data, const tw_t *twi, const
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         u64 v = x[k];
-        if (MODE == 0 || MODE == 6) v = csub(csub(csub(v, c.fourq), c.twoq), c.q); else v = csub(v, c.q);
+        if (MODE == 0 || MODE == 6 || MODE == 8) v = csub(csub(csub(v, c.fourq), c.twoq), c.q); else v = csub(v, c.q);
         p[k] = v;
     }
     if (threadIdx.x == 0) clk[blockIdx.x] = t1 - t0;
@@ -316,6 +331,9 @@ int main() {
     { std::vector<u64> rx;
       bench<6, 5>("integer, quotient summed on ALU", sms, d, in, d_ti, d_tf, c, &rx);
       size_t badx = 0; for (size_t i = 0; i < rx.size() && i < r3.size(); ++i) badx += rx[i] != r3[i];
+      printf("   parity vs integer: %zu mismatches\n", badx);
+      bench<8, 5>("integer, quotient by mad.hi.cc chain", sms, d, in, d_ti, d_tf, c, &rx);
+      badx = 0; for (size_t i = 0; i < rx.size() && i < r3.size(); ++i) badx += rx[i] != r3[i];
       printf("   parity vs integer: %zu mismatches\n", badx);
       bench<0, 6>("integer, 6 layers/iter", sms, d, in, d_ti, d_tf, c, &r3);
       bench<7, 6>("integer, csub-free 3-layer groups", sms, d, in, d_ti, d_tf, c, &rx);
