@@ -209,6 +209,14 @@ B200_API int b200_gadget_product(b200_keyswitch *ks, int levelQ, int levelP, con
  * 2*sum(sizes) polynomials ordered [limb i][window j][component].  pw2 == 0 forwards to b200_gadget_product. */
 B200_API int b200_gadget_product_bit_decomp(b200_keyswitch *ks, int levelQ, int levelP, int pw2, const int *sizes, const b200_poly *cx,
                                    const b200_poly *key, b200_poly *ct0, b200_poly *ct1);
+/* Hoisted key switch (one decomposition, many keys: rotations of a linear transform).
+ * b200_decompose_ntt: rlwe.Evaluator.DecomposeNTT (core/rlwe/evaluator_gadget_product.go:430-478) for an NTT-domain cx:
+ *   decomp receives beta*B polynomials ordered [digit][b], every digit over all limbs 0..levelQ and P_0..levelP, NTT domain,
+ *   canonical (BuffDecompQP[digit]).
+ * b200_gadget_product_hoisted: GadgetProductHoisted (:322-423): multiply-accumulate of `decomp` with `key` + ModDown. */
+B200_API int b200_decompose_ntt(b200_keyswitch *ks, int levelQ, int levelP, const b200_poly *cx, b200_poly *decomp);
+B200_API int b200_gadget_product_hoisted(b200_keyswitch *ks, int levelQ, int levelP, const b200_poly *decomp, const b200_poly *key,
+                                b200_poly *ct0, b200_poly *ct1);
 
 /* Ciphertext x ciphertext multiply with relinearisation, NTT domain in and out (BASELINE config 5):
  * (c0, c1, c2) = tensor(a, b) as b200_tensor, then (out0, out1) = (c0, c1) + GadgetProduct(c2, rlk)

@@ -440,6 +440,54 @@ int mod_down_ntt(b200_keyswitch *ks, int levelQ, int levelP, const u64 *p1, u64 
                          ks->d_moddown + (size_t)levelP * LQ);
 }
 
+// one multiply-accumulate pass over a group of nd <= MAC_DIGITS digits
+int launch_mac(b200_ctx *ctx, const u64 *cx, const MacGroup &mg, int nd, u64 *acc0, u64 *acc1, const int *d_limbs, int nl, int B, bool first) {
+    const int N = ctx->N;
+    int chunks = (N / 2 + 255) / 256;
+    if (chunks > 128) chunks = 128;
+    const dim3 grid(chunks, B * nl);
+    LaunchScope ls(ctx, "gadget_mac", (long long)B * nl * nd);
+    cudaStream_t st_ = b200_cur_stream(ctx);
+    const int f = first ? 1 : 0;
+    switch (nd) {
+    case 1: k_gadget_mac_group<1><<<grid, 256, 0, st_>>>(cx, mg, acc0, acc1, ctx->d_consts, d_limbs, nl, N, ctx->L, f); break;
+    case 2: k_gadget_mac_group<2><<<grid, 256, 0, st_>>>(cx, mg, acc0, acc1, ctx->d_consts, d_limbs, nl, N, ctx->L, f); break;
+    case 3: k_gadget_mac_group<3><<<grid, 256, 0, st_>>>(cx, mg, acc0, acc1, ctx->d_consts, d_limbs, nl, N, ctx->L, f); break;
+    default: k_gadget_mac_group<4><<<grid, 256, 0, st_>>>(cx, mg, acc0, acc1, ctx->d_consts, d_limbs, nl, N, ctx->L, f); break;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// DecomposeSingleNTT (evaluator_gadget_product.go:455-478) of digit d restricted to the owned limbs, without the copy of
+// the digit's own limbs (:466-468): DecomposeAndSplit (basis_extension.go:381-502) of the coefficient-domain input into every
+// owned limb outside the digit and the owned P limbs, then their NTT.
+int decompose_digit(b200_keyswitch *ks, int levelQ, int levelP, const u64 *cxinv, u64 *c2d, int B, Own o, int d) {
+    b200_ctx *ctx = ks->ctx;
+    const int nbPi = levelP + 1, LQ = ks->LQ, N = ctx->N;
+    const int st = d * nbPi, ed = std::min(st + nbPi, levelQ + 1);
+    std::vector<int> dst;
+    for (int j = o.q0; j < o.q1; ++j) if (j < st || j >= ed) dst.push_back(j);
+    for (int j = o.p0; j < o.p1; ++j) dst.push_back(LQ + j);
+    if (dst.empty()) return 0;
+    int rc = 0;
+    if (ed - st == 1) {                                                                  // single-limb digit (:402-428)
+        Extender *e;   // only used as a cached holder of the target list
+        if ((rc = get_extender(ks, range(st, ed), dst, false, &e))) return rc;
+        LaunchScope ls(ctx, "decompose_single", (long long)B * (int)dst.size());
+        k_decompose_single<<<dim3((N + 255) / 256, B), 256, 0, b200_cur_stream(ctx)>>>(cxinv, c2d, ctx->d_consts, st, e->d_dst, (int)dst.size(), N, ctx->L);
+    } else {                                                                             // exact centred conversion (:430-500)
+        Extender *e;
+        if ((rc = get_extender(ks, range(st, ed), dst, true, &e))) return rc;
+        if ((rc = run_extend(ks, e, cxinv, c2d, B, 1))) return rc;
+    }
+    // NTT of every owned limb outside the digit, and of the owned P limbs (:469-477)
+    const int a0 = o.q0, a1 = std::min(o.q1, st), b0 = std::max(o.q0, ed), b1 = o.q1;
+    if ((rc = ntt_range(ctx, c2d, c2d, B, a0, a1 - a0, false))) return rc;
+    if ((rc = ntt_range(ctx, c2d, c2d, B, b0, b1 - b0, false))) return rc;
+    return ntt_range(ctx, c2d, c2d, B, LQ + o.p0, o.p1 - o.p0, false);
+}
+
 // Digit loop of gadgetProductMultiplePLazy (:123-188) restricted to the owned limbs: decomposition of every digit
 // into the owned targets, their NTT, and the multiply-accumulate with the owned key limbs.  cxinv must hold ALL
 // Q limbs 0..levelQ in the coefficient domain (after the all-gather when sharded); cx the owned Q limbs in the NTT domain.
@@ -467,45 +515,14 @@ int decompose_mac(b200_keyswitch *ks, int levelQ, int levelP, const u64 *cx, con
             const int d = d0 + g;
             const int st = d * nbPi, ed = std::min(st + nbPi, levelQ + 1);
             u64 *c2d = c2 + (size_t)g * words;
-            std::vector<int> dst;
-            for (int j = o.q0; j < o.q1; ++j) if (j < st || j >= ed) dst.push_back(j);
-            for (int j = o.p0; j < o.p1; ++j) dst.push_back(LQ + j);
-            if (!dst.empty()) {
-                if (ed - st == 1) {                                                                  // single-limb digit (:402-428)
-                    Extender *e;   // only used as a cached holder of the target list
-                    if ((rc = get_extender(ks, range(st, ed), dst, false, &e))) break;
-                    LaunchScope ls(ctx, "decompose_single", (long long)B * (int)dst.size());
-                    k_decompose_single<<<dim3((N + 255) / 256, B), 256, 0, b200_cur_stream(ctx)>>>(cxinv, c2d, ctx->d_consts, st, e->d_dst, (int)dst.size(), N, ctx->L);
-                } else {                                                                             // exact centred conversion (:430-500)
-                    Extender *e;
-                    if ((rc = get_extender(ks, range(st, ed), dst, true, &e))) break;
-                    if ((rc = run_extend(ks, e, cxinv, c2d, B, 1))) break;
-                }
-                // DecomposeSingleNTT (:466-477): NTT of every owned limb outside the digit, and of the owned P limbs
-                const int a0 = o.q0, a1 = std::min(o.q1, st), b0 = std::max(o.q0, ed), b1 = o.q1;
-                if ((rc = ntt_range(ctx, c2d, c2d, B, a0, a1 - a0, false))) break;
-                if ((rc = ntt_range(ctx, c2d, c2d, B, b0, b1 - b0, false))) break;
-                if ((rc = ntt_range(ctx, c2d, c2d, B, LQ + o.p0, o.p1 - o.p0, false))) break;
-            }
+            if ((rc = decompose_digit(ks, levelQ, levelP, cxinv, c2d, B, o, d))) break;
             mg.op[g] = c2d;
             mg.k0[g] = key + (size_t)(2 * d) * ctx->L * N;
             mg.k1[g] = key + (size_t)(2 * d + 1) * ctx->L * N;
             mg.st[g] = st; mg.ed[g] = ed;
         }
         if (rc) break;
-        int chunks = (N / 2 + 255) / 256;
-        if (chunks > 128) chunks = 128;
-        const dim3 grid(chunks, B * (int)limbs.size());
-        LaunchScope ls(ctx, "gadget_mac", (long long)B * (int)limbs.size() * nd);
-        cudaStream_t st_ = b200_cur_stream(ctx);
-        const int first = d0 == 0, nl = (int)limbs.size();
-        switch (nd) {
-        case 1: k_gadget_mac_group<1><<<grid, 256, 0, st_>>>(cx, mg, acc0, acc1, ctx->d_consts, d_limbs, nl, N, ctx->L, first); break;
-        case 2: k_gadget_mac_group<2><<<grid, 256, 0, st_>>>(cx, mg, acc0, acc1, ctx->d_consts, d_limbs, nl, N, ctx->L, first); break;
-        case 3: k_gadget_mac_group<3><<<grid, 256, 0, st_>>>(cx, mg, acc0, acc1, ctx->d_consts, d_limbs, nl, N, ctx->L, first); break;
-        default: k_gadget_mac_group<4><<<grid, 256, 0, st_>>>(cx, mg, acc0, acc1, ctx->d_consts, d_limbs, nl, N, ctx->L, first); break;
-        }
-        CUDA_TRY(cudaGetLastError());
+        rc = launch_mac(ctx, cx, mg, nd, acc0, acc1, d_limbs, (int)limbs.size(), B, d0 == 0);
     }
     return rc;
 }
@@ -549,19 +566,7 @@ int bitdecomp_mac(b200_keyswitch *ks, int levelQ, int levelP, int pw2, const int
             mg.st[g] = mg.ed[g] = 0;   // no limb reads the input itself
         }
         if (rc) break;
-        int chunks = (N / 2 + 255) / 256;
-        if (chunks > 128) chunks = 128;
-        const dim3 grid(chunks, B * nl);
-        LaunchScope ls(ctx, "gadget_mac", (long long)B * nl * nd);
-        cudaStream_t st_ = b200_cur_stream(ctx);
-        const int first = d0 == 0;
-        switch (nd) {
-        case 1: k_gadget_mac_group<1><<<grid, 256, 0, st_>>>(cxinv, mg, acc0, acc1, ctx->d_consts, d_limbs, nl, N, ctx->L, first); break;
-        case 2: k_gadget_mac_group<2><<<grid, 256, 0, st_>>>(cxinv, mg, acc0, acc1, ctx->d_consts, d_limbs, nl, N, ctx->L, first); break;
-        case 3: k_gadget_mac_group<3><<<grid, 256, 0, st_>>>(cxinv, mg, acc0, acc1, ctx->d_consts, d_limbs, nl, N, ctx->L, first); break;
-        default: k_gadget_mac_group<4><<<grid, 256, 0, st_>>>(cxinv, mg, acc0, acc1, ctx->d_consts, d_limbs, nl, N, ctx->L, first); break;
-        }
-        CUDA_TRY(cudaGetLastError());
+        rc = launch_mac(ctx, cxinv, mg, nd, acc0, acc1, d_limbs, nl, B, d0 == 0);
     }
     return rc;
 }
@@ -659,6 +664,76 @@ extern "C" int b200_gadget_product(b200_keyswitch *ks, int levelQ, int levelP, c
     if ((rc = decompose_mac(ks, levelQ, levelP, cx->d, cxinv, key->d, c2, acc0, acc1, B, Own{0, levelQ + 1, 0, levelP + 1}))) return rc;
     if ((rc = mod_down_ntt(ks, levelQ, levelP, acc0, ct0->d, c2, B))) return rc;                 // eval.ModDown, NTT -> NTT (:40-45)
     return mod_down_ntt(ks, levelQ, levelP, acc1, ct1->d, c2, B);
+}
+
+// rlwe.Evaluator.DecomposeNTT (evaluator_gadget_product.go:430-452) for an NTT-domain input: the RNS decomposition of cx,
+// every digit extended to all limbs 0..levelQ and P_0..levelP, in the NTT domain and canonical, the digit's own limbs copied
+// from cx (:466-468).  `decomp` holds beta*B polynomials ordered [digit][b] (BuffDecompQP[digit]).
+extern "C" int b200_decompose_ntt(b200_keyswitch *ks, int levelQ, int levelP, const b200_poly *cx, b200_poly *decomp) {
+    CtxLock lk(ks ? ks->ctx : nullptr);
+    if (int rc = check_levels(ks, levelQ, levelP, "b200_decompose_ntt")) return rc;
+    if (int rc = check_poly(ks, cx, "b200_decompose_ntt")) return rc;
+    if (int rc = check_poly(ks, decomp, "b200_decompose_ntt")) return rc;
+    b200_ctx *ctx = ks->ctx;
+    const int nbPi = levelP + 1, beta = (levelQ + levelP + 1) / (levelP + 1), B = cx->batch, N = ctx->N;
+    if (decomp->batch < beta * B || decomp->d == cx->d) { b200_set_error("b200_decompose_ntt: decomp must hold beta*batch polynomials [digit][b], distinct from cx"); return B200_ESHAPE; }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const size_t words = (size_t)B * ctx->L * N;
+    if (int rc = ensure_ws(ks, words)) return rc;
+    u64 *cxinv = ks->ws;
+    int rc = ntt_range(ctx, cx->d, cxinv, B, 0, levelQ + 1, true);                               // ringQ.INTT(polyNTT, polyInvNTT) (:438-441)
+    if (rc) return rc;
+    const Own o{0, levelQ + 1, 0, levelP + 1};
+    for (int d = 0; d < beta; ++d) {
+        u64 *c2d = decomp->d + (size_t)d * words;
+        if ((rc = decompose_digit(ks, levelQ, levelP, cxinv, c2d, B, o, d))) return rc;
+        const int st = d * nbPi, ed = std::min(st + nbPi, levelQ + 1);
+        // copy(c2QiQ.Coeffs[x], c2NTT.Coeffs[x]) for the digit's own limbs: (ed-st)*N contiguous words of each polynomial
+        CUDA_TRY(cudaMemcpy2DAsync(c2d + (size_t)st * N, (size_t)ctx->L * N * sizeof(u64), cx->d + (size_t)st * N, (size_t)ctx->L * N * sizeof(u64),
+                                   (size_t)(ed - st) * N * sizeof(u64), B, cudaMemcpyDeviceToDevice, b200_cur_stream(ctx)));
+    }
+    return 0;
+}
+// rlwe.Evaluator.GadgetProductHoisted (:322-339, :341-423): the multiply-accumulate of an already decomposed input with a
+// gadget ciphertext, then ModDown.  decomp: the output of b200_decompose_ntt (beta*B polynomials); key as in b200_gadget_product.
+extern "C" int b200_gadget_product_hoisted(b200_keyswitch *ks, int levelQ, int levelP, const b200_poly *decomp, const b200_poly *key,
+                                           b200_poly *ct0, b200_poly *ct1) {
+    CtxLock lk(ks ? ks->ctx : nullptr);
+    if (int rc = check_levels(ks, levelQ, levelP, "b200_gadget_product_hoisted")) return rc;
+    for (const b200_poly *p : {decomp, key, (const b200_poly *)ct0, (const b200_poly *)ct1})
+        if (int rc = check_poly(ks, p, "b200_gadget_product_hoisted")) return rc;
+    b200_ctx *ctx = ks->ctx;
+    const int beta = (levelQ + levelP + 1) / (levelP + 1), B = ct0->batch, N = ctx->N, LQ = ks->LQ;
+    if (key->batch < 2 * beta) { b200_set_error("b200_gadget_product_hoisted: the key must hold 2*beta polynomials [digit][component]"); return B200_ESHAPE; }
+    if (decomp->batch < beta * B) { b200_set_error("b200_gadget_product_hoisted: decomp must hold beta*batch polynomials [digit][b]"); return B200_ESHAPE; }
+    if (ct1->batch != B || ct0->d == ct1->d) { b200_set_error("b200_gadget_product_hoisted: outputs must be two distinct polynomials of the same batch size"); return B200_ESHAPE; }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const size_t words = (size_t)B * ctx->L * N;
+    if (int rc = ensure_ws(ks, 3 * words)) return rc;
+    u64 *acc0 = ks->ws, *acc1 = ks->ws + words, *buf = ks->ws + 2 * words;
+    std::vector<int> limbs = range(0, levelQ + 1);
+    for (int j = 0; j <= levelP; ++j) limbs.push_back(LQ + j);
+    int *&d_limbs = ks->limb_lists[((0 * 64 + (levelQ + 1)) * 64 + 0) * 64 + (levelP + 1)];
+    if (!d_limbs) {
+        cudaError_t ce = upload(&d_limbs, limbs);
+        if (ce != cudaSuccess) return b200_cuda_fail(ce, "gadget product limb list");
+    }
+    int rc = 0;
+    for (int d0 = 0; d0 < beta && rc == 0; d0 += MAC_DIGITS) {
+        const int nd = std::min(MAC_DIGITS, beta - d0);
+        MacGroup mg{};
+        for (int g = 0; g < nd; ++g) {
+            const int d = d0 + g;
+            mg.op[g] = decomp->d + (size_t)d * words;
+            mg.k0[g] = key->d + (size_t)(2 * d) * ctx->L * N;
+            mg.k1[g] = key->d + (size_t)(2 * d + 1) * ctx->L * N;
+            mg.st[g] = mg.ed[g] = 0;   // the own limbs are already in the decomposition
+        }
+        rc = launch_mac(ctx, decomp->d, mg, nd, acc0, acc1, d_limbs, (int)limbs.size(), B, d0 == 0);
+    }
+    if (rc) return rc;
+    if ((rc = mod_down_ntt(ks, levelQ, levelP, acc0, ct0->d, buf, B))) return rc;
+    return mod_down_ntt(ks, levelQ, levelP, acc1, ct1->d, buf, B);
 }
 
 // rlwe.Evaluator.GadgetProduct for a gadget ciphertext with a power-of-two base (BaseTwoDecomposition = pw2 > 0, one

@@ -490,6 +490,13 @@ class KeySwitcher:
     def GadgetProduct(self, levelQ, levelP, cx, key, ct0, ct1):   # core/rlwe/evaluator_gadget_product.go:16-30
         check(lib().b200_gadget_product(self.h, levelQ, levelP, cx.h, key.h, ct0.h, ct1.h))
 
+    def DecomposeNTT(self, levelQ, levelP, cx, decomp):
+        """rlwe.Evaluator.DecomposeNTT (evaluator_gadget_product.go:430-478): decomp = beta*batch polynomials [digit][b]."""
+        check(lib().b200_decompose_ntt(self.h, levelQ, levelP, cx.h, decomp.h))
+
+    def GadgetProductHoisted(self, levelQ, levelP, decomp, key, ct0, ct1):   # :322-423
+        check(lib().b200_gadget_product_hoisted(self.h, levelQ, levelP, decomp.h, key.h, ct0.h, ct1.h))
+
     def GadgetProductBitDecomp(self, levelQ, levelP, pw2, sizes, cx, key, ct0, ct1):
         """GadgetProduct with a power-of-two base (evaluator_gadget_product.go:190-320); sizes = BaseTwoDecompositionVectorSize."""
         sz = (C.c_int * len(sizes))(*[int(v) for v in sizes])

@@ -507,6 +507,26 @@ def gadget_product(ringsQ, ringsP, levelQ, levelP, cx_ntt, key):
     return tuple(be.ModDownQPtoQNTT(levelQ, levelP, accQ[c], accP[c], ringsQ, ringsP) for c in range(2))
 
 
+def decompose_ntt(ringsQ, ringsP, levelQ, levelP, cx_ntt):
+    """rlwe.Evaluator.DecomposeNTT for an NTT-domain input (evaluator_gadget_product.go:430-478): per digit the pair
+    (c2Q [levelQ+1][N], c2P [levelP+1][N]), NTT domain, canonical, the digit's own limbs copied from cx_ntt."""
+    Q = [r.q for r in ringsQ]
+    P = [r.q for r in ringsP]
+    nbPi = levelP + 1
+    beta = (levelQ + levelP + 1) // (levelP + 1)
+    cx_inv = np.stack([ringsQ[i].INTT(cx_ntt[i]) for i in range(levelQ + 1)])
+    out = []
+    for d in range(beta):
+        c2Q, c2P = decompose_and_split(Q, P, levelQ, levelP, nbPi, d, cx_inv)
+        st, ed = d * nbPi, d * nbPi + nbPi
+        for x in range(levelQ + 1):
+            c2Q[x] = cx_ntt[x] if st <= x < ed else ringsQ[x].NTT(c2Q[x] % np.uint64(Q[x]))
+        for j in range(levelP + 1):
+            c2P[j] = ringsP[j].NTT(c2P[j] % np.uint64(P[j]))
+        out.append((c2Q, c2P))
+    return out
+
+
 def gadget_product_bit_decomp(ringsQ, ringsP, levelQ, pw2, sizes, cx_ntt, key):
     """rlwe.Evaluator.GadgetProduct for one special prime and a power-of-two base pw2 > 0:
     gadgetProductSinglePAndBitDecompLazy with mask != 0 (core/rlwe/evaluator_gadget_product.go:190-320) + ModDown (:33-45).

@@ -305,3 +305,41 @@ def test_gadget_product_single_special_prime_and_pow2_base(kind, N, LQ):
                         assert (g0[b, : levelQ + 1] == w0).all() and (g1[b, : levelQ + 1] == w1).all()
     with pytest.raises(b200ring.B200Error):
         ks.GadgetProductBitDecomp(LQ - 1, 0, 20, [1] * LQ, pcx, ring.NewPoly(1), ct0, ct1)      # key too small
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,N,LQ,LP", [("std", 32, 5, 2), ("m3", 48, 4, 1), ("m3", 3 * 2**10, 6, 3), ("std", 1 << 13, 7, 2)])
+def test_hoisted_decomposition_and_gadget_product(kind, N, LQ, LP):
+    """DecomposeNTT (evaluator_gadget_product.go:430-478) bit for bit against the oracle, and GadgetProductHoisted
+    (:322-423) on it == GadgetProduct, for two keys sharing one decomposition and at a lower level."""
+    Q, P, rq, rp = chains(kind, N, LQ, LP)
+    ring = b200ring.NewRing(N, Q + P)
+    ks = b200ring.KeySwitcher(ring, LQ)
+    rng = np.random.default_rng(31)
+    batch = 2
+    cx = np.stack([np.stack([rng.integers(0, q, N, dtype=np.uint64) for q in Q]) for _ in range(batch)])
+    pcx = _qp_poly(ring, LQ, batch, cx)
+    for levelQ, levelP in ((LQ - 1, LP - 1), (LQ - 2, LP - 1)):
+        beta = (levelQ + levelP + 1) // (levelP + 1)
+        dec = ring.NewPoly(beta * batch)
+        ks.DecomposeNTT(levelQ, levelP, pcx, dec)
+        got = dec.get().reshape(beta, batch, LQ + LP, N)
+        if N <= 3 * 2**10:
+            for b in range(batch):
+                want = O.decompose_ntt(rq, rp, levelQ, levelP, cx[b][: levelQ + 1])
+                for d in range(beta):
+                    assert (got[d, b, : levelQ + 1] == want[d][0]).all(), (d, b)
+                    assert (got[d, b, LQ: LQ + levelP + 1] == want[d][1]).all(), (d, b)
+        for seed in (1, 2):                                                   # two keys, one decomposition
+            kr = np.random.default_rng(seed)
+            hk = np.zeros((2 * beta, LQ + LP, N), dtype=np.uint64)
+            for l, m in enumerate(Q + P):
+                hk[:, l] = kr.integers(0, m, (2 * beta, N), dtype=np.uint64)
+            pkey = ring.NewPoly(2 * beta).set(hk)
+            h0, h1, g0, g1 = (ring.NewPoly(batch) for _ in range(4))
+            ks.GadgetProductHoisted(levelQ, levelP, dec, pkey, h0, h1)
+            ks.GadgetProduct(levelQ, levelP, pcx, pkey, g0, g1)
+            assert (h0.get()[:, : levelQ + 1] == g0.get()[:, : levelQ + 1]).all()
+            assert (h1.get()[:, : levelQ + 1] == g1.get()[:, : levelQ + 1]).all()
+    with pytest.raises(b200ring.B200Error):
+        ks.DecomposeNTT(LQ - 1, LP - 1, pcx, ring.NewPoly(1))
