@@ -125,9 +125,14 @@ def main():
         polys = [P(x) for x in t] + [P(rlk)] + [P(x) for x in o]
         ms = timed(lambda: ks.MulRelin(levelQ, levelP, *polys), 5, warm=2)
         ms_ks = timed(lambda: ks.GadgetProduct(levelQ, levelP, polys[0], polys[4], polys[5], polys[6]), 5, warm=2)
+        dec = ring.NewPoly(beta * B)
+        ms_dec = timed(lambda: ks.DecomposeNTT(levelQ, levelP, polys[0], dec), 5, warm=2)
+        ms_hoist = timed(lambda: ks.GadgetProductHoisted(levelQ, levelP, dec, polys[4], polys[5], polys[6]), 5, warm=2)
         rows.append({"config": "C5", "workload": "N=3*2^15, LQ=24, LP=6 (beta=%d): ct x ct multiply + relinearisation (b200_mul_relin), batch %d, one GPU" % (beta, B),
                      "ms_per_step": ms, "value": B / (ms * 1e-3), "unit": "ciphertext multiplies/s",
                      "gadget_product_ms": ms_ks, "key_switches_per_s": B / (ms_ks * 1e-3),
+                     "decompose_ntt_ms": ms_dec, "gadget_product_hoisted_ms": ms_hoist,
+                     "hoisted_key_switches_per_s": B / (ms_hoist * 1e-3),
                      "limb_transforms_per_key_switch": beta * (LQ + LP) + 2 * (LQ + LP), "note": "limb-sharded 2/4-GPU numbers: tools/bench_keyswitch.py"})
     for r in rows:
         print(json.dumps(r))
