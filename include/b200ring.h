@@ -217,6 +217,11 @@ B200_API int b200_gadget_product_bit_decomp(b200_keyswitch *ks, int levelQ, int 
 B200_API int b200_decompose_ntt(b200_keyswitch *ks, int levelQ, int levelP, const b200_poly *cx, b200_poly *decomp);
 B200_API int b200_gadget_product_hoisted(b200_keyswitch *ks, int levelQ, int levelP, const b200_poly *decomp, const b200_poly *key,
                                 b200_poly *ct0, b200_poly *ct1);
+/* rlwe.Evaluator.Automorphism (core/rlwe/evaluator_automorphism.go:13-60) on an NTT-domain ciphertext (ct0, ct1) of a
+ * power-of-two ring: (t0, t1) = GadgetProduct(ct1, key); t0 += ct0; out_c = AutomorphismNTT(t_c, galEl).  With decomp != NULL
+ * (the output of b200_decompose_ntt on ct1) it is AutomorphismHoisted (:62-108). */
+B200_API int b200_automorphism_ct(b200_keyswitch *ks, int levelQ, int levelP, const b200_poly *ct0, const b200_poly *ct1,
+                         const b200_poly *decomp, uint64_t galEl, const b200_poly *key, b200_poly *out0, b200_poly *out1);
 
 /* Ciphertext x ciphertext multiply with relinearisation, NTT domain in and out (BASELINE config 5):
  * (c0, c1, c2) = tensor(a, b) as b200_tensor, then (out0, out1) = (c0, c1) + GadgetProduct(c2, rlk)

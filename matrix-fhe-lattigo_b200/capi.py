@@ -51,6 +51,7 @@ SYMBOLS = {
     "b200_gadget_product": (C.c_int, [VP, C.c_int, C.c_int, VP, VP, VP, VP]),
     "b200_decompose_ntt": (C.c_int, [VP, C.c_int, C.c_int, VP, VP]),
     "b200_gadget_product_hoisted": (C.c_int, [VP, C.c_int, C.c_int, VP, VP, VP, VP]),
+    "b200_automorphism_ct": (C.c_int, [VP, C.c_int, C.c_int, VP, VP, VP, C.c_uint64, VP, VP, VP]),
     "b200_gadget_product_bit_decomp": (C.c_int, [VP, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), VP, VP, VP, VP]),
     "b200_mul_relin": (C.c_int, [VP, C.c_int, C.c_int, VP, VP, VP, VP, VP, VP, VP, C.c_int]),
     "b200_ntt_limbs": (C.c_int, [VP, VP, VP, C.c_int, C.c_int, C.c_int, C.c_int]),

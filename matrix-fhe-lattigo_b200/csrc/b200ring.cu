@@ -49,6 +49,17 @@ int b200_ensure_scratch(b200_ctx *ctx, size_t words) {
     return 0;
 }
 
+// second workspace (ctx->d_ws) for composite operators whose steps use d_scratch themselves
+int b200_ensure_scratch2(b200_ctx *ctx, size_t words) {
+    if (ctx->ws_words >= words) return 0;
+    CUDA_TRY(cudaStreamSynchronize(b200_cur_stream(ctx)));
+    if (ctx->d_ws) CUDA_TRY(cudaFree(ctx->d_ws));
+    ctx->d_ws = nullptr; ctx->ws_words = 0;
+    CUDA_TRY(cudaMalloc(&ctx->d_ws, words * sizeof(u64)));
+    ctx->ws_words = words;
+    return 0;
+}
+
 // ---- ring-degree validation (subring.go:14-30, ring.go:266,319-323) -------------------------------------
 static bool valid_3n_degree(int N, int *a_out, int *b_out) {
     if (N <= 0) return false;
@@ -719,13 +730,7 @@ extern "C" int b200_div_by_last_modulus_ntt(b200_ctx *ctx, const b200_poly *p0, 
     if (level < 1) return fail(B200_ESHAPE, "b200_div_by_last_modulus_ntt: needs level >= 1");
     CUDA_TRY(cudaSetDevice(ctx->device));
     const size_t words = (size_t)batch * ctx->L * ctx->N;
-    if (ctx->ws_words < words) {
-        CUDA_TRY(cudaStreamSynchronize(b200_cur_stream(ctx)));
-        if (ctx->d_ws) CUDA_TRY(cudaFree(ctx->d_ws));
-        ctx->d_ws = nullptr; ctx->ws_words = 0;
-        CUDA_TRY(cudaMalloc(&ctx->d_ws, words * sizeof(u64)));
-        ctx->ws_words = words;
-    }
+    if (int rc = b200_ensure_scratch2(ctx, words)) return rc;
     u64 *ws = ctx->d_ws;
     const size_t off = (size_t)level * ctx->N;
     auto ntt = [&](const u64 *src, u64 *dst, Span sp, bool inv) {

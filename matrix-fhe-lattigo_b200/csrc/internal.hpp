@@ -95,6 +95,7 @@ int b200_cuda_fail(cudaError_t e, const char *what);
     } while (0)
 
 int b200_ensure_scratch(b200_ctx *ctx, size_t words);
+int b200_ensure_scratch2(b200_ctx *ctx, size_t words);
 // the stream launchers enqueue on: the context's stream, or a per-thread override used by the pipelined
 // host-buffer entry point (b200_transform_host) while it drives its own compute stream
 cudaStream_t b200_cur_stream(b200_ctx *ctx);

@@ -841,3 +841,35 @@ extern "C" int b200_mul_relin(b200_keyswitch *ks, int levelQ, int levelP, const 
     if ((rc = mod_down_ntt(ks, levelQ, levelP, acc1, g, c2buf, B))) return rc;
     return launch_vec_op(ctx, B200_OP_ADD, t1, g, out1->d, spq, nullptr);
 }
+
+// rlwe.Evaluator.Automorphism (core/rlwe/evaluator_automorphism.go:13-60) on an NTT-domain ciphertext of degree 1 over a
+// power-of-two ring: (t0, t1) = GadgetProduct(ct1, galois key); t0 += ct0; out_c = AutomorphismNTT(t_c, galEl).
+// With decomp != NULL the key switch is the hoisted one (AutomorphismHoisted, :62-108) on the caller's DecomposeNTT(ct1).
+extern "C" int b200_automorphism_ct(b200_keyswitch *ks, int levelQ, int levelP, const b200_poly *ct0, const b200_poly *ct1,
+                                    const b200_poly *decomp, uint64_t galEl, const b200_poly *key, b200_poly *out0, b200_poly *out1) {
+    CtxLock lk(ks ? ks->ctx : nullptr);
+    if (int rc = check_levels(ks, levelQ, levelP, "b200_automorphism_ct")) return rc;
+    for (const b200_poly *p : {ct0, ct1, key, (const b200_poly *)out0, (const b200_poly *)out1})
+        if (int rc = check_poly(ks, p, "b200_automorphism_ct")) return rc;
+    if (decomp) if (int rc = check_poly(ks, decomp, "b200_automorphism_ct")) return rc;
+    b200_ctx *ctx = ks->ctx;
+    if (ctx->ring_type != B200_RING_STANDARD) { b200_set_error("N must be a power of two"); return B200_ESHAPE; }   // AutomorphismNTTIndex (ring/automorphism.go:14-16)
+    const int B = ct0->batch, N = ctx->N;
+    if (ct1->batch != B || out0->batch != B || out1->batch != B || out0->d == out1->d) { b200_set_error("b200_automorphism_ct: batch sizes do not match"); return B200_ESHAPE; }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const size_t words = (size_t)B * ctx->L * N;
+    // two result polynomials of our own next to the key switch's workspace (which it may re-allocate: grow it first)
+    const int beta = (levelQ + levelP + 1) / (levelP + 1);
+    if (int rc = ensure_ws(ks, (size_t)(3 + std::min(beta, MAC_DIGITS)) * words)) return rc;
+    if (int rc = b200_ensure_scratch2(ctx, 2 * words)) return rc;
+    u64 *t0 = ctx->d_ws, *t1 = ctx->d_ws + words;
+    b200_poly p0{ctx, t0, B, false}, p1{ctx, t1, B, false};
+    int rc = decomp ? b200_gadget_product_hoisted(ks, levelQ, levelP, decomp, key, &p0, &p1)
+                    : b200_gadget_product(ks, levelQ, levelP, ct1, key, &p0, &p1);
+    if (rc) return rc;
+    const Span spq{B, levelQ + 1, ctx->L, 0};
+    if ((rc = launch_vec_op(ctx, B200_OP_ADD, t0, ct0->d, t0, spq, nullptr))) return rc;          // ringQ.Add(ctTmp.Value[0], ctIn.Value[0], ctTmp.Value[0]) (:43)
+    const u64 nth = 2 * (u64)N;
+    if ((rc = launch_automorphism_ntt(ctx, t0, out0->d, nullptr, galEl, nth, N, ctx->L, B, levelQ + 1, 0))) return rc;
+    return launch_automorphism_ntt(ctx, t1, out1->d, nullptr, galEl, nth, N, ctx->L, B, levelQ + 1, 0);
+}

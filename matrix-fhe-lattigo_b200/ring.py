@@ -497,6 +497,11 @@ class KeySwitcher:
     def GadgetProductHoisted(self, levelQ, levelP, decomp, key, ct0, ct1):   # :322-423
         check(lib().b200_gadget_product_hoisted(self.h, levelQ, levelP, decomp.h, key.h, ct0.h, ct1.h))
 
+    def Automorphism(self, levelQ, levelP, ct0, ct1, galEl, key, out0, out1, decomp=None):
+        """rlwe.Evaluator.Automorphism / AutomorphismHoisted (core/rlwe/evaluator_automorphism.go:13-108), NTT domain."""
+        check(lib().b200_automorphism_ct(self.h, levelQ, levelP, ct0.h, ct1.h, decomp.h if decomp is not None else None,
+                                         int(galEl) % (1 << 64), key.h, out0.h, out1.h))
+
     def GadgetProductBitDecomp(self, levelQ, levelP, pw2, sizes, cx, key, ct0, ct1):
         """GadgetProduct with a power-of-two base (evaluator_gadget_product.go:190-320); sizes = BaseTwoDecompositionVectorSize."""
         sz = (C.c_int * len(sizes))(*[int(v) for v in sizes])

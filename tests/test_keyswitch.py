@@ -343,3 +343,49 @@ def test_hoisted_decomposition_and_gadget_product(kind, N, LQ, LP):
             assert (h1.get()[:, : levelQ + 1] == g1.get()[:, : levelQ + 1]).all()
     with pytest.raises(b200ring.B200Error):
         ks.DecomposeNTT(LQ - 1, LP - 1, pcx, ring.NewPoly(1))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,LQ,LP", [(64, 4, 2), (1 << 12, 5, 1)])
+def test_ciphertext_automorphism_is_keyswitch_add_permutation(N, LQ, LP):
+    """rlwe.Evaluator.Automorphism / AutomorphismHoisted (core/rlwe/evaluator_automorphism.go:13-108): the same words as
+    the reference's step sequence through the separate entry points, and the rotation identity with a noiseless key."""
+    Q, P, rq, rp = chains("std", N, LQ, LP)
+    ring = b200ring.NewRing(N, Q + P)
+    ks = b200ring.KeySwitcher(ring, LQ)
+    rng = np.random.default_rng(37)
+    levelQ, levelP = LQ - 1, LP - 1
+    beta = (levelQ + levelP + 1) // (levelP + 1)
+    batch, gal = 2, 5 ** 3 % (2 * N)
+    h0, h1 = (np.stack([np.stack([rng.integers(0, q, N, dtype=np.uint64) for q in Q]) for _ in range(batch)]) for _ in range(2))
+    ct0, ct1 = _qp_poly(ring, LQ, batch, h0), _qp_poly(ring, LQ, batch, h1)
+    s = np.array(rng.integers(0, 3, N), dtype=np.uint64)
+    sQ, sP = np.stack([r.NTT(s) for r in rq]), np.stack([r.NTT(s) for r in rp])
+    gk = gadget_key(Q, P, levelQ, levelP, N, sQ, sP)
+    hk = np.zeros((2 * beta, LQ + LP, N), dtype=np.uint64)
+    for d in range(beta):
+        for c in range(2):
+            hk[2 * d + c, :LQ], hk[2 * d + c, LQ:] = gk[d][c]
+    key = ring.NewPoly(2 * beta).set(hk)
+    o0, o1, g0, g1, a0, a1 = (ring.NewPoly(batch) for _ in range(6))
+    ks.Automorphism(levelQ, levelP, ct0, ct1, gal, key, o0, o1)
+    ks.GadgetProduct(levelQ, levelP, ct1, key, g0, g1)
+    rl = ring.AtLevel(levelQ)
+    rl.Add(g0, ct0, g0)
+    rl.AutomorphismNTT(g0, gal, a0); rl.AutomorphismNTT(g1, gal, a1)
+    assert (o0.get()[:, :LQ] == a0.get()[:, :LQ]).all() and (o1.get()[:, :LQ] == a1.get()[:, :LQ]).all()
+    dec = ring.NewPoly(beta * batch)
+    ks.DecomposeNTT(levelQ, levelP, ct1, dec)
+    ks.Automorphism(levelQ, levelP, ct0, ct1, gal, key, g0, g1, decomp=dec)
+    assert (g0.get()[:, :LQ] == o0.get()[:, :LQ]).all() and (g1.get()[:, :LQ] == o1.get()[:, :LQ]).all()
+    # noiseless key (g, g*s): GadgetProduct(ct1) = (ct1, ct1*s), so out = phi(ct0 + ct1), phi(ct1 * s) slot-wise
+    idx = O.automorphism_ntt_index(N, 2 * N, gal).astype(np.int64)
+    got0, got1 = o0.get(), o1.get()
+    for i, q in enumerate(Q):
+        for b in range(batch):
+            assert (got0[b, i] == O.vec_op("Add", q, h0[b, i], h1[b, i])[idx]).all()
+            assert (got1[b, i] == O.vec_op("MulCoeffsBarrett", q, h1[b, i], sQ[i])[idx]).all()
+    m = b200ring.NewRing(24, O.find_3n_rns_primes(24, 60, 3))
+    with pytest.raises(b200ring.B200Error):                                   # 3N rings have no automorphism tables (automorphism.go:14-16)
+        km = b200ring.KeySwitcher(m, 2)
+        km.Automorphism(1, 0, m.NewPoly(), m.NewPoly(), 5, m.NewPoly(4), m.NewPoly(), m.NewPoly())
