@@ -223,8 +223,11 @@ __device__ __forceinline__ u64 fold128(u64 a, u64 lo, u64 hi, u64 q, u64 qinv) {
     const u64 r = hi - __umul64hi(lo * qinv, q) + q;     // MRedLazy of the 128-bit sum: [0, 2q)
     return csub(csub(a + r, 2 * q), q);
 }
+#ifndef B200_MAC_MINB
+#define B200_MAC_MINB 1
+#endif
 template <int ND>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, B200_MAC_MINB)
 k_gadget_mac_group(const u64 *cx, MacGroup m, u64 *acc0, u64 *acc1, const LimbConst *__restrict__ consts, const int *limbs,
                    int nlimbs, int N, int Lbuf, int first) {
     // limb-major units: the polynomials of the batch that share a key limb run back to back, so the 2*ND key limbs
