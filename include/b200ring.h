@@ -258,6 +258,12 @@ B200_API int b200_div_by_last_modulus_ntt(b200_ctx *ctx, const b200_poly *p0, b2
 B200_API int b200_tensor(b200_ctx *ctx, const b200_poly *a0, const b200_poly *a1, const b200_poly *b0, const b200_poly *b1,
                 b200_poly *c0, b200_poly *c1, b200_poly *c2, int level, int mform_first);
 
+/* Ring.Shift (ring/operations.go:278-282): p2[j] = p1[(j + k) mod N] on every limb of the polynomial.
+ * Ring.MultByMonomial (:306-363): p2 = X^k * p1 with X^N = -1 on limbs 0..level; a negated zero is written as q, exactly
+ * like the Go loops.  p1 == p2 is allowed. */
+B200_API int b200_shift(b200_ctx *ctx, const b200_poly *p1, int k, b200_poly *p2);
+B200_API int b200_mult_by_monomial(b200_ctx *ctx, const b200_poly *p1, int k, b200_poly *p2, int level);
+
 /* ---- automorphisms X -> X^gen of power-of-two rings (ring/automorphism.go) -----------------------------------------
  * b200_automorphism_ntt_index: AutomorphismNTTIndex (:12-35), host only, N words.
  * b200_automorphism_ntt: Ring.AutomorphismNTT (:38-46), the table computed on the device; with add_lazy != 0 the result is

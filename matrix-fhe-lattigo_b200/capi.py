@@ -60,6 +60,8 @@ SYMBOLS = {
     "b200_div_by_last_modulus_ntt": (C.c_int, [VP, VP, VP, C.c_int, C.c_int]),
     "b200_tensor": (C.c_int, [VP, VP, VP, VP, VP, VP, VP, VP, C.c_int, C.c_int]),
     "b200_polymul": (C.c_int, [VP, VP, VP, VP, C.c_int]),
+    "b200_shift": (C.c_int, [VP, VP, C.c_int, VP]),
+    "b200_mult_by_monomial": (C.c_int, [VP, VP, C.c_int, VP, C.c_int]),
     "b200_unfold_ci_to_standard": (C.c_int, [VP, VP, VP, C.c_int]),
     "b200_automorphism_ntt_index": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, P64]),
     "b200_automorphism_ntt": (C.c_int, [VP, VP, C.c_uint64, VP, C.c_int, C.c_int]),

@@ -756,6 +756,42 @@ extern "C" int b200_tensor(b200_ctx *ctx, const b200_poly *a0, const b200_poly *
     return launch_tensor(ctx, a0->d, a1->d, b0->d, b1->d, c0->d, c1->d, c2->d, Span{batch, level + 1, ctx->L, 0}, mform_first != 0);
 }
 
+// Ring.Shift (ring/operations.go:278-282): p2 = p1 rotated left by k positions, ALL limbs of the polynomial (the Go loop
+// ranges over p1.Coeffs, not over the ring's level).  Ring.MultByMonomial (:306-363): p2 = X^k * p1 on limbs 0..level.
+// Both accept p1 == p2 like the reference (the operand is staged).
+static int rotate_common(b200_ctx *ctx, const b200_poly *p1, b200_poly *p2, int nl, int s, int neg, int mode, const char *who) {
+    int batch;
+    if (int rc = check_polys(ctx, nl - 1, who, {p1, p2}, &batch)) return rc;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const u64 *src = p1->d;
+    if (p1->d == p2->d) {
+        const size_t words = (size_t)batch * ctx->L * ctx->N;
+        if (int rc = b200_ensure_scratch(ctx, words)) return rc;
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_scratch, p1->d, words * sizeof(u64), cudaMemcpyDeviceToDevice, b200_cur_stream(ctx)));
+        src = ctx->d_scratch;
+    }
+    return launch_rotate(ctx, src, p2->d, batch, nl, s, neg, mode);
+}
+extern "C" int b200_shift(b200_ctx *ctx, const b200_poly *p1, int k, b200_poly *p2) {
+    CtxLock lk(ctx);
+    if (!ctx) return fail(B200_EINVAL, "b200_shift: ctx is NULL");
+    int s = k % ctx->N;
+    if (s < 0) s += ctx->N;
+    return rotate_common(ctx, p1, p2, ctx->L, s, 0, 0, "b200_shift");
+}
+extern "C" int b200_mult_by_monomial(b200_ctx *ctx, const b200_poly *p1, int k, b200_poly *p2, int level) {
+    CtxLock lk(ctx);
+    if (!ctx) return fail(B200_EINVAL, "b200_mult_by_monomial: ctx is NULL");
+    if (level < 0 || level >= ctx->L) return fail(B200_ESHAPE, "b200_mult_by_monomial: level out of range");
+    const long long twoN = 2LL * ctx->N;
+    const long long shift = (((long long)k + twoN) % twoN + twoN) % twoN;      // (k + 2N) % 2N of the reference for k > -2N
+    if (shift == 0) {                                                          // :312-320: plain copy of limbs 0..level
+        if (p1 && p2 && p1->d == p2->d) return 0;
+        return rotate_common(ctx, p1, p2, level + 1, 0, 0, 0, "b200_mult_by_monomial");
+    }
+    return rotate_common(ctx, p1, p2, level + 1, (int)(shift % ctx->N), shift >= ctx->N ? 1 : 0, 1, "b200_mult_by_monomial");
+}
+
 // ---- automorphisms X -> X^gen (ring/automorphism.go) ------------------------------------------------------------
 static u64 ring_nthroot(const b200_ctx *ctx) {
     return (ctx->ring_type == B200_RING_MATRIX ? 3 : ctx->ring_type == B200_RING_CONJUGATE_INVARIANT ? 4 : 2) * (u64)ctx->N;

@@ -219,6 +219,29 @@ k_automorphism_coeff(const u64 *in, u64 *out, const LimbConst *__restrict__ cons
     }
 }
 
+// Ring.Shift (ring/operations.go:278-282, utils.RotateSliceAllocFree): out[j] = in[(j + k) mod N], every limb.
+// Ring.MultByMonomial (:306-363): multiplication by X^k with X^N = -1, words exactly as the Go loops leave them
+// (a negated zero is q):  shift = (k + 2N) mod 2N, s = shift mod N, neg = shift >= N:
+//   j <  s: out[j] = neg ? in[N-s+j] : q - in[N-s+j];      j >= s: out[j] = neg ? q - in[j-s] : in[j-s].
+// mode 0 = Shift, 1 = MultByMonomial.  Not in place (the launcher stages aliased operands).
+__global__ void __launch_bounds__(256)
+k_rotate(const u64 *in, u64 *out, const LimbConst *__restrict__ consts, int N, int L, int nl, int s, int neg, int mode, int unit0) {
+    const int unit = unit0 + blockIdx.y, limb = unit % nl, b = unit / nl;
+    const size_t base = ((size_t)b * L + limb) * (size_t)N;
+    const u64 q = consts[limb].q;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x) {
+        if (mode == 0) {
+            int src = j + s;
+            if (src >= N) src -= N;
+            out[base + j] = in[base + src];
+        } else {
+            const bool wrap = j < s;
+            const u64 v = in[base + (wrap ? N - s + j : j - s)];
+            out[base + j] = (wrap != (neg != 0)) ? q - v : v;
+        }
+    }
+}
+
 // Rescale helper (ring/scaling.go:137-143): x = coefficient-domain last limb [0, q_l); for every lower limb i
 // t_i = (x (+ pHalf mod q_l)) + (q_i - pHalf mod q_i), reduced to [0, q_i).  ws is a [batch][Lbuf][N] buffer whose
 // limb `level` holds x; limbs 0..level-1 receive t_i.
@@ -292,6 +315,20 @@ int launch_automorphism_coeff(b200_ctx *ctx, const u64 *in, u64 *out, u64 gen, i
         const int nu = units - u0 < 65535 ? units - u0 : 65535;
         LaunchScope ls(ctx, "automorphism", nu);
         k_automorphism_coeff<<<dim3(chunks, nu), 256, 0, b200_cur_stream(ctx)>>>(in, out, ctx->d_consts, ctx->N, ctx->L, nl, gen, ci, u0);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int launch_rotate(b200_ctx *ctx, const u64 *in, u64 *out, int batch, int nl, int s, int neg, int mode) {
+    const int N = ctx->N;
+    int chunks = (N + 255) / 256;
+    if (chunks > 512) chunks = 512;
+    const int units = batch * nl;
+    for (int u0 = 0; u0 < units; u0 += 65535) {
+        const int nu = units - u0 < 65535 ? units - u0 : 65535;
+        LaunchScope ls(ctx, mode ? "mult_by_monomial" : "shift", nu);
+        k_rotate<<<dim3(chunks, nu), 256, 0, b200_cur_stream(ctx)>>>(in, out, ctx->d_consts, N, ctx->L, nl, s, neg, mode, u0);
     }
     CUDA_TRY(cudaGetLastError());
     return 0;

@@ -151,5 +151,6 @@ int launch_ci_fold(b200_ctx *ctx, const u64 *in, u64 *out, Span sp, bool inverse
 int launch_automorphism_ntt(b200_ctx *ctx, const u64 *in, u64 *out, const u64 *d_index, u64 gen, u64 nthroot, int n_in, int l_in,
                             int batch, int nl, int mode);
 int launch_automorphism_coeff(b200_ctx *ctx, const u64 *in, u64 *out, u64 gen, int batch, int nl);
+int launch_rotate(b200_ctx *ctx, const u64 *in, u64 *out, int batch, int nl, int s, int neg, int mode);
 int launch_ci_unfold(b200_ctx *ctx, const u64 *in, u64 *out, int N, int batch, int nl, int Lin, int Lout);
 int launch_polymul_big(b200_ctx *ctx, const u64 *a, const u64 *b, u64 *c, Span sp);

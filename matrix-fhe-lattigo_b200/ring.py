@@ -268,6 +268,51 @@ class Ring:
             raise ValueError("cannot StandardRing: the ring is not a conjugate-invariant ring")
         return NewRingFromType(self._N << 1, self._moduli[: self.level + 1], Standard, self.device)
 
+    def Shift(self, p1, k, p2):
+        """Ring.Shift (ring/operations.go:278-282): rotate every limb left by k."""
+        check(lib().b200_shift(self._ctx.h, p1.h, int(k), p2.h))
+
+    def MultByMonomial(self, p1, k, p2):
+        """Ring.MultByMonomial (ring/operations.go:306-363): p2 = X^k * p1, X^N = -1."""
+        check(lib().b200_mult_by_monomial(self._ctx.h, p1.h, int(k), p2.h, self.level))
+
+    # -- host-side scalar preparation + the scalar operators (ring/operations.go:151-267) --
+    def _mform_scalars(self, scalar_of_limb):
+        out = []
+        for s in self.SubRings[: self.level + 1]:
+            out.append(int(scalar_of_limb(s)) % s.Modulus * (1 << 64) % s.Modulus)      # MForm(scalar, q, BRedConstant)
+        return out
+
+    def MulScalar(self, p1, scalar, p2):                                                # :201-205
+        self.MulScalarMontgomery(p1, self._mform_scalars(lambda s: scalar), p2)
+
+    def MulScalarThenAdd(self, p1, scalar, p2):                                         # :208-212
+        self.MulScalarMontgomeryThenAdd(p1, self._mform_scalars(lambda s: scalar), p2)
+
+    def MulScalarThenSub(self, p1, scalar, p2):                                         # :223-228
+        self.MulScalarMontgomeryThenAdd(p1, self._mform_scalars(lambda s: s.Modulus - int(scalar) % s.Modulus), p2)
+
+    def MulRNSScalarMontgomery(self, p1, scalar, p2):                                   # :216-220
+        self.MulScalarMontgomery(p1, [int(v) for v in scalar[: self.level + 1]], p2)
+
+    def MulScalarBigint(self, p1, scalar, p2):                                          # :231-237
+        self.MulScalar(p1, scalar, p2)
+
+    def MulScalarBigintThenAdd(self, p1, scalar, p2):                                   # :240-247
+        self.MulScalarThenAdd(p1, scalar, p2)
+
+    def AddScalarBigint(self, p1, scalar, p2):                                          # :158-163
+        self.AddScalar(p1, [int(scalar) % s.Modulus for s in self.SubRings[: self.level + 1]], p2)
+
+    def SubScalarBigint(self, p1, scalar, p2):                                          # :193-198
+        self.SubScalar(p1, [int(scalar) % s.Modulus for s in self.SubRings[: self.level + 1]], p2)
+
+    def EvalPolyScalar(self, p1, scalar, p2):                                           # :269-275
+        p2.Copy(p1[-1])
+        for i in range(len(p1) - 1, 0, -1):
+            self.MulScalar(p2, scalar, p2)
+            self.Add(p2, p1[i - 1], p2)
+
     # -- automorphisms X -> X^gen (ring/automorphism.go); none of them works in place --
     def AutomorphismNTT(self, polIn, gen, polOut):
         check(lib().b200_automorphism_ntt(self._ctx.h, polIn.h, int(gen) % (1 << 64), polOut.h, self.level, 0))
