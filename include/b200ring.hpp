@@ -179,6 +179,29 @@ class Ring {
     }
     // fused NTT, NTT, MForm, MulCoeffsMontgomery, INTT (BASELINE config 4)
     void MulPoly(const Poly &a, const Poly &b, Poly &c) const { check(b200_polymul(ctx_.get(), a.handle(), b.handle(), c.handle(), level_)); }
+    // ring/automorphism.go, ring/operations.go:278-363, ring/conjugate_invariant.go (none of the automorphisms works in place)
+    static std::vector<uint64_t> AutomorphismNTTIndex(int N, uint64_t NthRoot, uint64_t GalEl) {
+        std::vector<uint64_t> index(N > 0 ? N : 0);
+        check(b200_automorphism_ntt_index(N, NthRoot, GalEl, index.data()));
+        return index;
+    }
+    void AutomorphismNTT(const Poly &in, uint64_t gen, Poly &out) const { check(b200_automorphism_ntt(ctx_.get(), in.handle(), gen, out.handle(), level_, 0)); }
+    void AutomorphismNTTWithIndex(const Poly &in, const std::vector<uint64_t> &index, Poly &out) const {
+        check(b200_automorphism_ntt_with_index(ctx_.get(), in.handle(), index.data(), index.size(), out.handle(), level_, 0));
+    }
+    void AutomorphismNTTWithIndexThenAddLazy(const Poly &in, const std::vector<uint64_t> &index, Poly &out) const {
+        check(b200_automorphism_ntt_with_index(ctx_.get(), in.handle(), index.data(), index.size(), out.handle(), level_, 1));
+    }
+    void Automorphism(const Poly &in, uint64_t gen, Poly &out) const { check(b200_automorphism(ctx_.get(), in.handle(), gen, out.handle(), level_)); }
+    void Shift(const Poly &p1, int k, Poly &p2) const { check(b200_shift(ctx_.get(), p1.handle(), k, p2.handle())); }
+    void MultByMonomial(const Poly &p1, int k, Poly &p2) const { check(b200_mult_by_monomial(ctx_.get(), p1.handle(), k, p2.handle(), level_)); }
+    // the receiver is the conjugate-invariant ring; polyStandard lives in a ring of twice the degree over the same moduli
+    void UnfoldConjugateInvariantToStandard(const Poly &polyCI, Poly &polyStandard) const {
+        check(b200_unfold_ci_to_standard(ctx_.get(), polyCI.handle(), polyStandard.handle(), level_));
+    }
+    void FoldStandardToConjugateInvariant(const Poly &polyStandard, const std::vector<uint64_t> &permuteNTTIndexInv, Poly &polyCI) const {
+        check(b200_fold_standard_to_ci(ctx_.get(), polyStandard.handle(), permuteNTTIndexInv.data(), permuteNTTIndexInv.size(), polyCI.handle(), level_));
+    }
     // NumberTheoreticTransformer (ring/ntt.go:15-22) for one prime, host slices
     void SubRingNTT(int limb, const std::vector<uint64_t> &p1, std::vector<uint64_t> &p2, bool inverse = false, bool lazy = false) const {
         check(b200_subring_ntt_host(ctx_.get(), limb, p1.data(), p2.data(), p1.size() < p2.size() ? p1.size() : p2.size(), inverse, lazy ? B200_LAZY : 0));
@@ -204,6 +227,21 @@ class KeySwitcher {
     void ModDownQPtoQNTT(int levelQ, int levelP, const Poly &p1, Poly &p2) const { check(b200_mod_down_ntt(ks_.get(), levelQ, levelP, p1.handle(), p2.handle())); }
     void GadgetProduct(int levelQ, int levelP, const Poly &cx, const Poly &key, Poly &ct0, Poly &ct1) const {
         check(b200_gadget_product(ks_.get(), levelQ, levelP, cx.handle(), key.handle(), ct0.handle(), ct1.handle()));
+    }
+    // one special prime with a power-of-two base (evaluator_gadget_product.go:190-320); sizes = BaseTwoDecompositionVectorSize
+    void GadgetProductBitDecomp(int levelQ, int levelP, int pw2, const std::vector<int> &sizes, const Poly &cx, const Poly &key, Poly &ct0, Poly &ct1) const {
+        check(b200_gadget_product_bit_decomp(ks_.get(), levelQ, levelP, pw2, sizes.data(), cx.handle(), key.handle(), ct0.handle(), ct1.handle()));
+    }
+    // hoisted form (evaluator_gadget_product.go:322-478): decomp holds beta*batch polynomials [digit][b]
+    void DecomposeNTT(int levelQ, int levelP, const Poly &cx, Poly &decomp) const { check(b200_decompose_ntt(ks_.get(), levelQ, levelP, cx.handle(), decomp.handle())); }
+    void GadgetProductHoisted(int levelQ, int levelP, const Poly &decomp, const Poly &key, Poly &ct0, Poly &ct1) const {
+        check(b200_gadget_product_hoisted(ks_.get(), levelQ, levelP, decomp.handle(), key.handle(), ct0.handle(), ct1.handle()));
+    }
+    // rlwe.Evaluator.Automorphism / AutomorphismHoisted (evaluator_automorphism.go:13-108), NTT domain
+    void Automorphism(int levelQ, int levelP, const Poly &ct0, const Poly &ct1, uint64_t galEl, const Poly &key, Poly &out0, Poly &out1,
+                      const Poly *decomp = nullptr) const {
+        check(b200_automorphism_ct(ks_.get(), levelQ, levelP, ct0.handle(), ct1.handle(), decomp ? decomp->handle() : nullptr, galEl, key.handle(),
+                                   out0.handle(), out1.handle()));
     }
     void MulRelin(int levelQ, int levelP, const Poly &a0, const Poly &a1, const Poly &b0, const Poly &b1, const Poly &rlk, Poly &o0, Poly &o1,
                   bool mform = true) const {

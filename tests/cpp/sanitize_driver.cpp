@@ -37,6 +37,20 @@ static void exercise(int N, const std::vector<uint64_t> &Q, int LQ, const char *
     const int ops[2] = {0, 1};
     ring::check(b200_transform_host(r.handle(), ha.data(), out.data(), batch, r.MaxLevel(), ops, 2, 0));
     EXPECT(out == ha);
+    if ((N & (N - 1)) == 0) {                                  // automorphisms and the monomial product (power-of-two rings)
+        const uint64_t gen = 5;
+        r.AutomorphismNTT(a, gen, c);
+        r.AutomorphismNTTWithIndex(a, ring::Ring::AutomorphismNTTIndex(N, 2 * (uint64_t)N, gen), d);
+        EXPECT(c.Get() == d.Get());
+        r.NTT(a, c); r.AutomorphismNTT(c, gen, d);             // AutomorphismNTT(NTT p) == NTT(Automorphism p)
+        r.Automorphism(a, gen, c); r.Reduce(c, c); r.NTT(c, c);
+        EXPECT(c.Get() == d.Get());
+        r.MultByMonomial(a, 1, c); r.MultByMonomial(c, 8, c); r.MultByMonomial(a, 9, d);
+        r.Reduce(c, c); r.Reduce(d, d);
+        EXPECT(c.Get() == d.Get());
+        r.Shift(a, 3, c); r.Shift(c, -3, c);
+        EXPECT(c.Get() == ha);
+    }
     if (LQ > 0) {
         b200_keyswitch *ks = nullptr;
         ring::check(b200_keyswitch_create(r.handle(), LQ, &ks));
@@ -62,6 +76,18 @@ int main() {
     exercise(1 << 17, {qi[0], qi[1]}, 0, "standard/2^17");
     exercise(3 << 12, q3, 3, "matrix/big-path");
     exercise(24, q3, 3, "matrix/resident");
+    {   // conjugate-invariant ring: round trip through the folding layer on both kernel families
+        for (int N : {64, 1 << 11}) {
+            ring::Ring r = ring::Ring::NewRingConjugateInvariant(N, {qi[0], qi[1]});
+            std::mt19937_64 g(7);
+            auto h = random_poly(g, 2, {qi[0], qi[1]}, N);
+            ring::Poly a = r.NewPoly(2), b = r.NewPoly(2);
+            a.Set(h);
+            r.NTT(a, b); r.INTT(b, b);
+            EXPECT(b.Get() == h);
+            std::printf("conjugate-invariant N=%d ok\n", N);
+        }
+    }
     std::printf(fails ? "FAILED\n" : "ok\n");
     return fails != 0;
 }
