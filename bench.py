@@ -32,6 +32,8 @@ MODULI = [0x1000000000248001, 0x1000000000b00001, 0x1000000000cf8001, 0x10000000
 L = len(MODULI)
 POLYS_PER_GPU = 128
 BYTES_PER_UNIT = 2 * N * 8            # algorithmic: read the limb once, write it once
+MODMULS_PER_UNIT = N // 2 + N + (N // 2) * 14       # cyclotomic layer + radix-3 layer + 14 radix-2 layers = 835 584
+BUTTERFLY_LOOP_PEAK = 850.0                           # G butterflies/s per B200, measured (see integer_roofline below)
 METRIC = "3N-NTT limb-transforms/sec at N=3*2^15, L=24"
 UNIT = "limb-transforms/s"
 WORKLOAD = "config3: 3N ring N=98304 (a=15,b=1), L=24 61-bit primes, batched NTT+INTT in place, limb-sharded"
@@ -279,6 +281,13 @@ def run_gpu(args):
     path_gbs = value / world * BYTES_PER_UNIT / 1e9
     path = {"achieved": path_gbs, "peak": peak, "unit": "GB/s per GPU", "frac": path_gbs / peak,
             "note": "whole transform (both passes) against 16*N algorithmic bytes per limb-transform"}
+    # the bound that actually binds: 64-bit modular butterflies on the integer pipes.  The ceiling is
+    # the register-resident loop of the same butterflies measured with tools/bfbench on this pool's B200s
+    # (profiles/r01_fp64_butterfly.txt: 850 G butterflies/s at 90 % multiply-pipe utilisation), not a datasheet number.
+    gbf = value / world * MODMULS_PER_UNIT / 1e9
+    integer = {"bound": "integer pipes", "achieved": gbf, "peak": BUTTERFLY_LOOP_PEAK, "unit": "G modular butterflies/s per GPU",
+               "frac": gbf / BUTTERFLY_LOOP_PEAK, "modmuls_per_limb_transform": MODMULS_PER_UNIT,
+               "peak_source": "tools/bfbench register-resident loop, profiles/r01_fp64_butterfly.txt"}
 
     # end to end through the C ABI with HOST buffers: pinned H2D + NTT + INTT + D2H inside the timed region
     e2e = None
@@ -298,7 +307,7 @@ def run_gpu(args):
                            "limb_transforms_per_step": world * units_per_step, "resident_bytes_per_gpu": nwords * 8,
                            "l2": "inputs (2.25 GiB per GPU) are larger than L2, no explicit flush",
                            "parallelism": "limb-sharded x%d, no collective" % world},
-                "roofline": roofline, "path_roofline": path, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+                "roofline": roofline, "path_roofline": path, "integer_roofline": integer, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
                 "clocks": clocks, "verified_against_oracle": verified}
         emit(line)
     if world > 1:
