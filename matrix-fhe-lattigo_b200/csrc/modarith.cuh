@@ -127,6 +127,15 @@ __device__ __forceinline__ u64 csub_fma(u64 x, u64 m, u64 nm) {
     return ((u64)madlo_u32(k, hi32(nm), hi32(r)) << 32) | lo32(r);
 }
 
+// x holds a two's-complement value in [-m, m): add m back if it is negative.  One sign test on the high word and two
+// predicated adds (3 instructions) instead of the 64-bit compare, two selects and the subtraction of csub (6).
+__device__ __forceinline__ u64 addback_neg(u64 x, u64 m) {
+    unsigned lo = lo32(x), hi = hi32(x);
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.s32 p, %1, 0;\n\t@p add.cc.u32 %0, %0, %2;\n\t@p addc.u32 %1, %1, %3;\n\t}"
+        : "+r"(lo), "+r"(hi) : "r"(lo32(m)), "r"(hi32(m)));
+    return ((u64)hi << 32) | lo;
+}
+
 // hi-word-only variant of csub_fma (2 ALU + 2 FMA): subtracts when hi32(x) > hi32(m).  The result is
 // < m + 2^32 for x < 2m + 2^32, which the lazy butterflies tolerate when 8q + 2^33 <= 2^64.
 __device__ __forceinline__ u64 csub_fma_hi(u64 x, u64 m, u64 nm) {

@@ -28,17 +28,27 @@
 #ifndef B200_CSUB_HI
 #define B200_CSUB_HI 0      // 1: compare high words only in the lazy conditional subtraction
 #endif
-// conditional subtraction of 4q inside the lazy butterflies: 1 = compare/select/subtract on the ALU pipe, 0 = as a
-// multiply-add by 2^64-4q on the multiply pipe.  Measured per kernel on B200: the forward (Cooley-Tukey) kernels are
-// 3-4 % faster with the ALU form, the inverse row kernels 1-2 % faster with the multiply-add form.
-#ifndef B200_CSUB_ALU_FWD
-#define B200_CSUB_ALU_FWD 1
+// Conditional subtraction of 4q inside the lazy butterflies, chosen per kernel family (each measured on B200):
+//   0 = multiply-add by 2^64-4q on the multiply pipe (compare + select + wide multiply-add)
+//   1 = compare / select / subtract on the ALU pipe (6 instructions)
+//   2 = subtract, then add 4q back if the result is negative: one sign test + two predicated adds; the subtraction folds
+//       into the three-input add that produces the value (inverse butterflies: 5 instead of 8 instructions)
+// Mode 2 against the previous choice: inverse rows -3.3 % (3N) / -6.1 % (2^16), inverse columns -0.5 %, forward rows
+// -1.5 % / -0.6 %, forward columns 2^16 -7.9 %, forward columns 3N +4.9 % (stays on mode 1).
+#ifndef B200_CSUB_FWD_ROWS
+#define B200_CSUB_FWD_ROWS 2
 #endif
-#ifndef B200_CSUB_ALU_INV
-#define B200_CSUB_ALU_INV 0        // inverse row kernels
+#ifndef B200_CSUB_FWD_COLS_STD
+#define B200_CSUB_FWD_COLS_STD 2
 #endif
-#ifndef B200_CSUB_ALU_INV_COLS
-#define B200_CSUB_ALU_INV_COLS 1   // inverse column kernels (1-1.5 % faster with the ALU form)
+#ifndef B200_CSUB_FWD_COLS_M3
+#define B200_CSUB_FWD_COLS_M3 1
+#endif
+#ifndef B200_CSUB_INV_ROWS
+#define B200_CSUB_INV_ROWS 2
+#endif
+#ifndef B200_CSUB_INV_COLS
+#define B200_CSUB_INV_COLS 2
 #endif
 #ifndef B200_CANON_EST
 #define B200_CANON_EST 1    // 1: final canonical reduction through a quotient estimate
@@ -140,16 +150,18 @@ __device__ __forceinline__ u64 csub4(u64 x, const QC &c) {
 // Harvey butterflies on the approximate Shoup product (shoup4: [0,4q)).  q < 2^61 so 8q fits in 64 bits.
 //   forward (Cooley-Tukey):   in [0,8q) -> out [0,8q)
 //   inverse (Gentleman-Sande): in [0,4q) -> out [0,4q)
+template <int MODE>
 __device__ __forceinline__ void bf_fwd(u64 &U, u64 &V, const tw_t w, const QC &c) {
-    const u64 u = csub4<B200_CSUB_ALU_FWD != 0>(U, c);
+    const u64 u = MODE == 2 ? addback_neg(U + c.nfourq, c.fourq) : csub4<MODE == 1>(U, c);
     const u64 t = shoup4(V, w.x, w.y, c.nq);
     U = u + t;
     V = u - t + c.fourq;
 }
-template <bool ALU>
+template <int MODE>
 __device__ __forceinline__ void bf_inv(u64 &U, u64 &V, const tw_t w, const QC &c) {
-    const u64 s = U + V, d = U - V + c.fourq;
-    U = csub4<ALU>(s, c);
+    const u64 d = U - V + c.fourq;
+    if (MODE == 2) U = addback_neg(U + V + c.nfourq, c.fourq);
+    else U = csub4<MODE == 1>(U + V, c);
     V = shoup4(d, w.x, w.y, c.nq);
 }
 // [0,8q) -> [0,q) and [0,4q) -> [0,2q)
@@ -165,7 +177,15 @@ __device__ __forceinline__ u64 to2q(u64 x, const QC &c) { return csub(x, c.twoq)
 
 // 2^LOGM-point sub-transform held in registers; x[k] ordered along the sub-dimension (MSB first);
 // P = heap index of the sub-transform's root node.
-template <int LOGM>
+// Inside a register group the role of every word in the next layer (kept operand U or multiplied operand V) is known at
+// compile time.  With B200_FWD_SIGNED_CHAIN a word that will be the U operand of the next layer is produced as value - 4q
+// (a free change of the constant in the three-input add), so that layer's conditional subtraction is only the sign test
+// and the two predicated adds (3 instructions instead of 5); the group's first layer takes unsigned words, its last layer
+// leaves unsigned words in [0,8q), so nothing changes outside the group.
+#ifndef B200_FWD_SIGNED_CHAIN
+#define B200_FWD_SIGNED_CHAIN 1
+#endif
+template <int LOGM, int MODE = B200_CSUB_FWD_ROWS>
 __device__ __forceinline__ void fwd_regs(u64 (&x)[1 << LOGM], unsigned P, const tw_t *__restrict__ tw, const QC &c) {
 #pragma unroll
     for (int j = 0; j < LOGM; ++j) {
@@ -174,11 +194,24 @@ __device__ __forceinline__ void fwd_regs(u64 (&x)[1 << LOGM], unsigned P, const 
         for (int g = 0; g < (1 << j); ++g) {
             const tw_t w = tw[(P << j) + g];
 #pragma unroll
-            for (int o = 0; o < half; ++o) bf_fwd(x[g * 2 * half + o], x[g * 2 * half + o + half], w, c);
+            for (int o = 0; o < half; ++o) {
+                if (MODE == 2 && B200_FWD_SIGNED_CHAIN) {
+                    u64 &U = x[g * 2 * half + o], &V = x[g * 2 * half + o + half];
+                    const int i0 = g * 2 * half + o, i1 = i0 + half, nh = half >> 1;
+                    const bool last = j + 1 >= LOGM;
+                    const bool u_next_is_u = !last && ((i0 / nh) & 1) == 0, v_next_is_u = !last && ((i1 / nh) & 1) == 0;
+                    const u64 u = addback_neg(j == 0 ? U + c.nfourq : U, c.fourq);      // layers >= 1 receive value - 4q
+                    const u64 t = shoup4(V, w.x, w.y, c.nq);
+                    U = u_next_is_u ? u + t + c.nfourq : u + t;
+                    V = v_next_is_u ? u - t : u - t + c.fourq;
+                } else {
+                    bf_fwd<MODE>(x[g * 2 * half + o], x[g * 2 * half + o + half], w, c);
+                }
+            }
         }
     }
 }
-template <int LOGM, int JMIN = 0, bool ALU = (B200_CSUB_ALU_INV != 0)>
+template <int LOGM, int JMIN = 0, int MODE = B200_CSUB_INV_ROWS>
 __device__ __forceinline__ void inv_regs(u64 (&x)[1 << LOGM], unsigned P, const tw_t *__restrict__ tw, const QC &c) {
 #pragma unroll
     for (int j = LOGM - 1; j >= JMIN; --j) {
@@ -187,7 +220,7 @@ __device__ __forceinline__ void inv_regs(u64 (&x)[1 << LOGM], unsigned P, const 
         for (int g = 0; g < (1 << j); ++g) {
             const tw_t w = tw[(P << j) + g];
 #pragma unroll
-            for (int o = 0; o < half; ++o) bf_inv<ALU>(x[g * 2 * half + o], x[g * 2 * half + o + half], w, c);
+            for (int o = 0; o < half; ++o) bf_inv<MODE>(x[g * 2 * half + o], x[g * 2 * half + o + half], w, c);
         }
     }
 }
@@ -466,14 +499,14 @@ k_cols_fwd_std16(const u64 *in, u64 *out, BigArgs a) {
     u64 x[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) x[k] = ldd(in + ibase + (size_t)(k * 32 + g) * 256 + c);      // rows k*32 + g
-    fwd_regs<3>(x, 1u, tw, qc);
+    fwd_regs<3, B200_CSUB_FWD_COLS_STD>(x, 1u, tw, qc);
 #pragma unroll
     for (int k = 0; k < 8; ++k) sm[pc((k * 32 + g) * CW + c)] = x[k];
     __syncthreads();
     const int lo2 = g & 3, hi3 = g >> 2;                                                 // rows hi3*32 + k*4 + lo2
 #pragma unroll
     for (int k = 0; k < 8; ++k) x[k] = sm[pc((hi3 * 32 + k * 4 + lo2) * CW + c)];
-    fwd_regs<3>(x, 8u + hi3, tw, qc);
+    fwd_regs<3, B200_CSUB_FWD_COLS_STD>(x, 8u + hi3, tw, qc);
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < 8; ++k) sm[pc((hi3 * 32 + k * 4 + lo2) * CW + c)] = x[k];
@@ -483,8 +516,8 @@ k_cols_fwd_std16(const u64 *in, u64 *out, BigArgs a) {
     {
         u64 (&lo)[4] = *reinterpret_cast<u64 (*)[4]>(&x[0]);
         u64 (&hi)[4] = *reinterpret_cast<u64 (*)[4]>(&x[4]);
-        fwd_regs<2>(lo, 64u + g * 2, tw, qc);
-        fwd_regs<2>(hi, 64u + g * 2 + 1, tw, qc);
+        fwd_regs<2, B200_CSUB_FWD_COLS_STD>(lo, 64u + g * 2, tw, qc);
+        fwd_regs<2, B200_CSUB_FWD_COLS_STD>(hi, 64u + g * 2 + 1, tw, qc);
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k) std_(out + obase + (size_t)(g * 8 + k) * 256 + c, x[k]);
@@ -509,8 +542,8 @@ k_cols_inv_std16(const u64 *in, u64 *out, BigArgs a) {
     {
         u64 (&lo)[4] = *reinterpret_cast<u64 (*)[4]>(&x[0]);
         u64 (&hi)[4] = *reinterpret_cast<u64 (*)[4]>(&x[4]);
-        inv_regs<2, 0, (B200_CSUB_ALU_INV_COLS != 0)>(lo, 64u + g * 2, tw, qc);
-        inv_regs<2, 0, (B200_CSUB_ALU_INV_COLS != 0)>(hi, 64u + g * 2 + 1, tw, qc);
+        inv_regs<2, 0, B200_CSUB_INV_COLS>(lo, 64u + g * 2, tw, qc);
+        inv_regs<2, 0, B200_CSUB_INV_COLS>(hi, 64u + g * 2 + 1, tw, qc);
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k) sm[pc((g * 8 + k) * CW + c)] = x[k];
@@ -518,14 +551,14 @@ k_cols_inv_std16(const u64 *in, u64 *out, BigArgs a) {
     const int lo2 = g & 3, hi3 = g >> 2;
 #pragma unroll
     for (int k = 0; k < 8; ++k) x[k] = sm[pc((hi3 * 32 + k * 4 + lo2) * CW + c)];
-    inv_regs<3, 0, (B200_CSUB_ALU_INV_COLS != 0)>(x, 8u + hi3, tw, qc);
+    inv_regs<3, 0, B200_CSUB_INV_COLS>(x, 8u + hi3, tw, qc);
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < 8; ++k) sm[pc((hi3 * 32 + k * 4 + lo2) * CW + c)] = x[k];
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < 8; ++k) x[k] = sm[pc((k * 32 + g) * CW + c)];
-    inv_regs<3, 1, (B200_CSUB_ALU_INV_COLS != 0)>(x, 1u, tw, qc);
+    inv_regs<3, 1, B200_CSUB_INV_COLS>(x, 1u, tw, qc);
 #pragma unroll
     for (int o = 0; o < 4; ++o) {   // last layer carries N^-1
         const u64 U = x[o], V = x[o + 4];
@@ -584,7 +617,7 @@ k_cols_fwd_m3_15(const u64 *in, u64 *out, BigArgs a) {
         }
 #pragma unroll
         for (int hd = 0; hd < 6; ++hd) {
-            bf_fwd(x[hd][0], x[hd][1], tw[6 + hd], qc);   // radix-2 layer 0 of block hd
+            bf_fwd<B200_CSUB_FWD_COLS_M3>(x[hd][0], x[hd][1], tw[6 + hd], qc);   // radix-2 layer 0 of block hd
 #pragma unroll
             for (int b = 0; b < 2; ++b) sm[pc((hd * 64 + b * 32 + g) * CW + c)] = x[hd][b];
         }
@@ -595,7 +628,7 @@ k_cols_fwd_m3_15(const u64 *in, u64 *out, BigArgs a) {
         const int lo2 = g & 3, top = g >> 2;
 #pragma unroll
         for (int k = 0; k < 8; ++k) x[k] = sm[pc((top * 32 + k * 4 + lo2) * CW + c)];
-        fwd_regs<3>(x, 12u + top, tw, qc);
+        fwd_regs<3, B200_CSUB_FWD_COLS_M3>(x, 12u + top, tw, qc);
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < 8; ++k) sm[pc((top * 32 + k * 4 + lo2) * CW + c)] = x[k];
@@ -606,8 +639,8 @@ k_cols_fwd_m3_15(const u64 *in, u64 *out, BigArgs a) {
         for (int k = 0; k < 8; ++k) x[k] = sm[pc((g * 8 + k) * CW + c)];
         u64 (&lo)[4] = *reinterpret_cast<u64 (*)[4]>(&x[0]);
         u64 (&hi)[4] = *reinterpret_cast<u64 (*)[4]>(&x[4]);
-        fwd_regs<2>(lo, 96u + g * 2, tw, qc);
-        fwd_regs<2>(hi, 96u + g * 2 + 1, tw, qc);
+        fwd_regs<2, B200_CSUB_FWD_COLS_M3>(lo, 96u + g * 2, tw, qc);
+        fwd_regs<2, B200_CSUB_FWD_COLS_M3>(hi, 96u + g * 2 + 1, tw, qc);
 #pragma unroll
         for (int k = 0; k < 8; ++k) std_(out + obase + (size_t)(g * 8 + k) * 256 + c, x[k]);
     }
@@ -632,15 +665,15 @@ k_cols_inv_m3_15(const u64 *in, u64 *out, BigArgs a) {
         for (int k = 0; k < 8; ++k) x[k] = ldd(in + ibase + (size_t)(g * 8 + k) * 256 + c);
         u64 (&lo)[4] = *reinterpret_cast<u64 (*)[4]>(&x[0]);
         u64 (&hi)[4] = *reinterpret_cast<u64 (*)[4]>(&x[4]);
-        inv_regs<2, 0, (B200_CSUB_ALU_INV_COLS != 0)>(lo, 96u + g * 2, tw, qc);
-        inv_regs<2, 0, (B200_CSUB_ALU_INV_COLS != 0)>(hi, 96u + g * 2 + 1, tw, qc);
+        inv_regs<2, 0, B200_CSUB_INV_COLS>(lo, 96u + g * 2, tw, qc);
+        inv_regs<2, 0, B200_CSUB_INV_COLS>(hi, 96u + g * 2 + 1, tw, qc);
 #pragma unroll
         for (int k = 0; k < 8; ++k) sm[pc((g * 8 + k) * CW + c)] = x[k];
         __syncthreads();
         const int lo2 = g & 3, top = g >> 2;
 #pragma unroll
         for (int k = 0; k < 8; ++k) x[k] = sm[pc((top * 32 + k * 4 + lo2) * CW + c)];
-        inv_regs<3, 0, (B200_CSUB_ALU_INV_COLS != 0)>(x, 12u + top, tw, qc);
+        inv_regs<3, 0, B200_CSUB_INV_COLS>(x, 12u + top, tw, qc);
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < 8; ++k) sm[pc((top * 32 + k * 4 + lo2) * CW + c)] = x[k];
@@ -653,7 +686,7 @@ k_cols_inv_m3_15(const u64 *in, u64 *out, BigArgs a) {
         for (int hd = 0; hd < 6; ++hd) {
 #pragma unroll
             for (int b = 0; b < 2; ++b) x[hd][b] = sm[pc((hd * 64 + b * 32 + g) * CW + c)];
-            bf_inv<(B200_CSUB_ALU_INV_COLS != 0)>(x[hd][0], x[hd][1], tw[6 + hd], qc);
+            bf_inv<B200_CSUB_INV_COLS>(x[hd][0], x[hd][1], tw[6 + hd], qc);
         }
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
@@ -711,11 +744,11 @@ __device__ __forceinline__ void col_group(const u64 *gin, size_t ibase, u64 *gou
         }
         const unsigned P = (unsigned)((ROOTS << (LOG - b0 - S)) + hi);
         if (!INV) {
-            fwd_regs<S>(x, P, tw, qc);
+            fwd_regs<S, (ROOTS == 1 ? B200_CSUB_FWD_COLS_STD : B200_CSUB_FWD_COLS_M3)>(x, P, tw, qc);
         } else if (!FOLD_NINV) {
-            inv_regs<S, 0, (B200_CSUB_ALU_INV_COLS != 0)>(x, P, tw, qc);
+            inv_regs<S, 0, B200_CSUB_INV_COLS>(x, P, tw, qc);
         } else {   // top group of the STANDARD inverse: the last layer carries N^-1
-            inv_regs<S, 1, (B200_CSUB_ALU_INV_COLS != 0)>(x, P, tw, qc);
+            inv_regs<S, 1, B200_CSUB_INV_COLS>(x, P, tw, qc);
 #pragma unroll
             for (int o = 0; o < M / 2; ++o) {
                 const u64 U = x[o], V = x[o + M / 2];
@@ -821,7 +854,7 @@ k_cols_m3_g(const u64 *in, u64 *out, BigArgs a) {
             }
 #pragma unroll
             for (int hd = 0; hd < 6; ++hd) {
-                if (S1 > 0) fwd_regs<S1>(x[hd], (unsigned)(6 + hd), tw, qc);
+                if (S1 > 0) fwd_regs<S1, B200_CSUB_FWD_COLS_M3>(x[hd], (unsigned)(6 + hd), tw, qc);
 #pragma unroll
                 for (int k = 0; k < MA; ++k) sm[pc((hd * U + k * ULO + ulo) * GCW + c)] = x[hd][k];
             }
@@ -851,7 +884,7 @@ k_cols_m3_g(const u64 *in, u64 *out, BigArgs a) {
             for (int hd = 0; hd < 6; ++hd) {
 #pragma unroll
                 for (int k = 0; k < MA; ++k) x[hd][k] = sm[pc((hd * U + k * ULO + ulo) * GCW + c)];
-                if (S1 > 0) inv_regs<S1, 0, (B200_CSUB_ALU_INV_COLS != 0)>(x[hd], (unsigned)(6 + hd), tw, qc);
+                if (S1 > 0) inv_regs<S1, 0, B200_CSUB_INV_COLS>(x[hd], (unsigned)(6 + hd), tw, qc);
             }
 #pragma unroll
             for (int k = 0; k < MA; ++k) {
