@@ -147,10 +147,15 @@ __device__ __forceinline__ u64 csub_fma_hi(u64 x, u64 m, u64 nm) {
 // x < 16q  ->  [0, q) through a 32-bit quotient estimate (1 shift + 1 mul.hi + 2 multiply-adds) and one
 // conditional subtraction, instead of a chain of three or four conditional subtractions.
 // FINAL_ALU: the last conditional subtraction as compare/select/subtract (ALU pipe) instead of a multiply-add.
-template <bool FINAL_ALU = false>
+// FINAL: last conditional subtraction as 0 = multiply-add, 1 = compare/select/subtract, 2 = one more q subtracted up front
+// (the +1 rides on the mad.hi that computes the estimate) and added back if the result is negative (sign test + two
+// predicated adds): 7 instructions for the whole reduction.
+template <int FINAL = 0>
 __device__ __forceinline__ u64 canon_est(u64 x, u64 q, u64 nq, unsigned sh, unsigned mul) {
-    const unsigned k = __umulhi((unsigned)(x >> sh), mul);
+    unsigned k;
+    if (FINAL == 2) asm("mad.hi.u32 %0, %1, %2, 1;" : "=r"(k) : "r"((unsigned)(x >> sh)), "r"(mul));
+    else k = __umulhi((unsigned)(x >> sh), mul);
     const u64 r = madwide_u32(k, lo32(nq), x);
     const u64 y = ((u64)madlo_u32(k, hi32(nq), hi32(r)) << 32) | lo32(r);
-    return FINAL_ALU ? csub(y, q) : csub_fma(y, q, nq);
+    return FINAL == 2 ? addback_neg(y, q) : FINAL == 1 ? csub(y, q) : csub_fma(y, q, nq);
 }

@@ -53,8 +53,12 @@
 #ifndef B200_CANON_EST
 #define B200_CANON_EST 1    // 1: final canonical reduction through a quotient estimate
 #endif
-#ifndef B200_CANON_FINAL_ALU_M3
-#define B200_CANON_FINAL_ALU_M3 0   // last conditional subtraction of the 3N forward row pass: 1 = compare/select, 0 = multiply-add
+// last conditional subtraction of the canonical reduction in the forward row pass (modes of canon_est)
+#ifndef B200_CANON_FINAL_M3
+#define B200_CANON_FINAL_M3 2
+#endif
+#ifndef B200_CANON_FINAL_STD
+#define B200_CANON_FINAL_STD 2
 #endif
 // columns per CTA in the hand-tuned column kernels (the generic family uses 8).  Measured on B200: all four tuned
 // kernels gain 2-6% from 4-column tiles (192-thread CTAs, shorter barrier waits).
@@ -165,14 +169,18 @@ __device__ __forceinline__ void bf_inv(u64 &U, u64 &V, const tw_t w, const QC &c
     V = shoup4(d, w.x, w.y, c.nq);
 }
 // [0,8q) -> [0,q) and [0,4q) -> [0,2q)
-template <bool FINAL_ALU = false>
+template <int FINAL = 0>
 __device__ __forceinline__ u64 canon8(u64 x, const QC &c) {
 #if B200_CANON_EST
-    return canon_est<FINAL_ALU>(x, c.q, c.nq, c.csh, c.cmul);
+    return canon_est<FINAL>(x, c.q, c.nq, c.csh, c.cmul);
 #else
     return csub(csub(csub(csub(x, c.fourq), c.twoq), c.q), c.q);
 #endif
 }
+// Conditional subtraction in add-back form for a value the caller already reduced by m (sum_minus_m in [-m, m)).  Used for
+// the last step of the power-of-two inverse column pass (-6 % on that kernel); the cyclotomic / radix-3 layers of the 3N
+// column kernels keep the compare/select form: converting them measured 8 % (forward) and 2 % (inverse) slower.
+__device__ __forceinline__ u64 red_ab(u64 sum_minus_m, u64 m) { return addback_neg(sum_minus_m, m); }
 __device__ __forceinline__ u64 to2q(u64 x, const QC &c) { return csub(x, c.twoq); }
 
 // 2^LOGM-point sub-transform held in registers; x[k] ordered along the sub-dimension (MSB first);
@@ -380,7 +388,7 @@ k_rows_fwd(const u64 *in, u64 *out, BigArgs a) {
     for (int k = 0; k < 8; ++k) x[k] = ldd(src + k * 32 + lane);
     row_fwd_core(x, buf, lane, P1, tw, qc);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) x[k] = (a.flags & B200_LAZY) ? csub(x[k], qc.fourq) : canon8<(!MATRIX || B200_CANON_FINAL_ALU_M3)>(x[k], qc);   // lazy: [0,4q) <= 6q-2
+    for (int k = 0; k < 8; ++k) x[k] = (a.flags & B200_LAZY) ? csub(x[k], qc.fourq) : canon8<(MATRIX ? B200_CANON_FINAL_M3 : B200_CANON_FINAL_STD)>(x[k], qc);   // lazy: [0,4q) <= 6q-2
     if (!MATRIX || (a.flags & B200_TREE_ORDER)) {
         u64 *dst = out + ur.out + (size_t)r * 256 + lane * 8;
         stg256(dst, x[0], x[1], x[2], x[3]);
@@ -564,7 +572,7 @@ k_cols_inv_std16(const u64 *in, u64 *out, BigArgs a) {
         const u64 U = x[o], V = x[o + 4];
         u64 X = shoup_lazy(U + V, ninv.x, ninv.y, q);
         u64 Y = shoup_lazy(U - V + qc.fourq, ninv_w1.x, ninv_w1.y, q);   // inputs < 4q
-        if (!lazy) { X = csub(X, q); Y = csub(Y, q); }
+        if (!lazy) { X = red_ab(X - q, q); Y = red_ab(Y - q, q); }
         x[o] = X; x[o + 4] = Y;
     }
 #pragma unroll
@@ -754,7 +762,7 @@ __device__ __forceinline__ void col_group(const u64 *gin, size_t ibase, u64 *gou
                 const u64 U = x[o], V = x[o + M / 2];
                 u64 X = shoup_lazy(U + V, ninv.x, ninv.y, qc.q);
                 u64 Y = shoup_lazy(U - V + qc.fourq, ninv_w1.x, ninv_w1.y, qc.q);
-                if (!lazy) { X = csub(X, qc.q); Y = csub(Y, qc.q); }
+                if (!lazy) { X = red_ab(X - qc.q, qc.q); Y = red_ab(Y - qc.q, qc.q); }
                 x[o] = X; x[o + M / 2] = Y;
             }
         }
