@@ -50,6 +50,9 @@
 #ifndef B200_CSUB_INV_COLS
 #define B200_CSUB_INV_COLS 2
 #endif
+#ifndef B200_R3INV_APPROX
+#define B200_R3INV_APPROX 1   // inverse radix-3 layer of the 3N column kernels on approximate-quotient products (-2.3 % on that kernel)
+#endif
 #ifndef B200_CANON_EST
 #define B200_CANON_EST 1    // 1: final canonical reduction through a quotient estimate
 #endif
@@ -702,15 +705,24 @@ k_cols_inv_m3_15(const u64 *in, u64 *out, BigArgs a) {
             for (int h = 0; h < 2; ++h) {   // inverse radix-3 (factor 3 deferred): [0,2q) -> [0,2q)
                 const tw_t z1 = tw[2 + 2 * h], z2 = tw[3 + 2 * h];
                 const u64 y0 = to2q(x[3 * h][b], qc), y1 = to2q(x[3 * h + 1][b], qc), y2 = to2q(x[3 * h + 2][b], qc);
+#if B200_R3INV_APPROX
+                // the three products feed only other products, so the approximate quotient ([0,4q)) is enough:
+                // offsets grow by 2q, every operand stays below 8q < 2^64
+                const u64 s = shoup4(y1 + twoq - y2, om.x, om.y, qc.nq);
+                x[3 * h][b] = csub(csub(y0 + y1 + y2, fourq), twoq);
+                x[3 * h + 1][b] = shoup4(y0 + fourq + twoq - y1 - s, z1.x, z1.y, qc.nq);
+                x[3 * h + 2][b] = shoup4(y0 + twoq - y2 + s, z2.x, z2.y, qc.nq);
+#else
                 const u64 s = shoup_lazy(y1 + twoq - y2, om.x, om.y, q);
                 x[3 * h][b] = csub(csub(y0 + y1 + y2, fourq), twoq);
                 x[3 * h + 1][b] = shoup_lazy(y0 + fourq - y1 - s, z1.x, z1.y, q);
                 x[3 * h + 2][b] = shoup_lazy(y0 + twoq - y2 + s, z2.x, z2.y, q);
+#endif
             }
 #pragma unroll
             for (int d = 0; d < 3; ++d) {   // inverse cyclotomic layer with the 2/N scaling
                 const u64 lo = x[d][b], hi = x[d + 3][b];
-                u64 hh = shoup_lazy(lo + twoq - hi, k1.x, k1.y, q);
+                u64 hh = shoup_lazy(lo + (B200_R3INV_APPROX ? fourq : twoq) - hi, k1.x, k1.y, q);
                 u64 ll = csub(shoup_lazy(lo, k2.x, k2.y, q) + twoq - shoup_lazy(hh, zeta.x, zeta.y, q), twoq);
                 if (!lazy) { ll = csub(ll, q); hh = csub(hh, q); }
                 x[d][b] = ll; x[d + 3][b] = hh;
@@ -900,15 +912,22 @@ k_cols_m3_g(const u64 *in, u64 *out, BigArgs a) {
                 for (int h = 0; h < 2; ++h) {   // inverse radix-3 (factor 3 deferred)
                     const tw_t z1 = tw[2 + 2 * h], z2 = tw[3 + 2 * h];
                     const u64 y0 = to2q(x[3 * h][k], qc), y1 = to2q(x[3 * h + 1][k], qc), y2 = to2q(x[3 * h + 2][k], qc);
+#if B200_R3INV_APPROX
+                    const u64 sgm = shoup4(y1 + twoq - y2, om.x, om.y, qc.nq);
+                    x[3 * h][k] = csub(csub(y0 + y1 + y2, fourq), twoq);
+                    x[3 * h + 1][k] = shoup4(y0 + fourq + twoq - y1 - sgm, z1.x, z1.y, qc.nq);
+                    x[3 * h + 2][k] = shoup4(y0 + twoq - y2 + sgm, z2.x, z2.y, qc.nq);
+#else
                     const u64 sgm = shoup_lazy(y1 + twoq - y2, om.x, om.y, q);
                     x[3 * h][k] = csub(csub(y0 + y1 + y2, fourq), twoq);
                     x[3 * h + 1][k] = shoup_lazy(y0 + fourq - y1 - sgm, z1.x, z1.y, q);
                     x[3 * h + 2][k] = shoup_lazy(y0 + twoq - y2 + sgm, z2.x, z2.y, q);
+#endif
                 }
 #pragma unroll
                 for (int d = 0; d < 3; ++d) {   // inverse cyclotomic layer with the 2/N scaling
                     const u64 lo = x[d][k], hi = x[d + 3][k];
-                    u64 hh = shoup_lazy(lo + twoq - hi, k1.x, k1.y, q);
+                    u64 hh = shoup_lazy(lo + (B200_R3INV_APPROX ? fourq : twoq) - hi, k1.x, k1.y, q);
                     u64 ll = csub(shoup_lazy(lo, k2.x, k2.y, q) + twoq - shoup_lazy(hh, zeta.x, zeta.y, q), twoq);
                     if (!lazy) { ll = csub(ll, q); hh = csub(hh, q); }
                     x[d][k] = ll; x[d + 3][k] = hh;
