@@ -120,6 +120,7 @@ struct BigArgs {
     int unit0, flags;
     int in_dense, out_dense;   // the pointer is a dense [chunk][N] ring buffer indexed by blockIdx.y
     PeerOut peers;             // GATHER kernels only: mirrors of `out` on other GPUs
+    u64 div_magic;             // ceil(2^40 / batch): unit / batch = (unit * div_magic) >> 40 for unit < 2^22, batch < 2^18; 0 = divide
 };
 
 // word offsets of this CTA's unit in the input and output buffers, and its prime
@@ -133,7 +134,8 @@ template <bool COLS = false>
 __device__ __forceinline__ UnitRef unit_ref(const BigArgs &a) {
     const int u = COLS ? blockIdx.y : blockIdx.x;
     const int unit = a.unit0 + u;
-    const int l = unit / a.sp.batch, b = unit - l * a.sp.batch;
+    // a runtime integer division costs ~30 instructions per thread (reciprocal + fix-ups); the host-prepared multiplier, 4
+    const int l = a.div_magic ? (int)(((u64)(unsigned)unit * a.div_magic) >> 40) : unit / a.sp.batch, b = unit - l * a.sp.batch;
     const size_t layout = ((size_t)b * a.sp.Lbuf + l) * (size_t)a.N;
     const size_t dense = (size_t)u * (size_t)a.N;
     return {a.in_dense ? dense : layout, a.out_dense ? dense : layout, a.sp.limb0 + l};
@@ -995,6 +997,12 @@ int env_int(const char *name, int dflt) {
     return v ? std::atoi(v) : dflt;
 }
 
+u64 unit_div_magic(const Span &sp) {
+    const long long units = (long long)sp.batch * sp.nl;
+    if (sp.batch >= (1 << 18) || units >= (1LL << 22)) return 0;
+    return ((1ULL << 40) + (u64)sp.batch - 1) / (u64)sp.batch;
+}
+
 template <typename K>
 int set_smem(K kern, size_t bytes) {
     if (bytes > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -1034,6 +1042,7 @@ int launch_ntt_big(b200_ctx *ctx, const u64 *in, u64 *out, Span sp, bool inverse
     const bool permute = matrix && !(flags & B200_TREE_ORDER);
     const int N = ctx->N, R = N / 256, cw = inverse ? (gather ? plan->cw_gather : plan->cw_inv) : plan->cw_fwd, vt = plan->vt;
     BigArgs a{ctx->d_consts, ctx->d_fwd, ctx->d_inv, ctx->d_misc, N, R, matrix ? ctx->a - 9 : 0, sp, 0, flags, 0, 0};
+    a.div_magic = unit_div_magic(sp);
     const kern_t ck = inverse ? (gather ? plan->cols_inv_gather : plan->cols_inv) : plan->cols_fwd;
     const int col_threads = inverse ? (gather ? plan->col_threads_gather : plan->col_threads_inv) : plan->col_threads_fwd;
     kern_t rk;
@@ -1094,6 +1103,7 @@ int launch_polymul_big(b200_ctx *ctx, const u64 *pa, const u64 *pb, u64 *pc, Spa
     const int N = ctx->N, R = N / 256;
     const int flags = matrix ? B200_TREE_ORDER : 0;
     BigArgs a{ctx->d_consts, ctx->d_fwd, ctx->d_inv, ctx->d_misc, N, R, matrix ? ctx->a - 9 : 0, sp, 0, flags, 0, 0};
+    a.div_magic = unit_div_magic(sp);
     const kern_t cf = plan->cols_fwd, ci = plan->cols_inv;
     auto col_smem_of = [R](int cw) { const int rows_total = R * cw; return (size_t)(rows_total + ((rows_total >> 6) << 3) + 8) * sizeof(u64); };
     const size_t smem_f = col_smem_of(plan->cw_fwd), smem_i = col_smem_of(plan->cw_inv);
