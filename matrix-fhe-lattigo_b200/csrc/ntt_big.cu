@@ -120,7 +120,7 @@ struct BigArgs {
     int unit0, flags;
     int in_dense, out_dense;   // the pointer is a dense [chunk][N] ring buffer indexed by blockIdx.y
     PeerOut peers;             // GATHER kernels only: mirrors of `out` on other GPUs
-    u64 div_magic;             // ceil(2^40 / batch): unit / batch = (unit * div_magic) >> 40 for unit < 2^22, batch < 2^18; 0 = divide
+    u64 div_magic;             // ceil(2^64 / batch): unit / batch = hi64(unit * div_magic) for unit, batch < 2^31; 0 = batch is 1
 };
 
 // word offsets of this CTA's unit in the input and output buffers, and its prime
@@ -135,7 +135,7 @@ __device__ __forceinline__ UnitRef unit_ref(const BigArgs &a) {
     const int u = COLS ? blockIdx.y : blockIdx.x;
     const int unit = a.unit0 + u;
     // a runtime integer division costs ~30 instructions per thread (reciprocal + fix-ups); the host-prepared multiplier, 4
-    const int l = a.div_magic ? (int)(((u64)(unsigned)unit * a.div_magic) >> 40) : unit / a.sp.batch, b = unit - l * a.sp.batch;
+    const int l = a.div_magic ? (int)__umul64hi((u64)(unsigned)unit, a.div_magic) : unit, b = unit - l * a.sp.batch;
     const size_t layout = ((size_t)b * a.sp.Lbuf + l) * (size_t)a.N;
     const size_t dense = (size_t)u * (size_t)a.N;
     return {a.in_dense ? dense : layout, a.out_dense ? dense : layout, a.sp.limb0 + l};
@@ -409,8 +409,12 @@ k_rows_fwd(const u64 *in, u64 *out, BigArgs a) {
         u64 *dst = out + ur.out + (size_t)blockIdx.y * RUN;
         {   // WARPS*32 = 32*RUN threads: thread -> (cr0, rem) once, then cr advances by 32 per step
             const int cr0 = threadIdx.x / RUN, rem = threadIdx.x - cr0 * RUN;
+            // stage_row(cr0 + 32 i) = stage_row(cr0) + 32 i (RUN + 1): constant shared-memory offsets, one running global pointer
+            const u64 *sp = sm + stage_row<RUN>(cr0) + rem;
+            u64 *gp = dst + (size_t)cr0 * run + rem;
+            const size_t gstep = 32 * run;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) std_(dst + (size_t)(cr0 + 32 * i) * run + rem, sm[stage_row<RUN>(cr0 + 32 * i) + rem]);
+            for (int i = 0; i < 8; ++i, gp += gstep) std_(gp, sp[i * 32 * (RUN + 1)]);
         }
     }
 }
@@ -441,10 +445,13 @@ k_rows_inv(const u64 *in, u64 *out, BigArgs a) {
         {
             const int cr0 = threadIdx.x / RUN, rem = threadIdx.x - cr0 * RUN;
             u64 v[8];
+            const u64 *gp = src + (size_t)cr0 * run + rem;
+            const size_t gstep = 32 * run;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = ldd(src + (size_t)(cr0 + 32 * i) * run + rem);     // all 8 loads in flight
+            for (int i = 0; i < 8; ++i, gp += gstep) v[i] = ldd(gp);     // all 8 loads in flight
+            u64 *sp = sm + stage_row<RUN>(cr0) + rem;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) sm[stage_row<RUN>(cr0 + 32 * i) + rem] = v[i];
+            for (int i = 0; i < 8; ++i) sp[i * 32 * (RUN + 1)] = v[i];
         }
         __syncthreads();
         const int rl = (int)rev_bits((unsigned)lane, 5);
@@ -998,9 +1005,9 @@ int env_int(const char *name, int dflt) {
 }
 
 u64 unit_div_magic(const Span &sp) {
-    const long long units = (long long)sp.batch * sp.nl;
-    if (sp.batch >= (1 << 18) || units >= (1LL << 22)) return 0;
-    return ((1ULL << 40) + (u64)sp.batch - 1) / (u64)sp.batch;
+    // m = ceil(2^64/d): unit*m/2^64 = unit/d + e with 0 <= e < unit/2^64 < 2^-33 < 1/d, so the floor is exact
+    if (sp.batch <= 1) return 0;
+    return ~0ULL / (u64)sp.batch + 1;
 }
 
 template <typename K>
