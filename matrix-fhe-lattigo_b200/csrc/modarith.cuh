@@ -157,5 +157,5 @@ __device__ __forceinline__ u64 canon_est(u64 x, u64 q, u64 nq, unsigned sh, unsi
     else k = __umulhi((unsigned)(x >> sh), mul);
     const u64 r = madwide_u32(k, lo32(nq), x);
     const u64 y = ((u64)madlo_u32(k, hi32(nq), hi32(r)) << 32) | lo32(r);
-    return FINAL == 2 ? addback_neg(y, q) : FINAL == 1 ? csub(y, q) : csub_fma(y, q, nq);
+    return FINAL == 3 ? y : FINAL == 2 ? addback_neg(y, q) : FINAL == 1 ? csub(y, q) : csub_fma(y, q, nq);   // 3: lazy, [0, 2q)
 }

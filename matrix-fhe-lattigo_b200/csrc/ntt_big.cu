@@ -53,6 +53,9 @@
 #ifndef B200_R3INV_APPROX
 #define B200_R3INV_APPROX 1   // inverse radix-3 layer of the 3N column kernels on approximate-quotient products (-2.3 % on that kernel)
 #endif
+#ifndef B200_CYCINV_APPROX
+#define B200_CYCINV_APPROX 0   // inverse cyclotomic layer on approximate-quotient products + quotient-estimate reduction: measured 3 % slower
+#endif
 #ifndef B200_CANON_EST
 #define B200_CANON_EST 1    // 1: final canonical reduction through a quotient estimate
 #endif
@@ -731,9 +734,16 @@ k_cols_inv_m3_15(const u64 *in, u64 *out, BigArgs a) {
 #pragma unroll
             for (int d = 0; d < 3; ++d) {   // inverse cyclotomic layer with the 2/N scaling
                 const u64 lo = x[d][b], hi = x[d + 3][b];
+                #if B200_CYCINV_APPROX
+                u64 hh = shoup4(lo + (B200_R3INV_APPROX ? fourq : twoq) - hi, k1.x, k1.y, qc.nq);                        // [0,4q)
+                u64 ll = shoup4(lo, k2.x, k2.y, qc.nq) + fourq - shoup4(hh, zeta.x, zeta.y, qc.nq);                      // (0,8q)
+                if (!lazy) { ll = canon_est<2>(ll, q, qc.nq, qc.csh, qc.cmul); hh = canon_est<2>(hh, q, qc.nq, qc.csh, qc.cmul); }
+                else { ll = canon_est<3>(ll, q, qc.nq, qc.csh, qc.cmul); hh = csub(hh, twoq); }
+#else
                 u64 hh = shoup_lazy(lo + (B200_R3INV_APPROX ? fourq : twoq) - hi, k1.x, k1.y, q);
                 u64 ll = csub(shoup_lazy(lo, k2.x, k2.y, q) + twoq - shoup_lazy(hh, zeta.x, zeta.y, q), twoq);
                 if (!lazy) { ll = csub(ll, q); hh = csub(hh, q); }
+#endif
                 x[d][b] = ll; x[d + 3][b] = hh;
             }
         }
@@ -936,9 +946,16 @@ k_cols_m3_g(const u64 *in, u64 *out, BigArgs a) {
 #pragma unroll
                 for (int d = 0; d < 3; ++d) {   // inverse cyclotomic layer with the 2/N scaling
                     const u64 lo = x[d][k], hi = x[d + 3][k];
+                    #if B200_CYCINV_APPROX
+                    u64 hh = shoup4(lo + (B200_R3INV_APPROX ? fourq : twoq) - hi, k1.x, k1.y, qc.nq);                        // [0,4q)
+                    u64 ll = shoup4(lo, k2.x, k2.y, qc.nq) + fourq - shoup4(hh, zeta.x, zeta.y, qc.nq);                      // (0,8q)
+                    if (!lazy) { ll = canon_est<2>(ll, q, qc.nq, qc.csh, qc.cmul); hh = canon_est<2>(hh, q, qc.nq, qc.csh, qc.cmul); }
+                    else { ll = canon_est<3>(ll, q, qc.nq, qc.csh, qc.cmul); hh = csub(hh, twoq); }
+#else
                     u64 hh = shoup_lazy(lo + (B200_R3INV_APPROX ? fourq : twoq) - hi, k1.x, k1.y, q);
                     u64 ll = csub(shoup_lazy(lo, k2.x, k2.y, q) + twoq - shoup_lazy(hh, zeta.x, zeta.y, q), twoq);
                     if (!lazy) { ll = csub(ll, q); hh = csub(hh, q); }
+#endif
                     x[d][k] = ll; x[d + 3][k] = hh;
                 }
             }
