@@ -119,14 +119,6 @@ __device__ __forceinline__ u64 shoup4(u64 x, u64 w, u64 ws, u64 nq) {
     r1 = madlo_u32(t1, lo32(nq), r1);
     return ((u64)r1 << 32) | lo32(r);
 }
-// x >= m ? x - m : x with the subtraction done as a multiply-add by nm = 2^64 - m on the FMA pipe:
-// 3 ALU (compare + select) + 2 FMA instructions instead of 6 ALU.
-__device__ __forceinline__ u64 csub_fma(u64 x, u64 m, u64 nm) {
-    const unsigned k = x >= m ? 1u : 0u;
-    const u64 r = madwide_u32(k, lo32(nm), x);
-    return ((u64)madlo_u32(k, hi32(nm), hi32(r)) << 32) | lo32(r);
-}
-
 // x holds a two's-complement value in [-m, m): add m back if it is negative.  One sign test on the high word and two
 // predicated adds (3 instructions) instead of the 64-bit compare, two selects and the subtraction of csub (6).
 __device__ __forceinline__ u64 addback_neg(u64 x, u64 m) {
@@ -134,6 +126,29 @@ __device__ __forceinline__ u64 addback_neg(u64 x, u64 m) {
     asm("{\n\t.reg .pred p;\n\tsetp.lt.s32 p, %1, 0;\n\t@p add.cc.u32 %0, %0, %2;\n\t@p addc.u32 %1, %1, %3;\n\t}"
         : "+r"(lo), "+r"(hi) : "r"(lo32(m)), "r"(hi32(m)));
     return ((u64)hi << 32) | lo;
+}
+
+// x*w mod q in [0, 2q) for ANY 64-bit x at the price of the approximate quotient: the multiply-add chain of shoup4 starts
+// from -2q instead of 0 (free), which leaves the value of shoup4 minus 2q in [-2q, 2q), and the sign-based add-back
+// (3 instructions) brings it to [0, 2q).  Same residue as the exact Shoup product, possibly the other representative.
+__device__ __forceinline__ u64 shoup2q(u64 x, u64 w, u64 ws, u64 nq, u64 twoq) {
+    const unsigned x0 = lo32(x), x1 = hi32(x);
+    const u64 t = mulwide_u32(x1, hi32(ws)) + hi32(mulwide_u32(x0, hi32(ws))) + hi32(mulwide_u32(x1, lo32(ws)));
+    const unsigned t0 = lo32(t), t1 = hi32(t);
+    const u64 r = madwide_u32(t0, lo32(nq), madwide_u32(x0, lo32(w), 0 - twoq));
+    unsigned r1 = hi32(r);
+    r1 = madlo_u32(x0, hi32(w), r1);
+    r1 = madlo_u32(x1, lo32(w), r1);
+    r1 = madlo_u32(t0, hi32(nq), r1);
+    r1 = madlo_u32(t1, lo32(nq), r1);
+    return addback_neg(((u64)r1 << 32) | lo32(r), twoq);
+}
+// x >= m ? x - m : x with the subtraction done as a multiply-add by nm = 2^64 - m on the FMA pipe:
+// 3 ALU (compare + select) + 2 FMA instructions instead of 6 ALU.
+__device__ __forceinline__ u64 csub_fma(u64 x, u64 m, u64 nm) {
+    const unsigned k = x >= m ? 1u : 0u;
+    const u64 r = madwide_u32(k, lo32(nm), x);
+    return ((u64)madlo_u32(k, hi32(nm), hi32(r)) << 32) | lo32(r);
 }
 
 // hi-word-only variant of csub_fma (2 ALU + 2 FMA): subtracts when hi32(x) > hi32(m).  The result is

@@ -56,6 +56,15 @@
 #ifndef B200_CYCINV_APPROX
 #define B200_CYCINV_APPROX 0   // inverse cyclotomic layer on approximate-quotient products + quotient-estimate reduction: measured 3 % slower
 #endif
+// products of the cyclotomic / radix-3 / N^-1 layers that must land in [0,2q): 1 = approximate quotient + sign-based
+// add-back (shoup2q, ~22 instructions), 0 = exact 64-bit quotient (shoup_lazy, ~30).  Measured on B200: fewer instructions
+// but the register-capped column kernels spill (forward 3N columns +40 %, inverse +3-5 %, 2^16 inverse +1 %): off.
+#ifndef B200_SHOUP2Q_INV
+#define B200_SHOUP2Q_INV 0
+#endif
+#ifndef B200_SHOUP2Q_FWD
+#define B200_SHOUP2Q_FWD 0
+#endif
 #ifndef B200_CANON_EST
 #define B200_CANON_EST 1    // 1: final canonical reduction through a quotient estimate
 #endif
@@ -190,6 +199,10 @@ __device__ __forceinline__ u64 canon8(u64 x, const QC &c) {
 // column kernels keep the compare/select form: converting them measured 8 % (forward) and 2 % (inverse) slower.
 __device__ __forceinline__ u64 red_ab(u64 sum_minus_m, u64 m) { return addback_neg(sum_minus_m, m); }
 __device__ __forceinline__ u64 to2q(u64 x, const QC &c) { return csub(x, c.twoq); }
+template <bool APPROX>
+__device__ __forceinline__ u64 mul2q(u64 x, const tw_t w, const QC &c) {
+    return APPROX ? shoup2q(x, w.x, w.y, c.nq, c.twoq) : shoup_lazy(x, w.x, w.y, c.q);
+}
 
 // 2^LOGM-point sub-transform held in registers; x[k] ordered along the sub-dimension (MSB first);
 // P = heap index of the sub-transform's root node.
@@ -585,8 +598,8 @@ k_cols_inv_std16(const u64 *in, u64 *out, BigArgs a) {
 #pragma unroll
     for (int o = 0; o < 4; ++o) {   // last layer carries N^-1
         const u64 U = x[o], V = x[o + 4];
-        u64 X = shoup_lazy(U + V, ninv.x, ninv.y, q);
-        u64 Y = shoup_lazy(U - V + qc.fourq, ninv_w1.x, ninv_w1.y, q);   // inputs < 4q
+        u64 X = mul2q<(B200_SHOUP2Q_INV != 0)>(U + V, ninv, qc);
+        u64 Y = mul2q<(B200_SHOUP2Q_INV != 0)>(U - V + qc.fourq, ninv_w1, qc);   // inputs < 4q
         if (!lazy) { X = red_ab(X - q, q); Y = red_ab(Y - q, q); }
         x[o] = X; x[o + 4] = Y;
     }
@@ -606,7 +619,7 @@ k_cols_fwd_m3_15(const u64 *in, u64 *out, BigArgs a) {
     const int limb = ur.limb;
     const size_t ibase = ur.in + (size_t)blockIdx.x * CW, obase = ur.out + (size_t)blockIdx.x * CW;
     const QC qc(a.consts[limb]);
-    const u64 q = qc.q, twoq = qc.twoq, fourq = qc.fourq;
+    const u64 twoq = qc.twoq, fourq = qc.fourq;
     const tw_t *__restrict__ tw = a.fwd + (size_t)limb * a.N;
     const tw_t om = a.misc[limb * MISC_COUNT + MISC_OMEGA3];
     const int t = threadIdx.x, c = t % CW, g = t / CW;   // g in [0,48)
@@ -622,7 +635,7 @@ k_cols_fwd_m3_15(const u64 *in, u64 *out, BigArgs a) {
 #pragma unroll
             for (int d = 0; d < 3; ++d) {   // cyclotomic layer: in [0,2q) -> [0,4q)
                 const u64 lo = x[d][b], hi = x[d + 3][b];
-                const u64 tt = shoup_lazy(hi, zeta.x, zeta.y, q);
+                const u64 tt = mul2q<(B200_SHOUP2Q_FWD != 0)>(hi, zeta, qc);
                 x[d][b] = lo + tt;
                 x[d + 3][b] = csub(lo + hi + twoq - tt, fourq);
             }
@@ -630,9 +643,9 @@ k_cols_fwd_m3_15(const u64 *in, u64 *out, BigArgs a) {
             for (int h = 0; h < 2; ++h) {   // radix-3 layer: [0,4q) -> [0,4q)
                 const tw_t z1 = tw[2 + 2 * h], z2 = tw[3 + 2 * h];
                 const u64 b0 = csub(x[3 * h][b], twoq);
-                const u64 t1 = shoup_lazy(x[3 * h + 1][b], z1.x, z1.y, q);
-                const u64 t2 = shoup_lazy(x[3 * h + 2][b], z2.x, z2.y, q);
-                const u64 t3 = shoup_lazy(t1 + twoq - t2, om.x, om.y, q);
+                const u64 t1 = mul2q<(B200_SHOUP2Q_FWD != 0)>(x[3 * h + 1][b], z1, qc);
+                const u64 t2 = mul2q<(B200_SHOUP2Q_FWD != 0)>(x[3 * h + 2][b], z2, qc);
+                const u64 t3 = mul2q<(B200_SHOUP2Q_FWD != 0)>(t1 + twoq - t2, om, qc);
                 x[3 * h][b] = csub(b0 + t1 + t2, fourq);
                 x[3 * h + 1][b] = csub(b0 + twoq - t2 + t3, fourq);
                 x[3 * h + 2][b] = csub(b0 + fourq - t1 - t3, fourq);
@@ -725,10 +738,10 @@ k_cols_inv_m3_15(const u64 *in, u64 *out, BigArgs a) {
                 x[3 * h + 1][b] = shoup4(y0 + fourq + twoq - y1 - s, z1.x, z1.y, qc.nq);
                 x[3 * h + 2][b] = shoup4(y0 + twoq - y2 + s, z2.x, z2.y, qc.nq);
 #else
-                const u64 s = shoup_lazy(y1 + twoq - y2, om.x, om.y, q);
+                const u64 s = mul2q<(B200_SHOUP2Q_INV != 0)>(y1 + twoq - y2, om, qc);
                 x[3 * h][b] = csub(csub(y0 + y1 + y2, fourq), twoq);
-                x[3 * h + 1][b] = shoup_lazy(y0 + fourq - y1 - s, z1.x, z1.y, q);
-                x[3 * h + 2][b] = shoup_lazy(y0 + twoq - y2 + s, z2.x, z2.y, q);
+                x[3 * h + 1][b] = mul2q<(B200_SHOUP2Q_INV != 0)>(y0 + fourq - y1 - s, z1, qc);
+                x[3 * h + 2][b] = mul2q<(B200_SHOUP2Q_INV != 0)>(y0 + twoq - y2 + s, z2, qc);
 #endif
             }
 #pragma unroll
@@ -740,8 +753,8 @@ k_cols_inv_m3_15(const u64 *in, u64 *out, BigArgs a) {
                 if (!lazy) { ll = canon_est<2>(ll, q, qc.nq, qc.csh, qc.cmul); hh = canon_est<2>(hh, q, qc.nq, qc.csh, qc.cmul); }
                 else { ll = canon_est<3>(ll, q, qc.nq, qc.csh, qc.cmul); hh = csub(hh, twoq); }
 #else
-                u64 hh = shoup_lazy(lo + (B200_R3INV_APPROX ? fourq : twoq) - hi, k1.x, k1.y, q);
-                u64 ll = csub(shoup_lazy(lo, k2.x, k2.y, q) + twoq - shoup_lazy(hh, zeta.x, zeta.y, q), twoq);
+                u64 hh = mul2q<(B200_SHOUP2Q_INV != 0)>(lo + (B200_R3INV_APPROX ? fourq : twoq) - hi, k1, qc);
+                u64 ll = csub(mul2q<(B200_SHOUP2Q_INV != 0)>(lo, k2, qc) + twoq - mul2q<(B200_SHOUP2Q_INV != 0)>(hh, zeta, qc), twoq);
                 if (!lazy) { ll = csub(ll, q); hh = csub(hh, q); }
 #endif
                 x[d][b] = ll; x[d + 3][b] = hh;
@@ -791,8 +804,8 @@ __device__ __forceinline__ void col_group(const u64 *gin, size_t ibase, u64 *gou
 #pragma unroll
             for (int o = 0; o < M / 2; ++o) {
                 const u64 U = x[o], V = x[o + M / 2];
-                u64 X = shoup_lazy(U + V, ninv.x, ninv.y, qc.q);
-                u64 Y = shoup_lazy(U - V + qc.fourq, ninv_w1.x, ninv_w1.y, qc.q);
+                u64 X = mul2q<(B200_SHOUP2Q_INV != 0)>(U + V, ninv, qc);
+                u64 Y = mul2q<(B200_SHOUP2Q_INV != 0)>(U - V + qc.fourq, ninv_w1, qc);
                 if (!lazy) { X = red_ab(X - qc.q, qc.q); Y = red_ab(Y - qc.q, qc.q); }
                 x[o] = X; x[o + M / 2] = Y;
             }
@@ -875,7 +888,7 @@ k_cols_m3_g(const u64 *in, u64 *out, BigArgs a) {
 #pragma unroll
                 for (int d = 0; d < 3; ++d) {   // cyclotomic layer: in [0,2q) -> [0,4q)
                     const u64 lo = x[d][k], hi = x[d + 3][k];
-                    const u64 tt = shoup_lazy(hi, zeta.x, zeta.y, q);
+                    const u64 tt = mul2q<(B200_SHOUP2Q_FWD != 0)>(hi, zeta, qc);
                     x[d][k] = lo + tt;
                     x[d + 3][k] = csub(lo + hi + twoq - tt, fourq);
                 }
@@ -883,9 +896,9 @@ k_cols_m3_g(const u64 *in, u64 *out, BigArgs a) {
                 for (int h = 0; h < 2; ++h) {   // radix-3 layer: [0,4q) -> [0,4q)
                     const tw_t z1 = tw[2 + 2 * h], z2 = tw[3 + 2 * h];
                     const u64 b0 = csub(x[3 * h][k], twoq);
-                    const u64 t1 = shoup_lazy(x[3 * h + 1][k], z1.x, z1.y, q);
-                    const u64 t2 = shoup_lazy(x[3 * h + 2][k], z2.x, z2.y, q);
-                    const u64 t3 = shoup_lazy(t1 + twoq - t2, om.x, om.y, q);
+                    const u64 t1 = mul2q<(B200_SHOUP2Q_FWD != 0)>(x[3 * h + 1][k], z1, qc);
+                    const u64 t2 = mul2q<(B200_SHOUP2Q_FWD != 0)>(x[3 * h + 2][k], z2, qc);
+                    const u64 t3 = mul2q<(B200_SHOUP2Q_FWD != 0)>(t1 + twoq - t2, om, qc);
                     x[3 * h][k] = csub(b0 + t1 + t2, fourq);
                     x[3 * h + 1][k] = csub(b0 + twoq - t2 + t3, fourq);
                     x[3 * h + 2][k] = csub(b0 + fourq - t1 - t3, fourq);
@@ -937,10 +950,10 @@ k_cols_m3_g(const u64 *in, u64 *out, BigArgs a) {
                     x[3 * h + 1][k] = shoup4(y0 + fourq + twoq - y1 - sgm, z1.x, z1.y, qc.nq);
                     x[3 * h + 2][k] = shoup4(y0 + twoq - y2 + sgm, z2.x, z2.y, qc.nq);
 #else
-                    const u64 sgm = shoup_lazy(y1 + twoq - y2, om.x, om.y, q);
+                    const u64 sgm = mul2q<(B200_SHOUP2Q_INV != 0)>(y1 + twoq - y2, om, qc);
                     x[3 * h][k] = csub(csub(y0 + y1 + y2, fourq), twoq);
-                    x[3 * h + 1][k] = shoup_lazy(y0 + fourq - y1 - sgm, z1.x, z1.y, q);
-                    x[3 * h + 2][k] = shoup_lazy(y0 + twoq - y2 + sgm, z2.x, z2.y, q);
+                    x[3 * h + 1][k] = mul2q<(B200_SHOUP2Q_INV != 0)>(y0 + fourq - y1 - sgm, z1, qc);
+                    x[3 * h + 2][k] = mul2q<(B200_SHOUP2Q_INV != 0)>(y0 + twoq - y2 + sgm, z2, qc);
 #endif
                 }
 #pragma unroll
@@ -952,8 +965,8 @@ k_cols_m3_g(const u64 *in, u64 *out, BigArgs a) {
                     if (!lazy) { ll = canon_est<2>(ll, q, qc.nq, qc.csh, qc.cmul); hh = canon_est<2>(hh, q, qc.nq, qc.csh, qc.cmul); }
                     else { ll = canon_est<3>(ll, q, qc.nq, qc.csh, qc.cmul); hh = csub(hh, twoq); }
 #else
-                    u64 hh = shoup_lazy(lo + (B200_R3INV_APPROX ? fourq : twoq) - hi, k1.x, k1.y, q);
-                    u64 ll = csub(shoup_lazy(lo, k2.x, k2.y, q) + twoq - shoup_lazy(hh, zeta.x, zeta.y, q), twoq);
+                    u64 hh = mul2q<(B200_SHOUP2Q_INV != 0)>(lo + (B200_R3INV_APPROX ? fourq : twoq) - hi, k1, qc);
+                    u64 ll = csub(mul2q<(B200_SHOUP2Q_INV != 0)>(lo, k2, qc) + twoq - mul2q<(B200_SHOUP2Q_INV != 0)>(hh, zeta, qc), twoq);
                     if (!lazy) { ll = csub(ll, q); hh = csub(hh, q); }
 #endif
                     x[d][k] = ll; x[d + 3][k] = hh;
