@@ -10,4 +10,8 @@ from .ring import (  # noqa: E402,F401
     Type, Standard, ConjugateInvariant, Matrix, Ring, SubRing, Poly, KeySwitcher, NewRing, NewRingFromType, NewRingConjugateInvariant, NewPoly, AutomorphismNTTIndex,
     UnmarshalJSON,
 )
+from .primes import (  # noqa: E402,F401
+    IsPrime, Find3NRNSPrimes, Find3NFriendlyPrime, OrderMod, HasPrimitiveMthRoot, PrimitiveRoot, FindPrimitiveRootOfUnity,
+    Find3NPrimitiveRoot, Derive3NRoots, Uint64Pow, NTTFriendlyPrimesGenerator, NewNTTFriendlyPrimesGenerator,
+)
 from . import sharding  # noqa: E402,F401

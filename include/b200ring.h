@@ -304,6 +304,38 @@ B200_API int b200_transform_host(b200_ctx *ctx, const uint64_t *host_in, uint64_
 B200_API int b200_subring_ntt_host(b200_ctx *ctx, int limb, const uint64_t *p1, uint64_t *p2, size_t n,
                           int inverse, int flags);
 
+/* ---- modulus and root search of the ring constructors (host only: no device is touched) ---------------
+ * What a caller runs before b200_ctx_create: core/rlwe/params.go:924,966,998 and core/rlwe/params_3n.go:804-805 pick
+ * the moduli chain with these, ring/ntt_3n.go:39 picks omega.  Same integers as the Go functions. */
+B200_API int b200_is_prime(uint64_t x);                                /* ring.IsPrime, ring/primes.go:11-13: 1 / 0 */
+/* ring.Find3NRNSPrimes (ring/primes_3n.go:11-43): the first `count` primes = 1 mod 3N above 2^bitSize, ascending,
+ * giving up after searchBudget candidates (B200_EINVAL, "could not find enough 3N-friendly primes (found i/count)"). */
+B200_API int b200_find_3n_rns_primes(int N, int bitSize, int count, int searchBudget, uint64_t *out);
+/* ring.Find3NFriendlyPrime (ring/primes.go:16-67): first prime k*3N+1 at or above 2^bitSize (1000 candidates), else below. */
+B200_API int b200_find_3n_friendly_prime(int N, int bitSize, uint64_t *out);
+B200_API int b200_order_mod(uint64_t g, uint64_t p, uint64_t *out);     /* ring.OrderMod, ring/primes_3n.go:78-91 */
+B200_API int b200_has_primitive_mth_root(uint64_t q, uint64_t m);       /* ring.HasPrimitiveMthRoot, :121-123: 1 / 0 */
+B200_API int b200_primitive_root(uint64_t q, uint64_t *g_out);          /* ring.PrimitiveRoot, ring/subring.go:218-251 */
+/* ring.FindPrimitiveRootOfUnity (ring/primes_3n.go:127-149): an element of exact order m.  The reference draws up to
+ * 256 random bases from crypto/rand, so any element of order m is a valid answer; here the bases come from
+ * splitmix64(seed).  seed == 0 returns the deterministic root g^((q-1)/m), g = b200_primitive_root(q)
+ * (ring.Find3NPrimitiveRoot, ring/subring.go:255-290) -- the omega b200_ctx_create uses when roots == NULL. */
+B200_API int b200_find_primitive_root_of_unity(uint64_t q, uint64_t m, uint64_t seed, uint64_t *out);
+/* ring.Derive3NRoots (ring/primes_3n.go:165-181): out = {omega, omega^(3^(b+1)) of order 2^a, omega^(2^a) of order
+ * 3^(b+1)}; B200_EINVAL unless omega has exact order 3N = 3 * 2^a * 3^b modulo the prime q. */
+B200_API int b200_derive_3n_roots(uint64_t q, int a, int b, uint64_t omega, uint64_t out[3]);
+/* ring.NTTFriendlyPrimesGenerator (ring/primes.go:69-277): primes 2^BitSize +/- k*NthRoot + 1.  The struct is the Go
+ * struct, field for field.  direction +1 = NextUpstreamPrimes(k), -1 = NextDownstreamPrimes(k), 0 =
+ * NextAlternatingPrimes(k); B200_EINVAL with the reference's message once a side overlaps the neighbouring bit size
+ * (where the Go NextUpstreamPrime would spin forever on a second call, primes.go:147-149, the error is returned again). */
+typedef struct b200_prime_gen {
+    double Size;
+    uint64_t NextPrime, PrevPrime, NthRoot;
+    int CheckNextPrime, CheckPrevPrime;
+} b200_prime_gen;
+B200_API int b200_prime_gen_init(b200_prime_gen *g, uint64_t BitSize, uint64_t NthRoot);
+B200_API int b200_prime_gen_next(b200_prime_gen *g, int direction, int k, uint64_t *out);
+
 /* Per-kernel device timing for the roofline report: between begin and end every kernel launch of this
  * context is bracketed by CUDA events on its stream.  end() writes one line per kernel name:
  * "<kernel> <total_ms> <launches> <limb-units processed>\n". */

@@ -37,6 +37,51 @@ inline bool IsValidRingDegreeFor3N(int N) {
     return t > 0 && (t & (t - 1)) == 0;
 }
 
+// ---- ring/primes.go, ring/primes_3n.go: modulus and root search (host only); Go `error` -> std::invalid_argument
+inline bool IsPrime(uint64_t x) { return b200_is_prime(x) != 0; }                                             // primes.go:11-13
+inline std::vector<uint64_t> Find3NRNSPrimes(int N, int bitSize, int count, int searchBudget) {                // primes_3n.go:11-43
+    std::vector<uint64_t> out(count > 0 ? count : 1);
+    check(b200_find_3n_rns_primes(N, bitSize, count, searchBudget, out.data()));
+    out.resize(count);
+    return out;
+}
+inline uint64_t Find3NFriendlyPrime(int N, int bitSize) { uint64_t q = 0; check(b200_find_3n_friendly_prime(N, bitSize, &q)); return q; }   // primes.go:16-67
+inline uint64_t OrderMod(uint64_t g, uint64_t p) { uint64_t o = 0; check(b200_order_mod(g, p, &o)); return o; }                    // primes_3n.go:78-91
+inline bool HasPrimitiveMthRoot(uint64_t q, uint64_t m) { return b200_has_primitive_mth_root(q, m) != 0; }                         // primes_3n.go:121-123
+inline uint64_t PrimitiveRoot(uint64_t q) { uint64_t g = 0; check(b200_primitive_root(q, &g)); return g; }                         // subring.go:218-251
+inline uint64_t FindPrimitiveRootOfUnity(uint64_t q, uint64_t m, uint64_t seed = 0) {                                              // primes_3n.go:127-149
+    uint64_t w = 0;
+    check(b200_find_primitive_root_of_unity(q, m, seed, &w));
+    return w;
+}
+inline uint64_t Find3NPrimitiveRoot(uint64_t p, uint64_t NthRoot) { return FindPrimitiveRootOfUnity(p, NthRoot, 0); }              // subring.go:255-290
+struct Roots3N { uint64_t omega3N, omega2Pow, omega3Pow; };
+inline Roots3N Derive3NRoots(uint64_t q, int a, int b, uint64_t omega) {                                                           // primes_3n.go:165-181
+    uint64_t o[3];
+    check(b200_derive_3n_roots(q, a, b, omega, o));
+    return Roots3N{o[0], o[1], o[2]};
+}
+class NTTFriendlyPrimesGenerator {                                                                                                 // primes.go:69-277
+  public:
+    NTTFriendlyPrimesGenerator(uint64_t BitSize, uint64_t NthRoot) { check(b200_prime_gen_init(&g_, BitSize, NthRoot)); }
+    std::vector<uint64_t> NextUpstreamPrimes(int k) { return next(1, k); }
+    std::vector<uint64_t> NextDownstreamPrimes(int k) { return next(-1, k); }
+    std::vector<uint64_t> NextAlternatingPrimes(int k) { return next(0, k); }
+    uint64_t NextUpstreamPrime() { return next(1, 1)[0]; }
+    uint64_t NextDownstreamPrime() { return next(-1, 1)[0]; }
+    uint64_t NextAlternatingPrime() { return next(0, 1)[0]; }
+
+  private:
+    std::vector<uint64_t> next(int direction, int k) {
+        std::vector<uint64_t> out(k > 0 ? k : 1);
+        check(b200_prime_gen_next(&g_, direction, k, out.data()));
+        out.resize(k > 0 ? k : 0);
+        return out;
+    }
+    b200_prime_gen g_;
+};
+inline NTTFriendlyPrimesGenerator NewNTTFriendlyPrimesGenerator(uint64_t BitSize, uint64_t NthRoot) { return NTTFriendlyPrimesGenerator(BitSize, NthRoot); }
+
 class Ring;
 
 // ring.Poly (ring/poly.go:13-24): device resident, `batch` polynomials of [L][N] words

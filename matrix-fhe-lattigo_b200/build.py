@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "lib", "libb200ring.so")
-SOURCES = ["b200ring.cu", "ewise.cu", "ntt_generic.cu", "ntt_big.cu", "keyswitch.cu"]
+SOURCES = ["b200ring.cu", "ewise.cu", "ntt_generic.cu", "ntt_big.cu", "keyswitch.cu", "primes.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr", "-ccbin", "g++"]

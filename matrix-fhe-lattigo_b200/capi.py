@@ -70,6 +70,16 @@ SYMBOLS = {
     "b200_fold_standard_to_ci": (C.c_int, [VP, VP, P64, C.c_size_t, VP, C.c_int]),
     "b200_transform_host": (C.c_int, [VP, VP, VP, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int]),
     "b200_subring_ntt_host": (C.c_int, [VP, C.c_int, P64, P64, C.c_size_t, C.c_int, C.c_int]),
+    "b200_is_prime": (C.c_int, [C.c_uint64]),
+    "b200_find_3n_rns_primes": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, P64]),
+    "b200_find_3n_friendly_prime": (C.c_int, [C.c_int, C.c_int, P64]),
+    "b200_order_mod": (C.c_int, [C.c_uint64, C.c_uint64, P64]),
+    "b200_has_primitive_mth_root": (C.c_int, [C.c_uint64, C.c_uint64]),
+    "b200_primitive_root": (C.c_int, [C.c_uint64, P64]),
+    "b200_find_primitive_root_of_unity": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, P64]),
+    "b200_derive_3n_roots": (C.c_int, [C.c_uint64, C.c_int, C.c_int, C.c_uint64, P64]),
+    "b200_prime_gen_init": (C.c_int, [VP, C.c_uint64, C.c_uint64]),
+    "b200_prime_gen_next": (C.c_int, [VP, C.c_int, C.c_int, P64]),
     "b200_ctx_launch_count": (C.c_uint64, [VP]),
     "b200_profile_begin": (C.c_int, [VP]),
     "b200_profile_end": (C.c_int, [VP, C.c_char_p, C.c_size_t]),

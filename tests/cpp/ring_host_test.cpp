@@ -24,6 +24,23 @@ int main(int argc, char **argv) {
     EXPECT(throws_invalid([&] { ring::Ring::NewRing(16, {Q[0] + 2}); }));              // not prime
     EXPECT(throws_invalid([&] { ring::Ring::NewRingFromType(16, Q, ring::Matrix); })); // Matrix needs 3N degree
     EXPECT(ring::IsValidRingDegreeFor3N(12) && ring::IsValidRingDegreeFor3N(16) && !ring::IsValidRingDegreeFor3N(20));
+    // ring/primes_3n.go, ring/primes.go: host-only modulus and root search (ring/ring_3n_test.go:42-73, ring/ring_test.go:195-245)
+    {
+        const std::vector<uint64_t> c3 = ring::Find3NRNSPrimes(98304, 60, 24, 1000);
+        EXPECT(c3.size() == 24 && c3.front() == 0x1000000000248001ULL && c3.back() == 0x10000000042b0001ULL);
+        EXPECT(ring::Find3NFriendlyPrime(12288, 60) == 0x10000000000a1001ULL && ring::IsPrime(c3[7]) && !ring::IsPrime(c3[7] + 2));
+        EXPECT(throws_invalid([&] { ring::Find3NRNSPrimes(98304, 60, 24, 10); }));
+        const uint64_t omega = ring::Find3NPrimitiveRoot(1117, 36);
+        const ring::Roots3N w = ring::Derive3NRoots(1117, 2, 1, omega);
+        EXPECT(ring::OrderMod(omega, 1117) == 36 && ring::OrderMod(w.omega2Pow, 1117) == 4 && ring::OrderMod(w.omega3Pow, 1117) == 9);
+        EXPECT(ring::OrderMod(ring::FindPrimitiveRootOfUnity(c3[0], 3 * 98304, 99), c3[0]) == 3 * 98304);
+        EXPECT(throws_invalid([&] { ring::Derive3NRoots(1117, 2, 1, w.omega2Pow); }));
+        ring::NTTFriendlyPrimesGenerator g = ring::NewNTTFriendlyPrimesGenerator(55, 1 << 17);
+        const std::vector<uint64_t> alt = g.NextAlternatingPrimes(3);
+        EXPECT(alt.size() == 3 && alt[0] == 0x80000000080001ULL && alt[1] == 0x80000000440001ULL && alt[2] == 0x7fffffffba0001ULL);
+        EXPECT(g.NextUpstreamPrime() > alt[1] && g.NextDownstreamPrime() < alt[2]);
+        EXPECT(throws_invalid([&] { ring::Ring::NewRing(98304, {c3[0], c3[0] + 3 * 98304}); }));   // second value is not prime
+    }
     if (no_gpu) { std::printf(fails ? "FAILED\n" : "ok (no gpu)\n"); return fails != 0; }
 
     // ring/ntt_test.go:17-32, N = 16, limb 0

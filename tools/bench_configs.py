@@ -20,7 +20,6 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 import b200ring  # noqa: E402
 import bench  # noqa: E402
-from oracle import oracle as O  # noqa: E402  (prime search only)
 
 PEAK = bench.peaks()[0] * 1e9
 QI60 = [0x1fffffffffe00001, 0x1fffffffffc80001, 0x1fffffffffb40001, 0x1fffffffff500001,
@@ -74,7 +73,7 @@ def main():
     rows = []
     if "C1" in want:
         N = 3 << 12
-        r = transform_config("C1", N, O.find_3n_rns_primes(N, 60, 1), 1, 50, "3N ring N=3*2^12, 1 prime, 1 polynomial, NTT+INTT round trip")
+        r = transform_config("C1", N, b200ring.Find3NRNSPrimes(N, 60, 1, 100000), 1, 50, "3N ring N=3*2^12, 1 prime, 1 polynomial, NTT+INTT round trip")
         r["note"] = "latency of two launches on one 96 KiB limb, not a throughput shape"
         rows.append(r)
     if "C2" in want:
@@ -111,7 +110,7 @@ def main():
         torch.cuda.empty_cache()
     if "C5" in want:
         N, LQ, LP, B = bench.N, 24, 6, 16
-        primes = O.find_3n_rns_primes(N, 60, LQ + LP)
+        primes = b200ring.Find3NRNSPrimes(N, 60, LQ + LP, 100000)
         ring = b200ring.NewRing(N, primes)
         ring.SetStream(torch.cuda.current_stream().cuda_stream)
         ks = b200ring.KeySwitcher(ring, LQ)

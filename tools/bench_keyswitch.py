@@ -16,7 +16,6 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 import b200ring  # noqa: E402
 from b200ring import sharding  # noqa: E402
-from oracle import oracle as O  # noqa: E402  (only to find the 3N-friendly primes of the shape)
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=16)
@@ -31,7 +30,7 @@ rank, local, world = sharding.init_process_group()
 dev = torch.device("cuda", local)
 torch.cuda.set_device(dev)
 N, LQ, LP, B = 3 << args.a, args.lq, args.lp, args.batch
-primes = O.find_3n_rns_primes(N, 60, LQ + LP)
+primes = b200ring.Find3NRNSPrimes(N, 60, LQ + LP, 100000)
 ring = b200ring.NewRing(N, primes, device=local)
 ring.SetStream(torch.cuda.current_stream().cuda_stream)
 ks = b200ring.KeySwitcher(ring, LQ)

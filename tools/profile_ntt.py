@@ -34,8 +34,7 @@ if args.ring == "3n":
     if args.a == 15:
         moduli = bench.MODULI[: args.limbs]
     else:
-        from oracle import oracle as O
-        moduli = O.find_3n_rns_primes(N, 60, args.limbs)
+        moduli = b200ring.Find3NRNSPrimes(N, 60, args.limbs, 100000)
 else:
     N, moduli = 1 << args.logn, QI60[: args.limbs]
 ring = b200ring.NewRing(N, moduli)
@@ -136,9 +135,8 @@ if os.environ.get("B200_PROFILE_NEXT"):
           % (Lq, Lq - 1, ms, args.polys, args.polys / (ms * 1e-3), args.polys * Lq, args.polys * Lq / (ms * 1e-3)))
 if os.environ.get("B200_PROFILE_KS"):
     # key-switch gadget product at the shape of BASELINE config 5: LQ ciphertext primes + LP special primes
-    from oracle import oracle as O
     LQ, LP, B = int(os.environ.get("KS_LQ", 24)), int(os.environ.get("KS_LP", 6)), int(os.environ.get("KS_B", 8))
-    primes = O.find_3n_rns_primes(N, 60, LQ + LP) if args.ring == "3n" else QI60[:LQ] + [0x1ffffffff6c80001, 0x1ffffffff6140001, 0x1ffffffff5f40001, 0x1ffffffff5700001, 0x1ffffffff4bc0001, 0x1ffffffff4380001][:LP]
+    primes = b200ring.Find3NRNSPrimes(N, 60, LQ + LP, 100000) if args.ring == "3n" else QI60[:LQ] + [0x1ffffffff6c80001, 0x1ffffffff6140001, 0x1ffffffff5f40001, 0x1ffffffff5700001, 0x1ffffffff4bc0001, 0x1ffffffff4380001][:LP]
     rqp = b200ring.NewRing(N, primes)
     rqp.SetStream(torch.cuda.current_stream().cuda_stream)
     ks = b200ring.KeySwitcher(rqp, LQ)
