@@ -24,6 +24,7 @@ ap.add_argument("--lp", type=int, default=6)
 ap.add_argument("--a", type=int, default=15)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--profile", action="store_true", help="per-kernel CUDA-event times of one call on every rank")
+ap.add_argument("--verify", action="store_true", help="compare this rank's Q limbs with the single-GPU b200_gadget_product on the same data")
 ap.add_argument("--fused", action="store_true", help="exchanges fused into the inverse transforms (peer stores over NVLink)")
 args = ap.parse_args()
 rank, local, world = sharding.init_process_group()
@@ -76,10 +77,17 @@ barrier()
 ms = sharding.max_over_ranks(e0.elapsed_time(e1) / args.reps, device=dev)
 q0, q1 = sharding.block_of_rank(levelQ + 1, world, rank)
 chk = int(o0[:, q0:q1].sum().item()) & 0xFFFFFFFF
+verified = None
+if args.verify:   # every rank holds the whole input (same seed): the unsharded product on this GPU is the check
+    r0, r1 = torch.zeros_like(cx_t), torch.zeros_like(cx_t)
+    ks.GadgetProduct(levelQ, levelP, b200ring.Poly.from_torch(ring, cx_t.clone()), key, b200ring.Poly.from_torch(ring, r0), b200ring.Poly.from_torch(ring, r1))
+    ring.Sync()
+    ok = bool(torch.equal(r0[:, q0:q1], o0[:, q0:q1]) and torch.equal(r1[:, q0:q1], o1[:, q0:q1]) and (q1 == q0 or int(r0[:, q0:q1].abs().sum().item()) != 0))
+    verified = sharding.max_over_ranks(0.0 if ok else 1.0, device=dev) == 0.0
 if rank == 0:
     print(json.dumps({"workload": "gadget product N=%d LQ=%d LP=%d beta=%d batch=%d" % (N, LQ, LP, beta, B), "n_gpus": world, "fused_exchanges": bool(args.fused),
                       "ms": ms, "key_switches_per_s": B / (ms * 1e-3), "limb_transforms_per_s": B * 180 / (ms * 1e-3) if (LQ, LP) == (24, 6) else None,
-                      "allgather_bytes_per_step": B * (LQ + 2 * LP) * N * 8, "checksum_rank0": chk}))
+                      "allgather_bytes_per_step": B * (LQ + 2 * LP) * N * 8, "checksum_rank0": chk, "verified_against_single_gpu": verified}))
 if args.profile:
     prof = ring.Profile(run)
     barrier()
