@@ -73,10 +73,13 @@ typedef struct b200_poly b200_poly; /* ring.Poly (ring/poly.go:13-24), device re
 #define B200_OP_MFORM 7                /* Ring.MForm            operations.go:285 vec_ops.go:778  */
 #define B200_OP_MFORM_LAZY 8           /* Ring.MFormLazy        operations.go:292 vec_ops.go:800  */
 #define B200_OP_IMFORM 9               /* Ring.IMForm           operations.go:299 vec_ops.go:822  */
+#define B200_OP_ZERO 10                /* ring.ZeroVec                                    vec_ops.go:847  (p1 ignored) */
 #define B200_OP_MUL_BARRETT 16         /* Ring.MulCoeffsBarrett             operations.go:60  */
 #define B200_OP_MUL_BARRETT_LAZY 17    /* Ring.MulCoeffsBarrettLazy         operations.go:67  */
 #define B200_OP_MUL_BARRETT_ADD 18     /* Ring.MulCoeffsBarrettThenAdd      operations.go:74  */
 #define B200_OP_MUL_BARRETT_ADD_LAZY 19/* Ring.MulCoeffsBarrettThenAddLazy  operations.go:81  */
+#define B200_OP_MUL_LAZY 20            /* SubRing.MulCoeffsLazy            subring_ops.go:55  vec_ops.go:169: low word of p1*p2 */
+#define B200_OP_MUL_LAZY_ADD_LAZY 21   /* SubRing.MulCoeffsLazyThenAddLazy subring_ops.go:62  vec_ops.go:193 */
 #define B200_OP_MUL_MONT 32            /* Ring.MulCoeffsMontgomery                 operations.go:88  */
 #define B200_OP_MUL_MONT_LAZY 33       /* Ring.MulCoeffsMontgomeryLazy             operations.go:95  */
 #define B200_OP_MUL_MONT_ADD 34        /* Ring.MulCoeffsMontgomeryThenAdd          operations.go:109 */
@@ -93,6 +96,18 @@ typedef struct b200_poly b200_poly; /* ring.Poly (ring/poly.go:13-24), device re
 #define B200_OP_SUB_SCALAR 52          /* SubRing.SubScalar                  subring_ops.go:195 */
 #define B200_OP_SUB_MULSCALAR_MONT_2Q 53 /* SubRing.SubThenMulScalarMontgomeryTwoModulus subring_ops.go:230:
                                             p3 = MRed(2q - p2 + p1, scalar_i)                          */
+#define B200_OP_ADD_LAZY_MULSCALAR_MONT 54 /* SubRing.AddLazyThenMulScalarMontgomery subring_ops.go:160: MRed(p1 + p2, scalar_i) */
+#define B200_OP_ADD_SCALAR_LAZY 55     /* SubRing.AddScalarLazy              subring_ops.go:181: p1 + scalar_i          */
+#define B200_OP_ADD_SCALAR_LAZY_NEG_2Q_LAZY 56 /* SubRing.AddScalarLazyThenNegTwoModulusLazy subring_ops.go:188: scalar_i + 2q - p1 */
+/* two scalars per limb: scalars[0..level] = scalar0_i, scalars[level+1..2*level+1] = scalar1_i */
+#define B200_OP_ADD_SCALAR_LAZY_MULSCALAR_MONT 57 /* SubRing.AddScalarLazyThenMulScalarMontgomery subring_ops.go:167: MRed(p1 + scalar0_i, scalarMont1_i) */
+#define B200_OP_MULSCALAR_MONT_ADD_SCALAR 58      /* SubRing.MulScalarMontgomeryThenAddScalar subring_ops.go:223: CRed(MRed(p1, scalarMont1_i) + scalar0_i) */
+#define B200_OP_MASK 59                /* ring.MaskVec vec_ops.go:870: (p1 >> scalar0_i) & scalar1_i                     */
+/* one scalar per limb and half (N % 4 == 0): words [0, N/2) use scalars[i], words [N/2, N) use scalars[level+1+i] */
+#define B200_OP_ADD_SCALAR_DOUBLE 60         /* Ring.AddDoubleRNSScalar        operations.go:167 */
+#define B200_OP_SUB_SCALAR_DOUBLE 61         /* Ring.SubDoubleRNSScalar        operations.go:177 */
+#define B200_OP_MULSCALAR_MONT_DOUBLE 62     /* Ring.MulDoubleRNSScalar        operations.go:250 (scalars already in Montgomery form) */
+#define B200_OP_MULSCALAR_MONT_ADD_DOUBLE 63 /* Ring.MulDoubleRNSScalarThenAdd operations.go:260 */
 
 /* ---- library ------------------------------------------------------------------------------- */
 B200_API const char *b200_last_error(void);   /* message of the last failure on this thread ("" if none) */
@@ -179,9 +194,13 @@ B200_API int b200_intt_limbs_gather(b200_ctx *ctx, const b200_poly *in, b200_pol
 
 /* ---- element-wise family: p3 = op(p1, p2 [, p3]) (ring/operations.go, ring/vec_ops.go) -------
  * p2 may be NULL for unary ops.  For *_SCALAR / MULSCALAR ops `scalars` holds one word per limb
- * (level+1 of them; Montgomery form where the Go method says so); otherwise NULL. */
+ * (level+1 of them; Montgomery form where the Go method says so), two per limb for op codes 57..63; otherwise NULL. */
 B200_API int b200_vec_op(b200_ctx *ctx, int op, const b200_poly *p1, const b200_poly *p2, b200_poly *p3,
                 int level, const uint64_t *scalars);
+/* Ring.MulByVectorMontgomery / MulByVectorMontgomeryThenAddLazy (ring/operations.go:366-377): every limb of every
+ * polynomial of p1 times the same N words (limb 0 of polynomial 0 of `vector`), p2 = MRed(p1, vector) or p2 += ... */
+B200_API int b200_mul_by_vector_montgomery(b200_ctx *ctx, const b200_poly *p1, const b200_poly *vector, b200_poly *p2,
+                                           int level, int then_add_lazy);
 
 /* ---- key switching: RNS basis extension, ModDown, gadget product ----------------------
  * The ring of `ctx` is the concatenated chain Q_0..Q_{LQ-1}, P_0..P_{LP-1} (what ringqp.Ring fans out over,

@@ -184,8 +184,18 @@ class Ring {
     void INTT(const Poly &p1, Poly &p2) const { check(b200_intt(ctx_.get(), p1.handle(), p2.handle(), level_, 0)); }
     void INTTLazy(const Poly &p1, Poly &p2) const { check(b200_intt(ctx_.get(), p1.handle(), p2.handle(), level_, B200_LAZY)); }
     // ring/operations.go (a representative subset by name; every op code is reachable through VecOp)
-    void VecOp(int op, const Poly &p1, const Poly *p2, Poly &p3) const {
-        check(b200_vec_op(ctx_.get(), op, p1.handle(), p2 ? p2->handle() : nullptr, p3.handle(), level_, nullptr));
+    // `scalars`: one word per limb (two per limb, scalar0 block then scalar1 block, for op codes 57..63)
+    void VecOp(int op, const Poly &p1, const Poly *p2, Poly &p3, const std::vector<uint64_t> *scalars = nullptr) const {
+        if (scalars && scalars->size() < (size_t)(level_ + 1) * (op >= B200_OP_ADD_SCALAR_LAZY_MULSCALAR_MONT ? 2 : 1))
+            throw Panic(B200_ESHAPE, "need one scalar per limb");
+        check(b200_vec_op(ctx_.get(), op, p1.handle(), p2 ? p2->handle() : nullptr, p3.handle(), level_, scalars ? scalars->data() : nullptr));
+    }
+    void Zero(Poly &p) const { VecOp(B200_OP_ZERO, p, nullptr, p); }                                                          // vec_ops.go:847
+    void MulByVectorMontgomery(const Poly &p1, const Poly &vector, Poly &p2) const {                                           // operations.go:366
+        check(b200_mul_by_vector_montgomery(ctx_.get(), p1.handle(), vector.handle(), p2.handle(), level_, 0));
+    }
+    void MulByVectorMontgomeryThenAddLazy(const Poly &p1, const Poly &vector, Poly &p2) const {                                // operations.go:373
+        check(b200_mul_by_vector_montgomery(ctx_.get(), p1.handle(), vector.handle(), p2.handle(), level_, 1));
     }
     void Add(const Poly &a, const Poly &b, Poly &c) const { VecOp(B200_OP_ADD, a, &b, c); }
     void Sub(const Poly &a, const Poly &b, Poly &c) const { VecOp(B200_OP_SUB, a, &b, c); }

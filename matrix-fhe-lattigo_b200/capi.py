@@ -44,6 +44,7 @@ SYMBOLS = {
     "b200_ntt": (C.c_int, [VP, VP, VP, C.c_int, C.c_int]),
     "b200_intt": (C.c_int, [VP, VP, VP, C.c_int, C.c_int]),
     "b200_vec_op": (C.c_int, [VP, C.c_int, VP, VP, VP, C.c_int, P64]),
+    "b200_mul_by_vector_montgomery": (C.c_int, [VP, VP, VP, VP, C.c_int, C.c_int]),
     "b200_keyswitch_create": (C.c_int, [VP, C.c_int, C.POINTER(VP)]),
     "b200_keyswitch_destroy": (None, [VP]),
     "b200_mod_up": (C.c_int, [VP, C.c_int, C.c_int, C.c_int, VP, VP]),

@@ -699,26 +699,40 @@ extern "C" int b200_vec_op(b200_ctx *ctx, int op, const b200_poly *p1, const b20
                            const uint64_t *scalars) {
     CtxLock lk(ctx);
     int batch;
-    const bool unary = (op >= B200_OP_NEG && op <= B200_OP_IMFORM) || (op >= B200_OP_MULSCALAR_MONT && op <= B200_OP_SUB_SCALAR);
-    if (unary) {
-        if (int rc = check_polys(ctx, level, "b200_vec_op", {p1, p3}, &batch)) return rc;
+    const bool binary = op <= B200_OP_SUB_LAZY || (op >= B200_OP_MUL_BARRETT && op <= B200_OP_MUL_MONT_LAZY_NEG) ||
+                        op == B200_OP_SUB_MULSCALAR_MONT_2Q || op == B200_OP_ADD_LAZY_MULSCALAR_MONT;
+    if (!binary) {
+        if (int rc = check_polys(ctx, level, "b200_vec_op", {op == B200_OP_ZERO && !p1 ? p3 : p1, p3}, &batch)) return rc;
     } else {
         if (int rc = check_polys(ctx, level, "b200_vec_op", {p1, p2, p3}, &batch)) return rc;
     }
+    if (op >= B200_OP_ADD_SCALAR_DOUBLE && op <= B200_OP_MULSCALAR_MONT_ADD_DOUBLE && (ctx->N & 3))
+        return fail(B200_ESHAPE, "b200_vec_op: the DoubleRNSScalar operators need N % 4 == 0");
     CUDA_TRY(cudaSetDevice(ctx->device));
     const u64 *d_sc = nullptr;
     if (op >= B200_OP_MULSCALAR_MONT) {
         if (!scalars) return fail(B200_EINVAL, "b200_vec_op: scalar op needs one scalar per limb");
+        const size_t ns = (size_t)(level + 1) * (op >= B200_OP_ADD_SCALAR_LAZY_MULSCALAR_MONT ? 2 : 1);
         // small per-call constant block; lives in the scratch-independent misc area of the stream order
         u64 *tmp = nullptr;
-        CUDA_TRY(cudaMallocAsync(&tmp, sizeof(u64) * (level + 1), ctx->stream));
-        CUDA_TRY(cudaMemcpyAsync(tmp, scalars, sizeof(u64) * (level + 1), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMallocAsync(&tmp, sizeof(u64) * ns, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(tmp, scalars, sizeof(u64) * ns, cudaMemcpyHostToDevice, ctx->stream));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));   // `scalars` is a pageable Go/host slice
         d_sc = tmp;
     }
-    int rc = launch_vec_op(ctx, op, p1->d, p2 ? p2->d : nullptr, p3->d, Span{batch, level + 1, ctx->L, 0}, d_sc);
+    int rc = launch_vec_op(ctx, op, p1 ? p1->d : p3->d, p2 ? p2->d : nullptr, p3->d, Span{batch, level + 1, ctx->L, 0}, d_sc);
     if (d_sc) cudaFreeAsync((void *)d_sc, ctx->stream);
     return rc;
+}
+
+extern "C" int b200_mul_by_vector_montgomery(b200_ctx *ctx, const b200_poly *p1, const b200_poly *vector, b200_poly *p2,
+                                             int level, int then_add_lazy) {
+    CtxLock lk(ctx);
+    int batch;
+    if (int rc = check_polys(ctx, level, "b200_mul_by_vector_montgomery", {p1, p2}, &batch)) return rc;
+    if (!vector || vector->ctx != ctx) return fail(B200_ESHAPE, "b200_mul_by_vector_montgomery: vector must be a polynomial of this ring");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    return launch_mul_by_vector(ctx, p1->d, vector->d, p2->d, Span{batch, level + 1, ctx->L, 0}, then_add_lazy != 0);
 }
 
 // Ring.DivRoundByLastModulusNTT / DivFloorByLastModulusNTT (ring/scaling.go:6-19,130-156) for the whole batch:

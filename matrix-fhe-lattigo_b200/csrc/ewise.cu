@@ -6,7 +6,7 @@
 namespace {
 
 template <int OP>
-__device__ __forceinline__ u64 apply(u64 x, u64 y, u64 z, u64 sc, const LimbConst &c) {
+__device__ __forceinline__ u64 apply(u64 x, u64 y, u64 z, u64 sc, u64 sc2, const LimbConst &c) {
     const u64 q = c.q;
     switch (OP) {
     case B200_OP_ADD: return csub(x + y, q);                                   // vec_ops.go:7-29
@@ -38,23 +38,40 @@ __device__ __forceinline__ u64 apply(u64 x, u64 y, u64 z, u64 sc, const LimbCons
     case B200_OP_ADD_SCALAR: return csub(x + sc, q);                                       // :575-595
     case B200_OP_SUB_SCALAR: return csub(x + q - sc, q);                                   // :642-662
     case B200_OP_SUB_MULSCALAR_MONT_2Q: return mred(2 * q - y + x, sc, q, c.qinv);         // :752-776
+    case B200_OP_ZERO: return 0;                                                           // :847-868
+    case B200_OP_MUL_LAZY: return x * y;                                                   // :169-191
+    case B200_OP_MUL_LAZY_ADD_LAZY: return z + x * y;                                      // :193-215
+    case B200_OP_ADD_LAZY_MULSCALAR_MONT: return mred(x + y, sc, q, c.qinv);               // :529-551
+    case B200_OP_ADD_SCALAR_LAZY: return x + sc;                                           // :597-617
+    case B200_OP_ADD_SCALAR_LAZY_NEG_2Q_LAZY: return sc + 2 * q - x;                       // :619-640
+    case B200_OP_ADD_SCALAR_LAZY_MULSCALAR_MONT: return mred(x + sc, sc2, q, c.qinv);      // :553-573
+    case B200_OP_MULSCALAR_MONT_ADD_SCALAR: return csub(mred(x, sc2, q, c.qinv) + sc, q);  // :730-750
+    case B200_OP_MASK: return sc >= 64 ? 0 : (x >> sc) & sc2;                              // :870-890 (a Go shift by >= 64 gives 0)
+    case B200_OP_ADD_SCALAR_DOUBLE: return csub(x + sc, q);                                // operations.go:167-173
+    case B200_OP_SUB_SCALAR_DOUBLE: return csub(x + q - sc, q);                            // :177-183
+    case B200_OP_MULSCALAR_MONT_DOUBLE: return mred(x, sc, q, c.qinv);                     // :250-256
+    case B200_OP_MULSCALAR_MONT_ADD_DOUBLE: return csub(z + mred(x, sc, q, c.qinv), q);    // :260-266
     }
     return 0;
 }
 
 template <int OP> struct traits {
     static constexpr bool binary = (OP <= B200_OP_SUB_LAZY) || (OP >= B200_OP_MUL_BARRETT && OP <= B200_OP_MUL_MONT_LAZY_NEG) ||
-                                   OP == B200_OP_SUB_MULSCALAR_MONT_2Q;
+                                   OP == B200_OP_SUB_MULSCALAR_MONT_2Q || OP == B200_OP_ADD_LAZY_MULSCALAR_MONT;
     static constexpr bool accum = OP == B200_OP_MUL_BARRETT_ADD || OP == B200_OP_MUL_BARRETT_ADD_LAZY ||
                                   OP == B200_OP_MUL_MONT_ADD || OP == B200_OP_MUL_MONT_ADD_LAZY ||
                                   OP == B200_OP_MUL_MONT_LAZY_ADD_LAZY || OP == B200_OP_MUL_MONT_SUB ||
                                   OP == B200_OP_MUL_MONT_SUB_LAZY || OP == B200_OP_MUL_MONT_LAZY_SUB_LAZY ||
-                                  OP == B200_OP_MULSCALAR_MONT_ADD;
+                                  OP == B200_OP_MULSCALAR_MONT_ADD || OP == B200_OP_MUL_LAZY_ADD_LAZY ||
+                                  OP == B200_OP_MULSCALAR_MONT_ADD_DOUBLE;
     static constexpr bool scalar = OP >= B200_OP_MULSCALAR_MONT;
+    static constexpr bool scalar2 = OP >= B200_OP_ADD_SCALAR_LAZY_MULSCALAR_MONT;   // a second scalar per limb at scalars[nl + limb]
+    static constexpr bool dbl = OP >= B200_OP_ADD_SCALAR_DOUBLE;                    // ... used for the second half of the limb
+    static constexpr bool nosrc = OP == B200_OP_ZERO;
 };
 
 // grid = (chunks per limb, units); a unit is one (poly, limb) pair; every thread owns 2 words per step.
-template <int OP>
+template <int OP, bool BCAST = false>   // BCAST: p2 is one N-word vector shared by every unit (MulByVectorMontgomery)
 __global__ void __launch_bounds__(256)
 k_vec_op(const u64 *p1, const u64 *p2, u64 *p3, const LimbConst *__restrict__ consts,
          const u64 *__restrict__ scalars, int N, Span sp, int unit0) {
@@ -63,21 +80,25 @@ k_vec_op(const u64 *p1, const u64 *p2, u64 *p3, const LimbConst *__restrict__ co
     const size_t base = ((size_t)(unit / sp.nl) * sp.Lbuf + limb) * (size_t)N;
     const LimbConst c = consts[sp.limb0 + limb];
     const u64 sc = traits<OP>::scalar ? scalars[limb] : 0;
+    const u64 sc2 = traits<OP>::scalar2 ? scalars[sp.nl + limb] : 0;
     const ulonglong2 *a = reinterpret_cast<const ulonglong2 *>(p1 + base);
-    const ulonglong2 *b = reinterpret_cast<const ulonglong2 *>(traits<OP>::binary ? p2 + base : p1 + base);
+    const ulonglong2 *b = reinterpret_cast<const ulonglong2 *>(traits<OP>::binary ? (BCAST ? p2 : p2 + base) : p1 + base);
     ulonglong2 *o = reinterpret_cast<ulonglong2 *>(p3 + base);
     const int n2 = N >> 1;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x) {
-        ulonglong2 x = a[i], y = make_ulonglong2(0, 0), z = make_ulonglong2(0, 0);
+        ulonglong2 x = make_ulonglong2(0, 0), y = make_ulonglong2(0, 0), z = make_ulonglong2(0, 0);
+        if (!traits<OP>::nosrc) x = a[i];
         if (traits<OP>::binary) y = b[i];
         if (traits<OP>::accum) z = o[i];
-        z.x = apply<OP>(x.x, y.x, z.x, sc, c);
-        z.y = apply<OP>(x.y, y.y, z.y, sc, c);
+        const bool second = traits<OP>::dbl && 2 * i >= n2;   // word 2i in [N/2, N)
+        const u64 s1 = second ? sc2 : sc;
+        z.x = apply<OP>(x.x, y.x, z.x, s1, sc2, c);
+        z.y = apply<OP>(x.y, y.y, z.y, s1, sc2, c);
         o[i] = z;
     }
 }
 
-template <int OP>
+template <int OP, bool BCAST = false>
 int run(b200_ctx *ctx, const u64 *p1, const u64 *p2, u64 *p3, Span sp, const u64 *d_scalars) {
     const int N = ctx->N, n2 = N >> 1;
     int chunks = (n2 + 255) / 256;
@@ -86,7 +107,7 @@ int run(b200_ctx *ctx, const u64 *p1, const u64 *p2, u64 *p3, Span sp, const u64
     for (int u0 = 0; u0 < units; u0 += 65535) {
         int nu = units - u0 < 65535 ? units - u0 : 65535;
         LaunchScope ls(ctx, "vec_op", nu);
-        k_vec_op<OP><<<dim3(chunks, nu), 256, 0, b200_cur_stream(ctx)>>>(p1, p2, p3, ctx->d_consts, d_scalars, N, sp, u0);
+        k_vec_op<OP, BCAST><<<dim3(chunks, nu), 256, 0, b200_cur_stream(ctx)>>>(p1, p2, p3, ctx->d_consts, d_scalars, N, sp, u0);
     }
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -374,8 +395,18 @@ int launch_vec_op(b200_ctx *ctx, int op, const u64 *p1, const u64 *p2, u64 *p3, 
         CASE(B200_OP_MUL_MONT_LAZY_SUB_LAZY) CASE(B200_OP_MUL_MONT_LAZY_NEG)
         CASE(B200_OP_MULSCALAR_MONT) CASE(B200_OP_MULSCALAR_MONT_LAZY) CASE(B200_OP_MULSCALAR_MONT_ADD)
         CASE(B200_OP_ADD_SCALAR) CASE(B200_OP_SUB_SCALAR) CASE(B200_OP_SUB_MULSCALAR_MONT_2Q)
+        CASE(B200_OP_ZERO) CASE(B200_OP_MUL_LAZY) CASE(B200_OP_MUL_LAZY_ADD_LAZY) CASE(B200_OP_ADD_LAZY_MULSCALAR_MONT)
+        CASE(B200_OP_ADD_SCALAR_LAZY) CASE(B200_OP_ADD_SCALAR_LAZY_NEG_2Q_LAZY) CASE(B200_OP_ADD_SCALAR_LAZY_MULSCALAR_MONT)
+        CASE(B200_OP_MULSCALAR_MONT_ADD_SCALAR) CASE(B200_OP_MASK) CASE(B200_OP_ADD_SCALAR_DOUBLE) CASE(B200_OP_SUB_SCALAR_DOUBLE)
+        CASE(B200_OP_MULSCALAR_MONT_DOUBLE) CASE(B200_OP_MULSCALAR_MONT_ADD_DOUBLE)
     }
 #undef CASE
     b200_set_error("b200_vec_op: unknown op code " + std::to_string(op));
     return B200_EINVAL;
+}
+
+// Ring.MulByVectorMontgomery[ThenAddLazy] (ring/operations.go:366-377): p2 of the kernel is one vector for all units
+int launch_mul_by_vector(b200_ctx *ctx, const u64 *p1, const u64 *vector, u64 *p3, Span sp, bool then_add_lazy) {
+    return then_add_lazy ? run<B200_OP_MUL_MONT_ADD_LAZY, true>(ctx, p1, vector, p3, sp, nullptr)
+                         : run<B200_OP_MUL_MONT, true>(ctx, p1, vector, p3, sp, nullptr);
 }

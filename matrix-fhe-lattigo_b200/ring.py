@@ -32,11 +32,17 @@ _OPS = {
     "MulCoeffsMontgomeryThenAddLazy": 35, "MulCoeffsMontgomeryLazyThenAddLazy": 36,
     "MulCoeffsMontgomeryThenSub": 37, "MulCoeffsMontgomeryThenSubLazy": 38,
     "MulCoeffsMontgomeryLazyThenSubLazy": 39, "MulCoeffsMontgomeryLazyThenNeg": 40,
+    "MulCoeffsLazy": 20, "MulCoeffsLazyThenAddLazy": 21,   # SubRing level only in the reference (subring_ops.go:55-66)
 }
 _UNARY = {"Neg", "Reduce", "ReduceLazy", "MForm", "MFormLazy", "IMForm"}
-_BINARY_SCALAR_OPS = {"SubThenMulScalarMontgomeryTwoModulus": 53}
+_BINARY_SCALAR_OPS = {"SubThenMulScalarMontgomeryTwoModulus": 53, "AddLazyThenMulScalarMontgomery": 54}
+# two scalars per limb, in the Go argument order (scalar0, scalarMont1): subring_ops.go:167, :223; MaskVec(p1, w, mask, p2)
+_TWO_SCALAR_OPS = {"AddScalarLazyThenMulScalarMontgomery": 57, "MulScalarMontgomeryThenAddScalar": 58}
+# Ring.*DoubleRNSScalar* (ring/operations.go:165-266): scalar0 for words [0, N/2), scalar1 for [N/2, N)
+_DOUBLE_OPS = {"AddDoubleRNSScalar": (60, False), "SubDoubleRNSScalar": (61, False), "MulDoubleRNSScalar": (62, True),
+               "MulDoubleRNSScalarThenAdd": (63, True)}
 _SCALAR_OPS = {"MulScalarMontgomery": 48, "MulScalarMontgomeryLazy": 49, "MulScalarMontgomeryThenAdd": 50,
-               "AddScalar": 51, "SubScalar": 52}
+               "AddScalar": 51, "SubScalar": 52, "AddScalarLazy": 55, "AddScalarLazyThenNegTwoModulusLazy": 56}
 
 
 def _is_valid_ring_degree_for_3n(N):   # ring/subring.go:14-30
@@ -498,11 +504,34 @@ class Ring:
     def _vec(self, op, p1, p2, p3, scalars=None):
         sc = None
         if scalars is not None:
-            vals = [int(s) for s in scalars]
-            if len(vals) < self.level + 1:
-                raise B200Error(-4, "need one scalar per limb")
-            sc = (C.c_uint64 * (self.level + 1))(*vals[: self.level + 1])
+            if len(scalars) == 2 and not np.isscalar(scalars[0]):   # two scalars per limb: ([scalar0_i], [scalar1_i])
+                if min(len(scalars[0]), len(scalars[1])) < self.level + 1:
+                    raise B200Error(-4, "need one scalar per limb")
+                vals = [int(s) for s in scalars[0][: self.level + 1]] + [int(s) for s in scalars[1][: self.level + 1]]
+            else:
+                vals = [int(s) for s in scalars]
+                if len(vals) < self.level + 1:
+                    raise B200Error(-4, "need one scalar per limb")
+                vals = vals[: self.level + 1]
+            sc = (C.c_uint64 * len(vals))(*vals)
         check(lib().b200_vec_op(self._ctx.h, op, p1.h, p2.h if p2 is not None else None, p3.h, self.level, sc))
+
+    def Zero(self, p):
+        """ring.ZeroVec on limbs 0..level of every polynomial of the batch (ring/vec_ops.go:847-868, Poly.Zero ring/poly.go)."""
+        self._vec(10, p, None, p)
+
+    def MaskVec(self, p1, w, mask, p2):
+        """ring.MaskVec (ring/vec_ops.go:870-890) on every limb: p2 = (p1 >> w) & mask."""
+        n = self.level + 1
+        self._vec(59, p1, None, p2, ([int(w)] * n, [int(mask)] * n))
+
+    def MulByVectorMontgomery(self, p1, vector, p2):
+        """Ring.MulByVectorMontgomery (ring/operations.go:366-370); `vector`: a Poly whose first limb holds the N words."""
+        check(lib().b200_mul_by_vector_montgomery(self._ctx.h, p1.h, vector.h, p2.h, self.level, 0))
+
+    def MulByVectorMontgomeryThenAddLazy(self, p1, vector, p2):
+        """Ring.MulByVectorMontgomeryThenAddLazy (ring/operations.go:373-377)."""
+        check(lib().b200_mul_by_vector_montgomery(self._ctx.h, p1.h, vector.h, p2.h, self.level, 1))
 
     def Equal(self, p1, p2):   # ring/ring.go:546-558: reduces both sides, then compares limbs 0..level
         a, b = self.NewPoly(p1.batch), self.NewPoly(p2.batch)
@@ -610,6 +639,33 @@ def _mk_binary_scalar(name, code):
 
 for _n, _c in _BINARY_SCALAR_OPS.items():
     setattr(Ring, _n, _mk_binary_scalar(_n, _c))
+
+
+def _mk_two_scalar(name, code):
+    def f(self, p1, scalars0, scalars1, p2):
+        self._vec(code, p1, None, p2, (list(scalars0), list(scalars1)))
+    f.__name__ = name
+    f.__doc__ = "per-limb SubRing.%s(p1, scalar0_i, scalarMont1_i, p2) -- ring/subring_ops.go" % name
+    return f
+
+
+def _mk_double(name, code, mform):
+    def f(self, p1, scalar0, scalar1, p2):
+        s0, s1 = list(scalar0), list(scalar1)
+        if mform:   # MForm(scalar_i, q_i, BRedConstant) on the host, like operations.go:253-254
+            qs = [sr.Modulus for sr in self.SubRings[: self.level + 1]]
+            s0 = [int(v) % q * (1 << 64) % q for v, q in zip(s0, qs)]
+            s1 = [int(v) % q * (1 << 64) % q for v, q in zip(s1, qs)]
+        self._vec(code, p1, None, p2, (s0, s1))
+    f.__name__ = name
+    f.__doc__ = "Ring.%s(p1, scalar0, scalar1 RNSScalar, p2) -- ring/operations.go:165-266" % name
+    return f
+
+
+for _n, _c in _TWO_SCALAR_OPS.items():
+    setattr(Ring, _n, _mk_two_scalar(_n, _c))
+for _n, (_c, _m) in _DOUBLE_OPS.items():
+    setattr(Ring, _n, _mk_double(_n, _c, _m))
 
 
 def NewRingFromType(N, Moduli, ringType, device=0, roots=None):

@@ -31,6 +31,10 @@ OPS = {
     "MulCoeffsMontgomeryLazyThenSubLazy": 39, "MulCoeffsMontgomeryLazyThenNeg": 40,
     "MulScalarMontgomery": 48, "MulScalarMontgomeryLazy": 49, "MulScalarMontgomeryThenAdd": 50,
     "AddScalar": 51, "SubScalar": 52, "SubThenMulScalarMontgomeryTwoModulus": 53,
+    "ZeroVec": 10, "MulCoeffsLazy": 20, "MulCoeffsLazyThenAddLazy": 21,
+    "AddLazyThenMulScalarMontgomery": 54, "AddScalarLazy": 55, "AddScalarLazyThenNegTwoModulusLazy": 56,
+    "AddScalarLazyThenMulScalarMontgomery": 57, "MulScalarMontgomeryThenAddScalar": 58, "MaskVec": 59,
+    "AddDoubleScalar": 60, "SubDoubleScalar": 61, "MulDoubleScalarMontgomery": 62, "MulDoubleScalarMontgomeryThenAdd": 63,
 }
 
 
@@ -75,6 +79,7 @@ def lib():
             "ref_automorphism_ntt_index": (C.c_int, [C.c_int, u64, u64, P64]),
             "ref_automorphism": (None, [C.c_int, u64, C.c_int, u64, P64, P64]),
             "ref_vec_op": (C.c_int, [C.c_int, C.c_int, u64, P64, P64, P64, u64]),
+            "ref_vec_op2": (C.c_int, [C.c_int, C.c_int, u64, P64, P64, P64, u64, u64]),
             "ref_3n_exponents": (C.c_int, [C.c_int, PI]),
             "ref_3n_forward_horner": (None, [C.c_int, u64, u64, P64, P64]),
             "ref_3n_forward_horner_at": (u64, [C.c_int, u64, u64, P64, C.c_int]),
@@ -131,13 +136,13 @@ def find_3n_rns_primes(N, bitsize, count, budget=1 << 20):
     return [int(x) for x in out]
 
 
-def vec_op(name, q, p1, p2=None, p3=None, scalar=0):
-    """One limb of ring/vec_ops.go; returns the new p3."""
+def vec_op(name, q, p1, p2=None, p3=None, scalar=0, scalar1=0):
+    """One limb of ring/vec_ops.go; returns the new p3.  scalar1: second scalar of the two-scalar operators."""
     p1 = _arr(p1)
     N = len(p1)
     p2a = _arr(p2) if p2 is not None else None
     out = _arr(p3).copy() if p3 is not None else np.zeros(N, dtype=np.uint64)
-    rc = lib().ref_vec_op(OPS[name], N, q, _p(p1), _p(p2a) if p2a is not None else None, _p(out), scalar)
+    rc = lib().ref_vec_op2(OPS[name], N, q, _p(p1), _p(p2a) if p2a is not None else None, _p(out), scalar, scalar1)
     if rc:
         raise ValueError(name)
     return out

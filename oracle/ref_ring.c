@@ -501,15 +501,29 @@ EXPORT void ref_automorphism(int N, u64 q, int ci, u64 gen, const u64 *in, u64 *
  * ------------------------------------------------------------------------- */
 enum {
     OP_ADD = 0, OP_ADD_LAZY, OP_SUB, OP_SUB_LAZY, OP_NEG, OP_REDUCE, OP_REDUCE_LAZY,
-    OP_MFORM, OP_MFORM_LAZY, OP_IMFORM,
-    OP_MUL_BARRETT = 16, OP_MUL_BARRETT_LAZY, OP_MUL_BARRETT_ADD, OP_MUL_BARRETT_ADD_LAZY,
+    OP_MFORM, OP_MFORM_LAZY, OP_IMFORM, OP_ZERO,
+    OP_MUL_BARRETT = 16, OP_MUL_BARRETT_LAZY, OP_MUL_BARRETT_ADD, OP_MUL_BARRETT_ADD_LAZY, OP_MUL_LAZY, OP_MUL_LAZY_ADD_LAZY,
     OP_MUL_MONT = 32, OP_MUL_MONT_LAZY, OP_MUL_MONT_ADD, OP_MUL_MONT_ADD_LAZY, OP_MUL_MONT_LAZY_ADD_LAZY,
     OP_MUL_MONT_SUB, OP_MUL_MONT_SUB_LAZY, OP_MUL_MONT_LAZY_SUB_LAZY, OP_MUL_MONT_LAZY_NEG,
     OP_MULSCALAR_MONT = 48, OP_MULSCALAR_MONT_LAZY, OP_MULSCALAR_MONT_ADD, OP_ADD_SCALAR, OP_SUB_SCALAR,
-    OP_SUB_MULSCALAR_MONT_2Q
+    OP_SUB_MULSCALAR_MONT_2Q, OP_ADD_LAZY_MULSCALAR_MONT, OP_ADD_SCALAR_LAZY, OP_ADD_SCALAR_LAZY_NEG_2Q_LAZY,
+    OP_ADD_SCALAR_LAZY_MULSCALAR_MONT, OP_MULSCALAR_MONT_ADD_SCALAR, OP_MASK,
+    OP_ADD_SCALAR_DOUBLE, OP_SUB_SCALAR_DOUBLE, OP_MULSCALAR_MONT_DOUBLE, OP_MULSCALAR_MONT_ADD_DOUBLE
 };
-/* p3 = op(p1, p2 [, p3]) on one limb; scalar used by the *_SCALAR ops. Returns 0, or -1 on unknown op. */
+/* p3 = op(p1, p2 [, p3]) on one limb; scalar (scalar0) and scalar1 used by the *_SCALAR ops: two-scalar operators take
+ * (scalar0, scalarMont1) in the Go argument order, MaskVec (w, mask), the Double operators of ring/operations.go:165-266
+ * scalar0 for words [0, N/2) and scalar1 for [N/2, N).  Returns 0, or -1 on unknown op. */
+EXPORT int ref_vec_op2(int op, int N, u64 q, const u64 *p1, const u64 *p2, u64 *p3, u64 scalar, u64 scalar1);
 EXPORT int ref_vec_op(int op, int N, u64 q, const u64 *p1, const u64 *p2, u64 *p3, u64 scalar) {
+    return ref_vec_op2(op, N, q, p1, p2, p3, scalar, 0);
+}
+EXPORT int ref_vec_op2(int op, int N, u64 q, const u64 *p1, const u64 *p2, u64 *p3, u64 scalar, u64 scalar1) {
+    if (op >= OP_ADD_SCALAR_DOUBLE && op <= OP_MULSCALAR_MONT_ADD_DOUBLE) {   /* two half-limb calls of the plain operator */
+        static const int plain[4] = {OP_ADD_SCALAR, OP_SUB_SCALAR, OP_MULSCALAR_MONT, OP_MULSCALAR_MONT_ADD};
+        const int h = N >> 1, o = plain[op - OP_ADD_SCALAR_DOUBLE];
+        if (ref_vec_op2(o, h, q, p1, NULL, p3, scalar, 0)) return -1;
+        return ref_vec_op2(o, N - h, q, p1 + h, NULL, p3 + h, scalar1, 0);
+    }
     u64 brc[2]; ref_gen_bred_constant(q, brc);
     u64 qinv = ref_gen_mred_constant(q), twoq = 2 * q;
     for (int i = 0; i < N; i++) {
@@ -544,6 +558,15 @@ EXPORT int ref_vec_op(int op, int N, u64 q, const u64 *p1, const u64 *p2, u64 *p
         case OP_ADD_SCALAR: z = cred(x + scalar, q); break;                               /* :575-595 */
         case OP_SUB_SCALAR: z = cred(x + q - scalar, q); break;                           /* :642-662 */
         case OP_SUB_MULSCALAR_MONT_2Q: z = ref_mred(twoq - y + x, scalar, q, qinv); break; /* :752-776 */
+        case OP_ZERO: z = 0; break;                                                       /* :847-868 */
+        case OP_MUL_LAZY: z = x * y; break;                                               /* :169-191 */
+        case OP_MUL_LAZY_ADD_LAZY: z += x * y; break;                                     /* :193-215 */
+        case OP_ADD_LAZY_MULSCALAR_MONT: z = ref_mred(x + y, scalar, q, qinv); break;     /* :529-551 */
+        case OP_ADD_SCALAR_LAZY: z = x + scalar; break;                                   /* :597-617 */
+        case OP_ADD_SCALAR_LAZY_NEG_2Q_LAZY: z = scalar + twoq - x; break;                /* :619-640 */
+        case OP_ADD_SCALAR_LAZY_MULSCALAR_MONT: z = ref_mred(x + scalar, scalar1, q, qinv); break;         /* :553-573 */
+        case OP_MULSCALAR_MONT_ADD_SCALAR: z = cred(ref_mred(x, scalar1, q, qinv) + scalar, q); break;     /* :730-750 */
+        case OP_MASK: z = scalar >= 64 ? 0 : (x >> scalar) & scalar1; break;              /* :870-890; Go: x >> w is 0 for w >= 64 */
         default: return -1;
         }
         p3[i] = z;

@@ -519,3 +519,81 @@ def test_sub_then_mulscalar_two_modulus_op():
     r.SubThenMulScalarMontgomeryTwoModulus(r.NewPoly().set(h1), r.NewPoly().set(h2), sc, out)
     for l, q in enumerate(moduli):
         assert (out.get()[0, l] == O.vec_op("SubThenMulScalarMontgomeryTwoModulus", q, h1[0, l], h2[0, l], scalar=sc[l])).all()
+
+
+@pytest.mark.parametrize("N", [16, 24, 3 * 2**10, 1 << 12])
+def test_remaining_vec_ops_bit_exact(N):
+    """The rest of the element-wise family: SubRing.MulCoeffsLazy[ThenAddLazy], AddLazyThenMulScalarMontgomery, AddScalarLazy,
+    AddScalarLazyThenNegTwoModulusLazy, AddScalarLazyThenMulScalarMontgomery, MulScalarMontgomeryThenAddScalar
+    (ring/subring_ops.go:55-66,160-230), ZeroVec / MaskVec (ring/vec_ops.go:847-890), Ring.*DoubleRNSScalar* and
+    MulByVectorMontgomery[ThenAddLazy] (ring/operations.go:165-266,366-377)."""
+    is3n = N % 3 == 0
+    moduli = O.find_3n_rns_primes(N, 60, 3) if is3n else QI60[18:21]
+    r = b200ring.NewRing(N, moduli)
+    batch, L = 2, len(moduli)
+    h1, h2, h3 = (rand_poly(s, batch, moduli, N) for s in (41, 42, 43))
+    h1[1] += h2[1]                                                   # lazy words in [0, 2q)
+    p1, p2 = r.NewPoly(batch).set(h1), r.NewPoly(batch).set(h2)
+    s0 = [1234567890123456789 % q for q in moduli]
+    s1 = [987654321987654321 % q for q in moduli]
+
+    def check(got, name, use2=False, use3=False, **kw):
+        for b in range(batch):
+            for l, q in enumerate(moduli):
+                kws = {k: v[l] for k, v in kw.items()}
+                want = O.vec_op(name, q, h1[b, l], h2[b, l] if use2 else None, h3[b, l] if use3 else None, **kws)
+                assert (got[b, l] == want).all(), (name, b, l)
+
+    for name, use3 in (("MulCoeffsLazy", False), ("MulCoeffsLazyThenAddLazy", True)):
+        p3 = r.NewPoly(batch).set(h3)
+        getattr(r, name)(p1, p2, p3)
+        check(p3.get(), name, use2=True, use3=use3)
+    p3 = r.NewPoly(batch).set(h3)
+    r.AddLazyThenMulScalarMontgomery(p1, p2, s1, p3)
+    check(p3.get(), "AddLazyThenMulScalarMontgomery", use2=True, scalar=s1)
+    for name in ("AddScalarLazy", "AddScalarLazyThenNegTwoModulusLazy"):
+        p3 = r.NewPoly(batch).set(h3)
+        getattr(r, name)(p1, s0, p3)
+        check(p3.get(), name, scalar=s0)
+    for name in ("AddScalarLazyThenMulScalarMontgomery", "MulScalarMontgomeryThenAddScalar"):
+        p3 = r.NewPoly(batch).set(h3)
+        getattr(r, name)(p1, s0, s1, p3)
+        check(p3.get(), name, scalar=s0, scalar1=s1)
+    for w, mask in [(0, 0xffff), (13, (1 << 20) - 1), (63, 1), (64, 2**64 - 1)]:
+        p3 = r.NewPoly(batch).set(h3)
+        r.MaskVec(p1, w, mask, p3)
+        check(p3.get(), "MaskVec", scalar=[w] * L, scalar1=[mask] * L)
+    # Double operators take plain RNS scalars; the multiplications lift them to Montgomery form like operations.go:253-254
+    hq = h1 % np.array(moduli, dtype=np.uint64)[None, :, None]
+    pq = r.NewPoly(batch).set(hq)
+    m0 = [v * 2**64 % q for v, q in zip(s0, moduli)]
+    m1 = [v * 2**64 % q for v, q in zip(s1, moduli)]
+    for name, oname, a0, a1, use3 in (("AddDoubleRNSScalar", "AddDoubleScalar", s0, s1, False), ("SubDoubleRNSScalar", "SubDoubleScalar", s0, s1, False),
+                                      ("MulDoubleRNSScalar", "MulDoubleScalarMontgomery", m0, m1, False),
+                                      ("MulDoubleRNSScalarThenAdd", "MulDoubleScalarMontgomeryThenAdd", m0, m1, True)):
+        p3 = r.NewPoly(batch).set(h3)
+        getattr(r, name)(pq, s0, s1, p3)
+        got = p3.get()
+        for b in range(batch):
+            for l, q in enumerate(moduli):
+                want = O.vec_op(oname, q, hq[b, l], None, h3[b, l] if use3 else None, scalar=a0[l], scalar1=a1[l])
+                assert (got[b, l] == want).all(), (name, b, l)
+    # one vector for every limb of every polynomial
+    vec = r.NewPoly(1).set(h2[:1])
+    for name, oname, use3 in (("MulByVectorMontgomery", "MulCoeffsMontgomery", False), ("MulByVectorMontgomeryThenAddLazy", "MulCoeffsMontgomeryThenAddLazy", True)):
+        p3 = r.NewPoly(batch).set(h3)
+        getattr(r, name)(p1, vec, p3)
+        got = p3.get()
+        for b in range(batch):
+            for l, q in enumerate(moduli):
+                want = O.vec_op(oname, q, h1[b, l], h2[0, 0], h3[b, l] if use3 else None)
+                assert (got[b, l] == want).all(), (name, b, l)
+    # ZeroVec at a lower level leaves the limbs above it alone
+    p3 = r.NewPoly(batch).set(h3)
+    r.AtLevel(L - 2).Zero(p3)
+    got = p3.get()
+    assert not got[:, : L - 1].any() and (got[:, L - 1] == h3[:, L - 1]).all()
+    if N % 4:
+        return
+    with pytest.raises(b200ring.B200Error):
+        r.AddScalarLazyThenMulScalarMontgomery(p1, s0[:1], s1, p3)

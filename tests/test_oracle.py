@@ -81,6 +81,39 @@ def test_vec_ops_against_python_ints():
     assert chk(O.vec_op("Reduce", q, big), [int(x) % q for x in big])
 
 
+def test_remaining_vec_ops_against_python_ints():
+    """The rest of ring/vec_ops.go / ring/subring_ops.go:55-66,160-230 and the Double operators of ring/operations.go:165-266,
+    word for word against Python integers (lazy results are the Go expressions modulo 2^64)."""
+    q = QI60[3]
+    rng = np.random.default_rng(11)
+    N, M = 64, 1 << 64
+    a = rng.integers(0, 2 * q, N, dtype=np.uint64)          # lazy inputs
+    b = rng.integers(0, 2 * q, N, dtype=np.uint64)
+    c = rng.integers(0, q, N, dtype=np.uint64)
+    rinv = pow(2**64, -1, q)
+    A, B, Cc = [int(x) for x in a], [int(x) for x in b], [int(x) for x in c]
+    s0, s1 = 1234567890123456789 % q, 987654321987654321 % q
+    ints = lambda got: [int(g) for g in got]
+    assert ints(O.vec_op("ZeroVec", q, a, None, c)) == [0] * N
+    assert ints(O.vec_op("MulCoeffsLazy", q, a, b)) == [x * y % M for x, y in zip(A, B)]
+    assert ints(O.vec_op("MulCoeffsLazyThenAddLazy", q, a, b, c)) == [(z + x * y) % M for x, y, z in zip(A, B, Cc)]
+    assert ints(O.vec_op("AddLazyThenMulScalarMontgomery", q, a, b, scalar=s1)) == [(x + y) * s1 * rinv % q for x, y in zip(A, B)]
+    assert ints(O.vec_op("AddScalarLazy", q, a, scalar=s0)) == [(x + s0) % M for x in A]
+    assert ints(O.vec_op("AddScalarLazyThenNegTwoModulusLazy", q, a, scalar=s0)) == [(s0 + 2 * q - x) % M for x in A]
+    assert ints(O.vec_op("AddScalarLazyThenMulScalarMontgomery", q, a, scalar=s0, scalar1=s1)) == [(x + s0) * s1 * rinv % q for x in A]
+    assert ints(O.vec_op("MulScalarMontgomeryThenAddScalar", q, a, scalar=s0, scalar1=s1)) == [(x * s1 * rinv + s0) % q for x in A]
+    for w, mask in [(0, 0xffff), (13, (1 << 20) - 1), (63, 1), (64, M - 1), (200, M - 1)]:
+        assert ints(O.vec_op("MaskVec", q, a, scalar=w, scalar1=mask)) == [(x >> w) & mask for x in A]
+    h = N // 2
+    Cq = [x % q for x in A]
+    cq = np.array(Cq, dtype=np.uint64)
+    assert ints(O.vec_op("AddDoubleScalar", q, cq, scalar=s0, scalar1=s1)) == [(x + (s0 if i < h else s1)) % q for i, x in enumerate(Cq)]
+    assert ints(O.vec_op("SubDoubleScalar", q, cq, scalar=s0, scalar1=s1)) == [(x - (s0 if i < h else s1)) % q for i, x in enumerate(Cq)]
+    assert ints(O.vec_op("MulDoubleScalarMontgomery", q, cq, scalar=s0, scalar1=s1)) == [x * (s0 if i < h else s1) * rinv % q for i, x in enumerate(Cq)]
+    assert ints(O.vec_op("MulDoubleScalarMontgomeryThenAdd", q, cq, None, c, scalar=s0, scalar1=s1)) == [
+        (z + x * (s0 if i < h else s1) * rinv) % q for i, (x, z) in enumerate(zip(Cq, Cc))]
+
+
 def test_3n_prototype_vectors():
     vec = json.load(open(os.path.join(GOLDEN, "ntt3n_proto.json")))["vectors"]
     assert len(vec) >= 8
