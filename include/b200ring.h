@@ -267,6 +267,14 @@ B200_API int b200_ks_mod_down_limbs(b200_keyswitch *ks, int levelQ, int levelP, 
  * ring/scaling.go:6-19) at `level` >= 1 for the whole batch: p1 limbs 0..level-1 = (p0 - [p0]_{q_level}) / q_level.
  * p0 in the NTT domain, canonical; p1 may equal p0 (limb `level` of p1 is left untouched). */
 B200_API int b200_div_by_last_modulus_ntt(b200_ctx *ctx, const b200_poly *p0, b200_poly *p1, int level, int round);
+/* Ring.DivFloorByLastModulus / DivRoundByLastModulus (ring/scaling.go:21-30,113-127): the same division on
+ * coefficient-domain polynomials.  p0 is only read (the Go DivRound leaves intermediate words in p0); p1 may equal p0. */
+B200_API int b200_div_by_last_modulus(b200_ctx *ctx, const b200_poly *p0, b200_poly *p1, int level, int round);
+/* Ring.Div{Floor,Round}ByLastModulusMany (ntt == 0, ring/scaling.go:57-91,160-192) / ...ManyNTT (ntt != 0, :32-55,130-158):
+ * nb_rescales (0..level) successive divisions by q_level, q_level-1, ...; the result is in limbs 0..level-nb_rescales of
+ * p1 (nb_rescales == 0 copies limbs 0..level).  The `buff` polynomial of the Go methods is internal. */
+B200_API int b200_div_by_last_modulus_many(b200_ctx *ctx, const b200_poly *p0, b200_poly *p1, int level, int nb_rescales,
+                                           int round, int ntt);
 
 /* ---- fused ciphertext tensor product in the NTT domain ----------------------------
  * (a0, a1) x (b0, b1) -> c0 = a0*b0, c1 = a0*b1 + a1*b0, c2 = a1*b1, slot-wise, in ONE pass over 4 inputs and

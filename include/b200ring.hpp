@@ -212,6 +212,13 @@ class Ring {
     // ring/scaling.go:130-156 and :6-19 (the Go `buff` argument is internal)
     void DivRoundByLastModulusNTT(const Poly &p0, Poly &p1) const { check(b200_div_by_last_modulus_ntt(ctx_.get(), p0.handle(), p1.handle(), level_, 1)); }
     void DivFloorByLastModulusNTT(const Poly &p0, Poly &p1) const { check(b200_div_by_last_modulus_ntt(ctx_.get(), p0.handle(), p1.handle(), level_, 0)); }
+    // ring/scaling.go:21-30,113-127 (coefficient domain) and :32-91,130-192 (nbRescales divisions; `buff` is internal)
+    void DivFloorByLastModulus(const Poly &p0, Poly &p1) const { check(b200_div_by_last_modulus(ctx_.get(), p0.handle(), p1.handle(), level_, 0)); }
+    void DivRoundByLastModulus(const Poly &p0, Poly &p1) const { check(b200_div_by_last_modulus(ctx_.get(), p0.handle(), p1.handle(), level_, 1)); }
+    void DivFloorByLastModulusMany(int nb, const Poly &p0, Poly &p1) const { check(b200_div_by_last_modulus_many(ctx_.get(), p0.handle(), p1.handle(), level_, nb, 0, 0)); }
+    void DivFloorByLastModulusManyNTT(int nb, const Poly &p0, Poly &p1) const { check(b200_div_by_last_modulus_many(ctx_.get(), p0.handle(), p1.handle(), level_, nb, 0, 1)); }
+    void DivRoundByLastModulusMany(int nb, const Poly &p0, Poly &p1) const { check(b200_div_by_last_modulus_many(ctx_.get(), p0.handle(), p1.handle(), level_, nb, 1, 0)); }
+    void DivRoundByLastModulusManyNTT(int nb, const Poly &p0, Poly &p1) const { check(b200_div_by_last_modulus_many(ctx_.get(), p0.handle(), p1.handle(), level_, nb, 1, 1)); }
     // NTT / INTT sequence on host-resident polynomials, copies overlapped with compute
     void TransformHost(const std::vector<uint64_t> &in, std::vector<uint64_t> &out, const std::vector<int> &ops) const {
         const size_t per = (size_t)ModuliChainLength() * N();

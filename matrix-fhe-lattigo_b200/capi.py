@@ -59,6 +59,8 @@ SYMBOLS = {
     "b200_ks_decompose_mac": (C.c_int, [VP, C.c_int, C.c_int, VP, VP, VP, VP, VP, C.c_int, C.c_int, C.c_int, C.c_int]),
     "b200_ks_mod_down_limbs": (C.c_int, [VP, C.c_int, C.c_int, VP, VP, C.c_int, C.c_int]),
     "b200_div_by_last_modulus_ntt": (C.c_int, [VP, VP, VP, C.c_int, C.c_int]),
+    "b200_div_by_last_modulus": (C.c_int, [VP, VP, VP, C.c_int, C.c_int]),
+    "b200_div_by_last_modulus_many": (C.c_int, [VP, VP, VP, C.c_int, C.c_int, C.c_int, C.c_int]),
     "b200_tensor": (C.c_int, [VP, VP, VP, VP, VP, VP, VP, VP, C.c_int, C.c_int]),
     "b200_polymul": (C.c_int, [VP, VP, VP, VP, C.c_int]),
     "b200_shift": (C.c_int, [VP, VP, C.c_int, VP]),

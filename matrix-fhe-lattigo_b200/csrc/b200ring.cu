@@ -737,8 +737,12 @@ extern "C" int b200_mul_by_vector_montgomery(b200_ctx *ctx, const b200_poly *p1,
 
 // Ring.DivRoundByLastModulusNTT / DivFloorByLastModulusNTT (ring/scaling.go:6-19,130-156) for the whole batch:
 // INTT of the last limb -> spread to the lower limbs -> NTT of those -> SubThenMulScalarMontgomeryTwoModulus.
+static int div_ntt_locked(b200_ctx *ctx, const b200_poly *p0, b200_poly *p1, int level, int round);
 extern "C" int b200_div_by_last_modulus_ntt(b200_ctx *ctx, const b200_poly *p0, b200_poly *p1, int level, int round) {
     CtxLock lk(ctx);
+    return div_ntt_locked(ctx, p0, p1, level, round);
+}
+static int div_ntt_locked(b200_ctx *ctx, const b200_poly *p0, b200_poly *p1, int level, int round) {
     int batch;
     if (int rc = check_polys(ctx, level, "b200_div_by_last_modulus_ntt", {p0, p1}, &batch)) return rc;
     if (level < 1) return fail(B200_ESHAPE, "b200_div_by_last_modulus_ntt: needs level >= 1");
@@ -757,6 +761,51 @@ extern "C" int b200_div_by_last_modulus_ntt(b200_ctx *ctx, const b200_poly *p0, 
     if ((rc = ntt(ws, ws, Span{batch, level, ctx->L, 0}, false))) return rc;             // :143
     return launch_vec_op(ctx, B200_OP_SUB_MULSCALAR_MONT_2Q, ws, p0->d, p1->d, Span{batch, level, ctx->L, 0},
                          ctx->d_rescale + (size_t)(level - 1) * ctx->L);                         // :144
+}
+
+// Ring.DivFloorByLastModulus / DivRoundByLastModulus (ring/scaling.go:21-30,113-127), coefficient domain
+extern "C" int b200_div_by_last_modulus(b200_ctx *ctx, const b200_poly *p0, b200_poly *p1, int level, int round) {
+    CtxLock lk(ctx);
+    int batch;
+    if (int rc = check_polys(ctx, level, "b200_div_by_last_modulus", {p0, p1}, &batch)) return rc;
+    if (level < 1) return fail(B200_ESHAPE, "b200_div_by_last_modulus: needs level >= 1");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    return launch_div_last(ctx, p0->d, p1->d, batch, level, round != 0);
+}
+
+// Ring.Div{Floor,Round}ByLastModulusMany[NTT] (ring/scaling.go:32-91,130-192): nb_rescales divisions by the last moduli
+// of levels level, level-1, ...; p1 limbs 0..level-nb_rescales hold the result.
+extern "C" int b200_div_by_last_modulus_many(b200_ctx *ctx, const b200_poly *p0, b200_poly *p1, int level, int nb_rescales,
+                                             int round, int ntt) {
+    CtxLock lk(ctx);
+    int batch;
+    if (int rc = check_polys(ctx, level, "b200_div_by_last_modulus_many", {p0, p1}, &batch)) return rc;
+    if (nb_rescales < 0 || nb_rescales > level) return fail(B200_ESHAPE, "b200_div_by_last_modulus_many: nb_rescales must be in [0, level]");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const size_t N = ctx->N, words = (size_t)batch * ctx->L * N;
+    if (nb_rescales == 0) {   // :33-36: p1.Copy(p0)
+        if (p0->d != p1->d)
+            CUDA_TRY(cudaMemcpy2DAsync(p1->d, ctx->L * N * sizeof(u64), p0->d, ctx->L * N * sizeof(u64), (size_t)(level + 1) * N * sizeof(u64), batch,
+                                       cudaMemcpyDeviceToDevice, b200_cur_stream(ctx)));
+        return 0;
+    }
+    if (ntt && nb_rescales == 1) return div_ntt_locked(ctx, p0, p1, level, round);   // :150-152 (and the same residues for the floor form)
+    if (!ntt && nb_rescales == 1) return launch_div_last(ctx, p0->d, p1->d, batch, level, round != 0);
+    if (int rc = b200_ensure_scratch2(ctx, words)) return rc;
+    u64 *ws = ctx->d_ws;
+    int rc = 0;
+    const u64 *src = p0->d;
+    if (ntt) {
+        if ((rc = launch_ntt(ctx, p0->d, ws, Span{batch, level + 1, ctx->L, 0}, true, 0))) return rc;   // rCpy.INTT(p0, buff)
+        src = ws;
+    }
+    for (int i = 0; i < nb_rescales; ++i) {
+        u64 *dst = (!ntt && i == nb_rescales - 1) ? p1->d : ws;
+        if ((rc = launch_div_last(ctx, src, dst, batch, level - i, round != 0))) return rc;
+        src = ws;
+    }
+    if (ntt) rc = launch_ntt(ctx, ws, p1->d, Span{batch, level + 1 - nb_rescales, ctx->L, 0}, false, 0);   // rCpy.NTT(buff, p1)
+    return rc;
 }
 
 extern "C" int b200_tensor(b200_ctx *ctx, const b200_poly *a0, const b200_poly *a1, const b200_poly *b0, const b200_poly *b1,

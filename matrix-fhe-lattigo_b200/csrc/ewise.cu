@@ -282,6 +282,39 @@ k_rescale_spread(u64 *ws, const LimbConst *__restrict__ consts, int N, int Lbuf,
     }
 }
 
+// Ring.DivFloorByLastModulus / DivRoundByLastModulus (ring/scaling.go:21-30,113-127): the coefficient-domain rescale.
+// Unit = (polynomial, limb i < level); x is the word of limb `level`, y the word of limb i, rc = RescaleConstants[level-1][i]:
+//   floor: MRed(2q_i - y + x, rc)                                                          (SubThenMulScalarMontgomeryTwoModulus)
+//   round: MRed(CRed(x + pHalf, q_level) + ((q_i - BRedAdd(pHalf, q_i)) + 2q_i - y), rc)   (AddScalar, AddScalarLazyThenNegTwoModulusLazy,
+//                                                                                          AddLazyThenMulScalarMontgomery)
+// in == out is allowed: limb `level` is only read.
+template <bool ROUND>
+__global__ void __launch_bounds__(256)
+k_div_last(const u64 *in, u64 *out, const LimbConst *__restrict__ consts, const u64 *__restrict__ rescale, int N, int Lbuf, int level, int unit0) {
+    const int unit = unit0 + blockIdx.y, b = unit / level, i = unit - b * level;
+    const LimbConst c = consts[i];
+    const u64 ql = consts[level].q, phalf = (ql - 1) >> 1, rc = rescale[i], q = c.q;
+    const u64 s = ROUND ? q - bred_add(phalf, q, c.brc_hi) : 0;
+    const ulonglong2 *xl = reinterpret_cast<const ulonglong2 *>(in + ((size_t)b * Lbuf + level) * (size_t)N);
+    const ulonglong2 *yi = reinterpret_cast<const ulonglong2 *>(in + ((size_t)b * Lbuf + i) * (size_t)N);
+    ulonglong2 *o = reinterpret_cast<ulonglong2 *>(out + ((size_t)b * Lbuf + i) * (size_t)N);
+    const int n2 = N >> 1;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n2; j += gridDim.x * blockDim.x) {
+        ulonglong2 x = xl[j];
+        const ulonglong2 y = yi[j];
+        ulonglong2 r;
+        if (ROUND) {
+            x.x = csub(x.x + phalf, ql); x.y = csub(x.y + phalf, ql);
+            r.x = mred(x.x + (s + 2 * q - y.x), rc, q, c.qinv);
+            r.y = mred(x.y + (s + 2 * q - y.y), rc, q, c.qinv);
+        } else {
+            r.x = mred(2 * q - y.x + x.x, rc, q, c.qinv);
+            r.y = mred(2 * q - y.y + x.y, rc, q, c.qinv);
+        }
+        o[j] = r;
+    }
+}
+
 }  // namespace
 
 int launch_ci_fold(b200_ctx *ctx, const u64 *in, u64 *out, Span sp, bool inverse) {
@@ -363,6 +396,22 @@ int launch_rescale_spread(b200_ctx *ctx, u64 *ws, int batch, int level, bool rou
         const int nb = batch - b0 < 65535 ? batch - b0 : 65535;
         LaunchScope ls(ctx, "rescale_spread", (long long)nb * level);
         k_rescale_spread<<<dim3(chunks, nb), 256, 0, b200_cur_stream(ctx)>>>(ws + (size_t)b0 * ctx->L * N, ctx->d_consts, N, ctx->L, level, round ? 1 : 0);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int launch_div_last(b200_ctx *ctx, const u64 *in, u64 *out, int batch, int level, bool round) {
+    const int N = ctx->N, n2 = N >> 1;
+    int chunks = (n2 + 255) / 256;
+    if (chunks > 1024) chunks = 1024;
+    const long long units = (long long)batch * level;
+    const u64 *rescale = ctx->d_rescale + (size_t)(level - 1) * ctx->L;
+    for (long long u0 = 0; u0 < units; u0 += 65535) {
+        const int nu = (int)(units - u0 < 65535 ? units - u0 : 65535);
+        LaunchScope ls(ctx, "div_last", nu);
+        if (round) k_div_last<true><<<dim3(chunks, nu), 256, 0, b200_cur_stream(ctx)>>>(in, out, ctx->d_consts, rescale, N, ctx->L, level, (int)u0);
+        else k_div_last<false><<<dim3(chunks, nu), 256, 0, b200_cur_stream(ctx)>>>(in, out, ctx->d_consts, rescale, N, ctx->L, level, (int)u0);
     }
     CUDA_TRY(cudaGetLastError());
     return 0;

@@ -128,6 +128,7 @@ struct Span {
     int batch, nl, Lbuf, limb0;
 };
 int launch_vec_op(b200_ctx *ctx, int op, const u64 *p1, const u64 *p2, u64 *p3, Span sp, const u64 *d_scalars);
+int launch_div_last(b200_ctx *ctx, const u64 *in, u64 *out, int batch, int level, bool round);
 int launch_mul_by_vector(b200_ctx *ctx, const u64 *p1, const u64 *vector, u64 *p3, Span sp, bool then_add_lazy);
 int launch_rescale_spread(b200_ctx *ctx, u64 *ws, int batch, int level, bool round);
 int launch_tensor(b200_ctx *ctx, const u64 *a0, const u64 *a1, const u64 *b0, const u64 *b1, u64 *c0, u64 *c1, u64 *c2,

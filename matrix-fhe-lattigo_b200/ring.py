@@ -496,6 +496,26 @@ class Ring:
         """ring/scaling.go:6-19."""
         check(lib().b200_div_by_last_modulus_ntt(self._ctx.h, p0.h, p1.h, self.level, 0))
 
+    def DivFloorByLastModulus(self, p0, p1):
+        """ring/scaling.go:21-30 (coefficient domain)."""
+        check(lib().b200_div_by_last_modulus(self._ctx.h, p0.h, p1.h, self.level, 0))
+
+    def DivRoundByLastModulus(self, p0, p1):
+        """ring/scaling.go:113-127 (coefficient domain; p0 is left unchanged unless p1 is p0)."""
+        check(lib().b200_div_by_last_modulus(self._ctx.h, p0.h, p1.h, self.level, 1))
+
+    def DivFloorByLastModulusMany(self, nbRescales, p0, p1):      # ring/scaling.go:57-91
+        check(lib().b200_div_by_last_modulus_many(self._ctx.h, p0.h, p1.h, self.level, int(nbRescales), 0, 0))
+
+    def DivFloorByLastModulusManyNTT(self, nbRescales, p0, p1):   # :32-55
+        check(lib().b200_div_by_last_modulus_many(self._ctx.h, p0.h, p1.h, self.level, int(nbRescales), 0, 1))
+
+    def DivRoundByLastModulusMany(self, nbRescales, p0, p1):      # :160-192
+        check(lib().b200_div_by_last_modulus_many(self._ctx.h, p0.h, p1.h, self.level, int(nbRescales), 1, 0))
+
+    def DivRoundByLastModulusManyNTT(self, nbRescales, p0, p1):   # :130-158
+        check(lib().b200_div_by_last_modulus_many(self._ctx.h, p0.h, p1.h, self.level, int(nbRescales), 1, 1))
+
     def TensorProduct(self, a0, a1, b0, b1, c0, c1, c2, mform=True):
         """(a0,a1) x (b0,b1) -> (c0,c1,c2) in one pass: the MForm/MulCoeffsMontgomery[ThenAdd] sequence of
         ckks.Evaluator.mulRelin (mform=True) or matrix_ckks.Evaluator.Mul (mform=False)."""

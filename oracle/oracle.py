@@ -323,6 +323,49 @@ def div_by_last_modulus_ntt(rings, p0, round=True):
     return out
 
 
+def rescale_constants(moduli, level):
+    """Ring.RescaleConstants[level-1] (ring/ring.go:361-379): MForm(q_i - q_level^-1 mod q_i) for i < level."""
+    ql = int(moduli[level])
+    return [(int(q) - pow(ql, int(q) - 2, int(q))) * (1 << 64) % int(q) for q in moduli[:level]]
+
+
+def div_by_last_modulus(moduli, p0, round=True):
+    """Ring.DivRoundByLastModulus / DivFloorByLastModulus (ring/scaling.go:21-30,113-127) on one coefficient-domain
+    polynomial p0[nl][N], statement by statement with the vector functions of ring/vec_ops.go; returns p1[nl-1][N]
+    (the Go DivRound also overwrites p0 with its intermediates: the copies made here play that role)."""
+    p0 = _arr(p0).copy()
+    level = p0.shape[0] - 1
+    rc = rescale_constants(moduli, level)
+    out = np.empty((level, p0.shape[1]), dtype=np.uint64)
+    if not round:
+        for i in range(level):   # :24-26
+            out[i] = vec_op("SubThenMulScalarMontgomeryTwoModulus", int(moduli[i]), p0[level], p0[i], scalar=rc[i])
+        return out
+    ql = int(moduli[level])
+    phalf = (ql - 1) >> 1
+    p0[level] = vec_op("AddScalar", ql, p0[level], scalar=phalf)                                   # :120
+    for i in range(level):
+        q = int(moduli[i])
+        p0[i] = vec_op("AddScalarLazyThenNegTwoModulusLazy", q, p0[i], scalar=q - phalf % q)       # :123 (BRedAdd(pHalf) = pHalf mod q)
+        out[i] = vec_op("AddLazyThenMulScalarMontgomery", q, p0[level], p0[i], scalar=rc[i])       # :124
+    return out
+
+
+def div_by_last_modulus_many(rings, moduli, p0, nb, round=True, ntt=False):
+    """Ring.Div{Floor,Round}ByLastModulusMany[NTT] (ring/scaling.go:32-91,130-192) on one polynomial p0[nl][N];
+    returns the nl - nb limbs of the result.  `rings`: the oracle SubRings (used by the NTT forms only)."""
+    p0 = _arr(p0)
+    nl = p0.shape[0]
+    if nb == 0:
+        return p0.copy()
+    if ntt and round and nb == 1:
+        return div_by_last_modulus_ntt(rings, p0, round=True)                                      # :150-152
+    buff = np.stack([rings[i].INTT(p0[i]) for i in range(nl)]) if ntt else p0.copy()               # :40 / :140
+    for k in range(nb):
+        buff = div_by_last_modulus(moduli[: nl - k], buff, round=round)
+    return np.stack([rings[i].NTT(buff[i]) for i in range(nl - nb)]) if ntt else buff
+
+
 def totatives(threeN):
     out = np.empty(threeN, dtype=np.int32)
     n = lib().ref_3n_exponents(threeN, out.ctypes.data_as(PI))

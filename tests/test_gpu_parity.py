@@ -597,3 +597,47 @@ def test_remaining_vec_ops_bit_exact(N):
         return
     with pytest.raises(b200ring.B200Error):
         r.AddScalarLazyThenMulScalarMontgomery(p1, s0[:1], s1, p3)
+
+
+@pytest.mark.parametrize("shape", [("std", 64, 4), ("std", 1 << 12, 4), ("m3", 24, 4), ("m3", 3 * 2**12, 3)])
+def test_div_by_last_modulus_coefficient_domain_and_many(shape):
+    """Ring.Div{Floor,Round}ByLastModulus and ...Many[NTT] (ring/scaling.go:21-192) against the oracle's statement-by-statement
+    restatement, batch of 2, in place and at a lower level."""
+    kind, N, L = shape
+    moduli = QI60[:L] if kind == "std" else O.find_3n_rns_primes(N, 60, L)
+    rings = [O.Pow2SubRing(N, q) if kind == "std" else O.ThreeNSubRing(N, q) for q in moduli]
+    r = b200ring.NewRing(N, moduli)
+    batch = 2
+    host = rand_poly(321, batch, moduli, N)
+    p0 = r.NewPoly(batch).set(host)
+    for rnd in (False, True):
+        p1 = r.NewPoly(batch)
+        (r.DivRoundByLastModulus if rnd else r.DivFloorByLastModulus)(p0, p1)
+        got = p1.get()
+        for b in range(batch):
+            assert (got[b, : L - 1] == O.div_by_last_modulus(moduli, host[b], round=rnd)).all(), (shape, rnd, b)
+        assert (p0.get() == host).all()
+        for ntt in (False, True):
+            name = "Div%sByLastModulusMany%s" % ("Round" if rnd else "Floor", "NTT" if ntt else "")
+            for nb in range(L):
+                p1 = r.NewPoly(batch).set(host[::-1].copy())
+                getattr(r, name)(nb, p0, p1)
+                got = p1.get()
+                for b in range(batch):
+                    want = O.div_by_last_modulus_many(rings, moduli, host[b], nb, round=rnd, ntt=ntt)
+                    assert (got[b, : L - nb] == want).all(), (shape, name, nb, b)
+                if nb:   # limbs above the result keep what they held
+                    assert (got[:, L - 1] == host[::-1][:, L - 1]).all()
+    # in place, at a lower level
+    q = r.NewPoly(batch).set(host)
+    r.AtLevel(L - 2).DivRoundByLastModulus(q, q)
+    got = q.get()
+    assert (got[1, : L - 2] == O.div_by_last_modulus(moduli[: L - 1], host[1, : L - 1], round=True)).all()
+    assert (got[:, L - 2:] == host[:, L - 2:]).all()
+    q = r.NewPoly(batch).set(host)
+    r.DivFloorByLastModulusManyNTT(2, q, q)
+    assert (q.get()[0, : L - 2] == O.div_by_last_modulus_many(rings, moduli, host[0], 2, round=False, ntt=True)).all()
+    with pytest.raises(b200ring.B200Error):
+        r.DivRoundByLastModulusMany(L, p0, p1)
+    with pytest.raises(b200ring.B200Error):
+        r.AtLevel(0).DivFloorByLastModulus(p0, p1)

@@ -240,3 +240,34 @@ def test_rescale_matches_big_integer_division(kind):
         for i in range(len(moduli) - 1):
             back = rings[i].INTT(got[i])
             assert [int(v) for v in back] == [w % moduli[i] for w in want], (kind, rnd, i)
+
+
+@pytest.mark.parametrize("kind", ["std", "m3"])
+def test_div_by_last_modulus_many_matches_big_integer_division(kind):
+    """ring/ring_test.go:242-331 (testDivFloorByLastModulusMany / testDivRoundByLastModulusMany): level successive
+    divisions of coefficients below Q/10 equal floored / rounded big-integer division, for the coefficient-domain and the
+    NTT-domain forms of ring/scaling.go:21-192."""
+    N = 32 if kind == "std" else 24
+    L = 4
+    moduli = QI60[:L] if kind == "std" else O.find_3n_rns_primes(N, 60, L)
+    rings = [O.Pow2SubRing(N, q) if kind == "std" else O.ThreeNSubRing(N, q) for q in moduli]
+    rng = np.random.default_rng(9)
+    Q = 1
+    for q in moduli:
+        Q *= q
+    coeffs = [int.from_bytes(rng.bytes(32), "little") % (Q // 10) for _ in range(N)]
+    p0 = np.array([[c % q for c in coeffs] for q in moduli], dtype=np.uint64)
+    p0_ntt = np.stack([r.NTT(p0[i]) for i, r in enumerate(rings)])
+    for rnd in (False, True):
+        for nb in range(L):
+            want = list(coeffs)
+            for j in range(nb):
+                ql = moduli[L - 1 - j]
+                want = [(c + (ql - 1) // 2) // ql if rnd else c // ql for c in want]
+            got = O.div_by_last_modulus_many(rings, moduli, p0, nb, round=rnd, ntt=False)
+            assert got.shape[0] == L - nb
+            for i in range(L - nb):
+                assert [int(v) for v in got[i]] == [w % moduli[i] for w in want], (kind, rnd, nb, i)
+            got = O.div_by_last_modulus_many(rings, moduli, p0_ntt, nb, round=rnd, ntt=True)
+            for i in range(L - nb):
+                assert [int(v) for v in rings[i].INTT(got[i])] == [w % moduli[i] for w in want], (kind, rnd, nb, i, "ntt")
