@@ -216,6 +216,9 @@ B200_API void b200_keyswitch_destroy(b200_keyswitch *ks);
 B200_API int b200_mod_up(b200_keyswitch *ks, int direction, int levelQ, int levelP, const b200_poly *in, b200_poly *out);
 /* BasisExtender.ModDownQPtoQNTT (:241-258): p1 in basis QP, NTT domain -> p2 limbs 0..levelQ = round(p1 / P), canonical */
 B200_API int b200_mod_down_ntt(b200_keyswitch *ks, int levelQ, int levelP, const b200_poly *p1, b200_poly *p2);
+/* BasisExtender.ModDownQPtoQ (to_p == 0, :223-236: p2 limbs 0..levelQ = round(p1 / P)) and ModDownQPtoP (to_p != 0, :264-279:
+ * p2 limbs LQ..LQ+levelP = (p1 - [p1]_Q) / Q with [.]_Q the centred residue) on coefficient-domain polynomials, canonical. */
+B200_API int b200_mod_down(b200_keyswitch *ks, int to_p, int levelQ, int levelP, const b200_poly *p1, b200_poly *p2);
 /* rlwe.Evaluator.GadgetProduct for NTT-domain operands (core/rlwe/evaluator_gadget_product.go:16-30, 123-188, 455-478;
  * with one special prime, levelP == 0, the reference's :190-320 with mask == 0, which gives the same result): ct = (<decomp(cx), key[.][0]>, <decomp(cx), key[.][1]>) / P mod Q.  cx: batch B, Q limbs used.
  * key: 2*beta polynomials ordered [digit][component], NTT domain and Montgomery form over QP

@@ -287,6 +287,8 @@ class KeySwitcher {
     void ModUpQtoP(int levelQ, int levelP, const Poly &polQ, Poly &polP) const { check(b200_mod_up(ks_.get(), 0, levelQ, levelP, polQ.handle(), polP.handle())); }
     void ModUpPtoQ(int levelP, int levelQ, const Poly &polP, Poly &polQ) const { check(b200_mod_up(ks_.get(), 1, levelQ, levelP, polP.handle(), polQ.handle())); }
     void ModDownQPtoQNTT(int levelQ, int levelP, const Poly &p1, Poly &p2) const { check(b200_mod_down_ntt(ks_.get(), levelQ, levelP, p1.handle(), p2.handle())); }
+    void ModDownQPtoQ(int levelQ, int levelP, const Poly &p1, Poly &p2) const { check(b200_mod_down(ks_.get(), 0, levelQ, levelP, p1.handle(), p2.handle())); }   // :223-236
+    void ModDownQPtoP(int levelQ, int levelP, const Poly &p1, Poly &p2) const { check(b200_mod_down(ks_.get(), 1, levelQ, levelP, p1.handle(), p2.handle())); }   // :264-279
     void GadgetProduct(int levelQ, int levelP, const Poly &cx, const Poly &key, Poly &ct0, Poly &ct1) const {
         check(b200_gadget_product(ks_.get(), levelQ, levelP, cx.handle(), key.handle(), ct0.handle(), ct1.handle()));
     }

@@ -49,6 +49,7 @@ SYMBOLS = {
     "b200_keyswitch_destroy": (None, [VP]),
     "b200_mod_up": (C.c_int, [VP, C.c_int, C.c_int, C.c_int, VP, VP]),
     "b200_mod_down_ntt": (C.c_int, [VP, C.c_int, C.c_int, VP, VP]),
+    "b200_mod_down": (C.c_int, [VP, C.c_int, C.c_int, C.c_int, VP, VP]),
     "b200_gadget_product": (C.c_int, [VP, C.c_int, C.c_int, VP, VP, VP, VP]),
     "b200_decompose_ntt": (C.c_int, [VP, C.c_int, C.c_int, VP, VP]),
     "b200_gadget_product_hoisted": (C.c_int, [VP, C.c_int, C.c_int, VP, VP, VP, VP]),

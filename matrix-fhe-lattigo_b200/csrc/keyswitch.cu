@@ -307,6 +307,7 @@ struct b200_keyswitch {
     u64 *ws = nullptr;                       // cxInv, c2, acc0, acc1: 4 polys of [batch][L][N]
     size_t ws_words = 0;
     u64 *d_moddown = nullptr;                // [LP][LQ]: q_i - moddown[levelP][i], the scalar of the final ModDown pass
+    u64 *d_moddown_qp = nullptr;             // [LQ][LP]: p_j - MForm((q_0..q_levelQ)^-1 mod p_j), the same for ModDownQPtoP (modDownConstantsQtoP, :61)
     std::map<int, int *> limb_lists;         // (levelQ, levelP) -> device list of the limbs the multiply-accumulate touches
 };
 
@@ -617,6 +618,17 @@ extern "C" int b200_keyswitch_create(b200_ctx *ctx, int LQ, b200_keyswitch **out
         for (int i = 0; i < LQ; ++i) sc[(size_t)j * LQ + i] = ctx->sub[i].q - ks->moddown[j][i];
     cudaError_t ce = upload(&ks->d_moddown, sc);
     if (ce != cudaSuccess) { delete ks; return b200_cuda_fail(ce, "b200_keyswitch_create"); }
+    std::vector<u64> sp((size_t)LQ * ks->LP);   // genmodDownConstants(ringP, ringQ) (:61): [levelQ][j]
+    for (int j = 0; j < ks->LP; ++j) {
+        const u64 pj = ctx->sub[LQ + j].q;
+        u64 prod = 1;
+        for (int i = 0; i < LQ; ++i) {
+            prod = hm::mulmod(prod, ctx->sub[i].q % pj, pj);
+            sp[(size_t)i * ks->LP + j] = pj - hm::mform(hm::invmod_prime(prod, pj), pj);
+        }
+    }
+    ce = upload(&ks->d_moddown_qp, sp);
+    if (ce != cudaSuccess) { cudaFree(ks->d_moddown); delete ks; return b200_cuda_fail(ce, "b200_keyswitch_create"); }
     *out = ks;
     return 0;
 }
@@ -624,7 +636,7 @@ extern "C" void b200_keyswitch_destroy(b200_keyswitch *ks) {
     if (!ks) return;
     cudaSetDevice(ks->ctx->device);
     for (auto &kv : ks->cache) kv.second.release();
-    cudaFree(ks->ws); cudaFree(ks->d_moddown);
+    cudaFree(ks->ws); cudaFree(ks->d_moddown); cudaFree(ks->d_moddown_qp);
     for (auto &kv : ks->limb_lists) cudaFree(kv.second);
     delete ks;
 }
@@ -653,6 +665,30 @@ extern "C" int b200_mod_down_ntt(b200_keyswitch *ks, int levelQ, int levelP, con
     const size_t words = (size_t)p1->batch * ks->ctx->L * ks->ctx->N;
     if (int rc = ensure_ws(ks, words)) return rc;
     return mod_down_ntt(ks, levelQ, levelP, p1->d, p2->d, ks->ws, p1->batch);
+}
+
+// BasisExtender.ModDownQPtoQ (:223-236, to_p == 0) / ModDownQPtoP (:264-279, to_p != 0): the coefficient-domain forms --
+// exact extension of the dropped basis into the kept one, then (p1 - ext) * (dropped product)^-1 on the kept limbs.
+extern "C" int b200_mod_down(b200_keyswitch *ks, int to_p, int levelQ, int levelP, const b200_poly *p1, b200_poly *p2) {
+    CtxLock lk(ks ? ks->ctx : nullptr);
+    if (int rc = check_levels(ks, levelQ, levelP, "b200_mod_down")) return rc;
+    if (int rc = check_poly(ks, p1, "b200_mod_down")) return rc;
+    if (int rc = check_poly(ks, p2, "b200_mod_down")) return rc;
+    if (p1->batch != p2->batch) { b200_set_error("b200_mod_down: batch sizes differ"); return B200_ESHAPE; }
+    b200_ctx *ctx = ks->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const int LQ = ks->LQ, batch = p1->batch;
+    if (int rc = ensure_ws(ks, (size_t)batch * ctx->L * ctx->N)) return rc;
+    Extender *e;
+    const std::vector<int> q = range(0, levelQ + 1), p = range(LQ, LQ + levelP + 1);
+    if (int rc = get_extender(ks, to_p ? q : p, to_p ? p : q, true, &e)) return rc;
+    if (int rc = run_extend(ks, e, p1->d, ks->ws, batch, 1)) return rc;
+    if (!to_p)
+        return launch_vec_op(ctx, B200_OP_SUB_MULSCALAR_MONT_2Q, ks->ws, p1->d, p2->d, Span{batch, levelQ + 1, ctx->L, 0},
+                             ks->d_moddown + (size_t)levelP * LQ);
+    const size_t off = (size_t)LQ * ctx->N;
+    return launch_vec_op(ctx, B200_OP_SUB_MULSCALAR_MONT_2Q, ks->ws + off, p1->d + off, p2->d + off, Span{batch, levelP + 1, ctx->L, LQ},
+                         ks->d_moddown_qp + (size_t)levelQ * ks->LP);
 }
 
 // rlwe.Evaluator.GadgetProduct (NTT-domain operands): evaluator_gadget_product.go:16-30,123-188,455-478.  With one special

@@ -581,6 +581,12 @@ class KeySwitcher:
     def ModDownQPtoQNTT(self, levelQ, levelP, p1, p2):   # :241-258
         check(lib().b200_mod_down_ntt(self.h, levelQ, levelP, p1.h, p2.h))
 
+    def ModDownQPtoQ(self, levelQ, levelP, p1, p2):   # :223-236 (coefficient domain)
+        check(lib().b200_mod_down(self.h, 0, levelQ, levelP, p1.h, p2.h))
+
+    def ModDownQPtoP(self, levelQ, levelP, p1, p2):   # :264-279 (coefficient domain; result in the P limbs of p2)
+        check(lib().b200_mod_down(self.h, 1, levelQ, levelP, p1.h, p2.h))
+
     def GadgetProduct(self, levelQ, levelP, cx, key, ct0, ct1):   # core/rlwe/evaluator_gadget_product.go:16-30
         check(lib().b200_gadget_product(self.h, levelQ, levelP, cx.h, key.h, ct0.h, ct1.h))
 

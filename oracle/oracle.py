@@ -466,6 +466,7 @@ class BasisExtender:
         rinv = lambda q: pow(2**64, 1, q)
         # genmodDownConstants (:24-49): Montgomery form of (p_0 ... p_j)^-1 mod q_i
         self.modDownPtoQ = [[(pow(_prod(self.P[: j + 1]), -1, q) * rinv(q)) % q for q in self.Q] for j in range(len(self.P))]
+        self.modDownQtoP = [[(pow(_prod(self.Q[: i + 1]), -1, p) * rinv(p)) % p for p in self.P] for i in range(len(self.Q))]   # :61
 
     def ModUpQtoP(self, levelQ, levelP, polQ):
         """:184-198  polQ [levelQ+1][N] -> polP [levelP+1][N] (lazy words exactly as the Go code leaves them)."""
@@ -480,6 +481,18 @@ class BasisExtender:
         buff = np.stack([vec_op("AddScalar", p, polP[j], scalar=PHalf % p) for j, p in enumerate(self.P[: levelP + 1])])
         ext = self.PtoQ[levelP].extend(buff, range(levelQ + 1))
         return np.stack([vec_op("SubScalar", q, ext[i], scalar=PHalf % q) for i, q in enumerate(self.Q[: levelQ + 1])])
+
+    def ModDownQPtoQ(self, levelQ, levelP, p1Q, p1P):
+        """:223-236  (coefficient domain) -> p2Q [levelQ+1][N], canonical."""
+        buffQ = self.ModUpPtoQ(levelP, levelQ, p1P)
+        return np.stack([vec_op("SubThenMulScalarMontgomeryTwoModulus", q, buffQ[i], p1Q[i], scalar=q - self.modDownPtoQ[levelP][i])
+                         for i, q in enumerate(self.Q[: levelQ + 1])])
+
+    def ModDownQPtoP(self, levelQ, levelP, p1Q, p1P):
+        """:264-279  (coefficient domain) -> p2P [levelP+1][N], canonical."""
+        buffP = self.ModUpQtoP(levelQ, levelP, p1Q)
+        return np.stack([vec_op("SubThenMulScalarMontgomeryTwoModulus", p, buffP[j], p1P[j], scalar=p - self.modDownQtoP[levelQ][j])
+                         for j, p in enumerate(self.P[: levelP + 1])])
 
     def ModDownQPtoQNTT(self, levelQ, levelP, p1Q, p1P, ringsQ, ringsP):
         """:241-258  (inputs NTT domain) -> p2Q [levelQ+1][N], canonical."""

@@ -62,6 +62,16 @@ def test_oracle_basis_extension_vs_big_integers():
     out = be.ModDownQPtoQNTT(3, 2, xQ, xP, rq, rp)
     for i, q in enumerate(Q):   # rounded division by P
         assert [int(v) for v in rq[i].INTT(out[i])] == [((x + Pp // 2) // Pp) % q for x in xs]
+    # the coefficient-domain forms (:223-236, :264-279)
+    cQ = np.array([[x % q for x in xs] for q in Q], dtype=np.uint64)
+    cP = np.array([[x % p for x in xs] for p in P], dtype=np.uint64)
+    out = be.ModDownQPtoQ(3, 2, cQ, cP)
+    for i, q in enumerate(Q):
+        assert [int(v) for v in out[i]] == [((x + Pp // 2) // Pp) % q for x in xs]
+    out = be.ModDownQPtoP(3, 2, cQ, cP)
+    centred = lambda x: x % Qp if x % Qp <= Qp // 2 else x % Qp - Qp
+    for j, p in enumerate(P):   # (x - [x]_Q) / Q with the centred residue
+        assert [int(v) for v in out[j]] == [((x - centred(x)) // Qp) % p for x in xs]
 
 
 @pytest.mark.parametrize("kind,N", [("std", 16), ("m3", 24)])
@@ -115,6 +125,14 @@ def test_mod_up_and_mod_down_bit_exact(kind, N, LQ, LP):
         for b in range(batch):
             want = be.ModDownQPtoQNTT(levelQ, levelP, hq[b][: levelQ + 1], hp[b][: levelP + 1], rq, rp)
             assert (got[b, : levelQ + 1] == want).all()
+        ks.ModDownQPtoQ(levelQ, levelP, pin, pout)
+        got = pout.get()
+        for b in range(batch):
+            assert (got[b, : levelQ + 1] == be.ModDownQPtoQ(levelQ, levelP, hq[b][: levelQ + 1], hp[b][: levelP + 1])).all()
+        ks.ModDownQPtoP(levelQ, levelP, pin, pout)
+        got = pout.get()
+        for b in range(batch):
+            assert (got[b, LQ: LQ + levelP + 1] == be.ModDownQPtoP(levelQ, levelP, hq[b][: levelQ + 1], hp[b][: levelP + 1])).all()
     with pytest.raises(b200ring.B200Error):
         ks.ModUpQtoP(LQ, 0, pin, pout)
     with pytest.raises(ValueError):
