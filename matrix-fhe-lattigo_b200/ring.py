@@ -274,6 +274,74 @@ class Ring:
             raise ValueError("cannot StandardRing: the ring is not a conjugate-invariant ring")
         return NewRingFromType(self._N << 1, self._moduli[: self.level + 1], Standard, self.device)
 
+    # -- host-side accessors and big-integer glue of ring/ring.go (no device arithmetic: CRT on downloaded words) --
+    def LogN(self):   # ring/ring.go:159-161
+        return (self._N - 1).bit_length()
+
+    def Modulus(self):   # :232-234: the product of the moduli at this level
+        m = 1
+        for q in self._moduli[: self.level + 1]:
+            m *= q
+        return m
+
+    def LogModuli(self):   # :170-175
+        import math
+        return sum(math.log2(q) for q in self._moduli[: self.level + 1])
+
+    def MRedConstants(self):   # :238-246
+        return [s.MRedConstant for s in self.SubRings[: self.level + 1]]
+
+    def BRedConstants(self):   # :249-257
+        return [s.BRedConstant for s in self.SubRings[: self.level + 1]]
+
+    def NewRNSScalar(self):   # ring/scalar.go:11-13
+        return [0] * (self.level + 1)
+
+    def NewMonomialXi(self, i):
+        """Ring.NewMonomialXi (ring/ring.go:408-430): the polynomial X^i (X^N = -1), coefficient domain."""
+        N = self._N
+        i &= (N << 1) - 1
+        if i >= N:
+            i -= N << 1
+        host = np.zeros((1, len(self._moduli), N), dtype=np.uint64)
+        for k, q in enumerate(self._moduli[: self.level + 1]):
+            if i < 0:
+                host[0, k, N + i] = q - 1
+            else:
+                host[0, k, i] = 1
+        return self.NewPoly().set(host)
+
+    def SetCoefficientsBigint(self, coeffs, p1, b=0):
+        """Ring.SetCoefficientsBigint (ring/ring.go:433-447): limb i of polynomial b of p1 <- coeffs mod q_i."""
+        for i, q in enumerate(self._moduli[: self.level + 1]):
+            limb = p1.get_limb(b, i)
+            limb[: len(coeffs)] = np.array([int(c) % q for c in coeffs], dtype=np.uint64)
+            p1.set_limb(b, i, limb)
+
+    def _crt(self, p1, gap, b, centred):
+        Q = self.Modulus()
+        rec = []
+        for q in self._moduli[: self.level + 1]:
+            m = Q // q
+            rec.append(m * pow(m, -1, q))
+        limbs = [p1.get_limb(b, k) for k in range(self.level + 1)]
+        out = []
+        for j in range(0, self._N, gap):
+            x = sum(int(limbs[k][j]) * rec[k] for k in range(self.level + 1)) % Q
+            out.append(x - Q if centred and x >= (Q >> 1) else x)
+        return out
+
+    def PolyToBigint(self, p1, gap=1, b=0):
+        """Ring.PolyToBigint (ring/ring.go:467-496): CRT reconstruction of the coefficients X^(i*gap), in [0, Q)."""
+        return self._crt(p1, gap, b, False)
+
+    def PolyToBigintCentered(self, p1, gap=1, b=0):
+        """Ring.PolyToBigintCentered (ring/ring.go:503-543): the same, in [-Q/2, Q/2) (values >= floor(Q/2) wrap)."""
+        return self._crt(p1, gap, b, True)
+
+    def PolyToString(self, p1, b=0):   # ring/ring.go:450-462
+        return [str(x) for x in self.PolyToBigint(p1, 1, b)]
+
     def Shift(self, p1, k, p2):
         """Ring.Shift (ring/operations.go:278-282): rotate every limb left by k."""
         check(lib().b200_shift(self._ctx.h, p1.h, int(k), p2.h))

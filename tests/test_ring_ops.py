@@ -98,3 +98,56 @@ def test_scalar_operators_match_big_integers():
     c = [x.get() for x in coeffs]
     for l, q in enumerate(Q):
         assert o.get()[0, l].tolist() == [(int(c[0][0, l, j]) + int(c[1][0, l, j]) * sc + int(c[2][0, l, j]) * sc * sc) % q for j in range(N)]
+
+
+@pytest.mark.parametrize("kind", ["std", "m3"])
+def test_div_by_last_modulus_many_like_the_reference(kind):
+    """ring/ring_test.go:242-331 as written there: random coefficients below Q/10 set with SetCoefficientsBigint, `level`
+    rescales with DivFloor/RoundByLastModulusMany[NTT], compared with big-integer division through PolyToBigint."""
+    N = 64 if kind == "std" else 48
+    Q = QI60[:4] if kind == "std" else b200ring.Find3NRNSPrimes(N, 60, 4, 100000)
+    r = b200ring.NewRing(N, Q)
+    level = r.Level()
+    rng = np.random.default_rng(17)
+    coeffs = [int.from_bytes(rng.bytes(32), "little") % (r.Modulus() // 10) for _ in range(N)]
+    p0, p1 = r.NewPoly(), r.NewPoly()
+    r.SetCoefficientsBigint(coeffs, p0)
+    assert r.PolyToBigint(p0) == coeffs and r.PolyToString(p0)[3] == str(coeffs[3])
+    assert r.PolyToBigint(p0, gap=4) == coeffs[::4]
+    cent = r.PolyToBigintCentered(p0)
+    assert all((c - x) % r.Modulus() == 0 and -(r.Modulus() // 2) - 1 <= c < r.Modulus() // 2 for c, x in zip(cent, coeffs))
+    for rnd in (False, True):
+        want = list(coeffs)
+        for j in range(level):
+            ql = Q[level - j]
+            want = [(c + (ql - 1) // 2) // ql if rnd else c // ql for c in want]
+        (r.DivRoundByLastModulusMany if rnd else r.DivFloorByLastModulusMany)(level, p0, p1)
+        assert r.AtLevel(0).PolyToBigint(p1) == [w % Q[0] for w in want]
+        pn = r.NewPoly()
+        r.NTT(p0, pn)
+        (r.DivRoundByLastModulusManyNTT if rnd else r.DivFloorByLastModulusManyNTT)(level, pn, p1)
+        r.AtLevel(0).INTT(p1, p1)
+        assert r.AtLevel(0).PolyToBigint(p1) == [w % Q[0] for w in want]
+    assert r.PolyToBigint(p0) == coeffs                      # the operand is left as it was
+
+
+def test_ring_accessors_and_monomial():
+    N, Q = 32, QI60[:3]
+    r = b200ring.NewRing(N, Q)
+    assert r.LogN() == 5 and r.Modulus() == Q[0] * Q[1] * Q[2] and r.AtLevel(1).Modulus() == Q[0] * Q[1]
+    assert abs(r.LogModuli() - sum(np.log2(float(q)) for q in Q)) < 1e-9
+    assert r.MRedConstants() == [pow(q, -1, 1 << 64) for q in Q] and r.BRedConstants() == [((1 << 128) // q >> 64, (1 << 128) // q & (2**64 - 1)) for q in Q]
+    assert r.NewRNSScalar() == [0, 0, 0]
+    for i in (0, 5, N, N + 3, 2 * N + 1, -1):
+        m = r.NewMonomialXi(i).get()[0]
+        k = i & (2 * N - 1)
+        for l, q in enumerate(Q):
+            want = np.zeros(N, dtype=np.uint64)
+            want[k % N] = 1 if k < N else q - 1
+            assert (m[l] == want).all(), (i, l)
+    # X^i through the ring product: MultByMonomial(p, i) == p * NewMonomialXi(i)
+    host = rand_poly(0xE1, 1, Q, N)
+    p, o, o2 = r.NewPoly().set(host), r.NewPoly(), r.NewPoly()
+    r.MultByMonomial(p, 7, o)
+    r.MulPoly(p, r.NewMonomialXi(7), o2)
+    assert (o.get() == o2.get()).all()
