@@ -115,7 +115,7 @@ def cpu_run(min_seconds, steps=None, warmup=0, threads=0):
     O.build()
     T = threads or O.num_threads()
     rings = [O.ThreeNSubRing(N, q) for q in MODULI]
-    polys = max(1, (2 * T + L - 1) // L)                      # >= 2 units per thread
+    polys = max(1, (16 * T + L - 1) // L)                     # >= 16 units per thread and direction: a step is ~0.1 s, long enough to amortise the thread start-up
     data = np.empty((polys * L, N), dtype=np.uint64)
     for u in range(polys * L):
         data[u] = O.fill_uniform(0xB2000003, u // L, u % L, MODULI[u % L], N)
