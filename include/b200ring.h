@@ -157,6 +157,9 @@ B200_API int b200_poly_download_limb(b200_poly *p, int b, int limb, uint64_t *ho
 /* the whole [batch][L][N] block from/to one contiguous host buffer (pinned for full PCIe rate) */
 B200_API int b200_poly_upload(b200_poly *p, const uint64_t *host, size_t n_words);
 B200_API int b200_poly_download(b200_poly *p, uint64_t *host, size_t n_words);
+/* Poly.Copy / CopyLvl (ring/poly.go:73-91): limbs 0..level (level < 0: all) of every polynomial of src into dst, on the
+ * device, ordered on the ring's stream.  dst == src is a no-op. */
+B200_API int b200_poly_copy(b200_poly *dst, const b200_poly *src, int level);
 
 /* ---- transforms ---------------------------------------------------------------------------
  * Ring.NTT / NTTLazy (ring/ntt.go:127-138) and Ring.INTT / INTTLazy (ring/ntt.go:141-152) on all

@@ -41,6 +41,7 @@ SYMBOLS = {
     "b200_poly_download_limb": (C.c_int, [VP, C.c_int, C.c_int, P64, C.c_size_t]),
     "b200_poly_upload": (C.c_int, [VP, VP, C.c_size_t]),
     "b200_poly_download": (C.c_int, [VP, VP, C.c_size_t]),
+    "b200_poly_copy": (C.c_int, [VP, VP, C.c_int]),
     "b200_ntt": (C.c_int, [VP, VP, VP, C.c_int, C.c_int]),
     "b200_intt": (C.c_int, [VP, VP, VP, C.c_int, C.c_int]),
     "b200_vec_op": (C.c_int, [VP, C.c_int, VP, VP, VP, C.c_int, P64]),

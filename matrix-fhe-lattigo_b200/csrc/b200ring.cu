@@ -485,6 +485,24 @@ extern "C" int b200_poly_download(b200_poly *p, uint64_t *host, size_t n_words) 
     return 0;
 }
 
+// Poly.Copy / CopyLvl (ring/poly.go:73-91): limbs 0..level of every polynomial of src into dst, device to device.
+// level < 0: all limbs.  Identical handles are skipped like the aliased limbs of the Go code (utils.Alias1D).
+extern "C" int b200_poly_copy(b200_poly *dst, const b200_poly *src, int level) {
+    CtxLock lk(dst ? dst->ctx : nullptr);
+    if (!dst || !src) return fail(B200_EINVAL, "b200_poly_copy: NULL argument");
+    if (dst->ctx != src->ctx) return fail(B200_ESHAPE, "b200_poly_copy: polynomials belong to different rings");
+    if (dst->batch != src->batch) return fail(B200_ESHAPE, "b200_poly_copy: batch sizes differ");
+    b200_ctx *ctx = dst->ctx;
+    if (level < 0) level = ctx->L - 1;
+    if (level >= ctx->L) return fail(B200_ESHAPE, "b200_poly_copy: level cannot be larger than max level");
+    if (dst->d == src->d) return 0;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const size_t pitch = (size_t)ctx->L * ctx->N * sizeof(u64);
+    CUDA_TRY(cudaMemcpy2DAsync(dst->d, pitch, src->d, pitch, (size_t)(level + 1) * ctx->N * sizeof(u64), dst->batch,
+                               cudaMemcpyDeviceToDevice, b200_cur_stream(ctx)));
+    return 0;
+}
+
 // ---- wire format ------------------------------------------------------------------
 // ring.Poly serialises as structs.Matrix[uint64] (ring/poly.go:97-160, utils/structs/matrix.go:57-128,
 // utils/structs/vector.go:43-100): u64 row count, then per limb a u64 length followed by the words, all

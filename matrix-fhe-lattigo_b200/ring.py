@@ -229,10 +229,27 @@ class Poly:
         return self.UnmarshalBinary(head + body, b)[1]
 
     def Copy(self, other):
-        self.set(other.get() if isinstance(other, Poly) else other)
+        """Poly.Copy (ring/poly.go:73-77); a device-to-device copy when `other` is a Poly, an upload otherwise."""
+        if isinstance(other, Poly):
+            check(lib().b200_poly_copy(self.h, other.h, -1))
+        else:
+            self.set(other)
+        return self
+
+    def CopyLvl(self, level, other):
+        """Poly.CopyLvl (ring/poly.go:81-91): limbs 0..level only."""
+        check(lib().b200_poly_copy(self.h, other.h, int(level)))
+        return self
 
     def CopyNew(self):
-        return Poly(self.ring, self.batch).set(self.get())
+        """Poly.CopyNew (ring/poly.go:63-70)."""
+        return Poly(self.ring, self.batch).Copy(self)
+
+    def Zero(self):
+        """Poly.Zero (ring/poly.go:56-60): every limb of every polynomial of the batch."""
+        r = self.ring
+        (r if r.level == r.MaxLevel() else r.AtLevel(r.MaxLevel())).Zero(self)
+        return self
 
     def Equal(self, other):
         return bool((self.get() == other.get()).all())

@@ -641,3 +641,25 @@ def test_div_by_last_modulus_coefficient_domain_and_many(shape):
         r.DivRoundByLastModulusMany(L, p0, p1)
     with pytest.raises(b200ring.B200Error):
         r.AtLevel(0).DivFloorByLastModulus(p0, p1)
+
+
+def test_poly_copy_copylvl_zero_on_device():
+    """Poly.Copy / CopyLvl / CopyNew / Zero (ring/poly.go:56-91) without a round trip through the host."""
+    N, moduli = 64, QI60[:3]
+    r = b200ring.NewRing(N, moduli)
+    a, b = rand_poly(7, 2, moduli, N), rand_poly(8, 2, moduli, N)
+    pa, pb = r.NewPoly(2).set(a), r.NewPoly(2).set(b)
+    pb.CopyLvl(1, pa)
+    got = pb.get()
+    assert (got[:, :2] == a[:, :2]).all() and (got[:, 2] == b[:, 2]).all()
+    pb.Copy(pa)
+    assert pb.Equal(pa) and (pa.CopyNew().get() == a).all()
+    pa.Copy(pa)
+    assert (pa.get() == a).all()
+    pb.Zero()
+    assert not pb.get().any()
+    r.AtLevel(0).NewPoly(2)
+    with pytest.raises(b200ring.B200Error):
+        pb.CopyLvl(3, pa)
+    with pytest.raises(b200ring.B200Error):
+        r.NewPoly(1).Copy(pa)
