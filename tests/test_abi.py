@@ -64,3 +64,30 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.replace("no oracle", ""), os.path.join(dirpath, f)
+
+
+def test_tools_never_import_the_oracle():
+    """tools/ are measurement helpers of the product path: like the package they must not execute anything under oracle/
+    (only tests/, smoke() and bench.py's CPU arms may)."""
+    for f in os.listdir(os.path.join(ROOT, "tools")):
+        if f.endswith(".py"):
+            text = open(os.path.join(ROOT, "tools", f)).read()
+            assert "from oracle" not in text and "import oracle" not in text, f
+
+
+def test_null_arguments_are_errors_not_crashes():
+    """Every entry point checks its handles before touching the device (the Go side would panic on a nil Poly)."""
+    import ctypes as C
+    L = capi.lib()
+    out = C.c_uint64(0)
+    assert L.b200_poly_copy(None, None, 0) == capi.B200_EINVAL
+    assert L.b200_vec_op(None, 0, None, None, None, 0, None) == capi.B200_EINVAL
+    assert L.b200_ntt(None, None, None, 0, 0) == capi.B200_EINVAL
+    assert L.b200_div_by_last_modulus(None, None, None, 1, 0) == capi.B200_EINVAL
+    assert L.b200_div_by_last_modulus_many(None, None, None, 1, 1, 0, 0) == capi.B200_EINVAL
+    assert L.b200_mul_by_vector_montgomery(None, None, None, None, 0, 0) == capi.B200_EINVAL
+    assert L.b200_mod_down(None, 0, 0, 0, None, None) == capi.B200_EINVAL
+    assert L.b200_find_3n_rns_primes(12, 60, 1, 10, None) == capi.B200_EINVAL
+    assert L.b200_order_mod(2, 7, None) == capi.B200_EINVAL
+    assert L.b200_prime_gen_next(None, 0, 1, C.byref(out)) == capi.B200_EINVAL
+    assert L.b200_last_error() != b""
