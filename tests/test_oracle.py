@@ -271,3 +271,27 @@ def test_div_by_last_modulus_many_matches_big_integer_division(kind):
             got = O.div_by_last_modulus_many(rings, moduli, p0_ntt, nb, round=rnd, ntt=True)
             for i in range(L - nb):
                 assert [int(v) for v in rings[i].INTT(got[i])] == [w % moduli[i] for w in want], (kind, rnd, nb, i, "ntt")
+
+
+def test_3n_small_prime_cases_of_the_reference():
+    """ring/ntt_3n_test.go:139-222 with the reference's own parameters (31-bit primes from Find3NRNSPrimes(N, 31, 1, 1<<16),
+    N = 12 and 24): round trip, eight Forward+Backward cycles, the zero and the all-ones vector; plus the definition
+    out[k] = f(omega^E[k]) (ntt_3n.go:99-108) for these small moduli."""
+    rng = np.random.default_rng(31)
+    for N in (12, 24):
+        q = O.find_3n_rns_primes(N, 31, 1)[0]
+        assert q.bit_length() == 32 and q % (3 * N) == 1
+        s = O.ThreeNSubRing(N, q)
+        ref = rng.integers(0, q, N, dtype=np.uint64)
+        cur = ref.copy()
+        for _ in range(8):
+            cur = s.INTT(s.NTT(cur))
+        assert (cur == ref).all()
+        for v in (np.zeros(N, dtype=np.uint64), np.ones(N, dtype=np.uint64)):
+            assert (s.INTT(s.NTT(v)) == v).all()
+        assert not s.NTT(np.zeros(N, dtype=np.uint64)).any()
+        E = [int(e) for e in O.totatives(3 * N)]
+        got = s.NTT(ref)
+        for k in range(N):
+            x = pow(s.omega, E[k], q)
+            assert int(got[k]) == sum(int(c) * pow(x, j, q) for j, c in enumerate(ref)) % q
