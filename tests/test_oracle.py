@@ -295,3 +295,32 @@ def test_3n_small_prime_cases_of_the_reference():
         for k in range(N):
             x = pow(s.omega, E[k], q)
             assert int(got[k]) == sum(int(c) * pow(x, j, q) for j, c in enumerate(ref)) % q
+
+
+def test_modular_reduction_random_words_property():
+    """ring/ring_test.go:534-670 (testModularReduction / testMForm) widened from the three edge values to seeded random 64-bit
+    words: every primitive of ring/modular_reduction.go equals big-integer arithmetic, for 61-bit, 60-bit 3N and 32-bit moduli."""
+    L = O.lib()
+    rng = np.random.default_rng(2024)
+    moduli = list(QI60[:4]) + list(O.find_3n_rns_primes(98304, 60, 2)) + list(O.find_3n_rns_primes(24, 31, 1)) + [0xffffffffffffffc5 >> 3 | 1]
+    moduli = [q for q in moduli if q % 2 == 1]
+    M = 1 << 64
+    for q in moduli[:7]:
+        brc = O.bred_constant(q)
+        qinv = L.ref_gen_mred_constant(q)
+        rinv = pow(M, -1, q)
+        xs = [int(v) for v in rng.integers(0, M, 200, dtype=np.uint64)]
+        ys = [int(v) for v in rng.integers(0, M, 200, dtype=np.uint64)]
+        for x, y in zip(xs, ys):
+            assert L.ref_bred_add(x, q, O._p(brc)) == x % q
+            lz = L.ref_bred_add_lazy(x, q, O._p(brc))
+            assert lz % q == x % q and lz < 2 * q
+            assert L.ref_mform(x, q, O._p(brc)) == (x << 64) % q
+            assert L.ref_imform(x, q, qinv) == x * rinv % q
+            assert L.ref_bred(x, y, q, O._p(brc)) == x * y % q
+            lz = L.ref_bred_lazy(x, y, q, O._p(brc))
+            assert lz % q == x * y % q and lz < 2 * q
+            yq = y % q                                  # MRed needs x*y < q*2^64
+            assert L.ref_mred(x, yq, q, qinv) == x * yq * rinv % q
+            lz = L.ref_mred_lazy(x, yq, q, qinv)
+            assert lz % q == x * yq * rinv % q and lz < 2 * q
