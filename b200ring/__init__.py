@@ -14,4 +14,5 @@ from .primes import (  # noqa: E402,F401
     IsPrime, Find3NRNSPrimes, Find3NFriendlyPrime, OrderMod, HasPrimitiveMthRoot, PrimitiveRoot, FindPrimitiveRootOfUnity,
     Find3NPrimitiveRoot, Derive3NRoots, Uint64Pow, NTTFriendlyPrimesGenerator, NewNTTFriendlyPrimesGenerator,
 )
+from . import scalar  # noqa: E402,F401
 from . import sharding  # noqa: E402,F401

@@ -11,6 +11,7 @@ import ctypes as C
 import numpy as np
 
 from . import capi
+from . import scalar as _scalar
 from .capi import B200Error, check, lib
 
 
@@ -311,8 +312,33 @@ class Ring:
     def BRedConstants(self):   # :249-257
         return [s.BRedConstant for s in self.SubRings[: self.level + 1]]
 
-    def NewRNSScalar(self):   # ring/scalar.go:11-13
+    # ring/scalar.go: RNSScalar helpers at this ring's level (host arithmetic, scalar.py)
+    def _chain(self):
+        return self._moduli[: self.level + 1]
+
+    def NewRNSScalar(self):
         return [0] * (self.level + 1)
+
+    def NewRNSScalarFromUInt64(self, v):
+        return _scalar.NewRNSScalarFromUInt64(self._chain(), v)
+
+    def NewRNSScalarFromBigint(self, v):
+        return _scalar.NewRNSScalarFromBigint(self._chain(), v)
+
+    def MFormRNSScalar(self, s1):
+        return _scalar.MFormRNSScalar(self._chain(), s1)
+
+    def NegRNSScalar(self, s1):
+        return _scalar.NegRNSScalar(self._chain(), s1)
+
+    def SubRNSScalar(self, s1, s2):
+        return _scalar.SubRNSScalar(self._chain(), s1, s2)
+
+    def MulRNSScalar(self, s1, s2):
+        return _scalar.MulRNSScalar(self._chain(), s1, s2)
+
+    def Inverse(self, a):
+        return _scalar.Inverse(self._chain(), a)
 
     def NewMonomialXi(self, i):
         """Ring.NewMonomialXi (ring/ring.go:408-430): the polynomial X^i (X^N = -1), coefficient domain."""
