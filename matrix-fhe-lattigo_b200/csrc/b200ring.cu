@@ -195,6 +195,78 @@ static void build_matrix(b200_ctx *ctx, int i, std::vector<tw_t> &fwd, std::vect
     misc[MISC_ZETA] = mk_tw(zeta, q);
 }
 
+// ---- fold arithmetic tables (solinas.cuh) ---------------------------------------------------------------
+// q = 2^k + c with the smallest |c|
+static void fold_shape(u64 q, int *k, long long *c) {
+    int b = 63;
+    while (b > 0 && !((q >> b) & 1)) --b;
+    const u64 lo = 1ULL << b;
+    if (b < 63 && q - lo > (lo << 1) - q) { *k = b + 1; *c = -(long long)((lo << 1) - q); }
+    else { *k = b; *c = (long long)(q - lo); }
+}
+static bool fold_split(long long v, int s, int *lo, int *hi) {
+    const long long h = (v + (1LL << (s - 1))) >> s;
+    if (h > 0x7fffffffLL || h < -0x80000000LL) return false;
+    *hi = (int)h;
+    *lo = (int)(v - h * (1LL << s));
+    return true;
+}
+// {w, w*2^32 mod q} as balanced residues split at bit k-32; false when a half does not fit 32 bits (a residue within
+// 2^(k-33) of +-q/2 for q > 2^k: about 2^-33 of all residues)
+static bool fold_entry(u64 w, u64 q, int k, stw_t *out) {
+    const u64 v = hm::mulmod(w, (1ULL << 32) % q, q);
+    const long long wb = w > q / 2 ? (long long)w - (long long)q : (long long)w;
+    const long long vb = v > q / 2 ? (long long)v - (long long)q : (long long)v;
+    return fold_split(wb, k - 32, &out->w_lo, &out->w_hi) && fold_split(vb, k - 32, &out->v_lo, &out->v_hi);
+}
+static bool fold_prime_ok(u64 q) {
+    int k; long long c;
+    fold_shape(q, &k, &c);
+    return k >= 50 && k <= 60 && (c < 0 ? -c : c) <= (1LL << 27);
+}
+// builds the device tables; leaves ctx->fold_ok false (and no tables) when the ring does not qualify
+static cudaError_t fold_setup(b200_ctx *ctx, const std::vector<tw_t> &fwd, const std::vector<tw_t> &inv, const std::vector<tw_t> &misc) {
+    const char *off = std::getenv("B200_NO_FOLD");
+    if (off && std::atoi(off)) return cudaSuccess;
+    const int L = ctx->L;
+    std::vector<SolConst> sol(L);
+    for (int i = 0; i < L; ++i) {
+        const u64 q = ctx->sub[i].q;
+        if (!fold_prime_ok(q)) return cudaSuccess;
+        int k; long long c;
+        fold_shape(q, &k, &c);
+        sol[i].q = q;
+        sol[i].bias = ((1ULL << 63) / q) * q;
+        sol[i].negc = (int)-c;
+        sol[i].two_s = 1u << (k - 32);
+        sol[i].sh = (unsigned)(k - 32);
+        sol[i].mask = (1u << (k - 32)) - 1;
+    }
+    auto conv = [&](const std::vector<tw_t> &src, size_t per_limb, std::vector<stw_t> &dst) {
+        dst.resize(src.size());
+        for (int i = 0; i < L; ++i) {
+            const u64 q = ctx->sub[i].q;
+            const int k = (int)sol[i].sh + 32;
+            for (size_t j = 0; j < per_limb; ++j)
+                if (!fold_entry(src[(size_t)i * per_limb + j].x, q, k, &dst[(size_t)i * per_limb + j])) return false;
+        }
+        return true;
+    };
+    std::vector<stw_t> f, v, m;
+    if (!conv(fwd, (size_t)ctx->N, f) || !conv(inv, (size_t)ctx->N, v) || !conv(misc, (size_t)MISC_COUNT, m)) return cudaSuccess;
+    auto up = [&](void **dst, const void *src, size_t bytes) -> cudaError_t {
+        cudaError_t e = cudaMalloc(dst, bytes);
+        if (e != cudaSuccess) return e;
+        return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+    };
+    cudaError_t e = up((void **)&ctx->d_sol, sol.data(), sizeof(SolConst) * L);
+    if (e == cudaSuccess) e = up((void **)&ctx->d_fwd_s, f.data(), sizeof(stw_t) * f.size());
+    if (e == cudaSuccess) e = up((void **)&ctx->d_inv_s, v.data(), sizeof(stw_t) * v.size());
+    if (e == cudaSuccess) e = up((void **)&ctx->d_misc_s, m.data(), sizeof(stw_t) * m.size());
+    if (e == cudaSuccess) ctx->fold_ok = true;
+    return e;
+}
+
 extern "C" int b200_ctx_create(int ring_type, int N, int L, const uint64_t *moduli, const uint64_t *roots,
                                int device, b200_ctx **out) {
     if (!out) return fail(B200_EINVAL, "b200_ctx_create: out is NULL");
@@ -316,6 +388,7 @@ extern "C" int b200_ctx_create(int ring_type, int N, int L, const uint64_t *modu
         for (int idx = 0; idx < N; ++idx) go2fast[pos[leaf[idx]]] = idx;
         e = up((void **)&ctx->d_go2fast, go2fast.data(), sizeof(int) * N);
     }
+    if (e == cudaSuccess) e = fold_setup(ctx, fwd, inv, misc);
     if (e != cudaSuccess) { b200_ctx_destroy(ctx); return b200_cuda_fail(e, "context table upload"); }
     int rc = big_tables_create(ctx);
     if (rc < 0) { b200_ctx_destroy(ctx); return rc; }
@@ -328,6 +401,7 @@ extern "C" void b200_ctx_destroy(b200_ctx *ctx) {
     cudaSetDevice(ctx->device);
     big_tables_destroy(ctx);
     cudaFree(ctx->d_consts); cudaFree(ctx->d_fwd); cudaFree(ctx->d_inv); cudaFree(ctx->d_misc);
+    cudaFree(ctx->d_sol); cudaFree(ctx->d_fwd_s); cudaFree(ctx->d_inv_s); cudaFree(ctx->d_misc_s);
     cudaFree(ctx->d_go2fast); cudaFree(ctx->d_scratch); cudaFree(ctx->d_ws); cudaFree(ctx->d_rescale); cudaFree(ctx->d_index);
     if (ctx->pipe.ready) {
         for (int i = 0; i < b200_ctx::HostPipe::NB; ++i) {

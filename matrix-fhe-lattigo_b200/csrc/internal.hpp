@@ -10,6 +10,7 @@
 
 #include "../../include/b200ring.h"
 #include "modarith.cuh"
+#include "solinas.cuh"
 
 // {w, ws}: a constant and its Shoup companion floor(w*2^64/q); one 128-bit load.
 typedef ulonglong2 tw_t;
@@ -40,6 +41,11 @@ struct b200_ctx {
     tw_t *d_fwd = nullptr;           // [L][N] forward twiddles (STANDARD: psi^brev(k); MATRIX: zetas)
     tw_t *d_inv = nullptr;           // [L][N] their inverses
     tw_t *d_misc = nullptr;          // [L][MISC_COUNT]
+    // fold arithmetic (solinas.cuh): set when every prime is 2^k + c with 50 <= k <= 60, |c| <= 2^27 and every twiddle
+    // splits into 32-bit halves; the tuned transforms then run on these tables instead of the Shoup ones
+    bool fold_ok = false;
+    SolConst *d_sol = nullptr;       // [L]
+    stw_t *d_fwd_s = nullptr, *d_inv_s = nullptr, *d_misc_s = nullptr;   // same indexing as d_fwd / d_inv / d_misc
     int *d_go2fast = nullptr;        // [N] MATRIX: reference slot k -> tree slot i
     u64 *d_scratch = nullptr;        // grown on demand (generic large-N path, polymul temporaries)
     size_t scratch_words = 0;

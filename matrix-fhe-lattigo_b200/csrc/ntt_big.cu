@@ -133,6 +133,9 @@ struct BigArgs {
     int in_dense, out_dense;   // the pointer is a dense [chunk][N] ring buffer indexed by blockIdx.y
     PeerOut peers;             // GATHER kernels only: mirrors of `out` on other GPUs
     u64 div_magic;             // ceil(2^64 / batch): unit / batch = hi64(unit * div_magic) for unit, batch < 2^31; 0 = batch is 1
+    // fold arithmetic (ntt_fold.cuh): per-prime constants and tables
+    const SolConst *sol;
+    const stw_t *fwd_s, *inv_s, *misc_s;
 };
 
 // word offsets of this CTA's unit in the input and output buffers, and its prime
@@ -980,6 +983,8 @@ k_cols_m3_g(const u64 *in, u64 *out, BigArgs a) {
     }
 }
 
+#include "ntt_fold.cuh"
+
 // ---- host side ---------------------------------------------------------------------------------------
 typedef void (*kern_t)(const u64 *, u64 *, BigArgs);
 
@@ -989,6 +994,10 @@ struct BigPlan {
     kern_t cols_fwd = nullptr, cols_inv = nullptr, cols_inv_gather = nullptr;
     int col_threads_fwd = 0, col_threads_inv = 0, col_threads_gather = 0;
     size_t chunk_units = 0;   // units per launch group so that a chunk's intermediate stays in L2
+    bool fold_rows = true, fold_cols = true;   // B200_FOLD_ROWS / B200_FOLD_COLS = 0 keep a pass on the Shoup kernels (A/B timing)
+    // fold-arithmetic column kernels of the shape (null: none, the row pass then folds what the Shoup column pass left)
+    kern_t cols_fwd_f = nullptr, cols_inv_f = nullptr, cols_inv_gather_f = nullptr;
+    int row_l0 = -1;                           // number of the row pass's first layer after cols_fwd_f
 };
 
 #define STD_G(L, A, B, C) case L: plan->cols_fwd = (kern_t)k_cols_std_g<L, A, B, C, false>; plan->cols_inv = (kern_t)k_cols_std_g<L, A, B, C, true>; \
@@ -1005,6 +1014,9 @@ bool pick_col_kernels(BigPlan *plan, bool matrix, int log, bool force_generic) {
             plan->cols_inv_gather = (kern_t)k_cols_inv_std16<B200_CW_GATHER, true>;
             plan->cw_fwd = B200_CW_STD_FWD; plan->cw_inv = B200_CW_STD_INV; plan->cw_gather = B200_CW_GATHER;
             plan->col_threads_fwd = B200_CW_STD_FWD * 32; plan->col_threads_inv = B200_CW_STD_INV * 32; plan->col_threads_gather = B200_CW_GATHER * 32;
+            plan->cols_fwd_f = (kern_t)k_cols_fwd_std16_f<B200_CW_STD_FWD>; plan->cols_inv_f = (kern_t)k_cols_inv_std16_f<B200_CW_STD_INV>;
+            plan->cols_inv_gather_f = (kern_t)k_cols_inv_std16_f<B200_CW_GATHER, true>;
+            plan->row_l0 = STD16_ROW_L0;
             return true;
         }
         switch (log) {
@@ -1017,6 +1029,9 @@ bool pick_col_kernels(BigPlan *plan, bool matrix, int log, bool force_generic) {
             plan->cols_inv_gather = (kern_t)k_cols_inv_m3_15<B200_CW_GATHER, true>;
             plan->cw_fwd = B200_CW_M3_FWD; plan->cw_inv = B200_CW_M3_INV; plan->cw_gather = B200_CW_GATHER;
             plan->col_threads_fwd = B200_CW_M3_FWD * 48; plan->col_threads_inv = B200_CW_M3_INV * 48; plan->col_threads_gather = B200_CW_GATHER * 48;
+            plan->cols_fwd_f = (kern_t)k_cols_fwd_m3_15_f<B200_CW_M3_FWD>; plan->cols_inv_f = (kern_t)k_cols_inv_m3_15_f<B200_CW_M3_INV>;
+            plan->cols_inv_gather_f = (kern_t)k_cols_inv_m3_15_f<B200_CW_GATHER, true>;
+            plan->row_l0 = M3_15_ROW_L0;
             return true;
         }
         switch (log) {
@@ -1056,6 +1071,8 @@ int big_tables_create(b200_ctx *ctx) {
     const bool generic = env_int("B200_GENERIC_COLS", 0) != 0;
     if (!matrix) plan->covered = ctx->logN >= 10 && ctx->logN <= 17 && pick_col_kernels(plan, false, ctx->logN - 8, generic);
     else plan->covered = ctx->b == 1 && ctx->a >= 10 && ctx->a <= 16 && pick_col_kernels(plan, true, ctx->a - 9, generic);
+    plan->fold_rows = env_int("B200_FOLD_ROWS", 1) != 0;
+    plan->fold_cols = env_int("B200_FOLD_COLS", 1) != 0;
     plan->vt = B200_VT_M3;   // 16-column tiles and 4-v row tiles were measured slower on B200 (fewer resident CTAs)
     int l2 = 0;
     cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, ctx->device);
@@ -1080,15 +1097,23 @@ int launch_ntt_big(b200_ctx *ctx, const u64 *in, u64 *out, Span sp, bool inverse
     const int N = ctx->N, R = N / 256, cw = inverse ? (gather ? plan->cw_gather : plan->cw_inv) : plan->cw_fwd, vt = plan->vt;
     BigArgs a{ctx->d_consts, ctx->d_fwd, ctx->d_inv, ctx->d_misc, N, R, matrix ? ctx->a - 9 : 0, sp, 0, flags, 0, 0};
     a.div_magic = unit_div_magic(sp);
-    const kern_t ck = inverse ? (gather ? plan->cols_inv_gather : plan->cols_inv) : plan->cols_fwd;
+    a.sol = ctx->d_sol; a.fwd_s = ctx->d_fwd_s; a.inv_s = ctx->d_inv_s; a.misc_s = ctx->d_misc_s;
+    const bool fold_rows = ctx->fold_ok && plan->fold_rows;
+    const bool fold_cols = fold_rows && plan->fold_cols && plan->cols_fwd_f;   // both passes on signed words
+    kern_t ck = inverse ? (gather ? plan->cols_inv_gather : plan->cols_inv) : plan->cols_fwd;
+    if (fold_cols) ck = inverse ? (gather ? plan->cols_inv_gather_f : plan->cols_inv_f) : plan->cols_fwd_f;
     const int col_threads = inverse ? (gather ? plan->col_threads_gather : plan->col_threads_inv) : plan->col_threads_fwd;
     kern_t rk;
     int row_warps;
     if (matrix) {
         rk = inverse ? (kern_t)k_rows_inv<true, B200_VT_M3> : (kern_t)k_rows_fwd<true, B200_VT_M3>;
+        if (fold_rows) rk = inverse ? (kern_t)k_rows_inv_f<true, B200_VT_M3, false> : (kern_t)k_rows_fwd_f<true, B200_VT_M3, -1>;
+        if (fold_cols) rk = inverse ? (kern_t)k_rows_inv_f<true, B200_VT_M3, true> : (kern_t)k_rows_fwd_f<true, B200_VT_M3, M3_15_ROW_L0>;
         row_warps = 6 * vt;
     } else {
         rk = inverse ? (kern_t)k_rows_inv<false, B200_VT_STD> : (kern_t)k_rows_fwd<false, B200_VT_STD>;
+        if (fold_rows) rk = inverse ? (kern_t)k_rows_inv_f<false, B200_VT_STD, false> : (kern_t)k_rows_fwd_f<false, B200_VT_STD, -1>;
+        if (fold_cols) rk = inverse ? (kern_t)k_rows_inv_f<false, B200_VT_STD, true> : (kern_t)k_rows_fwd_f<false, B200_VT_STD, STD16_ROW_L0>;
         row_warps = B200_VT_STD;
     }
     const int rows_total = R * cw;

@@ -1,0 +1,472 @@
+// ntt_fold.cuh -- the two-pass transforms of ntt_big.cu on the fold arithmetic of solinas.cuh (primes q = 2^k + c).
+// Included by ntt_big.cu inside its anonymous namespace: same tiling, same twiddle indexing (heap order), same slot
+// permutation; only the word type (signed, lazy), the butterflies and the reductions differ.  Where the folds sit and
+// which layers recentre by +-q is restated on intervals in tools/fold_ranges.py (tests/test_fold_ranges.py).
+#pragma once
+#include "solinas.cuh"
+
+#ifndef B200_TW_UNIFORM_HACK
+#define B200_TW_UNIFORM_HACK 0   // timing experiment only (wrong results): every lane of a warp uses the same twiddles
+#endif
+#if B200_TW_UNIFORM_HACK
+#define TWL(x) 0
+#else
+#define TWL(x) (x)
+#endif
+#ifndef B200_FOLD_WIDE_SHIFT
+#define B200_FOLD_WIDE_SHIFT 0   // 1: 2^s*B.lo through a sixth wide multiply instead of two shifts (measured slower, tools/solbench)
+#endif
+
+__device__ __forceinline__ s64 fmul(s64 y, const stw_t w, const SolConst &c) {
+#if B200_FOLD_WIDE_SHIFT
+    return sol_mul(y, w, c);
+#else
+    return sol_mul_sh(y, w, c);
+#endif
+}
+
+// forward (Cooley-Tukey) butterfly on signed words; KU / KV recentre the two outputs by -q / +q
+// (ku, kv are compile-time constants after unrolling)
+__device__ __forceinline__ void fbf_fwd(s64 &U, s64 &V, const stw_t w, const SolConst &c, bool ku, bool kv) {
+    const s64 t = fmul(V, w, c);
+    V = kv ? U - t + (s64)c.q : U - t;
+    U = ku ? U + t - (s64)c.q : U + t;
+}
+// The radix-2 layers of a transform are numbered 0, 1, .. across both passes, starting after the last fold of the
+// layers before them (the load, or the radix-3 layer of a 3N ring).  Every FWD_PERIOD layers all words are folded; in
+// between, the two outputs are recentred alternately (tools/fold_ranges.py FWD_PATTERN): the window of a folded word,
+// [0, 2^k], grows to +-5.6 * 2^k in five layers, inside the +-7.5 * 2^k a multiplied word may have.
+constexpr int FWD_PERIOD = 5;
+__host__ __device__ constexpr bool fwd_ku(int r) { return (r & 1) == 0; }
+__host__ __device__ constexpr bool fwd_kv(int r) { return (r & 1) == 1; }
+
+// LOGM forward layers of a register group whose first layer has number L0
+template <int LOGM, int L0>
+__device__ __forceinline__ void fwd_regs_f(s64 (&x)[1 << LOGM], unsigned P, const stw_t *__restrict__ tw, const SolConst &c) {
+#pragma unroll
+    for (int j = 0; j < LOGM; ++j) {
+        const int half = (1 << LOGM) >> (j + 1);
+        const int l = L0 + j, r = l % FWD_PERIOD;
+        if (l > 0 && r == 0) {
+#pragma unroll
+            for (int k = 0; k < (1 << LOGM); ++k) x[k] = sol_fold(x[k], c);
+        }
+#pragma unroll
+        for (int g = 0; g < (1 << j); ++g) {
+            const stw_t w = tw[(P << j) + g];
+#pragma unroll
+            for (int o = 0; o < half; ++o) fbf_fwd(x[g * 2 * half + o], x[g * 2 * half + o + half], w, c, fwd_ku(r), fwd_kv(r));
+        }
+    }
+}
+
+// inverse (Gentleman-Sande) butterfly: U' = U + V - KS*q (folded when FOLD), V' = (U - V)*w
+template <int KS, bool FOLD>
+__device__ __forceinline__ void fbf_inv(s64 &U, s64 &V, const stw_t w, const SolConst &c) {
+    const s64 d = U - V;
+    s64 s = KS ? U + V - (s64)c.q : U + V;
+    if (FOLD) s = sol_fold(s, c);
+    U = s;
+    V = fmul(d, w, c);
+}
+// LOGM inverse layers (innermost first); L0 = index of the group's first layer inside its pass.  The sums are
+// recentred by -q in odd layers and folded after them (tools/fold_ranges.py rows_inv).
+template <int LOGM, int L0, int JMIN = 0>
+__device__ __forceinline__ void inv_regs_f(s64 (&x)[1 << LOGM], unsigned P, const stw_t *__restrict__ tw, const SolConst &c) {
+#pragma unroll
+    for (int j = LOGM - 1; j >= JMIN; --j) {
+        const int half = (1 << LOGM) >> (j + 1);
+        const int l = L0 + (LOGM - 1 - j);
+#pragma unroll
+        for (int g = 0; g < (1 << j); ++g) {
+            const stw_t w = tw[(P << j) + g];
+#pragma unroll
+            for (int o = 0; o < half; ++o) {
+                if (l & 1) fbf_inv<1, true>(x[g * 2 * half + o], x[g * 2 * half + o + half], w, c);
+                else fbf_inv<0, false>(x[g * 2 * half + o], x[g * 2 * half + o + half], w, c);
+            }
+        }
+    }
+}
+
+// The 8 layers of one 256-word row held by one warp; same exchanges as row_fwd_core (ntt_big.cu).
+// in: c = k*32 + lane, words in (-2^(64-k)|c|, 2^k) (fold_u of anything)   out: c = lane*8 + k, |word| < 5.4 * 2^k
+template <int L0>
+__device__ __forceinline__ void row_fwd_core_f(s64 (&x)[8], u64 *buf, int lane, unsigned P1, const stw_t *__restrict__ tw, const SolConst &c) {
+    fwd_regs_f<3, L0>(x, P1, tw, c);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) buf[pad16(k * 32 + lane)] = (u64)x[k];
+    __syncwarp();
+    const int hi3 = lane & 7, lo2 = lane >> 3;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = (s64)buf[pad16(hi3 * 32 + k * 4 + lo2)];
+    fwd_regs_f<3, L0 + 3>(x, P1 * 8 + TWL(hi3), tw, c);
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) buf[pad16(hi3 * 32 + k * 4 + lo2)] = (u64)x[k];
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = (s64)buf[pad16(lane * 8 + k)];
+    s64 (&lo)[4] = *reinterpret_cast<s64 (*)[4]>(&x[0]);
+    s64 (&hi)[4] = *reinterpret_cast<s64 (*)[4]>(&x[4]);
+    fwd_regs_f<2, L0 + 6>(lo, P1 * 64 + TWL(lane * 2), tw, c);
+    fwd_regs_f<2, L0 + 6>(hi, P1 * 64 + TWL(lane * 2) + 1, tw, c);
+    __syncwarp();
+}
+// in: c = lane*8 + k, words in (-eps, 2^k + eps)   out: c = k*32 + lane; sums folded, products in (-0.6, 1.6) * 2^k
+__device__ __forceinline__ void row_inv_core_f(s64 (&x)[8], u64 *buf, int lane, unsigned P1, const stw_t *__restrict__ tw, const SolConst &c) {
+    {
+        s64 (&lo)[4] = *reinterpret_cast<s64 (*)[4]>(&x[0]);
+        s64 (&hi)[4] = *reinterpret_cast<s64 (*)[4]>(&x[4]);
+        inv_regs_f<2, 0>(lo, P1 * 64 + TWL(lane * 2), tw, c);
+        inv_regs_f<2, 0>(hi, P1 * 64 + TWL(lane * 2) + 1, tw, c);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) buf[pad16(lane * 8 + k)] = (u64)x[k];
+    __syncwarp();
+    const int hi3 = lane & 7, lo2 = lane >> 3;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = (s64)buf[pad16(hi3 * 32 + k * 4 + lo2)];
+    inv_regs_f<3, 2>(x, P1 * 8 + TWL(hi3), tw, c);
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) buf[pad16(hi3 * 32 + k * 4 + lo2)] = (u64)x[k];
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = (s64)buf[pad16(k * 32 + lane)];
+    inv_regs_f<3, 5>(x, P1, tw, c);
+}
+
+// L0 < 0: the column pass was a Shoup kernel (unsigned words below 8q): fold at the load, layers 0..7.
+// L0 >= 0: the column pass was a fold kernel that ran layers 0..L0-1 and left signed words.
+template <bool MATRIX, int VT, int L0>
+__global__ void __launch_bounds__((MATRIX ? 6 : 1) * VT * 32, MATRIX ? B200_MINB_ROWS_M3 * 2 / VT : B200_MINB_ROWS_STD_FWD * 4 / VT)
+k_rows_fwd_f(const u64 *in, u64 *out, BigArgs a) {
+    constexpr int RUN = 6 * VT;
+    extern __shared__ __align__(16) u64 sm[];
+    const UnitRef ur = unit_ref(a);
+    const int limb = ur.limb;
+    const SolConst sc = a.sol[limb];
+    const stw_t *__restrict__ tw = a.fwd_s + (size_t)limb * a.N;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int rowcode;
+    const int r = row_of<MATRIX, VT>(a, blockIdx.y, w, rowcode);
+    u64 *buf = sm + w * WROW;
+    const u64 *src = in + ur.in + (size_t)r * 256;
+    const unsigned P1 = (unsigned)(a.R + r);
+    s64 x[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = L0 >= 0 ? (s64)ldd(src + k * 32 + lane) : sol_fold_u(ldd(src + k * 32 + lane), sc);
+    row_fwd_core_f<(L0 >= 0 ? L0 : 0)>(x, buf, lane, P1, tw, sc);
+    u64 y[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) y[k] = sol_canon(x[k], sc);   // canonical also for NTTLazy (a subset of its range)
+    if (!MATRIX || (a.flags & B200_TREE_ORDER)) {
+        u64 *dst = out + ur.out + (size_t)r * 256 + lane * 8;
+        stg256(dst, y[0], y[1], y[2], y[3]);
+        stg256(dst + 4, y[4], y[5], y[6], y[7]);
+    } else {
+        __syncthreads();
+        const int rl = (int)rev_bits((unsigned)lane, 5);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sm[stage_row<RUN>((int)rev_bits((unsigned)k, 3) * 32 + rl) + rowcode] = y[k];
+        __syncthreads();
+        const size_t run = (size_t)6 << a.logU;
+        u64 *dst = out + ur.out + (size_t)blockIdx.y * RUN;
+        {
+            const int cr0 = threadIdx.x / RUN, rem = threadIdx.x - cr0 * RUN;
+            const u64 *sp = sm + stage_row<RUN>(cr0) + rem;
+            u64 *gp = dst + (size_t)cr0 * run + rem;
+            const size_t gstep = 32 * run;
+#pragma unroll
+            for (int i = 0; i < 8; ++i, gp += gstep) std_(gp, sp[i * 32 * (RUN + 1)]);
+        }
+    }
+}
+
+template <bool MATRIX, int VT, bool SIGNED_OUT>
+__global__ void __launch_bounds__((MATRIX ? 6 : 1) * VT * 32, MATRIX ? B200_MINB_ROWS_M3 * 2 / VT : B200_MINB_ROWS_STD_INV * 4 / VT)
+k_rows_inv_f(const u64 *in, u64 *out, BigArgs a) {
+    constexpr int RUN = 6 * VT;
+    extern __shared__ __align__(16) u64 sm[];
+    const UnitRef ur = unit_ref(a);
+    const int limb = ur.limb;
+    const SolConst sc = a.sol[limb];
+    const stw_t *__restrict__ tw = a.inv_s + (size_t)limb * a.N;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int rowcode;
+    const int r = row_of<MATRIX, VT>(a, blockIdx.y, w, rowcode);
+    u64 *buf = sm + w * WROW;
+    const unsigned P1 = (unsigned)(a.R + r);
+    u64 y[8];
+    if (!MATRIX || (a.flags & B200_TREE_ORDER)) {
+        const u64 *src = in + ur.in + (size_t)r * 256 + lane * 8;
+        ldg256(src, y[0], y[1], y[2], y[3]);
+        ldg256(src + 4, y[4], y[5], y[6], y[7]);
+    } else {
+        const size_t run = (size_t)6 << a.logU;
+        const u64 *src = in + ur.in + (size_t)blockIdx.y * RUN;
+        {
+            const int cr0 = threadIdx.x / RUN, rem = threadIdx.x - cr0 * RUN;
+            u64 v[8];
+            const u64 *gp = src + (size_t)cr0 * run + rem;
+            const size_t gstep = 32 * run;
+#pragma unroll
+            for (int i = 0; i < 8; ++i, gp += gstep) v[i] = ldd(gp);
+            u64 *sp = sm + stage_row<RUN>(cr0) + rem;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) sp[i * 32 * (RUN + 1)] = v[i];
+        }
+        __syncthreads();
+        const int rl = (int)rev_bits((unsigned)lane, 5);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) y[k] = sm[stage_row<RUN>((int)rev_bits((unsigned)k, 3) * 32 + rl) + rowcode];
+        __syncthreads();
+    }
+    s64 x[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = sol_fold_u(y[k], sc);      // any 64-bit input word
+    row_inv_core_f(x, buf, lane, P1, tw, sc);
+    u64 *dst = out + ur.out + (size_t)r * 256;
+    if (SIGNED_OUT) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) std_(dst + k * 32 + lane, (u64)x[k]);
+    } else {   // the Shoup column pass takes unsigned words below 4q: everything is above -q here
+#pragma unroll
+        for (int k = 0; k < 8; ++k) std_(dst + k * 32 + lane, (u64)(x[k] + (s64)sc.q));
+    }
+}
+
+// ====================================================================================================
+// column pass on the fold arithmetic: the hand-tuned headline shapes (same tiling as k_cols_*_m3_15 / k_cols_*_std16).
+// Inputs of the forward kernels are the caller's words, taken as they are: they must be below 4q (the reference's
+// transforms take words below 2q at most, ring/ntt.go:155-171).
+// ====================================================================================================
+
+// MATRIX, a = 15.  G1: cyclotomic layer, radix-3 layer, fold, radix-2 layer 0; G2: layers 1..3; G3: layers 4, 5 (all
+// words folded before layer 5); the row pass continues with layer 6.
+template <int CW>
+__global__ void __launch_bounds__(CW * 48, B200_MINB_COLS_M3_FWD * 8 / CW)
+k_cols_fwd_m3_15_f(const u64 *in, u64 *out, BigArgs a) {
+    extern __shared__ __align__(16) u64 sm[];
+    const UnitRef ur = unit_ref<true>(a);
+    const int limb = ur.limb;
+    const size_t ibase = ur.in + (size_t)blockIdx.x * CW, obase = ur.out + (size_t)blockIdx.x * CW;
+    const SolConst sc = a.sol[limb];
+    const s64 q = (s64)sc.q;
+    const stw_t *__restrict__ tw = a.fwd_s + (size_t)limb * a.N;
+    const stw_t om = a.misc_s[limb * MISC_COUNT + MISC_OMEGA3];
+    const int t = threadIdx.x, c = t % CW, g = t / CW;   // g in [0,48)
+    if (g < 32) {   // G1: rows hd*64 + b*32 + g
+        s64 x[6][2];
+#pragma unroll
+        for (int hd = 0; hd < 6; ++hd)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) x[hd][b] = (s64)ldd(in + ibase + (size_t)(hd * 64 + b * 32 + g) * 256 + c);
+        const stw_t zeta = tw[1];
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {   // cyclotomic layer: [0, 4) -> lo' in (-1.6, 4.6), hi' in (-3.6, 6.6)  (units of 2^k)
+                const s64 lo = x[d][b], hi = x[d + 3][b];
+                const s64 tt = fmul(hi, zeta, sc);
+                x[d][b] = lo + tt - q;
+                x[d + 3][b] = lo + hi - tt - 2 * q;
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {   // radix-3 layer, outputs folded
+                const stw_t z1 = tw[2 + 2 * h], z2 = tw[3 + 2 * h];
+                const s64 b0 = sol_fold(x[3 * h][b], sc);
+                const s64 t1 = fmul(x[3 * h + 1][b], z1, sc);
+                const s64 t2 = fmul(x[3 * h + 2][b], z2, sc);
+                const s64 t3 = fmul(t1 - t2, om, sc);
+                x[3 * h][b] = sol_fold(b0 + t1 + t2, sc);
+                x[3 * h + 1][b] = sol_fold(b0 - t2 + t3, sc);
+                x[3 * h + 2][b] = sol_fold(b0 - t1 - t3, sc);
+            }
+        }
+#pragma unroll
+        for (int hd = 0; hd < 6; ++hd) {
+            fbf_fwd(x[hd][0], x[hd][1], tw[6 + hd], sc, fwd_ku(0), fwd_kv(0));   // radix-2 layer 0 of block hd
+#pragma unroll
+            for (int b = 0; b < 2; ++b) sm[pc((hd * 64 + b * 32 + g) * CW + c)] = (u64)x[hd][b];
+        }
+    }
+    __syncthreads();
+    s64 x[8];
+    {   // G2: g = top*4 + lo2, top = hd*2 + u5 in [0,12); rows top*32 + k*4 + lo2
+        const int lo2 = g & 3, top = g >> 2;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = (s64)sm[pc((top * 32 + k * 4 + lo2) * CW + c)];
+        fwd_regs_f<3, 1>(x, 12u + top, tw, sc);
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sm[pc((top * 32 + k * 4 + lo2) * CW + c)] = (u64)x[k];
+    }
+    __syncthreads();
+    {   // G3: rows g*8 + k; sub-transform roots at depth 4: 96 + g*2 + {0,1}
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = (s64)sm[pc((g * 8 + k) * CW + c)];
+        s64 (&lo)[4] = *reinterpret_cast<s64 (*)[4]>(&x[0]);
+        s64 (&hi)[4] = *reinterpret_cast<s64 (*)[4]>(&x[4]);
+        fwd_regs_f<2, 4>(lo, 96u + g * 2, tw, sc);
+        fwd_regs_f<2, 4>(hi, 96u + g * 2 + 1, tw, sc);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) std_(out + obase + (size_t)(g * 8 + k) * 256 + c, (u64)x[k]);
+    }
+}
+constexpr int M3_15_ROW_L0 = 6;   // the row pass of this shape starts with layer 6
+
+// inverse: the row pass ran layers 0..7 and left signed words (sums folded, products in (-0.6, 1.6)); layers 8..13 here,
+// then the inverse radix-3 layer and the inverse cyclotomic layer with the 2/N scaling, canonical output
+template <int CW, bool GATHER = false>
+__global__ void __launch_bounds__(CW * 48, B200_MINB_COLS_M3_INV * 8 / CW)
+k_cols_inv_m3_15_f(const u64 *in, u64 *out, BigArgs a) {
+    extern __shared__ __align__(16) u64 sm[];
+    const UnitRef ur = unit_ref<true>(a);
+    const int limb = ur.limb;
+    const size_t ibase = ur.in + (size_t)blockIdx.x * CW, obase = ur.out + (size_t)blockIdx.x * CW;
+    const SolConst sc = a.sol[limb];
+    const stw_t *__restrict__ tw = a.inv_s + (size_t)limb * a.N;
+    const stw_t *mc = a.misc_s + limb * MISC_COUNT;
+    const int t = threadIdx.x, c = t % CW, g = t / CW;
+    {
+        s64 x[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = (s64)ldd(in + ibase + (size_t)(g * 8 + k) * 256 + c);
+        s64 (&lo)[4] = *reinterpret_cast<s64 (*)[4]>(&x[0]);
+        s64 (&hi)[4] = *reinterpret_cast<s64 (*)[4]>(&x[4]);
+        inv_regs_f<2, 8>(lo, 96u + g * 2, tw, sc);
+        inv_regs_f<2, 8>(hi, 96u + g * 2 + 1, tw, sc);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sm[pc((g * 8 + k) * CW + c)] = (u64)x[k];
+        __syncthreads();
+        const int lo2 = g & 3, top = g >> 2;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = (s64)sm[pc((top * 32 + k * 4 + lo2) * CW + c)];
+        inv_regs_f<3, 10>(x, 12u + top, tw, sc);
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sm[pc((top * 32 + k * 4 + lo2) * CW + c)] = (u64)x[k];
+    }
+    __syncthreads();
+    if (g < 32) {
+        const stw_t om = mc[MISC_OMEGA3], k1 = mc[MISC_K1], k2 = mc[MISC_K2], zeta = mc[MISC_ZETA];
+        s64 x[6][2];
+#pragma unroll
+        for (int hd = 0; hd < 6; ++hd) {
+#pragma unroll
+            for (int b = 0; b < 2; ++b) x[hd][b] = (s64)sm[pc((hd * 64 + b * 32 + g) * CW + c)];
+            fbf_inv<1, true>(x[hd][0], x[hd][1], tw[6 + hd], sc);   // layer 13
+        }
+        u64 y[6][2];
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {   // inverse radix-3 (factor 3 deferred): words in (-0.6, 1.6) -> x0 in (-1.8, 4.8), products
+                const stw_t z1 = tw[2 + 2 * h], z2 = tw[3 + 2 * h];
+                const s64 y0 = x[3 * h][b], y1 = x[3 * h + 1][b], y2 = x[3 * h + 2][b];
+                const s64 s = fmul(y1 - y2, om, sc);
+                x[3 * h][b] = y0 + y1 + y2;
+                x[3 * h + 1][b] = fmul(y0 - y1 - s, z1, sc);
+                x[3 * h + 2][b] = fmul(y0 - y2 + s, z2, sc);
+            }
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {   // inverse cyclotomic layer with the 2/N scaling: |lo - hi| < 6.6
+                const s64 lo = x[d][b], hi = x[d + 3][b];
+                const s64 hh = fmul(lo - hi, k1, sc);
+                const s64 ll = fmul(lo, k2, sc) - fmul(hh, zeta, sc);
+                y[d][b] = sol_canon(ll, sc);
+                y[d + 3][b] = sol_canon(hh, sc);
+            }
+        }
+#pragma unroll
+        for (int hd = 0; hd < 6; ++hd)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) store_out<GATHER>(a.peers, out, obase + (size_t)(hd * 64 + b * 32 + g) * 256 + c, y[hd][b]);
+    }
+}
+
+// STANDARD, log2(N) = 16: layers 0..7 on the row bits; the row pass continues with layer 8
+template <int CW>
+__global__ void __launch_bounds__(CW * 32, B200_MINB_COLS_STD * 8 / CW)
+k_cols_fwd_std16_f(const u64 *in, u64 *out, BigArgs a) {
+    extern __shared__ __align__(16) u64 sm[];
+    const UnitRef ur = unit_ref<true>(a);
+    const int limb = ur.limb;
+    const size_t ibase = ur.in + (size_t)blockIdx.x * CW, obase = ur.out + (size_t)blockIdx.x * CW;
+    const SolConst sc = a.sol[limb];
+    const stw_t *__restrict__ tw = a.fwd_s + (size_t)limb * a.N;
+    const int t = threadIdx.x, c = t % CW, g = t / CW;   // g in [0,32)
+    s64 x[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = (s64)ldd(in + ibase + (size_t)(k * 32 + g) * 256 + c);      // rows k*32 + g
+    fwd_regs_f<3, 0>(x, 1u, tw, sc);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sm[pc((k * 32 + g) * CW + c)] = (u64)x[k];
+    __syncthreads();
+    const int lo2 = g & 3, hi3 = g >> 2;                                                 // rows hi3*32 + k*4 + lo2
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = (s64)sm[pc((hi3 * 32 + k * 4 + lo2) * CW + c)];
+    fwd_regs_f<3, 3>(x, 8u + hi3, tw, sc);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sm[pc((hi3 * 32 + k * 4 + lo2) * CW + c)] = (u64)x[k];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = (s64)sm[pc((g * 8 + k) * CW + c)];                     // rows g*8 + k
+    {
+        s64 (&lo)[4] = *reinterpret_cast<s64 (*)[4]>(&x[0]);
+        s64 (&hi)[4] = *reinterpret_cast<s64 (*)[4]>(&x[4]);
+        fwd_regs_f<2, 6>(lo, 64u + g * 2, tw, sc);
+        fwd_regs_f<2, 6>(hi, 64u + g * 2 + 1, tw, sc);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) std_(out + obase + (size_t)(g * 8 + k) * 256 + c, (u64)x[k]);
+}
+constexpr int STD16_ROW_L0 = 8;
+
+template <int CW, bool GATHER = false>
+__global__ void __launch_bounds__(CW * 32, B200_MINB_COLS_STD * 8 / CW)
+k_cols_inv_std16_f(const u64 *in, u64 *out, BigArgs a) {
+    extern __shared__ __align__(16) u64 sm[];
+    const UnitRef ur = unit_ref<true>(a);
+    const int limb = ur.limb;
+    const size_t ibase = ur.in + (size_t)blockIdx.x * CW, obase = ur.out + (size_t)blockIdx.x * CW;
+    const SolConst sc = a.sol[limb];
+    const stw_t *__restrict__ tw = a.inv_s + (size_t)limb * a.N;
+    const stw_t ninv = a.misc_s[limb * MISC_COUNT + MISC_NINV], ninv_w1 = a.misc_s[limb * MISC_COUNT + MISC_NINV_W1];
+    const int t = threadIdx.x, c = t % CW, g = t / CW;
+    s64 x[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = (s64)ldd(in + ibase + (size_t)(g * 8 + k) * 256 + c);
+    {
+        s64 (&lo)[4] = *reinterpret_cast<s64 (*)[4]>(&x[0]);
+        s64 (&hi)[4] = *reinterpret_cast<s64 (*)[4]>(&x[4]);
+        inv_regs_f<2, 8>(lo, 64u + g * 2, tw, sc);
+        inv_regs_f<2, 8>(hi, 64u + g * 2 + 1, tw, sc);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sm[pc((g * 8 + k) * CW + c)] = (u64)x[k];
+    __syncthreads();
+    const int lo2 = g & 3, hi3 = g >> 2;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = (s64)sm[pc((hi3 * 32 + k * 4 + lo2) * CW + c)];
+    inv_regs_f<3, 10>(x, 8u + hi3, tw, sc);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sm[pc((hi3 * 32 + k * 4 + lo2) * CW + c)] = (u64)x[k];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = (s64)sm[pc((k * 32 + g) * CW + c)];
+    inv_regs_f<3, 13, 1>(x, 1u, tw, sc);   // layers 13, 14
+    u64 y[8];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {   // layer 15 carries N^-1: |U + V| < 6.4
+        const s64 U = x[o], V = x[o + 4];
+        y[o] = sol_canon(fmul(U + V, ninv, sc), sc);
+        y[o + 4] = sol_canon(fmul(U - V, ninv_w1, sc), sc);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) store_out<GATHER>(a.peers, out, obase + (size_t)(k * 32 + g) * 256 + c, y[k]);
+}

@@ -11,6 +11,37 @@
 #include "../matrix-fhe-lattigo_b200/csrc/modarith.cuh"
 #include "../matrix-fhe-lattigo_b200/csrc/solinas.cuh"
 
+
+// ---- design A (measured, not adopted): 31-bit split of y, twiddle halves of 32 bits, shift/mask fold.  The carry of the
+// low product into the high one and the shift/mask cost more than design B's sixth multiply (profiles/r02_solbench.txt).
+struct SolAConst { u64 q; u64 bias; int negc; unsigned sh; unsigned mask; unsigned pad_; };
+__device__ __forceinline__ unsigned funnel_r(unsigned lo, unsigned hi, unsigned s) {
+    unsigned r; asm("shf.r.clamp.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(lo), "r"(hi), "r"(s)); return r;
+}
+__device__ __forceinline__ s64 sola_mul(s64 y, const stw_t w, const SolAConst &c) {
+    const unsigned ylo = (unsigned)y, yhi = (unsigned)((u64)y >> 32);
+    const int y0 = (int)(ylo & 0x7fffffffu);
+    const int y1 = (int)funnel_r(ylo, yhi, 31);
+    s64 A = madwide_s32(y0, w.w_lo, (s64)c.bias);
+    A = madwide_s32(y1, w.v_lo, A);
+    s64 B = madwide_s32(y0, w.w_hi, (s64)((u64)A >> 32));
+    B = madwide_s32(y1, w.v_hi, B);
+    const unsigned blo = (unsigned)B, bhi = (unsigned)((u64)B >> 32);
+    const int shh = (int)funnel_r(blo, bhi, c.sh);
+    return madwide_s32(shh, c.negc, pack64((unsigned)A, blo & c.mask));
+}
+__device__ __forceinline__ s64 sola_fold(s64 v, const SolAConst &c) {
+    const unsigned lo = (unsigned)v, hi = (unsigned)((u64)v >> 32);
+    const int h = (int)hi >> c.sh;
+    return madwide_s32(h, c.negc, pack64(lo, hi & c.mask));
+}
+__device__ __forceinline__ u64 sola_canon(s64 v, const SolAConst &c) {
+    s64 r = sola_fold(v, c);
+    if (r < 0) r += (s64)c.q;
+    if (r >= (s64)c.q) r -= (s64)c.q;
+    return (u64)r;
+}
+
 typedef ulonglong2 tw_t;
 struct QC { u64 q, twoq, fourq, nq, nfourq; };
 
@@ -33,6 +64,23 @@ __device__ __forceinline__ void bf_sol(s64 &U, s64 &V, const stw_t w, const SolC
     V = KV ? U - t + (s64)c.q : U - t;
     U = KU ? U + t - (s64)c.q : U + t;
 }
+template <bool KU, bool KV>
+__device__ __forceinline__ void bf_sol_sh(s64 &U, s64 &V, const stw_t w, const SolConst &c) {
+    const s64 t = sol_mul_sh(V, w, c);
+    V = KV ? U - t + (s64)c.q : U - t;
+    U = KU ? U + t - (s64)c.q : U + t;
+}
+// all adds with three inputs: kz is a zero the compiler cannot see (keeps add-with-carry off the multiply pipe)
+template <int KU, int KV>
+__device__ __forceinline__ void bf_sol_3(s64 &U, s64 &V, const stw_t w, const SolConst &c, s64 kz) {
+    const s64 t = sol_mul_sh(V, w, c);
+    V = U - t + (KV ? (s64)c.q : kz);
+    U = U + t + (KU ? -(s64)c.q : kz);
+}
+__device__ __forceinline__ s64 sol_fold_3(s64 v, const SolConst &c, s64 kz) {
+    const unsigned lo = (unsigned)v, hi = (unsigned)((u64)v >> 32);
+    return mulwide_s32((int)hi >> c.sh, c.negc) + pack64(lo, hi & c.mask) + kz;
+}
 // inverse (Gentleman-Sande) butterfly: U' = U + V, V' = (U - V)*w
 __device__ __forceinline__ void bf_sol_inv(s64 &U, s64 &V, const stw_t w, const SolConst &c) {
     const s64 d = U - V;
@@ -48,7 +96,7 @@ __device__ __forceinline__ void bf_sol_inv(s64 &U, s64 &V, const stw_t w, const 
 //      4: design B (twiddles split at bit k-32), fold at the start of every 3-layer group, recentred with +-q
 //      5: design B without any fold (timing only: the words overflow)
 template <int MODE, int LAYERS>
-__global__ void __launch_bounds__(128, 8) k_bf(u64 *data, const tw_t *twi, const stw_t *twa, const stw_t *tws, QC c, SolAConst sa, SolConst sc, int iters, long long *clk) {
+__global__ void __launch_bounds__(128, 8) k_bf(u64 *data, const tw_t *twi, const stw_t *twa, const stw_t *tws, QC c, SolAConst sa, SolConst sc, int iters, long long *clk, s64 kz) {
     u64 x[8];
     s64 z[8];
     u64 *p = data + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
@@ -69,6 +117,14 @@ __global__ void __launch_bounds__(128, 8) k_bf(u64 *data, const tw_t *twi, const
 #pragma unroll
                 for (int k = 0; k < 8; ++k) z[k] = sola_fold(z[k], sa);
             }
+            if (MODE == 9 && (l & 3) == 0) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) z[k] = sol_fold_3(z[k], sc, kz);
+            }
+            if ((MODE == 6 || MODE == 7) && (l & 3) == 0) {   // fold every 4 layers
+#pragma unroll
+                for (int k = 0; k < 8; ++k) z[k] = sol_fold(z[k], sc);
+            }
             if (MODE == 4 && j == 0) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) z[k] = sol_fold(z[k], sc);
@@ -88,6 +144,15 @@ __global__ void __launch_bounds__(128, 8) k_bf(u64 *data, const tw_t *twi, const
                         z[i0] = sol_fold(z[i0], sc);
                     } else if (MODE == 4) {   // windows (in q): [0,1] -> +-1.48 -> +-2.45 -> +-3.43
                         if (j == 0) bf_sol<false, true>(z[i0], z[i1], tws[ti], sc); else bf_sol<true, false>(z[i0], z[i1], tws[ti], sc);
+                    } else if (MODE == 6) {   // recentring pattern of a 4-layer block: (0,1) (1,0) (1,0) (0,0)
+                        const int r = l & 3;
+                        if (r == 0) bf_sol<false, true>(z[i0], z[i1], tws[ti], sc); else if (r == 3) bf_sol<false, false>(z[i0], z[i1], tws[ti], sc); else bf_sol<true, false>(z[i0], z[i1], tws[ti], sc);
+                    } else if (MODE == 9) {
+                        const int r = l & 3;
+                        if (r == 0) bf_sol_3<0, 1>(z[i0], z[i1], tws[ti], sc, kz); else if (r == 3) bf_sol_3<0, 0>(z[i0], z[i1], tws[ti], sc, kz); else bf_sol_3<1, 0>(z[i0], z[i1], tws[ti], sc, kz);
+                    } else if (MODE == 7) {
+                        const int r = l & 3;
+                        if (r == 0) bf_sol_sh<false, true>(z[i0], z[i1], tws[ti], sc); else if (r == 3) bf_sol_sh<false, false>(z[i0], z[i1], tws[ti], sc); else bf_sol_sh<true, false>(z[i0], z[i1], tws[ti], sc);
                     } else {
                         bf_sol<false, false>(z[i0], z[i1], tws[ti], sc);
                     }
@@ -111,16 +176,18 @@ template <int MODE, int LAYERS>
 double bench(const char *name, int sms, u64 *d_data, const std::vector<u64> &host_in, const tw_t *twi, const stw_t *twa, const stw_t *tws, QC c,
              SolAConst sa, SolConst sc, std::vector<u64> *result) {
     const int iters = 64;
+    const char *only = getenv("SOL_ONLY");
+    if (only && atoi(only) != MODE * 10 + LAYERS) { result->clear(); return 0; }
     int occ = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bf<MODE, LAYERS>, 128, 0);
     const int blocks = sms * occ * 4;
     long long *clk; cudaMalloc(&clk, 8 * blocks);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     float best = 1e30f;
-    for (int r = 0; r < 5; ++r) {
+    for (int r = 0; r < (only ? 1 : 5); ++r) {
         cudaMemcpy(d_data, host_in.data(), host_in.size() * 8, cudaMemcpyHostToDevice);
         cudaEventRecord(e0);
-        k_bf<MODE, LAYERS><<<blocks, 128>>>(d_data, twi, twa, tws, c, sa, sc, iters, clk);
+        k_bf<MODE, LAYERS><<<blocks, 128>>>(d_data, twi, twa, tws, c, sa, sc, iters, clk, getenv("SOL_KZ") ? atoll(getenv("SOL_KZ")) : 0);
         cudaEventRecord(e1); cudaEventSynchronize(e1);
         float ms; cudaEventElapsedTime(&ms, e0, e1);
         if (ms < best) best = ms;
@@ -161,6 +228,7 @@ int main(int argc, char **argv) {
     if (((u64)1 << 63) - sa.bias > q / 2) sa.bias += q;
     SolConst sc{};
     sc.q = q; sc.negc = (int)-cc; sc.sh = (unsigned)(k - 32); sc.mask = (1u << (k - 32)) - 1; sc.two_s = 1u << (k - 32);
+    sc.bias = (u64)(((unsigned __int128)1 << 63) / q) * q;
     std::vector<tw_t> ti(TWN); std::vector<stw_t> ta(TWN), ts(TWN);
     u64 s = 0x9E3779B97F4A7C15ULL;
     auto rnd = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return s; };
@@ -198,8 +266,18 @@ int main(int argc, char **argv) {
       bench<4, 6>("design B, fold every 3 layers, 6 layers/iter", sms, d, in, d_ti, d_ta, d_ts, c, sa, sc, &ry);
       bad = 0; for (size_t i = 0; i < ry.size() && i < r3.size(); ++i) bad += ry[i] != r3[i];
       printf("   parity vs Shoup/Harvey: %zu mismatches\n", bad);
+      { std::vector<u64> r8, s8, t8;
+        bench<0, 8>("Shoup/Harvey, 8 layers per iteration", sms, d, in, d_ti, d_ta, d_ts, c, sa, sc, &r8);
+        bench<6, 8>("design B, fold every 4 layers, wide shifter", sms, d, in, d_ti, d_ta, d_ts, c, sa, sc, &s8);
+        bench<7, 8>("design B, fold every 4 layers, ALU shifter", sms, d, in, d_ti, d_ta, d_ts, c, sa, sc, &t8);
+        { std::vector<u64> u8; bench<9, 8>("design B, ALU shifter, every add with 3 inputs", sms, d, in, d_ti, d_ta, d_ts, c, sa, sc, &u8);
+          size_t b3 = 0; for (size_t i = 0; i < r8.size() && i < u8.size(); ++i) b3 += r8[i] != u8[i];
+          printf("   parity vs Shoup/Harvey: %zu mismatches\n", b3); }
+        size_t b1 = 0, b2 = 0; for (size_t i = 0; i < r8.size() && i < s8.size() && i < t8.size(); ++i) { b1 += r8[i] != s8[i]; b2 += r8[i] != t8[i]; }
+        printf("   parity vs Shoup/Harvey: %zu and %zu mismatches\n", b1, b2); }
       bench<5, 6>("design B, no fold (timing only)", sms, d, in, d_ti, d_ta, d_ts, c, sa, sc, &rx);
       bench<3, 6>("design B inverse butterfly, sums folded every layer", sms, d, in, d_ti, d_ta, d_ts, c, sa, sc, &rx); }
+    if (getenv("SOL_ONLY")) return 0;
     size_t n = std::min(r0.size(), std::min(r1.size(), r2.size())), bad1 = 0, bad2 = 0;
     for (size_t i = 0; i < n; ++i) { bad1 += r0[i] != r1[i]; bad2 += r0[i] != r2[i]; }
     printf("parity vs Shoup/Harvey over %zu words: fold %zu mismatches, recentred %zu mismatches\n", n, bad1, bad2);
