@@ -193,6 +193,7 @@ static void build_matrix(b200_ctx *ctx, int i, std::vector<tw_t> &fwd, std::vect
     misc[MISC_K1] = mk_tw(hm::mulmod(c, two_over_n, q), q);
     misc[MISC_K2] = mk_tw(two_over_n, q);
     misc[MISC_ZETA] = mk_tw(zeta, q);
+    misc[MISC_K4] = mk_tw(hm::invmod_prime((u64)N % q, q), q);
 }
 
 // ---- fold arithmetic tables (solinas.cuh) ---------------------------------------------------------------

@@ -28,6 +28,8 @@ struct SubRingHost {
 enum { MISC_OMEGA3 = 0, MISC_K1 = 1, MISC_K2 = 2, MISC_ZETA = 3, MISC_NINV = 4, MISC_NINV_W1 = 5, MISC_COUNT = 8 };
 // conjugate-invariant rings: the fourth roots of unity of the folding layer (RootsForward[1], RootsBackward[1])
 enum { MISC_CI_F = 6, MISC_CI_FINV = 7 };
+// MATRIX rings: N^-1 (the inverse cyclotomic layer in its two-product form, ntt_fold.cuh) shares the slot of MISC_NINV
+enum { MISC_K4 = 4 };
 
 struct b200_ctx {
     int ring_type = 0, N = 0, L = 0, device = 0;

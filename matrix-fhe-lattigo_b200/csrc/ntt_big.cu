@@ -986,6 +986,11 @@ k_cols_m3_g(const u64 *in, u64 *out, BigArgs a) {
 #include "ntt_fold.cuh"
 
 // ---- host side ---------------------------------------------------------------------------------------
+int env_int(const char *name, int dflt) {
+    const char *v = std::getenv(name);
+    return v ? std::atoi(v) : dflt;
+}
+
 typedef void (*kern_t)(const u64 *, u64 *, BigArgs);
 
 struct BigPlan {
@@ -998,6 +1003,7 @@ struct BigPlan {
     // fold-arithmetic column kernels of the shape (null: none, the row pass then folds what the Shoup column pass left)
     kern_t cols_fwd_f = nullptr, cols_inv_f = nullptr, cols_inv_gather_f = nullptr;
     int row_l0 = -1;                           // number of the row pass's first layer after cols_fwd_f
+    bool bal = false;                          // fold column kernels are the balanced form: CW*16 threads, unpadded tile
 };
 
 #define STD_G(L, A, B, C) case L: plan->cols_fwd = (kern_t)k_cols_std_g<L, A, B, C, false>; plan->cols_inv = (kern_t)k_cols_std_g<L, A, B, C, true>; \
@@ -1032,6 +1038,11 @@ bool pick_col_kernels(BigPlan *plan, bool matrix, int log, bool force_generic) {
             plan->cols_fwd_f = (kern_t)k_cols_fwd_m3_15_f<B200_CW_M3_FWD>; plan->cols_inv_f = (kern_t)k_cols_inv_m3_15_f<B200_CW_M3_INV>;
             plan->cols_inv_gather_f = (kern_t)k_cols_inv_m3_15_f<B200_CW_GATHER, true>;
             plan->row_l0 = M3_15_ROW_L0;
+            if (env_int("B200_COLS_BAL", 1)) {   // balanced small-CTA column kernels (ntt_fold.cuh); the GATHER form keeps 16-column tiles
+                plan->cols_fwd_f = (kern_t)k_cols_fwd_m3_15_b<B200_CW_M3_FWD>; plan->cols_inv_f = (kern_t)k_cols_inv_m3_15_b<B200_CW_M3_INV>;
+                plan->cols_inv_gather_f = (kern_t)k_cols_inv_m3_15_b<B200_CW_GATHER, true>;
+                plan->bal = true;
+            }
             return true;
         }
         switch (log) {
@@ -1043,11 +1054,6 @@ bool pick_col_kernels(BigPlan *plan, bool matrix, int log, bool force_generic) {
 }
 #undef STD_G
 #undef M3_G
-
-int env_int(const char *name, int dflt) {
-    const char *v = std::getenv(name);
-    return v ? std::atoi(v) : dflt;
-}
 
 u64 unit_div_magic(const Span &sp) {
     // m = ceil(2^64/d): unit*m/2^64 = unit/d + e with 0 <= e < unit/2^64 < 2^-33 < 1/d, so the floor is exact
@@ -1102,7 +1108,9 @@ int launch_ntt_big(b200_ctx *ctx, const u64 *in, u64 *out, Span sp, bool inverse
     const bool fold_cols = fold_rows && plan->fold_cols && plan->cols_fwd_f;   // both passes on signed words
     kern_t ck = inverse ? (gather ? plan->cols_inv_gather : plan->cols_inv) : plan->cols_fwd;
     if (fold_cols) ck = inverse ? (gather ? plan->cols_inv_gather_f : plan->cols_inv_f) : plan->cols_fwd_f;
-    const int col_threads = inverse ? (gather ? plan->col_threads_gather : plan->col_threads_inv) : plan->col_threads_fwd;
+    int col_threads = inverse ? (gather ? plan->col_threads_gather : plan->col_threads_inv) : plan->col_threads_fwd;
+    const bool bal = fold_cols && plan->bal;
+    if (bal) col_threads = cw * 16;
     kern_t rk;
     int row_warps;
     if (matrix) {
@@ -1117,9 +1125,10 @@ int launch_ntt_big(b200_ctx *ctx, const u64 *in, u64 *out, Span sp, bool inverse
         row_warps = B200_VT_STD;
     }
     const int rows_total = R * cw;
-    const size_t col_smem = (size_t)(rows_total + ((rows_total >> 6) << 3) + 8) * sizeof(u64);
+    const size_t col_smem = (bal ? (size_t)rows_total : (size_t)(rows_total + ((rows_total >> 6) << 3) + 8)) * sizeof(u64) + ((size_t)env_int("B200_COL_SMEM_EXTRA_KB", 0) << 10);
     size_t row_smem = (size_t)row_warps * WROW * sizeof(u64);
     if (matrix) row_smem = std::max(row_smem, (size_t)(256 * (6 * vt + 1) + 1) * sizeof(u64));
+    row_smem += (size_t)env_int("B200_ROW_SMEM_EXTRA_KB", 0) << 10;   // occupancy experiments only
     if (int rc = set_smem(ck, col_smem)) return rc;
     if (int rc = set_smem(rk, row_smem)) return rc;
     const int units = sp.batch * sp.nl;

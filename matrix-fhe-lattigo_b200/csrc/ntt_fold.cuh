@@ -159,8 +159,7 @@ k_rows_fwd_f(const u64 *in, u64 *out, BigArgs a) {
     for (int k = 0; k < 8; ++k) x[k] = L0 >= 0 ? (s64)ldd(src + k * 32 + lane) : sol_fold_u(ldd(src + k * 32 + lane), sc);
     row_fwd_core_f<(L0 >= 0 ? L0 : 0)>(x, buf, lane, P1, tw, sc);
     u64 y[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) y[k] = sol_canon(x[k], sc);   // canonical also for NTTLazy (a subset of its range)
+    sol_canon_n(y, x, sc);   // canonical also for NTTLazy (a subset of its range)
     if (!MATRIX || (a.flags & B200_TREE_ORDER)) {
         u64 *dst = out + ur.out + (size_t)r * 256 + lane * 8;
         stg256(dst, y[0], y[1], y[2], y[3]);
@@ -351,7 +350,7 @@ k_cols_inv_m3_15_f(const u64 *in, u64 *out, BigArgs a) {
     }
     __syncthreads();
     if (g < 32) {
-        const stw_t om = mc[MISC_OMEGA3], k1 = mc[MISC_K1], k2 = mc[MISC_K2], zeta = mc[MISC_ZETA];
+        const stw_t om = mc[MISC_OMEGA3], k1 = mc[MISC_K1], k4 = mc[MISC_K4];
         s64 x[6][2];
 #pragma unroll
         for (int hd = 0; hd < 6; ++hd) {
@@ -360,6 +359,7 @@ k_cols_inv_m3_15_f(const u64 *in, u64 *out, BigArgs a) {
             fbf_inv<1, true>(x[hd][0], x[hd][1], tw[6 + hd], sc);   // layer 13
         }
         u64 y[6][2];
+        s64 z[6][2];
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
 #pragma unroll
@@ -372,14 +372,16 @@ k_cols_inv_m3_15_f(const u64 *in, u64 *out, BigArgs a) {
                 x[3 * h + 2][b] = fmul(y0 - y2 + s, z2, sc);
             }
 #pragma unroll
-            for (int d = 0; d < 3; ++d) {   // inverse cyclotomic layer with the 2/N scaling: |lo - hi| < 6.6
+            for (int d = 0; d < 3; ++d) {   // inverse cyclotomic layer with the 2/N scaling: |lo +- hi| < 6.6
+                // hi = (lo' - hi')/(2 zeta - 1), lo = (lo' + hi' - hi)/2: two products and an exact halving instead of three products
                 const s64 lo = x[d][b], hi = x[d + 3][b];
                 const s64 hh = fmul(lo - hi, k1, sc);
-                const s64 ll = fmul(lo, k2, sc) - fmul(hh, zeta, sc);
-                y[d][b] = sol_canon(ll, sc);
-                y[d + 3][b] = sol_canon(hh, sc);
+                const s64 ll = fmul(lo + hi, k4, sc) - sol_half(hh, sc);
+                z[d][b] = ll;
+                z[d + 3][b] = hh;
             }
         }
+        sol_canon_n(reinterpret_cast<u64 (&)[12]>(y), reinterpret_cast<const s64 (&)[12]>(z), sc);
 #pragma unroll
         for (int hd = 0; hd < 6; ++hd)
 #pragma unroll
@@ -464,9 +466,170 @@ k_cols_inv_std16_f(const u64 *in, u64 *out, BigArgs a) {
 #pragma unroll
     for (int o = 0; o < 4; ++o) {   // layer 15 carries N^-1: |U + V| < 6.4
         const s64 U = x[o], V = x[o + 4];
-        y[o] = sol_canon(fmul(U + V, ninv, sc), sc);
-        y[o + 4] = sol_canon(fmul(U - V, ninv_w1, sc), sc);
+        x[o] = fmul(U + V, ninv, sc);
+        x[o + 4] = fmul(U - V, ninv_w1, sc);
     }
+    sol_canon_n(y, x, sc);
 #pragma unroll
     for (int k = 0; k < 8; ++k) store_out<GATHER>(a.peers, out, obase + (size_t)(k * 32 + g) * 256 + c, y[k]);
+}
+
+// ====================================================================================================
+// balanced column pass, MATRIX a = 15.  The tiled kernels above run their first (forward) / last (inverse) register
+// group on two thirds of the CTA (32 of 48 row groups) while the rest waits at the barrier: a quarter of all stall
+// samples of the forward kernel sit on that one barrier (profiles/r02_*).  Here a CTA is CW*16 threads and every
+// thread walks through 4 : 3 : 3 work items of the three phases, so that all warps are busy in all of them:
+//   phase A  cyclotomic + radix-3 layer on the 6 words (hd) of one (c, u):           CW*64 items, 4 per thread
+//   phase B  radix-2 layers 0..2 (u bits 5..3) on 8 words of one (c, hd, u & 7):     CW*48 items, 3 per thread
+//   phase C  radix-2 layers 3..5 (u bits 2..0) on 8 words of one (c, hd, u >> 3):    CW*48 items, 3 per thread
+// (inverse: C, B, A with the inverse layers).  The tile lives in shared memory between the phases, indexed
+// (row*CW + c) with bits 2-3 XOR-swizzled by the 32-word group so that all three access patterns are conflict-free
+// without padding.  Small CTAs (two warps at CW = 4) also mean 16-17 independent CTAs per SM instead of 8.
+// ====================================================================================================
+#ifndef B200_MINB_COLS_BAL
+#define B200_MINB_COLS_BAL 12    // CTAs per SM at CW = 4 (64 threads): 80 registers per thread.  Measured on B200 (cols_fwd / cols_inv, ms):
+                                 // 17 CTAs (56 regs, spills) 1.89 / 2.08, 14: 1.61 / 1.94, 12: 1.61 / 1.93, 10: 1.67 / 1.95, 8: 1.67 / 1.95
+#endif
+#ifndef B200_BAL_UNROLL
+#define B200_BAL_UNROLL 1
+#endif
+#define B200_PRAGMA_(x) _Pragma(#x)
+#define B200_UNROLL_(n) B200_PRAGMA_(unroll n)
+__device__ __forceinline__ int swz(int i) { return i ^ (((i >> 5) & 3) << 2); }
+
+template <int CW>
+__global__ void __launch_bounds__(CW * 16, (B200_MINB_COLS_BAL * 4 / CW) < 1 ? 1 : (B200_MINB_COLS_BAL * 4 / CW))
+k_cols_fwd_m3_15_b(const u64 *in, u64 *out, BigArgs a) {
+    constexpr int T = CW * 16;
+    extern __shared__ __align__(16) u64 sm[];
+    const UnitRef ur = unit_ref<true>(a);
+    const int limb = ur.limb;
+    const size_t ibase = ur.in + (size_t)blockIdx.x * CW, obase = ur.out + (size_t)blockIdx.x * CW;
+    const SolConst sc = a.sol[limb];
+    const s64 q = (s64)sc.q;
+    const stw_t *__restrict__ tw = a.fwd_s + (size_t)limb * a.N;
+    const int t = threadIdx.x;
+    {   // phase A
+        const stw_t om = a.misc_s[limb * MISC_COUNT + MISC_OMEGA3];
+        const stw_t zeta = tw[1];
+        const int c = t % CW, g = t / CW;   // g in [0,16)
+B200_UNROLL_(B200_BAL_UNROLL)
+        for (int r = 0; r < 4; ++r) {
+            const int u = g + 16 * r;
+            s64 x[6];
+#pragma unroll
+            for (int hd = 0; hd < 6; ++hd) x[hd] = (s64)ldd(in + ibase + (size_t)(hd * 64 + u) * 256 + c);
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {   // cyclotomic layer
+                const s64 lo = x[d], hi = x[d + 3];
+                const s64 tt = fmul(hi, zeta, sc);
+                x[d] = lo + tt - q;
+                x[d + 3] = lo + hi - tt - 2 * q;
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {   // radix-3 layer, outputs folded
+                const stw_t z1 = tw[2 + 2 * h], z2 = tw[3 + 2 * h];
+                const s64 b0 = sol_fold(x[3 * h], sc);
+                const s64 t1 = fmul(x[3 * h + 1], z1, sc);
+                const s64 t2 = fmul(x[3 * h + 2], z2, sc);
+                const s64 t3 = fmul(t1 - t2, om, sc);
+                x[3 * h] = sol_fold(b0 + t1 + t2, sc);
+                x[3 * h + 1] = sol_fold(b0 - t2 + t3, sc);
+                x[3 * h + 2] = sol_fold(b0 - t1 - t3, sc);
+            }
+#pragma unroll
+            for (int hd = 0; hd < 6; ++hd) sm[swz((hd * 64 + u) * CW + c)] = (u64)x[hd];
+        }
+    }
+    __syncthreads();
+B200_UNROLL_(B200_BAL_UNROLL)
+    for (int r = 0; r < 3; ++r) {   // phase B: rows hd*64 + k*8 + ulow
+        const int it = t + T * r, c = it % CW, rest = it / CW, ulow = rest & 7, hd = rest >> 3;
+        s64 x[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = (s64)sm[swz((hd * 64 + k * 8 + ulow) * CW + c)];
+        fwd_regs_f<3, 0>(x, 6u + hd, tw, sc);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sm[swz((hd * 64 + k * 8 + ulow) * CW + c)] = (u64)x[k];
+    }
+    __syncthreads();
+B200_UNROLL_(B200_BAL_UNROLL)
+    for (int r = 0; r < 3; ++r) {   // phase C: rows hd*64 + uhigh*8 + k
+        const int it = t + T * r, c = it % CW, rest = it / CW, uhigh = rest & 7, hd = rest >> 3;
+        s64 x[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = (s64)sm[swz((hd * 64 + uhigh * 8 + k) * CW + c)];
+        fwd_regs_f<3, 3>(x, (6u + hd) * 8 + uhigh, tw, sc);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) std_(out + obase + (size_t)(hd * 64 + uhigh * 8 + k) * 256 + c, (u64)x[k]);
+    }
+}
+
+template <int CW, bool GATHER = false>
+__global__ void __launch_bounds__(CW * 16, (B200_MINB_COLS_BAL * 4 / CW) < 1 ? 1 : (B200_MINB_COLS_BAL * 4 / CW))
+k_cols_inv_m3_15_b(const u64 *in, u64 *out, BigArgs a) {
+    constexpr int T = CW * 16;
+    extern __shared__ __align__(16) u64 sm[];
+    const UnitRef ur = unit_ref<true>(a);
+    const int limb = ur.limb;
+    const size_t ibase = ur.in + (size_t)blockIdx.x * CW, obase = ur.out + (size_t)blockIdx.x * CW;
+    const SolConst sc = a.sol[limb];
+    const stw_t *__restrict__ tw = a.inv_s + (size_t)limb * a.N;
+    const int t = threadIdx.x;
+B200_UNROLL_(B200_BAL_UNROLL)
+    for (int r = 0; r < 3; ++r) {   // phase C: layers 8..10 on u bits 0..2
+        const int it = t + T * r, c = it % CW, rest = it / CW, uhigh = rest & 7, hd = rest >> 3;
+        s64 x[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = (s64)ldd(in + ibase + (size_t)(hd * 64 + uhigh * 8 + k) * 256 + c);
+        inv_regs_f<3, 8>(x, (6u + hd) * 8 + uhigh, tw, sc);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sm[swz((hd * 64 + uhigh * 8 + k) * CW + c)] = (u64)x[k];
+    }
+    __syncthreads();
+B200_UNROLL_(B200_BAL_UNROLL)
+    for (int r = 0; r < 3; ++r) {   // phase B: layers 11..13 on u bits 3..5
+        const int it = t + T * r, c = it % CW, rest = it / CW, ulow = rest & 7, hd = rest >> 3;
+        s64 x[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = (s64)sm[swz((hd * 64 + k * 8 + ulow) * CW + c)];
+        inv_regs_f<3, 11>(x, 6u + hd, tw, sc);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sm[swz((hd * 64 + k * 8 + ulow) * CW + c)] = (u64)x[k];
+    }
+    __syncthreads();
+    {   // phase A: inverse radix-3 layer (factor 3 deferred) and inverse cyclotomic layer with the 2/N scaling
+        const stw_t *mc = a.misc_s + limb * MISC_COUNT;
+        const stw_t om = mc[MISC_OMEGA3], k1 = mc[MISC_K1], k4 = mc[MISC_K4];
+        const int c = t % CW, g = t / CW;
+B200_UNROLL_(B200_BAL_UNROLL)
+        for (int r = 0; r < 4; ++r) {
+            const int u = g + 16 * r;
+            s64 x[6];
+#pragma unroll
+            for (int hd = 0; hd < 6; ++hd) x[hd] = (s64)sm[swz((hd * 64 + u) * CW + c)];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const stw_t z1 = tw[2 + 2 * h], z2 = tw[3 + 2 * h];
+                const s64 y0 = x[3 * h], y1 = x[3 * h + 1], y2 = x[3 * h + 2];
+                const s64 s = fmul(y1 - y2, om, sc);
+                x[3 * h] = y0 + y1 + y2;
+                x[3 * h + 1] = fmul(y0 - y1 - s, z1, sc);
+                x[3 * h + 2] = fmul(y0 - y2 + s, z2, sc);
+            }
+            u64 y[6];
+            s64 z[6];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const s64 lo = x[d], hi = x[d + 3];
+                const s64 hh = fmul(lo - hi, k1, sc);
+                const s64 ll = fmul(lo + hi, k4, sc) - sol_half(hh, sc);
+                z[d] = ll;
+                z[d + 3] = hh;
+            }
+            sol_canon_n(y, z, sc);
+#pragma unroll
+            for (int hd = 0; hd < 6; ++hd) store_out<GATHER>(a.peers, out, obase + (size_t)(hd * 64 + u) * 256 + c, y[hd]);
+        }
+    }
 }

@@ -77,12 +77,33 @@ __device__ __forceinline__ s64 sol_fold_u(u64 v, const SolConst &c) {
 // canonical representative in [0, q) of a signed word with |v| < 2^63 - q.  v + bias is positive, its quotient word
 // h = (v + bias) >> k is in [0, 2^(64-k)), so the fold lands in (-2^(64-k)|c|, 2^k + 2^(64-k)|c|): one add-back of q
 // when negative and one subtraction when >= q (the latter only for c < 0).
-__device__ __forceinline__ u64 sol_canon(s64 v, const SolConst &c) {
+template <bool QBELOW>   // QBELOW: q = 2^k - |c| (the fold can land in [q, 2^k + ..) and needs one more subtraction)
+__device__ __forceinline__ u64 sol_canon_t(s64 v, const SolConst &c) {
     s64 r = sol_fold_u((u64)v + c.bias, c);
     unsigned lo = (unsigned)r, hi = (unsigned)((u64)r >> 32);
     asm("{\n\t.reg .pred p;\n\tsetp.lt.s32 p, %1, 0;\n\t@p add.cc.u32 %0, %0, %2;\n\t@p addc.u32 %1, %1, %3;\n\t}"
         : "+r"(lo), "+r"(hi) : "r"((unsigned)c.q), "r"((unsigned)(c.q >> 32)));
     u64 u = ((u64)hi << 32) | lo;
-    if (c.negc > 0) u = u >= c.q ? u - c.q : u;   // q = 2^k - |c|: the fold can land in [q, 2^k + ..)
+    if (QBELOW) u = u >= c.q ? u - c.q : u;
     return u;
+}
+__device__ __forceinline__ u64 sol_canon(s64 v, const SolConst &c) {
+    return c.negc > 0 ? sol_canon_t<true>(v, c) : sol_canon_t<false>(v, c);
+}
+// canonical reduction of N words behind ONE warp-uniform branch on the sign of c (the per-word form above if-converts the
+// extra subtraction into compares and selects for every word: 13 instead of 8 instructions per word)
+template <int N>
+__device__ __forceinline__ void sol_canon_n(u64 (&y)[N], const s64 (&x)[N], const SolConst &c) {
+    if (c.negc > 0) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) y[k] = sol_canon_t<true>(x[k], c);
+    } else {
+#pragma unroll
+        for (int k = 0; k < N; ++k) y[k] = sol_canon_t<false>(x[k], c);
+    }
+}
+// v/2 mod q on a signed lazy word: add q when v is odd (q is odd), then an exact arithmetic shift
+__device__ __forceinline__ s64 sol_half(s64 v, const SolConst &c) {
+    const s64 m = -(v & 1);
+    return (v + ((s64)c.q & m)) >> 1;
 }

@@ -1,0 +1,7 @@
+#!/bin/bash
+P="python tools/profile_ntt.py --polys 128 --time"
+L=matrix-fhe-lattigo_b200/lib
+{
+for v in bal12 bal10 bal8; do echo "== $v"; B200RING_LIB=$L/libb200ring_$v.so $P 2>&1 | tail -2; done
+} > gpurun_out/r2f.txt 2>&1
+cat gpurun_out/r2f.txt

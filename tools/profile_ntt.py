@@ -21,6 +21,7 @@ ap.add_argument("--iters", type=int, default=2)
 ap.add_argument("--time", action="store_true")
 ap.add_argument("--logn", type=int, default=16)
 ap.add_argument("--a", type=int, default=15)
+ap.add_argument("--tree", action="store_true", help="3N ring: keep NTT-domain slots in tree order (no slot permutation)")
 args = ap.parse_args()
 
 QI60 = [0x1fffffffffe00001, 0x1fffffffffc80001, 0x1fffffffffb40001, 0x1fffffffff500001,
@@ -37,6 +38,7 @@ if args.ring == "3n":
         moduli = b200ring.Find3NRNSPrimes(N, 60, args.limbs, 100000)
 else:
     N, moduli = 1 << args.logn, QI60[: args.limbs]
+TREE = {"tree_order": True} if args.tree else {}
 ring = b200ring.NewRing(N, moduli)
 ring.SetStream(torch.cuda.current_stream().cuda_stream)
 data = torch.empty((args.polys, len(moduli), N), dtype=torch.int64, device="cuda")
@@ -45,25 +47,25 @@ for l, q in enumerate(moduli):
 poly = b200ring.Poly.from_torch(ring, data)
 ref = data.clone()
 for _ in range(args.iters):
-    ring.NTT(poly, poly)
-    ring.INTT(poly, poly)
+    ring.NTT(poly, poly, **TREE)
+    ring.INTT(poly, poly, **TREE)
 torch.cuda.synchronize()
 assert os.environ.get("B200_SKIP_CHECK") or torch.equal(ref, data)
 if args.time:
     for _ in range(3):
-        ring.NTT(poly, poly); ring.INTT(poly, poly)
+        ring.NTT(poly, poly, **TREE); ring.INTT(poly, poly, **TREE)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = 10
     e0.record()
     for _ in range(reps):
-        ring.NTT(poly, poly); ring.INTT(poly, poly)
+        ring.NTT(poly, poly, **TREE); ring.INTT(poly, poly, **TREE)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     units = 2 * args.polys * len(moduli)
     rate = units / (ms * 1e-3)
     print("ring=%s polys=%d limbs=%d chunkMB=%s: %.3f ms/step  %.0f limb-transforms/s  %.1f%% of HBM roofline" % (
         args.ring + ":N=%d" % N, args.polys, len(moduli), os.environ.get("B200_CHUNK_MB", "dflt"), ms, rate, 100 * rate * 2 * N * 8 / 6.553e12))
-    prof = ring.Profile(lambda: (ring.NTT(poly, poly), ring.INTT(poly, poly)))
+    prof = ring.Profile(lambda: (ring.NTT(poly, poly, **TREE), ring.INTT(poly, poly, **TREE)))
     print("   ", {k: round(v["ms"], 3) for k, v in prof.items()})
 if os.environ.get("B200_PROFILE_MUL"):
     b = torch.empty_like(data)

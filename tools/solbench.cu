@@ -81,6 +81,41 @@ __device__ __forceinline__ s64 sol_fold_3(s64 v, const SolConst &c, s64 kz) {
     const unsigned lo = (unsigned)v, hi = (unsigned)((u64)v >> 32);
     return mulwide_s32((int)hi >> c.sh, c.negc) + pack64(lo, hi & c.mask) + kz;
 }
+// products without fused 64-bit addends: five mul.wide and explicit add-with-carry chains (is IMAD.WIDE with a register addend dearer?)
+__device__ __forceinline__ s64 add64_asm(s64 a, s64 b) {
+    unsigned lo, hi;
+    asm volatile("add.cc.u32 %0, %2, %4;\n\taddc.u32 %1, %3, %5;" : "=r"(lo), "=r"(hi)
+                 : "r"((unsigned)a), "r"((unsigned)((u64)a >> 32)), "r"((unsigned)b), "r"((unsigned)((u64)b >> 32)));
+    return pack64(lo, hi);
+}
+__device__ __forceinline__ s64 sol_mul_unfused(s64 y, const stw_t w, const SolConst &c) {
+    const unsigned ylo = (unsigned)y, yhi = (unsigned)((u64)y >> 32);
+    const int y0 = (int)ylo, y1 = (int)(yhi + (ylo >> 31));
+    const s64 A = add64_asm(mulwide_s32(y0, w.w_lo), mulwide_s32(y1, w.v_lo));
+    const s64 B = add64_asm(mulwide_s32(y0, w.w_hi), mulwide_s32(y1, w.v_hi));
+    const unsigned blo = (unsigned)B;
+    const s64 sh = pack64(blo << c.sh, blo >> (32 - c.sh));
+    return add64_asm(add64_asm(mulwide_s32((int)(B >> 32), c.negc), sh), A);
+}
+template <bool KU, bool KV>
+__device__ __forceinline__ void bf_sol_unfused(s64 &U, s64 &V, const stw_t w, const SolConst &c) {
+    const s64 t = sol_mul_unfused(V, w, c);
+    V = KV ? U - t + (s64)c.q : U - t;
+    U = KU ? U + t - (s64)c.q : U + t;
+}
+// the product chain starts from U, so X = U + y*w costs no addition; Y = 2U - X; no recentring (fold every 4 layers)
+__device__ __forceinline__ void bf_sol_chain(s64 &U, s64 &V, const stw_t w, const SolConst &c) {
+    const s64 y = V;
+    const unsigned ylo = (unsigned)y, yhi = (unsigned)((u64)y >> 32);
+    const int y0 = (int)ylo, y1 = (int)(yhi + (ylo >> 31));
+    s64 B = mulwide_s32(y0, w.w_hi); B = madwide_s32(y1, w.v_hi, B);
+    s64 T = madwide_s32(y0, w.w_lo, U); T = madwide_s32(y1, w.v_lo, T);
+    T = madwide_s32((int)(B >> 32), c.negc, T);
+    const unsigned blo = (unsigned)B;
+    const s64 X = T + pack64(blo << c.sh, blo >> (32 - c.sh));
+    V = U + U - X;
+    U = X;
+}
 // inverse (Gentleman-Sande) butterfly: U' = U + V, V' = (U - V)*w
 __device__ __forceinline__ void bf_sol_inv(s64 &U, s64 &V, const stw_t w, const SolConst &c) {
     const s64 d = U - V;
@@ -121,7 +156,7 @@ __global__ void __launch_bounds__(128, 8) k_bf(u64 *data, const tw_t *twi, const
 #pragma unroll
                 for (int k = 0; k < 8; ++k) z[k] = sol_fold_3(z[k], sc, kz);
             }
-            if ((MODE == 6 || MODE == 7) && (l & 3) == 0) {   // fold every 4 layers
+            if ((MODE == 6 || MODE == 7 || MODE == 10 || MODE == 11) && (l & 3) == 0) {   // fold every 4 layers
 #pragma unroll
                 for (int k = 0; k < 8; ++k) z[k] = sol_fold(z[k], sc);
             }
@@ -150,6 +185,11 @@ __global__ void __launch_bounds__(128, 8) k_bf(u64 *data, const tw_t *twi, const
                     } else if (MODE == 9) {
                         const int r = l & 3;
                         if (r == 0) bf_sol_3<0, 1>(z[i0], z[i1], tws[ti], sc, kz); else if (r == 3) bf_sol_3<0, 0>(z[i0], z[i1], tws[ti], sc, kz); else bf_sol_3<1, 0>(z[i0], z[i1], tws[ti], sc, kz);
+                    } else if (MODE == 10) {
+                        const int r = l & 3;
+                        if (r == 0) bf_sol_unfused<false, true>(z[i0], z[i1], tws[ti], sc); else if (r == 3) bf_sol_unfused<false, false>(z[i0], z[i1], tws[ti], sc); else bf_sol_unfused<true, false>(z[i0], z[i1], tws[ti], sc);
+                    } else if (MODE == 11) {
+                        bf_sol_chain(z[i0], z[i1], tws[ti], sc);
                     } else if (MODE == 7) {
                         const int r = l & 3;
                         if (r == 0) bf_sol_sh<false, true>(z[i0], z[i1], tws[ti], sc); else if (r == 3) bf_sol_sh<false, false>(z[i0], z[i1], tws[ti], sc); else bf_sol_sh<true, false>(z[i0], z[i1], tws[ti], sc);
@@ -273,6 +313,10 @@ int main(int argc, char **argv) {
         { std::vector<u64> u8; bench<9, 8>("design B, ALU shifter, every add with 3 inputs", sms, d, in, d_ti, d_ta, d_ts, c, sa, sc, &u8);
           size_t b3 = 0; for (size_t i = 0; i < r8.size() && i < u8.size(); ++i) b3 += r8[i] != u8[i];
           printf("   parity vs Shoup/Harvey: %zu mismatches\n", b3); }
+        { std::vector<u64> u8, v8; bench<10, 8>("design B, ALU shifter, unfused products (5 mul.wide + adds)", sms, d, in, d_ti, d_ta, d_ts, c, sa, sc, &u8);
+          bench<11, 8>("design B, product chain started from U, no recentring", sms, d, in, d_ti, d_ta, d_ts, c, sa, sc, &v8);
+          size_t b3 = 0, b4 = 0; for (size_t i = 0; i < r8.size() && i < u8.size() && i < v8.size(); ++i) { b3 += r8[i] != u8[i]; b4 += r8[i] != v8[i]; }
+          printf("   parity vs Shoup/Harvey: unfused %zu, chain %zu mismatches\n", b3, b4); }
         size_t b1 = 0, b2 = 0; for (size_t i = 0; i < r8.size() && i < s8.size() && i < t8.size(); ++i) { b1 += r8[i] != s8[i]; b2 += r8[i] != t8[i]; }
         printf("   parity vs Shoup/Harvey: %zu and %zu mismatches\n", b1, b2); }
       bench<5, 6>("design B, no fold (timing only)", sms, d, in, d_ti, d_ta, d_ts, c, sa, sc, &rx);
