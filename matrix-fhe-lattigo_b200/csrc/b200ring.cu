@@ -255,6 +255,32 @@ static cudaError_t fold_setup(b200_ctx *ctx, const std::vector<tw_t> &fwd, const
     };
     std::vector<stw_t> f, v, m;
     if (!conv(fwd, (size_t)ctx->N, f) || !conv(inv, (size_t)ctx->N, v) || !conv(misc, (size_t)MISC_COUNT, m)) return cudaSuccess;
+    // Row-pass order (ntt_fold.cuh, row_tw_offset): the 255 twiddles of the subtree under row node R + r move to the block
+    // [R + 255 r, R + 255 (r + 1)) in the order the lanes of the row kernels load them, so that one load instruction of a warp
+    // reads consecutive entries.  Heap indices below R (all the column pass uses) stay where they are.
+    if (ctx->N >= 512 && ctx->N % 256 == 0) {
+        const int N = ctx->N, R = N / 256;
+        auto reorder = [&](std::vector<stw_t> &t) {
+            std::vector<stw_t> o(t);
+            for (int i = 0; i < L; ++i) {
+                const stw_t *src = &t[(size_t)i * N];
+                stw_t *dst = &o[(size_t)i * N];
+                for (int h = R; h < N; ++h) {
+                    int d = 0;
+                    while ((h >> d) >= 2 * R) ++d;
+                    const int r = (h >> d) - R, k = h & ((1 << d) - 1);
+                    int off;
+                    if (d < 3) off = (1 << d) - 1 + k;
+                    else if (d < 6) { const int j = d - 3, hi3 = k >> j, g = k & ((1 << j) - 1); off = 7 + ((1 << j) - 1 + g) * 8 + hi3; }
+                    else { const int j = d - 6, sub = k >> j, g = k & ((1 << j) - 1), lane = sub >> 1, s2 = sub & 1; off = 63 + (s2 * 3 + (1 << j) - 1 + g) * 32 + lane; }
+                    dst[R + 255 * r + off] = src[h];
+                }
+            }
+            t.swap(o);
+        };
+        reorder(f);
+        reorder(v);
+    }
     auto up = [&](void **dst, const void *src, size_t bytes) -> cudaError_t {
         cudaError_t e = cudaMalloc(dst, bytes);
         if (e != cudaSuccess) return e;

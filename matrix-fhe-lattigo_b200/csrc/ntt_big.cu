@@ -84,6 +84,9 @@
 #define B200_CW_M3_INV 4
 #endif
 // the GATHER instantiations also store to peer GPUs: wider tiles make longer contiguous NVLink writes
+#ifndef B200_CW_BAL
+#define B200_CW_BAL 4     // columns per CTA of the balanced fold column kernels (env B200_CW_BAL: 4, 8 or 16)
+#endif
 #ifndef B200_CW_GATHER
 #define B200_CW_GATHER 16
 #endif
@@ -1003,6 +1006,7 @@ struct BigPlan {
     // fold-arithmetic column kernels of the shape (null: none, the row pass then folds what the Shoup column pass left)
     kern_t cols_fwd_f = nullptr, cols_inv_f = nullptr, cols_inv_gather_f = nullptr;
     int row_l0 = -1;                           // number of the row pass's first layer after cols_fwd_f
+    int cw_bal = 4;                            // columns per CTA of the balanced kernels
     bool bal = false;                          // fold column kernels are the balanced form: CW*16 threads, unpadded tile
 };
 
@@ -1039,7 +1043,10 @@ bool pick_col_kernels(BigPlan *plan, bool matrix, int log, bool force_generic) {
             plan->cols_inv_gather_f = (kern_t)k_cols_inv_m3_15_f<B200_CW_GATHER, true>;
             plan->row_l0 = M3_15_ROW_L0;
             if (env_int("B200_COLS_BAL", 1)) {   // balanced small-CTA column kernels (ntt_fold.cuh); the GATHER form keeps 16-column tiles
-                plan->cols_fwd_f = (kern_t)k_cols_fwd_m3_15_b<B200_CW_M3_FWD>; plan->cols_inv_f = (kern_t)k_cols_inv_m3_15_b<B200_CW_M3_INV>;
+                const int cwb = env_int("B200_CW_BAL", B200_CW_BAL);
+                if (cwb == 16) { plan->cols_fwd_f = (kern_t)k_cols_fwd_m3_15_b<16>; plan->cols_inv_f = (kern_t)k_cols_inv_m3_15_b<16>; plan->cw_bal = 16; }
+                else if (cwb == 8) { plan->cols_fwd_f = (kern_t)k_cols_fwd_m3_15_b<8>; plan->cols_inv_f = (kern_t)k_cols_inv_m3_15_b<8>; plan->cw_bal = 8; }
+                else { plan->cols_fwd_f = (kern_t)k_cols_fwd_m3_15_b<4>; plan->cols_inv_f = (kern_t)k_cols_inv_m3_15_b<4>; plan->cw_bal = 4; }
                 plan->cols_inv_gather_f = (kern_t)k_cols_inv_m3_15_b<B200_CW_GATHER, true>;
                 plan->bal = true;
             }
@@ -1100,16 +1107,17 @@ int launch_ntt_big(b200_ctx *ctx, const u64 *in, u64 *out, Span sp, bool inverse
     if (gather && !inverse) return 1;   // only the inverse transform has a fused all-gather
     const bool matrix = ctx->ring_type == B200_RING_MATRIX;
     const bool permute = matrix && !(flags & B200_TREE_ORDER);
-    const int N = ctx->N, R = N / 256, cw = inverse ? (gather ? plan->cw_gather : plan->cw_inv) : plan->cw_fwd, vt = plan->vt;
+    const bool fold_rows = ctx->fold_ok && plan->fold_rows;
+    const bool fold_cols = fold_rows && plan->fold_cols && plan->cols_fwd_f;   // both passes on signed words
+    const bool bal = fold_cols && plan->bal;
+    const int N = ctx->N, R = N / 256, vt = plan->vt;
+    const int cw = inverse ? (gather ? plan->cw_gather : (bal ? plan->cw_bal : plan->cw_inv)) : (bal ? plan->cw_bal : plan->cw_fwd);
     BigArgs a{ctx->d_consts, ctx->d_fwd, ctx->d_inv, ctx->d_misc, N, R, matrix ? ctx->a - 9 : 0, sp, 0, flags, 0, 0};
     a.div_magic = unit_div_magic(sp);
     a.sol = ctx->d_sol; a.fwd_s = ctx->d_fwd_s; a.inv_s = ctx->d_inv_s; a.misc_s = ctx->d_misc_s;
-    const bool fold_rows = ctx->fold_ok && plan->fold_rows;
-    const bool fold_cols = fold_rows && plan->fold_cols && plan->cols_fwd_f;   // both passes on signed words
     kern_t ck = inverse ? (gather ? plan->cols_inv_gather : plan->cols_inv) : plan->cols_fwd;
     if (fold_cols) ck = inverse ? (gather ? plan->cols_inv_gather_f : plan->cols_inv_f) : plan->cols_fwd_f;
     int col_threads = inverse ? (gather ? plan->col_threads_gather : plan->col_threads_inv) : plan->col_threads_fwd;
-    const bool bal = fold_cols && plan->bal;
     if (bal) col_threads = cw * 16;
     kern_t rk;
     int row_warps;

@@ -5,14 +5,6 @@
 #pragma once
 #include "solinas.cuh"
 
-#ifndef B200_TW_UNIFORM_HACK
-#define B200_TW_UNIFORM_HACK 0   // timing experiment only (wrong results): every lane of a warp uses the same twiddles
-#endif
-#if B200_TW_UNIFORM_HACK
-#define TWL(x) 0
-#else
-#define TWL(x) (x)
-#endif
 #ifndef B200_FOLD_WIDE_SHIFT
 #define B200_FOLD_WIDE_SHIFT 0   // 1: 2^s*B.lo through a sixth wide multiply instead of two shifts (measured slower, tools/solbench)
 #endif
@@ -60,6 +52,27 @@ __device__ __forceinline__ void fwd_regs_f(s64 (&x)[1 << LOGM], unsigned P, cons
     }
 }
 
+// The same on the row-pass order of the tables (b200ring.cu fold_setup): the twiddle of level j, block g of a register group
+// is base[((1 << j) - 1 + g) * STRIDE]; base and STRIDE say which group of the row it is (row_fwd_core_f).
+template <int LOGM, int L0, int STRIDE>
+__device__ __forceinline__ void fwd_regs_fr(s64 (&x)[1 << LOGM], const stw_t *__restrict__ base, const SolConst &c) {
+#pragma unroll
+    for (int j = 0; j < LOGM; ++j) {
+        const int half = (1 << LOGM) >> (j + 1);
+        const int l = L0 + j, r = l % FWD_PERIOD;
+        if (l > 0 && r == 0) {
+#pragma unroll
+            for (int k = 0; k < (1 << LOGM); ++k) x[k] = sol_fold(x[k], c);
+        }
+#pragma unroll
+        for (int g = 0; g < (1 << j); ++g) {
+            const stw_t w = base[((1 << j) - 1 + g) * STRIDE];
+#pragma unroll
+            for (int o = 0; o < half; ++o) fbf_fwd(x[g * 2 * half + o], x[g * 2 * half + o + half], w, c, fwd_ku(r), fwd_kv(r));
+        }
+    }
+}
+
 // inverse (Gentleman-Sande) butterfly: U' = U + V - KS*q (folded when FOLD), V' = (U - V)*w
 template <int KS, bool FOLD>
 __device__ __forceinline__ void fbf_inv(s64 &U, s64 &V, const stw_t w, const SolConst &c) {
@@ -89,18 +102,38 @@ __device__ __forceinline__ void inv_regs_f(s64 (&x)[1 << LOGM], unsigned P, cons
     }
 }
 
+template <int LOGM, int L0, int STRIDE>
+__device__ __forceinline__ void inv_regs_fr(s64 (&x)[1 << LOGM], const stw_t *__restrict__ base, const SolConst &c) {
+#pragma unroll
+    for (int j = LOGM - 1; j >= 0; --j) {
+        const int half = (1 << LOGM) >> (j + 1);
+        const int l = L0 + (LOGM - 1 - j);
+#pragma unroll
+        for (int g = 0; g < (1 << j); ++g) {
+            const stw_t w = base[((1 << j) - 1 + g) * STRIDE];
+#pragma unroll
+            for (int o = 0; o < half; ++o) {
+                if (l & 1) fbf_inv<1, true>(x[g * 2 * half + o], x[g * 2 * half + o + half], w, c);
+                else fbf_inv<0, false>(x[g * 2 * half + o], x[g * 2 * half + o + half], w, c);
+            }
+        }
+    }
+}
+
+// Twiddles of a row in row-pass order: block twr = table + R + 255*row; [0,7) the first group (warp-uniform), then 7 runs of
+// 8 entries (second group, indexed by hi3 = lane & 7), then 6 runs of 32 entries (third group, indexed by lane).
 // The 8 layers of one 256-word row held by one warp; same exchanges as row_fwd_core (ntt_big.cu).
 // in: c = k*32 + lane, words in (-2^(64-k)|c|, 2^k) (fold_u of anything)   out: c = lane*8 + k, |word| < 5.4 * 2^k
 template <int L0>
-__device__ __forceinline__ void row_fwd_core_f(s64 (&x)[8], u64 *buf, int lane, unsigned P1, const stw_t *__restrict__ tw, const SolConst &c) {
-    fwd_regs_f<3, L0>(x, P1, tw, c);
+__device__ __forceinline__ void row_fwd_core_f(s64 (&x)[8], u64 *buf, int lane, const stw_t *__restrict__ twr, const SolConst &c) {
+    fwd_regs_fr<3, L0, 1>(x, twr, c);
 #pragma unroll
     for (int k = 0; k < 8; ++k) buf[pad16(k * 32 + lane)] = (u64)x[k];
     __syncwarp();
     const int hi3 = lane & 7, lo2 = lane >> 3;
 #pragma unroll
     for (int k = 0; k < 8; ++k) x[k] = (s64)buf[pad16(hi3 * 32 + k * 4 + lo2)];
-    fwd_regs_f<3, L0 + 3>(x, P1 * 8 + TWL(hi3), tw, c);
+    fwd_regs_fr<3, L0 + 3, 8>(x, twr + 7 + hi3, c);
     __syncwarp();
 #pragma unroll
     for (int k = 0; k < 8; ++k) buf[pad16(hi3 * 32 + k * 4 + lo2)] = (u64)x[k];
@@ -109,17 +142,17 @@ __device__ __forceinline__ void row_fwd_core_f(s64 (&x)[8], u64 *buf, int lane, 
     for (int k = 0; k < 8; ++k) x[k] = (s64)buf[pad16(lane * 8 + k)];
     s64 (&lo)[4] = *reinterpret_cast<s64 (*)[4]>(&x[0]);
     s64 (&hi)[4] = *reinterpret_cast<s64 (*)[4]>(&x[4]);
-    fwd_regs_f<2, L0 + 6>(lo, P1 * 64 + TWL(lane * 2), tw, c);
-    fwd_regs_f<2, L0 + 6>(hi, P1 * 64 + TWL(lane * 2) + 1, tw, c);
+    fwd_regs_fr<2, L0 + 6, 32>(lo, twr + 63 + lane, c);
+    fwd_regs_fr<2, L0 + 6, 32>(hi, twr + 63 + 96 + lane, c);
     __syncwarp();
 }
 // in: c = lane*8 + k, words in (-eps, 2^k + eps)   out: c = k*32 + lane; sums folded, products in (-0.6, 1.6) * 2^k
-__device__ __forceinline__ void row_inv_core_f(s64 (&x)[8], u64 *buf, int lane, unsigned P1, const stw_t *__restrict__ tw, const SolConst &c) {
+__device__ __forceinline__ void row_inv_core_f(s64 (&x)[8], u64 *buf, int lane, const stw_t *__restrict__ twr, const SolConst &c) {
     {
         s64 (&lo)[4] = *reinterpret_cast<s64 (*)[4]>(&x[0]);
         s64 (&hi)[4] = *reinterpret_cast<s64 (*)[4]>(&x[4]);
-        inv_regs_f<2, 0>(lo, P1 * 64 + TWL(lane * 2), tw, c);
-        inv_regs_f<2, 0>(hi, P1 * 64 + TWL(lane * 2) + 1, tw, c);
+        inv_regs_fr<2, 0, 32>(lo, twr + 63 + lane, c);
+        inv_regs_fr<2, 0, 32>(hi, twr + 63 + 96 + lane, c);
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k) buf[pad16(lane * 8 + k)] = (u64)x[k];
@@ -127,14 +160,14 @@ __device__ __forceinline__ void row_inv_core_f(s64 (&x)[8], u64 *buf, int lane, 
     const int hi3 = lane & 7, lo2 = lane >> 3;
 #pragma unroll
     for (int k = 0; k < 8; ++k) x[k] = (s64)buf[pad16(hi3 * 32 + k * 4 + lo2)];
-    inv_regs_f<3, 2>(x, P1 * 8 + TWL(hi3), tw, c);
+    inv_regs_fr<3, 2, 8>(x, twr + 7 + hi3, c);
     __syncwarp();
 #pragma unroll
     for (int k = 0; k < 8; ++k) buf[pad16(hi3 * 32 + k * 4 + lo2)] = (u64)x[k];
     __syncwarp();
 #pragma unroll
     for (int k = 0; k < 8; ++k) x[k] = (s64)buf[pad16(k * 32 + lane)];
-    inv_regs_f<3, 5>(x, P1, tw, c);
+    inv_regs_fr<3, 5, 1>(x, twr, c);
 }
 
 // L0 < 0: the column pass was a Shoup kernel (unsigned words below 8q): fold at the load, layers 0..7.
@@ -153,11 +186,11 @@ k_rows_fwd_f(const u64 *in, u64 *out, BigArgs a) {
     const int r = row_of<MATRIX, VT>(a, blockIdx.y, w, rowcode);
     u64 *buf = sm + w * WROW;
     const u64 *src = in + ur.in + (size_t)r * 256;
-    const unsigned P1 = (unsigned)(a.R + r);
+    const stw_t *__restrict__ twr = tw + a.R + 255 * r;
     s64 x[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) x[k] = L0 >= 0 ? (s64)ldd(src + k * 32 + lane) : sol_fold_u(ldd(src + k * 32 + lane), sc);
-    row_fwd_core_f<(L0 >= 0 ? L0 : 0)>(x, buf, lane, P1, tw, sc);
+    row_fwd_core_f<(L0 >= 0 ? L0 : 0)>(x, buf, lane, twr, sc);
     u64 y[8];
     sol_canon_n(y, x, sc);   // canonical also for NTTLazy (a subset of its range)
     if (!MATRIX || (a.flags & B200_TREE_ORDER)) {
@@ -196,7 +229,7 @@ k_rows_inv_f(const u64 *in, u64 *out, BigArgs a) {
     int rowcode;
     const int r = row_of<MATRIX, VT>(a, blockIdx.y, w, rowcode);
     u64 *buf = sm + w * WROW;
-    const unsigned P1 = (unsigned)(a.R + r);
+    const stw_t *__restrict__ twr = tw + a.R + 255 * r;
     u64 y[8];
     if (!MATRIX || (a.flags & B200_TREE_ORDER)) {
         const u64 *src = in + ur.in + (size_t)r * 256 + lane * 8;
@@ -225,7 +258,7 @@ k_rows_inv_f(const u64 *in, u64 *out, BigArgs a) {
     s64 x[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) x[k] = sol_fold_u(y[k], sc);      // any 64-bit input word
-    row_inv_core_f(x, buf, lane, P1, tw, sc);
+    row_inv_core_f(x, buf, lane, twr, sc);
     u64 *dst = out + ur.out + (size_t)r * 256;
     if (SIGNED_OUT) {
 #pragma unroll
