@@ -309,7 +309,7 @@ extern "C" int b200_ctx_create(int ring_type, int N, int L, const uint64_t *modu
         return fail(B200_EINVAL, "invalid ring degree: the Standard ring needs N to be a power of 2 greater than 8");
     if (ring_type == B200_RING_CONJUGATE_INVARIANT && !pow2)   // the reference's 6N variant runs radix-2 butterflies on a non-power-of-two length
         return fail(B200_EINVAL, "invalid ring degree: the ConjugateInvariant ring needs N to be a power of 2 greater than 8");
-    if (ring_type == B200_RING_MATRIX && !(N % 3 == 0 && is3n && N >= 8 && a >= 1))   // ring.go:301-303
+    if (ring_type == B200_RING_MATRIX && !(N % 3 == 0 && is3n && a >= 1))   // ring.go:301-303, 319-323: every N = 2^a 3^b with a, b >= 1, N = 6 included
         return fail(B200_EINVAL, "matrix ring type requires N to satisfy 3N = 2^a * 3^{b+1} condition, got N=" + std::to_string(N));
     if (L <= 0 || !moduli) return fail(B200_EINVAL, "invalid ModuliChain (must be a non-empty []uint64)");   // ring.go:325-327
     {
@@ -349,8 +349,11 @@ extern "C" int b200_ctx_create(int ring_type, int N, int L, const uint64_t *modu
         while (bl < 64 && ((s.q - 1) >> bl)) ++bl;
         s.mask = bl >= 64 ? ~0ULL : ((1ULL << bl) - 1);   // subring.go:94
         {
-            // quotient estimate constants: xs = x >> sh has <= 32 bits for x < 16q; qs = q >> sh has <= 28 bits;
-            // mul = floor(2^32 / (qs + 1)) underestimates 2^(32+sh)/q by < 2^-26 relative.
+            // quotient estimate constants (canon_est, modarith.cuh): xs = x >> sh has <= 32 bits for x < 16q; qs = q >> sh has
+            // 28 bits.  mul = floor(2^32 / (qs + 1)) lies in [16, 32], so its truncation alone is worth up to 1/17 of the
+            // quotient: k = (xs * mul) >> 32 never exceeds floor(x / q) and falls short of it by at most one ONLY because
+            // x < 16q (deficit < 16/17 + 2^-27 * 16 < 1, plus the floor).  Do not reuse these constants for a wider input range;
+            // tests/test_canon_est.py restates the bound on random and extreme q.
             int bl = 0;
             while (bl < 64 && (s.q >> bl)) ++bl;
             const unsigned sh = bl > 28 ? (unsigned)(bl - 28) : 0u;
@@ -435,6 +438,7 @@ extern "C" void b200_ctx_destroy(b200_ctx *ctx) {
             cudaFree(ctx->pipe.buf[i]);
             cudaEventDestroy(ctx->pipe.up[i]); cudaEventDestroy(ctx->pipe.done[i]); cudaEventDestroy(ctx->pipe.freed[i]);
         }
+        cudaEventDestroy(ctx->pipe.entry);
         cudaStreamDestroy(ctx->pipe.h2d); cudaStreamDestroy(ctx->pipe.comp); cudaStreamDestroy(ctx->pipe.d2h);
     }
     delete ctx;
@@ -834,13 +838,13 @@ extern "C" int b200_vec_op(b200_ctx *ctx, int op, const b200_poly *p1, const b20
         const size_t ns = (size_t)(level + 1) * (op >= B200_OP_ADD_SCALAR_LAZY_MULSCALAR_MONT ? 2 : 1);
         // small per-call constant block; lives in the scratch-independent misc area of the stream order
         u64 *tmp = nullptr;
-        CUDA_TRY(cudaMallocAsync(&tmp, sizeof(u64) * ns, ctx->stream));
-        CUDA_TRY(cudaMemcpyAsync(tmp, scalars, sizeof(u64) * ns, cudaMemcpyHostToDevice, ctx->stream));
-        CUDA_TRY(cudaStreamSynchronize(ctx->stream));   // `scalars` is a pageable Go/host slice
+        CUDA_TRY(cudaMallocAsync(&tmp, sizeof(u64) * ns, b200_cur_stream(ctx)));
+        CUDA_TRY(cudaMemcpyAsync(tmp, scalars, sizeof(u64) * ns, cudaMemcpyHostToDevice, b200_cur_stream(ctx)));
+        CUDA_TRY(cudaStreamSynchronize(b200_cur_stream(ctx)));   // `scalars` is a pageable Go/host slice
         d_sc = tmp;
     }
     int rc = launch_vec_op(ctx, op, p1 ? p1->d : p3->d, p2 ? p2->d : nullptr, p3->d, Span{batch, level + 1, ctx->L, 0}, d_sc);
-    if (d_sc) cudaFreeAsync((void *)d_sc, ctx->stream);
+    if (d_sc) cudaFreeAsync((void *)d_sc, b200_cur_stream(ctx));
     return rc;
 }
 
@@ -1127,6 +1131,7 @@ extern "C" int b200_transform_host(b200_ctx *ctx, const uint64_t *host_in, uint6
             CUDA_TRY(cudaEventCreateWithFlags(&p.done[i], cudaEventDisableTiming));
             CUDA_TRY(cudaEventCreateWithFlags(&p.freed[i], cudaEventDisableTiming));
         }
+        CUDA_TRY(cudaEventCreateWithFlags(&p.entry, cudaEventDisableTiming));
         p.ready = true;
     }
     if (p.buf_words < (size_t)cpolys * poly_words) {
@@ -1139,6 +1144,11 @@ extern "C" int b200_transform_host(b200_ctx *ctx, const uint64_t *host_in, uint6
         p.buf_words = (size_t)cpolys * poly_words;
     }
     int rc = 0;
+    // The transforms below run on the pipeline's own stream but share the context scratch (slot permutation, layered
+    // large-N path) with whatever was queued earlier on the context's stream: wait for that work first.  The pipeline is
+    // drained before this call returns, so later work on the context's stream cannot overlap it either.
+    CUDA_TRY(cudaEventRecord(p.entry, ctx->stream));
+    CUDA_TRY(cudaStreamWaitEvent(p.comp, p.entry, 0));
     b200_set_stream_override(p.comp, true);
     // scratch for the slot permutation of MATRIX rings is sized once, before any work is in flight
     if (ctx->ring_type == B200_RING_MATRIX && !(flags & B200_TREE_ORDER))

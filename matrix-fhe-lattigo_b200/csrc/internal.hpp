@@ -75,6 +75,7 @@ struct b200_ctx {
         u64 *buf[NB] = {nullptr, nullptr, nullptr};
         size_t buf_words = 0;
         cudaEvent_t up[NB], done[NB], freed[NB];
+        cudaEvent_t entry = nullptr;   // orders the pipeline's compute stream after the work already queued on the context's stream
         bool ready = false;
     } pipe;
 };

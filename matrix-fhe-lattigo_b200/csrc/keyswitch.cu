@@ -25,7 +25,10 @@ namespace hm = hostmath;
 namespace {
 
 constexpr int EXT_THREADS = 128;
-constexpr int EXT_MAX_SRC = 64;
+// Source limbs of one extension: the Go code's y[32] buffer (ring/basis_extension.go:529) is the same cap.  Below it the
+// 128-bit accumulator cannot wrap (32 q^2 < 2^127 for q < 2^61) and the generic kernel's ns KiB of shared memory fits the
+// 48 KiB a kernel gets without opting in.
+constexpr int EXT_MAX_SRC = 32;
 
 // device-side description of one extension: source limbs -> target limbs
 struct ExtDesc {
@@ -68,7 +71,9 @@ k_basis_extend(const u64 *src, u64 *dst, const LimbConst *__restrict__ consts, E
         }
         u64 r = rhi - __umul64hi(rlo * c.qinv, c.q) + c.q + d.vtimesqmodp[(size_t)j * (d.ns + 1) + v];   // [0, 3p)
         r = csub(r + c.q - d.sub[j], c.q);                                                             // SubScalar
-        if (mode == 1) r = csub(csub(r, 2 * c.q), c.q);
+        // canonical form: r < 4p only while the accumulator's high word is below 2p, i.e. ns <= 16 for 61-bit primes
+        // (rhi < ns p^2 / 2^64 <= ns p / 8); longer digits go through the Barrett reduction of any 64-bit word
+        if (mode == 1) r = d.ns <= 16 ? csub(csub(r, 2 * c.q), c.q) : bred_add(r, c.q, c.brc_hi);
         o[(size_t)d.dst_limb[j] * N] = r;
     }
 }
@@ -308,7 +313,7 @@ struct b200_keyswitch {
     size_t ws_words = 0;
     u64 *d_moddown = nullptr;                // [LP][LQ]: q_i - moddown[levelP][i], the scalar of the final ModDown pass
     u64 *d_moddown_qp = nullptr;             // [LQ][LP]: p_j - MForm((q_0..q_levelQ)^-1 mod p_j), the same for ModDownQPtoP (modDownConstantsQtoP, :61)
-    std::map<int, int *> limb_lists;         // (levelQ, levelP) -> device list of the limbs the multiply-accumulate touches
+    std::map<long long, int *> limb_lists;   // (q0, q1, p0, p1) -> device list of the limbs the multiply-accumulate touches
 };
 
 namespace {
@@ -318,6 +323,11 @@ cudaError_t upload(T **dst, const std::vector<T> &v) {
     cudaError_t e = cudaMalloc(dst, sizeof(T) * std::max<size_t>(v.size(), 1));
     if (e != cudaSuccess) return e;
     return cudaMemcpy(*dst, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice);
+}
+
+// key of b200_keyswitch::limb_lists: four limb indices, 16 bits each (chains of any length the ring admits)
+static inline long long limb_list_key(int q0, int q1, int p0, int p1) {
+    return ((((long long)q0 << 16 | (long long)q1) << 16 | (long long)p0) << 16) | (long long)p1;
 }
 
 // GenModUpConstants (:95-166) for source limbs S and target limbs T of the ring, plus the centring scalars
@@ -514,7 +524,7 @@ int decompose_mac(b200_keyswitch *ks, int levelQ, int levelP, const u64 *cx, con
     std::vector<int> limbs = range(o.q0, o.q1);
     for (int j = o.p0; j < o.p1; ++j) limbs.push_back(LQ + j);
     if (limbs.empty()) return 0;
-    int *&d_limbs = ks->limb_lists[((o.q0 * 64 + o.q1) * 64 + o.p0) * 64 + o.p1];
+    int *&d_limbs = ks->limb_lists[limb_list_key(o.q0, o.q1, o.p0, o.p1)];
     if (!d_limbs) {
         cudaError_t ce = upload(&d_limbs, limbs);
         if (ce != cudaSuccess) return b200_cuda_fail(ce, "gadget product limb list");
@@ -551,7 +561,7 @@ int bitdecomp_mac(b200_keyswitch *ks, int levelQ, int levelP, int pw2, const int
     const int LQ = ks->LQ, N = ctx->N;
     std::vector<int> limbs = range(0, levelQ + 1);
     for (int j = 0; j <= levelP; ++j) limbs.push_back(LQ + j);
-    int *&d_limbs = ks->limb_lists[((0 * 64 + (levelQ + 1)) * 64 + 0) * 64 + (levelP + 1)];
+    int *&d_limbs = ks->limb_lists[limb_list_key(0, levelQ + 1, 0, levelP + 1)];
     if (!d_limbs) {
         cudaError_t ce = upload(&d_limbs, limbs);
         if (ce != cudaSuccess) return b200_cuda_fail(ce, "gadget product limb list");
@@ -763,7 +773,7 @@ extern "C" int b200_gadget_product_hoisted(b200_keyswitch *ks, int levelQ, int l
     u64 *acc0 = ks->ws, *acc1 = ks->ws + words, *buf = ks->ws + 2 * words;
     std::vector<int> limbs = range(0, levelQ + 1);
     for (int j = 0; j <= levelP; ++j) limbs.push_back(LQ + j);
-    int *&d_limbs = ks->limb_lists[((0 * 64 + (levelQ + 1)) * 64 + 0) * 64 + (levelP + 1)];
+    int *&d_limbs = ks->limb_lists[limb_list_key(0, levelQ + 1, 0, levelP + 1)];
     if (!d_limbs) {
         cudaError_t ce = upload(&d_limbs, limbs);
         if (ce != cudaSuccess) return b200_cuda_fail(ce, "gadget product limb list");

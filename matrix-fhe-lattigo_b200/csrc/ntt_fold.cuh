@@ -271,8 +271,9 @@ k_rows_inv_f(const u64 *in, u64 *out, BigArgs a) {
 
 // ====================================================================================================
 // column pass on the fold arithmetic: the hand-tuned headline shapes (same tiling as k_cols_*_m3_15 / k_cols_*_std16).
-// Inputs of the forward kernels are the caller's words, taken as they are: they must be below 4q (the reference's
-// transforms take words below 2q at most, ring/ntt.go:155-171).
+// Inputs of the forward kernels are the caller's words, taken as they are.  Contract: below 2q, what the reference's
+// transforms take (ring/ntt.go:155-171) and what the Shoup kernels of ntt_big.cu assume; the schedules hold up to
+// 4 * 2^k (3N) and 2.5 * 2^k (2^16), tools/fold_ranges.py.
 // ====================================================================================================
 
 // MATRIX, a = 15.  G1: cyclotomic layer, radix-3 layer, fold, radix-2 layer 0; G2: layers 1..3; G3: layers 4, 5 (all
@@ -400,7 +401,7 @@ k_cols_inv_m3_15_f(const u64 *in, u64 *out, BigArgs a) {
                 const stw_t z1 = tw[2 + 2 * h], z2 = tw[3 + 2 * h];
                 const s64 y0 = x[3 * h][b], y1 = x[3 * h + 1][b], y2 = x[3 * h + 2][b];
                 const s64 s = fmul(y1 - y2, om, sc);
-                x[3 * h][b] = y0 + y1 + y2;
+                x[3 * h][b] = sol_fold(y0 + y1 + y2, sc);   // folded: lo + hi of the cyclotomic layer must stay a valid multiplicand
                 x[3 * h + 1][b] = fmul(y0 - y1 - s, z1, sc);
                 x[3 * h + 2][b] = fmul(y0 - y2 + s, z2, sc);
             }
@@ -646,7 +647,7 @@ B200_UNROLL_(B200_BAL_UNROLL)
                 const stw_t z1 = tw[2 + 2 * h], z2 = tw[3 + 2 * h];
                 const s64 y0 = x[3 * h], y1 = x[3 * h + 1], y2 = x[3 * h + 2];
                 const s64 s = fmul(y1 - y2, om, sc);
-                x[3 * h] = y0 + y1 + y2;
+                x[3 * h] = sol_fold(y0 + y1 + y2, sc);   // folded: lo + hi of the cyclotomic layer must stay a valid multiplicand
                 x[3 * h + 1] = fmul(y0 - y1 - s, z1, sc);
                 x[3 * h + 2] = fmul(y0 - y2 + s, z2, sc);
             }

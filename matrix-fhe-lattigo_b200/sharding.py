@@ -138,7 +138,13 @@ class ShardedKeySwitch:
     path then store their output into every rank's copy over NVLink from inside their last kernel
     (b200_intt_limbs_gather); what is left of the collectives is a one-word all-reduce per exchange that orders the
     peers' reads after the writes.  Those two barriers also protect the buffers against the next call (a rank cannot
-    pass barrier k before every rank has finished the work it queued ahead of barrier k)."""
+    pass barrier k before every rank has finished the work it queued ahead of barrier k).
+
+    Stream contract: the barrier is a torch.distributed all-reduce, which torch orders against torch's CURRENT stream,
+    while the library's kernels (gather transforms, DecomposeMac, ModDownLimbs) run on the ring's stream.  Every call of
+    gadget_product therefore binds the ring to torch.cuda.current_stream() first (draining the stream the ring was on
+    if it differs), so the peer stores of one stream are what the barrier waits for -- also under
+    `with torch.cuda.stream(s):`."""
 
     def __init__(self, ks, ring, batch, rank, world_size):
         import torch
@@ -154,6 +160,16 @@ class ShardedKeySwitch:
             everyone[0] = mine
         self._mapped = [[ring.OpenPeer(everyone[r][i]) for r in range(world_size) if r != rank] for i in range(3)]
         self._flag = torch.zeros(1, dtype=torch.int32, device="cuda:%d" % ring.device)
+        self._stream = None
+
+    def _bind_stream(self):
+        """Run the library's kernels on the stream the collectives are ordered against."""
+        import torch
+        cur = torch.cuda.current_stream(self.ring.device).cuda_stream
+        if cur != self._stream:
+            self.ring.Sync()               # whatever was queued on the ring's previous stream is complete before the switch
+            self.ring.SetStream(cur)
+            self._stream = cur
 
     def _barrier(self):
         if self.world > 1:
@@ -163,6 +179,7 @@ class ShardedKeySwitch:
     def gadget_product(self, levelQ, levelP, cx, key, out0, out1):
         """cx: owned Q limbs valid (NTT domain); out0/out1: the owned Q limbs receive the result."""
         ks, ring, LQ = self.ks, self.ring, self.ks.LQ
+        self._bind_stream()
         q0, q1 = block_of_rank(levelQ + 1, self.world, self.rank)
         p0, p1 = block_of_rank(levelP + 1, self.world, self.rank)
         ring.INTTLimbsGather(cx, self.cxinv, q0, q1 - q0, self._mapped[0])

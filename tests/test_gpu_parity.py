@@ -199,7 +199,7 @@ def test_3n_prototype_vectors_on_gpu():
         assert [int(t) for t in y.get()[0, 0]] == O.py_3n_ntt(N, v["p"], v["w"], v["coeffs"])
 
 
-@pytest.mark.parametrize("N", [12, 18, 24, 36, 48, 96, 192, 3 * 2**7, 9 * 2**6, 3 * 2**10, 3 * 2**11, 3 * 2**12, 3 * 2**13, 27 * 2**10])
+@pytest.mark.parametrize("N", [6, 12, 18, 24, 36, 48, 96, 192, 3 * 2**7, 9 * 2**6, 3 * 2**10, 3 * 2**11, 3 * 2**12, 3 * 2**13, 27 * 2**10])
 def test_3n_matches_oracle_roundtrip_product(N):
     moduli = O.find_3n_rns_primes(N, 60, 2)
     batch = 2
@@ -388,14 +388,23 @@ def test_transform_host_pipelined_chunks():
         assert (out == host).all()
 
 
-@pytest.mark.parametrize("env", [{"B200_GENERIC_COLS": "1"}, {"B200_NO_BIG": "1"}])
+# power-of-two NTT-friendly primes the fold arithmetic admits: 2^60 + c and 2^55 - c (QI60 are 2^61 - c: Shoup path)
+FOLD_POW2_PRIMES = [0x1000000000980001, 0x1000000000b00001, 0x7fffffff380001]
+
+
+@pytest.mark.parametrize("env", [{"B200_GENERIC_COLS": "1"}, {"B200_NO_BIG": "1"}, {"B200_NO_FOLD": "1"}, {"B200_FOLD_COLS": "0"},
+                                 {"B200_COLS_BAL": "0"}, {"B200_CW_BAL": "16"}])
 @pytest.mark.parametrize("shape", [("std", 1 << 16), ("std", 1 << 15), ("m3", 3 * 2**15), ("m3", 3 * 2**14),
-                                   ("std", 1 << 10), ("std", 1 << 11), ("m3", 3 * 2**10), ("m3", 3 * 2**11), ("m3", 3 * 2**16)])
+                                   ("std", 1 << 10), ("std", 1 << 11), ("m3", 3 * 2**10), ("m3", 3 * 2**11), ("m3", 3 * 2**16),
+                                   ("stdf", 1 << 16), ("stdf", 1 << 13)])
 def test_alternative_kernel_paths_agree(env, shape, monkeypatch):
-    """The generic column-pass family and the shape-agnostic fallback (resident / layered kernels) must give the
-    same words as the default path: the knobs are read at ring construction."""
+    """The generic column-pass family, the shape-agnostic fallback (resident / layered kernels), the Shoup kernels
+    (B200_NO_FOLD), the fold row pass behind Shoup columns (B200_FOLD_COLS=0) and the tiled / wide-tile fold column
+    kernels must give the same words as the default path: the knobs are read at ring construction."""
     kind, N = shape
-    moduli = QI60[:2] if kind == "std" else O.find_3n_rns_primes(N, 60, 2)
+    if kind != "m3" and set(env) & {"B200_COLS_BAL", "B200_CW_BAL"}:
+        pytest.skip("balanced column kernels exist for the 3N headline shape only")
+    moduli = QI60[:2] if kind == "std" else FOLD_POW2_PRIMES if kind == "stdf" else O.find_3n_rns_primes(N, 60, 2)
     host = rand_poly(77, 2, moduli, N)
     ref = b200ring.NewRing(N, moduli)
     a, want = ref.NewPoly(2).set(host), ref.NewPoly(2)
@@ -410,6 +419,35 @@ def test_alternative_kernel_paths_agree(env, shape, monkeypatch):
     assert (got.get() == host).all()
     sub = O.ThreeNSubRing(N, moduli[1]) if kind == "m3" else O.Pow2SubRing(N, moduli[1])
     assert (want.get()[1, 1] == sub.NTT(host[1, 1])).all()
+
+
+def test_fold_arithmetic_extreme_inputs_headline_shape():
+    """The fold kernels work on signed lazy words: all-(q-1), all-zero and alternating 0 / q-1 inputs drive the
+    windows of tools/fold_ranges.py to their ends; results must still be the oracle's words (3N headline shape and the
+    power-of-two shape on fold primes), forward and inverse."""
+    for kind, N, moduli in (("m3", 3 * 2**15, C3_PRIMES[-2:]), ("std", 1 << 16, FOLD_POW2_PRIMES[:2])):
+        r = b200ring.NewRing(N, moduli)
+        subs = [O.ThreeNSubRing(N, q) if kind == "m3" else O.Pow2SubRing(N, q) for q in moduli]
+        host = np.zeros((3, len(moduli), N), dtype=np.uint64)
+        for l, q in enumerate(moduli):
+            host[0, l, :] = q - 1
+            host[1, l, ::2] = q - 1
+            host[2, l, : N // 2] = q - 1
+        p, o = r.NewPoly(3).set(host), r.NewPoly(3)
+        r.NTT(p, o)
+        got = o.get()
+        for b in range(3):
+            for l in range(len(moduli)):
+                assert (got[b, l] == subs[l].NTT(host[b, l])).all(), (kind, b, l)
+        r.INTT(o, o)
+        assert (o.get() == host).all()
+        # the inverse transform of the same extreme words taken as NTT-domain input
+        o.set(host)
+        r.INTT(o, o)
+        back = o.get()
+        for b in range(3):
+            for l in range(len(moduli)):
+                assert (back[b, l] == subs[l].INTT(host[b, l])).all(), (kind, b, l)
 
 
 def test_3n_lazy_and_tree_order_flags_headline_shape():

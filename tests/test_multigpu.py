@@ -141,6 +141,16 @@ cxp = ring.NewPoly(batch).set(mine); f0, f1 = ring.NewPoly(batch), ring.NewPoly(
 for _ in range(3):                                                        # repeated calls reuse the mapped buffers
     fused.gadget_product(levelQ, levelP, cxp, key, f0, f1)
 assert (f0.get()[:, q0:q1] == w0.get()[:, q0:q1]).all() and (f1.get()[:, q0:q1] == w1.get()[:, q0:q1]).all(), "fused sharded result differs"
+# under a non-default torch stream: the barrier's all-reduce is ordered against THAT stream, so the fused path must move
+# the ring onto it (ShardedKeySwitch._bind_stream); back-to-back calls with no host synchronisation in between
+side = torch.cuda.Stream()
+f0.set(np.zeros_like(hcx)); f1.set(np.zeros_like(hcx)); ring.Sync()
+with torch.cuda.stream(side):
+    for _ in range(4):
+        fused.gadget_product(levelQ, levelP, cxp, key, f0, f1)
+side.synchronize()
+assert (f0.get()[:, q0:q1] == w0.get()[:, q0:q1]).all() and (f1.get()[:, q0:q1] == w1.get()[:, q0:q1]).all(), "fused result differs on a side stream"
+ring.SetStream(torch.cuda.current_stream().cuda_stream)
 fused.close()
 dist.barrier(); dist.destroy_process_group()
 os.write(1, ("rank" + str(rank) + "-ok\n").encode())

@@ -80,51 +80,41 @@ def check_word(v, what=""):
 
 
 # ---- forward radix-2 layers (Cooley-Tukey): U' = U + T - ku*q, V' = U - T + kv*q ------------------------------------
-FWD_PERIOD = 5
-FWD_PATTERN = [(1, 0), (0, 1), (1, 0), (0, 1), (1, 0)]   # (ku, kv) of the r-th layer after a fold (ntt_fold.cuh: fwd_ku / fwd_kv)
+FWD_PERIOD = 5   # ntt_fold.cuh: every FWD_PERIOD layers all words are folded; layer l recentres U (l % 5 even) or V (odd)
 
 
-def fwd_layers(w, n, r0=0, log=None, name=""):
-    for i in range(n):
-        ku, kv = FWD_PATTERN[r0 + i]
-        t = mul(w, "%s layer %d" % (name, r0 + i))
-        o0 = w + t - ku * Q
-        o1 = w - t + kv * Q
-        w = check_word(o0.union(o1), name)
-        if log is not None:
-            log.append("%s r=%d: %s" % (name, r0 + i, w))
-    return w
-
-
-# ---- inverse radix-2 layers (Gentleman-Sande): U' = U + V - ks*q, V' = (U - V)*w -----------------------------------------
-def inv_layer(ws, wp, ks, name=""):
-    """ws / wp: windows of the words that were sums / products in the previous layer (a pair is two of one kind)"""
-    outs, outp = None, None
-    for w in (ws, wp):
-        if w is None:
-            continue
-        d = w - w
-        t = mul(d, name)
-        s = check_word(w + w - ks * Q, name)
-        outs = s if outs is None else outs.union(s)
-        outp = t if outp is None else outp.union(t)
-    return outs, outp
-
-
-def rows_fwd(log=None):
-    """k_rows_fwd_f: fold_u at the load, layers 0-3, fold, layers 4-7, canonical reduction"""
-    w = fold_u()
-    w = fwd_layers(w, 4, 0, log, "rows_fwd a")
-    w = fold(w)
-    w = fwd_layers(w, 4, 0, log, "rows_fwd b")
-    assert w.mag() < S64 - Q, "canonical reduction needs |v| < 2^63 - q"
-    return w
-
-
-def inv_layers(ws, wp, n, l0=0, log=None, name=""):
-    """n Gentleman-Sande layers of ntt_fold.cuh inv_regs_f: the sums of odd layers are recentred by -q and folded"""
+def fwd_layers(w, l0, n, log=None, name=""):
+    """layers l0 .. l0+n-1 of fwd_regs_f / fwd_regs_fr (numbered across both passes)"""
     for l in range(l0, l0 + n):
-        ws, wp = inv_layer(ws, wp, l & 1, "%s layer %d" % (name, l))
+        r = l % FWD_PERIOD
+        if l > 0 and r == 0:
+            w = fold(w)
+        ku, kv = (1, 0) if r % 2 == 0 else (0, 1)
+        t = mul(w, "%s layer %d" % (name, l))
+        w = check_word((w + t - ku * Q).union(w - t + kv * Q), name)
+        if log is not None:
+            log.append("%s layer %d: %s" % (name, l, w))
+    return w
+
+
+def canon(w, what):
+    assert w.mag() < S64 - Q, "canonical reduction needs |v| < 2^63 - q (%s: %s)" % (what, w)
+    return Iv(0, Q)
+
+
+# ---- inverse radix-2 layers (Gentleman-Sande): U' = U + V - ks*q (folded in odd layers), V' = (U - V)*w ------------------
+def inv_layers(ws, wp, l0, n, log=None, name=""):
+    """ws / wp: windows of the words that were sums / products in the previous layer (a pair is two of one kind)"""
+    for l in range(l0, l0 + n):
+        outs, outp = None, None
+        for w in (ws, wp):
+            if w is None:
+                continue
+            t = mul(w - w, "%s layer %d" % (name, l))
+            sm = check_word(w + w - (l & 1) * Q, name)
+            outs = sm if outs is None else outs.union(sm)
+            outp = t if outp is None else outp.union(t)
+        ws, wp = outs, outp
         if l & 1:
             ws = fold(ws)
         if log is not None:
@@ -132,15 +122,74 @@ def inv_layers(ws, wp, n, l0=0, log=None, name=""):
     return ws, wp
 
 
-def rows_inv(log=None):
-    """k_rows_inv_f: fold_u at the load, 8 layers"""
-    ws, wp = inv_layers(fold_u(), None, 8, 0, log, "rows_inv")
-    return ws.union(wp)
+def forward_3n(log=None, radix2_layers=14):
+    """k_cols_fwd_m3_15_{f,b} + k_rows_fwd_f: caller's words below 4 * 2^k (contract: below 2q); cyclotomic layer, radix-3 layer (outputs folded),
+    radix-2 layers 0..13, canonical reduction"""
+    w = Iv(0, 4)
+    tt = mul(w, "cyclotomic")
+    lo = check_word(w + tt - Q, "cyclotomic lo")
+    hi = check_word(w + w - tt - 2 * Q, "cyclotomic hi")
+    x = lo.union(hi)
+    b0 = fold(x)
+    t1 = mul(x, "radix-3 t1")
+    t3 = mul(t1 - t1, "radix-3 t3")
+    out = fold(check_word((b0 + t1 + t1).union(b0 - t1 + t3).union(b0 - t1 - t3), "radix-3"))
+    if log is not None:
+        log.append("forward 3N after the radix-3 layer: %s" % out)
+    w = fwd_layers(out, 0, radix2_layers, log, "forward 3N")
+    return canon(w, "forward 3N")
+
+
+def forward_std(log=None, layers=16):
+    """k_cols_fwd_std16_f + k_rows_fwd_f: caller's words below 2.5 * 2^k (the reference's transforms take words below
+    2q, ring/ntt.go:155-171), layers 0..15 with the first fold before layer 5, canonical reduction"""
+    w = fwd_layers(Iv(0, F(5, 2)), 0, layers, log, "forward 2^16")
+    return canon(w, "forward 2^16")
+
+
+def rows_fwd_after_shoup(log=None):
+    """k_rows_fwd_f<.., -1>: the Shoup column pass left unsigned words below 8q: fold_u at the load, layers 0..7"""
+    return canon(fwd_layers(fold_u(), 0, 8, log, "rows after Shoup columns"), "rows after Shoup columns")
+
+
+def inverse_3n(log=None):
+    """k_rows_inv_f + k_cols_inv_m3_15_{f,b}: fold_u of any input word, radix-2 layers 0..13, inverse radix-3 layer,
+    inverse cyclotomic layer in its two-product form (hh = k1 (lo - hi), ll = k4 (lo + hi) - hh / 2), canonical"""
+    ws, wp = inv_layers(fold_u(), None, 0, 14, log, "inverse 3N")
+    y = ws.union(wp)
+    sg = mul(y - y, "inverse radix-3 s")
+    x0 = fold(check_word(y + y + y, "inverse radix-3 x0"))          # folded: lo + hi below must stay a valid multiplicand
+    x12 = mul(check_word(y - y - sg, "inverse radix-3 operand"), "inverse radix-3 x1, x2")
+    x = x0.union(x12)
+    hh = mul(check_word(x - x, "inverse cyclotomic lo - hi"), "inverse cyclotomic hh")
+    half = Iv((hh.lo - Q) / 2, (hh.hi + Q) / 2)                      # sol_half: (v + q) >> 1 for odd v
+    ll = check_word(mul(check_word(x + x, "inverse cyclotomic lo + hi"), "inverse cyclotomic ll") - half, "inverse cyclotomic ll")
+    if log is not None:
+        log.append("inverse 3N: x0 %s, products %s, ll %s, hh %s" % (x0, x12, ll, hh))
+    canon(ll, "inverse 3N ll")
+    return canon(hh, "inverse 3N hh")
+
+
+def inverse_std(log=None):
+    """k_rows_inv_f + k_cols_inv_std16_f: layers 0..14, then the last layer carries N^-1 on both outputs"""
+    ws, wp = inv_layers(fold_u(), None, 0, 15, log, "inverse 2^16")
+    w = ws.union(wp)
+    out = mul(check_word(w + w, "last layer sum"), "last layer").union(mul(w - w, "last layer difference"))
+    return canon(out, "inverse 2^16")
+
+
+def rows_inv_to_shoup(log=None):
+    """k_rows_inv_f<.., false>: 8 layers, then + q so that the Shoup column pass sees unsigned words below 4q"""
+    ws, wp = inv_layers(fold_u(), None, 0, 8, log, "rows before Shoup columns")
+    w = ws.union(wp) + Q
+    assert w.lo >= 0 and w.hi < 4 * Q, w
+    return w
 
 
 def check_all():
     log = []
-    out = {"rows_fwd": rows_fwd(log), "rows_inv": rows_inv(log)}
+    out = {"forward_3n": forward_3n(log), "inverse_3n": inverse_3n(log), "forward_std": forward_std(log), "inverse_std": inverse_std(log),
+           "rows_fwd_after_shoup": rows_fwd_after_shoup(log), "rows_inv_to_shoup": rows_inv_to_shoup(log)}
     return out, log
 
 
