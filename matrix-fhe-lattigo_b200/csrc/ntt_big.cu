@@ -1183,9 +1183,15 @@ int launch_polymul_big(b200_ctx *ctx, const u64 *pa, const u64 *pb, u64 *pc, Spa
     const int flags = matrix ? B200_TREE_ORDER : 0;
     BigArgs a{ctx->d_consts, ctx->d_fwd, ctx->d_inv, ctx->d_misc, N, R, matrix ? ctx->a - 9 : 0, sp, 0, flags, 0, 0};
     a.div_magic = unit_div_magic(sp);
-    const kern_t cf = plan->cols_fwd, ci = plan->cols_inv;
-    auto col_smem_of = [R](int cw) { const int rows_total = R * cw; return (size_t)(rows_total + ((rows_total >> 6) << 3) + 8) * sizeof(u64); };
-    const size_t smem_f = col_smem_of(plan->cw_fwd), smem_i = col_smem_of(plan->cw_inv);
+    a.sol = ctx->d_sol; a.fwd_s = ctx->d_fwd_s; a.inv_s = ctx->d_inv_s; a.misc_s = ctx->d_misc_s;
+    // fold arithmetic end to end when the ring qualifies: fold column kernels on both sides of k_rows_mul_f
+    const bool fold = ctx->fold_ok && plan->fold_rows && plan->fold_cols && plan->cols_fwd_f && plan->cols_inv_f && env_int("B200_FOLD_MUL", 1);
+    const kern_t cf = fold ? plan->cols_fwd_f : plan->cols_fwd, ci = fold ? plan->cols_inv_f : plan->cols_inv;
+    const bool bal = fold && plan->bal;
+    const int cwf = bal ? plan->cw_bal : plan->cw_fwd, cwi = bal ? plan->cw_bal : plan->cw_inv;
+    const int thr_f = bal ? cwf * 16 : plan->col_threads_fwd, thr_i = bal ? cwi * 16 : plan->col_threads_inv;
+    auto col_smem_of = [R, bal](int cw) { const int rows_total = R * cw; return (bal ? (size_t)rows_total : (size_t)(rows_total + ((rows_total >> 6) << 3) + 8)) * sizeof(u64); };
+    const size_t smem_f = col_smem_of(cwf), smem_i = col_smem_of(cwi);
     const size_t row_smem = (size_t)4 * WROW * sizeof(u64);
     if (int rc = set_smem(cf, smem_f)) return rc;
     if (int rc = set_smem(ci, smem_i)) return rc;
@@ -1194,7 +1200,7 @@ int launch_polymul_big(b200_ctx *ctx, const u64 *pa, const u64 *pb, u64 *pc, Spa
     const int chunk = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(budget / ((size_t)N * sizeof(u64)), 65535), (size_t)units));
     if (int rc = b200_ensure_scratch(ctx, (size_t)2 * chunk * N)) return rc;
     u64 *ta = ctx->d_scratch, *tb = ctx->d_scratch + (size_t)chunk * N;
-    const int tiles_f = 256 / plan->cw_fwd, tiles_i = 256 / plan->cw_inv, row_tiles = R / 4;
+    const int tiles_f = 256 / cwf, tiles_i = 256 / cwi, row_tiles = R / 4;
     cudaStream_t st = b200_cur_stream(ctx);
     for (int u0 = 0; u0 < units; u0 += chunk) {
         const int nu = std::min(chunk, units - u0);
@@ -1205,13 +1211,15 @@ int launch_polymul_big(b200_ctx *ctx, const u64 *pa, const u64 *pb, u64 *pc, Spa
         from_dense.in_dense = 1;
         const dim3 gf(tiles_f, nu), gi(tiles_i, nu);
         { LaunchScope ls(ctx, matrix ? "cols_fwd_m3" : "cols_fwd_std", nu);
-          cf<<<gf, plan->col_threads_fwd, smem_f, st>>>(pa, ta, to_dense); }
+          cf<<<gf, thr_f, smem_f, st>>>(pa, ta, to_dense); }
         { LaunchScope ls(ctx, matrix ? "cols_fwd_m3" : "cols_fwd_std", nu);
-          cf<<<gf, plan->col_threads_fwd, smem_f, st>>>(pb, tb, to_dense); }
+          cf<<<gf, thr_f, smem_f, st>>>(pb, tb, to_dense); }
         { LaunchScope ls(ctx, "rows_mul", nu);
-          k_rows_mul<<<dim3(nu, row_tiles), 128, row_smem, st>>>(ta, tb, dense); }
+          if (!fold) k_rows_mul<<<dim3(nu, row_tiles), 128, row_smem, st>>>(ta, tb, dense);
+          else if (matrix) k_rows_mul_f<M3_15_ROW_L0><<<dim3(nu, row_tiles), 128, row_smem, st>>>(ta, tb, dense);
+          else k_rows_mul_f<STD16_ROW_L0><<<dim3(nu, row_tiles), 128, row_smem, st>>>(ta, tb, dense); }
         { LaunchScope ls(ctx, matrix ? "cols_inv_m3" : "cols_inv_std", nu);
-          ci<<<gi, plan->col_threads_inv, smem_i, st>>>(ta, pc, from_dense); }
+          ci<<<gi, thr_i, smem_i, st>>>(ta, pc, from_dense); }
     }
     CUDA_TRY(cudaGetLastError());
     return 0;

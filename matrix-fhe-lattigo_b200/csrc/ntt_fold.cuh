@@ -269,6 +269,41 @@ k_rows_inv_f(const u64 *in, u64 *out, BigArgs a) {
     }
 }
 
+// Fused row stage of the ring product on the fold arithmetic (k_rows_mul of ntt_big.cu): both operands arrive from a fold
+// column pass (signed words, layers 0..L0-1 done), run the 8 forward row layers, are brought to [0, q) and multiplied
+// (Barrett, canonical), and the product runs the 8 inverse row layers; signed words go on to the fold inverse column pass.
+template <int L0>
+__global__ void __launch_bounds__(128, B200_MINB_ROWS_MUL)
+k_rows_mul_f(u64 *ta, const u64 *tb, BigArgs a) {
+    extern __shared__ __align__(16) u64 sm[];
+    const UnitRef ur = unit_ref(a);
+    const int limb = ur.limb;
+    const LimbConst lc = a.consts[limb];
+    const SolConst sc = a.sol[limb];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int r = blockIdx.y * 4 + w;
+    const stw_t *__restrict__ twr = a.fwd_s + (size_t)limb * a.N + a.R + 255 * r;
+    const stw_t *__restrict__ twri = a.inv_s + (size_t)limb * a.N + a.R + 255 * r;
+    u64 *buf = sm + w * WROW;
+    u64 *pa = ta + ur.in + (size_t)r * 256;
+    const u64 *pb = tb + ur.in + (size_t)r * 256;
+    s64 x[8], y[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = (s64)pa[k * 32 + lane];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) y[k] = (s64)pb[k * 32 + lane];
+    row_fwd_core_f<L0>(x, buf, lane, twr, sc);
+    row_fwd_core_f<L0>(y, buf, lane, twr, sc);
+    u64 cx[8], cy[8];
+    sol_canon_n(cx, x, sc);
+    sol_canon_n(cy, y, sc);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = (s64)bred(cx[k], cy[k], lc.q, lc.brc_hi, lc.brc_lo);
+    row_inv_core_f(x, buf, lane, twri, sc);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) pa[k * 32 + lane] = (u64)x[k];
+}
+
 // ====================================================================================================
 // column pass on the fold arithmetic: the hand-tuned headline shapes (same tiling as k_cols_*_m3_15 / k_cols_*_std16).
 // Inputs of the forward kernels are the caller's words, taken as they are.  Contract: below 2q, what the reference's
