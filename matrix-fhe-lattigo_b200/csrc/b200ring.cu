@@ -196,6 +196,33 @@ static void build_matrix(b200_ctx *ctx, int i, std::vector<tw_t> &fwd, std::vect
     misc[MISC_K4] = mk_tw(hm::invmod_prime((u64)N % q, q), q);
 }
 
+// Row-pass order of a twiddle table (the row kernels of ntt_big.cu / ntt_fold.cuh): the 255 twiddles of the subtree under row
+// node R + r (R = N/256) move to the block [R + 255 r, R + 255 (r + 1)) in the order the lanes load them -- 7 entries of the
+// first register group (warp-uniform), 7 runs of 8 entries (second group, indexed by lane & 7), 6 runs of 32 entries (third
+// group, indexed by lane) -- so that one load instruction of a warp reads consecutive entries instead of a strided set
+// (L1 data-pipe wavefronts were the busiest resource of the row kernels).  Heap indices below R, all the column pass uses,
+// stay where they are.
+template <typename T>
+static void row_pass_order(std::vector<T> &t, int L, int N) {
+    const int R = N / 256;
+    std::vector<T> o(t);
+    for (int i = 0; i < L; ++i) {
+        const T *src = &t[(size_t)i * N];
+        T *dst = &o[(size_t)i * N];
+        for (int h = R; h < N; ++h) {
+            int d = 0;
+            while ((h >> d) >= 2 * R) ++d;
+            const int r = (h >> d) - R, k = h & ((1 << d) - 1);
+            int off;
+            if (d < 3) off = (1 << d) - 1 + k;
+            else if (d < 6) { const int j = d - 3, hi3 = k >> j, g = k & ((1 << j) - 1); off = 7 + ((1 << j) - 1 + g) * 8 + hi3; }
+            else { const int j = d - 6, sub = k >> j, g = k & ((1 << j) - 1), lane = sub >> 1, s2 = sub & 1; off = 63 + (s2 * 3 + (1 << j) - 1 + g) * 32 + lane; }
+            dst[R + 255 * r + off] = src[h];
+        }
+    }
+    t.swap(o);
+}
+
 // ---- fold arithmetic tables (solinas.cuh) ---------------------------------------------------------------
 // q = 2^k + c with the smallest |c|
 static void fold_shape(u64 q, int *k, long long *c) {
@@ -255,31 +282,9 @@ static cudaError_t fold_setup(b200_ctx *ctx, const std::vector<tw_t> &fwd, const
     };
     std::vector<stw_t> f, v, m;
     if (!conv(fwd, (size_t)ctx->N, f) || !conv(inv, (size_t)ctx->N, v) || !conv(misc, (size_t)MISC_COUNT, m)) return cudaSuccess;
-    // Row-pass order (ntt_fold.cuh, row_tw_offset): the 255 twiddles of the subtree under row node R + r move to the block
-    // [R + 255 r, R + 255 (r + 1)) in the order the lanes of the row kernels load them, so that one load instruction of a warp
-    // reads consecutive entries.  Heap indices below R (all the column pass uses) stay where they are.
     if (ctx->N >= 512 && ctx->N % 256 == 0) {
-        const int N = ctx->N, R = N / 256;
-        auto reorder = [&](std::vector<stw_t> &t) {
-            std::vector<stw_t> o(t);
-            for (int i = 0; i < L; ++i) {
-                const stw_t *src = &t[(size_t)i * N];
-                stw_t *dst = &o[(size_t)i * N];
-                for (int h = R; h < N; ++h) {
-                    int d = 0;
-                    while ((h >> d) >= 2 * R) ++d;
-                    const int r = (h >> d) - R, k = h & ((1 << d) - 1);
-                    int off;
-                    if (d < 3) off = (1 << d) - 1 + k;
-                    else if (d < 6) { const int j = d - 3, hi3 = k >> j, g = k & ((1 << j) - 1); off = 7 + ((1 << j) - 1 + g) * 8 + hi3; }
-                    else { const int j = d - 6, sub = k >> j, g = k & ((1 << j) - 1), lane = sub >> 1, s2 = sub & 1; off = 63 + (s2 * 3 + (1 << j) - 1 + g) * 32 + lane; }
-                    dst[R + 255 * r + off] = src[h];
-                }
-            }
-            t.swap(o);
-        };
-        reorder(f);
-        reorder(v);
+        row_pass_order(f, L, ctx->N);
+        row_pass_order(v, L, ctx->N);
     }
     auto up = [&](void **dst, const void *src, size_t bytes) -> cudaError_t {
         cudaError_t e = cudaMalloc(dst, bytes);
@@ -419,6 +424,12 @@ extern "C" int b200_ctx_create(int ring_type, int N, int L, const uint64_t *modu
         e = up((void **)&ctx->d_go2fast, go2fast.data(), sizeof(int) * N);
     }
     if (e == cudaSuccess) e = fold_setup(ctx, fwd, inv, misc);
+    if (e == cudaSuccess && N >= 512 && N % 256 == 0) {   // shapes the two-pass kernels may cover: row-pass copies of the Shoup tables
+        row_pass_order(fwd, L, N);
+        row_pass_order(inv, L, N);
+        e = up((void **)&ctx->d_fwd_r, fwd.data(), sizeof(tw_t) * fwd.size());
+        if (e == cudaSuccess) e = up((void **)&ctx->d_inv_r, inv.data(), sizeof(tw_t) * inv.size());
+    }
     if (e != cudaSuccess) { b200_ctx_destroy(ctx); return b200_cuda_fail(e, "context table upload"); }
     int rc = big_tables_create(ctx);
     if (rc < 0) { b200_ctx_destroy(ctx); return rc; }
@@ -430,7 +441,7 @@ extern "C" void b200_ctx_destroy(b200_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     big_tables_destroy(ctx);
-    cudaFree(ctx->d_consts); cudaFree(ctx->d_fwd); cudaFree(ctx->d_inv); cudaFree(ctx->d_misc);
+    cudaFree(ctx->d_consts); cudaFree(ctx->d_fwd); cudaFree(ctx->d_inv); cudaFree(ctx->d_misc); cudaFree(ctx->d_fwd_r); cudaFree(ctx->d_inv_r);
     cudaFree(ctx->d_sol); cudaFree(ctx->d_fwd_s); cudaFree(ctx->d_inv_s); cudaFree(ctx->d_misc_s);
     cudaFree(ctx->d_go2fast); cudaFree(ctx->d_scratch); cudaFree(ctx->d_ws); cudaFree(ctx->d_rescale); cudaFree(ctx->d_index);
     if (ctx->pipe.ready) {

@@ -139,6 +139,7 @@ struct BigArgs {
     // fold arithmetic (ntt_fold.cuh): per-prime constants and tables
     const SolConst *sol;
     const stw_t *fwd_s, *inv_s, *misc_s;
+    const tw_t *fwd_r, *inv_r;   // copies of fwd / inv with the entries the row pass reads in row-pass order (b200ring.cu)
 };
 
 // word offsets of this CTA's unit in the input and output buffers, and its prime
@@ -220,14 +221,26 @@ __device__ __forceinline__ u64 mul2q(u64 x, const tw_t w, const QC &c) {
 #ifndef B200_FWD_SIGNED_CHAIN
 #define B200_FWD_SIGNED_CHAIN 1
 #endif
-template <int LOGM, int MODE = B200_CSUB_FWD_ROWS>
-__device__ __forceinline__ void fwd_regs(u64 (&x)[1 << LOGM], unsigned P, const tw_t *__restrict__ tw, const QC &c) {
+// Where a register group finds the twiddle of level j, block g: heap order (table[(P << j) + g], the column pass and the
+// generic kernels) or the row-pass order of the second table copy (b200ring.cu row_pass_order: base[((1 << j) - 1 + g) * STRIDE],
+// consecutive lanes of a warp read consecutive entries).
+struct TwHeap {
+    const tw_t *__restrict__ tw; unsigned P;
+    __device__ __forceinline__ tw_t operator()(int j, int g) const { return tw[(P << j) + g]; }
+};
+template <int STRIDE>
+struct TwRow {
+    const tw_t *__restrict__ base;
+    __device__ __forceinline__ tw_t operator()(int j, int g) const { return base[((1 << j) - 1 + g) * STRIDE]; }
+};
+template <int LOGM, int MODE, class TW>
+__device__ __forceinline__ void fwd_regs_t(u64 (&x)[1 << LOGM], const TW tw, const QC &c) {
 #pragma unroll
     for (int j = 0; j < LOGM; ++j) {
         const int half = (1 << LOGM) >> (j + 1);
 #pragma unroll
         for (int g = 0; g < (1 << j); ++g) {
-            const tw_t w = tw[(P << j) + g];
+            const tw_t w = tw(j, g);
 #pragma unroll
             for (int o = 0; o < half; ++o) {
                 if (MODE == 2 && B200_FWD_SIGNED_CHAIN) {
@@ -246,18 +259,26 @@ __device__ __forceinline__ void fwd_regs(u64 (&x)[1 << LOGM], unsigned P, const 
         }
     }
 }
-template <int LOGM, int JMIN = 0, int MODE = B200_CSUB_INV_ROWS>
-__device__ __forceinline__ void inv_regs(u64 (&x)[1 << LOGM], unsigned P, const tw_t *__restrict__ tw, const QC &c) {
+template <int LOGM, int MODE = B200_CSUB_FWD_ROWS>
+__device__ __forceinline__ void fwd_regs(u64 (&x)[1 << LOGM], unsigned P, const tw_t *__restrict__ tw, const QC &c) {
+    fwd_regs_t<LOGM, MODE>(x, TwHeap{tw, P}, c);
+}
+template <int LOGM, int JMIN, int MODE, class TW>
+__device__ __forceinline__ void inv_regs_t(u64 (&x)[1 << LOGM], const TW tw, const QC &c) {
 #pragma unroll
     for (int j = LOGM - 1; j >= JMIN; --j) {
         const int half = (1 << LOGM) >> (j + 1);
 #pragma unroll
         for (int g = 0; g < (1 << j); ++g) {
-            const tw_t w = tw[(P << j) + g];
+            const tw_t w = tw(j, g);
 #pragma unroll
             for (int o = 0; o < half; ++o) bf_inv<MODE>(x[g * 2 * half + o], x[g * 2 * half + o + half], w, c);
         }
     }
+}
+template <int LOGM, int JMIN = 0, int MODE = B200_CSUB_INV_ROWS>
+__device__ __forceinline__ void inv_regs(u64 (&x)[1 << LOGM], unsigned P, const tw_t *__restrict__ tw, const QC &c) {
+    inv_regs_t<LOGM, JMIN, MODE>(x, TwHeap{tw, P}, c);
 }
 
 #ifndef B200_STREAM_DATA
@@ -329,35 +350,17 @@ __device__ __forceinline__ int row_of(const BigArgs &a, int tile, int w, int &ro
     return (hd << a.logU) + u;
 }
 
-#ifndef B200_TW_PREFETCH
-#define B200_TW_PREFETCH 0
-#endif
-// Warm L1 with the twiddles of groups 2 and 3 of row node P1 (heap order: level k of the row's subtree is the
-// contiguous run tw[P1*2^k, (P1+1)*2^k)): 31 lines of 128 B, one per lane, requested while the row's data loads are
-// still in flight so that the later, dependent twiddle loads hit L1 instead of waiting on L2.
-__device__ __forceinline__ void prefetch_row_twiddles(const tw_t *__restrict__ tw, unsigned P1, int lane) {
-#if B200_TW_PREFETCH
-    // lines (8 entries of 16 B each): level 3: 1, level 4: 2, level 5: 4, level 6: 8, level 7: 16
-    const int lvl = lane < 1 ? 3 : lane < 3 ? 4 : lane < 7 ? 5 : lane < 15 ? 6 : 7;
-    const int line = lane - ((1 << (lvl - 3)) - 1);
-    if (lane < 31) {
-        const tw_t *p = tw + ((size_t)P1 << lvl) + (size_t)line * 8;
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-    }
-#endif
-}
-
 // The 8 layers of one 256-word row held by one warp (x[k]: 8 words per lane, buf: the warp's exchange buffer).
 // forward: in  c = k*32 + lane  (values < 8q)  ->  out c = lane*8 + k  (values < 8q)
-__device__ __forceinline__ void row_fwd_core(u64 (&x)[8], u64 *buf, int lane, unsigned P1, const tw_t *__restrict__ tw, const QC &qc) {
-    fwd_regs<3>(x, P1, tw, qc);
+__device__ __forceinline__ void row_fwd_core(u64 (&x)[8], u64 *buf, int lane, const tw_t *__restrict__ twr, const QC &qc) {
+    fwd_regs_t<3, B200_CSUB_FWD_ROWS>(x, TwRow<1>{twr}, qc);
 #pragma unroll
     for (int k = 0; k < 8; ++k) buf[pad16(k * 32 + lane)] = x[k];
     __syncwarp();
     const int hi3 = lane & 7, lo2 = lane >> 3;
 #pragma unroll
     for (int k = 0; k < 8; ++k) x[k] = buf[pad16(hi3 * 32 + k * 4 + lo2)];
-    fwd_regs<3>(x, P1 * 8 + hi3, tw, qc);
+    fwd_regs_t<3, B200_CSUB_FWD_ROWS>(x, TwRow<8>{twr + 7 + hi3}, qc);
     __syncwarp();
 #pragma unroll
     for (int k = 0; k < 8; ++k) buf[pad16(hi3 * 32 + k * 4 + lo2)] = x[k];
@@ -366,17 +369,17 @@ __device__ __forceinline__ void row_fwd_core(u64 (&x)[8], u64 *buf, int lane, un
     for (int k = 0; k < 8; ++k) x[k] = buf[pad16(lane * 8 + k)];
     u64 (&lo)[4] = *reinterpret_cast<u64 (*)[4]>(&x[0]);
     u64 (&hi)[4] = *reinterpret_cast<u64 (*)[4]>(&x[4]);
-    fwd_regs<2>(lo, P1 * 64 + lane * 2, tw, qc);
-    fwd_regs<2>(hi, P1 * 64 + lane * 2 + 1, tw, qc);
+    fwd_regs_t<2, B200_CSUB_FWD_ROWS>(lo, TwRow<32>{twr + 63 + lane}, qc);
+    fwd_regs_t<2, B200_CSUB_FWD_ROWS>(hi, TwRow<32>{twr + 63 + 96 + lane}, qc);
     __syncwarp();   // the buffer may be reused by the caller
 }
 // inverse: in  c = lane*8 + k  (values < 4q)  ->  out c = k*32 + lane  (values < 4q)
-__device__ __forceinline__ void row_inv_core(u64 (&x)[8], u64 *buf, int lane, unsigned P1, const tw_t *__restrict__ tw, const QC &qc) {
+__device__ __forceinline__ void row_inv_core(u64 (&x)[8], u64 *buf, int lane, const tw_t *__restrict__ twr, const QC &qc) {
     {
         u64 (&lo)[4] = *reinterpret_cast<u64 (*)[4]>(&x[0]);
         u64 (&hi)[4] = *reinterpret_cast<u64 (*)[4]>(&x[4]);
-        inv_regs<2>(lo, P1 * 64 + lane * 2, tw, qc);
-        inv_regs<2>(hi, P1 * 64 + lane * 2 + 1, tw, qc);
+        inv_regs_t<2, 0, B200_CSUB_INV_ROWS>(lo, TwRow<32>{twr + 63 + lane}, qc);
+        inv_regs_t<2, 0, B200_CSUB_INV_ROWS>(hi, TwRow<32>{twr + 63 + 96 + lane}, qc);
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k) buf[pad16(lane * 8 + k)] = x[k];
@@ -384,14 +387,14 @@ __device__ __forceinline__ void row_inv_core(u64 (&x)[8], u64 *buf, int lane, un
     const int hi3 = lane & 7, lo2 = lane >> 3;
 #pragma unroll
     for (int k = 0; k < 8; ++k) x[k] = buf[pad16(hi3 * 32 + k * 4 + lo2)];
-    inv_regs<3>(x, P1 * 8 + hi3, tw, qc);
+    inv_regs_t<3, 0, B200_CSUB_INV_ROWS>(x, TwRow<8>{twr + 7 + hi3}, qc);
     __syncwarp();
 #pragma unroll
     for (int k = 0; k < 8; ++k) buf[pad16(hi3 * 32 + k * 4 + lo2)] = x[k];
     __syncwarp();
 #pragma unroll
     for (int k = 0; k < 8; ++k) x[k] = buf[pad16(k * 32 + lane)];
-    inv_regs<3>(x, P1, tw, qc);
+    inv_regs_t<3, 0, B200_CSUB_INV_ROWS>(x, TwRow<1>{twr}, qc);
 }
 
 template <bool MATRIX, int VT>   // warps per CTA: MATRIX 6*VT, STANDARD VT
@@ -402,18 +405,16 @@ k_rows_fwd(const u64 *in, u64 *out, BigArgs a) {
     const UnitRef ur = unit_ref(a);
     const int limb = ur.limb;
     const QC qc(a.consts[limb]);
-    const tw_t *__restrict__ tw = a.fwd + (size_t)limb * a.N;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     int rowcode;
     const int r = row_of<MATRIX, VT>(a, blockIdx.y, w, rowcode);
     u64 *buf = sm + w * WROW;
     const u64 *src = in + ur.in + (size_t)r * 256;
-    const unsigned P1 = (unsigned)(a.R + r);
-    prefetch_row_twiddles(tw, P1, lane);
+    const tw_t *__restrict__ twr = a.fwd_r + (size_t)limb * a.N + a.R + 255 * r;
     u64 x[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) x[k] = ldd(src + k * 32 + lane);
-    row_fwd_core(x, buf, lane, P1, tw, qc);
+    row_fwd_core(x, buf, lane, twr, qc);
 #pragma unroll
     for (int k = 0; k < 8; ++k) x[k] = (a.flags & B200_LAZY) ? csub(x[k], qc.fourq) : canon8<(MATRIX ? B200_CANON_FINAL_M3 : B200_CANON_FINAL_STD)>(x[k], qc);   // lazy: [0,4q) <= 6q-2
     if (!MATRIX || (a.flags & B200_TREE_ORDER)) {
@@ -449,13 +450,11 @@ k_rows_inv(const u64 *in, u64 *out, BigArgs a) {
     const UnitRef ur = unit_ref(a);
     const int limb = ur.limb;
     const QC qc(a.consts[limb]);
-    const tw_t *__restrict__ tw = a.inv + (size_t)limb * a.N;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     int rowcode;
     const int r = row_of<MATRIX, VT>(a, blockIdx.y, w, rowcode);
     u64 *buf = sm + w * WROW;
-    const unsigned P1 = (unsigned)(a.R + r);
-    prefetch_row_twiddles(tw, P1, lane);
+    const tw_t *__restrict__ twr = a.inv_r + (size_t)limb * a.N + a.R + 255 * r;
     u64 x[8];
     if (!MATRIX || (a.flags & B200_TREE_ORDER)) {
         const u64 *src = in + ur.in + (size_t)r * 256 + lane * 8;
@@ -481,7 +480,7 @@ k_rows_inv(const u64 *in, u64 *out, BigArgs a) {
         for (int k = 0; k < 8; ++k) x[k] = sm[stage_row<RUN>((int)rev_bits((unsigned)k, 3) * 32 + rl) + rowcode];
         __syncthreads();
     }
-    row_inv_core(x, buf, lane, P1, tw, qc);
+    row_inv_core(x, buf, lane, twr, qc);
     u64 *dst = out + ur.out + (size_t)r * 256;
 #pragma unroll
     for (int k = 0; k < 8; ++k) std_(dst + k * 32 + lane, x[k]);
@@ -498,11 +497,10 @@ k_rows_mul(u64 *ta, const u64 *tb, BigArgs a) {
     const int limb = ur.limb;
     const LimbConst lc = a.consts[limb];
     const QC qc(lc);
-    const tw_t *__restrict__ tw = a.fwd + (size_t)limb * a.N, *__restrict__ twi = a.inv + (size_t)limb * a.N;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int r = blockIdx.y * 4 + w;
     u64 *buf = sm + w * WROW;
-    const unsigned P1 = (unsigned)(a.R + r);
+    const tw_t *__restrict__ twr = a.fwd_r + (size_t)limb * a.N + a.R + 255 * r, *__restrict__ twri = a.inv_r + (size_t)limb * a.N + a.R + 255 * r;
     u64 *pa = ta + ur.in + (size_t)r * 256;
     const u64 *pb = tb + ur.in + (size_t)r * 256;
     u64 x[8], y[8];
@@ -510,12 +508,12 @@ k_rows_mul(u64 *ta, const u64 *tb, BigArgs a) {
     for (int k = 0; k < 8; ++k) x[k] = pa[k * 32 + lane];
 #pragma unroll
     for (int k = 0; k < 8; ++k) y[k] = pb[k * 32 + lane];
-    row_fwd_core(x, buf, lane, P1, tw, qc);
-    row_fwd_core(y, buf, lane, P1, tw, qc);
+    row_fwd_core(x, buf, lane, twr, qc);
+    row_fwd_core(y, buf, lane, twr, qc);
 #pragma unroll
     for (int k = 0; k < 8; ++k)   // canonical operands -> Barrett product in [0, 2q)
         x[k] = bred_lazy(canon8(x[k], qc), canon8(y[k], qc), lc.q, lc.brc_hi, lc.brc_lo);
-    row_inv_core(x, buf, lane, P1, twi, qc);
+    row_inv_core(x, buf, lane, twri, qc);
 #pragma unroll
     for (int k = 0; k < 8; ++k) pa[k * 32 + lane] = x[k];
 }
@@ -1084,6 +1082,7 @@ int big_tables_create(b200_ctx *ctx) {
     const bool generic = env_int("B200_GENERIC_COLS", 0) != 0;
     if (!matrix) plan->covered = ctx->logN >= 10 && ctx->logN <= 17 && pick_col_kernels(plan, false, ctx->logN - 8, generic);
     else plan->covered = ctx->b == 1 && ctx->a >= 10 && ctx->a <= 16 && pick_col_kernels(plan, true, ctx->a - 9, generic);
+    if (!ctx->d_fwd_r || !ctx->d_inv_r) plan->covered = false;   // the row kernels read the row-pass copies of the tables
     plan->fold_rows = env_int("B200_FOLD_ROWS", 1) != 0;
     plan->fold_cols = env_int("B200_FOLD_COLS", 1) != 0;
     plan->vt = B200_VT_M3;   // 16-column tiles and 4-v row tiles were measured slower on B200 (fewer resident CTAs)
@@ -1115,6 +1114,7 @@ int launch_ntt_big(b200_ctx *ctx, const u64 *in, u64 *out, Span sp, bool inverse
     BigArgs a{ctx->d_consts, ctx->d_fwd, ctx->d_inv, ctx->d_misc, N, R, matrix ? ctx->a - 9 : 0, sp, 0, flags, 0, 0};
     a.div_magic = unit_div_magic(sp);
     a.sol = ctx->d_sol; a.fwd_s = ctx->d_fwd_s; a.inv_s = ctx->d_inv_s; a.misc_s = ctx->d_misc_s;
+    a.fwd_r = ctx->d_fwd_r; a.inv_r = ctx->d_inv_r;
     kern_t ck = inverse ? (gather ? plan->cols_inv_gather : plan->cols_inv) : plan->cols_fwd;
     if (fold_cols) ck = inverse ? (gather ? plan->cols_inv_gather_f : plan->cols_inv_f) : plan->cols_fwd_f;
     int col_threads = inverse ? (gather ? plan->col_threads_gather : plan->col_threads_inv) : plan->col_threads_fwd;
@@ -1184,6 +1184,7 @@ int launch_polymul_big(b200_ctx *ctx, const u64 *pa, const u64 *pb, u64 *pc, Spa
     BigArgs a{ctx->d_consts, ctx->d_fwd, ctx->d_inv, ctx->d_misc, N, R, matrix ? ctx->a - 9 : 0, sp, 0, flags, 0, 0};
     a.div_magic = unit_div_magic(sp);
     a.sol = ctx->d_sol; a.fwd_s = ctx->d_fwd_s; a.inv_s = ctx->d_inv_s; a.misc_s = ctx->d_misc_s;
+    a.fwd_r = ctx->d_fwd_r; a.inv_r = ctx->d_inv_r;
     // fold arithmetic end to end when the ring qualifies: fold column kernels on both sides of k_rows_mul_f
     const bool fold = ctx->fold_ok && plan->fold_rows && plan->fold_cols && plan->cols_fwd_f && plan->cols_inv_f && env_int("B200_FOLD_MUL", 1);
     const kern_t cf = fold ? plan->cols_fwd_f : plan->cols_fwd, ci = fold ? plan->cols_inv_f : plan->cols_inv;
