@@ -52,6 +52,25 @@ __device__ __forceinline__ void fwd_regs_f(s64 (&x)[1 << LOGM], unsigned P, cons
     }
 }
 
+#ifndef B200_TW_SPLIT64
+#define B200_TW_SPLIT64 0   // 1: first and second register group of the row pass load a twiddle as two 64-bit loads (see ld_tw): measured 2.5 % slower
+#endif
+// A 128-bit load of a warp costs at least 4 L1 data-pipe wavefronts whatever it touches (quarter-warp granularity,
+// tools/l1bench), a 64-bit load one per 128-byte line.  The first two register groups of a row read warp-uniform or
+// 8-distinct entries, so two 64-bit loads would be 2 wavefronts against 4 -- but the second load instruction costs more
+// than the wavefronts save on B200 (rows_fwd 1.716 -> 1.758 ms), so the single 128-bit load stays.
+template <int STRIDE>
+__device__ __forceinline__ stw_t ld_tw(const stw_t *p) {
+    if (B200_TW_SPLIT64 && STRIDE < 32) {
+        u64 a, b;
+        asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(a) : "l"(p));
+        asm volatile("ld.global.nc.u64 %0, [%1+8];" : "=l"(b) : "l"(p));
+        stw_t w;
+        w.w_lo = (int)(unsigned)a; w.w_hi = (int)(unsigned)(a >> 32); w.v_lo = (int)(unsigned)b; w.v_hi = (int)(unsigned)(b >> 32);
+        return w;
+    }
+    return *p;
+}
 // The same on the row-pass order of the tables (b200ring.cu fold_setup): the twiddle of level j, block g of a register group
 // is base[((1 << j) - 1 + g) * STRIDE]; base and STRIDE say which group of the row it is (row_fwd_core_f).
 template <int LOGM, int L0, int STRIDE>
@@ -66,7 +85,7 @@ __device__ __forceinline__ void fwd_regs_fr(s64 (&x)[1 << LOGM], const stw_t *__
         }
 #pragma unroll
         for (int g = 0; g < (1 << j); ++g) {
-            const stw_t w = base[((1 << j) - 1 + g) * STRIDE];
+            const stw_t w = ld_tw<STRIDE>(base + ((1 << j) - 1 + g) * STRIDE);
 #pragma unroll
             for (int o = 0; o < half; ++o) fbf_fwd(x[g * 2 * half + o], x[g * 2 * half + o + half], w, c, fwd_ku(r), fwd_kv(r));
         }
@@ -110,7 +129,7 @@ __device__ __forceinline__ void inv_regs_fr(s64 (&x)[1 << LOGM], const stw_t *__
         const int l = L0 + (LOGM - 1 - j);
 #pragma unroll
         for (int g = 0; g < (1 << j); ++g) {
-            const stw_t w = base[((1 << j) - 1 + g) * STRIDE];
+            const stw_t w = ld_tw<STRIDE>(base + ((1 << j) - 1 + g) * STRIDE);
 #pragma unroll
             for (int o = 0; o < half; ++o) {
                 if (l & 1) fbf_inv<1, true>(x[g * 2 * half + o], x[g * 2 * half + o + half], w, c);
