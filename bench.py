@@ -33,7 +33,7 @@ L = len(MODULI)
 POLYS_PER_GPU = 128
 BYTES_PER_UNIT = 2 * N * 8            # algorithmic: read the limb once, write it once
 MODMULS_PER_UNIT = N // 2 + N + (N // 2) * 14       # cyclotomic layer + radix-3 layer + 14 radix-2 layers = 835 584
-BUTTERFLY_LOOP_PEAK = 850.0                           # G butterflies/s per B200, measured (see integer_roofline below)
+BUTTERFLY_LOOP_PEAK = 1083.0                          # G butterflies/s per B200, measured (see integer_roofline below)
 METRIC = "3N-NTT limb-transforms/sec at N=3*2^15, L=24"
 UNIT = "limb-transforms/s"
 WORKLOAD = "config3: 3N ring N=98304 (a=15,b=1), L=24 61-bit primes, batched NTT+INTT in place, limb-sharded"
@@ -270,7 +270,7 @@ def run_gpu(args):
         achieved = per_launch_bytes / (d["ms"] / d["launches"] * 1e-3) / 1e9
         traffic = None
         try:   # DRAM bytes per launch from the committed ncu --set full capture of this command (profiles/)
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
             traffic = tj["dram_bytes_per_unit"][dom] * d["units"] / d["launches"]
         except Exception:
             pass
@@ -282,12 +282,12 @@ def run_gpu(args):
     path = {"achieved": path_gbs, "peak": peak, "unit": "GB/s per GPU", "frac": path_gbs / peak,
             "note": "whole transform (both passes) against 16*N algorithmic bytes per limb-transform"}
     # the bound that actually binds: 64-bit modular butterflies on the integer pipes.  The ceiling is
-    # the register-resident loop of the same butterflies measured with tools/bfbench on this pool's B200s
-    # (profiles/r01_fp64_butterfly.txt: 850 G butterflies/s at 90 % multiply-pipe utilisation), not a datasheet number.
+    # the register-resident loop of the same fold butterflies measured with tools/solbench on this pool's B200s
+    # (profiles/r02_solbench.txt: 1 083 G butterflies/s; the Shoup/Harvey butterfly of round 1 reaches 919), not a datasheet number.
     gbf = value / world * MODMULS_PER_UNIT / 1e9
     integer = {"bound": "integer pipes", "achieved": gbf, "peak": BUTTERFLY_LOOP_PEAK, "unit": "G modular butterflies/s per GPU",
                "frac": gbf / BUTTERFLY_LOOP_PEAK, "modmuls_per_limb_transform": MODMULS_PER_UNIT,
-               "peak_source": "tools/bfbench register-resident loop, profiles/r01_fp64_butterfly.txt"}
+               "peak_source": "tools/solbench register-resident loop of the fold butterfly, profiles/r02_solbench.txt"}
 
     # end to end through the C ABI with HOST buffers: pinned H2D + NTT + INTT + D2H inside the timed region
     e2e = None
