@@ -1010,9 +1010,13 @@ struct BigPlan {
 
 #define STD_G(L, A, B, C) case L: plan->cols_fwd = (kern_t)k_cols_std_g<L, A, B, C, false>; plan->cols_inv = (kern_t)k_cols_std_g<L, A, B, C, true>; \
                                   plan->cols_inv_gather = (kern_t)k_cols_std_g<L, A, B, C, true, true>; \
+                                  plan->cols_fwd_f = (kern_t)k_cols_std_g_f<L, A, B, C, false>; plan->cols_inv_f = (kern_t)k_cols_std_g_f<L, A, B, C, true>; \
+                                  plan->cols_inv_gather_f = (kern_t)k_cols_std_g_f<L, A, B, C, true, true>; plan->row_l0 = L; \
                                   plan->col_threads_fwd = plan->col_threads_inv = plan->col_threads_gather = std_col_threads(L); break;
 #define M3_G(L, A, B, C) case L: plan->cols_fwd = (kern_t)k_cols_m3_g<L, A, B, C, false>; plan->cols_inv = (kern_t)k_cols_m3_g<L, A, B, C, true>; \
                                  plan->cols_inv_gather = (kern_t)k_cols_m3_g<L, A, B, C, true, true>; \
+                                 plan->cols_fwd_f = (kern_t)k_cols_m3_g_f<L, A, B, C, false>; plan->cols_inv_f = (kern_t)k_cols_m3_g_f<L, A, B, C, true>; \
+                                 plan->cols_inv_gather_f = (kern_t)k_cols_m3_g_f<L, A, B, C, true, true>; plan->row_l0 = L; \
                                  plan->col_threads_fwd = plan->col_threads_inv = plan->col_threads_gather = m3_col_threads(L); break;
 // column-pass kernels for a ring shape: the hand-tuned ones for the two headline shapes, the generic family otherwise
 bool pick_col_kernels(BigPlan *plan, bool matrix, int log, bool force_generic) {
@@ -1099,6 +1103,30 @@ void big_tables_destroy(b200_ctx *ctx) {
     ctx->big = nullptr;
 }
 
+// forward row kernel behind a fold column pass that ran radix-2 layers 0..l0-1: the fold schedule (ntt_fold.cuh) depends on
+// the layer number modulo FWD_PERIOD only, so five instantiations serve every shape
+template <bool MATRIX, int VT>
+static kern_t rows_fwd_after_fold_cols(int l0) {
+    static_assert(FWD_PERIOD == 5, "one instantiation per residue class of the first row layer");
+    switch ((l0 - 1) % 5) {
+        case 0: return (kern_t)k_rows_fwd_f<MATRIX, VT, 1>;
+        case 1: return (kern_t)k_rows_fwd_f<MATRIX, VT, 2>;
+        case 2: return (kern_t)k_rows_fwd_f<MATRIX, VT, 3>;
+        case 3: return (kern_t)k_rows_fwd_f<MATRIX, VT, 4>;
+        default: return (kern_t)k_rows_fwd_f<MATRIX, VT, 5>;
+    }
+}
+typedef void (*mulkern_t)(u64 *, const u64 *, BigArgs);
+static mulkern_t rows_mul_after_fold_cols(int l0) {
+    switch ((l0 - 1) % 5) {
+        case 0: return k_rows_mul_f<1>;
+        case 1: return k_rows_mul_f<2>;
+        case 2: return k_rows_mul_f<3>;
+        case 3: return k_rows_mul_f<4>;
+        default: return k_rows_mul_f<5>;
+    }
+}
+
 int launch_ntt_big(b200_ctx *ctx, const u64 *in, u64 *out, Span sp, bool inverse, int flags, const PeerOut *peers) {
     BigPlan *plan = (BigPlan *)ctx->big;
     if (!plan || !plan->covered) return 1;
@@ -1124,12 +1152,12 @@ int launch_ntt_big(b200_ctx *ctx, const u64 *in, u64 *out, Span sp, bool inverse
     if (matrix) {
         rk = inverse ? (kern_t)k_rows_inv<true, B200_VT_M3> : (kern_t)k_rows_fwd<true, B200_VT_M3>;
         if (fold_rows) rk = inverse ? (kern_t)k_rows_inv_f<true, B200_VT_M3, false> : (kern_t)k_rows_fwd_f<true, B200_VT_M3, -1>;
-        if (fold_cols) rk = inverse ? (kern_t)k_rows_inv_f<true, B200_VT_M3, true> : (kern_t)k_rows_fwd_f<true, B200_VT_M3, M3_15_ROW_L0>;
+        if (fold_cols) rk = inverse ? (kern_t)k_rows_inv_f<true, B200_VT_M3, true> : rows_fwd_after_fold_cols<true, B200_VT_M3>(plan->row_l0);
         row_warps = 6 * vt;
     } else {
         rk = inverse ? (kern_t)k_rows_inv<false, B200_VT_STD> : (kern_t)k_rows_fwd<false, B200_VT_STD>;
         if (fold_rows) rk = inverse ? (kern_t)k_rows_inv_f<false, B200_VT_STD, false> : (kern_t)k_rows_fwd_f<false, B200_VT_STD, -1>;
-        if (fold_cols) rk = inverse ? (kern_t)k_rows_inv_f<false, B200_VT_STD, true> : (kern_t)k_rows_fwd_f<false, B200_VT_STD, STD16_ROW_L0>;
+        if (fold_cols) rk = inverse ? (kern_t)k_rows_inv_f<false, B200_VT_STD, true> : rows_fwd_after_fold_cols<false, B200_VT_STD>(plan->row_l0);
         row_warps = B200_VT_STD;
     }
     const int rows_total = R * cw;
@@ -1217,8 +1245,7 @@ int launch_polymul_big(b200_ctx *ctx, const u64 *pa, const u64 *pb, u64 *pc, Spa
           cf<<<gf, thr_f, smem_f, st>>>(pb, tb, to_dense); }
         { LaunchScope ls(ctx, "rows_mul", nu);
           if (!fold) k_rows_mul<<<dim3(nu, row_tiles), 128, row_smem, st>>>(ta, tb, dense);
-          else if (matrix) k_rows_mul_f<M3_15_ROW_L0><<<dim3(nu, row_tiles), 128, row_smem, st>>>(ta, tb, dense);
-          else k_rows_mul_f<STD16_ROW_L0><<<dim3(nu, row_tiles), 128, row_smem, st>>>(ta, tb, dense); }
+          else rows_mul_after_fold_cols(plan->row_l0)<<<dim3(nu, row_tiles), 128, row_smem, st>>>(ta, tb, dense); }
         { LaunchScope ls(ctx, matrix ? "cols_inv_m3" : "cols_inv_std", nu);
           ci<<<gi, thr_i, smem_i, st>>>(ta, pc, from_dense); }
     }

@@ -721,3 +721,196 @@ B200_UNROLL_(B200_BAL_UNROLL)
         }
     }
 }
+
+// ====================================================================================================
+// generic column pass on the fold arithmetic: the shapes k_cols_std_g / k_cols_m3_g of ntt_big.cu cover (STANDARD
+// N = 2^10..2^17, MATRIX N = 3*2^10..3*2^16), same tiling (GCW columns per CTA, register groups of <= 3 layers, padded
+// shared-memory tile), signed lazy words.  The radix-2 layers are numbered across both passes as in the headline kernels
+// (forward: from 0 after the load / the radix-3 layer, the row pass continues with LOG; inverse: the row pass ran 0..7, the
+// column pass starts at 8); the fold schedule depends on the number only.
+// ====================================================================================================
+template <int S, int ROOTS, int LOG, bool INV, bool FROM_G, bool TO_G, bool LAST_STD, int L0, bool GATHER = false>
+__device__ __forceinline__ void col_group_f(const u64 *gin, size_t ibase, u64 *gout, size_t obase, u64 *sm, int b0,
+                                            const stw_t *__restrict__ tw, const SolConst &sc, const stw_t ninv, const stw_t ninv_w1,
+                                            const PeerOut *po = nullptr) {
+    constexpr int M = 1 << S;
+    const int ntiles = (GCW * ROOTS) << (LOG - S);
+    for (int t = threadIdx.x; t < ntiles; t += blockDim.x) {
+        const int c = t & (GCW - 1), rest = t >> GCW_LOG;
+        const int lo = rest & ((1 << b0) - 1), hi = rest >> b0;
+        const int row0 = (hi << (b0 + S)) + lo;
+        s64 x[M];
+#pragma unroll
+        for (int k = 0; k < M; ++k) {
+            const int row = row0 + (k << b0);
+            x[k] = (s64)(FROM_G ? ldd(gin + ibase + (size_t)row * 256 + c) : sm[pc(row * GCW + c)]);
+        }
+        const unsigned P = (unsigned)((ROOTS << (LOG - b0 - S)) + hi);
+        u64 y[M];
+        if (!INV) {
+            fwd_regs_f<S, L0>(x, P, tw, sc);
+        } else if (!LAST_STD) {
+            inv_regs_f<S, L0>(x, P, tw, sc);
+        } else {   // top group of the STANDARD inverse: the last layer carries N^-1, canonical output
+            inv_regs_f<S, L0, 1>(x, P, tw, sc);
+#pragma unroll
+            for (int o = 0; o < M / 2; ++o) {
+                const s64 U = x[o], V = x[o + M / 2];
+                x[o] = fmul(U + V, ninv, sc);
+                x[o + M / 2] = fmul(U - V, ninv_w1, sc);
+            }
+            sol_canon_n(y, x, sc);
+        }
+#pragma unroll
+        for (int k = 0; k < M; ++k) {
+            const int row = row0 + (k << b0);
+            const u64 v = (INV && LAST_STD) ? y[k] : (u64)x[k];
+            if (TO_G) { if (GATHER) store_out<true>(*po, gout, obase + (size_t)row * 256 + c, v); else std_(gout + obase + (size_t)row * 256 + c, v); }
+            else sm[pc(row * GCW + c)] = v;
+        }
+    }
+}
+
+template <int LOGR, int S1, int S2, int S3, bool INV, bool GATHER = false>
+__global__ void __launch_bounds__(std_col_threads(LOGR), minb_for(std_col_threads(LOGR), 1024))
+k_cols_std_g_f(const u64 *in, u64 *out, BigArgs a) {
+    static_assert(S1 + S2 + S3 == LOGR && S1 >= 1 && S2 >= 1, "group sizes");
+    extern __shared__ __align__(16) u64 sm[];
+    const UnitRef ur = unit_ref<true>(a);
+    const int limb = ur.limb;
+    const size_t ibase = ur.in + (size_t)blockIdx.x * GCW, obase = ur.out + (size_t)blockIdx.x * GCW;
+    const SolConst sc = a.sol[limb];
+    const stw_t *__restrict__ tw = (INV ? a.inv_s : a.fwd_s) + (size_t)limb * a.N;
+    const stw_t ninv = a.misc_s[limb * MISC_COUNT + MISC_NINV], ninv_w1 = a.misc_s[limb * MISC_COUNT + MISC_NINV_W1];
+    constexpr int S3e = S3 ? S3 : 1;
+    if (!INV) {
+        col_group_f<S1, 1, LOGR, false, true, false, false, 0>(in, ibase, out, obase, sm, S2 + S3, tw, sc, ninv, ninv_w1);
+        __syncthreads();
+        if (S3 == 0) {
+            col_group_f<S2, 1, LOGR, false, false, true, false, S1>(in, ibase, out, obase, sm, 0, tw, sc, ninv, ninv_w1);
+        } else {
+            col_group_f<S2, 1, LOGR, false, false, false, false, S1>(in, ibase, out, obase, sm, S3, tw, sc, ninv, ninv_w1);
+            __syncthreads();
+            col_group_f<S3e, 1, LOGR, false, false, true, false, S1 + S2>(in, ibase, out, obase, sm, 0, tw, sc, ninv, ninv_w1);
+        }
+    } else {
+        if (S3 == 0) {
+            col_group_f<S2, 1, LOGR, true, true, false, false, 8>(in, ibase, out, obase, sm, 0, tw, sc, ninv, ninv_w1);
+        } else {
+            col_group_f<S3e, 1, LOGR, true, true, false, false, 8>(in, ibase, out, obase, sm, 0, tw, sc, ninv, ninv_w1);
+            __syncthreads();
+            col_group_f<S2, 1, LOGR, true, false, false, false, 8 + S3>(in, ibase, out, obase, sm, S3, tw, sc, ninv, ninv_w1);
+        }
+        __syncthreads();
+        col_group_f<S1, 1, LOGR, true, false, true, true, 8 + S3 + S2, GATHER>(in, ibase, out, obase, sm, S2 + S3, tw, sc, ninv, ninv_w1, &a.peers);
+    }
+}
+
+// MATRIX: first group = cyclotomic + radix-3 + S1 radix-2 layers on 6*2^S1 words; then groups on the u bits
+template <int LOGU, int S1, int S2, int S3, bool INV, bool GATHER = false>
+__global__ void __launch_bounds__(m3_col_threads(LOGU), minb_for(m3_col_threads(LOGU), 768))
+k_cols_m3_g_f(const u64 *in, u64 *out, BigArgs a) {
+    static_assert(S1 + S2 + S3 == LOGU && S2 >= 1, "group sizes");
+    extern __shared__ __align__(16) u64 sm[];
+    const UnitRef ur = unit_ref<true>(a);
+    const int limb = ur.limb;
+    const size_t ibase = ur.in + (size_t)blockIdx.x * GCW, obase = ur.out + (size_t)blockIdx.x * GCW;
+    const SolConst sc = a.sol[limb];
+    const s64 q = (s64)sc.q;
+    const stw_t *__restrict__ tw = (INV ? a.inv_s : a.fwd_s) + (size_t)limb * a.N;
+    const stw_t *mc = a.misc_s + limb * MISC_COUNT;
+    const stw_t om = mc[MISC_OMEGA3], none = stw_t{0, 0, 0, 0};
+    constexpr int MA = 1 << S1, U = 1 << LOGU, ULO = U >> S1, S3e = S3 ? S3 : 1;
+    if (!INV) {
+        for (int t = threadIdx.x; t < GCW * ULO; t += blockDim.x) {
+            const int c = t & (GCW - 1), ulo = t >> GCW_LOG;
+            s64 x[6][MA];
+#pragma unroll
+            for (int hd = 0; hd < 6; ++hd)
+#pragma unroll
+                for (int k = 0; k < MA; ++k) x[hd][k] = (s64)ldd(in + ibase + (size_t)(hd * U + k * ULO + ulo) * 256 + c);
+            const stw_t zeta = tw[1];
+#pragma unroll
+            for (int k = 0; k < MA; ++k) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {   // cyclotomic layer
+                    const s64 lo = x[d][k], hi = x[d + 3][k];
+                    const s64 tt = fmul(hi, zeta, sc);
+                    x[d][k] = lo + tt - q;
+                    x[d + 3][k] = lo + hi - tt - 2 * q;
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {   // radix-3 layer, outputs folded
+                    const stw_t z1 = tw[2 + 2 * h], z2 = tw[3 + 2 * h];
+                    const s64 b0 = sol_fold(x[3 * h][k], sc);
+                    const s64 t1 = fmul(x[3 * h + 1][k], z1, sc);
+                    const s64 t2 = fmul(x[3 * h + 2][k], z2, sc);
+                    const s64 t3 = fmul(t1 - t2, om, sc);
+                    x[3 * h][k] = sol_fold(b0 + t1 + t2, sc);
+                    x[3 * h + 1][k] = sol_fold(b0 - t2 + t3, sc);
+                    x[3 * h + 2][k] = sol_fold(b0 - t1 - t3, sc);
+                }
+            }
+#pragma unroll
+            for (int hd = 0; hd < 6; ++hd) {
+                if (S1 > 0) fwd_regs_f<S1, 0>(x[hd], (unsigned)(6 + hd), tw, sc);
+#pragma unroll
+                for (int k = 0; k < MA; ++k) sm[pc((hd * U + k * ULO + ulo) * GCW + c)] = (u64)x[hd][k];
+            }
+        }
+        __syncthreads();
+        if (S3 == 0) {
+            col_group_f<S2, 6, LOGU, false, false, true, false, S1>(in, ibase, out, obase, sm, 0, tw, sc, none, none);
+        } else {
+            col_group_f<S2, 6, LOGU, false, false, false, false, S1>(in, ibase, out, obase, sm, S3, tw, sc, none, none);
+            __syncthreads();
+            col_group_f<S3e, 6, LOGU, false, false, true, false, S1 + S2>(in, ibase, out, obase, sm, 0, tw, sc, none, none);
+        }
+    } else {
+        if (S3 == 0) {
+            col_group_f<S2, 6, LOGU, true, true, false, false, 8>(in, ibase, out, obase, sm, 0, tw, sc, none, none);
+        } else {
+            col_group_f<S3e, 6, LOGU, true, true, false, false, 8>(in, ibase, out, obase, sm, 0, tw, sc, none, none);
+            __syncthreads();
+            col_group_f<S2, 6, LOGU, true, false, false, false, 8 + S3>(in, ibase, out, obase, sm, S3, tw, sc, none, none);
+        }
+        __syncthreads();
+        const stw_t k1 = mc[MISC_K1], k4 = mc[MISC_K4];
+        for (int t = threadIdx.x; t < GCW * ULO; t += blockDim.x) {
+            const int c = t & (GCW - 1), ulo = t >> GCW_LOG;
+            s64 x[6][MA];
+#pragma unroll
+            for (int hd = 0; hd < 6; ++hd) {
+#pragma unroll
+                for (int k = 0; k < MA; ++k) x[hd][k] = (s64)sm[pc((hd * U + k * ULO + ulo) * GCW + c)];
+                if (S1 > 0) inv_regs_f<S1, 8 + S3 + S2>(x[hd], (unsigned)(6 + hd), tw, sc);
+            }
+#pragma unroll
+            for (int k = 0; k < MA; ++k) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {   // inverse radix-3 (factor 3 deferred), x0 folded
+                    const stw_t z1 = tw[2 + 2 * h], z2 = tw[3 + 2 * h];
+                    const s64 y0 = x[3 * h][k], y1 = x[3 * h + 1][k], y2 = x[3 * h + 2][k];
+                    const s64 sg = fmul(y1 - y2, om, sc);
+                    // the last radix-2 layer is number LOGU + 7: when that is even its sums arrive unfolded (up to 3.2 * 2^k)
+                    // and three of them would pass 2^63: one of them is folded first (tools/fold_ranges.py inverse_3n)
+                    x[3 * h][k] = sol_fold((((LOGU + 7) & 1) ? y0 : sol_fold(y0, sc)) + y1 + y2, sc);
+                    x[3 * h + 1][k] = fmul(y0 - y1 - sg, z1, sc);
+                    x[3 * h + 2][k] = fmul(y0 - y2 + sg, z2, sc);
+                }
+                s64 z[6];
+                u64 y[6];
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {   // inverse cyclotomic layer, two products and a halving
+                    const s64 lo = x[d][k], hi = x[d + 3][k];
+                    const s64 hh = fmul(lo - hi, k1, sc);
+                    z[d] = fmul(lo + hi, k4, sc) - sol_half(hh, sc);
+                    z[d + 3] = hh;
+                }
+                sol_canon_n(y, z, sc);
+#pragma unroll
+                for (int hd = 0; hd < 6; ++hd) store_out<GATHER>(a.peers, out, obase + (size_t)(hd * U + k * ULO + ulo) * 256 + c, y[hd]);
+            }
+        }
+    }
+}

@@ -627,6 +627,13 @@ class Ring:
     def DivRoundByLastModulusManyNTT(self, nbRescales, p0, p1):   # :130-158
         check(lib().b200_div_by_last_modulus_many(self._ctx.h, p0.h, p1.h, self.level, int(nbRescales), 1, 1))
 
+    def Rescale(self, nbRescales, c0, c1, out0, out1):
+        """ckks.Evaluator.Rescale on the two polynomials of a ciphertext (schemes/ckks/evaluator.go:500-541, and the
+        matrix_ckks form :208-243): DivRoundByLastModulusManyNTT of each component; the caller lowers its level by
+        nbRescales (use AtLevel(level - nbRescales) afterwards)."""
+        self.DivRoundByLastModulusManyNTT(nbRescales, c0, out0)
+        self.DivRoundByLastModulusManyNTT(nbRescales, c1, out1)
+
     def TensorProduct(self, a0, a1, b0, b1, c0, c1, c2, mform=True):
         """(a0,a1) x (b0,b1) -> (c0,c1,c2) in one pass: the MForm/MulCoeffsMontgomery[ThenAdd] sequence of
         ckks.Evaluator.mulRelin (mform=True) or matrix_ckks.Evaluator.Mul (mform=False)."""
@@ -722,6 +729,29 @@ class KeySwitcher:
         """ct x ct multiply + relinearisation in the NTT domain: tensor product, GadgetProduct(c2, rlk), add
         (schemes/ckks/evaluator.go:821-853)."""
         check(lib().b200_mul_relin(self.h, levelQ, levelP, a0.h, a1.h, b0.h, b1.h, rlk.h, out0.h, out1.h, int(mform)))
+
+    def _tmp(self, batch):
+        t = getattr(self, "_tmp_polys", None)
+        if t is None or t[0].batch != batch:
+            t = self._tmp_polys = (self.ring.NewPoly(batch), self.ring.NewPoly(batch))
+        return t
+
+    def Relinearize(self, levelQ, levelP, c0, c1, c2, rlk, out0, out1):
+        """rlwe.Evaluator.Relinearize (core/rlwe/evaluator_evaluationkey.go:125-153): GadgetProduct(c2, rlk) into the
+        evaluator's buffers, then out_i = c_i + tmp_i on the limbs 0..levelQ."""
+        t0, t1 = self._tmp(c2.batch)
+        self.GadgetProduct(levelQ, levelP, c2, rlk, t0, t1)
+        rq = self.ring.AtLevel(levelQ)
+        rq.Add(c0, t0, out0)
+        rq.Add(c1, t1, out1)
+
+    def ApplyEvaluationKey(self, levelQ, levelP, c0, c1, evk, out0, out1):
+        """rlwe.Evaluator.ApplyEvaluationKey for equal ring degrees (evaluator_evaluationkey.go:37-108 -> applyEvaluationKey
+        :110-117): GadgetProduct(c1, evk), out0 = c0 + tmp0, out1 = tmp1 (CopyLvl)."""
+        t0, t1 = self._tmp(c1.batch)
+        self.GadgetProduct(levelQ, levelP, c1, evk, t0, t1)
+        self.ring.AtLevel(levelQ).Add(c0, t0, out0)
+        out1.CopyLvl(levelQ, t1)
 
     # limb-sharded steps (see sharding.gadget_product_sharded)
     def DecomposeMac(self, levelQ, levelP, cx, cxinv, key, acc0, acc1, q0, q1, p0, p1):

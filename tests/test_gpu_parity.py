@@ -239,6 +239,40 @@ def test_3n_matches_oracle_roundtrip_product(N):
     assert (c.get() == got).all()                                        # fused product == operator sequence
 
 
+@pytest.mark.parametrize("N", [12, 24, 96, 3 * 2**10, 3 * 2**12])
+def test_3n_small_prime_cases_of_the_reference_on_gpu(N):
+    """ring/ntt_3n_test.go:139-222 with the reference's own parameters on the GPU path: 31-bit primes from
+    Find3NRNSPrimes(N, 31, .., 1<<16) (32-bit words, far from the 60/61-bit chains of the other cases: the Shoup kernels with
+    their quotient-estimate reduction, resident and two-pass shapes): NTT == oracle, eight Forward+Backward cycles, the zero
+    and the all-ones vector, and at the reference's own sizes the definition out[k] = f(omega^E[k])."""
+    moduli = O.find_3n_rns_primes(N, 31, 2)
+    assert all(q.bit_length() == 32 and q % (3 * N) == 1 for q in moduli)
+    r = b200ring.NewRing(N, moduli)
+    subs = [O.ThreeNSubRing(N, q) for q in moduli]
+    host = rand_poly(31, 2, moduli, N)
+    p, o = r.NewPoly(2).set(host), r.NewPoly(2)
+    r.NTT(p, o)
+    got = o.get()
+    for b in range(2):
+        for l in range(2):
+            assert (got[b, l] == subs[l].NTT(host[b, l])).all(), (N, b, l)
+    if N <= 24:
+        q, s = moduli[0], subs[0]
+        E = [int(e) for e in O.totatives(3 * N)]
+        for k in range(N):
+            x = pow(s.omega, E[k], q)
+            assert int(got[0, 0, k]) == sum(int(c) * pow(x, j, q) for j, c in enumerate(host[0, 0])) % q
+    z = r.NewPoly(2).set(host)
+    for _ in range(8):
+        r.NTT(z, z); r.INTT(z, z)
+    assert (z.get() == host).all()
+    for v in (np.zeros_like(host), np.ones_like(host)):
+        r.NTT(z.set(v), z); r.INTT(z, z)
+        assert (z.get() == v).all()
+    r.NTT(z.set(np.zeros_like(host)), z)
+    assert not z.get().any()
+
+
 def test_3n_random_omega_from_go_side():
     """the Go transformer draws omega at random; the bridge passes it and slots must follow it."""
     N = 48

@@ -214,6 +214,16 @@ def test_mul_relin_is_tensor_plus_gadget_product(kind, N, LQ, LP):
     rl = ring.AtLevel(levelQ)
     rl.Add(c0, g0, g0); rl.Add(c1, g1, g1)
     assert (o0.get()[:, :LQ] == g0.get()[:, :LQ]).all() and (o1.get()[:, :LQ] == g1.get()[:, :LQ]).all()
+    # rlwe.Evaluator.Relinearize as one call of the mirror (evaluator_evaluationkey.go:125-153) and ApplyEvaluationKey
+    # (:110-117: out0 = c0 + gp0, out1 = gp1)
+    r0, r1 = ring.NewPoly(batch), ring.NewPoly(batch)
+    ks.Relinearize(levelQ, levelP, c0, c1, c2, rlk, r0, r1)
+    assert (r0.get()[:, :LQ] == o0.get()[:, :LQ]).all() and (r1.get()[:, :LQ] == o1.get()[:, :LQ]).all()
+    e0, e1, p0, p1 = (ring.NewPoly(batch) for _ in range(4))
+    ks.ApplyEvaluationKey(levelQ, levelP, c0, c2, rlk, e0, e1)
+    ks.GadgetProduct(levelQ, levelP, c2, rlk, p0, p1)
+    rl.Add(c0, p0, p0)
+    assert (e0.get()[:, :LQ] == p0.get()[:, :LQ]).all() and (e1.get()[:, :LQ] == p1.get()[:, :LQ]).all()
     # algebra: out0 = a0 b0 + (a1 b1) s2, out1 = a0 b1 + a1 b0   (slot-wise, mod q)
     got0, got1 = o0.get(), o1.get()
     for b in range(batch):

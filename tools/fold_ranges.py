@@ -152,13 +152,14 @@ def rows_fwd_after_shoup(log=None):
     return canon(fwd_layers(fold_u(), 0, 8, log, "rows after Shoup columns"), "rows after Shoup columns")
 
 
-def inverse_3n(log=None):
+def inverse_3n(log=None, radix2_layers=14):
     """k_rows_inv_f + k_cols_inv_m3_15_{f,b}: fold_u of any input word, radix-2 layers 0..13, inverse radix-3 layer,
     inverse cyclotomic layer in its two-product form (hh = k1 (lo - hi), ll = k4 (lo + hi) - hh / 2), canonical"""
-    ws, wp = inv_layers(fold_u(), None, 0, 14, log, "inverse 3N")
+    ws, wp = inv_layers(fold_u(), None, 0, radix2_layers, log, "inverse 3N")
     y = ws.union(wp)
     sg = mul(y - y, "inverse radix-3 s")
-    x0 = fold(check_word(y + y + y, "inverse radix-3 x0"))          # folded: lo + hi below must stay a valid multiplicand
+    y0 = y if (radix2_layers - 1) & 1 else fold(y)                   # last layer even: its sums arrive unfolded, one summand is folded first
+    x0 = fold(check_word(y0 + y + y, "inverse radix-3 x0"))         # folded: lo + hi below must stay a valid multiplicand
     x12 = mul(check_word(y - y - sg, "inverse radix-3 operand"), "inverse radix-3 x1, x2")
     x = x0.union(x12)
     hh = mul(check_word(x - x, "inverse cyclotomic lo - hi"), "inverse cyclotomic hh")
@@ -170,9 +171,9 @@ def inverse_3n(log=None):
     return canon(hh, "inverse 3N hh")
 
 
-def inverse_std(log=None):
+def inverse_std(log=None, layers=16):
     """k_rows_inv_f + k_cols_inv_std16_f: layers 0..14, then the last layer carries N^-1 on both outputs"""
-    ws, wp = inv_layers(fold_u(), None, 0, 15, log, "inverse 2^16")
+    ws, wp = inv_layers(fold_u(), None, 0, layers - 1, log, "inverse 2^16")
     w = ws.union(wp)
     out = mul(check_word(w + w, "last layer sum"), "last layer").union(mul(w - w, "last layer difference"))
     return canon(out, "inverse 2^16")
@@ -187,9 +188,16 @@ def rows_inv_to_shoup(log=None):
 
 
 def check_all():
+    """the headline shapes with their logs, then every shape the generic fold column kernels cover (same schedule, other depths)"""
     log = []
     out = {"forward_3n": forward_3n(log), "inverse_3n": inverse_3n(log), "forward_std": forward_std(log), "inverse_std": inverse_std(log),
            "rows_fwd_after_shoup": rows_fwd_after_shoup(log), "rows_inv_to_shoup": rows_inv_to_shoup(log)}
+    for a in range(10, 17):          # N = 3 * 2^a: a - 1 radix-2 layers
+        out["forward_3n_a%d" % a] = forward_3n(None, a - 1)
+        out["inverse_3n_a%d" % a] = inverse_3n(None, a - 1)
+    for logn in range(10, 18):       # N = 2^logn
+        out["forward_std_%d" % logn] = forward_std(None, logn)
+        out["inverse_std_%d" % logn] = inverse_std(None, logn)
     return out, log
 
 
