@@ -113,6 +113,11 @@ typedef struct b200_poly b200_poly; /* ring.Poly (ring/poly.go:13-24), device re
 B200_API const char *b200_last_error(void);   /* message of the last failure on this thread ("" if none) */
 B200_API const char *b200_version(void);
 B200_API int b200_device_count(void);         /* 0 when no CUDA device is visible */
+/* Where the twiddle of heap index h (h = (R + row) * 2^d + k, R = N/256, the subtree under one 256-word row) sits in the
+ * row-pass copies of the tables the two-pass kernels read (no reference counterpart: the Go tables are the heap order,
+ * ring/subring.go:187-205; b200_ctx_roots still returns that order).  Host only, no device needed: returns the index in
+ * [R, N), h itself for h < R, -1 for an invalid N or h. */
+B200_API int b200_row_pass_index(int N, int heap_index);
 
 /* ---- context: ring.NewRing / NewRingFromType / NewRingWithCustomNTT (ring/ring.go:264-356) ----
  * Validates like the reference (ring degree ring.go:319-323 / subring.go:14-30, non-empty and

@@ -15,6 +15,7 @@ SYMBOLS = {
     "b200_last_error": (C.c_char_p, []),
     "b200_version": (C.c_char_p, []),
     "b200_device_count": (C.c_int, []),
+    "b200_row_pass_index": (C.c_int, [C.c_int, C.c_int]),
     "b200_ctx_create": (C.c_int, [C.c_int, C.c_int, C.c_int, P64, P64, C.c_int, C.POINTER(VP)]),
     "b200_ctx_destroy": (None, [VP]),
     "b200_ctx_set_stream": (C.c_int, [VP, VP]),

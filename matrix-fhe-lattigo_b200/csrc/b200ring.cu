@@ -202,6 +202,22 @@ static void build_matrix(b200_ctx *ctx, int i, std::vector<tw_t> &fwd, std::vect
 // group, indexed by lane) -- so that one load instruction of a warp reads consecutive entries instead of a strided set
 // (L1 data-pipe wavefronts were the busiest resource of the row kernels).  Heap indices below R, all the column pass uses,
 // stay where they are.
+static int row_pass_index(int N, int h) {
+    const int R = N / 256;
+    if (h < R) return h;
+    int d = 0;
+    while ((h >> d) >= 2 * R) ++d;
+    const int r = (h >> d) - R, k = h & ((1 << d) - 1);
+    int off;
+    if (d < 3) off = (1 << d) - 1 + k;
+    else if (d < 6) { const int j = d - 3, hi3 = k >> j, g = k & ((1 << j) - 1); off = 7 + ((1 << j) - 1 + g) * 8 + hi3; }
+    else { const int j = d - 6, sub = k >> j, g = k & ((1 << j) - 1), lane = sub >> 1, s2 = sub & 1; off = 63 + (s2 * 3 + (1 << j) - 1 + g) * 32 + lane; }
+    return R + 255 * r + off;
+}
+extern "C" int b200_row_pass_index(int N, int heap_index) {
+    if (N < 512 || N % 256 != 0 || heap_index < 0 || heap_index >= N) return -1;
+    return row_pass_index(N, heap_index);
+}
 template <typename T>
 static void row_pass_order(std::vector<T> &t, int L, int N) {
     const int R = N / 256;
@@ -209,16 +225,7 @@ static void row_pass_order(std::vector<T> &t, int L, int N) {
     for (int i = 0; i < L; ++i) {
         const T *src = &t[(size_t)i * N];
         T *dst = &o[(size_t)i * N];
-        for (int h = R; h < N; ++h) {
-            int d = 0;
-            while ((h >> d) >= 2 * R) ++d;
-            const int r = (h >> d) - R, k = h & ((1 << d) - 1);
-            int off;
-            if (d < 3) off = (1 << d) - 1 + k;
-            else if (d < 6) { const int j = d - 3, hi3 = k >> j, g = k & ((1 << j) - 1); off = 7 + ((1 << j) - 1 + g) * 8 + hi3; }
-            else { const int j = d - 6, sub = k >> j, g = k & ((1 << j) - 1), lane = sub >> 1, s2 = sub & 1; off = 63 + (s2 * 3 + (1 << j) - 1 + g) * 32 + lane; }
-            dst[R + 255 * r + off] = src[h];
-        }
+        for (int h = R; h < N; ++h) dst[row_pass_index(N, h)] = src[h];
     }
     t.swap(o);
 }

@@ -91,3 +91,36 @@ def test_null_arguments_are_errors_not_crashes():
     assert L.b200_order_mod(2, 7, None) == capi.B200_EINVAL
     assert L.b200_prime_gen_next(None, 0, 1, C.byref(out)) == capi.B200_EINVAL
     assert L.b200_last_error() != b""
+
+
+@pytest.mark.parametrize("N", [1 << 10, 1 << 16, 3 << 10, 3 << 15])
+def test_row_pass_order_is_a_permutation_of_the_row_subtrees(N):
+    """The row-pass copies of the twiddle tables permute the heap indices [R, N): host-only entry point,
+    no device.  Every row subtree {(R + r) * 2^d + k} lands in its own block [R + 255 r, R + 255 (r + 1)), first the 7
+    entries of depths 0..2 in heap order, then depths 3..5 as runs of 8 indexed by the top three bits of k, then depths
+    6, 7 as runs of 32 indexed by lane = (k >> (d - 6)) >> 1."""
+    L = capi.load_library()
+    R = N // 256
+    assert L.b200_row_pass_index(N, 0) == 0 and L.b200_row_pass_index(N, R - 1) == R - 1      # column-pass indices stay
+    assert L.b200_row_pass_index(N, N) == -1 and L.b200_row_pass_index(100, 5) == -1
+    seen = set()
+    for r in (0, 1, R // 2, R - 1):
+        block = []
+        for d in range(8):
+            for k in range(1 << d):
+                i = L.b200_row_pass_index(N, ((R + r) << d) + k)
+                assert R + 255 * r <= i < R + 255 * (r + 1)
+                block.append(i)
+                if d < 3:
+                    assert i == R + 255 * r + (1 << d) - 1 + k
+                elif d < 6:
+                    j = d - 3
+                    assert i == R + 255 * r + 7 + ((1 << j) - 1 + (k & ((1 << j) - 1))) * 8 + (k >> j)
+                else:
+                    j = d - 6
+                    sub = k >> j
+                    assert i == R + 255 * r + 63 + ((sub & 1) * 3 + (1 << j) - 1 + (k & ((1 << j) - 1))) * 32 + (sub >> 1)
+        assert sorted(block) == list(range(R + 255 * r, R + 255 * (r + 1)))
+        seen.update(block)
+    if N <= 3 << 10:
+        assert sorted(L.b200_row_pass_index(N, h) for h in range(R, N)) == list(range(R, N))
