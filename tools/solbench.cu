@@ -116,6 +116,20 @@ __device__ __forceinline__ void bf_sol_chain(s64 &U, s64 &V, const stw_t w, cons
     V = U + U - X;
     U = X;
 }
+// the shifted term joins the two butterfly additions as a third input (X = U + T + sh, Y = U - T - sh) instead of being added
+// to the product first: two 64-bit additions fewer per butterfly, no recentring (fold every 4 layers)
+__device__ __forceinline__ void bf_sol_3in(s64 &U, s64 &V, const stw_t w, const SolConst &c) {
+    const s64 y = V;
+    const unsigned ylo = (unsigned)y, yhi = (unsigned)((u64)y >> 32);
+    const int y0 = (int)ylo, y1 = (int)(yhi + (ylo >> 31));
+    s64 A = mulwide_s32(y0, w.w_lo); A = madwide_s32(y1, w.v_lo, A);
+    s64 B = mulwide_s32(y0, w.w_hi); B = madwide_s32(y1, w.v_hi, B);
+    const s64 T = madwide_s32((int)(B >> 32), c.negc, A);
+    const unsigned blo = (unsigned)B;
+    const s64 sh = pack64(blo << c.sh, blo >> (32 - c.sh));
+    V = U - T - sh;
+    U = U + T + sh;
+}
 // inverse (Gentleman-Sande) butterfly: U' = U + V, V' = (U - V)*w
 __device__ __forceinline__ void bf_sol_inv(s64 &U, s64 &V, const stw_t w, const SolConst &c) {
     const s64 d = U - V;
@@ -156,7 +170,7 @@ __global__ void __launch_bounds__(128, 8) k_bf(u64 *data, const tw_t *twi, const
 #pragma unroll
                 for (int k = 0; k < 8; ++k) z[k] = sol_fold_3(z[k], sc, kz);
             }
-            if ((MODE == 6 || MODE == 7 || MODE == 10 || MODE == 11) && (l & 3) == 0) {   // fold every 4 layers
+            if ((MODE == 6 || MODE == 7 || MODE == 10 || MODE == 11 || MODE == 12) && (l & 3) == 0) {   // fold every 4 layers
 #pragma unroll
                 for (int k = 0; k < 8; ++k) z[k] = sol_fold(z[k], sc);
             }
@@ -190,6 +204,8 @@ __global__ void __launch_bounds__(128, 8) k_bf(u64 *data, const tw_t *twi, const
                         if (r == 0) bf_sol_unfused<false, true>(z[i0], z[i1], tws[ti], sc); else if (r == 3) bf_sol_unfused<false, false>(z[i0], z[i1], tws[ti], sc); else bf_sol_unfused<true, false>(z[i0], z[i1], tws[ti], sc);
                     } else if (MODE == 11) {
                         bf_sol_chain(z[i0], z[i1], tws[ti], sc);
+                    } else if (MODE == 12) {
+                        bf_sol_3in(z[i0], z[i1], tws[ti], sc);
                     } else if (MODE == 7) {
                         const int r = l & 3;
                         if (r == 0) bf_sol_sh<false, true>(z[i0], z[i1], tws[ti], sc); else if (r == 3) bf_sol_sh<false, false>(z[i0], z[i1], tws[ti], sc); else bf_sol_sh<true, false>(z[i0], z[i1], tws[ti], sc);
@@ -316,7 +332,10 @@ int main(int argc, char **argv) {
         { std::vector<u64> u8, v8; bench<10, 8>("design B, ALU shifter, unfused products (5 mul.wide + adds)", sms, d, in, d_ti, d_ta, d_ts, c, sa, sc, &u8);
           bench<11, 8>("design B, product chain started from U, no recentring", sms, d, in, d_ti, d_ta, d_ts, c, sa, sc, &v8);
           size_t b3 = 0, b4 = 0; for (size_t i = 0; i < r8.size() && i < u8.size() && i < v8.size(); ++i) { b3 += r8[i] != u8[i]; b4 += r8[i] != v8[i]; }
-          printf("   parity vs Shoup/Harvey: unfused %zu, chain %zu mismatches\n", b3, b4); }
+          printf("   parity vs Shoup/Harvey: unfused %zu, chain %zu mismatches\n", b3, b4);
+          std::vector<u64> w8; bench<12, 8>("design B, shifted term as third input of both additions", sms, d, in, d_ti, d_ta, d_ts, c, sa, sc, &w8);
+          size_t b5 = 0; for (size_t i = 0; i < r8.size() && i < w8.size(); ++i) b5 += r8[i] != w8[i];
+          printf("   parity vs Shoup/Harvey: three-input %zu mismatches\n", b5); }
         size_t b1 = 0, b2 = 0; for (size_t i = 0; i < r8.size() && i < s8.size() && i < t8.size(); ++i) { b1 += r8[i] != s8[i]; b2 += r8[i] != t8[i]; }
         printf("   parity vs Shoup/Harvey: %zu and %zu mismatches\n", b1, b2); }
       bench<5, 6>("design B, no fold (timing only)", sms, d, in, d_ti, d_ta, d_ts, c, sa, sc, &rx);
