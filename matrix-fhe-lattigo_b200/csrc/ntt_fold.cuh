@@ -1,7 +1,8 @@
 // ntt_fold.cuh -- the two-pass transforms of ntt_big.cu on the fold arithmetic of solinas.cuh (primes q = 2^k + c).
-// Included by ntt_big.cu inside its anonymous namespace: same tiling, same twiddle indexing (heap order), same slot
-// permutation; only the word type (signed, lazy), the butterflies and the reductions differ.  Where the folds sit and
-// which layers recentre by +-q is restated on intervals in tools/fold_ranges.py (tests/test_fold_ranges.py).
+// Included by ntt_big.cu inside its anonymous namespace: same two-pass split, same twiddle indexing (heap order in the
+// column pass, row-pass order in the row pass), same slot permutation; the word type (signed, lazy), the butterflies, the
+// reductions and the tiling of the headline column pass (balanced kernels) differ.  Where the folds sit and which layers
+// recentre by +-q is restated on intervals in tools/fold_ranges.py (tests/test_fold_ranges.py).
 #pragma once
 #include "solinas.cuh"
 
@@ -32,49 +33,38 @@ constexpr int FWD_PERIOD = 5;
 __host__ __device__ constexpr bool fwd_ku(int r) { return (r & 1) == 0; }
 __host__ __device__ constexpr bool fwd_kv(int r) { return (r & 1) == 1; }
 
-// LOGM forward layers of a register group whose first layer has number L0
-template <int LOGM, int L0>
-__device__ __forceinline__ void fwd_regs_f(s64 (&x)[1 << LOGM], unsigned P, const stw_t *__restrict__ tw, const SolConst &c) {
-#pragma unroll
-    for (int j = 0; j < LOGM; ++j) {
-        const int half = (1 << LOGM) >> (j + 1);
-        const int l = L0 + j, r = l % FWD_PERIOD;
-        if (l > 0 && r == 0) {
-#pragma unroll
-            for (int k = 0; k < (1 << LOGM); ++k) x[k] = sol_fold(x[k], c);
-        }
-#pragma unroll
-        for (int g = 0; g < (1 << j); ++g) {
-            const stw_t w = tw[(P << j) + g];
-#pragma unroll
-            for (int o = 0; o < half; ++o) fbf_fwd(x[g * 2 * half + o], x[g * 2 * half + o + half], w, c, fwd_ku(r), fwd_kv(r));
-        }
-    }
-}
-
+// where a register group finds the twiddle of level j, block g (TwHeap / TwRow of ntt_big.cu, on the fold tables)
+struct TwHeapS {
+    const stw_t *__restrict__ tw; unsigned P;
+    __device__ __forceinline__ stw_t operator()(int j, int g) const { return tw[(P << j) + g]; }
+};
 #ifndef B200_TW_SPLIT64
-#define B200_TW_SPLIT64 0   // 1: first and second register group of the row pass load a twiddle as two 64-bit loads (see ld_tw): measured 2.5 % slower
+#define B200_TW_SPLIT64 0   // 1: first and second register group of the row pass load a twiddle as two 64-bit loads: measured 2.5 % slower
 #endif
 // A 128-bit load of a warp costs at least 4 L1 data-pipe wavefronts whatever it touches (quarter-warp granularity,
 // tools/l1bench), a 64-bit load one per 128-byte line.  The first two register groups of a row read warp-uniform or
 // 8-distinct entries, so two 64-bit loads would be 2 wavefronts against 4 -- but the second load instruction costs more
 // than the wavefronts save on B200 (rows_fwd 1.716 -> 1.758 ms), so the single 128-bit load stays.
 template <int STRIDE>
-__device__ __forceinline__ stw_t ld_tw(const stw_t *p) {
-    if (B200_TW_SPLIT64 && STRIDE < 32) {
-        u64 a, b;
-        asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(a) : "l"(p));
-        asm volatile("ld.global.nc.u64 %0, [%1+8];" : "=l"(b) : "l"(p));
-        stw_t w;
-        w.w_lo = (int)(unsigned)a; w.w_hi = (int)(unsigned)(a >> 32); w.v_lo = (int)(unsigned)b; w.v_hi = (int)(unsigned)(b >> 32);
-        return w;
+struct TwRowS {
+    const stw_t *__restrict__ base;
+    __device__ __forceinline__ stw_t operator()(int j, int g) const {
+        const stw_t *p = base + ((1 << j) - 1 + g) * STRIDE;
+        if (B200_TW_SPLIT64 && STRIDE < 32) {
+            u64 a, b;
+            asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(a) : "l"(p));
+            asm volatile("ld.global.nc.u64 %0, [%1+8];" : "=l"(b) : "l"(p));
+            stw_t w;
+            w.w_lo = (int)(unsigned)a; w.w_hi = (int)(unsigned)(a >> 32); w.v_lo = (int)(unsigned)b; w.v_hi = (int)(unsigned)(b >> 32);
+            return w;
+        }
+        return *p;
     }
-    return *p;
-}
-// The same on the row-pass order of the tables (b200ring.cu fold_setup): the twiddle of level j, block g of a register group
-// is base[((1 << j) - 1 + g) * STRIDE]; base and STRIDE say which group of the row it is (row_fwd_core_f).
-template <int LOGM, int L0, int STRIDE>
-__device__ __forceinline__ void fwd_regs_fr(s64 (&x)[1 << LOGM], const stw_t *__restrict__ base, const SolConst &c) {
+};
+
+// LOGM forward layers of a register group whose first layer has number L0
+template <int LOGM, int L0, class TW>
+__device__ __forceinline__ void fwd_regs_ft(s64 (&x)[1 << LOGM], const TW tw, const SolConst &c) {
 #pragma unroll
     for (int j = 0; j < LOGM; ++j) {
         const int half = (1 << LOGM) >> (j + 1);
@@ -85,11 +75,20 @@ __device__ __forceinline__ void fwd_regs_fr(s64 (&x)[1 << LOGM], const stw_t *__
         }
 #pragma unroll
         for (int g = 0; g < (1 << j); ++g) {
-            const stw_t w = ld_tw<STRIDE>(base + ((1 << j) - 1 + g) * STRIDE);
+            const stw_t w = tw(j, g);
 #pragma unroll
             for (int o = 0; o < half; ++o) fbf_fwd(x[g * 2 * half + o], x[g * 2 * half + o + half], w, c, fwd_ku(r), fwd_kv(r));
         }
     }
+}
+template <int LOGM, int L0>
+__device__ __forceinline__ void fwd_regs_f(s64 (&x)[1 << LOGM], unsigned P, const stw_t *__restrict__ tw, const SolConst &c) {
+    fwd_regs_ft<LOGM, L0>(x, TwHeapS{tw, P}, c);
+}
+// the same on the row-pass order of the tables (b200ring.cu row_pass_order): base and STRIDE say which group of the row it is
+template <int LOGM, int L0, int STRIDE>
+__device__ __forceinline__ void fwd_regs_fr(s64 (&x)[1 << LOGM], const stw_t *__restrict__ base, const SolConst &c) {
+    fwd_regs_ft<LOGM, L0>(x, TwRowS<STRIDE>{base}, c);
 }
 
 // inverse (Gentleman-Sande) butterfly: U' = U + V - KS*q (folded when FOLD), V' = (U - V)*w
@@ -101,17 +100,17 @@ __device__ __forceinline__ void fbf_inv(s64 &U, s64 &V, const stw_t w, const Sol
     U = s;
     V = fmul(d, w, c);
 }
-// LOGM inverse layers (innermost first); L0 = index of the group's first layer inside its pass.  The sums are
-// recentred by -q in odd layers and folded after them (tools/fold_ranges.py rows_inv).
-template <int LOGM, int L0, int JMIN = 0>
-__device__ __forceinline__ void inv_regs_f(s64 (&x)[1 << LOGM], unsigned P, const stw_t *__restrict__ tw, const SolConst &c) {
+// LOGM inverse layers (innermost first); L0 = number of the group's first layer (0 = first layer of the row pass).  The sums
+// are recentred by -q in odd layers and folded after them (tools/fold_ranges.py inv_layers).
+template <int LOGM, int L0, int JMIN, class TW>
+__device__ __forceinline__ void inv_regs_ft(s64 (&x)[1 << LOGM], const TW tw, const SolConst &c) {
 #pragma unroll
     for (int j = LOGM - 1; j >= JMIN; --j) {
         const int half = (1 << LOGM) >> (j + 1);
         const int l = L0 + (LOGM - 1 - j);
 #pragma unroll
         for (int g = 0; g < (1 << j); ++g) {
-            const stw_t w = tw[(P << j) + g];
+            const stw_t w = tw(j, g);
 #pragma unroll
             for (int o = 0; o < half; ++o) {
                 if (l & 1) fbf_inv<1, true>(x[g * 2 * half + o], x[g * 2 * half + o + half], w, c);
@@ -120,23 +119,13 @@ __device__ __forceinline__ void inv_regs_f(s64 (&x)[1 << LOGM], unsigned P, cons
         }
     }
 }
-
+template <int LOGM, int L0, int JMIN = 0>
+__device__ __forceinline__ void inv_regs_f(s64 (&x)[1 << LOGM], unsigned P, const stw_t *__restrict__ tw, const SolConst &c) {
+    inv_regs_ft<LOGM, L0, JMIN>(x, TwHeapS{tw, P}, c);
+}
 template <int LOGM, int L0, int STRIDE>
 __device__ __forceinline__ void inv_regs_fr(s64 (&x)[1 << LOGM], const stw_t *__restrict__ base, const SolConst &c) {
-#pragma unroll
-    for (int j = LOGM - 1; j >= 0; --j) {
-        const int half = (1 << LOGM) >> (j + 1);
-        const int l = L0 + (LOGM - 1 - j);
-#pragma unroll
-        for (int g = 0; g < (1 << j); ++g) {
-            const stw_t w = ld_tw<STRIDE>(base + ((1 << j) - 1 + g) * STRIDE);
-#pragma unroll
-            for (int o = 0; o < half; ++o) {
-                if (l & 1) fbf_inv<1, true>(x[g * 2 * half + o], x[g * 2 * half + o + half], w, c);
-                else fbf_inv<0, false>(x[g * 2 * half + o], x[g * 2 * half + o + half], w, c);
-            }
-        }
-    }
+    inv_regs_ft<LOGM, L0, 0>(x, TwRowS<STRIDE>{base}, c);
 }
 
 // Twiddles of a row in row-pass order: block twr = table + R + 255*row; [0,7) the first group (warp-uniform), then 7 runs of
