@@ -85,13 +85,18 @@ def test_constructor_and_tables_bit_identical():
     assert ci.StandardRing().N() == 2048 and std.StandardRing() is std
 
 
+# NTT-friendly primes 2^60 + c and 2^55 - c (= 1 mod 2^18): the fold-arithmetic kernels run behind the folding layer
+FOLD_PRIMES = [0x1000000000980001, 0x1000000000b00001, 0x7fffffff380001]
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("logN", [4, 6, 9, 10, 12, 13, 15, 16, 17])
-def test_ntt_matches_oracle(logN):
+@pytest.mark.parametrize("logN,primes", [(n, "qi60") for n in (4, 6, 9, 10, 12, 13, 15, 16, 17)] + [(n, "fold") for n in (10, 13, 16)])
+def test_ntt_matches_oracle(logN, primes):
     """Every kernel family behind the folding layer: resident (N <= 2^9 ... in shared memory), tuned two-pass
-    (2^10..2^17).  Forward, inverse, lazy variants, in place and out of place, bit for bit."""
+    (2^10..2^17) on Shoup arithmetic (Qi60) and on fold arithmetic (primes 2^k + c).  Forward, inverse, lazy variants, in place
+    and out of place, bit for bit."""
     N = 1 << logN
-    moduli = QI60[:3 if logN < 16 else 2]
+    moduli = QI60[:3 if logN < 16 else 2] if primes == "qi60" else FOLD_PRIMES[:3 if logN < 16 else 2]
     batch = 3 if logN < 15 else 1
     r = b200ring.NewRingConjugateInvariant(N, moduli)
     host = rand_poly(0xC2 + logN, batch, moduli, N)
