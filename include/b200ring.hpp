@@ -219,6 +219,8 @@ class Ring {
     void DivFloorByLastModulusManyNTT(int nb, const Poly &p0, Poly &p1) const { check(b200_div_by_last_modulus_many(ctx_.get(), p0.handle(), p1.handle(), level_, nb, 0, 1)); }
     void DivRoundByLastModulusMany(int nb, const Poly &p0, Poly &p1) const { check(b200_div_by_last_modulus_many(ctx_.get(), p0.handle(), p1.handle(), level_, nb, 1, 0)); }
     void DivRoundByLastModulusManyNTT(int nb, const Poly &p0, Poly &p1) const { check(b200_div_by_last_modulus_many(ctx_.get(), p0.handle(), p1.handle(), level_, nb, 1, 1)); }
+    // ckks.Evaluator.Rescale on the two polynomials of a ciphertext (schemes/ckks/evaluator.go:500-541); the caller lowers its level by nb
+    void Rescale(int nb, const Poly &c0, const Poly &c1, Poly &out0, Poly &out1) const { DivRoundByLastModulusManyNTT(nb, c0, out0); DivRoundByLastModulusManyNTT(nb, c1, out1); }
     // NTT / INTT sequence on host-resident polynomials, copies overlapped with compute
     void TransformHost(const std::vector<uint64_t> &in, std::vector<uint64_t> &out, const std::vector<int> &ops) const {
         const size_t per = (size_t)ModuliChainLength() * N();
@@ -310,6 +312,21 @@ class KeySwitcher {
     void MulRelin(int levelQ, int levelP, const Poly &a0, const Poly &a1, const Poly &b0, const Poly &b1, const Poly &rlk, Poly &o0, Poly &o1,
                   bool mform = true) const {
         check(b200_mul_relin(ks_.get(), levelQ, levelP, a0.handle(), a1.handle(), b0.handle(), b1.handle(), rlk.handle(), o0.handle(), o1.handle(), mform));
+    }
+    // rlwe.Evaluator.Relinearize (core/rlwe/evaluator_evaluationkey.go:125-153): GadgetProduct(c2, rlk) into two temporaries,
+    // then out_i = c_i + tmp_i on the limbs 0..levelQ
+    void Relinearize(int levelQ, int levelP, const Poly &c0, const Poly &c1, const Poly &c2, const Poly &rlk, Poly &out0, Poly &out1) const {
+        Poly t0 = ring_.NewPoly(c2.Batch()), t1 = ring_.NewPoly(c2.Batch());
+        GadgetProduct(levelQ, levelP, c2, rlk, t0, t1);
+        const Ring rq = ring_.AtLevel(levelQ);
+        rq.Add(c0, t0, out0);
+        rq.Add(c1, t1, out1);
+    }
+    // rlwe.Evaluator.ApplyEvaluationKey for equal ring degrees (:37-117): GadgetProduct(c1, evk), out0 = c0 + tmp0, out1 = tmp1
+    void ApplyEvaluationKey(int levelQ, int levelP, const Poly &c0, const Poly &c1, const Poly &evk, Poly &out0, Poly &out1) const {
+        Poly t0 = ring_.NewPoly(c1.Batch());
+        GadgetProduct(levelQ, levelP, c1, evk, t0, out1);
+        ring_.AtLevel(levelQ).Add(c0, t0, out0);
     }
 
   private:
