@@ -21,6 +21,7 @@ ap.add_argument("--iters", type=int, default=2)
 ap.add_argument("--time", action="store_true")
 ap.add_argument("--logn", type=int, default=16)
 ap.add_argument("--a", type=int, default=15)
+ap.add_argument("--fold-primes", action="store_true", help="power-of-two ring on primes 2^60 + c (fold arithmetic) instead of the 61-bit Qi60 chain")
 ap.add_argument("--tree", action="store_true", help="3N ring: keep NTT-domain slots in tree order (no slot permutation)")
 args = ap.parse_args()
 
@@ -38,6 +39,9 @@ if args.ring == "3n":
         moduli = b200ring.Find3NRNSPrimes(N, 60, args.limbs, 100000)
 else:
     N, moduli = 1 << args.logn, QI60[: args.limbs]
+    if args.fold_primes:
+        gen = b200ring.NTTFriendlyPrimesGenerator(60, 2 * N)
+        moduli = gen.NextUpstreamPrimes(args.limbs)
 TREE = {"tree_order": True} if args.tree else {}
 ring = b200ring.NewRing(N, moduli)
 ring.SetStream(torch.cuda.current_stream().cuda_stream)
