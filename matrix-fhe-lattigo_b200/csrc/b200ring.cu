@@ -254,10 +254,13 @@ static bool fold_entry(u64 w, u64 q, int k, stw_t *out) {
     const long long vb = v > q / 2 ? (long long)v - (long long)q : (long long)v;
     return fold_split(wb, k - 32, &out->w_lo, &out->w_hi) && fold_split(vb, k - 32, &out->v_lo, &out->v_hi);
 }
+// The windows of the fold arithmetic are stated in units of 2^k (tools/fold_ranges.py): the term c*B.hi of a product is at
+// most |c| * 2^30 / 2^k of a unit, so |c| <= 2^(k-33) keeps it at the 1/8 the interval model assumes for every k (2^27 at
+// k = 60; a bound of 2^27 for all k would let a 55-bit prime with a 27-bit c push products four units off).
 static bool fold_prime_ok(u64 q) {
     int k; long long c;
     fold_shape(q, &k, &c);
-    return k >= 50 && k <= 60 && (c < 0 ? -c : c) <= (1LL << 27);
+    return k >= 50 && k <= 60 && (c < 0 ? -c : c) <= (1LL << (k - 33));
 }
 // builds the device tables; leaves ctx->fold_ok false (and no tables) when the ring does not qualify
 static cudaError_t fold_setup(b200_ctx *ctx, const std::vector<tw_t> &fwd, const std::vector<tw_t> &inv, const std::vector<tw_t> &misc) {

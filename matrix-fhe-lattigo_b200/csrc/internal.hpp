@@ -45,7 +45,7 @@ struct b200_ctx {
     tw_t *d_misc = nullptr;          // [L][MISC_COUNT]
     tw_t *d_fwd_r = nullptr, *d_inv_r = nullptr;   // rings the two-pass kernels cover: copies of d_fwd / d_inv whose entries of heap index >= N/256
                                      // (all the row pass reads) sit in row-pass order (row_pass_order, b200ring.cu)
-    // fold arithmetic (solinas.cuh): set when every prime is 2^k + c with 50 <= k <= 60, |c| <= 2^27 and every twiddle
+    // fold arithmetic (solinas.cuh): set when every prime is 2^k + c with 50 <= k <= 60, |c| <= 2^(k-33) and every twiddle
     // splits into 32-bit halves; the tuned transforms then run on these tables instead of the Shoup ones
     bool fold_ok = false;
     SolConst *d_sol = nullptr;       // [L]

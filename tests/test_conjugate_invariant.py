@@ -85,8 +85,8 @@ def test_constructor_and_tables_bit_identical():
     assert ci.StandardRing().N() == 2048 and std.StandardRing() is std
 
 
-# NTT-friendly primes 2^60 + c and 2^55 - c (= 1 mod 2^18): the fold-arithmetic kernels run behind the folding layer
-FOLD_PRIMES = [0x1000000000980001, 0x1000000000b00001, 0x7fffffff380001]
+# NTT-friendly primes 2^60 + c and 2^55 + c (= 1 mod 2^18, |c| <= 2^(k-33)): the fold-arithmetic kernels run behind the folding layer
+FOLD_PRIMES = [0x1000000000980001, 0x1000000000b00001, 0x80000000080001]
 
 
 @pytest.mark.gpu

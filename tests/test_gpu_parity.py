@@ -422,8 +422,8 @@ def test_transform_host_pipelined_chunks():
         assert (out == host).all()
 
 
-# power-of-two NTT-friendly primes the fold arithmetic admits: 2^60 + c and 2^55 - c (QI60 are 2^61 - c: Shoup path)
-FOLD_POW2_PRIMES = [0x1000000000980001, 0x1000000000b00001, 0x7fffffff380001]
+# power-of-two NTT-friendly primes the fold arithmetic admits (|c| <= 2^(k-33)): 2^60 + c and 2^55 + c (QI60 are 2^61 - c: Shoup path)
+FOLD_POW2_PRIMES = [0x1000000000980001, 0x1000000000b00001, 0x80000000080001]
 
 
 @pytest.mark.parametrize("env", [{"B200_GENERIC_COLS": "1"}, {"B200_NO_BIG": "1"}, {"B200_NO_FOLD": "1"}, {"B200_FOLD_COLS": "0"},

@@ -13,8 +13,9 @@ All quantities are in units of 2^k (k = bit position of the prime's leading term
 """
 from fractions import Fraction as F
 
-K = 60                      # worst case of the fast path: the largest k it admits
-C_MAX = F(2) ** 27          # and the largest |c|
+K = 60                      # worst case of the fast path: the largest k it admits (least headroom below 2^63)
+C_MAX = F(2) ** 27          # and the largest |c| there; the fast path admits |c| <= 2^(k-33), which scales every window
+                            # below to the same number of units of 2^k for smaller k (b200ring.cu fold_prime_ok)
 UNIT = F(2) ** K
 Q = 1 + C_MAX / UNIT        # q in units of 2^k (c > 0 is the worse sign for the upper ends)
 S64 = F(2) ** 63 / UNIT     # 8 units
