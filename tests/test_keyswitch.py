@@ -100,8 +100,9 @@ def _qp_poly(ring, LQ, batch, q_part=None, p_part=None):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("kind,N,LQ,LP", [("std", 64, 4, 3), ("m3", 48, 5, 2), ("std", 1 << 12, 6, 2)])
+@pytest.mark.parametrize("kind,N,LQ,LP", [("std", 64, 4, 3), ("m3", 48, 5, 2), ("std", 1 << 12, 6, 2), ("std", 64, 20, 3), ("m3", 48, 18, 2)])
 def test_mod_up_and_mod_down_bit_exact(kind, N, LQ, LP):
+    # LQ = 18, 20: more than 16 source limbs in ModUpQtoP (the generic extension kernel; the accumulator's high word passes 2p there)
     Q, P, rq, rp = chains(kind, N, LQ, LP)
     ring = b200ring.NewRing(N, Q + P)
     ks = b200ring.KeySwitcher(ring, LQ)
@@ -141,7 +142,7 @@ def test_mod_up_and_mod_down_bit_exact(kind, N, LQ, LP):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("kind,N,LQ,LP", [("std", 32, 5, 2), ("m3", 24, 4, 2), ("m3", 3 * 2**10, 6, 3), ("std", 1 << 13, 7, 2),
-                                          ("m3", 3 * 2**15, 6, 2)])
+                                          ("m3", 3 * 2**15, 6, 2), ("m3", 24, 18, 17)])   # last: digits of 18 limbs, the canonical reduction of long digits
 def test_gadget_product_matches_oracle_and_exact_property(kind, N, LQ, LP):
     Q, P, rq, rp = chains(kind, N, LQ, LP)
     ring = b200ring.NewRing(N, Q + P)
