@@ -100,6 +100,9 @@ static void build_standard(b200_ctx *ctx, int i, std::vector<tw_t> &fwd, std::ve
     const u64 ninv = hm::invmod_prime((u64)N % q, q);
     misc[MISC_NINV] = mk_tw(ninv, q);
     misc[MISC_NINV_W1] = mk_tw(hm::mulmod(ninv, inv[1].x, q), q);
+    const u64 r64 = hm::mform(1, q);   // 2^64 mod q
+    misc[MISC_NINVM] = mk_tw(hm::mulmod(ninv, r64, q), q);
+    misc[MISC_NINV_W1M] = mk_tw(hm::mulmod(hm::mulmod(ninv, inv[1].x, q), r64, q), q);
 }
 
 // CONJUGATE_INVARIANT tables (NewRingConjugateInvariant, ring.go:280-282: NthRoot = 4N).  The Go-format tables hold 2N
@@ -194,6 +197,9 @@ static void build_matrix(b200_ctx *ctx, int i, std::vector<tw_t> &fwd, std::vect
     misc[MISC_K2] = mk_tw(two_over_n, q);
     misc[MISC_ZETA] = mk_tw(zeta, q);
     misc[MISC_K4] = mk_tw(hm::invmod_prime((u64)N % q, q), q);
+    const u64 r64 = hm::mform(1, q);   // 2^64 mod q
+    misc[MISC_K1M] = mk_tw(hm::mulmod(hm::mulmod(c, two_over_n, q), r64, q), q);
+    misc[MISC_K4M] = mk_tw(hm::mulmod(hm::invmod_prime((u64)N % q, q), r64, q), q);
 }
 
 // Row-pass order of a twiddle table (the row kernels of ntt_big.cu / ntt_fold.cuh): the 255 twiddles of the subtree under row

@@ -30,6 +30,12 @@ enum { MISC_OMEGA3 = 0, MISC_K1 = 1, MISC_K2 = 2, MISC_ZETA = 3, MISC_NINV = 4, 
 enum { MISC_CI_F = 6, MISC_CI_FINV = 7 };
 // MATRIX rings: N^-1 (the inverse cyclotomic layer in its two-product form, ntt_fold.cuh) shares the slot of MISC_NINV
 enum { MISC_K4 = 4 };
+// The inverse scaling constants times 2^64 mod q, for the fused ring product on the fold path: its slot-wise product is a
+// Montgomery product (x*y*2^-64, 9 wide multiplies instead of Barrett's 18) and the inverse transform that follows gives the
+// factor back for free.  MATRIX: slots 5, 6; STANDARD: slots 6, 7 (conjugate-invariant rings, which own 6 and 7, do not take
+// the fused path).  Selected in the inverse column kernels by the internal flag B200_FLAG_MONT_SCALE.
+enum { MISC_K1M = 5, MISC_K4M = 6, MISC_NINVM = 6, MISC_NINV_W1M = 7 };
+#define B200_FLAG_MONT_SCALE 0x100
 
 struct b200_ctx {
     int ring_type = 0, N = 0, L = 0, device = 0;

@@ -1238,6 +1238,7 @@ int launch_polymul_big(b200_ctx *ctx, const u64 *pa, const u64 *pb, u64 *pc, Spa
         to_dense.out_dense = 1;
         dense.in_dense = dense.out_dense = 1;
         from_dense.in_dense = 1;
+        if (fold) from_dense.flags |= B200_FLAG_MONT_SCALE;   // k_rows_mul_f multiplies Montgomery-wise: the inverse column pass scales by N^-1 * 2^64
         const dim3 gf(tiles_f, nu), gi(tiles_i, nu);
         { LaunchScope ls(ctx, matrix ? "cols_fwd_m3" : "cols_fwd_std", nu);
           cf<<<gf, thr_f, smem_f, st>>>(pa, ta, to_dense); }

@@ -279,7 +279,8 @@ k_rows_inv_f(const u64 *in, u64 *out, BigArgs a) {
 
 // Fused row stage of the ring product on the fold arithmetic (k_rows_mul of ntt_big.cu): both operands arrive from a fold
 // column pass (signed words, layers 0..L0-1 done), run the 8 forward row layers, are brought to [0, q) and multiplied
-// (Barrett, canonical), and the product runs the 8 inverse row layers; signed words go on to the fold inverse column pass.
+// (Montgomery product of the two canonical words: x*y*2^-64, half the wide multiplies of a Barrett product; the inverse
+// column pass gives the 2^64 back with its scaling constants), and the product runs the 8 inverse row layers; signed words go on to the fold inverse column pass.
 template <int L0>
 __global__ void __launch_bounds__(128, B200_MINB_ROWS_MUL)
 k_rows_mul_f(u64 *ta, const u64 *tb, BigArgs a) {
@@ -306,7 +307,7 @@ k_rows_mul_f(u64 *ta, const u64 *tb, BigArgs a) {
     sol_canon_n(cx, x, sc);
     sol_canon_n(cy, y, sc);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) x[k] = (s64)bred(cx[k], cy[k], lc.q, lc.brc_hi, lc.brc_lo);
+    for (int k = 0; k < 8; ++k) x[k] = (s64)mred(cx[k], cy[k], lc.q, lc.qinv);   // x*y*2^-64, canonical; the inverse column pass scales by N^-1 * 2^64 (B200_FLAG_MONT_SCALE)
     row_inv_core_f(x, buf, lane, twri, sc);
 #pragma unroll
     for (int k = 0; k < 8; ++k) pa[k * 32 + lane] = (u64)x[k];
@@ -427,7 +428,8 @@ k_cols_inv_m3_15_f(const u64 *in, u64 *out, BigArgs a) {
     }
     __syncthreads();
     if (g < 32) {
-        const stw_t om = mc[MISC_OMEGA3], k1 = mc[MISC_K1], k4 = mc[MISC_K4];
+        const bool msc = a.flags & B200_FLAG_MONT_SCALE;   // fused ring product: the scaling constants carry the 2^64 of its Montgomery product
+        const stw_t om = mc[MISC_OMEGA3], k1 = mc[msc ? MISC_K1M : MISC_K1], k4 = mc[msc ? MISC_K4M : MISC_K4];
         s64 x[6][2];
 #pragma unroll
         for (int hd = 0; hd < 6; ++hd) {
@@ -514,7 +516,8 @@ k_cols_inv_std16_f(const u64 *in, u64 *out, BigArgs a) {
     const size_t ibase = ur.in + (size_t)blockIdx.x * CW, obase = ur.out + (size_t)blockIdx.x * CW;
     const SolConst sc = a.sol[limb];
     const stw_t *__restrict__ tw = a.inv_s + (size_t)limb * a.N;
-    const stw_t ninv = a.misc_s[limb * MISC_COUNT + MISC_NINV], ninv_w1 = a.misc_s[limb * MISC_COUNT + MISC_NINV_W1];
+    const bool msc = a.flags & B200_FLAG_MONT_SCALE;   // fused ring product: N^-1 carries the 2^64 of its Montgomery product
+    const stw_t ninv = a.misc_s[limb * MISC_COUNT + (msc ? MISC_NINVM : MISC_NINV)], ninv_w1 = a.misc_s[limb * MISC_COUNT + (msc ? MISC_NINV_W1M : MISC_NINV_W1)];
     const int t = threadIdx.x, c = t % CW, g = t / CW;
     s64 x[8];
 #pragma unroll
@@ -677,7 +680,8 @@ B200_UNROLL_(B200_BAL_UNROLL)
     __syncthreads();
     {   // phase A: inverse radix-3 layer (factor 3 deferred) and inverse cyclotomic layer with the 2/N scaling
         const stw_t *mc = a.misc_s + limb * MISC_COUNT;
-        const stw_t om = mc[MISC_OMEGA3], k1 = mc[MISC_K1], k4 = mc[MISC_K4];
+        const bool msc = a.flags & B200_FLAG_MONT_SCALE;   // fused ring product: the scaling constants carry the 2^64 of its Montgomery product
+        const stw_t om = mc[MISC_OMEGA3], k1 = mc[msc ? MISC_K1M : MISC_K1], k4 = mc[msc ? MISC_K4M : MISC_K4];
         const int c = t % CW, g = t / CW;
 B200_UNROLL_(B200_BAL_UNROLL)
         for (int r = 0; r < 4; ++r) {
@@ -770,7 +774,8 @@ k_cols_std_g_f(const u64 *in, u64 *out, BigArgs a) {
     const size_t ibase = ur.in + (size_t)blockIdx.x * GCW, obase = ur.out + (size_t)blockIdx.x * GCW;
     const SolConst sc = a.sol[limb];
     const stw_t *__restrict__ tw = (INV ? a.inv_s : a.fwd_s) + (size_t)limb * a.N;
-    const stw_t ninv = a.misc_s[limb * MISC_COUNT + MISC_NINV], ninv_w1 = a.misc_s[limb * MISC_COUNT + MISC_NINV_W1];
+    const bool msc = a.flags & B200_FLAG_MONT_SCALE;   // fused ring product: N^-1 carries the 2^64 of its Montgomery product
+    const stw_t ninv = a.misc_s[limb * MISC_COUNT + (msc ? MISC_NINVM : MISC_NINV)], ninv_w1 = a.misc_s[limb * MISC_COUNT + (msc ? MISC_NINV_W1M : MISC_NINV_W1)];
     constexpr int S3e = S3 ? S3 : 1;
     if (!INV) {
         col_group_f<S1, 1, LOGR, false, true, false, false, 0>(in, ibase, out, obase, sm, S2 + S3, tw, sc, ninv, ninv_w1);
@@ -864,7 +869,8 @@ k_cols_m3_g_f(const u64 *in, u64 *out, BigArgs a) {
             col_group_f<S2, 6, LOGU, true, false, false, false, 8 + S3>(in, ibase, out, obase, sm, S3, tw, sc, none, none);
         }
         __syncthreads();
-        const stw_t k1 = mc[MISC_K1], k4 = mc[MISC_K4];
+        const bool msc = a.flags & B200_FLAG_MONT_SCALE;
+        const stw_t k1 = mc[msc ? MISC_K1M : MISC_K1], k4 = mc[msc ? MISC_K4M : MISC_K4];
         for (int t = threadIdx.x; t < GCW * ULO; t += blockDim.x) {
             const int c = t & (GCW - 1), ulo = t >> GCW_LOG;
             s64 x[6][MA];

@@ -455,6 +455,31 @@ def test_alternative_kernel_paths_agree(env, shape, monkeypatch):
     assert (want.get()[1, 1] == sub.NTT(host[1, 1])).all()
 
 
+@pytest.mark.parametrize("shape", [("std", 1 << 16), ("std", 1 << 13), ("m3", 3 * 2**15), ("m3", 3 * 2**14)])
+def test_fused_product_on_fold_primes_equals_operator_sequence(shape):
+    """b200_polymul on the fold path multiplies slot-wise with a Montgomery product and lets the inverse column pass give
+    the 2^64 back; the operator sequence NTT, MForm, MulCoeffsMontgomery, INTT of
+    ring/ring_test.go:106-110 runs through other kernels (no scaled constants) and must give the same words; a monomial
+    operand pins the product itself (X^j * b is a signed rotation in the power-of-two ring)."""
+    kind, N = shape
+    moduli = FOLD_POW2_PRIMES[:2] if kind == "std" else C3_PRIMES[3:5] if N == 3 * 2**15 else O.find_3n_rns_primes(N, 60, 2)
+    r = b200ring.NewRing(N, moduli)
+    ha, hb = rand_poly(71, 2, moduli, N), rand_poly(72, 2, moduli, N)
+    a, b, c, d, e = (r.NewPoly(2) for _ in range(5))
+    a.set(ha); b.set(hb)
+    r.MulPoly(a, b, c)
+    r.NTT(a, d); r.NTT(b, e); r.MForm(d, d); r.MulCoeffsMontgomery(d, e, d); r.INTT(d, d)
+    assert (c.get() == d.get()).all()
+    if kind == "std":
+        j = 5
+        mono = np.zeros_like(ha); mono[:, :, j] = 1
+        r.MulPoly(a.set(mono), b, c)
+        got = c.get()
+        for l, q in enumerate(moduli):
+            want = np.concatenate([(np.uint64(q) - hb[:, l, N - j:]) % np.uint64(q), hb[:, l, : N - j]], axis=1)
+            assert (got[:, l] == want).all()
+
+
 def test_fold_arithmetic_extreme_inputs_headline_shape():
     """The fold kernels work on signed lazy words: all-(q-1), all-zero and alternating 0 / q-1 inputs drive the
     windows of tools/fold_ranges.py to their ends; results must still be the oracle's words (3N headline shape and the
