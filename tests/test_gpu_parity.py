@@ -760,3 +760,17 @@ def test_poly_copy_copylvl_zero_on_device():
         pb.CopyLvl(3, pa)
     with pytest.raises(b200ring.B200Error):
         r.NewPoly(1).Copy(pa)
+
+
+def test_fold_and_shoup_implementations_agree_on_structured_and_random_inputs():
+    """tools/stress_fold_vs_shoup.py: the two independent transform programs (fold arithmetic / Shoup arithmetic, the latter
+    forced with B200_NO_FOLD=1) on all 24 primes of BASELINE config 3 at N = 3*2^15, a generic 3N shape and two power-of-two
+    rings on fold primes: all-(q-1), alternating, 2q-1 (top of the input contract) and random words through NTT, INTT,
+    NTTLazy and the tree-order variants, bit for bit."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "stress_fold_vs_shoup.py"), "--rounds", "5"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count(": ok") == 4
