@@ -11,3 +11,4 @@ ncu --set full --clock-control none --import-source on -k regex:"k_rows|k_cols" 
 ./tools/solbench > gpurun_out/r02_solbench.txt 2>&1
 ./tools/pipebench2 > gpurun_out/r02_pipebench2.txt 2>&1
 cat gpurun_out/r02_pytest_gpu.txt; cat gpurun_out/r02_bench.json | cut -c1-600; tail -3 gpurun_out/r02_ncu_f.log
+ncu --set full --clock-control none --import-source on -k regex:"_inv_" --launch-skip 10 -c 2 -f -o gpurun_out/r02_bench_kernels_inv python bench.py --steps 1 --warmup 3 --no-cpu --no-e2e --no-verify > gpurun_out/r02_ncu_f2.log 2>&1
